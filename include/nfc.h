@@ -1,0 +1,117 @@
+/* nfc.h -- C ABI of libnfc_b200.so: the B200 (sm_100a) hot path of NeuralFreeConvection.jl.
+ *
+ * The reference has no FFI; its seam is the SciML protocol (an out-of-place ODEProblem whose
+ * f(u,p,t) closes over the operators, solved with u0=/p= overrides).  Each entry point below
+ * replaces the numerical work behind one reference call site (file:line into the reference):
+ *
+ *   nfc_create / nfc_destroy   FreeConvectionNDE(NN, ds; iterations)        src/free_convection_nde.jl:1-47
+ *                              ConvectiveAdjustmentNDE(NN, ds; iterations)  src/convective_adjustment_nde.jl:1-57
+ *   nfc_set_weights            Flux.destructure(NN) -> theta                src/solve.jl:2, src/training.jl:43
+ *   nfc_rhs                    the closure dT/dt(T, p, t)                   src/free_convection_nde.jl:29-38,
+ *                                                                           src/convective_adjustment_nde.jl:33-48
+ *   nfc_solve                  solve_nde(nde, NN, T0, alg, nde_params)      src/solve.jl:1-6
+ *   nfc_diagnose_flux          flux diagnosis loop of solve_nde(ds, ...)    src/solve.jl:32-48
+ *   nfc_loss_grad              nde_loss + Zygote gradient                   src/training.jl:45-48,70
+ *
+ * Conventions
+ *   - plain C, host pointers unless the name ends in _dev; the caller owns every buffer for the
+ *     duration of the call only; the handle owns device memory, streams, scratch.
+ *   - every call returns 0 on success, negative on usage / CUDA error (text via nfc_last_error).
+ *     Per-column numerical trouble is reported in status[] (0 ok, 1 maxiters, 2 NaN/Inf, 3 dt underflow,
+ *     4 adjoint tape overflow), never as a call failure -- the reference treats solver retcodes as warnings.
+ *   - calls on one handle are serialised by the caller; host-pointer calls are synchronous.
+ *   - there is NO CPU fallback: without a CUDA device nfc_create fails.
+ *
+ * Layouts (Julia column-major == C row-major with reversed dims)
+ *   T, dTdt, T0   [B][Nz]           Julia Nz x B;      index 0 = deepest cell, already T_scaling'ed
+ *   colp          [B][3]            (bottom_flux, top_flux, K_CA) per column, wT_scaling'ed fluxes
+ *                                   (FreeConvectionNDEParameters / ConvectiveAdjustmentNDEParameters,
+ *                                    src/free_convection_nde.jl:49-62, src/convective_adjustment_nde.jl:59-72)
+ *   glob          [4]               (sigma_T, sigma_wT, H, tau)
+ *   theta         [n_params]        Flux.destructure order: [conv weight(k), conv bias(1)], then per Dense:
+ *                                   weight (out x in, column-major), bias
+ *   Tout, Ttrue   [B][n_save][Nz]   Julia Nz x n_save x B
+ *   wT            [B][n_save][Nz+1]
+ */
+#ifndef NFC_H
+#define NFC_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NFC_MAX_LAYERS 8
+#define NFC_ACT_IDENTITY 0
+#define NFC_ACT_RELU 1
+#define NFC_NDE_FREE_CONVECTION 0      /* K_CA column of colp is ignored (treated as 0) */
+#define NFC_NDE_CONVECTIVE_ADJUSTMENT 1
+#define NFC_ALG_TSIT5 0
+
+typedef struct nfc_handle nfc_handle;
+
+typedef struct nfc_config {
+    int32_t struct_size;                          /* = sizeof(nfc_config), ABI guard */
+    int32_t Nz;                                   /* grid points; this build: 32 */
+    int32_t conv_width;                           /* 0 = none, else Conv((k,1),1=>1,relu) front-end (2 or 4) */
+    int32_t n_layers;                             /* Dense layers */
+    int32_t layer_dims[NFC_MAX_LAYERS + 1];       /* in_0, out_0, out_1, ... */
+    int32_t activations[NFC_MAX_LAYERS];          /* NFC_ACT_* per Dense layer */
+    int32_t nde_type;                             /* NFC_NDE_* */
+    int32_t alg;                                  /* NFC_ALG_TSIT5 */
+    float reltol;                                 /* src/solve.jl:4 -> 1e-4 */
+    float abstol;                                 /* DiffEqBase default 1e-6 */
+    float fixed_dt;                               /* > 0: adaptive=false, dt=fixed_dt (test / fixed-step use) */
+    int32_t max_iters;                            /* DiffEqBase default 100000 */
+    int32_t n_save;                               /* length(saveat) */
+    const float* saveat;                          /* [n_save] ascending, saveat[0] = t0 = 0, saveat[n_save-1] = tf */
+    int32_t device;                               /* CUDA device ordinal */
+    int32_t adjoint_max_steps;                    /* tape capacity per column for nfc_loss_grad (0 = default 1024) */
+    float adjoint_reltol;                         /* 0 = reltol */
+    float adjoint_abstol;                         /* 0 = abstol */
+    int32_t reserved[8];
+} nfc_config;
+
+typedef struct nfc_counters {
+    int64_t columns;            /* columns processed by the last solve / loss_grad call */
+    int64_t steps_accepted;     /* forward Tsit5 steps accepted, all columns */
+    int64_t steps_rejected;     /* forward Tsit5 steps rejected */
+    int64_t adj_steps_accepted; /* backward (adjoint) steps accepted */
+    int64_t adj_steps_rejected;
+    int64_t kernel_launches;    /* kernels launched by the last call */
+    float   last_kernel_ms;     /* device time of the last call's main kernel(s), CUDA events */
+    float   last_adjoint_ms;
+} nfc_counters;
+
+int32_t nfc_create(const nfc_config* cfg, nfc_handle** out);
+int32_t nfc_destroy(nfc_handle* h);
+const char* nfc_last_error(const nfc_handle* h);   /* h may be NULL: error of the last failed nfc_create */
+int64_t nfc_n_params(const nfc_handle* h);
+int32_t nfc_set_weights(nfc_handle* h, const float* theta, int64_t n);
+int32_t nfc_set_saveat(nfc_handle* h, const float* saveat, int32_t n_save);
+int32_t nfc_get_counters(const nfc_handle* h, nfc_counters* out);
+
+/* host-buffer calls (the drop-in boundary) */
+int32_t nfc_rhs(nfc_handle* h, const float* T, const float* colp, const float* glob, float* dTdt, int64_t B);
+int32_t nfc_solve(nfc_handle* h, const float* T0, const float* colp, const float* glob, float* Tout,
+                  int32_t* naccept, int32_t* nreject, int32_t* status, int64_t B);
+int32_t nfc_diagnose_flux(nfc_handle* h, const float* Tsol, const float* colp, float* wT, int64_t B);
+int32_t nfc_loss_grad(nfc_handle* h, const float* T0, const float* colp, const float* glob, const float* Ttrue,
+                      double* loss, float* grad_theta, int32_t* status, int64_t B);
+
+/* device-buffer calls: same semantics, pointers are device memory on cfg.device, work is enqueued on
+ * `stream` (a cudaStream_t passed as void*; NULL = the handle's own stream) and NOT synchronised. */
+int32_t nfc_rhs_dev(nfc_handle* h, const float* T, const float* colp, const float* glob, float* dTdt, int64_t B, void* stream);
+int32_t nfc_solve_dev(nfc_handle* h, const float* T0, const float* colp, const float* glob, float* Tout,
+                      int32_t* naccept, int32_t* nreject, int32_t* status, int64_t B, void* stream);
+/* loss_sum_dev: double[2] = (sum of squared residuals, number of residuals) of this rank's columns;
+ * grad_dev: float[n_params] = d(sum of squared residuals / n_total)/dtheta with n_total = n_total_columns*n_save*Nz,
+ * so that a SUM all-reduce over ranks yields the global-batch gradient (src/training.jl:47 mean over all sims). */
+int32_t nfc_loss_grad_dev(nfc_handle* h, const float* T0, const float* colp, const float* glob, const float* Ttrue,
+                          double* loss_sum_dev, float* grad_dev, int32_t* status, int64_t B, int64_t n_total_columns,
+                          void* stream);
+int32_t nfc_sync(nfc_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NFC_H */

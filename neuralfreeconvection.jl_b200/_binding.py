@@ -1,0 +1,208 @@
+"""ctypes binding of libnfc_b200.so (include/nfc.h).  No CPU fallback: if the CUDA library is missing or
+no B200 is visible, construction raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnfc_b200.so")
+NFC_MAX_LAYERS = 8
+
+EXPORTS = ["nfc_create", "nfc_destroy", "nfc_last_error", "nfc_n_params", "nfc_set_weights", "nfc_set_saveat",
+           "nfc_get_counters", "nfc_rhs", "nfc_solve", "nfc_diagnose_flux", "nfc_loss_grad", "nfc_rhs_dev",
+           "nfc_solve_dev", "nfc_loss_grad_dev", "nfc_sync"]
+
+
+class NfcConfig(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("Nz", C.c_int32), ("conv_width", C.c_int32), ("n_layers", C.c_int32),
+                ("layer_dims", C.c_int32 * (NFC_MAX_LAYERS + 1)), ("activations", C.c_int32 * NFC_MAX_LAYERS),
+                ("nde_type", C.c_int32), ("alg", C.c_int32), ("reltol", C.c_float), ("abstol", C.c_float),
+                ("fixed_dt", C.c_float), ("max_iters", C.c_int32), ("n_save", C.c_int32),
+                ("saveat", C.POINTER(C.c_float)), ("device", C.c_int32), ("adjoint_max_steps", C.c_int32),
+                ("adjoint_reltol", C.c_float), ("adjoint_abstol", C.c_float), ("reserved", C.c_int32 * 8)]
+
+
+class NfcCounters(C.Structure):
+    _fields_ = [("columns", C.c_int64), ("steps_accepted", C.c_int64), ("steps_rejected", C.c_int64),
+                ("adj_steps_accepted", C.c_int64), ("adj_steps_rejected", C.c_int64), ("kernel_launches", C.c_int64),
+                ("last_kernel_ms", C.c_float), ("last_adjoint_ms", C.c_float)]
+
+
+_lib = None
+
+
+def load():
+    """dlopen the in-tree CUDA library.  Raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run ./build.sh (nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    fp, ip, dp, vp = C.POINTER(C.c_float), C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_void_p
+    lib.nfc_create.argtypes = [C.POINTER(NfcConfig), C.POINTER(vp)]
+    lib.nfc_destroy.argtypes = [vp]
+    lib.nfc_last_error.argtypes = [vp]
+    lib.nfc_last_error.restype = C.c_char_p
+    lib.nfc_n_params.argtypes = [vp]
+    lib.nfc_n_params.restype = C.c_int64
+    lib.nfc_set_weights.argtypes = [vp, fp, C.c_int64]
+    lib.nfc_set_saveat.argtypes = [vp, fp, C.c_int32]
+    lib.nfc_get_counters.argtypes = [vp, C.POINTER(NfcCounters)]
+    lib.nfc_rhs.argtypes = [vp, fp, fp, fp, fp, C.c_int64]
+    lib.nfc_solve.argtypes = [vp, fp, fp, fp, fp, ip, ip, ip, C.c_int64]
+    lib.nfc_diagnose_flux.argtypes = [vp, fp, fp, fp, C.c_int64]
+    lib.nfc_loss_grad.argtypes = [vp, fp, fp, fp, fp, dp, fp, ip, C.c_int64]
+    lib.nfc_rhs_dev.argtypes = [vp, vp, vp, vp, vp, C.c_int64, vp]
+    lib.nfc_solve_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int64, vp]
+    lib.nfc_loss_grad_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int64, vp]
+    lib.nfc_sync.argtypes = [vp]
+    for name in EXPORTS:
+        if name not in ("nfc_last_error", "nfc_n_params"):
+            getattr(lib, name).restype = C.c_int32
+    _lib = lib
+    return lib
+
+
+def _f32(a):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return a
+
+
+def _fp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32)) if a is not None else None
+
+
+class NfcError(RuntimeError):
+    pass
+
+
+class Handle:
+    """Owns one nfc_handle (device buffers, stream).  Thin, 1:1 with include/nfc.h."""
+
+    def __init__(self, conv_width, layers, nde_type, saveat, reltol=1e-4, abstol=1e-6, fixed_dt=0.0, device=0,
+                 max_iters=100000, adjoint_max_steps=0, adjoint_reltol=0.0, adjoint_abstol=0.0, Nz=32):
+        self.lib = load()
+        cfg = NfcConfig()
+        cfg.struct_size = C.sizeof(NfcConfig)
+        cfg.Nz = Nz
+        cfg.conv_width = conv_width
+        if len(layers) > NFC_MAX_LAYERS:
+            raise NfcError("too many Dense layers")
+        cfg.n_layers = len(layers)
+        dims = [layers[0][0]] + [o for _, o, _ in layers]
+        for i, d in enumerate(dims):
+            cfg.layer_dims[i] = d
+        for i, (_, _, a) in enumerate(layers):
+            cfg.activations[i] = a
+        cfg.nde_type = nde_type
+        cfg.alg = 0
+        cfg.reltol, cfg.abstol, cfg.fixed_dt = reltol, abstol, fixed_dt
+        cfg.max_iters = max_iters
+        self.saveat = _f32(saveat)
+        cfg.n_save = self.saveat.size
+        cfg.saveat = _fp(self.saveat)
+        cfg.device = device
+        cfg.adjoint_max_steps = adjoint_max_steps
+        cfg.adjoint_reltol, cfg.adjoint_abstol = adjoint_reltol, adjoint_abstol
+        self.Nz = Nz
+        self.n_save = int(cfg.n_save)
+        self.device = device
+        h = C.c_void_p()
+        rc = self.lib.nfc_create(C.byref(cfg), C.byref(h))
+        if rc != 0:
+            raise NfcError(f"nfc_create failed ({rc}): {self.lib.nfc_last_error(None).decode()}")
+        self.h = h
+        self.n_params = int(self.lib.nfc_n_params(h))
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise NfcError(f"{what} failed ({rc}): {self.lib.nfc_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.nfc_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_weights(self, theta):
+        theta = _f32(theta)
+        self._check(self.lib.nfc_set_weights(self.h, _fp(theta), theta.size), "nfc_set_weights")
+
+    def set_saveat(self, saveat):
+        self.saveat = _f32(saveat)
+        self.n_save = self.saveat.size
+        self._check(self.lib.nfc_set_saveat(self.h, _fp(self.saveat), self.n_save), "nfc_set_saveat")
+
+    def counters(self):
+        c = NfcCounters()
+        self._check(self.lib.nfc_get_counters(self.h, C.byref(c)), "nfc_get_counters")
+        return {k: getattr(c, k) for k, _ in NfcCounters._fields_}
+
+    # ---- host-buffer calls ----
+    def rhs(self, T, colp, glob):
+        T, colp, glob = _f32(T), _f32(colp), _f32(glob)
+        B = T.shape[0]
+        out = np.empty_like(T)
+        self._check(self.lib.nfc_rhs(self.h, _fp(T), _fp(colp), _fp(glob), _fp(out), B), "nfc_rhs")
+        return out
+
+    def solve(self, T0, colp, glob, out=None):
+        T0, colp, glob = _f32(T0), _f32(colp), _f32(glob)
+        B = T0.shape[0]
+        if out is None:
+            out = np.empty((B, self.n_save, self.Nz), dtype=np.float32)
+        na, nr, st = (np.zeros(B, dtype=np.int32) for _ in range(3))
+        self._check(self.lib.nfc_solve(self.h, _fp(T0), _fp(colp), _fp(glob), _fp(out), _ip(na), _ip(nr), _ip(st), B),
+                    "nfc_solve")
+        return dict(T=out, naccept=na, nreject=nr, status=st)
+
+    def diagnose_flux(self, Tsol, colp):
+        Tsol, colp = _f32(Tsol), _f32(colp)
+        B = Tsol.shape[0]
+        wT = np.empty((B, self.n_save, self.Nz + 1), dtype=np.float32)
+        self._check(self.lib.nfc_diagnose_flux(self.h, _fp(Tsol), _fp(colp), _fp(wT), B), "nfc_diagnose_flux")
+        return wT
+
+    def loss_grad(self, T0, colp, glob, Ttrue):
+        T0, colp, glob, Ttrue = _f32(T0), _f32(colp), _f32(glob), _f32(Ttrue)
+        B = T0.shape[0]
+        grad = np.zeros(self.n_params, dtype=np.float32)
+        st = np.zeros(B, dtype=np.int32)
+        loss = C.c_double(0.0)
+        self._check(self.lib.nfc_loss_grad(self.h, _fp(T0), _fp(colp), _fp(glob), _fp(Ttrue), C.byref(loss), _fp(grad),
+                                           _ip(st), B), "nfc_loss_grad")
+        return dict(loss=loss.value, grad=grad, status=st)
+
+    # ---- device-buffer calls (torch tensors on this handle's device; plumbing only) ----
+    def rhs_dev(self, T, colp, glob, out, stream=None):
+        self._check(self.lib.nfc_rhs_dev(self.h, T.data_ptr(), colp.data_ptr(), glob.data_ptr(), out.data_ptr(),
+                                         T.shape[0], stream), "nfc_rhs_dev")
+
+    def solve_dev(self, T0, colp, glob, Tout, naccept=None, nreject=None, status=None, stream=None):
+        p = lambda t: t.data_ptr() if t is not None else None
+        self._check(self.lib.nfc_solve_dev(self.h, T0.data_ptr(), colp.data_ptr(), glob.data_ptr(), Tout.data_ptr(),
+                                           p(naccept), p(nreject), p(status), T0.shape[0], stream), "nfc_solve_dev")
+
+    def loss_grad_dev(self, T0, colp, glob, Ttrue, loss_sum, grad, status=None, n_total_columns=None, stream=None):
+        B = T0.shape[0]
+        self._check(self.lib.nfc_loss_grad_dev(self.h, T0.data_ptr(), colp.data_ptr(), glob.data_ptr(), Ttrue.data_ptr(),
+                                               loss_sum.data_ptr(), grad.data_ptr(),
+                                               status.data_ptr() if status is not None else None, B,
+                                               n_total_columns if n_total_columns is not None else B, stream),
+                    "nfc_loss_grad_dev")
+
+    def sync(self):
+        self._check(self.lib.nfc_sync(self.h), "nfc_sync")

@@ -1,0 +1,287 @@
+"""Host-side mirror of the reference's API for the NDE hot path (Julia is not available in this image, so
+the host language is Python over the C ABI; `julia/FreeConvectionB200.jl` is the ccall shim a maintainer
+would drop into the reference).  Names, argument order and error behaviour follow the reference:
+
+    Chain / Dense / Conv / destructure          Flux 0.12.6 as used at train_free_convection_nde.jl:125-156, src/solve.jl:2
+    ZeroMeanUnitVarianceScaling                 train_free_convection_nde.jl:216-217 (OceanParameterizations)
+    FreeConvectionNDE, ...Parameters            src/free_convection_nde.jl:1-62
+    ConvectiveAdjustmentNDE, ...Parameters      src/convective_adjustment_nde.jl:1-72
+    solve_nde (2 methods)                       src/solve.jl:1-51
+    train_neural_differential_equation          src/training.jl:34-78 (Julia: train_neural_differential_equation!)
+    ADAM                                        Flux.ADAM defaults (train_free_convection_nde.jl:245)
+
+All numerics run in libnfc_b200.so on the GPU; nothing here evaluates the network or integrates on the CPU.
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _binding as B_
+from .synthetic import Scaling as ZeroMeanUnitVarianceScaling  # same object as the synthetic generator uses
+
+ACT_IDENTITY, ACT_RELU = 0, 1
+identity, relu = ACT_IDENTITY, ACT_RELU
+
+
+# ------------------------------------------------------------------------------------------------
+# Flux-like containers (parameters only; evaluation happens on the GPU)
+# ------------------------------------------------------------------------------------------------
+class Dense:
+    """Dense(in, out, act): weight is out x in, bias out (Flux field names `weight`, `bias`)."""
+
+    def __init__(self, n_in, n_out, act=identity, rng=None):
+        rng = rng or np.random.default_rng()
+        lim = np.sqrt(6.0 / (n_in + n_out))                       # Flux glorot_uniform
+        self.weight = rng.uniform(-lim, lim, (n_out, n_in)).astype(np.float32)
+        self.bias = np.zeros(n_out, dtype=np.float32)
+        self.act = act
+
+
+class Conv:
+    """Conv((k,1), 1=>1, relu) front-end of the conv-2 / conv-4 Chains (train_free_convection_nde.jl:138-153)."""
+
+    def __init__(self, k, act=relu, rng=None):
+        rng = rng or np.random.default_rng()
+        lim = np.sqrt(6.0 / (k + k))
+        self.weight = rng.uniform(-lim, lim, k).astype(np.float32)
+        self.bias = np.zeros(1, dtype=np.float32)
+        self.act = act
+
+
+class Chain:
+    def __init__(self, *layers):
+        self.layers = list(layers)
+
+    def params(self):
+        return [p for l in self.layers for p in (l.weight, l.bias)]
+
+    @property
+    def conv_width(self):
+        return self.layers[0].weight.size if isinstance(self.layers[0], Conv) else 0
+
+    @property
+    def dense_spec(self):
+        return [(l.weight.shape[1], l.weight.shape[0], l.act) for l in self.layers if isinstance(l, Dense)]
+
+
+def named_chain(arch="dense-default", Nz=32, seed=0):
+    """The five architectures of train_free_convection_nde.jl:125-153."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    if arch == "dense-default":
+        return Chain(Dense(Nz, 4 * Nz, relu, rng), Dense(4 * Nz, 4 * Nz, relu, rng), Dense(4 * Nz, Nz - 1, identity, rng))
+    if arch == "dense-wider":
+        return Chain(Dense(Nz, 8 * Nz, relu, rng), Dense(8 * Nz, 8 * Nz, relu, rng), Dense(8 * Nz, Nz - 1, identity, rng))
+    if arch == "dense-deeper":
+        return Chain(Dense(Nz, 4 * Nz, relu, rng), Dense(4 * Nz, 4 * Nz, relu, rng), Dense(4 * Nz, 4 * Nz, relu, rng),
+                     Dense(4 * Nz, Nz - 1, identity, rng))
+    if arch in ("conv-2", "conv-4"):
+        k = int(arch[-1])
+        return Chain(Conv(k, relu, rng), Dense(Nz - k + 1, 4 * Nz, relu, rng), Dense(4 * Nz, 4 * Nz, relu, rng),
+                     Dense(4 * Nz, Nz - 1, identity, rng))
+    raise ValueError(f"Invalid neural network architecture: {arch}")
+
+
+def destructure(NN: Chain):
+    """Flux.destructure: flat Float32 vector (layer order; weight column-major, then bias) and a re-builder."""
+    theta = np.concatenate([np.asarray(p, dtype=np.float32).reshape(-1, order="F") for p in NN.params()])
+
+    def reconstruct(flat):
+        flat = np.asarray(flat, dtype=np.float32)
+        out = Chain(*[_clone(l) for l in NN.layers])
+        off = 0
+        for l in out.layers:
+            for name in ("weight", "bias"):
+                p = getattr(l, name)
+                setattr(l, name, flat[off:off + p.size].reshape(p.shape, order="F").copy())
+                off += p.size
+        return out                     # like Flux's _restructure, extra trailing elements are ignored
+
+    return theta, reconstruct
+
+
+def _clone(l):
+    c = object.__new__(type(l))
+    c.weight, c.bias, c.act = l.weight.copy(), l.bias.copy(), l.act
+    return c
+
+
+# ------------------------------------------------------------------------------------------------
+# Datasets: the slice of Oceananigans' FieldDataset the NDE path touches (ds["T"], ds["wT"], metadata)
+# ------------------------------------------------------------------------------------------------
+@dataclass
+class ColumnDataset:
+    T: np.ndarray                 # [Nz, Nt]   horizontally averaged temperature (unscaled)
+    wT: np.ndarray                # [Nz+1, Nt] turbulent heat flux on faces (unscaled)
+    zc: np.ndarray                # [Nz] cell centres (negative, index 0 deepest)
+    zf: np.ndarray                # [Nz+1]
+    times: np.ndarray             # [Nt] seconds
+    metadata: dict = field(default_factory=dict)   # "temperature_flux"
+
+
+class _NDE:
+    """What `FreeConvectionNDE(NN, ds; iterations)` returns in the reference: an ODEProblem with tspan/saveat
+    (src/free_convection_nde.jl:40-46); here it also owns the GPU handle."""
+
+    nde_type = None
+
+    def __init__(self, NN, ds, iterations=None, device=0, reltol=1e-4, abstol=1e-6, **kw):
+        Nz, Nt = ds.T.shape
+        self.Nz, self.Nt = Nz, Nt
+        self.H = abs(float(ds.zf[0]))
+        self.tau = float(ds.times[-1])
+        if iterations is None:
+            iterations = range(1, Nt + 1)
+        iterations = np.asarray(list(iterations))
+        self.iterations = iterations
+        self.tspan = (np.float32(0.0), np.float32(iterations.max() / Nt))
+        self.saveat = np.linspace(self.tspan[0], self.tspan[1], len(iterations)).astype(np.float32)
+        self.handle = B_.Handle(NN.conv_width, NN.dense_spec, self.nde_type, self.saveat, reltol=reltol, abstol=abstol,
+                                device=device, Nz=Nz, **kw)
+
+
+class FreeConvectionNDE(_NDE):
+    nde_type = 0
+
+
+class ConvectiveAdjustmentNDE(_NDE):
+    nde_type = 1
+
+
+def FreeConvectionNDEParameters(ds, T_scaling, wT_scaling):
+    """[bottom_flux, top_flux, sigma_T, sigma_wT, H, tau] as Float32 (src/free_convection_nde.jl:49-62)."""
+    H, tau = abs(float(ds.zf[0])), float(ds.times[-1])
+    return np.array([wT_scaling(ds.wT[0, 0]), wT_scaling(ds.metadata["temperature_flux"]), T_scaling.sigma,
+                     wT_scaling.sigma, H, tau], dtype=np.float32)
+
+
+def ConvectiveAdjustmentNDEParameters(ds, T_scaling, wT_scaling, K_CA):
+    """7-vector with trailing K_CA (src/convective_adjustment_nde.jl:59-72)."""
+    return np.concatenate([FreeConvectionNDEParameters(ds, T_scaling, wT_scaling), np.float32([K_CA])])
+
+
+def _split_params(nde, nde_params):
+    p = np.asarray(nde_params, dtype=np.float32)
+    want = 6 if nde.nde_type == 0 else 7
+    if p.shape[-1] != want:       # the reference would mis-slice silently; be loud instead
+        raise ValueError(f"{type(nde).__name__} needs {want} trailing parameters, got {p.shape[-1]}")
+    p2 = np.atleast_2d(p)
+    colp = np.zeros((p2.shape[0], 3), dtype=np.float32)
+    colp[:, 0:2] = p2[:, 0:2]
+    if want == 7:
+        colp[:, 2] = p2[:, 6]
+    glob = p2[0, 2:6].copy()
+    if not np.all(p2[:, 2:6] == glob):
+        raise ValueError("sigma_T, sigma_wT, H, tau must be shared by all columns of one call")
+    return colp, glob
+
+
+def solve_nde(*args, **kw):
+    """solve_nde(nde, NN, T0, alg, nde_params) -> Array [Nz, n_save]  (src/solve.jl:1-6), or batched: T0 [B, Nz]
+    with nde_params [B, 6|7] -> [B, n_save, Nz];
+    solve_nde(ds, NN, NDEType, nde_params, algorithm, T_scaling, wT_scaling; T0=None) -> (T, wT)  (src/solve.jl:8-51)."""
+    if isinstance(args[0], _NDE):
+        nde, NN, T0, alg, nde_params = args
+        _check_alg(alg)
+        theta, _ = destructure(NN)
+        nde.handle.set_weights(theta)
+        colp, glob = _split_params(nde, nde_params)
+        T0 = np.asarray(T0, dtype=np.float32)
+        single = T0.ndim == 1
+        res = nde.handle.solve(np.atleast_2d(T0), colp, glob)
+        nde.last = res
+        return res["T"][0].T.copy() if single else res["T"]
+    ds, NN, NDEType, nde_params, algorithm, T_scaling, wT_scaling = args
+    T0 = kw.get("T0")
+    nde = NDEType(NN, ds)
+    if T0 is None:
+        T0 = T_scaling(ds.T[:, 0])
+    if len(nde_params) < 7:
+        raise IndexError("solve_nde(ds, ...) reads nde_params[7] (src/solve.jl:30): pass ConvectiveAdjustmentNDEParameters")
+    p = np.asarray(nde_params, dtype=np.float32)
+    T = solve_nde(nde, NN, T0, algorithm, p if nde.nde_type == 1 else p[:6])          # [Nz, Nt]
+    colp, _ = _split_params(nde, p if nde.nde_type == 1 else p[:6])
+    wT = nde.handle.diagnose_flux(T.T[None], colp)[0].T                                 # [Nz+1, Nt]
+    return dict(T=T_scaling.inv(T), wT=wT_scaling.inv(wT))
+
+
+def _check_alg(alg):
+    name = alg if isinstance(alg, str) else type(alg).__name__
+    if name not in ("Tsit5", "Tsit5()"):
+        raise NotImplementedError(f"time stepper {name}: this build implements Tsit5 (ROCK4 is SURVEY.md row f2)")
+
+
+class Tsit5:
+    pass
+
+
+class ADAM:
+    """Flux.ADAM(eta=1e-3, beta=(0.9, 0.999)), eps = 1e-8 [UPSTREAM Flux 0.12.6]."""
+
+    def __init__(self, eta=1e-3, beta=(0.9, 0.999), eps=1e-8):
+        self.eta, self.beta, self.eps = eta, beta, eps
+        self.m = self.v = None
+        self.bp = [1.0, 1.0]
+
+    def update(self, theta, g):
+        if self.m is None:
+            self.m, self.v = np.zeros_like(theta), np.zeros_like(theta)
+        b1, b2 = self.beta
+        self.m = b1 * self.m + (1 - b1) * g
+        self.v = b2 * self.v + (1 - b2) * g * g
+        self.bp[0] *= b1
+        self.bp[1] *= b2
+        return theta - self.eta * (self.m / (1 - self.bp[0])) / (np.sqrt(self.v / (1 - self.bp[1])) + self.eps)
+
+
+def train_neural_differential_equation(NN, NDEType, nde_params, algorithm, datasets, T_scaling, iterations, opt, epochs,
+                                       history_filepath=None, device=0, callback=None):
+    """train_neural_differential_equation!(...) (src/training.jl:34-78): full-batch ADAM on the MSE between the NDE
+    solutions and the scaled truth of every training simulation.  One epoch = one nfc_loss_grad call (all simulations
+    in one launch) + the callback's loss re-evaluation (src/training.jl:53-68).  Returns the best-loss Chain
+    (GalacticOptim returns sol.minimizer, src/training.jl:74)."""
+    _check_alg(algorithm)
+    ids = sorted(datasets.keys())
+    it = np.asarray(list(iterations)) - 1                                   # Julia 1-based -> 0-based
+    T0 = np.stack([T_scaling(datasets[i].T[:, 0]) for i in ids]).astype(np.float32)
+    ndes = {i: NDEType(NN, datasets[i], iterations=iterations, device=device) for i in ids[:1]}   # shared handle
+    nde = ndes[ids[0]]
+    true_sols = np.stack([T_scaling(datasets[i].T[:, it]).T for i in ids]).astype(np.float32)     # [B, n_save, Nz]
+    P = np.stack([np.asarray(nde_params[i], dtype=np.float32) for i in ids])
+    colp, glob = _split_params(nde, P if nde.nde_type == 1 else P[:, :6])
+    theta, reconstruct = destructure(NN)
+    best = (np.inf, theta.copy())
+    history = []
+    t0 = time.time()
+    for epoch in range(1, epochs + 1):
+        nde.handle.set_weights(theta)
+        res = nde.handle.loss_grad(T0, colp, glob, true_sols)
+        if res["loss"] < best[0]:
+            best = (res["loss"], theta.copy())
+        runtime = time.time() - t0
+        history.append(dict(epoch=epoch, mean_loss=res["loss"], runtime=runtime))
+        if callback is not None:
+            callback(epoch, theta, res["loss"])
+        _inscribe_history(history_filepath, epoch, theta, res["loss"], runtime)
+        t0 = time.time()
+        theta = opt.update(theta, res["grad"]).astype(np.float32)
+    NN_final = reconstruct(best[1])
+    NN_final.history = history
+    return NN_final
+
+
+def _inscribe_history(path, epoch, theta, loss, runtime):
+    """inscribe_history (src/training.jl:3-12) -- keys neural_network/<e>, mean_loss/<e>, runtime/<e>; stored as .npz
+    because JLD2 is a Julia format."""
+    if path is None:
+        return
+    import os
+    if not path.endswith(".npz"):
+        path += ".npz"
+    prev = dict(np.load(path)) if os.path.exists(path) else {}
+    prev[f"neural_network/{epoch}"] = theta
+    prev[f"mean_loss/{epoch}"] = np.float64(loss)
+    prev[f"runtime/{epoch}"] = np.float64(runtime)
+    np.savez(path, **prev)

@@ -1,0 +1,403 @@
+// nfc_api.cu -- the C ABI of libnfc_b200.so (declared in include/nfc.h).  sm_100a only, no CPU fallback.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "nfc_host.h"
+#include "nfc_forward.cuh"
+#include "nfc_launch.h"
+
+using namespace nfc;
+
+namespace {
+
+Arch classify(const nfc_config& c) {
+    if (c.Nz != NZ) return ARCH_NONE;
+    const int cw = c.conv_width, nl = c.n_layers;
+    if (nl < 2 || nl > NFC_MAX_LAYERS) return ARCH_NONE;
+    const int in0 = NZ - (cw ? cw - 1 : 0);
+    if (c.layer_dims[0] != in0 || c.layer_dims[nl] != NZ - 1) return ARCH_NONE;
+    const int H = c.layer_dims[1];
+    for (int l = 1; l < nl; ++l) if (c.layer_dims[l] != H) return ARCH_NONE;
+    for (int l = 0; l < nl - 1; ++l) if (c.activations[l] != NFC_ACT_RELU) return ARCH_NONE;
+    if (c.activations[nl - 1] != NFC_ACT_IDENTITY) return ARCH_NONE;
+    if (cw == 0 && H == 128 && nl == 3) return ARCH_DEFAULT;
+    if (cw == 0 && H == 256 && nl == 3) return ARCH_WIDER;
+    if (cw == 0 && H == 128 && nl == 4) return ARCH_DEEPER;
+    if (cw == 2 && H == 128 && nl == 3) return ARCH_CONV2;
+    if (cw == 4 && H == 128 && nl == 3) return ARCH_CONV4;
+    return ARCH_NONE;
+}
+
+#define NFC_DISPATCH(h, FN, ...)                                      \
+    switch ((h)->arch) {                                              \
+        case ARCH_DEFAULT: return FN<NetDefault>(__VA_ARGS__);        \
+        case ARCH_WIDER: return FN<NetWider>(__VA_ARGS__);            \
+        case ARCH_DEEPER: return FN<NetDeeper>(__VA_ARGS__);          \
+        case ARCH_CONV2: return FN<NetConv2>(__VA_ARGS__);            \
+        case ARCH_CONV4: return FN<NetConv4>(__VA_ARGS__);            \
+        default: return fail(h, -3, "unsupported architecture");      \
+    }
+
+template <class N>
+int arch_setup(nfc_handle* h) {
+    h->n_params = N::T_TOTAL;
+    h->n_packed = N::P_TOTAL;
+    constexpr bool WS = Launch<N>::WS;
+    constexpr int NW = Launch<N>::NW;
+    NFC_CUDA(h, cudaFuncSetAttribute(rhs_init_kernel<N, WS, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<N>(8)));
+    NFC_CUDA(h, cudaFuncSetAttribute(rhs_init_kernel<N, WS, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<N>(8)));
+    NFC_CUDA(h, cudaFuncSetAttribute(diagnose_flux_kernel<N, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<N>(8)));
+    NFC_CUDA(h, cudaFuncSetAttribute(solve_kernel<N, WS, NW, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<N>(NW)));
+    NFC_CUDA(h, cudaFuncSetAttribute(solve_kernel<N, WS, NW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<N>(NW)));
+    return adjoint_setup<N>(h);
+}
+
+template <class N>
+int do_pack(nfc_handle* h) {
+    pack_weights_kernel<N><<<(N::P_TOTAL + 255) / 256, 256, 0, h->stream>>>(h->d_theta.p, h->d_wpack.p);
+    NFC_CUDA(h, cudaGetLastError());
+    return 0;
+}
+
+inline float prefactor(const float* glob) { return glob[1] / glob[0] * glob[3] / glob[2]; }   // src/convective_adjustment_nde.jl:47
+
+template <class N>
+int do_rhs(nfc_handle* h, const float* T, const float* colp, float pref, float* out, int64_t B, cudaStream_t st) {
+    constexpr bool WS = Launch<N>::WS;
+    const long long groups = (B + CPW - 1) / CPW;
+    const int grid = (int)std::min<long long>(h->num_sms, (groups + 7) / 8);
+    rhs_init_kernel<N, WS, 0><<<grid, 256, smem_bytes<N>(8), st>>>(h->d_wpack.p, T, colp, out, nullptr, B, pref,
+                                                                   h->cfg.nde_type == NFC_NDE_CONVECTIVE_ADJUSTMENT, h->cfg.reltol,
+                                                                   h->cfg.abstol, h->saveat.back(), h->cfg.fixed_dt);
+    NFC_CUDA(h, cudaGetLastError());
+    h->last_launches += 1;
+    return 0;
+}
+
+template <class N>
+int do_diagnose(nfc_handle* h, const float* Tsol, const float* colp, float* wT, int64_t B, cudaStream_t st) {
+    constexpr bool WS = Launch<N>::WS;
+    const long long groups = (B * h->cfg.n_save + CPW - 1) / CPW;
+    const int grid = (int)std::min<long long>(h->num_sms, (groups + 7) / 8);
+    diagnose_flux_kernel<N, WS><<<grid, 256, smem_bytes<N>(8), st>>>(h->d_wpack.p, Tsol, colp, wT, B, h->cfg.n_save,
+                                                                     h->cfg.nde_type == NFC_NDE_CONVECTIVE_ADJUSTMENT);
+    NFC_CUDA(h, cudaGetLastError());
+    h->last_launches += 1;
+    return 0;
+}
+
+// forward solve (RECORD=false) or forward pass of loss_grad (RECORD=true)
+template <class N, bool RECORD>
+int launch_solve(nfc_handle* h, SolveParams& P, cudaStream_t st) {
+    constexpr bool WS = Launch<N>::WS;
+    constexpr int NW = Launch<N>::NW;
+    const long long B = P.B;
+    NFC_CUDA(h, h->d_k1.ensure((size_t)B * NZ));
+    NFC_CUDA(h, h->d_dt.ensure((size_t)B));
+    P.wpack = h->d_wpack.p;
+    P.k1_init = h->d_k1.p;
+    P.dt_init = h->d_dt.p;
+    P.saveat = h->d_saveat.p;
+    P.counters = h->d_counters.p;
+    P.n_save = h->cfg.n_save;
+    P.max_iters = h->cfg.max_iters;
+    P.use_kca = h->cfg.nde_type == NFC_NDE_CONVECTIVE_ADJUSTMENT;
+    P.tf = h->saveat.back();
+    P.reltol = h->cfg.reltol; P.abstol = h->cfg.abstol; P.fixed_dt = h->cfg.fixed_dt;
+    NFC_CUDA(h, cudaMemsetAsync(h->d_counters.p, 0, sizeof(unsigned long long) * CTR_COUNT, st));
+    NFC_CUDA(h, cudaEventRecord(h->ev[0], st));
+    const long long groups = (B + CPW - 1) / CPW;
+    const int grid0 = (int)std::min<long long>(h->num_sms, (groups + 7) / 8);
+    rhs_init_kernel<N, WS, 1><<<grid0, 256, smem_bytes<N>(8), st>>>(h->d_wpack.p, P.T0, P.colp, h->d_k1.p, h->d_dt.p, B, P.pref, P.use_kca,
+                                                                    P.reltol, P.abstol, P.tf, P.fixed_dt);
+    NFC_CUDA(h, cudaGetLastError());
+    const int grid = (int)std::min<long long>(h->num_sms, (groups + NW - 1) / NW);
+    solve_kernel<N, WS, NW, RECORD><<<grid, NW * 32, smem_bytes<N>(NW), st>>>(P);
+    NFC_CUDA(h, cudaGetLastError());
+    NFC_CUDA(h, cudaEventRecord(h->ev[1], st));
+    h->ev_fwd_valid = true;
+    h->last_launches += 2;
+    h->last_columns = B;
+    return 0;
+}
+
+}  // namespace
+// the adjoint's host code reuses launch_solve<N, true> (forward pass in RECORD mode)
+template <class N>
+int nfc_launch_record(nfc_handle* h, nfc::SolveParams& P, cudaStream_t st) { return launch_solve<N, true>(h, P, st); }
+#include "nfc_adjoint.cuh"
+namespace {
+
+template <class N>
+int do_solve(nfc_handle* h, const float* T0, const float* colp, float pref, float* Tout, int* nacc, int* nrej, int* status, int64_t B,
+             cudaStream_t st) {
+    SolveParams P{};
+    P.T0 = T0; P.colp = colp; P.pref = pref; P.Tout = Tout; P.naccept = nacc; P.nreject = nrej; P.status = status; P.B = B;
+    return launch_solve<N, false>(h, P, st);
+}
+
+template <class N>
+int do_loss_grad(nfc_handle* h, const float* T0, const float* colp, float pref, const float* Ttrue, double* loss_sum_dev, float* grad_dev,
+                 int* status, int64_t B, int64_t n_total_columns, cudaStream_t st) {
+    return adjoint_loss_grad<N, Launch<N>::WS, Launch<N>::NW>(h, T0, colp, pref, Ttrue, loss_sum_dev, grad_dev, status, B, n_total_columns, st);
+}
+
+int check_ready(nfc_handle* h, int64_t B) {
+    if (!h) return -1;
+    if (B < 0) return fail(h, -2, "negative column count");
+    if (!h->weights_set) return fail(h, -2, "nfc_set_weights has not been called");
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e != cudaSuccess) return fail(h, -10, "cudaSetDevice(%d): %s", h->device, cudaGetErrorString(e));
+    return 0;
+}
+
+}  // namespace
+
+
+extern "C" {
+
+const char* nfc_last_error(const nfc_handle* h) { return h ? h->err.c_str() : create_error().c_str(); }
+
+int32_t nfc_create(const nfc_config* cfg, nfc_handle** out) {
+    if (!cfg || !out) return fail(nullptr, -1, "null argument");
+    *out = nullptr;
+    if (cfg->struct_size != (int32_t)sizeof(nfc_config)) return fail(nullptr, -2, "nfc_config.struct_size %d != %zu", cfg->struct_size, sizeof(nfc_config));
+    if (cfg->Nz != NZ) return fail(nullptr, -3, "this build supports Nz = 32 only (got %d)", cfg->Nz);
+    if (cfg->alg != NFC_ALG_TSIT5) return fail(nullptr, -3, "unsupported algorithm id %d (Tsit5 = 0)", cfg->alg);
+    if (cfg->nde_type != NFC_NDE_FREE_CONVECTION && cfg->nde_type != NFC_NDE_CONVECTIVE_ADJUSTMENT) return fail(nullptr, -2, "bad nde_type");
+    if (cfg->n_save < 1 || !cfg->saveat) return fail(nullptr, -2, "saveat must hold at least one time");
+    if (!(cfg->reltol > 0.f) || !(cfg->abstol >= 0.f)) return fail(nullptr, -2, "bad tolerances");
+    const Arch a = classify(*cfg);
+    if (a == ARCH_NONE)
+        return fail(nullptr, -3, "unsupported Chain: need [Conv(2|4)] -> Dense(in,H,relu) -> Dense(H,H,relu)x(1|2) -> Dense(H,31), H in {128,256}");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return fail(nullptr, -11, "no CUDA device (libnfc_b200 has no CPU fallback): %s", cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, -2, "device %d out of range (%d devices)", cfg->device, ndev);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, cfg->device);
+    if (e != cudaSuccess) return fail(nullptr, -10, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10) return fail(nullptr, -11, "device %d is sm_%d%d; libnfc_b200 is built for sm_100a only", cfg->device, prop.major, prop.minor);
+    nfc_handle* h = new nfc_handle();
+    h->cfg = *cfg;
+    if (h->cfg.max_iters <= 0) h->cfg.max_iters = 100000;
+    if (h->cfg.adjoint_max_steps <= 0) h->cfg.adjoint_max_steps = 1024;
+    if (!(h->cfg.adjoint_reltol > 0.f)) h->cfg.adjoint_reltol = h->cfg.reltol;
+    if (!(h->cfg.adjoint_abstol > 0.f)) h->cfg.adjoint_abstol = h->cfg.abstol;
+    h->saveat.assign(cfg->saveat, cfg->saveat + cfg->n_save);
+    h->cfg.saveat = nullptr;
+    h->arch = a;
+    h->device = cfg->device;
+    h->num_sms = prop.multiProcessorCount;
+    auto bail = [&](int code) { create_error() = h->err; nfc_destroy(h); return code; };
+    if (cudaSetDevice(h->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return bail(-10); }
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "cudaStreamCreate failed"; return bail(-10); }
+    for (auto& ev : h->ev) if (cudaEventCreate(&ev) != cudaSuccess) { h->err = "cudaEventCreate failed"; return bail(-10); }
+    int rc = [&]() -> int { NFC_DISPATCH(h, arch_setup, h); }();
+    if (rc) return bail(rc);
+    if (h->d_theta.ensure(h->n_params) || h->d_wpack.ensure(h->n_packed) || h->d_saveat.ensure(h->saveat.size()) ||
+        h->d_counters.ensure(CTR_COUNT)) { h->err = "cudaMalloc failed"; return bail(-10); }
+    if (cudaMemcpy(h->d_saveat.p, h->saveat.data(), sizeof(float) * h->saveat.size(), cudaMemcpyHostToDevice) != cudaSuccess) { h->err = "saveat upload failed"; return bail(-10); }
+    cudaMemset(h->d_counters.p, 0, sizeof(unsigned long long) * CTR_COUNT);
+    *out = h;
+    return 0;
+}
+
+int32_t nfc_destroy(nfc_handle* h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    h->d_theta.release(); h->d_wpack.release(); h->d_saveat.release(); h->d_k1.release(); h->d_dt.release(); h->d_counters.release();
+    h->s_T0.release(); h->s_colp.release(); h->s_out.release(); h->s_true.release(); h->s_grad.release();
+    h->s_nacc.release(); h->s_nrej.release(); h->s_status.release(); h->s_loss.release();
+    h->a_resid.release(); h->a_tape.release(); h->a_gacc.release(); h->a_tlen.release(); h->a_gsum.release();
+    for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+int64_t nfc_n_params(const nfc_handle* h) { return h ? h->n_params : -1; }
+
+int32_t nfc_set_weights(nfc_handle* h, const float* theta, int64_t n) {
+    if (!h || !theta) return -1;
+    if (n != h->n_params) return fail(h, -2, "theta has %lld elements, the Chain needs %lld", (long long)n, (long long)h->n_params);
+    NFC_CUDA(h, cudaSetDevice(h->device));
+    NFC_CUDA(h, cudaMemcpyAsync(h->d_theta.p, theta, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+    int rc = [&]() -> int { NFC_DISPATCH(h, do_pack, h); }();
+    if (rc) return rc;
+    NFC_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->weights_set = true;
+    return 0;
+}
+
+int32_t nfc_set_saveat(nfc_handle* h, const float* saveat, int32_t n_save) {
+    if (!h || !saveat || n_save < 1) return -1;
+    NFC_CUDA(h, cudaSetDevice(h->device));
+    NFC_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->saveat.assign(saveat, saveat + n_save);
+    h->cfg.n_save = n_save;
+    NFC_CUDA(h, h->d_saveat.ensure(n_save));
+    NFC_CUDA(h, cudaMemcpy(h->d_saveat.p, saveat, sizeof(float) * n_save, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int32_t nfc_sync(nfc_handle* h) {
+    if (!h) return -1;
+    NFC_CUDA(h, cudaSetDevice(h->device));
+    NFC_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int32_t nfc_get_counters(const nfc_handle* hc, nfc_counters* out) {
+    nfc_handle* h = const_cast<nfc_handle*>(hc);
+    if (!h || !out) return -1;
+    NFC_CUDA(h, cudaSetDevice(h->device));
+    NFC_CUDA(h, cudaDeviceSynchronize());
+    unsigned long long c[CTR_COUNT];
+    NFC_CUDA(h, cudaMemcpy(c, h->d_counters.p, sizeof c, cudaMemcpyDeviceToHost));
+    memset(out, 0, sizeof *out);
+    out->columns = h->last_columns;
+    out->steps_accepted = (int64_t)c[CTR_ACCEPT];
+    out->steps_rejected = (int64_t)c[CTR_REJECT];
+    out->adj_steps_accepted = (int64_t)c[CTR_ADJ_ACCEPT];
+    out->adj_steps_rejected = (int64_t)c[CTR_ADJ_REJECT];
+    out->kernel_launches = h->last_launches;
+    if (h->ev_fwd_valid) cudaEventElapsedTime(&out->last_kernel_ms, h->ev[0], h->ev[1]);
+    if (h->ev_adj_valid) cudaEventElapsedTime(&out->last_adjoint_ms, h->ev[2], h->ev[3]);
+    return 0;
+}
+
+// ------------------------------------------ device-pointer calls ------------------------------------------
+int32_t nfc_rhs_dev(nfc_handle* h, const float* T, const float* colp, const float* glob, float* dTdt, int64_t B, void* stream) {
+    if (int rc = check_ready(h, B)) return rc;
+    if (B == 0) return 0;
+    // glob is tiny: read it on the host side of the call (device pointer -> 16-byte D2H)
+    float g[4];
+    NFC_CUDA(h, cudaMemcpy(g, glob, sizeof g, cudaMemcpyDefault));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    h->last_launches = 0;
+    NFC_DISPATCH(h, do_rhs, h, T, colp, prefactor(g), dTdt, B, st);
+}
+
+int32_t nfc_solve_dev(nfc_handle* h, const float* T0, const float* colp, const float* glob, float* Tout, int32_t* naccept, int32_t* nreject,
+                      int32_t* status, int64_t B, void* stream) {
+    if (int rc = check_ready(h, B)) return rc;
+    if (B == 0) return 0;
+    float g[4];
+    NFC_CUDA(h, cudaMemcpy(g, glob, sizeof g, cudaMemcpyDefault));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    h->last_launches = 0;
+    NFC_DISPATCH(h, do_solve, h, T0, colp, prefactor(g), Tout, naccept, nreject, status, B, st);
+}
+
+int32_t nfc_loss_grad_dev(nfc_handle* h, const float* T0, const float* colp, const float* glob, const float* Ttrue, double* loss_sum_dev,
+                          float* grad_dev, int32_t* status, int64_t B, int64_t n_total_columns, void* stream) {
+    if (int rc = check_ready(h, B)) return rc;
+    float g[4];
+    NFC_CUDA(h, cudaMemcpy(g, glob, sizeof g, cudaMemcpyDefault));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    h->last_launches = 0;
+    NFC_DISPATCH(h, do_loss_grad, h, T0, colp, prefactor(g), Ttrue, loss_sum_dev, grad_dev, status, B, n_total_columns, st);
+}
+
+// ------------------------------------------ host-pointer calls ------------------------------------------
+int32_t nfc_rhs(nfc_handle* h, const float* T, const float* colp, const float* glob, float* dTdt, int64_t B) {
+    if (int rc = check_ready(h, B)) return rc;
+    if (B == 0) return 0;
+    if (!T || !colp || !glob || !dTdt) return fail(h, -1, "null argument");
+    NFC_CUDA(h, h->s_T0.ensure((size_t)B * NZ));
+    NFC_CUDA(h, h->s_colp.ensure((size_t)B * 3));
+    NFC_CUDA(h, h->s_out.ensure((size_t)B * NZ));
+    NFC_CUDA(h, cudaMemcpyAsync(h->s_T0.p, T, sizeof(float) * B * NZ, cudaMemcpyHostToDevice, h->stream));
+    NFC_CUDA(h, cudaMemcpyAsync(h->s_colp.p, colp, sizeof(float) * B * 3, cudaMemcpyHostToDevice, h->stream));
+    h->last_launches = 0;
+    int rc = [&]() -> int { NFC_DISPATCH(h, do_rhs, h, h->s_T0.p, h->s_colp.p, prefactor(glob), h->s_out.p, B, h->stream); }();
+    if (rc) return rc;
+    NFC_CUDA(h, cudaMemcpyAsync(dTdt, h->s_out.p, sizeof(float) * B * NZ, cudaMemcpyDeviceToHost, h->stream));
+    NFC_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int32_t nfc_solve(nfc_handle* h, const float* T0, const float* colp, const float* glob, float* Tout, int32_t* naccept, int32_t* nreject,
+                  int32_t* status, int64_t B) {
+    if (int rc = check_ready(h, B)) return rc;
+    if (B == 0) return 0;
+    if (!T0 || !colp || !glob || !Tout) return fail(h, -1, "null argument");
+    const size_t nout = (size_t)B * h->cfg.n_save * NZ;
+    NFC_CUDA(h, h->s_T0.ensure((size_t)B * NZ));
+    NFC_CUDA(h, h->s_colp.ensure((size_t)B * 3));
+    NFC_CUDA(h, h->s_out.ensure(nout));
+    NFC_CUDA(h, h->s_nacc.ensure(B));
+    NFC_CUDA(h, h->s_nrej.ensure(B));
+    NFC_CUDA(h, h->s_status.ensure(B));
+    NFC_CUDA(h, cudaMemcpyAsync(h->s_T0.p, T0, sizeof(float) * B * NZ, cudaMemcpyHostToDevice, h->stream));
+    NFC_CUDA(h, cudaMemcpyAsync(h->s_colp.p, colp, sizeof(float) * B * 3, cudaMemcpyHostToDevice, h->stream));
+    h->last_launches = 0;
+    int rc = [&]() -> int {
+        NFC_DISPATCH(h, do_solve, h, h->s_T0.p, h->s_colp.p, prefactor(glob), h->s_out.p, h->s_nacc.p, h->s_nrej.p, h->s_status.p, B, h->stream);
+    }();
+    if (rc) return rc;
+    NFC_CUDA(h, cudaMemcpyAsync(Tout, h->s_out.p, sizeof(float) * nout, cudaMemcpyDeviceToHost, h->stream));
+    if (naccept) NFC_CUDA(h, cudaMemcpyAsync(naccept, h->s_nacc.p, sizeof(int) * B, cudaMemcpyDeviceToHost, h->stream));
+    if (nreject) NFC_CUDA(h, cudaMemcpyAsync(nreject, h->s_nrej.p, sizeof(int) * B, cudaMemcpyDeviceToHost, h->stream));
+    if (status) NFC_CUDA(h, cudaMemcpyAsync(status, h->s_status.p, sizeof(int) * B, cudaMemcpyDeviceToHost, h->stream));
+    NFC_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int32_t nfc_diagnose_flux(nfc_handle* h, const float* Tsol, const float* colp, float* wT, int64_t B) {
+    if (int rc = check_ready(h, B)) return rc;
+    if (B == 0) return 0;
+    if (!Tsol || !colp || !wT) return fail(h, -1, "null argument");
+    const size_t nin = (size_t)B * h->cfg.n_save * NZ, nout = (size_t)B * h->cfg.n_save * (NZ + 1);
+    NFC_CUDA(h, h->s_true.ensure(nin));
+    NFC_CUDA(h, h->s_colp.ensure((size_t)B * 3));
+    NFC_CUDA(h, h->s_out.ensure(nout));
+    NFC_CUDA(h, cudaMemcpyAsync(h->s_true.p, Tsol, sizeof(float) * nin, cudaMemcpyHostToDevice, h->stream));
+    NFC_CUDA(h, cudaMemcpyAsync(h->s_colp.p, colp, sizeof(float) * B * 3, cudaMemcpyHostToDevice, h->stream));
+    h->last_launches = 0;
+    int rc = [&]() -> int { NFC_DISPATCH(h, do_diagnose, h, h->s_true.p, h->s_colp.p, h->s_out.p, B, h->stream); }();
+    if (rc) return rc;
+    NFC_CUDA(h, cudaMemcpyAsync(wT, h->s_out.p, sizeof(float) * nout, cudaMemcpyDeviceToHost, h->stream));
+    NFC_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int32_t nfc_loss_grad(nfc_handle* h, const float* T0, const float* colp, const float* glob, const float* Ttrue, double* loss, float* grad_theta,
+                      int32_t* status, int64_t B) {
+    if (int rc = check_ready(h, B)) return rc;
+    if (B == 0) return fail(h, -2, "loss over zero columns is undefined");
+    if (!T0 || !colp || !glob || !Ttrue || !loss || !grad_theta) return fail(h, -1, "null argument");
+    const size_t ntraj = (size_t)B * h->cfg.n_save * NZ;
+    NFC_CUDA(h, h->s_T0.ensure((size_t)B * NZ));
+    NFC_CUDA(h, h->s_colp.ensure((size_t)B * 3));
+    NFC_CUDA(h, h->s_true.ensure(ntraj));
+    NFC_CUDA(h, h->s_grad.ensure(h->n_params));
+    NFC_CUDA(h, h->s_loss.ensure(2));
+    NFC_CUDA(h, h->s_status.ensure(B));
+    NFC_CUDA(h, cudaMemcpyAsync(h->s_T0.p, T0, sizeof(float) * B * NZ, cudaMemcpyHostToDevice, h->stream));
+    NFC_CUDA(h, cudaMemcpyAsync(h->s_colp.p, colp, sizeof(float) * B * 3, cudaMemcpyHostToDevice, h->stream));
+    NFC_CUDA(h, cudaMemcpyAsync(h->s_true.p, Ttrue, sizeof(float) * ntraj, cudaMemcpyHostToDevice, h->stream));
+    h->last_launches = 0;
+    int rc = [&]() -> int {
+        NFC_DISPATCH(h, do_loss_grad, h, h->s_T0.p, h->s_colp.p, prefactor(glob), h->s_true.p, h->s_loss.p, h->s_grad.p, h->s_status.p, B, B, h->stream);
+    }();
+    if (rc) return rc;
+    double ls[2];
+    NFC_CUDA(h, cudaMemcpyAsync(ls, h->s_loss.p, sizeof ls, cudaMemcpyDeviceToHost, h->stream));
+    NFC_CUDA(h, cudaMemcpyAsync(grad_theta, h->s_grad.p, sizeof(float) * h->n_params, cudaMemcpyDeviceToHost, h->stream));
+    if (status) NFC_CUDA(h, cudaMemcpyAsync(status, h->s_status.p, sizeof(int) * B, cudaMemcpyDeviceToHost, h->stream));
+    NFC_CUDA(h, cudaStreamSynchronize(h->stream));
+    *loss = ls[0] / ls[1];
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,77 @@
+// nfc_host.h -- host-side state of one nfc_handle (device buffers, stream, events) shared by nfc_api.cu and nfc_adjoint.cuh
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/nfc.h"
+
+namespace nfc {
+
+enum Arch { ARCH_DEFAULT = 0, ARCH_WIDER = 1, ARCH_DEEPER = 2, ARCH_CONV2 = 3, ARCH_CONV4 = 4, ARCH_NONE = -1 };
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace nfc
+
+struct nfc_handle {
+    nfc_config cfg;
+    std::vector<float> saveat;
+    nfc::Arch arch = nfc::ARCH_NONE;
+    int device = 0, num_sms = 0;
+    int64_t n_params = 0, n_packed = 0;
+    bool weights_set = false;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool ev_fwd_valid = false, ev_adj_valid = false;
+    nfc::DevBuf<float> d_theta, d_wpack, d_saveat, d_k1, d_dt;
+    nfc::DevBuf<unsigned long long> d_counters;
+    // host-call staging
+    nfc::DevBuf<float> s_T0, s_colp, s_out, s_true, s_grad;
+    nfc::DevBuf<int> s_nacc, s_nrej, s_status;
+    nfc::DevBuf<double> s_loss;
+    // adjoint scratch
+    nfc::DevBuf<float> a_resid, a_tape, a_gacc;
+    nfc::DevBuf<int> a_tlen;
+    nfc::DevBuf<double> a_gsum;
+    int64_t last_columns = 0, last_launches = 0;
+    std::string err;
+};
+
+namespace nfc {
+
+inline std::string& create_error() { static thread_local std::string e; return e; }
+
+inline int fail(nfc_handle* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else create_error() = buf;
+    return code;
+}
+
+#define NFC_CUDA(h, call)                                                                              \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess) return nfc::fail(h, -10, "CUDA error %s at %s:%d (%s)", cudaGetErrorName(e__), __FILE__, __LINE__, cudaGetErrorString(e__)); \
+    } while (0)
+
+}  // namespace nfc

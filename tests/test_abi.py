@@ -1,0 +1,105 @@
+"""CPU tests of the boundary: the C-ABI library loads, exports every symbol include/nfc.h declares, the ctypes
+struct mirrors the C struct, and the host-side mirror of the reference API behaves (no compute calls: no GPU here)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    hdr = open(os.path.join(ROOT, "include", "nfc.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(nfc_[a-z_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol(nfc):
+    lib = nfc.load()
+    names = _declared()
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/nfc.h but not exported by libnfc_b200.so"
+    assert set(nfc.EXPORTS) == set(names)
+
+
+def test_config_struct_matches_c_layout(nfc, tmp_path):
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "nfc.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n",'
+                   'sizeof(nfc_config), offsetof(nfc_config, saveat), offsetof(nfc_config, device), sizeof(nfc_counters),'
+                   'offsetof(nfc_counters, last_kernel_ms));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    sz, off_save, off_dev, szc, off_ms = map(int, subprocess.check_output([str(exe)]).split())
+    B = nfc._binding
+    assert C.sizeof(B.NfcConfig) == sz and B.NfcConfig.saveat.offset == off_save and B.NfcConfig.device.offset == off_dev
+    assert C.sizeof(B.NfcCounters) == szc and B.NfcCounters.last_kernel_ms.offset == off_ms
+
+
+def test_no_cpu_fallback(nfc):
+    """Without a GPU nfc_create must fail loudly (never compute on the CPU)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from oracle import nde_oracle as O
+    with pytest.raises(nfc.NfcError, match="no CUDA device|CUDA"):
+        nfc.Handle(0, O.chain_spec()[1], 1, np.linspace(0, 1, 9))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "neuralfreeconvection.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "nde_oracle" not in txt, f"{f} uses the oracle"
+
+
+def test_destructure_roundtrip_and_layout(nfc):
+    from oracle import nde_oracle as O
+    for arch in ["dense-default", "dense-wider", "dense-deeper", "conv-2", "conv-4"]:
+        NN = nfc.named_chain(arch, seed=1)
+        theta, re_ = nfc.destructure(NN)
+        cw, layers = O.chain_spec(arch)
+        assert theta.size == O.n_params(cw, layers) and NN.conv_width == cw and NN.dense_spec == layers
+        conv, dense = O.unpack_theta(theta, cw, layers)
+        dl = [l for l in NN.layers if isinstance(l, nfc.Dense)]
+        for (W, b, _), l in zip(dense, dl):
+            assert np.array_equal(W, l.weight) and np.array_equal(b, l.bias)
+        NN2 = re_(theta * 2)
+        assert np.array_equal(NN2.layers[-1].weight, NN.layers[-1].weight * 2)
+        assert np.array_equal(nfc.destructure(NN2)[0], theta * 2)
+
+
+def test_parameter_vectors_follow_reference_order(nfc):
+    syn = nfc.synthetic
+    Ts, wTs = syn.reference_scalings()
+    zc = syn.cell_centres()
+    zf = -256.0 + np.arange(33) * 8.0
+    ds = nfc.ColumnDataset(T=np.zeros((32, 1153)), wT=np.zeros((33, 1153)), zc=zc, zf=zf, times=np.arange(1153) * 600.0,
+                           metadata={"temperature_flux": 5.1e-6})
+    p6 = nfc.FreeConvectionNDEParameters(ds, Ts, wTs)
+    p7 = nfc.ConvectiveAdjustmentNDEParameters(ds, Ts, wTs, 2)
+    assert p6.dtype == np.float32 and p6.shape == (6,) and p7.shape == (7,) and p7[6] == 2
+    np.testing.assert_allclose(p6, [wTs(0.0), wTs(5.1e-6), Ts.sigma, wTs.sigma, 256.0, 691200.0], rtol=1e-6)
+    np.testing.assert_array_equal(p7[:6], p6)
+
+
+def test_scaling_is_zero_mean_unit_variance(nfc):
+    x = np.random.default_rng(0).normal(3.0, 2.0, (32, 100))
+    s = nfc.ZeroMeanUnitVarianceScaling.fit(x)
+    y = s(x)
+    assert abs(y.mean()) < 1e-12 and abs(y.std(ddof=1) - 1) < 1e-12
+    np.testing.assert_allclose(s.inv(y), x, rtol=1e-12)
+
+
+def test_adam_matches_flux_update_rule(nfc):
+    opt = nfc.ADAM()
+    th = np.ones(4)
+    g = np.array([1.0, -2.0, 0.5, 0.0])
+    th1 = opt.update(th, g)
+    # first step of ADAM moves every non-zero-gradient coordinate by ~eta
+    np.testing.assert_allclose(th1, th - 1e-3 * np.sign(g) * (np.abs(g) / (np.abs(g) + 1e-8)), rtol=1e-6)
