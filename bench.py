@@ -1,0 +1,254 @@
+#!/usr/bin/env python
+"""bench.py -- NDE column-steps/sec (forward solve) on N B200s of one node.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run, one rank per GPU)
+    python bench.py --impl reference ...                     (the CPU port of the reference path on the host cores)
+
+A "step" is one pass of the hot path over one batch: the batched Tsit5 solve of BASELINE config 2
+(65,536 independent columns, varied surface flux / stratification, ConvectiveAdjustmentNDE K_CA = 2, default Chain,
+129 save points = the training `iterations = 1:9:1153`), weights random-init as the reference (Glorot x 1e-5).
+One column-step = one attempted Tsit5 step of one column (6 new RHS evaluations) -- SURVEY.md 8d.
+Columns shard across ranks with no data-path collective (weak scaling: 65,536 columns per GPU).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "nde_column_steps_per_sec_fwd"
+UNIT = "column-steps/s"
+COLUMNS_PER_GPU = 65536
+N_SAVE = 129
+FLOPS_PER_COLUMN_STEP = 6 * 2 * (32 * 128 + 128 * 128 + 128 * 31)      # 293,376 (default Chain)
+WORKLOAD = ("config2: 65536 columns/GPU, ConvectiveAdjustmentNDE K_CA=2, dense-default Chain (24735 params, Glorot x1e-5), "
+            "Tsit5 reltol 1e-4 abstol 1e-6, saveat 129 points on [0,1]")
+
+
+def make_inputs(B, seed):
+    import nfc_b200
+    syn = nfc_b200.synthetic
+    d = syn.make_columns("ocean", B=B, seed=seed, K_CA=2.0)
+    NN = nfc_b200.named_chain("dense-default", seed=0)                  # Flux glorot_uniform, zero biases
+    for p in NN.params():
+        p *= 1e-5                                                       # train_free_convection_nde.jl:158-160
+    theta, _ = nfc_b200.destructure(NN)
+    return d, NN.conv_width, NN.dense_spec, theta, syn.saveat(N_SAVE)
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+
+
+def cpu_reference_run(steps, warmup, sample_columns, nthreads):
+    """Times the CPU port (oracle/nde_oracle.c, OpenMP over columns) on a bounded sample of the same workload."""
+    from oracle import c_oracle as CO
+    d, cw, layers, theta, sv = make_inputs(sample_columns, seed=1)
+    times, nsteps = [], 0
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        r = CO.solve(d["T0"], theta, cw, layers, d["colp"], d["glob"], sv, nthreads=nthreads)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+            nsteps = int((r["naccept"] + r["nreject"]).sum())
+    return nsteps * len(times) / sum(times), 1e3 * sum(times) / len(times), nsteps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    sample = 8192
+    value, ms, nsteps = cpu_reference_run(args.steps, max(args.warmup, 1), sample, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": WORKLOAD, "note": "CPU port of the reference path; the Julia reference cannot run "
+                                            "here (no julia in the image); port omits the reference's per-call allocations"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{sample} of the 65536 columns per step, {nsteps} column-steps, OpenMP over columns"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--columns", type=int, default=COLUMNS_PER_GPU, help="columns per GPU (default: BASELINE config 2)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import nfc_b200
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback (use --impl reference for the CPU port)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    warmup = max(args.warmup, 3)
+    B = args.columns
+
+    d, cw, layers, theta, sv = make_inputs(B, seed=1 + rank)
+    h = nfc_b200.Handle(cw, layers, 1, sv, device=local_rank)
+    h.set_weights(theta)
+    T0, colp = (torch.from_numpy(d[k]).to(dev) for k in ("T0", "colp"))
+    glob = d["glob"]                                                    # four host scalars
+    Tout = torch.empty((B, N_SAVE, 32), device=dev, dtype=torch.float32)
+    na, nr, st = (torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(3))
+    tstream = torch.cuda.Stream(device=dev)         # a real (non-NULL) stream: NULL would mean "the handle's own stream"
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident throughput (`value`) ----------------
+    for _ in range(warmup):
+        h.solve_dev(T0, colp, glob, Tout, na, nr, st, stream=stream)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms = []
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        h.solve_dev(T0, colp, glob, Tout, na, nr, st, stream=stream)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    total_ms = e0.elapsed_time(e1)
+    cnt = h.counters()                                      # counters + CUDA-event time of the LAST step's kernels
+    kernel_ms = cnt["last_kernel_ms"]
+    steps_per_pass = cnt["steps_accepted"] + cnt["steps_rejected"]
+    assert int(st.abs().sum()) == 0, "solver status != 0 in the bench workload"
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    s = torch.tensor([float(steps_per_pass)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    total_ms_max, steps_all = float(t.item()), float(s.item())
+    value = steps_all * args.steps / (total_ms_max * 1e-3)
+
+    # ---------------- end to end through the host-buffer C ABI (`e2e`) ----------------
+    hT0 = torch.from_numpy(d["T0"]).pin_memory()
+    hcolp = torch.from_numpy(d["colp"]).pin_memory()
+    hglob = d["glob"]
+    hout = torch.empty((B, N_SAVE, 32), dtype=torch.float32).pin_memory()
+    h.solve(hT0.numpy(), hcolp.numpy(), hglob, out=hout.numpy())                # warm (allocates staging)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = h.solve(hT0.numpy(), hcolp.numpy(), hglob, out=hout.numpy())
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_steps = int((r["naccept"] + r["nreject"]).sum())
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    se = torch.tensor([float(e2e_steps)], device=dev, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.all_reduce(se, op=dist.ReduceOp.SUM)
+    e2e_value = float(se.item()) * args.steps / float(te.item())
+    h2d = hT0.numel() * 4 + hcolp.numel() * 4
+    d2h = hout.numel() * 4 + 3 * B * 4
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    # ---------------- roofline of the dominant kernel (solve_kernel) ----------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except OSError:
+        pass
+    fp32_peak = nfc_b200.measure_fp32_peak(local_rank, 50.0)                   # TFLOP/s, measured on this GPU now
+    achieved = FLOPS_PER_COLUMN_STEP * steps_per_pass / (kernel_ms * 1e-3) / 1e12
+    alg_bytes = B * (128 + 12 + N_SAVE * 128 + 12)
+    roofline = {"bound": "fp32_fma", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+                "traffic": None, "peak_source": "measured in this run: pure-FFMA kernel in libnfc_b200 (nominal 148x128x2x1.965GHz = 74.4)",
+                "flops_per_column_step": FLOPS_PER_COLUMN_STEP, "kernel": "solve_kernel (+ rhs_init_kernel)", "kernel_ms": kernel_ms,
+                "hbm": {"achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs", 6650.0),
+                        "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback", "algorithmic_bytes": alg_bytes}}
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        sample = 2048
+        v, ms, nst = cpu_reference_run(1, 1, sample, cores)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{sample} of the {B} columns, {nst} column-steps, {ms:.0f} ms, C port of the reference path (OpenMP over columns)"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "columns_per_gpu": B, "column_steps_per_pass_rank0": steps_per_pass,
+                       "l2": "outputs (1.08 GB/step) exceed the 126 MB L2; no explicit flush", "parallelism": f"columns sharded x{world}, no collective"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(cnt["kernel_launches"]) * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

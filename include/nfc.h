@@ -98,8 +98,9 @@ int32_t nfc_diagnose_flux(nfc_handle* h, const float* Tsol, const float* colp, f
 int32_t nfc_loss_grad(nfc_handle* h, const float* T0, const float* colp, const float* glob, const float* Ttrue,
                       double* loss, float* grad_theta, int32_t* status, int64_t B);
 
-/* device-buffer calls: same semantics, pointers are device memory on cfg.device, work is enqueued on
- * `stream` (a cudaStream_t passed as void*; NULL = the handle's own stream) and NOT synchronised. */
+/* device-buffer calls: same semantics, array pointers are device memory on cfg.device (glob stays a HOST pointer:
+ * four scalars), work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = the handle's own stream)
+ * and NOT synchronised. */
 int32_t nfc_rhs_dev(nfc_handle* h, const float* T, const float* colp, const float* glob, float* dTdt, int64_t B, void* stream);
 int32_t nfc_solve_dev(nfc_handle* h, const float* T0, const float* colp, const float* glob, float* Tout,
                       int32_t* naccept, int32_t* nreject, int32_t* status, int64_t B, void* stream);
@@ -110,6 +111,10 @@ int32_t nfc_loss_grad_dev(nfc_handle* h, const float* T0, const float* colp, con
                           double* loss_sum_dev, float* grad_dev, int32_t* status, int64_t B, int64_t n_total_columns,
                           void* stream);
 int32_t nfc_sync(nfc_handle* h);
+
+/* Roofline denominator for this path: sustained FP32 FMA throughput of `device`, measured with a
+ * pure-FFMA kernel (16 independent chains per thread, full occupancy) over ~`ms_target` milliseconds. */
+int32_t nfc_measure_fp32_peak(int32_t device, float ms_target, double* tflops);
 
 #ifdef __cplusplus
 }

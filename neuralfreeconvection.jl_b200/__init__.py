@@ -4,12 +4,12 @@ The directory name contains a dot, so it is imported through the root-level `nfc
 (`import nfc_b200`), which loads this package with importlib.
 """
 from . import _binding, api, synthetic
-from ._binding import Handle, NfcError, load, LIB_PATH, EXPORTS
+from ._binding import Handle, NfcError, load, LIB_PATH, EXPORTS, measure_fp32_peak
 from .api import (ADAM, Chain, ColumnDataset, Conv, ConvectiveAdjustmentNDE, ConvectiveAdjustmentNDEParameters, Dense,
                   FreeConvectionNDE, FreeConvectionNDEParameters, Tsit5, ZeroMeanUnitVarianceScaling, destructure,
                   named_chain, solve_nde, train_neural_differential_equation)
 
-__all__ = ["Handle", "NfcError", "load", "LIB_PATH", "EXPORTS", "ADAM", "Chain", "ColumnDataset", "Conv",
+__all__ = ["measure_fp32_peak", "Handle", "NfcError", "load", "LIB_PATH", "EXPORTS", "ADAM", "Chain", "ColumnDataset", "Conv",
            "ConvectiveAdjustmentNDE", "ConvectiveAdjustmentNDEParameters", "Dense", "FreeConvectionNDE",
            "FreeConvectionNDEParameters", "Tsit5", "ZeroMeanUnitVarianceScaling", "destructure", "named_chain",
            "solve_nde", "train_neural_differential_equation", "synthetic", "api", "_binding"]

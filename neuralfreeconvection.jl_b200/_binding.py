@@ -13,7 +13,7 @@ NFC_MAX_LAYERS = 8
 
 EXPORTS = ["nfc_create", "nfc_destroy", "nfc_last_error", "nfc_n_params", "nfc_set_weights", "nfc_set_saveat",
            "nfc_get_counters", "nfc_rhs", "nfc_solve", "nfc_diagnose_flux", "nfc_loss_grad", "nfc_rhs_dev",
-           "nfc_solve_dev", "nfc_loss_grad_dev", "nfc_sync"]
+           "nfc_solve_dev", "nfc_loss_grad_dev", "nfc_sync", "nfc_measure_fp32_peak"]
 
 
 class NfcConfig(C.Structure):
@@ -60,6 +60,7 @@ def load():
     lib.nfc_solve_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int64, vp]
     lib.nfc_loss_grad_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int64, vp]
     lib.nfc_sync.argtypes = [vp]
+    lib.nfc_measure_fp32_peak.argtypes = [C.c_int32, C.c_float, dp]
     for name in EXPORTS:
         if name not in ("nfc_last_error", "nfc_n_params"):
             getattr(lib, name).restype = C.c_int32
@@ -82,6 +83,15 @@ def _ip(a):
 
 class NfcError(RuntimeError):
     pass
+
+
+def measure_fp32_peak(device=0, ms_target=50.0):
+    """Sustained FP32 FMA TFLOP/s of `device` (pure-FFMA kernel inside libnfc_b200)."""
+    out = C.c_double(0.0)
+    rc = load().nfc_measure_fp32_peak(device, ms_target, C.byref(out))
+    if rc != 0:
+        raise NfcError(f"nfc_measure_fp32_peak failed ({rc}): {load().nfc_last_error(None).decode()}")
+    return out.value
 
 
 class Handle:
@@ -187,18 +197,26 @@ class Handle:
         return dict(loss=loss.value, grad=grad, status=st)
 
     # ---- device-buffer calls (torch tensors on this handle's device; plumbing only) ----
+    @staticmethod
+    def _glob(glob):
+        g = _f32(glob.detach().cpu().numpy() if hasattr(glob, "detach") else glob)
+        return g, g.ctypes.data
+
     def rhs_dev(self, T, colp, glob, out, stream=None):
-        self._check(self.lib.nfc_rhs_dev(self.h, T.data_ptr(), colp.data_ptr(), glob.data_ptr(), out.data_ptr(),
+        g, gp = self._glob(glob)
+        self._check(self.lib.nfc_rhs_dev(self.h, T.data_ptr(), colp.data_ptr(), gp, out.data_ptr(),
                                          T.shape[0], stream), "nfc_rhs_dev")
 
     def solve_dev(self, T0, colp, glob, Tout, naccept=None, nreject=None, status=None, stream=None):
         p = lambda t: t.data_ptr() if t is not None else None
-        self._check(self.lib.nfc_solve_dev(self.h, T0.data_ptr(), colp.data_ptr(), glob.data_ptr(), Tout.data_ptr(),
+        g, gp = self._glob(glob)
+        self._check(self.lib.nfc_solve_dev(self.h, T0.data_ptr(), colp.data_ptr(), gp, Tout.data_ptr(),
                                            p(naccept), p(nreject), p(status), T0.shape[0], stream), "nfc_solve_dev")
 
     def loss_grad_dev(self, T0, colp, glob, Ttrue, loss_sum, grad, status=None, n_total_columns=None, stream=None):
         B = T0.shape[0]
-        self._check(self.lib.nfc_loss_grad_dev(self.h, T0.data_ptr(), colp.data_ptr(), glob.data_ptr(), Ttrue.data_ptr(),
+        g, gp = self._glob(glob)
+        self._check(self.lib.nfc_loss_grad_dev(self.h, T0.data_ptr(), colp.data_ptr(), gp, Ttrue.data_ptr(),
                                                loss_sum.data_ptr(), grad.data_ptr(),
                                                status.data_ptr() if status is not None else None, B,
                                                n_total_columns if n_total_columns is not None else B, stream),

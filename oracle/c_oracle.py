@@ -84,3 +84,24 @@ def loss_grad(T0, theta, conv_width, layers, colp, glob, saveat, Ttrue, reltol=1
                                 C.c_int(nthreads))
     assert rc == 0, rc
     return dict(loss=loss.value, grad=grad, dT0=dT0, naccept=na)
+
+
+def loss_grad_continuous(T0, theta, conv_width, layers, colp, glob, saveat, Ttrue, reltol=1e-4, abstol=1e-6, fixed_dt=0.0,
+                         adj_reltol=None, adj_abstol=None, nthreads=1):
+    """Continuous (InterpolatingAdjoint-like) gradient: the algorithm the CUDA backward kernel implements."""
+    T0, theta, colp, glob, saveat, Ttrue = (_f32(a) for a in (T0, theta, colp, glob, saveat, Ttrue))
+    B, Nz = T0.shape
+    n_save = saveat.size
+    grad = np.zeros(theta.size, dtype=np.float32)
+    dT0 = np.zeros_like(T0)
+    na = np.zeros(B, dtype=np.int32)
+    nr = np.zeros(B, dtype=np.int32)
+    loss = C.c_double(0.0)
+    cw, nl, dims, acts, keep = _net(conv_width, layers)
+    rc = lib().oracle_loss_grad_continuous(C.c_int(Nz), cw, nl, dims, acts, _p(theta), _p(T0), _p(colp), _p(glob), _p(saveat),
+                                           C.c_int(n_save), C.c_float(reltol), C.c_float(abstol), C.c_float(fixed_dt),
+                                           C.c_float(adj_reltol if adj_reltol else reltol),
+                                           C.c_float(adj_abstol if adj_abstol else abstol), _p(Ttrue), C.byref(loss), _p(grad),
+                                           _p(dT0), _p(na, C.c_int32), _p(nr, C.c_int32), C.c_int64(B), C.c_int(nthreads))
+    assert rc == 0, rc
+    return dict(loss=loss.value, grad=grad, dT0=dT0, adj_naccept=na, adj_nreject=nr)

@@ -301,6 +301,214 @@ static void adjoint_column(const net_t *n, const float *th, const float *T0, con
     if (dT0) memcpy(dT0, lam, sizeof(float) * N);
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * Continuous adjoint (what DiffEqSensitivity's InterpolatingAdjoint does for src/training.jl:70, restated):
+ *   forward pass keeps a dense tape (per accepted step: t, h, u_n and the Tsit5 interpolant in power basis),
+ *   backward pass integrates  d(lam)/dt = -J_f(u(t))^T lam  from tf to 0 with its OWN adaptive Tsit5
+ *   (same PI controller), u(t) from the tape, lam jumps by dL/du(t_i) at the save times (tstops),
+ *   dL/dtheta = integral of (df/dtheta)^T lam dt accumulated with the step's quadrature weights h*b_s.
+ * Differences to the reference, on purpose (DESIGN.md "adjoint"): error control acts on lam only (the
+ * reference also puts the 24 742 parameter-gradient components into the error norm), and lam is carried
+ * un-normalised (jumps = residuals, the factor 2/N applied at the end) so that the tolerance does not
+ * depend on the batch size.  No FSAL in the backward pass (every stage contributes to the quadrature).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct { float t, h; float u[64], c1[64], c2[64], c3[64], c4[64]; } dtape_entry_t;
+typedef struct { dtape_entry_t *e; int n, cap; } dtape_t;
+
+static const float TS_C[7] = {0.f, 0.161f, 0.327f, 0.9f, 0.9800255409045097f, 1.f, 1.f};
+
+static void dtape_push(dtape_t *tp, float t, float h, const float *u, float k[7][MAXW], int N) {
+    if (tp->n == tp->cap) { tp->cap = tp->cap ? 2 * tp->cap : 256; tp->e = (dtape_entry_t *)realloc(tp->e, sizeof(dtape_entry_t) * tp->cap); }
+    dtape_entry_t *e = &tp->e[tp->n++]; e->t = t; e->h = h;
+    for (int i = 0; i < N; ++i) {
+        float c1 = 0.f, c2 = 0.f, c3 = 0.f, c4 = 0.f;
+        for (int j = 0; j < 7; ++j) { c1 += RI[j][0] * k[j][i]; c2 += RI[j][1] * k[j][i]; c3 += RI[j][2] * k[j][i]; c4 += RI[j][3] * k[j][i]; }
+        e->u[i] = u[i]; e->c1[i] = c1; e->c2[i] = c2; e->c3[i] = c3; e->c4[i] = c4;
+    }
+}
+
+/* forward pass with dense tape + residuals at the save points; returns sum of squared residuals */
+static double forward_record(const net_t *n, const float *th, const float *T0, const float *colp, float pref, const float *saveat, int n_save,
+                             float reltol, float abstol, float fixed_dt, const float *Ttrue, float *resid, dtape_t *tape, int *nacc, int *nrej,
+                             int *status, actbuf_t *ab) {
+    int N = n->Nz; float u[MAXW], k[7][MAXW], y[MAXW], unew[MAXW];
+    double sse = 0.0;
+    for (int i = 0; i < N; ++i) u[i] = T0[i];
+    float tf = saveat[n_save - 1], t = 0.f; int si = 0; *nacc = 0; *nrej = 0; *status = 0;
+    rhs_eval(n, th, u, colp, pref, k[0], ab);
+    float dt = fixed_dt > 0.f ? fixed_dt : initial_dt(n, th, u, k[0], colp, pref, reltol, abstol, tf, ab);
+    float qold = 1e-4f;
+    while (si < n_save && saveat[si] <= t) {
+        for (int i = 0; i < N; ++i) { float r = u[i] - Ttrue[(int64_t)si * N + i]; resid[(int64_t)si * N + i] = r; sse += (double)r * r; }
+        ++si;
+    }
+    for (int iter = 0; iter < 100000 && t < tf; ++iter) {
+        float h = fminf(dt, tf - t);
+        int last = (t + h) >= tf * (1.0f - 1e-6f);
+        if (last) h = tf - t;
+        for (int s = 2; s <= 7; ++s) {
+            float a[6]; a_row(s, a);
+            for (int i = 0; i < N; ++i) { float acc = 0.f; for (int j = 0; j < s - 1; ++j) acc += a[j] * k[j][i]; y[i] = u[i] + h * acc; }
+            if (s == 7) memcpy(unew, y, sizeof(float) * N);
+            rhs_eval(n, th, y, colp, pref, k[s - 1], ab);
+        }
+        float ss = 0.f;
+        for (int i = 0; i < N; ++i) {
+            float e = 0.f; for (int j = 0; j < 7; ++j) e += BT[j] * k[j][i];
+            e *= h; float sc = abstol + fmaxf(fabsf(u[i]), fabsf(unew[i])) * reltol; e /= sc; ss += e * e;
+        }
+        float EEst = sqrtf(ss / (float)N);
+        if (!isfinite(EEst)) { *status = 2; break; }
+        int accept; float dtnew;
+        if (fixed_dt > 0.f) { accept = 1; dtnew = h; }
+        else {
+            float q11 = powf(EEst, 0.14f), q = q11 / powf(qold, 0.08f);
+            q = fmaxf(0.1f, fminf(5.0f, q / 0.9f));
+            accept = EEst <= 1.0f;
+            dtnew = accept ? h / q : h / fminf(5.0f, q11 / 0.9f);
+        }
+        if (accept) {
+            float tn = last ? tf : t + h;
+            dtape_push(tape, t, h, u, k, N);
+            const dtape_entry_t *e = &tape->e[tape->n - 1];
+            while (si < n_save && saveat[si] <= tn) {
+                float th1 = fminf((saveat[si] - t) / h, 1.0f);
+                for (int i = 0; i < N; ++i) {
+                    float v = e->u[i] + h * (th1 * (e->c1[i] + th1 * (e->c2[i] + th1 * (e->c3[i] + th1 * e->c4[i]))));
+                    float r = v - Ttrue[(int64_t)si * N + i]; resid[(int64_t)si * N + i] = r; sse += (double)r * r;
+                }
+                ++si;
+            }
+            memcpy(u, unew, sizeof(float) * N); memcpy(k[0], k[6], sizeof(float) * N);
+            t = tn; if (fixed_dt <= 0.f) qold = fmaxf(EEst, 1e-4f); ++*nacc;
+        } else ++*nrej;
+        dt = dtnew;
+        if (dt < 1e-12f) { *status = 3; break; }
+    }
+    if (*status == 0 && t < tf) *status = 1;
+    return sse;
+}
+
+/* u(t) from the tape; *pn is the running interval index (moved monotonically in either direction) */
+static void tape_eval(const dtape_t *tp, int *pn, float t, float *u, int N) {
+    int n = *pn;
+    while (n > 0 && t < tp->e[n].t) --n;
+    while (n + 1 < tp->n && t > tp->e[n].t + tp->e[n].h) ++n;
+    *pn = n;
+    const dtape_entry_t *e = &tp->e[n];
+    float th = (t - e->t) / e->h; th = fminf(fmaxf(th, 0.f), 1.f);
+    for (int i = 0; i < N; ++i) u[i] = e->u[i] + e->h * (th * (e->c1[i] + th * (e->c2[i] + th * (e->c3[i] + th * e->c4[i]))));
+}
+
+/* backward pass of one column: g (double, un-normalised: caller scales by 2/N_total) */
+static void adjoint_continuous(const net_t *n, const float *th, const float *colp, float pref, const float *saveat, int n_save, const float *resid,
+                               const dtape_t *tape, float reltol, float abstol, float fixed_dt, double *g, double *gstep, float *lam_out,
+                               int *nacc, int *nrej, actbuf_t *ab) {
+    int N = n->Nz; float lam[MAXW], lams[7][MAXW], kap[7][MAXW], us[7][MAXW], lnew[MAXW], tmp[MAXW];
+    *nacc = 0; *nrej = 0;
+    for (int i = 0; i < N; ++i) lam[i] = 0.f;
+    if (tape->n == 0) { if (lam_out) memcpy(lam_out, lam, sizeof(float) * N); return; }
+    int in = tape->n - 1;
+    float t = saveat[n_save - 1];
+    float dt = fixed_dt > 0.f ? fixed_dt : tape->e[in].h;
+    float qold = 1e-4f;
+    for (int si = n_save - 1; si >= 1; --si) {
+        for (int i = 0; i < N; ++i) lam[i] += resid[(int64_t)si * N + i];
+        float tstop = saveat[si - 1];
+        for (int iter = 0; iter < 100000 && t > tstop; ++iter) {
+            float h = fminf(dt, t - tstop);
+            int last = (t - h) <= tstop + 1e-6f * saveat[n_save - 1];
+            if (last) h = t - tstop;
+            for (int p = 0; p < n->n_params; ++p) gstep[p] = 0.0;
+            for (int s = 1; s <= 7; ++s) {
+                float a[6]; if (s > 1) a_row(s, a);
+                for (int i = 0; i < N; ++i) { float acc = 0.f; for (int j = 0; j < s - 1; ++j) acc += a[j] * kap[j][i]; lams[s - 1][i] = lam[i] + h * acc; }
+                float ts = (s == 7 && last) ? tstop : t - TS_C[s - 1] * h;
+                tape_eval(tape, &in, ts, us[s - 1], N);
+                /* kappa_s = J^T lam_s ; parameter quadrature weight h*b_s folded into a scaled copy of lam_s */
+                for (int i = 0; i < N; ++i) kap[s - 1][i] = 0.f;
+                float bw = 0.f; { float b[6]; a_row(7, b); if (s <= 6) bw = h * b[s - 1]; }
+                if (bw != 0.f) {
+                    for (int i = 0; i < N; ++i) tmp[i] = bw * lams[s - 1][i];
+                    float dummy[MAXW]; for (int i = 0; i < N; ++i) dummy[i] = 0.f;
+                    rhs_vjp(n, th, us[s - 1], colp, pref, tmp, dummy, gstep, ab);
+                    for (int i = 0; i < N; ++i) kap[s - 1][i] = dummy[i] / bw;
+                } else {
+                    double *gnull = gstep; /* weight zero: evaluate J^T lam without touching the quadrature */
+                    double keep0 = 0; (void)keep0; (void)gnull;
+                    static __thread double *scratch = NULL; static __thread int64_t scratch_n = 0;
+                    if (scratch_n < n->n_params) { scratch = (double *)realloc(scratch, sizeof(double) * n->n_params); scratch_n = n->n_params; }
+                    rhs_vjp(n, th, us[s - 1], colp, pref, lams[s - 1], kap[s - 1], scratch, ab);
+                }
+            }
+            memcpy(lnew, lams[6], sizeof(float) * N);
+            float ss = 0.f;
+            for (int i = 0; i < N; ++i) {
+                float e = 0.f; for (int j = 0; j < 7; ++j) e += BT[j] * kap[j][i];
+                e *= h; float sc = abstol + fmaxf(fabsf(lam[i]), fabsf(lnew[i])) * reltol; e /= sc; ss += e * e;
+            }
+            float EEst = sqrtf(ss / (float)N);
+            int accept; float dtnew;
+            if (fixed_dt > 0.f) { accept = 1; dtnew = fixed_dt; }
+            else if (!isfinite(EEst)) { accept = 0; dtnew = h * 0.2f; }
+            else {
+                float q11 = powf(EEst, 0.14f), q = q11 / powf(qold, 0.08f);
+                q = fmaxf(0.1f, fminf(5.0f, q / 0.9f));
+                accept = EEst <= 1.0f;
+                dtnew = accept ? h / q : h / fminf(5.0f, q11 / 0.9f);
+            }
+            if (accept) {
+                for (int p = 0; p < n->n_params; ++p) g[p] += gstep[p];
+                memcpy(lam, lnew, sizeof(float) * N);
+                t = last ? tstop : t - h;
+                if (fixed_dt <= 0.f) qold = fmaxf(EEst, 1e-4f);
+                ++*nacc;
+            } else ++*nrej;
+            dt = dtnew;
+            if (dt < 1e-12f) break;
+        }
+    }
+    for (int i = 0; i < N; ++i) lam[i] += resid[i];     /* save point at t0 (only dL/dT0 sees it) */
+    if (lam_out) memcpy(lam_out, lam, sizeof(float) * N);
+}
+
+int oracle_loss_grad_continuous(int Nz, int conv_width, int n_layers, const int *dims, const int *acts, const float *theta,
+                                const float *T0, const float *colp, const float *glob, const float *saveat, int n_save,
+                                float reltol, float abstol, float fixed_dt, float adj_reltol, float adj_abstol, const float *Ttrue, double *loss,
+                                float *grad, float *dT0, int32_t *adj_naccept, int32_t *adj_nreject, int64_t B, int nthreads) {
+    net_t n; if (net_init(&n, Nz, conv_width, n_layers, dims, acts)) return -1;
+    float pref = glob[1] / glob[0] * glob[3] / glob[2];
+    if (nthreads < 1) nthreads = 1;
+    double ntot = (double)B * n_save * Nz, sse_all = 0.0;
+    double *gall = (double *)calloc((size_t)n.n_params * nthreads, sizeof(double));
+#pragma omp parallel num_threads(nthreads) reduction(+ : sse_all)
+    {
+        int tid = 0;
+#ifdef _OPENMP
+        tid = omp_get_thread_num();
+#endif
+        actbuf_t *ab = (actbuf_t *)malloc(sizeof(actbuf_t));
+        double *g = gall + (size_t)tid * n.n_params;
+        double *gstep = (double *)malloc(sizeof(double) * n.n_params);
+        float *resid = (float *)malloc(sizeof(float) * n_save * Nz);
+#pragma omp for schedule(dynamic, 1)
+        for (int64_t b = 0; b < B; ++b) {
+            int na, nr, st, ba, br; dtape_t tape = {0, 0, 0}; float lam0[MAXW];
+            sse_all += forward_record(&n, theta, T0 + b * Nz, colp + b * 3, pref, saveat, n_save, reltol, abstol, fixed_dt,
+                                      Ttrue + b * (int64_t)n_save * Nz, resid, &tape, &na, &nr, &st, ab);
+            adjoint_continuous(&n, theta, colp + b * 3, pref, saveat, n_save, resid, &tape, adj_reltol, adj_abstol, fixed_dt, g, gstep, lam0, &ba, &br, ab);
+            if (dT0) for (int i = 0; i < Nz; ++i) dT0[b * Nz + i] = (float)(2.0 / ntot * lam0[i]);
+            if (adj_naccept) adj_naccept[b] = ba; if (adj_nreject) adj_nreject[b] = br;
+            free(tape.e);
+        }
+        free(ab); free(gstep); free(resid);
+    }
+    for (int64_t p = 0; p < n.n_params; ++p) { double s = 0.0; for (int t = 0; t < nthreads; ++t) s += gall[(size_t)t * n.n_params + p]; grad[p] = (float)(2.0 / ntot * s); }
+    free(gall);
+    *loss = sse_all / ntot;
+    return 0;
+}
+
 /* ------------------------------- exported entry points ------------------------------- */
 int oracle_n_params(int Nz, int conv_width, int n_layers, const int *dims, const int *acts, int64_t *out) {
     net_t n; if (net_init(&n, Nz, conv_width, n_layers, dims, acts)) return -1; *out = n.n_params; return 0;

@@ -1,0 +1,218 @@
+"""GPU parity tests of the forward path (through the C ABI): CUDA kernels vs the CPU oracle (restatement of the
+reference, parity unpinned -- SURVEY.md 8c) on the same seeded inputs, golden vectors, and size-independent
+properties at BASELINE sizes.  Tolerances are the ones BASELINE.json's north_star states."""
+import numpy as np
+import pytest
+
+from conftest import golden, rel_l2
+from oracle import c_oracle as CO
+from oracle import nde_oracle as O
+
+pytestmark = pytest.mark.gpu
+ARCHS = ["dense-default", "dense-wider", "dense-deeper", "conv-2", "conv-4"]
+RHS_TOL = 1e-5      # per-step RHS, Float32, relative (norm-wise per column)
+TRAJ_TOL = 1e-3     # full-trajectory temperature, relative
+
+
+def _handle(nfc, arch="dense-default", nde_type=1, saveat=None, **kw):
+    cw, layers = O.chain_spec(arch)
+    return nfc.Handle(cw, layers, nde_type, nfc.synthetic.saveat(33) if saveat is None else saveat, **kw), cw, layers
+
+
+@pytest.mark.parametrize("arch", ARCHS)
+def test_rhs_golden(nfc, gpu_ok, arch):
+    g = golden(f"rhs_{arch}.npz")
+    h, cw, layers = _handle(nfc, arch)
+    h.set_weights(g["theta"])
+    f = h.rhs(g["T"], g["colp"], g["glob"])
+    assert rel_l2(f, g["dTdt"]).max() < RHS_TOL
+
+
+@pytest.mark.parametrize("arch", ARCHS)
+@pytest.mark.parametrize("B", [1, 7, 8, 9, 1000, 4099])
+def test_rhs_vs_oracle_ragged(nfc, gpu_ok, arch, B):
+    d = nfc.synthetic.make_columns("ocean", B=B, seed=B)
+    rng = np.random.default_rng(B)
+    T = (d["T0"] + 0.3 * rng.standard_normal(d["T0"].shape)).astype(np.float32)
+    colp = d["colp"].copy()
+    colp[:, 2] = rng.uniform(0, 10, B)
+    h, cw, layers = _handle(nfc, arch)
+    theta = O.glorot_theta(cw, layers, 5, 1.0)
+    theta[-31:] = 0.1
+    h.set_weights(theta)
+    f = h.rhs(T, colp, d["glob"])
+    ref = O.rhs(T, theta, cw, layers, colp, d["glob"], np.float64)
+    assert rel_l2(f, ref).max() < RHS_TOL
+    # heat-budget identity holds for the kernel too (no oracle needed)
+    pref = O.prefactor(d["glob"], np.float64)
+    np.testing.assert_allclose(f.astype(np.float64).sum(1) / 32, -pref * (colp[:, 1].astype(np.float64) - colp[:, 0]), rtol=2e-3, atol=1e-4)
+
+
+def test_rhs_free_convection_ignores_kca(nfc, gpu_ok):
+    """FreeConvectionNDE == ConvectiveAdjustmentNDE with K_CA = 0, bit for bit."""
+    d = nfc.synthetic.make_columns("ocean", B=64, seed=3)
+    cw, layers = O.chain_spec()
+    theta = O.glorot_theta(cw, layers, 1, 1.0)
+    hf, _, _ = _handle(nfc, nde_type=0)
+    hc, _, _ = _handle(nfc, nde_type=1)
+    hf.set_weights(theta)
+    hc.set_weights(theta)
+    c0 = d["colp"].copy()
+    c0[:, 2] = 0
+    assert np.array_equal(hf.rhs(d["T0"], d["colp"], d["glob"]), hc.rhs(d["T0"], c0, d["glob"]))
+
+
+@pytest.mark.parametrize("tag", ["1e-5", "0p3", "1p0"])
+@pytest.mark.parametrize("K", [0, 2])
+def test_trajectory_golden(nfc, gpu_ok, tag, K):
+    g = golden(f"traj_{tag}_K{K}.npz")
+    h, cw, layers = _handle(nfc, saveat=g["saveat"])
+    theta = O.glorot_theta(cw, layers, int(g["theta_seed"]), float(g["theta_scale"]))
+    h.set_weights(theta)
+    r = h.solve(g["T0"], g["colp"], g["glob"])
+    assert (r["status"] == 0).all()
+    assert rel_l2(r["T"], g["T_truth"]).max() < TRAJ_TOL
+    assert rel_l2(r["T"], g["T_tsit5_f64"]).max() < TRAJ_TOL
+    np.testing.assert_array_equal(r["T"][:, 0], g["T0"])
+    assert abs(int(r["naccept"].sum()) - int(g["naccept"].sum())) <= max(27, 0.05 * g["naccept"].sum())
+
+
+@pytest.mark.parametrize("arch", ARCHS)
+def test_solve_vs_c_oracle_all_chains(nfc, gpu_ok, arch):
+    """Same float32 algorithm on CPU and GPU: trajectories within tolerance, step counts close."""
+    B = 203
+    d = nfc.synthetic.make_columns("ocean", B=B, seed=11)
+    sv = nfc.synthetic.saveat(17)
+    h, cw, layers = _handle(nfc, arch, saveat=sv)
+    theta = O.glorot_theta(cw, layers, 2, 0.3)
+    h.set_weights(theta)
+    r = h.solve(d["T0"], d["colp"], d["glob"])
+    c = CO.solve(d["T0"], theta, cw, layers, d["colp"], d["glob"], sv, nthreads=8)
+    assert (r["status"] == 0).all() and (c["status"] == 0).all()
+    assert rel_l2(r["T"], c["T"]).max() < TRAJ_TOL
+    tot_g, tot_c = int((r["naccept"] + r["nreject"]).sum()), int((c["naccept"] + c["nreject"]).sum())
+    assert abs(tot_g - tot_c) <= 0.03 * tot_c
+    cnt = h.counters()
+    assert cnt["steps_accepted"] == int(r["naccept"].sum()) and cnt["steps_rejected"] == int(r["nreject"].sum())
+
+
+def test_solve_fixed_step_matches_oracle_tightly(nfc, gpu_ok):
+    """adaptive=false removes controller divergence: GPU and C oracle run the identical step grid."""
+    B = 64
+    d = nfc.synthetic.make_columns("ocean", B=B, seed=5)
+    sv = nfc.synthetic.saveat(9)
+    h, cw, layers = _handle(nfc, saveat=sv, fixed_dt=1 / 256)
+    theta = O.glorot_theta(cw, layers, 2, 1.0)
+    h.set_weights(theta)
+    r = h.solve(d["T0"], d["colp"], d["glob"])
+    c = CO.solve(d["T0"], theta, cw, layers, d["colp"], d["glob"], sv, fixed_dt=1 / 256, nthreads=8)
+    assert (r["naccept"] == 256).all() and (r["nreject"] == 0).all()
+    assert rel_l2(r["T"], c["T"]).max() < 2e-5
+
+
+def test_solve_columns_are_independent_and_order_free(nfc, gpu_ok):
+    """Slot refill / queue order must not leak between columns: permuting the batch permutes the output bit for bit."""
+    B = 777
+    d = nfc.synthetic.make_columns("ocean", B=B, seed=9)
+    sv = nfc.synthetic.saveat(5)
+    h, cw, layers = _handle(nfc, saveat=sv)
+    h.set_weights(O.glorot_theta(cw, layers, 2, 0.3))
+    r = h.solve(d["T0"], d["colp"], d["glob"])
+    perm = np.random.default_rng(0).permutation(B)
+    rp = h.solve(d["T0"][perm], d["colp"][perm], d["glob"])
+    assert np.array_equal(rp["T"], r["T"][perm])
+    assert np.array_equal(rp["naccept"], r["naccept"][perm])
+    r1 = h.solve(d["T0"][5:6], d["colp"][5:6], d["glob"])
+    assert np.array_equal(r1["T"][0], r["T"][5])
+
+
+def test_solve_edge_cases(nfc, gpu_ok):
+    d = nfc.synthetic.make_columns("training9")
+    h, cw, layers = _handle(nfc, saveat=nfc.synthetic.saveat(1153))
+    theta = O.glorot_theta(cw, layers, 0, 1e-5)
+    h.set_weights(theta)
+    r = h.solve(d["T0"][:0], d["colp"][:0], d["glob"])            # empty batch
+    assert r["T"].shape == (0, 1153, 32)
+    r = h.solve(d["T0"], d["colp"], d["glob"])                    # config 1 shape: 1153 saves, x1e-5 weights
+    assert r["T"].shape == (9, 1153, 32) and np.isfinite(r["T"]).all() and (r["status"] == 0).all()
+    c = CO.solve(d["T0"], theta, cw, layers, d["colp"], d["glob"], nfc.synthetic.saveat(1153))
+    assert rel_l2(r["T"], c["T"]).max() < TRAJ_TOL
+    with pytest.raises(nfc.NfcError, match="elements"):           # wrong theta length is a usage error
+        h.set_weights(theta[:-1])
+    # NaN input: reported per column in status[], never as a call failure (reference: retcode warnings)
+    Tbad = d["T0"].copy()
+    Tbad[3, 7] = np.nan
+    r = h.solve(Tbad, d["colp"], d["glob"])
+    assert r["status"][3] == 2 and (np.delete(r["status"], 3) == 0).all()
+
+
+def test_diagnose_flux_matches_oracle(nfc, gpu_ok):
+    d = nfc.synthetic.make_columns("training9")
+    sv = nfc.synthetic.saveat(9)
+    h, cw, layers = _handle(nfc, saveat=sv)
+    theta = O.glorot_theta(cw, layers, 0, 1.0)
+    h.set_weights(theta)
+    r = h.solve(d["T0"], d["colp"], d["glob"])
+    wT = h.diagnose_flux(r["T"], d["colp"])
+    ref = np.stack([O.total_flux(r["T"][:, n], theta, cw, layers, d["colp"], np.float64) for n in range(9)], axis=1)
+    assert rel_l2(wT, ref).max() < RHS_TOL
+
+
+def test_reference_api_mirror_single_column(nfc, gpu_ok):
+    """solve_nde(nde, NN, T0, alg, nde_params) |> Array is Nz x n_save, and the ds-method un-scales (src/solve.jl)."""
+    syn = nfc.synthetic
+    Ts, wTs = syn.reference_scalings()
+    d = syn.make_columns("single")
+    zf = -256.0 + np.arange(33) * 8.0
+    Tds = np.repeat(Ts.inv(d["T0"][0])[:, None], 1153, axis=1)
+    ds = nfc.ColumnDataset(T=Tds, wT=np.zeros((33, 1153)), zc=syn.cell_centres(), zf=zf, times=np.arange(1153) * 600.0,
+                           metadata={"temperature_flux": float(syn.heat_flux(1e-8))})
+    NN = nfc.named_chain("dense-default", seed=0)
+    for l in NN.layers:
+        l.weight *= 0.3
+    p = nfc.ConvectiveAdjustmentNDEParameters(ds, Ts, wTs, 2)
+    nde = nfc.ConvectiveAdjustmentNDE(NN, ds, iterations=range(1, 1154, 9))
+    assert nde.saveat.size == 129 and abs(float(nde.tspan[1]) - 1.0) < 1e-7
+    T = nfc.solve_nde(nde, NN, Ts(ds.T[:, 0]), nfc.Tsit5(), p)
+    assert T.shape == (32, 129)
+    theta, _ = nfc.destructure(NN)
+    cw, layers = O.chain_spec()
+    colp = np.array([[p[0], p[1], p[6]]], dtype=np.float32)
+    c = CO.solve(Ts(ds.T[:, 0])[None], theta, cw, layers, colp, p[2:6], nde.saveat)
+    assert rel_l2(T.T[None], c["T"]).max() < TRAJ_TOL
+    with pytest.raises(ValueError):                                   # 6-vector into the CA type
+        nfc.solve_nde(nde, NN, Ts(ds.T[:, 0]), nfc.Tsit5(), p[:6])
+    out = nfc.solve_nde(ds, NN, nfc.ConvectiveAdjustmentNDE, p, nfc.Tsit5(), Ts, wTs)
+    assert out["T"].shape == (32, 1153) and out["wT"].shape == (33, 1153)
+    np.testing.assert_allclose(out["T"][:, 0], ds.T[:, 0], rtol=1e-5)
+
+
+def test_full_size_properties_65536(nfc, gpu_ok):
+    """BASELINE config 2 (65,536 columns, 129 saves): heat budget of every column at every save time
+    (integral of T changes by -pref (top-bottom) t), first save == T0, all statuses ok."""
+    import torch
+    B = 65536
+    d = nfc.synthetic.make_columns("ocean", B=B, seed=1)
+    sv = nfc.synthetic.saveat(129)
+    h, cw, layers = _handle(nfc, saveat=sv)
+    h.set_weights(O.glorot_theta(cw, layers, 0, 0.3))
+    dev = torch.device("cuda:0")
+    T0, colp = (torch.from_numpy(d[k]).to(dev) for k in ("T0", "colp"))
+    glob = d["glob"]
+    Tout = torch.empty((B, 129, 32), device=dev)
+    na, nr, st = (torch.zeros(B, dtype=torch.int32, device=dev) for _ in range(3))
+    h.solve_dev(T0, colp, glob, Tout, na, nr, st)
+    h.sync()
+    assert int(st.abs().sum()) == 0
+    assert torch.equal(Tout[:, 0], T0)
+    pref = float(O.prefactor(d["glob"], np.float64))
+    mean_T = Tout.double().mean(dim=2)                                          # [B, 129]
+    want = mean_T[:, :1] - pref * (colp[:, 1:2] - colp[:, 0:1]).double() * torch.from_numpy(sv).to(dev).double()[None]
+    err = (mean_T - want).abs().max().item()
+    assert err < 2e-4, err
+    cnt = h.counters()
+    assert cnt["steps_accepted"] == int(na.sum()) and cnt["columns"] == B
+    # a random sample of columns against the C oracle
+    idx = np.random.default_rng(0).choice(B, 64, replace=False)
+    c = CO.solve(d["T0"][idx], O.glorot_theta(cw, layers, 0, 0.3), cw, layers, d["colp"][idx], d["glob"], sv, nthreads=8)
+    assert rel_l2(Tout[torch.from_numpy(idx).to(dev)].cpu().numpy(), c["T"]).max() < TRAJ_TOL
