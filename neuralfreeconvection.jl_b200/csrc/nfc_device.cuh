@@ -89,21 +89,26 @@ struct Net {
     static constexpr int IN0 = NZ - (CONVW_ ? CONVW_ - 1 : 0);
     static constexpr int NOUT = NZ - 1;
     static constexpr int NPL = H_ / 32;                 // hidden neurons per lane
-    // packed (shared-memory) layout, in floats
+    // packed (shared-memory) layout, in floats.  Rows are padded by 4 floats (RSW = H+4, RSL = 36): with a
+    // row stride == 4 (mod 32) banks, both the forward access (lane -> 4 consecutive floats of ONE row) and the
+    // transposed access of the adjoint (lane -> its OWN row, same 4 columns) are conflict-free LDS.128.
+    static constexpr int RSW = H_ + 4;                  // row stride of [*][H] matrices
+    static constexpr int RSL = 36;                      // row stride of the last layer [H][32]
     static constexpr int P_CONV = 0;                    // CONVW weights + bias, padded to 8
-    static constexpr int P_W0 = 8;                      // [IN0][H] lane-permuted
-    static constexpr int P_B0 = P_W0 + IN0 * H_;        // [H] lane-permuted
-    static constexpr int P_HID = P_B0 + H_;             // (NHID-1) x { [H][H], [H] }
-    static constexpr int HID_STRIDE = H_ * H_ + H_;
-    static constexpr int P_WL = P_HID + (NHID_ - 1) * HID_STRIDE;   // [H][32] (column 31 zero)
-    static constexpr int P_BL = P_WL + H_ * 32;         // [32]
+    static constexpr int P_W0 = 8;                      // [IN0][RSW] lane-permuted columns
+    static constexpr int P_B0 = P_W0 + IN0 * RSW;       // [H] lane-permuted
+    static constexpr int P_HID = P_B0 + H_;             // (NHID-1) x { [H][RSW], [H] }
+    static constexpr int HIDP_STRIDE = H_ * RSW + H_;
+    static constexpr int P_WL = P_HID + (NHID_ - 1) * HIDP_STRIDE;   // [H][RSL] (column 31.. zero)
+    static constexpr int P_BL = P_WL + H_ * RSL;        // [32]
     static constexpr int P_TOTAL = P_BL + 32;           // multiple of 4 floats (16 B) by construction
+    static constexpr int HID_STRIDE = H_ * H_ + H_;     // theta stride of one hidden layer
     // Flux.destructure layout, in floats
     static constexpr int T_CONV = 0;
     static constexpr int T_W0 = CONVW_ ? CONVW_ + 1 : 0;
     static constexpr int T_B0 = T_W0 + IN0 * H_;
     static constexpr int T_HID = T_B0 + H_;
-    static constexpr int T_WL = T_HID + (NHID_ - 1) * HID_STRIDE;
+    static constexpr int T_WL = T_HID + (NHID_ - 1) * (H_ * H_ + H_);
     static constexpr int T_BL = T_WL + H_ * NOUT;
     static constexpr int T_TOTAL = T_BL + NOUT;
     // per-warp activation scratch, in floats: X[32][8] | A[H][8] | B[H][8] | Y[8][33]
@@ -114,7 +119,7 @@ struct Net {
     static constexpr int S_TOTAL = ((S_Y + CPW * YS + 3) / 4) * 4;
 };
 
-// packed index -> theta index (or -1 for zero padding); used by the pack kernel and by the gradient unpack
+// packed index -> theta index (or -1 for zero padding); used by the pack kernel
 template <class N>
 __host__ __device__ inline int packed_to_theta(int p) {
     if (p < N::P_W0) {
@@ -122,18 +127,25 @@ __host__ __device__ inline int packed_to_theta(int p) {
         return N::T_CONV + p;                                  // w[0..CONVW-1], bias at CONVW
     }
     if (p < N::P_B0) {                                          // W0[k][NPL*lane + j] = W[k][lane + 32 j]
-        int q = p - N::P_W0, k = q / N::H, r = q % N::H, lane = r / N::NPL, j = r % N::NPL;
+        int q = p - N::P_W0, k = q / N::RSW, r = q % N::RSW;
+        if (r >= N::H) return -1;
+        int lane = r / N::NPL, j = r % N::NPL;
         return N::T_W0 + k * N::H + lane + 32 * j;
     }
     if (p < N::P_HID) { int r = p - N::P_B0, lane = r / N::NPL, j = r % N::NPL; return N::T_B0 + lane + 32 * j; }
     if (p < N::P_WL) {
-        int q = p - N::P_HID, l = q / N::HID_STRIDE, r0 = q % N::HID_STRIDE;
+        int q = p - N::P_HID, l = q / N::HIDP_STRIDE, r0 = q % N::HIDP_STRIDE;
         int tbase = N::T_HID + l * N::HID_STRIDE;
-        if (r0 < N::H * N::H) { int k = r0 / N::H, r = r0 % N::H, lane = r / N::NPL, j = r % N::NPL; return tbase + k * N::H + lane + 32 * j; }
-        int r = r0 - N::H * N::H, lane = r / N::NPL, j = r % N::NPL;
+        if (r0 < N::H * N::RSW) {
+            int k = r0 / N::RSW, r = r0 % N::RSW;
+            if (r >= N::H) return -1;
+            int lane = r / N::NPL, j = r % N::NPL;
+            return tbase + k * N::H + lane + 32 * j;
+        }
+        int r = r0 - N::H * N::RSW, lane = r / N::NPL, j = r % N::NPL;
         return tbase + N::H * N::H + lane + 32 * j;
     }
-    if (p < N::P_BL) { int q = p - N::P_WL, k = q / 32, n = q % 32; return n < N::NOUT ? N::T_WL + k * N::NOUT + n : -1; }
+    if (p < N::P_BL) { int q = p - N::P_WL, k = q / N::RSL, n = q % N::RSL; return n < N::NOUT ? N::T_WL + k * N::NOUT + n : -1; }
     int n = p - N::P_BL;
     return n < N::NOUT ? N::T_BL + n : -1;
 }
@@ -180,7 +192,7 @@ __device__ __forceinline__ void stage_weights(float* sW, const float* __restrict
 
 // ---- Dense layers on a warp tile ----------------------------------------------------------------------
 // out[n][c] = act(b[n] + sum_k W[k][n] in[k][c]),  in: [K][8], out: [32*NPL][8] (row = neuron), weights lane-permuted.
-template <int K, int NPL, bool RELU>
+template <int K, int NPL, int RS, bool RELU>
 __device__ __forceinline__ void dense_hidden(const float* __restrict__ W, const float* __restrict__ Bv, const float* __restrict__ in,
                                              float* __restrict__ out, int lane) {
     static_assert(NPL == 4 || NPL == 8, "hidden width must be 128 or 256");
@@ -199,7 +211,7 @@ __device__ __forceinline__ void dense_hidden(const float* __restrict__ W, const 
         const float x[CPW] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
 #pragma unroll
         for (int j4 = 0; j4 < NPL / 4; ++j4) {
-            const float4 w4 = *reinterpret_cast<const float4*>(wp + k * (32 * NPL) + 4 * j4);
+            const float4 w4 = *reinterpret_cast<const float4*>(wp + k * RS + 4 * j4);
             const float w[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -224,7 +236,7 @@ __device__ __forceinline__ void dense_hidden(const float* __restrict__ W, const 
 }
 
 // last layer Dense(H, Nz-1) (identity): lane == output neuron (lane 31 is zero padding); result -> Y[c][lane]
-template <int K>
+template <int K, int RS>
 __device__ __forceinline__ void dense_last(const float* __restrict__ W, const float* __restrict__ Bv, const float* __restrict__ in,
                                            float* __restrict__ Y, int lane) {
     float acc[CPW];
@@ -233,7 +245,7 @@ __device__ __forceinline__ void dense_last(const float* __restrict__ W, const fl
     for (int c = 0; c < CPW; ++c) acc[c] = b;
 #pragma unroll 8
     for (int k = 0; k < K; ++k) {
-        const float w = W[k * 32 + lane];
+        const float w = W[k * RS + lane];
         const float4 x0 = *reinterpret_cast<const float4*>(in + k * CPW);
         const float4 x1 = *reinterpret_cast<const float4*>(in + k * CPW + 4);
         acc[0] = fmaf(w, x0.x, acc[0]); acc[1] = fmaf(w, x0.y, acc[1]); acc[2] = fmaf(w, x0.z, acc[2]); acc[3] = fmaf(w, x0.w, acc[3]);
@@ -271,17 +283,17 @@ __device__ __forceinline__ void nn_forward_tile(const float* __restrict__ sW, fl
         *reinterpret_cast<float4*>(sX + lane * CPW + 4) = make_float4(x[4], x[5], x[6], x[7]);
     }
     __syncwarp();
-    dense_hidden<N::IN0, N::NPL, true>(sW + N::P_W0, sW + N::P_B0, sX, sA, lane);
+    dense_hidden<N::IN0, N::NPL, N::RSW, true>(sW + N::P_W0, sW + N::P_B0, sX, sA, lane);
     __syncwarp();
     float* in = sA;
     float* out = sB;
 #pragma unroll
     for (int l = 0; l < N::NHID - 1; ++l) {
-        dense_hidden<N::H, N::NPL, true>(sW + N::P_HID + l * N::HID_STRIDE, sW + N::P_HID + l * N::HID_STRIDE + N::H * N::H, in, out, lane);
+        dense_hidden<N::H, N::NPL, N::RSW, true>(sW + N::P_HID + l * N::HIDP_STRIDE, sW + N::P_HID + l * N::HIDP_STRIDE + N::H * N::RSW, in, out, lane);
         __syncwarp();
         float* t = in; in = out; out = t;
     }
-    dense_last<N::H>(sW + N::P_WL, sW + N::P_BL, in, sY, lane);
+    dense_last<N::H, N::RSL>(sW + N::P_WL, sW + N::P_BL, in, sY, lane);
     __syncwarp();
 }
 
