@@ -1,17 +1,579 @@
-// nfc_adjoint.cuh -- loss + continuous-adjoint gradient (src/training.jl:45-48,70).  [stub: filled in next]
+// nfc_adjoint.cuh -- loss + gradient (src/training.jl:45-48,70).
+//
+// The reference differentiates solve(...) with DiffEqSensitivity's continuous adjoint (InterpolatingAdjoint +
+// ZygoteVJP, src/solve.jl:5): a second ODE, d(lam)/dt = -J_f(u(t))^T lam, is integrated backwards with the same
+// adaptive algorithm, u(t) comes from the forward solution's dense output, lam jumps by dL/du(t_i) at the save
+// times and dL/dtheta is the time integral of (df/dtheta)^T lam.  The same algorithm runs here, batched:
+//
+//   forward  solve_kernel<RECORD>: residuals at the save points + a dense tape (u_n and the Tsit5 interpolant in
+//            power basis per accepted step);
+//   backward adjoint_kernel: one CTA per SM, 8 warps x 8 column slots, per-slot adaptive Tsit5 on lam with tstops at
+//            the save times, slots refilled from a queue.  Per stage every warp recomputes the hidden activations
+//            at u(t_s) and back-propagates lam_s through the Chain (warp-private, transposed products read the SAME
+//            padded weight copy as the forward pass); the weight-gradient contraction  dW_l += delta_l a_{l-1}^T
+//            runs CTA-wide over all 64 columns (quadrature weight h*b_s folded into delta), so every accumulator
+//            is touched once per 64 outer products.  Accumulators are per-CTA, plain (atomic-free) read-modify-write
+//            in L2; a last kernel reduces them over CTAs in double.
+//            A rejected backward step is undone by replaying it with weight -h*b_s ("cancel" pass), so the
+//            quadrature never needs per-column gradient storage.
+//
+// Deliberate differences to DiffEqSensitivity (DESIGN.md "Adjoint"): error control acts on lam only; lam is carried
+// un-normalised (jumps = residuals, 2/N applied at the end) so tolerances do not depend on the batch size; no FSAL
+// in the backward pass.  oracle/nde_oracle.c:adjoint_continuous is the CPU twin of exactly this algorithm.
 #pragma once
 #include "nfc_forward.cuh"
 #include "nfc_host.h"
 #include "nfc_launch.h"
 
+template <class N>
+int nfc_launch_record(nfc_handle* h, nfc::SolveParams& P, cudaStream_t st, bool first_chunk);
+
 namespace nfc {
 
+constexpr int ADJ_NW = 8;   // the CTA-wide dW contraction maps 256 threads onto a 16 x 16 grid of register tiles
+
+struct AdjParams {
+    const float* wpack;
+    const float* colp;          // [B][3]
+    const float* saveat;        // [n_save]
+    const float* resid;         // [B][n_save][32]
+    const float* tape;          // [B][tape_cap][TAPE_STRIDE]
+    const int* tape_len;        // [B]
+    int* status;                // [B] forward status in, adjoint failures merged in
+    float* gacc;                // [gridDim.x][n_params]  per-CTA accumulators, Flux theta layout
+    unsigned long long* counters;
+    long long B;
+    int n_save, tape_cap, max_iters, use_kca, n_params;
+    float pref, tf, reltol, abstol, fixed_dt;
+};
+
 template <class N>
-int adjoint_setup(nfc_handle* h) { (void)h; return 0; }
+struct AdjScratch {     // per-warp shared-memory scratch of the backward pass, in floats; every buffer is [rows][8 columns]
+    static constexpr int ACT0 = 0;                                  // a_0 = u(t_s)                 [32][8]
+    static constexpr int ACT1 = NZ * CPW;                           // a_1 .. a_NHID                [H][8] each
+    static constexpr int DL = ACT1 + N::NHID * N::H * CPW;          // delta of the last layer / u-bar staging [32][8]
+    static constexpr int TMP = DL + NZ * CPW;                       // delta ping-pong buffer       [H][8]
+    static constexpr int TOTAL = TMP + N::H * CPW;
+    static __device__ __forceinline__ int act(int l) { return l == 0 ? ACT0 : ACT1 + (l - 1) * N::H * CPW; }
+};
+
+struct AdjSlots {
+    int col[CPW];
+    float t[CPW], dt[CPW], h[CPW], qold[CPW], tstop[CPW], bot[CPW], top[CPW], kca[CPW], dt_retry[CPW];
+    int si[CPW], nacc[CPW], nrej[CPW], flag[CPW], mode[CPW], ipos[CPW], tlen[CPW], status[CPW];
+};
+enum : int { AFL_ACCEPT = 1, AFL_LAST = 2, AFL_DONE = 4, AFL_JUMP = 8 };
+
+__constant__ float c_adj_a[7][6] = {
+    {0.f, 0.f, 0.f, 0.f, 0.f, 0.f},
+    {NFC_A21, 0.f, 0.f, 0.f, 0.f, 0.f},
+    {NFC_A31, NFC_A32, 0.f, 0.f, 0.f, 0.f},
+    {NFC_A41, NFC_A42, NFC_A43, 0.f, 0.f, 0.f},
+    {NFC_A51, NFC_A52, NFC_A53, NFC_A54, 0.f, 0.f},
+    {NFC_A61, NFC_A62, NFC_A63, NFC_A64, NFC_A65, 0.f},
+    {NFC_B1, NFC_B2, NFC_B3, NFC_B4, NFC_B5, NFC_B6}};
+__constant__ float c_adj_c[7] = {0.f, 0.161f, 0.327f, 0.9f, 0.9800255409045097f, 1.f, 1.f};
+__constant__ float c_adj_b[7] = {NFC_B1, NFC_B2, NFC_B3, NFC_B4, NFC_B5, NFC_B6, 0.f};
+
+// ---- transposed products on a warp tile: out[k][c] = mask(k,c) * sum_n W[k][pos(n)] din[n][c], lane owns rows k = lane + 32 i ----
+// hidden layer: W is [K][RS] with columns in packed order (position NPL*fl + j  <->  neuron fl + 32 j)
+template <int KR, int NPL, int RS, bool MASK>
+__device__ __forceinline__ void dense_T_hidden(const float* __restrict__ W, const float* __restrict__ din, const float* __restrict__ act,
+                                               float* __restrict__ out, int lane, int krows) {
+    float acc[KR][CPW];
+#pragma unroll
+    for (int i = 0; i < KR; ++i)
+#pragma unroll
+        for (int c = 0; c < CPW; ++c) acc[i][c] = 0.f;
+    const bool rowok = lane < krows;           // only relevant for KR == 1 (first layer: krows = IN0 <= 32)
+#pragma unroll 2
+    for (int fl = 0; fl < 32; ++fl) {
+#pragma unroll
+        for (int j4 = 0; j4 < NPL / 4; ++j4) {
+            float dv[4][CPW];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float* r = din + (fl + 32 * (4 * j4 + j)) * CPW;
+                const float4 d0 = *reinterpret_cast<const float4*>(r), d1 = *reinterpret_cast<const float4*>(r + 4);
+                dv[j][0] = d0.x; dv[j][1] = d0.y; dv[j][2] = d0.z; dv[j][3] = d0.w; dv[j][4] = d1.x; dv[j][5] = d1.y; dv[j][6] = d1.z; dv[j][7] = d1.w;
+            }
+#pragma unroll
+            for (int i = 0; i < KR; ++i) {
+                float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (KR > 1 || rowok) w = *reinterpret_cast<const float4*>(W + (lane + 32 * i) * RS + NPL * fl + 4 * j4);
+#pragma unroll
+                for (int c = 0; c < CPW; ++c) {
+                    float a = acc[i][c];
+                    a = fmaf(w.x, dv[0][c], a); a = fmaf(w.y, dv[1][c], a); a = fmaf(w.z, dv[2][c], a); a = fmaf(w.w, dv[3][c], a);
+                    acc[i][c] = a;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < KR; ++i) {
+        const int k = lane + 32 * i;
+        float o[CPW];
+        if (MASK) {
+            const float4 a0 = *reinterpret_cast<const float4*>(act + k * CPW), a1 = *reinterpret_cast<const float4*>(act + k * CPW + 4);
+            o[0] = a0.x > 0.f ? acc[i][0] : 0.f; o[1] = a0.y > 0.f ? acc[i][1] : 0.f; o[2] = a0.z > 0.f ? acc[i][2] : 0.f; o[3] = a0.w > 0.f ? acc[i][3] : 0.f;
+            o[4] = a1.x > 0.f ? acc[i][4] : 0.f; o[5] = a1.y > 0.f ? acc[i][5] : 0.f; o[6] = a1.z > 0.f ? acc[i][6] : 0.f; o[7] = a1.w > 0.f ? acc[i][7] : 0.f;
+        } else {
+#pragma unroll
+            for (int c = 0; c < CPW; ++c) o[c] = acc[i][c];
+        }
+        *reinterpret_cast<float4*>(out + k * CPW) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(out + k * CPW + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    }
+}
+
+// last layer: W is [H][RSL], column n == neuron n (n < 31; columns 31..35 are zero)
+template <int KR, int RS>
+__device__ __forceinline__ void dense_T_last(const float* __restrict__ W, const float* __restrict__ din, const float* __restrict__ act,
+                                             float* __restrict__ out, int lane) {
+    float acc[KR][CPW];
+#pragma unroll
+    for (int i = 0; i < KR; ++i)
+#pragma unroll
+        for (int c = 0; c < CPW; ++c) acc[i][c] = 0.f;
+#pragma unroll 2
+    for (int n4 = 0; n4 < 8; ++n4) {
+        float dv[4][CPW];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float* r = din + (4 * n4 + j) * CPW;
+            const float4 d0 = *reinterpret_cast<const float4*>(r), d1 = *reinterpret_cast<const float4*>(r + 4);
+            dv[j][0] = d0.x; dv[j][1] = d0.y; dv[j][2] = d0.z; dv[j][3] = d0.w; dv[j][4] = d1.x; dv[j][5] = d1.y; dv[j][6] = d1.z; dv[j][7] = d1.w;
+        }
+#pragma unroll
+        for (int i = 0; i < KR; ++i) {
+            const float4 w = *reinterpret_cast<const float4*>(W + (lane + 32 * i) * RS + 4 * n4);
+#pragma unroll
+            for (int c = 0; c < CPW; ++c) {
+                float a = acc[i][c];
+                a = fmaf(w.x, dv[0][c], a); a = fmaf(w.y, dv[1][c], a); a = fmaf(w.z, dv[2][c], a); a = fmaf(w.w, dv[3][c], a);
+                acc[i][c] = a;
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < KR; ++i) {
+        const int k = lane + 32 * i;
+        const float4 a0 = *reinterpret_cast<const float4*>(act + k * CPW), a1 = *reinterpret_cast<const float4*>(act + k * CPW + 4);
+        *reinterpret_cast<float4*>(out + k * CPW) =
+            make_float4(a0.x > 0.f ? acc[i][0] : 0.f, a0.y > 0.f ? acc[i][1] : 0.f, a0.z > 0.f ? acc[i][2] : 0.f, a0.w > 0.f ? acc[i][3] : 0.f);
+        *reinterpret_cast<float4*>(out + k * CPW + 4) =
+            make_float4(a1.x > 0.f ? acc[i][4] : 0.f, a1.y > 0.f ? acc[i][5] : 0.f, a1.z > 0.f ? acc[i][6] : 0.f, a1.w > 0.f ? acc[i][7] : 0.f);
+    }
+}
+
+// ---- CTA-wide weight-gradient contraction: gW[k][n] += sum over the CTA's 64 columns of A[k][c] * D[n][c] -----------------
+// A / D are the per-warp [rows][8] buffers (warp w's copy at +w*WSTRIDE).  256 threads = 16 x 16 register tiles, rows interleaved
+// (k = TK + 16 i, n = TN + 16 j) so that the LDS.128 of a warp hit distinct banks.  gW is this CTA's private accumulator
+// (row-major [KROWS][NCOLS] == Flux's column-major out x in), updated by plain read-modify-write.
+template <int KROWS, int NCOLS, int WSTRIDE>
+__device__ __forceinline__ void dw_gemm(const float* __restrict__ A0, const float* __restrict__ D0, float* __restrict__ gW, float* __restrict__ gb) {
+    constexpr int KI = (KROWS + 15) / 16, NJ = (NCOLS + 15) / 16;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int TK = (wid >> 1) * 4 + (lane >> 3), TN = (wid & 1) * 8 + (lane & 7);
+    const int hsel = ((lane & 7) >> 2) * 4;       // lanes with tn >= 4 read the second half-row first (bank spreading)
+    float acc[KI][NJ], bacc[NJ];
+#pragma unroll
+    for (int i = 0; i < KI; ++i)
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) acc[i][j] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) bacc[j] = 0.f;
+#pragma unroll 1
+    for (int w = 0; w < ADJ_NW; ++w) {
+        const float* A = A0 + w * WSTRIDE;
+        const float* D = D0 + w * WSTRIDE;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int hd = (half * 4) ^ hsel;        // which 4 of the 8 columns this pass covers (same for both operands)
+            float4 a[KI], d[NJ];
+#pragma unroll
+            for (int i = 0; i < KI; ++i) a[i] = *reinterpret_cast<const float4*>(A + (TK + 16 * i) * CPW + hd);
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) d[j] = *reinterpret_cast<const float4*>(D + (TN + 16 * j) * CPW + hd);
+#pragma unroll
+            for (int i = 0; i < KI; ++i)
+#pragma unroll
+                for (int j = 0; j < NJ; ++j) {
+                    float s = acc[i][j];
+                    s = fmaf(a[i].x, d[j].x, s); s = fmaf(a[i].y, d[j].y, s); s = fmaf(a[i].z, d[j].z, s); s = fmaf(a[i].w, d[j].w, s);
+                    acc[i][j] = s;
+                }
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) bacc[j] += (d[j].x + d[j].y) + (d[j].z + d[j].w);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < KI; ++i) {
+        const int k = TK + 16 * i;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int n = TN + 16 * j;
+            if (k < KROWS && n < NCOLS) { float* p = gW + k * NCOLS + n; *p = *p + acc[i][j]; }
+        }
+    }
+    if (TK == 0) {
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const int n = TN + 16 * j;
+            if (n < NCOLS) gb[n] += bacc[j];
+        }
+    }
+}
+
+template <class N>
+__device__ __forceinline__ bool adj_fill_slot(const AdjParams& P, AdjSlots* sl, int c, float& lam, int lane) {
+    // returns false when the queue is exhausted (slot left inactive)
+    while (true) {
+        long long next = 0;
+        if (lane == 0) next = (long long)atomicAdd(&P.counters[CTR_ADJ_QUEUE], 1ULL);
+        next = __shfl_sync(FULL, next, 0);
+        if (next >= P.B) {
+            lam = 0.f;
+            if (lane == 0) { sl->col[c] = -1; sl->h[c] = 0.f; sl->t[c] = 0.f; sl->tstop[c] = 0.f; sl->kca[c] = 0.f; sl->flag[c] = 0; sl->mode[c] = 0; sl->tlen[c] = 0; sl->ipos[c] = 0; }
+            return false;
+        }
+        const int len = P.tape_len[next];
+        const int st = P.status ? P.status[next] : 0;
+        if (st != ST_OK || len <= 0 || P.n_save < 2) continue;      // nothing to differentiate (or forward failed: reported in status[])
+        lam = P.resid[(next * P.n_save + (P.n_save - 1)) * NZ + lane];      // jump at tf
+        if (lane == 0) {
+            const float* last = P.tape + ((long long)next * P.tape_cap + (len - 1)) * TAPE_STRIDE;
+            sl->col[c] = (int)next; sl->t[c] = P.tf; sl->tstop[c] = P.saveat[P.n_save - 2]; sl->si[c] = P.n_save - 2;
+            sl->dt[c] = P.fixed_dt > 0.f ? P.fixed_dt : last[TAPE_H]; sl->qold[c] = 1e-4f; sl->nacc[c] = 0; sl->nrej[c] = 0; sl->flag[c] = 0;
+            sl->mode[c] = 0; sl->ipos[c] = len - 1; sl->tlen[c] = len; sl->status[c] = ST_OK; sl->dt_retry[c] = 0.f;
+            sl->bot[c] = P.colp[next * 3 + 0]; sl->top[c] = P.colp[next * 3 + 1]; sl->kca[c] = P.use_kca ? P.colp[next * 3 + 2] : 0.f;
+        }
+        return true;
+    }
+}
+
+template <class N, bool WS>
+__global__ void __launch_bounds__(ADJ_NW * 32, 1) adjoint_kernel(const AdjParams P) {
+    using S = AdjScratch<N>;
+    extern __shared__ __align__(16) float smem[];
+    __shared__ uint64_t bar;
+    __shared__ AdjSlots slots[ADJ_NW];
+    const float* sW = WS ? smem : P.wpack;
+    if (WS) stage_weights(smem, P.wpack, N::P_TOTAL, &bar);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* scratch0 = smem + (WS ? N::P_TOTAL : 0);
+    float* ws = scratch0 + warp * S::TOTAL;
+    AdjSlots* sl = &slots[warp];
+    float* g = P.gacc + (size_t)blockIdx.x * P.n_params;
+    const float c0 = P.pref * (float)NZ;
+
+    float lam[CPW], kap[7][CPW], ls[CPW];
+#pragma unroll
+    for (int c = 0; c < CPW; ++c) {
+#pragma unroll
+        for (int j = 0; j < 7; ++j) kap[j][c] = 0.f;
+        ls[c] = 0.f;
+        adj_fill_slot<N>(P, sl, c, lam[c], lane);
+    }
+    __syncwarp();
+
+    while (true) {
+        bool any = false;
+#pragma unroll
+        for (int c = 0; c < CPW; ++c) any |= sl->col[c] >= 0;
+        if (!__syncthreads_or(any ? 1 : 0)) break;
+        if (lane < CPW && sl->col[lane] >= 0) {
+            if (sl->mode[lane] == 0) {
+                const float t = sl->t[lane], ts = sl->tstop[lane];
+                float h = fminf(sl->dt[lane], t - ts);
+                int fl = 0;
+                if (t - h <= ts + 1e-6f * P.tf) { h = t - ts; fl = AFL_LAST; }
+                sl->h[lane] = h; sl->flag[lane] = fl;
+            } else {
+                sl->flag[lane] &= AFL_LAST;          // cancel pass replays the rejected step (same h, same tstop logic)
+            }
+        }
+        __syncwarp();
+
+        // ------------------------------------------------ 7 stages ------------------------------------------------
+#pragma unroll 1
+        for (int s = 0; s < 7; ++s) {
+            const float a0 = c_adj_a[s][0], a1 = c_adj_a[s][1], a2 = c_adj_a[s][2], a3 = c_adj_a[s][3], a4 = c_adj_a[s][4], a5 = c_adj_a[s][5];
+            const float cs = c_adj_c[s], bs = c_adj_b[s];
+            float us[CPW], uca[CPW], winv[CPW], fb[CPW];
+#pragma unroll
+            for (int c = 0; c < CPW; ++c) {
+                float acc = a0 * kap[0][c];
+                acc = fmaf(a1, kap[1][c], acc); acc = fmaf(a2, kap[2][c], acc); acc = fmaf(a3, kap[3][c], acc);
+                acc = fmaf(a4, kap[4][c], acc); acc = fmaf(a5, kap[5][c], acc);
+                const float hc = sl->h[c];
+                ls[c] = fmaf(hc, acc, lam[c]);
+                // u(t_s) from the forward tape
+                const int col = sl->col[c];
+                float u = 0.f;
+                if (col >= 0) {
+                    const float tcur = sl->t[c];
+                    const float ts = (s == 6 && (sl->flag[c] & AFL_LAST)) ? sl->tstop[c] : tcur - cs * hc;
+                    const float* base = P.tape + (long long)col * P.tape_cap * TAPE_STRIDE;
+                    int n = sl->ipos[c];
+                    const int len = sl->tlen[c];
+                    float tn = base[(long long)n * TAPE_STRIDE + TAPE_T], hn = base[(long long)n * TAPE_STRIDE + TAPE_H];
+                    while (n > 0 && ts < tn) { --n; tn = base[(long long)n * TAPE_STRIDE + TAPE_T]; hn = base[(long long)n * TAPE_STRIDE + TAPE_H]; }
+                    while (n + 1 < len && ts > tn + hn) { ++n; tn = base[(long long)n * TAPE_STRIDE + TAPE_T]; hn = base[(long long)n * TAPE_STRIDE + TAPE_H]; }
+                    __syncwarp();
+                    if (lane == 0) sl->ipos[c] = n;
+                    const float th = fminf(fmaxf((ts - tn) / hn, 0.f), 1.f);
+                    const float* e = base + (long long)n * TAPE_STRIDE;
+                    u = fmaf(hn, th * fmaf(th, fmaf(th, fmaf(th, e[4 * NZ + lane], e[3 * NZ + lane]), e[2 * NZ + lane]), e[NZ + lane]), e[lane]);
+                }
+                us[c] = u;
+                // quadrature weight folded into the back-propagated vector (stage 7 carries weight 0: propagate unscaled, skip dW)
+                const float sgn = sl->mode[c] ? -1.f : 1.f;
+                const float w = (s < 6 && col >= 0) ? sgn * hc * bs : 1.f;
+                winv[c] = 1.f / w;
+                const float lw = w * ls[c];
+                const float lwlo = __shfl_up_sync(FULL, lw, 1);
+                const float ulo = __shfl_up_sync(FULL, u, 1);
+                const float Fb = lane > 0 ? c0 * (lw - lwlo) : 0.f;                 // dL/dF_k, faces k = 1..31
+                const float kk = sl->kca[c] * (float)NZ;
+                const float sca = (lane > 0 && kk * (u - ulo) < 0.f) ? kk * Fb : 0.f;
+                float shi = __shfl_down_sync(FULL, sca, 1);
+                if (lane == NZ - 1) shi = 0.f;
+                uca[c] = shi - sca;
+                fb[c] = Fb;          // delta of the output layer: row n = k - 1  (row 31 = 0)
+            }
+            // write a_0 and the output-layer delta (rows shifted by one: neuron n <-> face n+1)
+            {
+                float* a0p = ws + S::ACT0 + lane * CPW;
+                *reinterpret_cast<float4*>(a0p) = make_float4(us[0], us[1], us[2], us[3]);
+                *reinterpret_cast<float4*>(a0p + 4) = make_float4(us[4], us[5], us[6], us[7]);
+                float* dlp = ws + S::DL + ((lane + NZ - 1) & (NZ - 1)) * CPW;
+                *reinterpret_cast<float4*>(dlp) = make_float4(fb[0], fb[1], fb[2], fb[3]);
+                *reinterpret_cast<float4*>(dlp + 4) = make_float4(fb[4], fb[5], fb[6], fb[7]);
+            }
+            __syncwarp();
+            // forward: hidden activations a_1 .. a_NHID (the output layer itself is not needed)
+            dense_hidden<N::IN0, N::NPL, N::RSW, true>(sW + N::P_W0, sW + N::P_B0, ws + S::ACT0, ws + S::act(1), lane);
+            __syncwarp();
+#pragma unroll
+            for (int l = 1; l < N::NHID; ++l) {
+                dense_hidden<N::H, N::NPL, N::RSW, true>(sW + N::P_HID + (l - 1) * N::HIDP_STRIDE, sW + N::P_HID + (l - 1) * N::HIDP_STRIDE + N::H * N::RSW,
+                                                         ws + S::act(l), ws + S::act(l + 1), lane);
+                __syncwarp();
+            }
+            // backward through the output layer
+            float* dcur = ws + S::DL;
+            float* dnext = ws + S::TMP;
+            int dcur_off = S::DL, dnext_off = S::TMP;
+            dense_T_last<N::NPL, N::RSL>(sW + N::P_WL, dcur, ws + S::act(N::NHID), dnext, lane);
+            const bool do_dw = s < 6;
+            __syncthreads();
+            if (do_dw) dw_gemm<N::H, N::NOUT, S::TOTAL>(scratch0 + S::act(N::NHID), scratch0 + dcur_off, g + N::T_WL, g + N::T_BL);
+            __syncthreads();
+            dcur_off = dnext_off;
+            // hidden layers l = NHID-1 .. 1  (Dense_l : a_l -> a_{l+1})
+#pragma unroll
+            for (int l = N::NHID - 1; l >= 1; --l) {
+                dnext_off = (dcur_off == S::TMP) ? S::act(l + 1) : S::TMP;
+                dense_T_hidden<N::NPL, N::NPL, N::RSW, true>(sW + N::P_HID + (l - 1) * N::HIDP_STRIDE, ws + dcur_off, ws + S::act(l), ws + dnext_off, lane, N::H);
+                __syncthreads();
+                if (do_dw) dw_gemm<N::H, N::H, S::TOTAL>(scratch0 + S::act(l), scratch0 + dcur_off, g + N::T_HID + (l - 1) * N::HID_STRIDE,
+                                                         g + N::T_HID + (l - 1) * N::HID_STRIDE + N::H * N::H);
+                __syncthreads();
+                dcur_off = dnext_off;
+            }
+            // first layer: u-bar = W0^T delta_1  -> DL buffer (free since the output-layer dW is done)
+            dense_T_hidden<1, N::NPL, N::RSW, false>(sW + N::P_W0, ws + dcur_off, nullptr, ws + S::DL, lane, N::IN0);
+            __syncthreads();
+            if (do_dw) dw_gemm<N::IN0, N::H, S::TOTAL>(scratch0 + S::ACT0, scratch0 + dcur_off, g + N::T_W0, g + N::T_B0);
+            __syncthreads();
+            // kappa_s = J^T lam_s
+            {
+                const float4 u0 = *reinterpret_cast<const float4*>(ws + S::DL + lane * CPW), u1 = *reinterpret_cast<const float4*>(ws + S::DL + lane * CPW + 4);
+                const float ub[CPW] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+                for (int c = 0; c < CPW; ++c) {
+                    const float v = (ub[c] + uca[c]) * winv[c];
+                    if (s == 0) kap[0][c] = v;
+                    else if (s == 1) kap[1][c] = v;
+                    else if (s == 2) kap[2][c] = v;
+                    else if (s == 3) kap[3][c] = v;
+                    else if (s == 4) kap[4][c] = v;
+                    else if (s == 5) kap[5][c] = v;
+                    else kap[6][c] = v;
+                }
+            }
+            __syncwarp();
+        }
+        // after the loop: ls == lam_new (stage-7 input), kap[6] == J^T lam_new
+
+        // ---- error estimate on lam ----
+        float ee = 0.f;
+#pragma unroll
+        for (int c = 0; c < CPW; ++c) {
+            float e = NFC_BT1 * kap[0][c];
+            e = fmaf(NFC_BT2, kap[1][c], e); e = fmaf(NFC_BT3, kap[2][c], e); e = fmaf(NFC_BT4, kap[3][c], e);
+            e = fmaf(NFC_BT5, kap[4][c], e); e = fmaf(NFC_BT6, kap[5][c], e); e = fmaf(NFC_BT7, kap[6][c], e);
+            e *= sl->h[c];
+            const float sc = P.abstol + fmaxf(fabsf(lam[c]), fabsf(ls[c])) * P.reltol;
+            const float r = e / sc;
+            const float ss = warp_sum(r * r);
+            if (lane == c) ee = sqrtf(ss * (1.f / NZ));
+        }
+        if (lane < CPW && sl->col[lane] >= 0) {
+            int fl = sl->flag[lane];
+            if (sl->mode[lane]) {                              // cancel pass done: retry with the reduced step
+                sl->mode[lane] = 0;
+                sl->dt[lane] = sl->dt_retry[lane];
+            } else {
+                const float h = sl->h[lane];
+                bool accept;
+                float dtnew;
+                if (P.fixed_dt > 0.f) { accept = true; dtnew = P.fixed_dt; }
+                else if (!isfinite(ee)) { accept = false; dtnew = 0.2f * h; }
+                else {
+                    const float q11 = powf(ee, 0.14f);
+                    float q = q11 / powf(sl->qold[lane], 0.08f);
+                    q = fmaxf(0.1f, fminf(5.0f, q / 0.9f));
+                    accept = ee <= 1.0f;
+                    dtnew = accept ? h / q : h / fminf(5.0f, q11 / 0.9f);
+                }
+                if (accept) {
+                    fl |= AFL_ACCEPT;
+                    sl->t[lane] = (fl & AFL_LAST) ? sl->tstop[lane] : sl->t[lane] - h;
+                    if (P.fixed_dt <= 0.f) sl->qold[lane] = fmaxf(ee, 1e-4f);
+                    sl->nacc[lane] += 1;
+                    sl->dt[lane] = dtnew;
+                    if (fl & AFL_LAST) {
+                        if (sl->si[lane] >= 1) { fl |= AFL_JUMP; }
+                        else fl |= AFL_DONE;
+                    }
+                } else {
+                    sl->nrej[lane] += 1;
+                    sl->mode[lane] = 1;                        // undo this step's quadrature contribution next iteration
+                    sl->dt_retry[lane] = dtnew;
+                    if (dtnew < 1e-12f || sl->nacc[lane] + sl->nrej[lane] >= P.max_iters) { sl->status[lane] = dtnew < 1e-12f ? ST_DT_UNDERFLOW : ST_MAXITERS; }
+                }
+                if (sl->nacc[lane] + sl->nrej[lane] >= P.max_iters && !(fl & AFL_DONE)) sl->status[lane] = ST_MAXITERS;
+            }
+            // a failed column still runs its pending cancel pass (mode == 1) before it is retired
+            if (sl->status[lane] != ST_OK && sl->mode[lane] == 0) fl |= AFL_DONE;
+            sl->flag[lane] = fl;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < CPW; ++c) {
+            const int fl = sl->flag[c];
+            if (fl & AFL_ACCEPT) {
+                lam[c] = ls[c];
+                if (fl & AFL_JUMP) {
+                    const int si = sl->si[c];
+                    lam[c] += P.resid[((long long)sl->col[c] * P.n_save + si) * NZ + lane];
+                }
+            }
+        }
+        __syncwarp();
+        if (lane < CPW && (sl->flag[lane] & AFL_JUMP)) {
+            const int si = sl->si[lane] - 1;
+            sl->si[lane] = si;
+            sl->tstop[lane] = P.saveat[si];
+        }
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < CPW; ++c) {
+            if (sl->flag[c] & AFL_DONE) {
+                if (lane == 0) {
+                    const int col = sl->col[c];
+                    if (sl->status[c] != ST_OK && P.status) P.status[col] = sl->status[c];
+                    atomicAdd(&P.counters[CTR_ADJ_ACCEPT], (unsigned long long)sl->nacc[c]);
+                    atomicAdd(&P.counters[CTR_ADJ_REJECT], (unsigned long long)sl->nrej[c]);
+                }
+                __syncwarp();
+                adj_fill_slot<N>(P, sl, c, lam[c], lane);
+#pragma unroll
+                for (int j = 0; j < 7; ++j) kap[j][c] = 0.f;
+                ls[c] = 0.f;
+            }
+        }
+        __syncwarp();
+    }
+}
+
+__global__ void grad_reduce_kernel(const float* __restrict__ gacc, int ncta, int n_params, double scale, float* __restrict__ grad) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_params) return;
+    double s = 0.0;
+    for (int b = 0; b < ncta; ++b) s += (double)gacc[(size_t)b * n_params + p];
+    grad[p] = (float)(scale * s);
+}
+
+__global__ void set_loss_count_kernel(double* loss_sum, double count) { loss_sum[1] = count; }
+
+// ------------------------------------------------ host side ------------------------------------------------
+template <class N> struct AdjLaunch { static constexpr bool WS = sizeof(float) * (N::P_TOTAL + ADJ_NW * AdjScratch<N>::TOTAL) + 4096 <= 232448; };
+template <class N> constexpr size_t adj_smem_bytes() { return sizeof(float) * ((AdjLaunch<N>::WS ? N::P_TOTAL : 0) + (size_t)ADJ_NW * AdjScratch<N>::TOTAL); }
+
+template <class N>
+int adjoint_setup(nfc_handle* h) {
+    if (N::CONVW != 0) return 0;   // conv front-end: forward only in this build (nfc_loss_grad reports unsupported)
+    NFC_CUDA(h, cudaFuncSetAttribute(adjoint_kernel<N, AdjLaunch<N>::WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adj_smem_bytes<N>()));
+    return 0;
+}
 
 template <class N, bool WS, int NW>
-int adjoint_loss_grad(nfc_handle* h, const float*, const float*, float, const float*, double*, float*, int*, int64_t, int64_t, cudaStream_t) {
-    return fail(h, -4, "nfc_loss_grad: adjoint kernels not built yet");
+int adjoint_loss_grad(nfc_handle* h, const float* T0, const float* colp, float pref, const float* Ttrue, double* loss_sum_dev, float* grad_dev,
+                      int* status, int64_t B, int64_t n_total_columns, cudaStream_t st) {
+    if (N::CONVW != 0) return fail(h, -4, "nfc_loss_grad: Chains with a Conv front-end are forward-only in this build");
+    if (!loss_sum_dev || !grad_dev) return fail(h, -1, "null output");
+    const int n_save = h->cfg.n_save, cap = h->cfg.adjoint_max_steps, grid = h->num_sms;
+    NFC_CUDA(h, cudaMemsetAsync(loss_sum_dev, 0, 2 * sizeof(double), st));
+    NFC_CUDA(h, h->a_gacc.ensure((size_t)grid * h->n_params));
+    NFC_CUDA(h, cudaMemsetAsync(h->a_gacc.p, 0, sizeof(float) * (size_t)grid * h->n_params, st));
+    if (B == 0) {
+        NFC_CUDA(h, cudaMemsetAsync(grad_dev, 0, sizeof(float) * h->n_params, st));
+        return 0;
+    }
+    // chunk the batch so that tape + residuals stay inside the scratch budget (default 16 GiB, NFC_TAPE_GIB overrides)
+    double budget = 16.0;
+    if (const char* e = getenv("NFC_TAPE_GIB")) budget = atof(e) > 0 ? atof(e) : budget;
+    const size_t per_col = sizeof(float) * ((size_t)cap * TAPE_STRIDE + (size_t)n_save * NZ);
+    int64_t chunk = (int64_t)(budget * 1073741824.0 / (double)per_col);
+    if (chunk < 1024) chunk = 1024;
+    if (chunk > B) chunk = B;
+    NFC_CUDA(h, h->a_tape.ensure((size_t)chunk * cap * TAPE_STRIDE));
+    NFC_CUDA(h, h->a_resid.ensure((size_t)chunk * n_save * NZ));
+    NFC_CUDA(h, h->a_tlen.ensure((size_t)chunk));
+    int* st_all = status;
+    if (!st_all) { NFC_CUDA(h, h->s_status.ensure((size_t)B)); st_all = h->s_status.p; }
+    bool first = true;
+    NFC_CUDA(h, cudaEventRecord(h->ev[2], st));
+    for (int64_t off = 0; off < B; off += chunk) {
+        const int64_t nb = std::min<int64_t>(chunk, B - off);
+        SolveParams P{};
+        P.T0 = T0 + off * NZ; P.colp = colp + off * 3; P.pref = pref; P.B = nb; P.status = st_all + off;
+        P.Ttrue = Ttrue + off * (int64_t)n_save * NZ; P.resid = h->a_resid.p; P.tape = h->a_tape.p; P.tape_len = h->a_tlen.p;
+        P.loss_sum = loss_sum_dev; P.tape_cap = cap;
+        if (int rc = nfc_launch_record<N>(h, P, st, first)) return rc;
+        AdjParams A{};
+        A.wpack = h->d_wpack.p; A.colp = colp + off * 3; A.saveat = h->d_saveat.p; A.resid = h->a_resid.p; A.tape = h->a_tape.p;
+        A.tape_len = h->a_tlen.p; A.status = st_all + off; A.gacc = h->a_gacc.p; A.counters = h->d_counters.p; A.B = nb; A.n_save = n_save;
+        A.tape_cap = cap; A.max_iters = h->cfg.max_iters; A.use_kca = h->cfg.nde_type == NFC_NDE_CONVECTIVE_ADJUSTMENT; A.n_params = (int)h->n_params;
+        A.pref = pref; A.tf = h->saveat.back(); A.reltol = h->cfg.adjoint_reltol; A.abstol = h->cfg.adjoint_abstol; A.fixed_dt = h->cfg.fixed_dt;
+        adjoint_kernel<N, AdjLaunch<N>::WS><<<grid, ADJ_NW * 32, adj_smem_bytes<N>(), st>>>(A);
+        NFC_CUDA(h, cudaGetLastError());
+        h->last_launches += 1;
+        first = false;
+    }
+    const double ntot = (double)n_total_columns * n_save * NZ;
+    grad_reduce_kernel<<<((int)h->n_params + 255) / 256, 256, 0, st>>>(h->a_gacc.p, grid, (int)h->n_params, 2.0 / ntot, grad_dev);
+    set_loss_count_kernel<<<1, 1, 0, st>>>(loss_sum_dev, (double)B * n_save * NZ);
+    NFC_CUDA(h, cudaGetLastError());
+    NFC_CUDA(h, cudaEventRecord(h->ev[3], st));
+    h->ev_adj_valid = true;
+    h->last_launches += 2;
+    h->last_columns = B;
+    return 0;
 }
 
 }  // namespace nfc

@@ -1,7 +1,9 @@
 // nfc_api.cu -- the C ABI of libnfc_b200.so (declared in include/nfc.h).  sm_100a only, no CPU fallback.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -97,7 +99,7 @@ int do_diagnose(nfc_handle* h, const float* Tsol, const float* colp, float* wT, 
 
 // forward solve (RECORD=false) or forward pass of loss_grad (RECORD=true)
 template <class N, bool RECORD>
-int launch_solve(nfc_handle* h, SolveParams& P, cudaStream_t st) {
+int launch_solve(nfc_handle* h, SolveParams& P, cudaStream_t st, bool reset_counters = true) {
     constexpr bool WS = Launch<N>::WS;
     constexpr int NW = Launch<N>::NW;
     const long long B = P.B;
@@ -113,7 +115,12 @@ int launch_solve(nfc_handle* h, SolveParams& P, cudaStream_t st) {
     P.use_kca = h->cfg.nde_type == NFC_NDE_CONVECTIVE_ADJUSTMENT;
     P.tf = h->saveat.back();
     P.reltol = h->cfg.reltol; P.abstol = h->cfg.abstol; P.fixed_dt = h->cfg.fixed_dt;
-    NFC_CUDA(h, cudaMemsetAsync(h->d_counters.p, 0, sizeof(unsigned long long) * CTR_COUNT, st));
+    if (reset_counters) {
+        NFC_CUDA(h, cudaMemsetAsync(h->d_counters.p, 0, sizeof(unsigned long long) * CTR_COUNT, st));
+    } else {   // later chunks of one loss_grad call: only the two work-queue heads restart
+        NFC_CUDA(h, cudaMemsetAsync(h->d_counters.p + CTR_QUEUE, 0, sizeof(unsigned long long), st));
+        NFC_CUDA(h, cudaMemsetAsync(h->d_counters.p + CTR_ADJ_QUEUE, 0, sizeof(unsigned long long), st));
+    }
     NFC_CUDA(h, cudaEventRecord(h->ev[0], st));
     const long long groups = (B + CPW - 1) / CPW;
     const int grid0 = (int)std::min<long long>(h->num_sms, (groups + NW - 1) / NW);
@@ -133,7 +140,7 @@ int launch_solve(nfc_handle* h, SolveParams& P, cudaStream_t st) {
 }  // namespace
 // the adjoint's host code reuses launch_solve<N, true> (forward pass in RECORD mode)
 template <class N>
-int nfc_launch_record(nfc_handle* h, nfc::SolveParams& P, cudaStream_t st) { return launch_solve<N, true>(h, P, st); }
+int nfc_launch_record(nfc_handle* h, nfc::SolveParams& P, cudaStream_t st, bool first_chunk) { return launch_solve<N, true>(h, P, st, first_chunk); }
 #include "nfc_adjoint.cuh"
 namespace {
 

@@ -131,7 +131,24 @@ struct WarpSlots {
 };
 enum : int { FL_ACCEPT = 1, FL_LAST = 2, FL_DONE = 4 };
 
-constexpr int TAPE_STRIDE = 8 * NZ + 8;   // u, k1..k7 (8 x 32) + (t, h, pad...) ; see nfc_adjoint.cuh
+// adjoint tape entry (one per accepted step): u_n, c1..c4 (Tsit5 dense output in power basis:
+// u(t_n + th h) = u_n + h th (c1 + th (c2 + th (c3 + th c4)))), then (t_n, h_n); see nfc_adjoint.cuh
+constexpr int TAPE_STRIDE = 5 * NZ + 8;
+constexpr int TAPE_T = 5 * NZ, TAPE_H = 5 * NZ + 1;
+
+// c_p = sum_j R[j][p] k_j  (R = OrdinaryDiffEq Tsit5 interpolant coefficients, same numbers as tsit5_btheta)
+__device__ __forceinline__ void tsit5_power_basis(const float (&ks)[7][CPW], int c, float& c1, float& c2, float& c3, float& c4) {
+    c1 = ks[0][c];
+    c2 = -2.763706197274826f * ks[0][c];
+    c2 = fmaf(0.13169999999999998f, ks[1][c], c2); c2 = fmaf(3.9302962368947516f, ks[2][c], c2); c2 = fmaf(-12.411077166933676f, ks[3][c], c2);
+    c2 = fmaf(37.50931341651104f, ks[4][c], c2); c2 = fmaf(-27.896526289197286f, ks[5][c], c2); c2 = fmaf(1.5f, ks[6][c], c2);
+    c3 = 2.9132554618219126f * ks[0][c];
+    c3 = fmaf(-0.2234f, ks[1][c], c3); c3 = fmaf(-5.941033872131505f, ks[2][c], c3); c3 = fmaf(30.33818863028232f, ks[3][c], c3);
+    c3 = fmaf(-88.1789048947664f, ks[4][c], c3); c3 = fmaf(65.09189467479366f, ks[5][c], c3); c3 = fmaf(-4.0f, ks[6][c], c3);
+    c4 = -1.0530884977290216f * ks[0][c];
+    c4 = fmaf(0.1017f, ks[1][c], c4); c4 = fmaf(2.490627285651253f, ks[2][c], c4); c4 = fmaf(-16.548102889244902f, ks[3][c], c4);
+    c4 = fmaf(47.37952196281928f, ks[4][c], c4); c4 = fmaf(-34.87065786149661f, ks[5][c], c4); c4 = fmaf(2.5f, ks[6][c], c4);
+}
 
 // Tsit5 a-matrix rows for stages 2..7 (row 7 == b), zero padded so that one runtime loop serves every stage:
 // the Dense-layer code then exists once in the kernel (instruction-cache resident) instead of six times.
@@ -297,30 +314,32 @@ __global__ void __launch_bounds__(NW * 32, 1) solve_kernel(const SolveParams P) 
                 const float t0 = sl->t[c], h = sl->h[c], tn = sl->tnew[c];
                 int si = sl->si[c];
                 float sse = 0.f;
+                float pc1 = 0.f, pc2 = 0.f, pc3 = 0.f, pc4 = 0.f;
                 if (RECORD) {
-                    // tape entry: u_n, k1..k7, (t_n, h_n)  -- consumed by the continuous adjoint's interpolation
+                    tsit5_power_basis(ks, c, pc1, pc2, pc3, pc4);
                     const int n = sl->tlen[c];
                     if (n < P.tape_cap) {
                         float* e = P.tape + ((long long)col * P.tape_cap + n) * TAPE_STRIDE;
-                        e[lane] = u[c];
-#pragma unroll
-                        for (int j = 0; j < 7; ++j) e[(j + 1) * NZ + lane] = ks[j][c];
-                        if (lane == 0) { e[8 * NZ] = t0; e[8 * NZ + 1] = h; }
+                        e[lane] = u[c]; e[NZ + lane] = pc1; e[2 * NZ + lane] = pc2; e[3 * NZ + lane] = pc3; e[4 * NZ + lane] = pc4;
+                        if (lane == 0) { e[TAPE_T] = t0; e[TAPE_H] = h; }
                     }
                 }
                 while (si < P.n_save) {
                     const float ts = P.saveat[si];
                     if (ts > tn) break;
                     const float th = fminf((ts - t0) / h, 1.0f);
-                    float b[7];
-                    tsit5_btheta(th, b);
-                    float inc = b[0] * ks[0][c];
-#pragma unroll
-                    for (int j = 1; j < 7; ++j) inc = fmaf(b[j], ks[j][c], inc);
-                    const float v = fmaf(h, inc, u[c]);
                     const long long o = (col * P.n_save + si) * NZ + lane;
-                    if (RECORD) { const float r = v - P.Ttrue[o]; P.resid[o] = r; sse = fmaf(r, r, sse); }
-                    else P.Tout[o] = v;
+                    if (RECORD) {
+                        const float v = fmaf(h, th * fmaf(th, fmaf(th, fmaf(th, pc4, pc3), pc2), pc1), u[c]);
+                        const float r = v - P.Ttrue[o]; P.resid[o] = r; sse = fmaf(r, r, sse);
+                    } else {
+                        float b[7];
+                        tsit5_btheta(th, b);
+                        float inc = b[0] * ks[0][c];
+#pragma unroll
+                        for (int j = 1; j < 7; ++j) inc = fmaf(b[j], ks[j][c], inc);
+                        P.Tout[o] = fmaf(h, inc, u[c]);
+                    }
                     ++si;
                 }
                 if (RECORD && si != sl->si[c]) lsum += (double)warp_sum(sse);

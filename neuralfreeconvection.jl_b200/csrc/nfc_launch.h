@@ -15,7 +15,7 @@ using NetConv4 = Net<128, 2, 4>;     // conv-4
 template <class N> struct Launch;
 template <> struct Launch<NetDefault> { static constexpr bool WS = true;  static constexpr int NW = 8; };
 template <> struct Launch<NetWider>   { static constexpr bool WS = false; static constexpr int NW = 8; };   // 330 KB of weights
-template <> struct Launch<NetDeeper>  { static constexpr bool WS = true;  static constexpr int NW = 6; };
+template <> struct Launch<NetDeeper>  { static constexpr bool WS = true;  static constexpr int NW = 5; };   // 172 KB of weights + 5 x 10 KB
 template <> struct Launch<NetConv2>   { static constexpr bool WS = true;  static constexpr int NW = 8; };
 template <> struct Launch<NetConv4>   { static constexpr bool WS = true;  static constexpr int NW = 8; };
 
