@@ -3,7 +3,7 @@
 The directory name contains a dot, so it is imported through the root-level `nfc_b200` alias module
 (`import nfc_b200`), which loads this package with importlib.
 """
-from . import _binding, api, synthetic
+from . import _binding, api, distributed, synthetic
 from ._binding import Handle, NfcError, load, LIB_PATH, EXPORTS, measure_fp32_peak
 from .api import (ADAM, Chain, ColumnDataset, Conv, ConvectiveAdjustmentNDE, ConvectiveAdjustmentNDEParameters, Dense,
                   FreeConvectionNDE, FreeConvectionNDEParameters, Tsit5, ZeroMeanUnitVarianceScaling, destructure,
@@ -12,4 +12,4 @@ from .api import (ADAM, Chain, ColumnDataset, Conv, ConvectiveAdjustmentNDE, Con
 __all__ = ["measure_fp32_peak", "Handle", "NfcError", "load", "LIB_PATH", "EXPORTS", "ADAM", "Chain", "ColumnDataset", "Conv",
            "ConvectiveAdjustmentNDE", "ConvectiveAdjustmentNDEParameters", "Dense", "FreeConvectionNDE",
            "FreeConvectionNDEParameters", "Tsit5", "ZeroMeanUnitVarianceScaling", "destructure", "named_chain",
-           "solve_nde", "train_neural_differential_equation", "synthetic", "api", "_binding"]
+           "solve_nde", "train_neural_differential_equation", "synthetic", "api", "_binding", "distributed"]
