@@ -14,6 +14,7 @@
 #include "nfc_host.h"
 #include "nfc_forward.cuh"
 #include "nfc_launch.h"
+#include "nfc_tc.cuh"
 
 using namespace nfc;
 
@@ -72,6 +73,14 @@ inline float prefactor(const float* glob) { return glob[1] / glob[0] * glob[3] /
 
 template <class N>
 int do_rhs(nfc_handle* h, const float* T, const float* colp, float pref, float* out, int64_t B, cudaStream_t st) {
+    if (h->use_tc && h->arch == ARCH_DEFAULT) {
+        const long long ntiles = (B + tc::TILE - 1) / tc::TILE;
+        const int grid = (int)std::min<long long>(h->num_sms, ntiles);
+        tc::rhs_tc_kernel<<<grid, tc::NTHREADS, tc::IMG_BYTES, st>>>(h->d_wimg.p, T, colp, out, B, pref, h->cfg.nde_type == NFC_NDE_CONVECTIVE_ADJUSTMENT);
+        NFC_CUDA(h, cudaGetLastError());
+        h->last_launches += 1;
+        return 0;
+    }
     constexpr bool WS = Launch<N>::WS;
     constexpr int NW = Launch<N>::NW;
     const long long groups = (B + CPW - 1) / CPW;
@@ -254,6 +263,12 @@ int32_t nfc_create(const nfc_config* cfg, nfc_handle** out) {
     for (auto& ev : h->ev) if (cudaEventCreate(&ev) != cudaSuccess) { h->err = "cudaEventCreate failed"; return bail(-10); }
     int rc = [&]() -> int { NFC_DISPATCH(h, arch_setup, h); }();
     if (rc) return bail(rc);
+    if (h->arch == ARCH_DEFAULT) {
+        if (h->d_wimg.ensure(tc::IMG_BYTES)) { h->err = "cudaMalloc failed"; return bail(-10); }
+        if (cudaFuncSetAttribute(tc::rhs_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::IMG_BYTES) != cudaSuccess) { h->err = "cudaFuncSetAttribute(tc) failed"; return bail(-10); }
+        const char* e = getenv("NFC_TC");
+        h->use_tc = e && atoi(e) != 0;
+    }
     if (h->d_theta.ensure(h->n_params) || h->d_wpack.ensure(h->n_packed) || h->d_saveat.ensure(h->saveat.size()) ||
         h->d_counters.ensure(CTR_COUNT)) { h->err = "cudaMalloc failed"; return bail(-10); }
     if (cudaMemcpy(h->d_saveat.p, h->saveat.data(), sizeof(float) * h->saveat.size(), cudaMemcpyHostToDevice) != cudaSuccess) { h->err = "saveat upload failed"; return bail(-10); }
@@ -266,7 +281,7 @@ int32_t nfc_destroy(nfc_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    h->d_theta.release(); h->d_wpack.release(); h->d_saveat.release(); h->d_k1.release(); h->d_dt.release(); h->d_counters.release();
+    h->d_wimg.release(); h->d_theta.release(); h->d_wpack.release(); h->d_saveat.release(); h->d_k1.release(); h->d_dt.release(); h->d_counters.release();
     h->s_T0.release(); h->s_colp.release(); h->s_out.release(); h->s_true.release(); h->s_grad.release();
     h->s_nacc.release(); h->s_nrej.release(); h->s_status.release(); h->s_loss.release();
     h->a_resid.release(); h->a_tape.release(); h->a_gacc.release(); h->a_tlen.release(); h->a_gsum.release();
@@ -285,6 +300,11 @@ int32_t nfc_set_weights(nfc_handle* h, const float* theta, int64_t n) {
     NFC_CUDA(h, cudaMemcpyAsync(h->d_theta.p, theta, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
     int rc = [&]() -> int { NFC_DISPATCH(h, do_pack, h); }();
     if (rc) return rc;
+    if (h->arch == ARCH_DEFAULT) {
+        const int n = 128 * 32 + 128 * 128 + 32 * 128 + 288;
+        tc::pack_weights_tc_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_theta.p, h->d_wimg.p);
+        NFC_CUDA(h, cudaGetLastError());
+    }
     NFC_CUDA(h, cudaStreamSynchronize(h->stream));
     h->weights_set = true;
     return 0;

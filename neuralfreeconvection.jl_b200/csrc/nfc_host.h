@@ -41,6 +41,8 @@ struct nfc_handle {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool ev_fwd_valid = false, ev_adj_valid = false;
     nfc::DevBuf<float> d_theta, d_wpack, d_saveat, d_k1, d_dt;
+    nfc::DevBuf<unsigned char> d_wimg;      // tensor-core weight image (default Chain only)
+    bool use_tc = false;
     nfc::DevBuf<unsigned long long> d_counters;
     // host-call staging
     nfc::DevBuf<float> s_T0, s_colp, s_out, s_true, s_grad;

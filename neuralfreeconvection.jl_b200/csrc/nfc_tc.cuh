@@ -1,0 +1,333 @@
+// nfc_tc.cuh -- tensor-core (tcgen05 / TMEM) evaluation of the Chain for a tile of 128 ocean columns.
+//
+// One CTA = one tile of 128 columns = the M dimension of a tcgen05.mma (M = 128 TMEM lanes, lane == ocean column).
+// Dense layer l:  D[128 x N_l] (fp32, TMEM) = A[128 x K_l] * W_l^T   with
+//   * A (activations of the 128 columns) living in TENSOR MEMORY as the A operand (TS form of tcgen05.mma): the
+//     epilogue threads write it with tcgen05.st, so activations never touch shared memory;
+//   * W_l in shared memory as the K-major, no-swizzle UMMA B operand (8 x 16-byte core matrices), staged once per CTA
+//     by the bulk-copy engine;
+//   * FP32-faithful arithmetic from BF16 tensor cores: every fp32 value is split into three bf16 terms
+//     x = x1 + x2 + x3 (8+8+8 significand bits) and the product keeps the six terms down to 2^-16:
+//     a1b1 + a1b2 + a2b1 + a2b2 + a1b3 + a3b1  (dropped terms <= 2^-24 relative) -- six kind::f16 MMAs per k-step,
+//     accumulated in fp32 in TMEM.  BF16 keeps fp32's exponent range, so no scaling is needed (weights x1e-5 are fine).
+// Thread roles: warps 0..7 = 256 "column" threads (two per ocean column: warp w and w+4 own TMEM lanes 32 (w%4)..+31,
+// half h = w/4 owns levels / units [16h,16h+16) / [64h,64h+64)), warp 8 = MMA issuer (one elected lane).
+// Only the default Chain Dense(32,128,relu) -> Dense(128,128,relu) -> Dense(128,31) is instantiated here.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "nfc_device.cuh"
+
+namespace nfc {
+namespace tc {
+
+constexpr int TILE = 128;                 // ocean columns per CTA
+constexpr int H = 128;                    // hidden width
+constexpr int NCT = 256;                  // column threads
+constexpr int NTHREADS = NCT + 32;        // + MMA warp
+// tensor-memory columns (32-bit cells per lane)
+constexpr int TM_D = 0;                   // accumulator, up to 128 columns
+constexpr int TM_A = 128;                 // A operand: 3 splits x 64 columns (K = 128 bf16 packed two per cell)
+constexpr int TM_COLS = 512;
+// shared-memory image (bytes): three bf16 splits of each weight matrix in UMMA K-major no-swizzle layout, then biases
+constexpr int W1_BYTES = 128 * 32 * 2;    // N = 128, K = 32
+constexpr int W2_BYTES = 128 * 128 * 2;   // N = 128, K = 128
+constexpr int W3_BYTES = 32 * 128 * 2;    // N = 32 (31 + zero row), K = 128
+constexpr int OFF_W1 = 0;
+constexpr int OFF_W2 = OFF_W1 + 3 * W1_BYTES;
+constexpr int OFF_W3 = OFF_W2 + 3 * W2_BYTES;
+constexpr int OFF_B = OFF_W3 + 3 * W3_BYTES;           // b1[128] b2[128] b3[32] fp32
+constexpr int IMG_BYTES = OFF_B + (128 + 128 + 32) * 4;   // 148 608 B
+
+// byte offset of element (n, k) inside one split image of an [N][K] matrix: K chunks of 8 elements are LBO apart,
+// groups of 8 rows are SBO = 128 B apart, a core matrix is 8 rows x 16 B
+__host__ __device__ constexpr int umma_off(int n, int k, int N) { return (k >> 3) * (N * 16) + (n >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2; }
+
+// ---- PTX wrappers ----------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem desc]   (kind::f16, bf16 inputs, fp32 accumulate)
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+                 "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {   // kind::f16: A = B = BF16 (1), C = F32 (1), both K-major
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ uint64_t make_bdesc(uint32_t smem_addr, int N) {   // K-major, SWIZZLE_NONE: LBO = N*16 B, SBO = 128 B
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(((uint32_t)N * 16) >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
+}
+
+// x = x1 + x2 + x3 in bf16; the pair (even, odd) is packed as (low, high) half of one 32-bit cell
+__device__ __forceinline__ void split3(float v0, float v1, uint32_t& p1, uint32_t& p2, uint32_t& p3) {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(v1), "f"(v0));
+    const float r0 = v0 - __uint_as_float(p1 << 16), r1 = v1 - __uint_as_float(p1 & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p2) : "f"(r1), "f"(r0));
+    const float s0 = r0 - __uint_as_float(p2 << 16), s1 = r1 - __uint_as_float(p2 & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p3) : "f"(s1), "f"(s0));
+}
+
+// ---- weight image: theta (Flux layout) -> three bf16 splits per layer in UMMA layout + fp32 biases ----------------------
+__global__ void pack_weights_tc_kernel(const float* __restrict__ theta, unsigned char* __restrict__ img) {
+    using N = Net<128, 2, 0>;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n1 = 128 * 32, n2 = 128 * 128, n3 = 32 * 128;
+    float w = 0.f;
+    int off = 0, bytes = 0;
+    if (i < n1) { const int n = i % 128, k = i / 128; w = theta[N::T_W0 + k * 128 + n]; off = OFF_W1 + umma_off(n, k, 128); bytes = W1_BYTES; }
+    else if (i < n1 + n2) { const int q = i - n1, n = q % 128, k = q / 128; w = theta[N::T_HID + k * 128 + n]; off = OFF_W2 + umma_off(n, k, 128); bytes = W2_BYTES; }
+    else if (i < n1 + n2 + n3) {
+        const int q = i - n1 - n2, n = q % 32, k = q / 32;
+        w = n < 31 ? theta[N::T_WL + k * 31 + n] : 0.f;
+        off = OFF_W3 + umma_off(n, k, 32); bytes = W3_BYTES;
+    } else if (i < n1 + n2 + n3 + 288) {
+        const int q = i - n1 - n2 - n3;
+        float b = 0.f;
+        if (q < 128) b = theta[N::T_B0 + q];
+        else if (q < 256) b = theta[N::T_HID + 128 * 128 + (q - 128)];
+        else if (q - 256 < 31) b = theta[N::T_BL + (q - 256)];
+        reinterpret_cast<float*>(img + OFF_B)[q] = b;
+        return;
+    } else return;
+    const __nv_bfloat16 b1 = __float2bfloat16_rn(w);
+    const float r1 = w - __bfloat162float(b1);
+    const __nv_bfloat16 b2 = __float2bfloat16_rn(r1);
+    const __nv_bfloat16 b3 = __float2bfloat16_rn(r1 - __bfloat162float(b2));
+    *reinterpret_cast<__nv_bfloat16*>(img + off) = b1;
+    *reinterpret_cast<__nv_bfloat16*>(img + off + bytes) = b2;
+    *reinterpret_cast<__nv_bfloat16*>(img + off + 2 * bytes) = b3;
+}
+
+// ---- shared state of one CTA ------------------------------------------------------------------------------------------
+struct TcShared {
+    uint64_t bar_w;        // weight image landed
+    uint64_t bar_a;        // A operand written by the 256 column threads (count 256)
+    uint64_t bar_d;        // accumulator ready (tcgen05.commit)
+    uint32_t tmem_base;
+    int stop;
+    float xch[2][TILE][2]; // y_15 / y_16 exchange between the two threads of a column (double buffered by evaluation parity)
+    float part[TILE][2];   // partial error norms
+};
+
+// MMA issuer: all six split products of one Dense layer.  a_cols = K/2 columns per split, layer = 0,1,2
+__device__ __forceinline__ void issue_layer(uint32_t tmem_base, uint32_t smem_img, int layer) {
+    const int K = layer == 0 ? 32 : 128, Nn = layer == 2 ? 32 : 128;
+    const uint32_t woff = layer == 0 ? OFF_W1 : (layer == 1 ? OFF_W2 : OFF_W3);
+    const uint32_t wbytes = layer == 0 ? W1_BYTES : (layer == 1 ? W2_BYTES : W3_BYTES);
+    const uint32_t idesc = layer == 2 ? make_idesc(128, 32) : make_idesc(128, 128);
+    const uint32_t d = tmem_base + TM_D;
+    // (a split, b split): smallest terms first so the big a1 b1 term lands on an already formed tail
+    const int sa[6] = {2, 0, 1, 1, 0, 0};
+    const int sb[6] = {0, 2, 1, 0, 1, 0};
+    uint32_t acc = 0;
+#pragma unroll 1
+    for (int p = 0; p < 6; ++p) {
+        const uint32_t a0 = tmem_base + TM_A + sa[p] * 64;
+        const uint32_t b0 = smem_img + woff + sb[p] * wbytes;
+        for (int j = 0; j < K / 16; ++j) {
+            mma_ts(d, a0 + 8 * j, make_bdesc(b0 + 2 * j * (Nn * 16), Nn), idesc, acc);
+            acc = 1;
+        }
+    }
+}
+
+// Column-thread side of one Chain evaluation.  y[16]: this thread's 16 levels of the stage input (level 16 h + i).
+// Returns nn[i] = NN output n = 16 h + i - 1  (i = 0..16; nn[0] of h = 0 and nn[16] of h = 1 are unused / boundary faces).
+__device__ __forceinline__ void chain_eval(TcShared* S, const float* sbias, const float (&y)[16], float (&nn)[17], int& pd, int lane, int wq, int h) {
+    const uint32_t tl = S->tmem_base + ((uint32_t)(32 * wq) << 16);     // this warp's TMEM lane window
+    // ---- layer-1 A operand: levels 16h..16h+15 -> 8 cells per split at columns 8h
+    {
+        uint32_t p1[8], p2[8], p3[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) split3(y[2 * i], y[2 * i + 1], p1[i], p2[i], p3[i]);
+        tmem_st8(tl + TM_A + 0 * 64 + 8 * h, p1);
+        tmem_st8(tl + TM_A + 1 * 64 + 8 * h, p2);
+        tmem_st8(tl + TM_A + 2 * 64 + 8 * h, p3);
+        wait_st();
+        fence_before_sync();
+        mbar_arrive(&S->bar_a);
+    }
+    // ---- hidden layers: D -> bias, relu, split -> A operand of the next layer (units 64h .. 64h+63 -> cells 32h .. 32h+31)
+#pragma unroll 1
+    for (int l = 0; l < 2; ++l) {
+        mbar_wait(&S->bar_d, pd); pd ^= 1;
+        fence_after_sync();
+        const float* b = sbias + 128 * l + 64 * h;
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+            uint32_t r[16];
+            tmem_ld16(tl + TM_D + 64 * h + 16 * q, r);
+            wait_ld();
+            uint32_t p1[8], p2[8], p3[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float v0 = fmaxf(__uint_as_float(r[2 * i]) + b[16 * q + 2 * i], 0.f);
+                const float v1 = fmaxf(__uint_as_float(r[2 * i + 1]) + b[16 * q + 2 * i + 1], 0.f);
+                split3(v0, v1, p1[i], p2[i], p3[i]);
+            }
+            tmem_st8(tl + TM_A + 0 * 64 + 32 * h + 8 * q, p1);
+            tmem_st8(tl + TM_A + 1 * 64 + 32 * h + 8 * q, p2);
+            tmem_st8(tl + TM_A + 2 * 64 + 32 * h + 8 * q, p3);
+        }
+        wait_st();
+        fence_before_sync();
+        mbar_arrive(&S->bar_a);
+    }
+    // ---- output layer: NN[16h-1 .. 16h+15]
+    mbar_wait(&S->bar_d, pd); pd ^= 1;
+    fence_after_sync();
+    {
+        uint32_t r[16], r0 = 0;
+        tmem_ld16(tl + TM_D + 16 * h, r);
+        if (h) tmem_ld1(tl + TM_D + 15, r0);
+        wait_ld();
+        const float* b3 = sbias + 256;
+        nn[0] = h ? __uint_as_float(r0) + b3[15] : 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) nn[i + 1] = __uint_as_float(r[i]) + b3[16 * h + i];
+    }
+    fence_before_sync();     // the next evaluation's tcgen05.st / MMA may overwrite D and A
+}
+
+// MMA warp main loop: three layers per Chain evaluation until the column threads raise `stop`
+__device__ __forceinline__ void mma_warp_loop(TcShared* S, uint32_t smem_img, int lane) {
+    if (lane == 0) {
+        int pa = 0, layer = 0;
+        while (true) {
+            mbar_wait(&S->bar_a, pa); pa ^= 1;
+            if (*reinterpret_cast<volatile int*>(&S->stop)) break;
+            fence_after_sync();
+            issue_layer(S->tmem_base, smem_img, layer);
+            mma_commit(&S->bar_d);
+            layer = layer == 2 ? 0 : layer + 1;
+        }
+    }
+    __syncwarp();
+}
+
+// common prologue: barriers, TMEM allocation, weight image.  Returns after everything is visible to all threads.
+__device__ __forceinline__ void tc_prologue(TcShared* S, unsigned char* simg, const unsigned char* gimg, int warp) {
+    if (threadIdx.x == 0) {
+        mbar_init(&S->bar_w, 1);
+        mbar_init(&S->bar_a, NCT);
+        mbar_init(&S->bar_d, 1);
+        S->stop = 0;
+    }
+    __syncthreads();
+    if (warp == 8) tmem_alloc(&S->tmem_base, TM_COLS);
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&S->bar_w, IMG_BYTES);
+        for (unsigned off = 0; off < (unsigned)IMG_BYTES; off += 32768u) {
+            const unsigned n = IMG_BYTES - off < 32768u ? IMG_BYTES - off : 32768u;
+            bulk_g2s(simg + off, gimg + off, n, &S->bar_w);
+        }
+    }
+    mbar_wait(&S->bar_w, 0);
+    // generic-proxy view of the image is not needed by the MMA (async proxy reads smem); biases are read by LDS after this wait
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+}
+
+// ---- test / nfc_rhs kernel: f(T) for whole tiles of 128 columns ---------------------------------------------------------
+__global__ void __launch_bounds__(NTHREADS, 1)
+rhs_tc_kernel(const unsigned char* __restrict__ gimg, const float* __restrict__ T, const float* __restrict__ colp, float* __restrict__ out,
+              long long B, float pref, int use_kca) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ TcShared S;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    tc_prologue(&S, smem_raw, gimg, warp);
+    const uint32_t smem_img = smem_u32(smem_raw);
+    const float* sbias = reinterpret_cast<const float*>(smem_raw + OFF_B);
+    const long long ntiles = (B + TILE - 1) / TILE;
+    if (warp == 8) {
+        mma_warp_loop(&S, smem_img, lane);
+    } else {
+        const int wq = warp & 3, h = warp >> 2, c = 32 * wq + lane;
+        int pd = 0, xb = 0;
+        for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+            const long long col = tile * TILE + c;
+            const bool ok = col < B;
+            float y[16], nn[17];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 v = ok ? *reinterpret_cast<const float4*>(T + col * NZ + 16 * h + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+                y[4 * i] = v.x; y[4 * i + 1] = v.y; y[4 * i + 2] = v.z; y[4 * i + 3] = v.w;
+            }
+            xb ^= 1;
+            S.xch[xb][c][h] = h ? y[0] : y[15];             // h = 0 publishes y_15, h = 1 publishes y_16
+            chain_eval(&S, sbias, y, nn, pd, lane, wq, h);  // its mbarrier traffic orders the exchange (double buffered: see TcShared)
+            const float bot = ok ? colp[col * 3 + 0] : 0.f, top = ok ? colp[col * 3 + 1] : 0.f;
+            const float kk = (ok && use_kca) ? colp[col * 3 + 2] * (float)NZ : 0.f;
+            // faces k = 16h .. 16h+16 ; F_0 = bottom, F_32 = top, else NN[k-1] - min(0, K (y_k - y_{k-1}) / dz)
+            float F[17];
+            const float ynb = S.xch[xb][c][1 - h];         // h = 0: y_16 ; h = 1: y_15
+#pragma unroll
+            for (int i = 0; i <= 16; ++i) {
+                const int k = 16 * h + i;
+                const float yk = i < 16 ? y[i] : ynb;       // level k     (i == 16 only for h = 0 -> y_16)
+                const float ykm = i > 0 ? y[i - 1] : ynb;   // level k - 1 (i == 0  only for h = 1 -> y_15)
+                float f = nn[i] - fminf(kk * (yk - ykm), 0.f);
+                if (k == 0) f = bot;
+                if (k == NZ) f = top;
+                F[i] = f;
+            }
+            if (ok) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float4 o;
+                    o.x = -pref * ((F[4 * i + 1] - F[4 * i]) * (float)NZ); o.y = -pref * ((F[4 * i + 2] - F[4 * i + 1]) * (float)NZ);
+                    o.z = -pref * ((F[4 * i + 3] - F[4 * i + 2]) * (float)NZ); o.w = -pref * ((F[4 * i + 4] - F[4 * i + 3]) * (float)NZ);
+                    *reinterpret_cast<float4*>(out + col * NZ + 16 * h + 4 * i) = o;
+                }
+            }
+        }
+        // release the MMA warp
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        if (threadIdx.x == 0) S.stop = 1;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        mbar_arrive(&S.bar_a);
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(S.tmem_base, TM_COLS);
+}
+
+}  // namespace tc
+}  // namespace nfc
