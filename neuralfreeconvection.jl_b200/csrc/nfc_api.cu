@@ -136,8 +136,13 @@ int launch_solve(nfc_handle* h, SolveParams& P, cudaStream_t st, bool reset_coun
     rhs_init_kernel<N, WS, 1><<<grid0, NW * 32, smem_bytes<N>(NW), st>>>(h->d_wpack.p, P.T0, P.colp, h->d_k1.p, h->d_dt.p, B, P.pref, P.use_kca,
                                                                     P.reltol, P.abstol, P.tf, P.fixed_dt);
     NFC_CUDA(h, cudaGetLastError());
-    const int grid = (int)std::min<long long>(h->num_sms, (groups + NW - 1) / NW);
-    solve_kernel<N, WS, NW, RECORD><<<grid, NW * 32, smem_bytes<N>(NW), st>>>(P);
+    if (!RECORD && h->use_tc && h->arch == ARCH_DEFAULT) {
+        const int gridt = (int)std::min<long long>(h->num_sms, (B + tc::TILE - 1) / tc::TILE);
+        tc::solve_tc_kernel<<<gridt, tc::NTHREADS, tc::IMG_BYTES, st>>>(h->d_wimg.p, P);
+    } else {
+        const int grid = (int)std::min<long long>(h->num_sms, (groups + NW - 1) / NW);
+        solve_kernel<N, WS, NW, RECORD><<<grid, NW * 32, smem_bytes<N>(NW), st>>>(P);
+    }
     NFC_CUDA(h, cudaGetLastError());
     NFC_CUDA(h, cudaEventRecord(h->ev[1], st));
     h->ev_fwd_valid = true;
@@ -265,7 +270,8 @@ int32_t nfc_create(const nfc_config* cfg, nfc_handle** out) {
     if (rc) return bail(rc);
     if (h->arch == ARCH_DEFAULT) {
         if (h->d_wimg.ensure(tc::IMG_BYTES)) { h->err = "cudaMalloc failed"; return bail(-10); }
-        if (cudaFuncSetAttribute(tc::rhs_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::IMG_BYTES) != cudaSuccess) { h->err = "cudaFuncSetAttribute(tc) failed"; return bail(-10); }
+        if (cudaFuncSetAttribute(tc::rhs_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::IMG_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(tc::solve_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::IMG_BYTES) != cudaSuccess) { h->err = "cudaFuncSetAttribute(tc) failed"; return bail(-10); }
         const char* e = getenv("NFC_TC");
         h->use_tc = e && atoi(e) != 0;
     }

@@ -11,7 +11,7 @@
 //     a1b1 + a1b2 + a2b1 + a2b2 + a1b3 + a3b1  (dropped terms <= 2^-24 relative) -- six kind::f16 MMAs per k-step,
 //     accumulated in fp32 in TMEM.  BF16 keeps fp32's exponent range, so no scaling is needed (weights x1e-5 are fine).
 // Thread roles: warps 0..7 = 256 "column" threads (two per ocean column: warp w and w+4 own TMEM lanes 32 (w%4)..+31,
-// half h = w/4 owns levels / units [16h,16h+16) / [64h,64h+64)), warp 8 = MMA issuer (one elected lane).
+// half h = w/4 owns levels / units [16h,16h+16) / [64h,64h+64)), warps 8..11 = MMA warpgroup (warp 8, one elected lane, issues; the group gives its registers to the column threads with setmaxnreg).
 // Only the default Chain Dense(32,128,relu) -> Dense(128,128,relu) -> Dense(128,31) is instantiated here.
 #pragma once
 #include <cuda_bf16.h>
@@ -24,7 +24,8 @@ namespace tc {
 constexpr int TILE = 128;                 // ocean columns per CTA
 constexpr int H = 128;                    // hidden width
 constexpr int NCT = 256;                  // column threads
-constexpr int NTHREADS = NCT + 32;        // + MMA warp
+constexpr int NTHREADS = NCT + 128;       // + the MMA warpgroup (only its first warp works; a full warpgroup is needed for setmaxnreg)
+constexpr int REGS_MMA = 40, REGS_COL = 232;   // (168 - 40) * 128 freed == (232 - 168) * 256 claimed
 // tensor-memory columns (32-bit cells per lane)
 constexpr int TM_D = 0;                   // accumulator, up to 128 columns
 constexpr int TM_A = 128;                 // A operand: 3 splits x 64 columns (K = 128 bf16 packed two per cell)
@@ -51,6 +52,8 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+template <int R> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
@@ -142,7 +145,9 @@ struct TcShared {
     uint32_t tmem_base;
     int stop;
     float xch[2][TILE][2]; // y_15 / y_16 exchange between the two threads of a column (double buffered by evaluation parity)
-    float part[TILE][2];   // partial error norms
+    float part[2][TILE][2];// partial error norms (double buffered)
+    int newcol[TILE];      // refill hand-off between the two threads of a column
+    int any;
 };
 
 // MMA issuer: all six split products of one Dense layer.  a_cols = K/2 columns per split, layer = 0,1,2
@@ -225,6 +230,25 @@ __device__ __forceinline__ void chain_eval(TcShared* S, const float* sbias, cons
     fence_before_sync();     // the next evaluation's tcgen05.st / MMA may overwrite D and A
 }
 
+
+// f (16 levels of this thread) from the Chain output and the stage input: faces k = 16h .. 16h+16,
+// F_0 = bottom, F_32 = top, else NN[k-1] - min(0, K_CA (y_k - y_{k-1}) / dz);  f_k = -pref (F_{k+1} - F_k) / dz
+__device__ __forceinline__ void faces_to_f(const float (&y)[16], float ynb, const float (&nn)[17], float bot, float top, float kk, float pref,
+                                           int h, float (&f)[16]) {
+    float Fprev = 0.f;
+#pragma unroll
+    for (int i = 0; i <= 16; ++i) {
+        const int k = 16 * h + i;
+        const float yk = i < 16 ? y[i < 16 ? i : 0] : ynb;       // level k     (i == 16 only matters for h = 0 -> y_16)
+        const float ykm = i > 0 ? y[i > 0 ? i - 1 : 0] : ynb;    // level k - 1 (i == 0  only matters for h = 1 -> y_15)
+        float F = nn[i] - fminf(kk * (yk - ykm), 0.f);
+        if (k == 0) F = bot;
+        if (k == NZ) F = top;
+        if (i > 0) f[i - 1] = -pref * ((F - Fprev) * (float)NZ);
+        Fprev = F;
+    }
+}
+
 // MMA warp main loop: three layers per Chain evaluation until the column threads raise `stop`
 __device__ __forceinline__ void mma_warp_loop(TcShared* S, uint32_t smem_img, int lane) {
     if (lane == 0) {
@@ -276,9 +300,11 @@ rhs_tc_kernel(const unsigned char* __restrict__ gimg, const float* __restrict__ 
     const uint32_t smem_img = smem_u32(smem_raw);
     const float* sbias = reinterpret_cast<const float*>(smem_raw + OFF_B);
     const long long ntiles = (B + TILE - 1) / TILE;
-    if (warp == 8) {
-        mma_warp_loop(&S, smem_img, lane);
+    if (warp >= 8) {
+        reg_dec<REGS_MMA>();
+        if (warp == 8) mma_warp_loop(&S, smem_img, lane);
     } else {
+        reg_inc<REGS_COL>();
         const int wq = warp & 3, h = warp >> 2, c = 32 * wq + lane;
         int pd = 0, xb = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -295,25 +321,12 @@ rhs_tc_kernel(const unsigned char* __restrict__ gimg, const float* __restrict__ 
             chain_eval(&S, sbias, y, nn, pd, lane, wq, h);  // its mbarrier traffic orders the exchange (double buffered: see TcShared)
             const float bot = ok ? colp[col * 3 + 0] : 0.f, top = ok ? colp[col * 3 + 1] : 0.f;
             const float kk = (ok && use_kca) ? colp[col * 3 + 2] * (float)NZ : 0.f;
-            // faces k = 16h .. 16h+16 ; F_0 = bottom, F_32 = top, else NN[k-1] - min(0, K (y_k - y_{k-1}) / dz)
-            float F[17];
-            const float ynb = S.xch[xb][c][1 - h];         // h = 0: y_16 ; h = 1: y_15
-#pragma unroll
-            for (int i = 0; i <= 16; ++i) {
-                const int k = 16 * h + i;
-                const float yk = i < 16 ? y[i] : ynb;       // level k     (i == 16 only for h = 0 -> y_16)
-                const float ykm = i > 0 ? y[i - 1] : ynb;   // level k - 1 (i == 0  only for h = 1 -> y_15)
-                float f = nn[i] - fminf(kk * (yk - ykm), 0.f);
-                if (k == 0) f = bot;
-                if (k == NZ) f = top;
-                F[i] = f;
-            }
+            float f[16];
+            faces_to_f(y, S.xch[xb][c][1 - h], nn, bot, top, kk, pref, h, f);
             if (ok) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    float4 o;
-                    o.x = -pref * ((F[4 * i + 1] - F[4 * i]) * (float)NZ); o.y = -pref * ((F[4 * i + 2] - F[4 * i + 1]) * (float)NZ);
-                    o.z = -pref * ((F[4 * i + 3] - F[4 * i + 2]) * (float)NZ); o.w = -pref * ((F[4 * i + 4] - F[4 * i + 3]) * (float)NZ);
+                    const float4 o = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
                     *reinterpret_cast<float4*>(out + col * NZ + 16 * h + 4 * i) = o;
                 }
             }
@@ -322,6 +335,214 @@ rhs_tc_kernel(const unsigned char* __restrict__ gimg, const float* __restrict__ 
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (threadIdx.x == 0) S.stop = 1;
         asm volatile("bar.sync 1, 256;" ::: "memory");
+        mbar_arrive(&S.bar_a);
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 8) tmem_dealloc(S.tmem_base, TM_COLS);
+}
+
+}  // namespace tc
+}  // namespace nfc
+
+// =====================================================================================================================
+// Persistent adaptive Tsit5 solve on the tensor-core Chain: one CTA per SM, 128 column slots (two threads per column),
+// every slot with its own PI controller, finished slots refilled from the global queue (same semantics as
+// nfc_forward.cuh:solve_kernel; src/solve.jl:4).
+// =====================================================================================================================
+#include "nfc_forward.cuh"
+
+namespace nfc {
+namespace tc {
+
+__device__ __forceinline__ void cta_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned char* __restrict__ gimg, const SolveParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ TcShared S;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    tc_prologue(&S, smem_raw, gimg, warp);
+    const uint32_t smem_img = smem_u32(smem_raw);
+    const float* sbias = reinterpret_cast<const float*>(smem_raw + OFF_B);
+    if (warp >= 8) {
+        reg_dec<REGS_MMA>();
+        if (warp == 8) mma_warp_loop(&S, smem_img, lane);
+    } else {
+        reg_inc<REGS_COL>();
+        const int wq = warp & 3, h = warp >> 2, c = 32 * wq + lane;
+        int pd = 0, xb = 0, pb = 0;
+        float u[16], ks[7][16], y[16];
+        int col = -1, si = 0, nacc = 0, nrej = 0, status = ST_OK;
+        float t = 0.f, dt = 0.f, qold = 1e-4f, bot = 0.f, top = 0.f, kk = 0.f;
+        bool queue_empty = false, done = true;       // done => slot wants a (new) column
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            u[i] = 0.f;
+#pragma unroll
+            for (int j = 0; j < 7; ++j) ks[j][i] = 0.f;
+        }
+        while (true) {
+            // ---------------- retire / refill ----------------
+            if (h == 0) {
+                int nc = -2;                                    // -2: keep the current column
+                if (done) {
+                    if (col >= 0) {
+                        if (P.naccept) P.naccept[col] = nacc;
+                        if (P.nreject) P.nreject[col] = nrej;
+                        if (P.status) P.status[col] = status;
+                        atomicAdd(&P.counters[CTR_ACCEPT], (unsigned long long)nacc);
+                        atomicAdd(&P.counters[CTR_REJECT], (unsigned long long)nrej);
+                    }
+                    nc = -1;
+                    if (!queue_empty) {
+                        const long long nx = (long long)atomicAdd(&P.counters[CTR_QUEUE], 1ULL);
+                        if (nx < P.B) nc = (int)nx; else queue_empty = true;
+                    }
+                }
+                S.newcol[c] = nc;
+            }
+            if (threadIdx.x == 0) S.any = 0;
+            cta_bar();
+            {
+                const int nc = S.newcol[c];
+                if (nc != -2) {
+                    col = nc; done = false; nacc = 0; nrej = 0; status = ST_OK; t = 0.f; qold = 1e-4f; si = 0;
+#pragma unroll
+                    for (int j = 1; j < 7; ++j)
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) ks[j][i] = 0.f;
+                    if (nc >= 0) {
+                        const long long o = (long long)nc * NZ + 16 * h;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 a = *reinterpret_cast<const float4*>(P.T0 + o + 4 * i), b = *reinterpret_cast<const float4*>(P.k1_init + o + 4 * i);
+                            u[4 * i] = a.x; u[4 * i + 1] = a.y; u[4 * i + 2] = a.z; u[4 * i + 3] = a.w;
+                            ks[0][4 * i] = b.x; ks[0][4 * i + 1] = b.y; ks[0][4 * i + 2] = b.z; ks[0][4 * i + 3] = b.w;
+                        }
+                        dt = P.dt_init[nc];
+                        bot = P.colp[(long long)nc * 3 + 0]; top = P.colp[(long long)nc * 3 + 1];
+                        kk = P.use_kca ? P.colp[(long long)nc * 3 + 2] * (float)NZ : 0.f;
+                        while (si < P.n_save && P.saveat[si] <= 0.f) {
+                            float* o2 = P.Tout + ((long long)nc * P.n_save + si) * NZ + 16 * h;
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(o2 + 4 * i) = make_float4(u[4 * i], u[4 * i + 1], u[4 * i + 2], u[4 * i + 3]);
+                            ++si;
+                        }
+                    } else {
+                        queue_empty = true;
+                        dt = 0.f; bot = 0.f; top = 0.f; kk = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) { u[i] = 0.f; ks[0][i] = 0.f; }
+                    }
+                }
+                if (col >= 0) S.any = 1;
+            }
+            cta_bar();
+            if (!S.any) break;
+            // ---------------- one attempted Tsit5 step ----------------
+            float hs = 0.f;
+            bool last = false;
+            if (col >= 0) {
+                hs = fminf(dt, P.tf - t);
+                if (t + hs >= P.tf * (1.0f - 1e-6f)) { hs = P.tf - t; last = true; }
+            }
+#pragma unroll 1
+            for (int s = 0; s < 6; ++s) {
+                const float a0 = c_tsit5_a[s][0], a1 = c_tsit5_a[s][1], a2 = c_tsit5_a[s][2], a3 = c_tsit5_a[s][3], a4 = c_tsit5_a[s][4], a5 = c_tsit5_a[s][5];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float acc = a0 * ks[0][i];
+                    acc = fmaf(a1, ks[1][i], acc); acc = fmaf(a2, ks[2][i], acc); acc = fmaf(a3, ks[3][i], acc);
+                    acc = fmaf(a4, ks[4][i], acc); acc = fmaf(a5, ks[5][i], acc);
+                    y[i] = fmaf(hs, acc, u[i]);
+                }
+                xb ^= 1;
+                S.xch[xb][c][h] = h ? y[0] : y[15];
+                float nn[17], f[16];
+                chain_eval(&S, sbias, y, nn, pd, lane, wq, h);
+                faces_to_f(y, S.xch[xb][c][1 - h], nn, bot, top, kk, P.pref, h, f);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    if (s == 0) ks[1][i] = f[i];
+                    else if (s == 1) ks[2][i] = f[i];
+                    else if (s == 2) ks[3][i] = f[i];
+                    else if (s == 3) ks[4][i] = f[i];
+                    else if (s == 4) ks[5][i] = f[i];
+                    else ks[6][i] = f[i];
+                }
+            }
+            // y == u_new, ks[6] == f(u_new)
+            float part = 0.f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                float e = NFC_BT1 * ks[0][i];
+                e = fmaf(NFC_BT2, ks[1][i], e); e = fmaf(NFC_BT3, ks[2][i], e); e = fmaf(NFC_BT4, ks[3][i], e);
+                e = fmaf(NFC_BT5, ks[4][i], e); e = fmaf(NFC_BT6, ks[5][i], e); e = fmaf(NFC_BT7, ks[6][i], e);
+                e *= hs;
+                const float r = e / (P.abstol + fmaxf(fabsf(u[i]), fabsf(y[i])) * P.reltol);
+                part = fmaf(r, r, part);
+            }
+            pb ^= 1;
+            S.part[pb][c][h] = part;
+            cta_bar();
+            if (col >= 0) {
+                const float ee = sqrtf((S.part[pb][c][0] + S.part[pb][c][1]) * (1.f / NZ));    // same order in both threads of the column
+                bool accept;
+                float dtnew;
+                if (!isfinite(ee)) { status = ST_NAN; accept = false; dtnew = hs; }
+                else if (P.fixed_dt > 0.f) { accept = true; dtnew = P.fixed_dt; }
+                else {
+                    const float q11 = powf(ee, 0.14f);
+                    float q = q11 / powf(qold, 0.08f);
+                    q = fmaxf(0.1f, fminf(5.0f, q / 0.9f));
+                    accept = ee <= 1.0f;
+                    dtnew = accept ? hs / q : hs / fminf(5.0f, q11 / 0.9f);
+                }
+                if (accept) {
+                    const float tn = last ? P.tf : t + hs;
+                    while (si < P.n_save) {
+                        const float ts = P.saveat[si];
+                        if (ts > tn) break;
+                        const float th = fminf((ts - t) / hs, 1.0f);
+                        float b[7];
+                        tsit5_btheta(th, b);
+                        float* o2 = P.Tout + ((long long)col * P.n_save + si) * NZ + 16 * h;
+#pragma unroll
+                        for (int i4 = 0; i4 < 4; ++i4) {
+                            float v[4];
+#pragma unroll
+                            for (int m = 0; m < 4; ++m) {
+                                const int i = 4 * i4 + m;
+                                float inc = b[0] * ks[0][i];
+                                inc = fmaf(b[1], ks[1][i], inc); inc = fmaf(b[2], ks[2][i], inc); inc = fmaf(b[3], ks[3][i], inc);
+                                inc = fmaf(b[4], ks[4][i], inc); inc = fmaf(b[5], ks[5][i], inc); inc = fmaf(b[6], ks[6][i], inc);
+                                v[m] = fmaf(hs, inc, u[i]);
+                            }
+                            *reinterpret_cast<float4*>(o2 + 4 * i4) = make_float4(v[0], v[1], v[2], v[3]);
+                        }
+                        ++si;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) { u[i] = y[i]; ks[0][i] = ks[6][i]; }
+                    t = tn;
+                    if (P.fixed_dt <= 0.f) qold = fmaxf(ee, 1e-4f);
+                    ++nacc;
+                    if (tn >= P.tf) done = true;
+                } else {
+                    ++nrej;
+                }
+                dt = dtnew;
+                if (status == ST_OK && !done) {
+                    if (dtnew < 1e-12f) status = ST_DT_UNDERFLOW;
+                    else if (nacc + nrej >= P.max_iters) status = ST_MAXITERS;
+                }
+                if (status != ST_OK) done = true;
+            }
+        }
+        // release the MMA warp
+        cta_bar();
+        if (threadIdx.x == 0) S.stop = 1;
+        cta_bar();
         mbar_arrive(&S.bar_a);
     }
     fence_before_sync();
