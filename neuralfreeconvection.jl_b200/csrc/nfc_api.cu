@@ -138,6 +138,7 @@ int launch_solve(nfc_handle* h, SolveParams& P, cudaStream_t st, bool reset_coun
     NFC_CUDA(h, cudaGetLastError());
     if (!RECORD && h->use_tc && h->arch == ARCH_DEFAULT) {
         const int gridt = (int)std::min<long long>(h->num_sms, (B + tc::TILE - 1) / tc::TILE);
+        if (const char* e = getenv("NFC_TC_NPROD")) P.tape_cap = atoi(e);   // timing experiments only (results are wrong for < 6)
         tc::solve_tc_kernel<<<gridt, tc::NTHREADS, tc::IMG_BYTES, st>>>(h->d_wimg.p, P);
     } else {
         const int grid = (int)std::min<long long>(h->num_sms, (groups + NW - 1) / NW);

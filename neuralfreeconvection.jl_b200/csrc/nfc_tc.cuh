@@ -10,8 +10,11 @@
 //     x = x1 + x2 + x3 (8+8+8 significand bits) and the product keeps the six terms down to 2^-16:
 //     a1b1 + a1b2 + a2b1 + a2b2 + a1b3 + a3b1  (dropped terms <= 2^-24 relative) -- six kind::f16 MMAs per k-step,
 //     accumulated in fp32 in TMEM.  BF16 keeps fp32's exponent range, so no scaling is needed (weights x1e-5 are fine).
-// Thread roles: warps 0..7 = 256 "column" threads (two per ocean column: warp w and w+4 own TMEM lanes 32 (w%4)..+31,
-// half h = w/4 owns levels / units [16h,16h+16) / [64h,64h+64)), warps 8..11 = MMA warpgroup (warp 8, one elected lane, issues; the group gives its registers to the column threads with setmaxnreg).
+// Thread roles: warps 0..15 = 512 "column" threads, FOUR per ocean column: warps w, w+4, w+8, w+12 own TMEM lanes
+// 32 (w%4)..+31 and quarter q = w/4 owns levels [8q, 8q+8) and hidden units [32q, 32q+32) -- 4 column warps per SM
+// sub-partition hide the epilogue's latencies.  Warps 16..19 = MMA warpgroup (warp 16, one elected lane, issues; the
+// group hands its registers to the column threads with setmaxnreg).  The Runge-Kutta stage vectors k2..k7 of the solve
+// kernel live in the 192 tensor-memory columns the GEMMs do not use, so the ODE state costs 16 registers per thread.
 // Only the default Chain Dense(32,128,relu) -> Dense(128,128,relu) -> Dense(128,31) is instantiated here.
 #pragma once
 #include <cuda_bf16.h>
@@ -23,12 +26,13 @@ namespace tc {
 
 constexpr int TILE = 128;                 // ocean columns per CTA
 constexpr int H = 128;                    // hidden width
-constexpr int NCT = 256;                  // column threads
+constexpr int NCT = 512;                  // column threads (4 per ocean column)
 constexpr int NTHREADS = NCT + 128;       // + the MMA warpgroup (only its first warp works; a full warpgroup is needed for setmaxnreg)
-constexpr int REGS_MMA = 40, REGS_COL = 232;   // (168 - 40) * 128 freed == (232 - 168) * 256 claimed
+constexpr int REGS_MMA = 32, REGS_COL = 112;   // launch: 96/thread; (96 - 32) * 128 freed == (112 - 96) * 512 claimed
 // tensor-memory columns (32-bit cells per lane)
 constexpr int TM_D = 0;                   // accumulator, up to 128 columns
 constexpr int TM_A = 128;                 // A operand: 3 splits x 64 columns (K = 128 bf16 packed two per cell)
+constexpr int TM_K = 320;                 // k2..k7 of the ODE solve: 6 x 32 columns (level = column offset)
 constexpr int TM_COLS = 512;
 // shared-memory image (bytes): three bf16 splits of each weight matrix in UMMA K-major no-swizzle layout, then biases
 constexpr int W1_BYTES = 128 * 32 * 2;    // N = 128, K = 32
@@ -70,6 +74,16 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
         "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// same, descriptor given as (lo, hi) words: per k-step only the 14-bit address field in the low word moves
+template <bool ACC>
+__device__ __forceinline__ void mma_ts2(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi, uint32_t idesc) {
+    if (ACC)
+        asm volatile("{\n\t.reg .b64 bd;\n\t.reg .pred p;\n\tsetp.eq.u32 p, 1, 1;\n\tmov.b64 bd, {%2, %3};\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc) : "memory");
+    else
+        asm volatile("{\n\t.reg .b64 bd;\n\t.reg .pred p;\n\tsetp.ne.u32 p, 1, 1;\n\tmov.b64 bd, {%2, %3};\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], bd, %4, p;\n\t}" ::"r"(d_tmem), "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc) : "memory");
+}
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -81,13 +95,34 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr)
         : "memory");
 }
-__device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& r) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
-}
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
                  "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                  : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8f(uint32_t taddr, float (&f)[8]) {
+    uint32_t r[8];
+    tmem_ld8(taddr, r);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st8f(uint32_t taddr, const float (&f)[8]) {
+    uint32_t r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = __float_as_uint(f[i]);
+    tmem_st8(taddr, r);
+}
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t& r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr) : "memory");
 }
 
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N) {   // kind::f16: A = B = BF16 (1), C = F32 (1), both K-major
@@ -144,103 +179,118 @@ struct TcShared {
     uint64_t bar_d;        // accumulator ready (tcgen05.commit)
     uint32_t tmem_base;
     int stop;
-    float xch[2][TILE][2]; // y_15 / y_16 exchange between the two threads of a column (double buffered by evaluation parity)
-    float part[2][TILE][2];// partial error norms (double buffered)
-    int newcol[TILE];      // refill hand-off between the two threads of a column
+    int nprod;             // split products issued per k-step (6 = FP32-faithful; fewer only for timing experiments)
+    float xch[2][TILE][4][2]; // first / last level of every quarter, exchanged between the four threads of a column (double buffered)
+    float part[2][TILE][4];   // partial error norms (double buffered)
+    int newcol[TILE];         // refill hand-off between the four threads of a column
     int any;
 };
 
-// MMA issuer: all six split products of one Dense layer.  a_cols = K/2 columns per split, layer = 0,1,2
-__device__ __forceinline__ void issue_layer(uint32_t tmem_base, uint32_t smem_img, int layer) {
-    const int K = layer == 0 ? 32 : 128, Nn = layer == 2 ? 32 : 128;
-    const uint32_t woff = layer == 0 ? OFF_W1 : (layer == 1 ? OFF_W2 : OFF_W3);
-    const uint32_t wbytes = layer == 0 ? W1_BYTES : (layer == 1 ? W2_BYTES : W3_BYTES);
-    const uint32_t idesc = layer == 2 ? make_idesc(128, 32) : make_idesc(128, 128);
+// MMA issuer: all six split products of one Dense layer, fully unrolled: per MMA one 32-bit add on the descriptor's
+// address field (k-step stride 2*LBO), one add on the TMEM column, the tcgen05.mma itself.  (A first version built every
+// descriptor in a runtime loop and was issue-bound at ~98 cycles per MMA against 64 / 16 cycles of tensor-pipe time.)
+template <int LAYER>
+__device__ __forceinline__ void issue_layer(uint32_t tmem_base, uint32_t smem_img, int nprod) {
+    constexpr int K = LAYER == 0 ? 32 : 128, Nn = LAYER == 2 ? 32 : 128;
+    constexpr uint32_t woff = LAYER == 0 ? OFF_W1 : (LAYER == 1 ? OFF_W2 : OFF_W3);
+    constexpr uint32_t wbytes = LAYER == 0 ? W1_BYTES : (LAYER == 1 ? W2_BYTES : W3_BYTES);
+    constexpr uint32_t idesc = make_idesc(128, Nn);
+    constexpr uint32_t kstep = (2u * Nn * 16u) >> 4;            // descriptor address-field increment per k-step (16 elements)
     const uint32_t d = tmem_base + TM_D;
+    const uint64_t desc0 = make_bdesc(smem_img + woff, Nn);
+    const uint32_t lo0 = (uint32_t)desc0, hi0 = (uint32_t)(desc0 >> 32);
+    const uint32_t a_base = tmem_base + TM_A;
     // (a split, b split): smallest terms first so the big a1 b1 term lands on an already formed tail
-    const int sa[6] = {2, 0, 1, 1, 0, 0};
-    const int sb[6] = {0, 2, 1, 0, 1, 0};
-    uint32_t acc = 0;
-#pragma unroll 1
-    for (int p = 0; p < 6; ++p) {
-        const uint32_t a0 = tmem_base + TM_A + sa[p] * 64;
-        const uint32_t b0 = smem_img + woff + sb[p] * wbytes;
-        for (int j = 0; j < K / 16; ++j) {
-            mma_ts(d, a0 + 8 * j, make_bdesc(b0 + 2 * j * (Nn * 16), Nn), idesc, acc);
-            acc = 1;
+    constexpr int sa[6] = {2, 0, 1, 1, 0, 0};
+    constexpr int sb[6] = {0, 2, 1, 0, 1, 0};
+    if (nprod >= 6) {
+#pragma unroll
+        for (int p = 0; p < 6; ++p) {
+#pragma unroll
+            for (int j = 0; j < K / 16; ++j) {
+                const uint32_t blo = lo0 + ((sb[p] * wbytes) >> 4) + kstep * j;      // compile-time offset, no carry out of the 14-bit field
+                if (p == 0 && j == 0) mma_ts2<false>(d, a_base + sa[p] * 64 + 8 * j, blo, hi0, idesc);
+                else mma_ts2<true>(d, a_base + sa[p] * 64 + 8 * j, blo, hi0, idesc);
+            }
         }
+    } else {   // timing experiments only
+        uint32_t acc = 0;
+        for (int p = 6 - nprod; p < 6; ++p)
+            for (int j = 0; j < K / 16; ++j) { mma_ts(d, a_base + sa[p] * 64 + 8 * j, desc0 + (uint64_t)(((sb[p] * wbytes) >> 4) + kstep * j), idesc, acc); acc = 1; }
     }
 }
 
-// Column-thread side of one Chain evaluation.  y[16]: this thread's 16 levels of the stage input (level 16 h + i).
-// Returns nn[i] = NN output n = 16 h + i - 1  (i = 0..16; nn[0] of h = 0 and nn[16] of h = 1 are unused / boundary faces).
-__device__ __forceinline__ void chain_eval(TcShared* S, const float* sbias, const float (&y)[16], float (&nn)[17], int& pd, int lane, int wq, int h) {
+// Column-thread side of one Chain evaluation.  y[8]: this thread's 8 levels of the stage input (level 8 q + i).
+// Returns nn[i] = NN output n = 8 q + i - 1  (i = 0..8; nn[0] of q = 0 and nn[8] of q = 3 belong to the boundary faces).
+__device__ __forceinline__ void chain_eval(TcShared* S, const float* sbias, const float (&y)[8], float (&nn)[9], int& pd, int wq, int q) {
     const uint32_t tl = S->tmem_base + ((uint32_t)(32 * wq) << 16);     // this warp's TMEM lane window
-    // ---- layer-1 A operand: levels 16h..16h+15 -> 8 cells per split at columns 8h
+    // ---- layer-1 A operand: levels 8q..8q+7 -> 4 cells per split at columns 4q
     {
-        uint32_t p1[8], p2[8], p3[8];
+        uint32_t p1[4], p2[4], p3[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) split3(y[2 * i], y[2 * i + 1], p1[i], p2[i], p3[i]);
-        tmem_st8(tl + TM_A + 0 * 64 + 8 * h, p1);
-        tmem_st8(tl + TM_A + 1 * 64 + 8 * h, p2);
-        tmem_st8(tl + TM_A + 2 * 64 + 8 * h, p3);
+        for (int i = 0; i < 4; ++i) split3(y[2 * i], y[2 * i + 1], p1[i], p2[i], p3[i]);
+        tmem_st4(tl + TM_A + 0 * 64 + 4 * q, p1);
+        tmem_st4(tl + TM_A + 1 * 64 + 4 * q, p2);
+        tmem_st4(tl + TM_A + 2 * 64 + 4 * q, p3);
         wait_st();
         fence_before_sync();
         mbar_arrive(&S->bar_a);
     }
-    // ---- hidden layers: D -> bias, relu, split -> A operand of the next layer (units 64h .. 64h+63 -> cells 32h .. 32h+31)
+    // ---- hidden layers: D -> bias, relu, split -> A operand of the next layer (units 32q .. 32q+31 -> cells 16q .. 16q+15)
 #pragma unroll 1
     for (int l = 0; l < 2; ++l) {
         mbar_wait(&S->bar_d, pd); pd ^= 1;
         fence_after_sync();
-        const float* b = sbias + 128 * l + 64 * h;
-#pragma unroll 1
-        for (int q = 0; q < 4; ++q) {
+        const float* b = sbias + 128 * l + 32 * q;
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
             uint32_t r[16];
-            tmem_ld16(tl + TM_D + 64 * h + 16 * q, r);
+            tmem_ld16(tl + TM_D + 32 * q + 16 * ch, r);
             wait_ld();
             uint32_t p1[8], p2[8], p3[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float v0 = fmaxf(__uint_as_float(r[2 * i]) + b[16 * q + 2 * i], 0.f);
-                const float v1 = fmaxf(__uint_as_float(r[2 * i + 1]) + b[16 * q + 2 * i + 1], 0.f);
-                split3(v0, v1, p1[i], p2[i], p3[i]);
+            for (int i = 0; i < 4; ++i) {
+                const float4 bb = *reinterpret_cast<const float4*>(b + 16 * ch + 4 * i);
+                const float v0 = fmaxf(__uint_as_float(r[4 * i]) + bb.x, 0.f), v1 = fmaxf(__uint_as_float(r[4 * i + 1]) + bb.y, 0.f);
+                const float v2 = fmaxf(__uint_as_float(r[4 * i + 2]) + bb.z, 0.f), v3 = fmaxf(__uint_as_float(r[4 * i + 3]) + bb.w, 0.f);
+                split3(v0, v1, p1[2 * i], p2[2 * i], p3[2 * i]);
+                split3(v2, v3, p1[2 * i + 1], p2[2 * i + 1], p3[2 * i + 1]);
             }
-            tmem_st8(tl + TM_A + 0 * 64 + 32 * h + 8 * q, p1);
-            tmem_st8(tl + TM_A + 1 * 64 + 32 * h + 8 * q, p2);
-            tmem_st8(tl + TM_A + 2 * 64 + 32 * h + 8 * q, p3);
+            tmem_st8(tl + TM_A + 0 * 64 + 16 * q + 8 * ch, p1);
+            tmem_st8(tl + TM_A + 1 * 64 + 16 * q + 8 * ch, p2);
+            tmem_st8(tl + TM_A + 2 * 64 + 16 * q + 8 * ch, p3);
         }
         wait_st();
         fence_before_sync();
         mbar_arrive(&S->bar_a);
     }
-    // ---- output layer: NN[16h-1 .. 16h+15]
+    // ---- output layer: NN[8q-1 .. 8q+7]
     mbar_wait(&S->bar_d, pd); pd ^= 1;
     fence_after_sync();
     {
-        uint32_t r[16], r0 = 0;
-        tmem_ld16(tl + TM_D + 16 * h, r);
-        if (h) tmem_ld1(tl + TM_D + 15, r0);
+        uint32_t r[8], r0 = 0;
+        tmem_ld8(tl + TM_D + 8 * q, r);
+        if (q) tmem_ld1(tl + TM_D + 8 * q - 1, r0);
         wait_ld();
         const float* b3 = sbias + 256;
-        nn[0] = h ? __uint_as_float(r0) + b3[15] : 0.f;
+        nn[0] = q ? __uint_as_float(r0) + b3[8 * q - 1] : 0.f;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) nn[i + 1] = __uint_as_float(r[i]) + b3[16 * h + i];
+        for (int i = 0; i < 8; ++i) nn[i + 1] = __uint_as_float(r[i]) + b3[8 * q + i];
     }
     fence_before_sync();     // the next evaluation's tcgen05.st / MMA may overwrite D and A
 }
 
-
-// f (16 levels of this thread) from the Chain output and the stage input: faces k = 16h .. 16h+16,
+// f (8 levels of this thread) from the Chain output and the stage input: faces k = 8q .. 8q+8,
 // F_0 = bottom, F_32 = top, else NN[k-1] - min(0, K_CA (y_k - y_{k-1}) / dz);  f_k = -pref (F_{k+1} - F_k) / dz
-__device__ __forceinline__ void faces_to_f(const float (&y)[16], float ynb, const float (&nn)[17], float bot, float top, float kk, float pref,
-                                           int h, float (&f)[16]) {
+// ylo = y_{8q-1} (from quarter q-1), yhi = y_{8q+8} (from quarter q+1)
+__device__ __forceinline__ void faces_to_f(const float (&y)[8], float ylo, float yhi, const float (&nn)[9], float bot, float top, float kk,
+                                           float pref, int q, float (&f)[8]) {
     float Fprev = 0.f;
 #pragma unroll
-    for (int i = 0; i <= 16; ++i) {
-        const int k = 16 * h + i;
-        const float yk = i < 16 ? y[i < 16 ? i : 0] : ynb;       // level k     (i == 16 only matters for h = 0 -> y_16)
-        const float ykm = i > 0 ? y[i > 0 ? i - 1 : 0] : ynb;    // level k - 1 (i == 0  only matters for h = 1 -> y_15)
+    for (int i = 0; i <= 8; ++i) {
+        const int k = 8 * q + i;
+        const float yk = i < 8 ? y[i < 8 ? i : 0] : yhi;
+        const float ykm = i > 0 ? y[i > 0 ? i - 1 : 0] : ylo;
         float F = nn[i] - fminf(kk * (yk - ykm), 0.f);
         if (k == 0) F = bot;
         if (k == NZ) F = top;
@@ -257,7 +307,9 @@ __device__ __forceinline__ void mma_warp_loop(TcShared* S, uint32_t smem_img, in
             mbar_wait(&S->bar_a, pa); pa ^= 1;
             if (*reinterpret_cast<volatile int*>(&S->stop)) break;
             fence_after_sync();
-            issue_layer(S->tmem_base, smem_img, layer);
+            if (layer == 0) issue_layer<0>(S->tmem_base, smem_img, S->nprod);
+            else if (layer == 1) issue_layer<1>(S->tmem_base, smem_img, S->nprod);
+            else issue_layer<2>(S->tmem_base, smem_img, S->nprod);
             mma_commit(&S->bar_d);
             layer = layer == 2 ? 0 : layer + 1;
         }
@@ -266,15 +318,16 @@ __device__ __forceinline__ void mma_warp_loop(TcShared* S, uint32_t smem_img, in
 }
 
 // common prologue: barriers, TMEM allocation, weight image.  Returns after everything is visible to all threads.
-__device__ __forceinline__ void tc_prologue(TcShared* S, unsigned char* simg, const unsigned char* gimg, int warp) {
+__device__ __forceinline__ void tc_prologue(TcShared* S, unsigned char* simg, const unsigned char* gimg, int warp, int nprod = 6) {
     if (threadIdx.x == 0) {
         mbar_init(&S->bar_w, 1);
         mbar_init(&S->bar_a, NCT);
         mbar_init(&S->bar_d, 1);
         S->stop = 0;
+        S->nprod = nprod;
     }
     __syncthreads();
-    if (warp == 8) tmem_alloc(&S->tmem_base, TM_COLS);
+    if (warp == NCT / 32) tmem_alloc(&S->tmem_base, TM_COLS);
     if (threadIdx.x == 0) {
         mbar_expect_tx(&S->bar_w, IMG_BYTES);
         for (unsigned off = 0; off < (unsigned)IMG_BYTES; off += 32768u) {
@@ -300,46 +353,44 @@ rhs_tc_kernel(const unsigned char* __restrict__ gimg, const float* __restrict__ 
     const uint32_t smem_img = smem_u32(smem_raw);
     const float* sbias = reinterpret_cast<const float*>(smem_raw + OFF_B);
     const long long ntiles = (B + TILE - 1) / TILE;
-    if (warp >= 8) {
+    if (warp >= NCT / 32) {
         reg_dec<REGS_MMA>();
-        if (warp == 8) mma_warp_loop(&S, smem_img, lane);
+        if (warp == NCT / 32) mma_warp_loop(&S, smem_img, lane);
     } else {
         reg_inc<REGS_COL>();
-        const int wq = warp & 3, h = warp >> 2, c = 32 * wq + lane;
+        const int wq = warp & 3, q = warp >> 2, c = 32 * wq + lane;
         int pd = 0, xb = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const long long col = tile * TILE + c;
             const bool ok = col < B;
-            float y[16], nn[17];
+            float y[8], nn[9], f[8];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 v = ok ? *reinterpret_cast<const float4*>(T + col * NZ + 16 * h + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < 2; ++i) {
+                const float4 v = ok ? *reinterpret_cast<const float4*>(T + col * NZ + 8 * q + 4 * i) : make_float4(0.f, 0.f, 0.f, 0.f);
                 y[4 * i] = v.x; y[4 * i + 1] = v.y; y[4 * i + 2] = v.z; y[4 * i + 3] = v.w;
             }
             xb ^= 1;
-            S.xch[xb][c][h] = h ? y[0] : y[15];             // h = 0 publishes y_15, h = 1 publishes y_16
-            chain_eval(&S, sbias, y, nn, pd, lane, wq, h);  // its mbarrier traffic orders the exchange (double buffered: see TcShared)
+            S.xch[xb][c][q][0] = y[0];
+            S.xch[xb][c][q][1] = y[7];
+            chain_eval(&S, sbias, y, nn, pd, wq, q);          // its mbarrier traffic orders the exchange (double buffered)
             const float bot = ok ? colp[col * 3 + 0] : 0.f, top = ok ? colp[col * 3 + 1] : 0.f;
             const float kk = (ok && use_kca) ? colp[col * 3 + 2] * (float)NZ : 0.f;
-            float f[16];
-            faces_to_f(y, S.xch[xb][c][1 - h], nn, bot, top, kk, pref, h, f);
+            const float ylo = q > 0 ? S.xch[xb][c][q - 1][1] : 0.f, yhi = q < 3 ? S.xch[xb][c][q + 1][0] : 0.f;
+            faces_to_f(y, ylo, yhi, nn, bot, top, kk, pref, q, f);
             if (ok) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float4 o = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-                    *reinterpret_cast<float4*>(out + col * NZ + 16 * h + 4 * i) = o;
-                }
+                *reinterpret_cast<float4*>(out + col * NZ + 8 * q) = make_float4(f[0], f[1], f[2], f[3]);
+                *reinterpret_cast<float4*>(out + col * NZ + 8 * q + 4) = make_float4(f[4], f[5], f[6], f[7]);
             }
         }
         // release the MMA warp
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, 512;" ::: "memory");
         if (threadIdx.x == 0) S.stop = 1;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        asm volatile("bar.sync 1, 512;" ::: "memory");
         mbar_arrive(&S.bar_a);
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(S.tmem_base, TM_COLS);
+    if (warp == NCT / 32) tmem_dealloc(S.tmem_base, TM_COLS);
 }
 
 }  // namespace tc
@@ -355,35 +406,55 @@ rhs_tc_kernel(const unsigned char* __restrict__ gimg, const float* __restrict__ 
 namespace nfc {
 namespace tc {
 
-__device__ __forceinline__ void cta_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void cta_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+// k_j (j = 2..7) chunk of this thread in tensor memory: column TM_K + 32 (j-2) + 8 q, 8 cells
+__device__ __forceinline__ uint32_t kaddr(uint32_t tl, int j, int q) { return tl + TM_K + 32 * (j - 2) + 8 * q; }
+
+// acc[i] = sum_j coef[j] * k_j[i] over j = 1..6 (k1 in registers, k2..k6 from tensor memory)
+__device__ __forceinline__ void combine6(uint32_t tl, int q, const float (&k1)[8], const float* coef, float (&acc)[8]) {
+    float kb[8], kc[8];
+    tmem_ld8f(kaddr(tl, 2, q), kb);
+    tmem_ld8f(kaddr(tl, 3, q), kc);
+    wait_ld();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc[i] = coef[0] * k1[i]; acc[i] = fmaf(coef[1], kb[i], acc[i]); acc[i] = fmaf(coef[2], kc[i], acc[i]); }
+    tmem_ld8f(kaddr(tl, 4, q), kb);
+    tmem_ld8f(kaddr(tl, 5, q), kc);
+    wait_ld();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc[i] = fmaf(coef[3], kb[i], acc[i]); acc[i] = fmaf(coef[4], kc[i], acc[i]); }
+    tmem_ld8f(kaddr(tl, 6, q), kb);
+    wait_ld();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = fmaf(coef[5], kb[i], acc[i]);
+}
 
 __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned char* __restrict__ gimg, const SolveParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ TcShared S;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    tc_prologue(&S, smem_raw, gimg, warp);
+    tc_prologue(&S, smem_raw, gimg, warp, (P.tape_cap >= 1 && P.tape_cap <= 6) ? P.tape_cap : 6);   // tape_cap is unused by this kernel: timing knob
     const uint32_t smem_img = smem_u32(smem_raw);
     const float* sbias = reinterpret_cast<const float*>(smem_raw + OFF_B);
-    if (warp >= 8) {
+    if (warp >= NCT / 32) {
         reg_dec<REGS_MMA>();
-        if (warp == 8) mma_warp_loop(&S, smem_img, lane);
+        if (warp == NCT / 32) mma_warp_loop(&S, smem_img, lane);
     } else {
         reg_inc<REGS_COL>();
-        const int wq = warp & 3, h = warp >> 2, c = 32 * wq + lane;
+        const int wq = warp & 3, q = warp >> 2, c = 32 * wq + lane;
+        const uint32_t tl = S.tmem_base + ((uint32_t)(32 * wq) << 16);
         int pd = 0, xb = 0, pb = 0;
-        float u[16], ks[7][16], y[16];
+        float u[8], k1[8], y[8];
         int col = -1, si = 0, nacc = 0, nrej = 0, status = ST_OK;
         float t = 0.f, dt = 0.f, qold = 1e-4f, bot = 0.f, top = 0.f, kk = 0.f;
         bool queue_empty = false, done = true;       // done => slot wants a (new) column
+        const float zero8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            u[i] = 0.f;
-#pragma unroll
-            for (int j = 0; j < 7; ++j) ks[j][i] = 0.f;
-        }
+        for (int i = 0; i < 8; ++i) { u[i] = 0.f; k1[i] = 0.f; }
         while (true) {
             // ---------------- retire / refill ----------------
-            if (h == 0) {
+            if (q == 0) {
                 int nc = -2;                                    // -2: keep the current column
                 if (done) {
                     if (col >= 0) {
@@ -405,34 +476,38 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
             cta_bar();
             {
                 const int nc = S.newcol[c];
+                // tcgen05.ld/st are warp-collective: NEVER issue them under a lane-dependent branch.  k2..k7 are dead at a
+                // step boundary, so when any lane of the warp changes column the whole warp's k region is cleared
+                // (stale stage vectors meet zero tableau entries and must stay finite).
+                if (__any_sync(FULL, nc != -2)) {
+#pragma unroll
+                    for (int j = 2; j <= 7; ++j) tmem_st8f(kaddr(tl, j, q), zero8);
+                    wait_st();
+                }
                 if (nc != -2) {
                     col = nc; done = false; nacc = 0; nrej = 0; status = ST_OK; t = 0.f; qold = 1e-4f; si = 0;
-#pragma unroll
-                    for (int j = 1; j < 7; ++j)
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) ks[j][i] = 0.f;
                     if (nc >= 0) {
-                        const long long o = (long long)nc * NZ + 16 * h;
+                        const long long o = (long long)nc * NZ + 8 * q;
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
+                        for (int i = 0; i < 2; ++i) {
                             const float4 a = *reinterpret_cast<const float4*>(P.T0 + o + 4 * i), b = *reinterpret_cast<const float4*>(P.k1_init + o + 4 * i);
                             u[4 * i] = a.x; u[4 * i + 1] = a.y; u[4 * i + 2] = a.z; u[4 * i + 3] = a.w;
-                            ks[0][4 * i] = b.x; ks[0][4 * i + 1] = b.y; ks[0][4 * i + 2] = b.z; ks[0][4 * i + 3] = b.w;
+                            k1[4 * i] = b.x; k1[4 * i + 1] = b.y; k1[4 * i + 2] = b.z; k1[4 * i + 3] = b.w;
                         }
                         dt = P.dt_init[nc];
                         bot = P.colp[(long long)nc * 3 + 0]; top = P.colp[(long long)nc * 3 + 1];
                         kk = P.use_kca ? P.colp[(long long)nc * 3 + 2] * (float)NZ : 0.f;
                         while (si < P.n_save && P.saveat[si] <= 0.f) {
-                            float* o2 = P.Tout + ((long long)nc * P.n_save + si) * NZ + 16 * h;
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(o2 + 4 * i) = make_float4(u[4 * i], u[4 * i + 1], u[4 * i + 2], u[4 * i + 3]);
+                            float* o2 = P.Tout + ((long long)nc * P.n_save + si) * NZ + 8 * q;
+                            *reinterpret_cast<float4*>(o2) = make_float4(u[0], u[1], u[2], u[3]);
+                            *reinterpret_cast<float4*>(o2 + 4) = make_float4(u[4], u[5], u[6], u[7]);
                             ++si;
                         }
                     } else {
                         queue_empty = true;
                         dt = 0.f; bot = 0.f; top = 0.f; kk = 0.f;
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) { u[i] = 0.f; ks[0][i] = 0.f; }
+                        for (int i = 0; i < 8; ++i) { u[i] = 0.f; k1[i] = 0.f; }
                     }
                 }
                 if (col >= 0) S.any = 1;
@@ -446,57 +521,66 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
                 hs = fminf(dt, P.tf - t);
                 if (t + hs >= P.tf * (1.0f - 1e-6f)) { hs = P.tf - t; last = true; }
             }
+            float k7[8];
 #pragma unroll 1
             for (int s = 0; s < 6; ++s) {
-                const float a0 = c_tsit5_a[s][0], a1 = c_tsit5_a[s][1], a2 = c_tsit5_a[s][2], a3 = c_tsit5_a[s][3], a4 = c_tsit5_a[s][4], a5 = c_tsit5_a[s][5];
+                float acc[8];
+                combine6(tl, q, k1, c_tsit5_a[s], acc);
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float acc = a0 * ks[0][i];
-                    acc = fmaf(a1, ks[1][i], acc); acc = fmaf(a2, ks[2][i], acc); acc = fmaf(a3, ks[3][i], acc);
-                    acc = fmaf(a4, ks[4][i], acc); acc = fmaf(a5, ks[5][i], acc);
-                    y[i] = fmaf(hs, acc, u[i]);
-                }
+                for (int i = 0; i < 8; ++i) y[i] = fmaf(hs, acc[i], u[i]);
                 xb ^= 1;
-                S.xch[xb][c][h] = h ? y[0] : y[15];
-                float nn[17], f[16];
-                chain_eval(&S, sbias, y, nn, pd, lane, wq, h);
-                faces_to_f(y, S.xch[xb][c][1 - h], nn, bot, top, kk, P.pref, h, f);
+                S.xch[xb][c][q][0] = y[0];
+                S.xch[xb][c][q][1] = y[7];
+                float nn[9], f[8];
+                chain_eval(&S, sbias, y, nn, pd, wq, q);
+                const float ylo = q > 0 ? S.xch[xb][c][q - 1][1] : 0.f, yhi = q < 3 ? S.xch[xb][c][q + 1][0] : 0.f;
+                faces_to_f(y, ylo, yhi, nn, bot, top, kk, P.pref, q, f);
+                tmem_st8f(kaddr(tl, s + 2, q), f);
+                wait_st();
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    if (s == 0) ks[1][i] = f[i];
-                    else if (s == 1) ks[2][i] = f[i];
-                    else if (s == 2) ks[3][i] = f[i];
-                    else if (s == 3) ks[4][i] = f[i];
-                    else if (s == 4) ks[5][i] = f[i];
-                    else ks[6][i] = f[i];
-                }
+                for (int i = 0; i < 8; ++i) k7[i] = f[i];          // after s == 5 this is k7 = f(u_new) (FSAL)
             }
-            // y == u_new, ks[6] == f(u_new)
+            // y == u_new, k7 == f(u_new); error estimate = h * sum btilde_j k_j
             float part = 0.f;
+            {
+                const float bt[6] = {NFC_BT1, NFC_BT2, NFC_BT3, NFC_BT4, NFC_BT5, NFC_BT6};
+                float e[8];
+                combine6(tl, q, k1, bt, e);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                float e = NFC_BT1 * ks[0][i];
-                e = fmaf(NFC_BT2, ks[1][i], e); e = fmaf(NFC_BT3, ks[2][i], e); e = fmaf(NFC_BT4, ks[3][i], e);
-                e = fmaf(NFC_BT5, ks[4][i], e); e = fmaf(NFC_BT6, ks[5][i], e); e = fmaf(NFC_BT7, ks[6][i], e);
-                e *= hs;
-                const float r = e / (P.abstol + fmaxf(fabsf(u[i]), fabsf(y[i])) * P.reltol);
-                part = fmaf(r, r, part);
+                for (int i = 0; i < 8; ++i) {
+                    const float ei = fmaf(NFC_BT7, k7[i], e[i]) * hs;
+                    const float r = ei / (P.abstol + fmaxf(fabsf(u[i]), fabsf(y[i])) * P.reltol);
+                    part = fmaf(r, r, part);
+                }
             }
             pb ^= 1;
-            S.part[pb][c][h] = part;
+            S.part[pb][c][q] = part;
+            // dense output in power basis, u(t + th h) = u + h th (k1 + th (c2 + th (c3 + th c4))): computed by the whole warp
+            // (tensor-memory loads are warp-collective), consumed below under lane-divergent control flow
+            float c2[8], c3[8], c4[8];
+            {
+                const float r2[6] = {-2.763706197274826f, 0.13169999999999998f, 3.9302962368947516f, -12.411077166933676f, 37.50931341651104f, -27.896526289197286f};
+                const float r3[6] = {2.9132554618219126f, -0.2234f, -5.941033872131505f, 30.33818863028232f, -88.1789048947664f, 65.09189467479366f};
+                const float r4[6] = {-1.0530884977290216f, 0.1017f, 2.490627285651253f, -16.548102889244902f, 47.37952196281928f, -34.87065786149661f};
+                combine6(tl, q, k1, r2, c2);
+                combine6(tl, q, k1, r3, c3);
+                combine6(tl, q, k1, r4, c4);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { c2[i] = fmaf(1.5f, k7[i], c2[i]); c3[i] = fmaf(-4.0f, k7[i], c3[i]); c4[i] = fmaf(2.5f, k7[i], c4[i]); }
+            }
             cta_bar();
             if (col >= 0) {
-                const float ee = sqrtf((S.part[pb][c][0] + S.part[pb][c][1]) * (1.f / NZ));    // same order in both threads of the column
+                const float ee = sqrtf(((S.part[pb][c][0] + S.part[pb][c][1]) + (S.part[pb][c][2] + S.part[pb][c][3])) * (1.f / NZ));
                 bool accept;
                 float dtnew;
                 if (!isfinite(ee)) { status = ST_NAN; accept = false; dtnew = hs; }
                 else if (P.fixed_dt > 0.f) { accept = true; dtnew = P.fixed_dt; }
                 else {
                     const float q11 = powf(ee, 0.14f);
-                    float q = q11 / powf(qold, 0.08f);
-                    q = fmaxf(0.1f, fminf(5.0f, q / 0.9f));
+                    float qq = q11 / powf(qold, 0.08f);
+                    qq = fmaxf(0.1f, fminf(5.0f, qq / 0.9f));
                     accept = ee <= 1.0f;
-                    dtnew = accept ? hs / q : hs / fminf(5.0f, q11 / 0.9f);
+                    dtnew = accept ? hs / qq : hs / fminf(5.0f, q11 / 0.9f);
                 }
                 if (accept) {
                     const float tn = last ? P.tf : t + hs;
@@ -504,26 +588,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
                         const float ts = P.saveat[si];
                         if (ts > tn) break;
                         const float th = fminf((ts - t) / hs, 1.0f);
-                        float b[7];
-                        tsit5_btheta(th, b);
-                        float* o2 = P.Tout + ((long long)col * P.n_save + si) * NZ + 16 * h;
+                        float* o2 = P.Tout + ((long long)col * P.n_save + si) * NZ + 8 * q;
+                        float v[8];
 #pragma unroll
-                        for (int i4 = 0; i4 < 4; ++i4) {
-                            float v[4];
-#pragma unroll
-                            for (int m = 0; m < 4; ++m) {
-                                const int i = 4 * i4 + m;
-                                float inc = b[0] * ks[0][i];
-                                inc = fmaf(b[1], ks[1][i], inc); inc = fmaf(b[2], ks[2][i], inc); inc = fmaf(b[3], ks[3][i], inc);
-                                inc = fmaf(b[4], ks[4][i], inc); inc = fmaf(b[5], ks[5][i], inc); inc = fmaf(b[6], ks[6][i], inc);
-                                v[m] = fmaf(hs, inc, u[i]);
-                            }
-                            *reinterpret_cast<float4*>(o2 + 4 * i4) = make_float4(v[0], v[1], v[2], v[3]);
-                        }
+                        for (int i = 0; i < 8; ++i) v[i] = fmaf(hs, th * fmaf(th, fmaf(th, fmaf(th, c4[i], c3[i]), c2[i]), k1[i]), u[i]);
+                        *reinterpret_cast<float4*>(o2) = make_float4(v[0], v[1], v[2], v[3]);
+                        *reinterpret_cast<float4*>(o2 + 4) = make_float4(v[4], v[5], v[6], v[7]);
                         ++si;
                     }
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) { u[i] = y[i]; ks[0][i] = ks[6][i]; }
+                    for (int i = 0; i < 8; ++i) { u[i] = y[i]; k1[i] = k7[i]; }
                     t = tn;
                     if (P.fixed_dt <= 0.f) qold = fmaxf(ee, 1e-4f);
                     ++nacc;
@@ -547,7 +621,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 8) tmem_dealloc(S.tmem_base, TM_COLS);
+    if (warp == NCT / 32) tmem_dealloc(S.tmem_base, TM_COLS);
 }
 
 }  // namespace tc
