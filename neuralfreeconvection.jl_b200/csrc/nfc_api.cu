@@ -131,6 +131,26 @@ int launch_solve(nfc_handle* h, SolveParams& P, cudaStream_t st, bool reset_coun
         NFC_CUDA(h, cudaMemsetAsync(h->d_counters.p + CTR_ADJ_QUEUE, 0, sizeof(unsigned long long), st));
     }
     NFC_CUDA(h, cudaEventRecord(h->ev[0], st));
+    // Schedule: columns that took the most steps in the previous call of this batch size go first, so the queue drains with short
+    // columns and the persistent CTAs finish together (the same columns are re-solved every epoch).  Results do not depend on it.
+    P.order = nullptr; P.work = nullptr;
+    if (!RECORD && h->use_sched && B >= 4096) {
+        NFC_CUDA(h, h->d_work.ensure((size_t)B));
+        NFC_CUDA(h, h->d_order.ensure((size_t)B));
+        NFC_CUDA(h, h->d_hist.ensure(SCHED_BUCKETS));
+        if (h->sched_B == B) {
+            NFC_CUDA(h, cudaMemsetAsync(h->d_hist.p, 0, sizeof(int) * SCHED_BUCKETS, st));
+            const int nb = (int)((B + 255) / 256);
+            sched_hist_kernel<<<nb, 256, 0, st>>>(h->d_work.p, h->d_hist.p, B);
+            sched_scan_kernel<<<1, SCHED_BUCKETS, 0, st>>>(h->d_hist.p);
+            sched_scatter_kernel<<<nb, 256, 0, st>>>(h->d_work.p, h->d_hist.p, h->d_order.p, B);
+            NFC_CUDA(h, cudaGetLastError());
+            P.order = h->d_order.p;
+            h->last_launches += 3;
+        }
+        P.work = h->d_work.p;
+        h->sched_B = B;
+    }
     const long long groups = (B + CPW - 1) / CPW;
     const int grid0 = (int)std::min<long long>(h->num_sms, (groups + NW - 1) / NW);
     rhs_init_kernel<N, WS, 1><<<grid0, NW * 32, smem_bytes<N>(NW), st>>>(h->d_wpack.p, P.T0, P.colp, h->d_k1.p, h->d_dt.p, B, P.pref, P.use_kca,
@@ -273,8 +293,9 @@ int32_t nfc_create(const nfc_config* cfg, nfc_handle** out) {
         if (h->d_wimg.ensure(tc::IMG_BYTES)) { h->err = "cudaMalloc failed"; return bail(-10); }
         if (cudaFuncSetAttribute(tc::rhs_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::IMG_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(tc::solve_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::IMG_BYTES) != cudaSuccess) { h->err = "cudaFuncSetAttribute(tc) failed"; return bail(-10); }
-        const char* e = getenv("NFC_TC");
-        h->use_tc = e && atoi(e) != 0;
+        if (const char* e2 = getenv("NFC_SCHED")) h->use_sched = atoi(e2) != 0;
+        const char* e = getenv("NFC_TC");          // tensor-core forward path is the default for this Chain; NFC_TC=0 selects the SIMT kernels
+        h->use_tc = !(e && atoi(e) == 0);
     }
     if (h->d_theta.ensure(h->n_params) || h->d_wpack.ensure(h->n_packed) || h->d_saveat.ensure(h->saveat.size()) ||
         h->d_counters.ensure(CTR_COUNT)) { h->err = "cudaMalloc failed"; return bail(-10); }
@@ -288,7 +309,7 @@ int32_t nfc_destroy(nfc_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    h->d_wimg.release(); h->d_theta.release(); h->d_wpack.release(); h->d_saveat.release(); h->d_k1.release(); h->d_dt.release(); h->d_counters.release();
+    h->d_work.release(); h->d_order.release(); h->d_hist.release(); h->d_wimg.release(); h->d_theta.release(); h->d_wpack.release(); h->d_saveat.release(); h->d_k1.release(); h->d_dt.release(); h->d_counters.release();
     h->s_T0.release(); h->s_colp.release(); h->s_out.release(); h->s_true.release(); h->s_grad.release();
     h->s_nacc.release(); h->s_nrej.release(); h->s_status.release(); h->s_loss.release();
     h->a_resid.release(); h->a_tape.release(); h->a_gacc.release(); h->a_tlen.release(); h->a_gsum.release();

@@ -21,6 +21,8 @@ struct SolveParams {
     const float* k1_init;      // [B][32]  f(u0)
     const float* dt_init;      // [B]
     const float* saveat;       // [n_save]
+    const int* order;          // [B] queue position -> column (longest-first schedule from the previous call) or null
+    int* work;                 // [B] attempted steps per column of THIS call (feeds the next call's schedule) or null
     float* Tout;               // [B][n_save][32]
     int* naccept;              // [B] (may be null)
     int* nreject;
@@ -196,6 +198,7 @@ __device__ __forceinline__ void fill_slot(const SolveParams& P, WarpSlots* sl, i
     if (lane == 0) next = (long long)atomicAdd(&P.counters[CTR_QUEUE], 1ULL);
     next = __shfl_sync(FULL, next, 0);
     if (next < P.B) {
+        if (P.order) next = P.order[next];
         u = P.T0[next * NZ + lane];
         k1 = P.k1_init[next * NZ + lane];
         int si = 0;
@@ -363,6 +366,7 @@ __global__ void __launch_bounds__(NW * 32, 1) solve_kernel(const SolveParams P) 
                     if (P.naccept) P.naccept[col] = sl->nacc[c];
                     if (P.nreject) P.nreject[col] = sl->nrej[c];
                     if (P.status) P.status[col] = sl->status[c];
+                    if (P.work) P.work[col] = sl->nacc[c] + sl->nrej[c];
                     if (RECORD) P.tape_len[col] = sl->tlen[c] < P.tape_cap ? sl->tlen[c] : P.tape_cap;
                     atomicAdd(&P.counters[CTR_ACCEPT], (unsigned long long)sl->nacc[c]);
                     atomicAdd(&P.counters[CTR_REJECT], (unsigned long long)sl->nrej[c]);
@@ -376,6 +380,25 @@ __global__ void __launch_bounds__(NW * 32, 1) solve_kernel(const SolveParams P) 
         __syncwarp();
     }
     if (RECORD && lane == 0) atomicAdd(P.loss_sum, lsum);
+}
+
+// ---- longest-first schedule from the previous call's per-column step counts (counting sort, 1024 buckets, descending) ----
+constexpr int SCHED_BUCKETS = 1024;
+__global__ void sched_hist_kernel(const int* __restrict__ work, int* __restrict__ hist, long long B) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) atomicAdd(&hist[min(max(work[i], 0), SCHED_BUCKETS - 1)], 1);
+}
+__global__ void sched_scan_kernel(int* __restrict__ hist) {   // in place: hist[b] = number of columns in longer buckets (b' > b)
+    __shared__ int s[SCHED_BUCKETS];
+    const int t = threadIdx.x;
+    s[t] = hist[SCHED_BUCKETS - 1 - t];
+    __syncthreads();
+    for (int off = 1; off < SCHED_BUCKETS; off <<= 1) { const int v = t >= off ? s[t - off] : 0; __syncthreads(); s[t] += v; __syncthreads(); }
+    hist[SCHED_BUCKETS - 1 - t] = t ? s[t - 1] : 0;
+}
+__global__ void sched_scatter_kernel(const int* __restrict__ work, int* __restrict__ hist, int* __restrict__ order, long long B) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) order[atomicAdd(&hist[min(max(work[i], 0), SCHED_BUCKETS - 1)], 1)] = (int)i;
 }
 
 // Flux diagnosis epilogue of solve_nde(ds, ...) (src/solve.jl:32-48): wT[n] = [bottom; NN(T_n); top] - min(0, K_CA dT/dz)

@@ -43,6 +43,10 @@ struct nfc_handle {
     nfc::DevBuf<float> d_theta, d_wpack, d_saveat, d_k1, d_dt;
     nfc::DevBuf<unsigned char> d_wimg;      // tensor-core weight image (default Chain only)
     bool use_tc = false;
+    // longest-first scheduling: per-column attempted steps of the previous forward call with the same batch size
+    nfc::DevBuf<int> d_work, d_order, d_hist;
+    int64_t sched_B = -1;       // batch size d_work is valid for (-1: none)
+    bool use_sched = true;
     nfc::DevBuf<unsigned long long> d_counters;
     // host-call staging
     nfc::DevBuf<float> s_T0, s_colp, s_out, s_true, s_grad;

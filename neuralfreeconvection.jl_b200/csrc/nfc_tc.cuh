@@ -461,13 +461,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
                         if (P.naccept) P.naccept[col] = nacc;
                         if (P.nreject) P.nreject[col] = nrej;
                         if (P.status) P.status[col] = status;
+                        if (P.work) P.work[col] = nacc + nrej;
                         atomicAdd(&P.counters[CTR_ACCEPT], (unsigned long long)nacc);
                         atomicAdd(&P.counters[CTR_REJECT], (unsigned long long)nrej);
                     }
                     nc = -1;
                     if (!queue_empty) {
                         const long long nx = (long long)atomicAdd(&P.counters[CTR_QUEUE], 1ULL);
-                        if (nx < P.B) nc = (int)nx; else queue_empty = true;
+                        if (nx < P.B) nc = P.order ? P.order[nx] : (int)nx; else queue_empty = true;
                     }
                 }
                 S.newcol[c] = nc;

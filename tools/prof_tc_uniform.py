@@ -1,0 +1,17 @@
+import os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import nfc_b200
+syn = nfc_b200.synthetic
+NN = nfc_b200.named_chain("dense-default", seed=0)
+for p in NN.params(): p *= 1e-5
+theta, _ = nfc_b200.destructure(NN)
+dev = torch.device("cuda:0")
+B = 148 * 128
+d = syn.make_columns("ocean", B=B, seed=1)
+T0, colp = torch.from_numpy(d["T0"]).to(dev), torch.from_numpy(d["colp"]).to(dev)
+Tout = torch.empty((B, 2, 32), device=dev); st = torch.zeros(B, dtype=torch.int32, device=dev)
+h = nfc_b200.Handle(NN.conv_width, NN.dense_spec, 1, syn.saveat(2), fixed_dt=1 / 64); h.set_weights(theta)
+for i in range(2):
+    h.solve_dev(T0, colp, d["glob"], Tout, None, None, st); c = h.counters()
+print(c["last_kernel_ms"], flush=True)
