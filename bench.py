@@ -241,6 +241,34 @@ def main():
                     "peak_source": "measured in this run: pure-FFMA kernel in libnfc_b200 (nominal 148x128x2x1.965GHz = 74.4)",
                     "flops_per_column_step": FLOPS_PER_COLUMN_STEP, "kernel": "solve_kernel (+ rhs_init_kernel)", "kernel_ms": kernel_ms, "hbm": hbm}
 
+    # ---------------- second BASELINE metric: adjoint gradient, seconds per epoch ----------------
+    # epoch = one loss + gradient over the batch (src/training.jl:45-48,70): (a) BASELINE config 3, the 9 training simulations;
+    # (b) a 16384-column batch of the config-2 distribution (what a GPU-sized training set costs)
+    adjoint = None
+    if world == 1:
+        try:
+            syn = nfc_b200.synthetic
+            adjoint = {}
+            for tag, dd in (("config3_9sims", syn.make_columns("training9")), ("ocean_16384", syn.make_columns("ocean", B=16384, seed=2))):
+                nb = dd["T0"].shape[0]
+                Tt = torch.from_numpy(np.repeat(dd["T0"][:, None, :], N_SAVE, axis=1) * np.float32(0.98)).to(dev)
+                a0, ac = torch.from_numpy(dd["T0"]).to(dev), torch.from_numpy(dd["colp"]).to(dev)
+                g = torch.empty(h.n_params, device=dev)
+                ls = torch.zeros(2, dtype=torch.float64, device=dev)
+                sta = torch.zeros(nb, dtype=torch.int32, device=dev)
+                for it in range(3):
+                    torch.cuda.synchronize()
+                    t0 = time.perf_counter()
+                    h.loss_grad_dev(a0, ac, dd["glob"], Tt, ls, g, sta, n_total_columns=nb, stream=stream)
+                    torch.cuda.synchronize()
+                    dt_ = time.perf_counter() - t0
+                ca = h.counters()
+                adjoint[tag] = {"sec_per_epoch": dt_, "columns": nb, "fwd_column_steps": ca["steps_accepted"] + ca["steps_rejected"],
+                                "adjoint_column_steps": ca["adj_steps_accepted"] + ca["adj_steps_rejected"], "device_ms": ca["last_adjoint_ms"],
+                                "adjoint_column_steps_per_sec": (ca["adj_steps_accepted"] + ca["adj_steps_rejected"]) / max(ca["last_adjoint_ms"] * 1e-3, 1e-9)}
+        except Exception as e:                                     # the forward metric must not die with the extra one
+            adjoint = {"error": str(e)}
+
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -255,7 +283,7 @@ def main():
             "config": {"workload": WORKLOAD, "kernel_path": "tcgen05" if use_tc else "simt", "columns_per_gpu": B, "column_steps_per_pass_rank0": steps_per_pass,
                        "l2": "outputs (1.08 GB/step) exceed the 126 MB L2; no explicit flush", "parallelism": f"columns sharded x{world}, no collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(cnt["kernel_launches"]) * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline}
+            "gpu_launches": int(cnt["kernel_launches"]) * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "adjoint": adjoint}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

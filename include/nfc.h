@@ -65,7 +65,7 @@ typedef struct nfc_config {
     int32_t n_save;                               /* length(saveat) */
     const float* saveat;                          /* [n_save] ascending, saveat[0] = t0 = 0, saveat[n_save-1] = tf */
     int32_t device;                               /* CUDA device ordinal */
-    int32_t adjoint_max_steps;                    /* tape capacity per column for nfc_loss_grad (0 = default 1024) */
+    int32_t adjoint_max_steps;                    /* accepted forward steps kept per column for nfc_loss_grad (0 = default 512; overflow -> status 4) */
     float adjoint_reltol;                         /* 0 = reltol */
     float adjoint_abstol;                         /* 0 = abstol */
     int32_t reserved[8];
@@ -111,6 +111,8 @@ int32_t nfc_loss_grad_dev(nfc_handle* h, const float* T0, const float* colp, con
                           double* loss_sum_dev, float* grad_dev, int32_t* status, int64_t B, int64_t n_total_columns,
                           void* stream);
 int32_t nfc_sync(nfc_handle* h);
+/* diagnostics: attempted backward (adjoint) steps per column of the last nfc_loss_grad chunk (the analogue of naccept + nreject) */
+int32_t nfc_get_adjoint_steps(nfc_handle* h, int32_t* out, int64_t n);
 
 /* Roofline denominator for this path: sustained FP32 FMA throughput of `device`, measured with a
  * pure-FFMA kernel (16 independent chains per thread, full occupancy) over ~`ms_target` milliseconds. */

@@ -13,7 +13,7 @@ NFC_MAX_LAYERS = 8
 
 EXPORTS = ["nfc_create", "nfc_destroy", "nfc_last_error", "nfc_n_params", "nfc_set_weights", "nfc_set_saveat",
            "nfc_get_counters", "nfc_rhs", "nfc_solve", "nfc_diagnose_flux", "nfc_loss_grad", "nfc_rhs_dev",
-           "nfc_solve_dev", "nfc_loss_grad_dev", "nfc_sync", "nfc_measure_fp32_peak"]
+           "nfc_solve_dev", "nfc_loss_grad_dev", "nfc_sync", "nfc_measure_fp32_peak", "nfc_get_adjoint_steps"]
 
 
 class NfcConfig(C.Structure):
@@ -60,6 +60,7 @@ def load():
     lib.nfc_solve_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int64, vp]
     lib.nfc_loss_grad_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int64, vp]
     lib.nfc_sync.argtypes = [vp]
+    lib.nfc_get_adjoint_steps.argtypes = [vp, ip, C.c_int64]
     lib.nfc_measure_fp32_peak.argtypes = [C.c_int32, C.c_float, dp]
     for name in EXPORTS:
         if name not in ("nfc_last_error", "nfc_n_params"):
@@ -221,6 +222,11 @@ class Handle:
                                                status.data_ptr() if status is not None else None, B,
                                                n_total_columns if n_total_columns is not None else B, stream),
                     "nfc_loss_grad_dev")
+
+    def adjoint_steps(self, n):
+        out = np.zeros(n, dtype=np.int32)
+        self._check(self.lib.nfc_get_adjoint_steps(self.h, _ip(out), n), "nfc_get_adjoint_steps")
+        return out
 
     def sync(self):
         self._check(self.lib.nfc_sync(self.h), "nfc_sync")

@@ -39,7 +39,9 @@ struct AdjParams {
     const float* resid;         // [B][n_save][32]
     const float* tape;          // [B][tape_cap][TAPE_STRIDE]
     const int* tape_len;        // [B]
+    const int* order;           // [B] queue position -> column, longest forward solve first (or null)
     int* status;                // [B] forward status in, adjoint failures merged in
+    int* adj_steps;             // [B] attempted backward steps per column (diagnostics) or null
     float* gacc;                // [gridDim.x][n_params]  per-CTA accumulators, Flux theta layout
     unsigned long long* counters;
     long long B;
@@ -238,6 +240,7 @@ __device__ __forceinline__ bool adj_fill_slot(const AdjParams& P, AdjSlots* sl, 
             if (lane == 0) { sl->col[c] = -1; sl->h[c] = 0.f; sl->t[c] = 0.f; sl->tstop[c] = 0.f; sl->kca[c] = 0.f; sl->flag[c] = 0; sl->mode[c] = 0; sl->tlen[c] = 0; sl->ipos[c] = 0; }
             return false;
         }
+        if (P.order) next = P.order[next];
         const int len = P.tape_len[next];
         const int st = P.status ? P.status[next] : 0;
         if (st != ST_OK || len <= 0 || P.n_save < 2) continue;      // nothing to differentiate (or forward failed: reported in status[])
@@ -486,6 +489,7 @@ __global__ void __launch_bounds__(ADJ_NW * 32, 1) adjoint_kernel(const AdjParams
                 if (lane == 0) {
                     const int col = sl->col[c];
                     if (sl->status[c] != ST_OK && P.status) P.status[col] = sl->status[c];
+                    if (P.adj_steps) P.adj_steps[col] = sl->nacc[c] + sl->nrej[c];
                     atomicAdd(&P.counters[CTR_ADJ_ACCEPT], (unsigned long long)sl->nacc[c]);
                     atomicAdd(&P.counters[CTR_ADJ_REJECT], (unsigned long long)sl->nrej[c]);
                 }
@@ -534,8 +538,8 @@ int adjoint_loss_grad(nfc_handle* h, const float* T0, const float* colp, float p
         NFC_CUDA(h, cudaMemsetAsync(grad_dev, 0, sizeof(float) * h->n_params, st));
         return 0;
     }
-    // chunk the batch so that tape + residuals stay inside the scratch budget (default 16 GiB, NFC_TAPE_GIB overrides)
-    double budget = 16.0;
+    // chunk the batch so that tape + residuals stay inside the scratch budget (default 48 GiB of the 180 GB, NFC_TAPE_GIB overrides)
+    double budget = 48.0;
     if (const char* e = getenv("NFC_TAPE_GIB")) budget = atof(e) > 0 ? atof(e) : budget;
     const size_t per_col = sizeof(float) * ((size_t)cap * TAPE_STRIDE + (size_t)n_save * NZ);
     int64_t chunk = (int64_t)(budget * 1073741824.0 / (double)per_col);
@@ -555,7 +559,26 @@ int adjoint_loss_grad(nfc_handle* h, const float* T0, const float* colp, float p
         P.Ttrue = Ttrue + off * (int64_t)n_save * NZ; P.resid = h->a_resid.p; P.tape = h->a_tape.p; P.tape_len = h->a_tlen.p;
         P.loss_sum = loss_sum_dev; P.tape_cap = cap;
         if (int rc = nfc_launch_record<N>(h, P, st, first)) return rc;
+        // backward queue: columns with the longest forward solves first (their backward solves are the longest too)
+        const int* order = nullptr;
+        if (h->use_sched && nb >= 2048) {
+            NFC_CUDA(h, h->d_order.ensure((size_t)nb));
+            NFC_CUDA(h, h->d_hist.ensure(SCHED_BUCKETS));
+            NFC_CUDA(h, cudaMemsetAsync(h->d_hist.p, 0, sizeof(int) * SCHED_BUCKETS, st));
+            const int nblk = (int)((nb + 255) / 256);
+            sched_hist_kernel<<<nblk, 256, 0, st>>>(h->a_tlen.p, h->d_hist.p, nb);
+            sched_scan_kernel<<<1, SCHED_BUCKETS, 0, st>>>(h->d_hist.p);
+            sched_scatter_kernel<<<nblk, 256, 0, st>>>(h->a_tlen.p, h->d_hist.p, h->d_order.p, nb);
+            NFC_CUDA(h, cudaGetLastError());
+            order = h->d_order.p;
+            h->last_launches += 3;
+        }
         AdjParams A{};
+        A.order = order;
+        NFC_CUDA(h, h->a_adjsteps.ensure((size_t)nb));
+        NFC_CUDA(h, cudaMemsetAsync(h->a_adjsteps.p, 0, sizeof(int) * nb, st));
+        A.adj_steps = h->a_adjsteps.p;
+        h->a_adjsteps_n = nb;
         A.wpack = h->d_wpack.p; A.colp = colp + off * 3; A.saveat = h->d_saveat.p; A.resid = h->a_resid.p; A.tape = h->a_tape.p;
         A.tape_len = h->a_tlen.p; A.status = st_all + off; A.gacc = h->a_gacc.p; A.counters = h->d_counters.p; A.B = nb; A.n_save = n_save;
         A.tape_cap = cap; A.max_iters = h->cfg.max_iters; A.use_kca = h->cfg.nde_type == NFC_NDE_CONVECTIVE_ADJUSTMENT; A.n_params = (int)h->n_params;

@@ -275,7 +275,7 @@ int32_t nfc_create(const nfc_config* cfg, nfc_handle** out) {
     nfc_handle* h = new nfc_handle();
     h->cfg = *cfg;
     if (h->cfg.max_iters <= 0) h->cfg.max_iters = 100000;
-    if (h->cfg.adjoint_max_steps <= 0) h->cfg.adjoint_max_steps = 1024;
+    if (h->cfg.adjoint_max_steps <= 0) h->cfg.adjoint_max_steps = 512;
     if (!(h->cfg.adjoint_reltol > 0.f)) h->cfg.adjoint_reltol = h->cfg.reltol;
     if (!(h->cfg.adjoint_abstol > 0.f)) h->cfg.adjoint_abstol = h->cfg.abstol;
     h->saveat.assign(cfg->saveat, cfg->saveat + cfg->n_save);
@@ -312,7 +312,7 @@ int32_t nfc_destroy(nfc_handle* h) {
     h->d_work.release(); h->d_order.release(); h->d_hist.release(); h->d_wimg.release(); h->d_theta.release(); h->d_wpack.release(); h->d_saveat.release(); h->d_k1.release(); h->d_dt.release(); h->d_counters.release();
     h->s_T0.release(); h->s_colp.release(); h->s_out.release(); h->s_true.release(); h->s_grad.release();
     h->s_nacc.release(); h->s_nrej.release(); h->s_status.release(); h->s_loss.release();
-    h->a_resid.release(); h->a_tape.release(); h->a_gacc.release(); h->a_tlen.release(); h->a_gsum.release();
+    h->a_resid.release(); h->a_tape.release(); h->a_gacc.release(); h->a_tlen.release(); h->a_adjsteps.release(); h->a_gsum.release();
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
@@ -346,6 +346,15 @@ int32_t nfc_set_saveat(nfc_handle* h, const float* saveat, int32_t n_save) {
     h->cfg.n_save = n_save;
     NFC_CUDA(h, h->d_saveat.ensure(n_save));
     NFC_CUDA(h, cudaMemcpy(h->d_saveat.p, saveat, sizeof(float) * n_save, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+int32_t nfc_get_adjoint_steps(nfc_handle* h, int32_t* out, int64_t n) {
+    if (!h || !out) return -1;
+    NFC_CUDA(h, cudaSetDevice(h->device));
+    NFC_CUDA(h, cudaDeviceSynchronize());
+    if (n > h->a_adjsteps_n) return fail(h, -2, "only %lld columns in the last loss_grad chunk", (long long)h->a_adjsteps_n);
+    NFC_CUDA(h, cudaMemcpy(out, h->a_adjsteps.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
     return 0;
 }
 

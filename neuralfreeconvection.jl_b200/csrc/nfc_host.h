@@ -54,7 +54,8 @@ struct nfc_handle {
     nfc::DevBuf<double> s_loss;
     // adjoint scratch
     nfc::DevBuf<float> a_resid, a_tape, a_gacc;
-    nfc::DevBuf<int> a_tlen;
+    nfc::DevBuf<int> a_tlen, a_adjsteps;
+    int64_t a_adjsteps_n = 0;
     nfc::DevBuf<double> a_gsum;
     int64_t last_columns = 0, last_launches = 0;
     std::string err;
