@@ -12,8 +12,8 @@
 //            at u(t_s) and back-propagates lam_s through the Chain (warp-private, transposed products read the SAME
 //            padded weight copy as the forward pass); the weight-gradient contraction  dW_l += delta_l a_{l-1}^T
 //            runs CTA-wide over all 64 columns (quadrature weight h*b_s folded into delta), so every accumulator
-//            is touched once per 64 outer products.  Accumulators are per-CTA, plain (atomic-free) read-modify-write
-//            in L2; a last kernel reduces them over CTAs in double.
+//            is touched once per 64 outer products.  Accumulators are per-CTA (no contention), updated with
+//            fire-and-forget RED.ADD.F32 in L2; a last kernel reduces them over CTAs in double.
 //            A rejected backward step is undone by replaying it with weight -h*b_s ("cancel" pass), so the
 //            quadrature never needs per-column gradient storage.
 //
@@ -172,9 +172,11 @@ __device__ __forceinline__ void dense_T_last(const float* __restrict__ W, const 
 // ---- CTA-wide weight-gradient contraction: gW[k][n] += sum over the CTA's 64 columns of A[k][c] * D[n][c] -----------------
 // A / D are the per-warp [rows][8] buffers (warp w's copy at +w*WSTRIDE).  256 threads = 16 x 16 register tiles, rows interleaved
 // (k = TK + 16 i, n = TN + 16 j) so that the LDS.128 of a warp hit distinct banks.  gW is this CTA's private accumulator
-// (row-major [KROWS][NCOLS] == Flux's column-major out x in), updated by plain read-modify-write.
+// (row-major [KROWS][NCOLS] == Flux's column-major out x in), updated with no-return reductions (RED.ADD.F32): a plain
+// load-add-store stalled every thread on L2 load latency (30 % of all stall samples in ncu); the addresses are CTA-private.
 template <int KROWS, int NCOLS, int WSTRIDE>
-__device__ __forceinline__ void dw_gemm(const float* __restrict__ A0, const float* __restrict__ D0, float* __restrict__ gW, float* __restrict__ gb) {
+__device__ __forceinline__ void dw_gemm(const float* __restrict__ A0, const float* __restrict__ D0, float* __restrict__ gW, float* __restrict__ gb,
+                                        const int* __restrict__ warp_active) {
     constexpr int KI = (KROWS + 15) / 16, NJ = (NCOLS + 15) / 16;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int TK = (wid >> 1) * 4 + (lane >> 3), TN = (wid & 1) * 8 + (lane & 7);
@@ -188,6 +190,7 @@ __device__ __forceinline__ void dw_gemm(const float* __restrict__ A0, const floa
     for (int j = 0; j < NJ; ++j) bacc[j] = 0.f;
 #pragma unroll 1
     for (int w = 0; w < ADJ_NW; ++w) {
+        if (!warp_active[w]) continue;               // warps without a live column contribute nothing (and do not fill their buffers)
         const float* A = A0 + w * WSTRIDE;
         const float* D = D0 + w * WSTRIDE;
 #pragma unroll
@@ -216,14 +219,14 @@ __device__ __forceinline__ void dw_gemm(const float* __restrict__ A0, const floa
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
             const int n = TN + 16 * j;
-            if (k < KROWS && n < NCOLS) { float* p = gW + k * NCOLS + n; *p = *p + acc[i][j]; }
+            if (k < KROWS && n < NCOLS) atomicAdd(gW + k * NCOLS + n, acc[i][j]);   // RED.ADD.F32: fire-and-forget, address private to this CTA
         }
     }
     if (TK == 0) {
 #pragma unroll
         for (int j = 0; j < NJ; ++j) {
             const int n = TN + 16 * j;
-            if (n < NCOLS) gb[n] += bacc[j];
+            if (n < NCOLS) atomicAdd(gb + n, bacc[j]);
         }
     }
 }
@@ -262,6 +265,7 @@ __global__ void __launch_bounds__(ADJ_NW * 32, 1) adjoint_kernel(const AdjParams
     extern __shared__ __align__(16) float smem[];
     __shared__ uint64_t bar;
     __shared__ AdjSlots slots[ADJ_NW];
+    __shared__ int warp_active[ADJ_NW];
     const float* sW = WS ? smem : P.wpack;
     if (WS) stage_weights(smem, P.wpack, N::P_TOTAL, &bar);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -285,7 +289,9 @@ __global__ void __launch_bounds__(ADJ_NW * 32, 1) adjoint_kernel(const AdjParams
         bool any = false;
 #pragma unroll
         for (int c = 0; c < CPW; ++c) any |= sl->col[c] >= 0;
+        if (lane == 0) warp_active[warp] = any ? 1 : 0;
         if (!__syncthreads_or(any ? 1 : 0)) break;
+        const bool wact = any;                   // warp-uniform: this warp has at least one live column in this iteration
         if (lane < CPW && sl->col[lane] >= 0) {
             if (sl->mode[lane] == 0) {
                 const float t = sl->t[lane], ts = sl->tstop[lane];
@@ -305,6 +311,9 @@ __global__ void __launch_bounds__(ADJ_NW * 32, 1) adjoint_kernel(const AdjParams
             const float a0 = c_adj_a[s][0], a1 = c_adj_a[s][1], a2 = c_adj_a[s][2], a3 = c_adj_a[s][3], a4 = c_adj_a[s][4], a5 = c_adj_a[s][5];
             const float cs = c_adj_c[s], bs = c_adj_b[s];
             float us[CPW], uca[CPW], winv[CPW], fb[CPW];
+#pragma unroll
+            for (int c = 0; c < CPW; ++c) { us[c] = 0.f; uca[c] = 0.f; winv[c] = 1.f; fb[c] = 0.f; }
+            if (wact) {
 #pragma unroll
             for (int c = 0; c < CPW; ++c) {
                 float acc = a0 * kap[0][c];
@@ -346,8 +355,9 @@ __global__ void __launch_bounds__(ADJ_NW * 32, 1) adjoint_kernel(const AdjParams
                 uca[c] = shi - sca;
                 fb[c] = Fb;          // delta of the output layer: row n = k - 1  (row 31 = 0)
             }
+            }   // wact
             // write a_0 and the output-layer delta (rows shifted by one: neuron n <-> face n+1)
-            {
+            if (wact) {
                 float* a0p = ws + S::ACT0 + lane * CPW;
                 *reinterpret_cast<float4*>(a0p) = make_float4(us[0], us[1], us[2], us[3]);
                 *reinterpret_cast<float4*>(a0p + 4) = make_float4(us[4], us[5], us[6], us[7]);
@@ -357,42 +367,44 @@ __global__ void __launch_bounds__(ADJ_NW * 32, 1) adjoint_kernel(const AdjParams
             }
             __syncwarp();
             // forward: hidden activations a_1 .. a_NHID (the output layer itself is not needed)
-            dense_hidden<N::IN0, N::NPL, N::RSW, true>(sW + N::P_W0, sW + N::P_B0, ws + S::ACT0, ws + S::act(1), lane);
-            __syncwarp();
-#pragma unroll
-            for (int l = 1; l < N::NHID; ++l) {
-                dense_hidden<N::H, N::NPL, N::RSW, true>(sW + N::P_HID + (l - 1) * N::HIDP_STRIDE, sW + N::P_HID + (l - 1) * N::HIDP_STRIDE + N::H * N::RSW,
-                                                         ws + S::act(l), ws + S::act(l + 1), lane);
+            if (wact) {
+                dense_hidden<N::IN0, N::NPL, N::RSW, true>(sW + N::P_W0, sW + N::P_B0, ws + S::ACT0, ws + S::act(1), lane);
                 __syncwarp();
+#pragma unroll
+                for (int l = 1; l < N::NHID; ++l) {
+                    dense_hidden<N::H, N::NPL, N::RSW, true>(sW + N::P_HID + (l - 1) * N::HIDP_STRIDE, sW + N::P_HID + (l - 1) * N::HIDP_STRIDE + N::H * N::RSW,
+                                                             ws + S::act(l), ws + S::act(l + 1), lane);
+                    __syncwarp();
+                }
             }
             // backward through the output layer
             float* dcur = ws + S::DL;
             float* dnext = ws + S::TMP;
             int dcur_off = S::DL, dnext_off = S::TMP;
-            dense_T_last<N::NPL, N::RSL>(sW + N::P_WL, dcur, ws + S::act(N::NHID), dnext, lane);
+            if (wact) dense_T_last<N::NPL, N::RSL>(sW + N::P_WL, dcur, ws + S::act(N::NHID), dnext, lane);
             const bool do_dw = s < 6;
             __syncthreads();
-            if (do_dw) dw_gemm<N::H, N::NOUT, S::TOTAL>(scratch0 + S::act(N::NHID), scratch0 + dcur_off, g + N::T_WL, g + N::T_BL);
+            if (do_dw) dw_gemm<N::H, N::NOUT, S::TOTAL>(scratch0 + S::act(N::NHID), scratch0 + dcur_off, g + N::T_WL, g + N::T_BL, warp_active);
             __syncthreads();
             dcur_off = dnext_off;
             // hidden layers l = NHID-1 .. 1  (Dense_l : a_l -> a_{l+1})
 #pragma unroll
             for (int l = N::NHID - 1; l >= 1; --l) {
                 dnext_off = (dcur_off == S::TMP) ? S::act(l + 1) : S::TMP;
-                dense_T_hidden<N::NPL, N::NPL, N::RSW, true>(sW + N::P_HID + (l - 1) * N::HIDP_STRIDE, ws + dcur_off, ws + S::act(l), ws + dnext_off, lane, N::H);
+                if (wact) dense_T_hidden<N::NPL, N::NPL, N::RSW, true>(sW + N::P_HID + (l - 1) * N::HIDP_STRIDE, ws + dcur_off, ws + S::act(l), ws + dnext_off, lane, N::H);
                 __syncthreads();
                 if (do_dw) dw_gemm<N::H, N::H, S::TOTAL>(scratch0 + S::act(l), scratch0 + dcur_off, g + N::T_HID + (l - 1) * N::HID_STRIDE,
-                                                         g + N::T_HID + (l - 1) * N::HID_STRIDE + N::H * N::H);
+                                                         g + N::T_HID + (l - 1) * N::HID_STRIDE + N::H * N::H, warp_active);
                 __syncthreads();
                 dcur_off = dnext_off;
             }
             // first layer: u-bar = W0^T delta_1  -> DL buffer (free since the output-layer dW is done)
-            dense_T_hidden<1, N::NPL, N::RSW, false>(sW + N::P_W0, ws + dcur_off, nullptr, ws + S::DL, lane, N::IN0);
+            if (wact) dense_T_hidden<1, N::NPL, N::RSW, false>(sW + N::P_W0, ws + dcur_off, nullptr, ws + S::DL, lane, N::IN0);
             __syncthreads();
-            if (do_dw) dw_gemm<N::IN0, N::H, S::TOTAL>(scratch0 + S::ACT0, scratch0 + dcur_off, g + N::T_W0, g + N::T_B0);
+            if (do_dw) dw_gemm<N::IN0, N::H, S::TOTAL>(scratch0 + S::ACT0, scratch0 + dcur_off, g + N::T_W0, g + N::T_B0, warp_active);
             __syncthreads();
             // kappa_s = J^T lam_s
-            {
+            if (wact) {
                 const float4 u0 = *reinterpret_cast<const float4*>(ws + S::DL + lane * CPW), u1 = *reinterpret_cast<const float4*>(ws + S::DL + lane * CPW + 4);
                 const float ub[CPW] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
 #pragma unroll
