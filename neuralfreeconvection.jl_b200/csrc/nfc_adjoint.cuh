@@ -359,8 +359,23 @@ __global__ void __launch_bounds__(ADJ_NW * 32, 1) adjoint_kernel(const AdjParams
             // write a_0 and the output-layer delta (rows shifted by one: neuron n <-> face n+1)
             if (wact) {
                 float* a0p = ws + S::ACT0 + lane * CPW;
-                *reinterpret_cast<float4*>(a0p) = make_float4(us[0], us[1], us[2], us[3]);
-                *reinterpret_cast<float4*>(a0p + 4) = make_float4(us[4], us[5], us[6], us[7]);
+                if (N::CONVW == 0) {
+                    *reinterpret_cast<float4*>(a0p) = make_float4(us[0], us[1], us[2], us[3]);
+                    *reinterpret_cast<float4*>(a0p + 4) = make_float4(us[4], us[5], us[6], us[7]);
+                } else {
+                    // a_0 = relu(conv(u)): Flux Conv((k,1),1=>1,relu), flipped kernel (train_free_convection_nde.jl:138-153)
+                    float x[CPW];
+                    const float cb = sW[N::P_CONV + N::CONVW];
+#pragma unroll
+                    for (int c = 0; c < CPW; ++c) {
+                        float acc = 0.f;
+#pragma unroll
+                        for (int j = 0; j < N::CONVW; ++j) acc = fmaf(sW[N::P_CONV + j], __shfl_down_sync(FULL, us[c], N::CONVW - 1 - j), acc);
+                        x[c] = lane < N::IN0 ? fmaxf(acc + cb, 0.f) : 0.f;
+                    }
+                    *reinterpret_cast<float4*>(a0p) = make_float4(x[0], x[1], x[2], x[3]);
+                    *reinterpret_cast<float4*>(a0p + 4) = make_float4(x[4], x[5], x[6], x[7]);
+                }
                 float* dlp = ws + S::DL + ((lane + NZ - 1) & (NZ - 1)) * CPW;
                 *reinterpret_cast<float4*>(dlp) = make_float4(fb[0], fb[1], fb[2], fb[3]);
                 *reinterpret_cast<float4*>(dlp + 4) = make_float4(fb[4], fb[5], fb[6], fb[7]);
@@ -406,7 +421,36 @@ __global__ void __launch_bounds__(ADJ_NW * 32, 1) adjoint_kernel(const AdjParams
             // kappa_s = J^T lam_s
             if (wact) {
                 const float4 u0 = *reinterpret_cast<const float4*>(ws + S::DL + lane * CPW), u1 = *reinterpret_cast<const float4*>(ws + S::DL + lane * CPW + 4);
-                const float ub[CPW] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+                float ub[CPW] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+                if (N::CONVW != 0) {
+                    // back through relu(conv(u)): d_i = [pre_i > 0] dx_i ; u-bar_m = sum_j w_j d_{m-(k-1-j)} ; conv weight / bias gradient
+                    const float cb = sW[N::P_CONV + N::CONVW];
+                    float gw[N::CONVW > 0 ? N::CONVW : 1], gbc = 0.f;
+#pragma unroll
+                    for (int j = 0; j < N::CONVW; ++j) gw[j] = 0.f;
+#pragma unroll
+                    for (int c = 0; c < CPW; ++c) {
+                        float pre = cb, sh[N::CONVW > 0 ? N::CONVW : 1];
+#pragma unroll
+                        for (int j = 0; j < N::CONVW; ++j) { sh[j] = __shfl_down_sync(FULL, us[c], N::CONVW - 1 - j); pre = fmaf(sW[N::P_CONV + j], sh[j], pre); }
+                        const float d = (lane < N::IN0 && pre > 0.f) ? ub[c] : 0.f;
+                        gbc += d;
+                        float ubar = 0.f;
+#pragma unroll
+                        for (int j = 0; j < N::CONVW; ++j) {
+                            gw[j] = fmaf(d, sh[j], gw[j]);
+                            const float dd = __shfl_up_sync(FULL, d, N::CONVW - 1 - j);
+                            if (lane >= N::CONVW - 1 - j) ubar = fmaf(sW[N::P_CONV + j], dd, ubar);
+                        }
+                        ub[c] = ubar;
+                    }
+                    if (do_dw) {
+#pragma unroll
+                        for (int j = 0; j < N::CONVW; ++j) { const float t = warp_sum(gw[j]); if (lane == 0) atomicAdd(g + N::T_CONV + j, t); }
+                        const float t = warp_sum(gbc);
+                        if (lane == 0) atomicAdd(g + N::T_CONV + N::CONVW, t);
+                    }
+                }
 #pragma unroll
                 for (int c = 0; c < CPW; ++c) {
                     const float v = (ub[c] + uca[c]) * winv[c];
@@ -532,7 +576,6 @@ template <class N> constexpr size_t adj_smem_bytes() { return sizeof(float) * ((
 
 template <class N>
 int adjoint_setup(nfc_handle* h) {
-    if (N::CONVW != 0) return 0;   // conv front-end: forward only in this build (nfc_loss_grad reports unsupported)
     NFC_CUDA(h, cudaFuncSetAttribute(adjoint_kernel<N, AdjLaunch<N>::WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adj_smem_bytes<N>()));
     return 0;
 }
@@ -540,7 +583,6 @@ int adjoint_setup(nfc_handle* h) {
 template <class N, bool WS, int NW>
 int adjoint_loss_grad(nfc_handle* h, const float* T0, const float* colp, float pref, const float* Ttrue, double* loss_sum_dev, float* grad_dev,
                       int* status, int64_t B, int64_t n_total_columns, cudaStream_t st) {
-    if (N::CONVW != 0) return fail(h, -4, "nfc_loss_grad: Chains with a Conv front-end are forward-only in this build");
     if (!loss_sum_dev || !grad_dev) return fail(h, -1, "null output");
     const int n_save = h->cfg.n_save, cap = h->cfg.adjoint_max_steps, grid = h->num_sms;
     NFC_CUDA(h, cudaMemsetAsync(loss_sum_dev, 0, 2 * sizeof(double), st));

@@ -96,18 +96,12 @@ def test_batch_split_and_chunking(nfc, gpu_ok, monkeypatch):
     assert _rel(ch["grad"], full["grad"]) < 2e-4 and abs(ch["loss"] - full["loss"]) / full["loss"] < 1e-6
 
 
-@pytest.mark.parametrize("arch", ["dense-deeper", "dense-wider"])
+@pytest.mark.parametrize("arch", ["dense-deeper", "dense-wider", "conv-2", "conv-4"])
 def test_other_chains_vs_c_oracle(nfc, gpu_ok, arch):
     d, cw, layers, theta, sv, colp, Ttrue, h = _setup(nfc, arch=arch, scale=1.0, K=2.0, n_save=17)
     r = h.loss_grad(d["T0"], colp, d["glob"], Ttrue)
     o = CO.loss_grad_continuous(d["T0"], theta, cw, layers, colp, d["glob"], sv, Ttrue, nthreads=8)
     assert abs(r["loss"] - o["loss"]) / o["loss"] < 1e-3 and _rel(r["grad"], o["grad"]) < 2e-3
-
-
-def test_conv_chains_are_forward_only(nfc, gpu_ok):
-    d, cw, layers, theta, sv, colp, Ttrue, h = _setup(nfc, arch="conv-2", n_save=5)
-    with pytest.raises(nfc.NfcError, match="forward-only"):
-        h.loss_grad(d["T0"], colp, d["glob"], Ttrue)
 
 
 def test_tape_overflow_is_reported_per_column(nfc, gpu_ok):
