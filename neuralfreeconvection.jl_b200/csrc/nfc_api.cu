@@ -107,8 +107,11 @@ int do_diagnose(nfc_handle* h, const float* Tsol, const float* colp, float* wT, 
 }
 
 // forward solve (RECORD=false) or forward pass of loss_grad (RECORD=true)
+// hist_total / hist_off: the per-column step history (longest-first schedule) is kept for the whole host-level batch; a call that
+// solves the batch in pieces passes the batch size and this piece's offset
 template <class N, bool RECORD>
-int launch_solve(nfc_handle* h, SolveParams& P, cudaStream_t st, bool reset_counters = true) {
+int launch_solve(nfc_handle* h, SolveParams& P, cudaStream_t st, bool reset_counters = true, int64_t hist_total = -1, int64_t hist_off = 0,
+                 bool last_piece = true) {
     constexpr bool WS = Launch<N>::WS;
     constexpr int NW = Launch<N>::NW;
     const long long B = P.B;
@@ -130,26 +133,34 @@ int launch_solve(nfc_handle* h, SolveParams& P, cudaStream_t st, bool reset_coun
         NFC_CUDA(h, cudaMemsetAsync(h->d_counters.p + CTR_QUEUE, 0, sizeof(unsigned long long), st));
         NFC_CUDA(h, cudaMemsetAsync(h->d_counters.p + CTR_ADJ_QUEUE, 0, sizeof(unsigned long long), st));
     }
-    NFC_CUDA(h, cudaEventRecord(h->ev[0], st));
+    if (reset_counters) NFC_CUDA(h, cudaEventRecord(h->ev[0], st));
+    if (hist_total < 0) hist_total = B;
     // Schedule: columns that took the most steps in the previous call of this batch size go first, so the queue drains with short
     // columns and the persistent CTAs finish together (the same columns are re-solved every epoch).  Results do not depend on it.
     P.order = nullptr; P.work = nullptr;
     if (!RECORD && h->use_sched && B >= 4096) {
-        NFC_CUDA(h, h->d_work.ensure((size_t)B));
+        if (h->sched_B != hist_total) {                      // new batch size: forget the history
+            NFC_CUDA(h, cudaStreamSynchronize(st));
+            h->d_work.release();
+            h->sched_valid.assign(8, false);
+        }
+        NFC_CUDA(h, h->d_work.ensure((size_t)hist_total));
         NFC_CUDA(h, h->d_order.ensure((size_t)B));
         NFC_CUDA(h, h->d_hist.ensure(SCHED_BUCKETS));
-        if (h->sched_B == B) {
+        const int piece = (int)std::min<int64_t>(7, hist_off / std::max<int64_t>(B, 1));
+        if (h->sched_B == hist_total && h->sched_valid[piece]) {
             NFC_CUDA(h, cudaMemsetAsync(h->d_hist.p, 0, sizeof(int) * SCHED_BUCKETS, st));
             const int nb = (int)((B + 255) / 256);
-            sched_hist_kernel<<<nb, 256, 0, st>>>(h->d_work.p, h->d_hist.p, B);
+            sched_hist_kernel<<<nb, 256, 0, st>>>(h->d_work.p + hist_off, h->d_hist.p, B);
             sched_scan_kernel<<<1, SCHED_BUCKETS, 0, st>>>(h->d_hist.p);
-            sched_scatter_kernel<<<nb, 256, 0, st>>>(h->d_work.p, h->d_hist.p, h->d_order.p, B);
+            sched_scatter_kernel<<<nb, 256, 0, st>>>(h->d_work.p + hist_off, h->d_hist.p, h->d_order.p, B);
             NFC_CUDA(h, cudaGetLastError());
             P.order = h->d_order.p;
             h->last_launches += 3;
         }
-        P.work = h->d_work.p;
-        h->sched_B = B;
+        P.work = h->d_work.p + hist_off;
+        h->sched_B = hist_total;
+        h->sched_valid[piece] = true;
     }
     const long long groups = (B + CPW - 1) / CPW;
     const int grid0 = (int)std::min<long long>(h->num_sms, (groups + NW - 1) / NW);
@@ -165,10 +176,9 @@ int launch_solve(nfc_handle* h, SolveParams& P, cudaStream_t st, bool reset_coun
         solve_kernel<N, WS, NW, RECORD><<<grid, NW * 32, smem_bytes<N>(NW), st>>>(P);
     }
     NFC_CUDA(h, cudaGetLastError());
-    NFC_CUDA(h, cudaEventRecord(h->ev[1], st));
-    h->ev_fwd_valid = true;
+    if (last_piece) { NFC_CUDA(h, cudaEventRecord(h->ev[1], st)); h->ev_fwd_valid = true; }
     h->last_launches += 2;
-    h->last_columns = B;
+    h->last_columns = reset_counters ? B : h->last_columns + B;
     return 0;
 }
 
@@ -181,10 +191,10 @@ namespace {
 
 template <class N>
 int do_solve(nfc_handle* h, const float* T0, const float* colp, float pref, float* Tout, int* nacc, int* nrej, int* status, int64_t B,
-             cudaStream_t st) {
+             cudaStream_t st, bool first = true, int64_t hist_total = -1, int64_t hist_off = 0, bool last_piece = true) {
     SolveParams P{};
     P.T0 = T0; P.colp = colp; P.pref = pref; P.Tout = Tout; P.naccept = nacc; P.nreject = nrej; P.status = status; P.B = B;
-    return launch_solve<N, false>(h, P, st);
+    return launch_solve<N, false>(h, P, st, first, hist_total, hist_off, last_piece);
 }
 
 template <class N>
@@ -285,7 +295,9 @@ int32_t nfc_create(const nfc_config* cfg, nfc_handle** out) {
     h->num_sms = prop.multiProcessorCount;
     auto bail = [&](int code) { create_error() = h->err; nfc_destroy(h); return code; };
     if (cudaSetDevice(h->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return bail(-10); }
-    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "cudaStreamCreate failed"; return bail(-10); }
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "cudaStreamCreate failed"; return bail(-10); }
+    for (auto& ev : h->ev_chunk) if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { h->err = "cudaEventCreate failed"; return bail(-10); }
     for (auto& ev : h->ev) if (cudaEventCreate(&ev) != cudaSuccess) { h->err = "cudaEventCreate failed"; return bail(-10); }
     int rc = [&]() -> int { NFC_DISPATCH(h, arch_setup, h); }();
     if (rc) return bail(rc);
@@ -314,6 +326,8 @@ int32_t nfc_destroy(nfc_handle* h) {
     h->s_nacc.release(); h->s_nrej.release(); h->s_status.release(); h->s_loss.release();
     h->a_resid.release(); h->a_tape.release(); h->a_gacc.release(); h->a_tlen.release(); h->a_adjsteps.release(); h->a_gsum.release();
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : h->ev_chunk) if (ev) cudaEventDestroy(ev);
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -449,11 +463,31 @@ int32_t nfc_solve(nfc_handle* h, const float* T0, const float* colp, const float
     NFC_CUDA(h, cudaMemcpyAsync(h->s_T0.p, T0, sizeof(float) * B * NZ, cudaMemcpyHostToDevice, h->stream));
     NFC_CUDA(h, cudaMemcpyAsync(h->s_colp.p, colp, sizeof(float) * B * 3, cudaMemcpyHostToDevice, h->stream));
     h->last_launches = 0;
-    int rc = [&]() -> int {
-        NFC_DISPATCH(h, do_solve, h, h->s_T0.p, h->s_colp.p, prefactor(glob), h->s_out.p, h->s_nacc.p, h->s_nrej.p, h->s_status.p, B, h->stream);
-    }();
-    if (rc) return rc;
-    NFC_CUDA(h, cudaMemcpyAsync(Tout, h->s_out.p, sizeof(float) * nout, cudaMemcpyDeviceToHost, h->stream));
+    // Large batches are solved in three pieces so that the device->host copy of one piece (the trajectories dominate the
+    // end-to-end time: 1.08 GB for 65 536 columns x 129 saves) overlaps the solve of the next one (second stream; measured +32 % end to end).
+    int npieces = (B >= 65536) ? 3 : 1;
+    if (const char* e = getenv("NFC_E2E_PIECES")) npieces = std::max(1, std::min(4, atoi(e)));
+    if (B < 8192 * npieces) npieces = 1;
+    const int64_t piece = ((B + npieces - 1) / npieces + 127) / 128 * 128;
+    const float pref = prefactor(glob);
+    int k = 0;
+    for (int64_t off = 0; off < B; off += piece, ++k) {
+        const int64_t nb = std::min<int64_t>(piece, B - off);
+        const bool lastp = off + nb >= B;
+        int rc = [&]() -> int {
+            NFC_DISPATCH(h, do_solve, h, h->s_T0.p + off * NZ, h->s_colp.p + off * 3, pref, h->s_out.p + off * h->cfg.n_save * NZ, h->s_nacc.p + off,
+                         h->s_nrej.p + off, h->s_status.p + off, nb, h->stream, k == 0, B, off, lastp);
+        }();
+        if (rc) return rc;
+        cudaStream_t cs = npieces > 1 ? h->copy_stream : h->stream;
+        if (npieces > 1) {
+            NFC_CUDA(h, cudaEventRecord(h->ev_chunk[k], h->stream));
+            NFC_CUDA(h, cudaStreamWaitEvent(cs, h->ev_chunk[k], 0));
+        }
+        NFC_CUDA(h, cudaMemcpyAsync(Tout + off * h->cfg.n_save * NZ, h->s_out.p + off * h->cfg.n_save * NZ, sizeof(float) * nb * h->cfg.n_save * NZ,
+                                    cudaMemcpyDeviceToHost, cs));
+    }
+    if (npieces > 1) NFC_CUDA(h, cudaStreamSynchronize(h->copy_stream));
     if (naccept) NFC_CUDA(h, cudaMemcpyAsync(naccept, h->s_nacc.p, sizeof(int) * B, cudaMemcpyDeviceToHost, h->stream));
     if (nreject) NFC_CUDA(h, cudaMemcpyAsync(nreject, h->s_nrej.p, sizeof(int) * B, cudaMemcpyDeviceToHost, h->stream));
     if (status) NFC_CUDA(h, cudaMemcpyAsync(status, h->s_status.p, sizeof(int) * B, cudaMemcpyDeviceToHost, h->stream));

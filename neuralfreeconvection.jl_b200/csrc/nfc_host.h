@@ -37,7 +37,8 @@ struct nfc_handle {
     int device = 0, num_sms = 0;
     int64_t n_params = 0, n_packed = 0;
     bool weights_set = false;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool ev_fwd_valid = false, ev_adj_valid = false;
     nfc::DevBuf<float> d_theta, d_wpack, d_saveat, d_k1, d_dt;
@@ -46,6 +47,7 @@ struct nfc_handle {
     // longest-first scheduling: per-column attempted steps of the previous forward call with the same batch size
     nfc::DevBuf<int> d_work, d_order, d_hist;
     int64_t sched_B = -1;       // batch size d_work is valid for (-1: none)
+    std::vector<bool> sched_valid = std::vector<bool>(8, false);   // per piece of a host-level batch: history present
     bool use_sched = true;
     nfc::DevBuf<unsigned long long> d_counters;
     // host-call staging

@@ -216,3 +216,25 @@ def test_full_size_properties_65536(nfc, gpu_ok):
     idx = np.random.default_rng(0).choice(B, 64, replace=False)
     c = CO.solve(d["T0"][idx], O.glorot_theta(cw, layers, 0, 0.3), cw, layers, d["colp"][idx], d["glob"], sv, nthreads=8)
     assert rel_l2(Tout[torch.from_numpy(idx).to(dev)].cpu().numpy(), c["T"]).max() < TRAJ_TOL
+
+
+def test_kca_sweep_ensemble(nfc, gpu_ok):
+    """BASELINE config 5 (i): the K_CA sweep of figureC_optimize_convective_adjustment.jl:50-59 -- 100 log-spaced K_CA in
+    [1e-3, 10] x the 9 training columns as ONE batch with per-column K_CA, zero-weight network and Glorot weights."""
+    d = nfc.synthetic.make_columns("training9")
+    K = np.logspace(-3, 1, 100).astype(np.float32)
+    T0 = np.tile(d["T0"], (100, 1))
+    colp = np.tile(d["colp"], (100, 1))
+    colp[:, 2] = np.repeat(K, 9)
+    sv = nfc.synthetic.saveat(9)
+    cw, layers = O.chain_spec()
+    h, _, _ = _handle(nfc, saveat=sv)
+    for theta in (np.zeros(24735, np.float32), O.glorot_theta(cw, layers, 0, 0.3)):
+        h.set_weights(theta)
+        r = h.solve(T0, colp, d["glob"])
+        c = CO.solve(T0, theta, cw, layers, colp, d["glob"], sv, nthreads=8)
+        assert (r["status"] == 0).all()
+        assert rel_l2(r["T"], c["T"]).max() < TRAJ_TOL
+    # larger K_CA = stiffer = more steps (figure C's runtime curve)
+    steps = (r["naccept"] + r["nreject"]).reshape(100, 9).sum(1)
+    assert steps[-1] > 3 * steps[0]
