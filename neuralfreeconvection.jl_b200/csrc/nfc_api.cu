@@ -170,7 +170,22 @@ int launch_solve(nfc_handle* h, SolveParams& P, cudaStream_t st, bool reset_coun
     if (!RECORD && h->use_tc && h->arch == ARCH_DEFAULT) {
         const int gridt = (int)std::min<long long>(h->num_sms, (B + tc::TILE - 1) / tc::TILE);
         if (const char* e = getenv("NFC_TC_NPROD")) P.tape_cap = atoi(e);   // timing experiments only (results are wrong for < 6)
+        if (getenv("NFC_TC_DEBUG")) {                                        // phase timers of CTA 0 (clock64), printed after the kernel
+            NFC_CUDA(h, h->a_resid.ensure(64));
+            NFC_CUDA(h, cudaMemsetAsync(h->a_resid.p, 0, 256, st));
+            P.resid = h->a_resid.p;
+        }
         tc::solve_tc_kernel<<<gridt, tc::NTHREADS, tc::IMG_BYTES, st>>>(h->d_wimg.p, P);
+        if (P.resid) {
+            long long dbg[32];
+            NFC_CUDA(h, cudaStreamSynchronize(st));
+            NFC_CUDA(h, cudaMemcpy(dbg, P.resid, sizeof dbg, cudaMemcpyDeviceToHost));
+            for (int l = 0; l < 3; ++l)
+                fprintf(stderr, "[nfc tc debug] layer %d: n %lld | MMA thread: wait A0 %.0f, issue half0 %.0f, wait A1 %.0f, issue half1+commit %.0f cycles | column thread 0 waits for D %.0f\n",
+                        l, dbg[5 * l + 4], (double)dbg[5 * l] / dbg[5 * l + 4], (double)dbg[5 * l + 1] / dbg[5 * l + 4], (double)dbg[5 * l + 2] / dbg[5 * l + 4],
+                        (double)dbg[5 * l + 3] / dbg[5 * l + 4], (double)dbg[16 + l] / dbg[5 * l + 4]);
+            fprintf(stderr, "[nfc tc debug] column thread 0 total %lld cycles, %.0f per Chain evaluation\n", dbg[19], (double)dbg[19] / dbg[4]);
+        }
     } else {
         const int grid = (int)std::min<long long>(h->num_sms, (groups + NW - 1) / NW);
         solve_kernel<N, WS, NW, RECORD><<<grid, NW * 32, smem_bytes<N>(NW), st>>>(P);

@@ -153,7 +153,15 @@ __global__ void pack_weights_tc_kernel(const float* __restrict__ theta, unsigned
     else if (i < n1 + n2 + n3) {
         const int q = i - n1 - n2, n = q % 32, k = q / 32;
         w = n < 31 ? theta[N::T_WL + k * 31 + n] : 0.f;
-        off = OFF_W3 + umma_off(n, k, 32); bytes = W3_BYTES;
+        // output layer: the three splits are stacked along N (rows 32 s + n of ONE [96][128] operand), see issue_layer<2>
+        const __nv_bfloat16 c1 = __float2bfloat16_rn(w);
+        const float q1 = w - __bfloat162float(c1);
+        const __nv_bfloat16 c2 = __float2bfloat16_rn(q1);
+        const __nv_bfloat16 c3 = __float2bfloat16_rn(q1 - __bfloat162float(c2));
+        *reinterpret_cast<__nv_bfloat16*>(img + OFF_W3 + umma_off(n, k, 96)) = c1;
+        *reinterpret_cast<__nv_bfloat16*>(img + OFF_W3 + umma_off(32 + n, k, 96)) = c2;
+        *reinterpret_cast<__nv_bfloat16*>(img + OFF_W3 + umma_off(64 + n, k, 96)) = c3;
+        return;
     } else if (i < n1 + n2 + n3 + 288) {
         const int q = i - n1 - n2 - n3;
         float b = 0.f;
@@ -175,7 +183,8 @@ __global__ void pack_weights_tc_kernel(const float* __restrict__ theta, unsigned
 // ---- shared state of one CTA ------------------------------------------------------------------------------------------
 struct TcShared {
     uint64_t bar_w;        // weight image landed
-    uint64_t bar_a;        // A operand written by the 256 column threads (count 256)
+    uint64_t bar_a;        // first half of the A operand written by all column threads (even k-steps of the next layer)
+    uint64_t bar_a1;       // second half written (odd k-steps)
     uint64_t bar_d;        // accumulator ready (tcgen05.commit)
     uint32_t tmem_base;
     int stop;
@@ -189,9 +198,10 @@ struct TcShared {
 // MMA issuer: all six split products of one Dense layer, fully unrolled: per MMA one 32-bit add on the descriptor's
 // address field (k-step stride 2*LBO), one add on the TMEM column, the tcgen05.mma itself.  (A first version built every
 // descriptor in a runtime loop and was issue-bound at ~98 cycles per MMA against 64 / 16 cycles of tensor-pipe time.)
-template <int LAYER>
+// HALF selects the k-steps whose A cells are published first (even) or second (odd); the very first MMA of a layer overwrites D
+template <int LAYER, int HALF>
 __device__ __forceinline__ void issue_layer(uint32_t tmem_base, uint32_t smem_img, int nprod) {
-    constexpr int K = LAYER == 0 ? 32 : 128, Nn = LAYER == 2 ? 32 : 128;
+    constexpr int K = LAYER == 0 ? 32 : 128, Nn = LAYER == 2 ? 96 : 128;
     constexpr uint32_t woff = LAYER == 0 ? OFF_W1 : (LAYER == 1 ? OFF_W2 : OFF_W3);
     constexpr uint32_t wbytes = LAYER == 0 ? W1_BYTES : (LAYER == 1 ? W2_BYTES : W3_BYTES);
     constexpr uint32_t idesc = make_idesc(128, Nn);
@@ -203,26 +213,38 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem_base, uint32_t smem_im
     // (a split, b split): smallest terms first so the big a1 b1 term lands on an already formed tail
     constexpr int sa[6] = {2, 0, 1, 1, 0, 0};
     constexpr int sb[6] = {0, 2, 1, 0, 1, 0};
-    if (nprod >= 6) {
+    if (LAYER == 2) {
+        // Output layer (31 neurons): a TS-form MMA costs ~61 cycles whatever N is (the A operand read from tensor memory, 4 KB per
+        // k-step at 64 B/cycle, is the limit), so the three weight splits are stacked along N: one N = 96 MMA per A split,
+        // D[:, 0:32] + D[:, 32:64] + D[:, 64:96] = A (B1 + B2 + B3) with all nine product terms, 24 MMAs instead of 48.
+#pragma unroll
+        for (int sA = 2; sA >= 0; --sA) {
+#pragma unroll
+            for (int j = HALF; j < K / 16; j += 2) {
+                if (sA == 2 && j == 0) mma_ts2<false>(d, a_base + sA * 64 + 8 * j, lo0 + kstep * j, hi0, idesc);
+                else mma_ts2<true>(d, a_base + sA * 64 + 8 * j, lo0 + kstep * j, hi0, idesc);
+            }
+        }
+    } else if (nprod >= 6) {
 #pragma unroll
         for (int p = 0; p < 6; ++p) {
 #pragma unroll
-            for (int j = 0; j < K / 16; ++j) {
+            for (int j = HALF; j < K / 16; j += 2) {
                 const uint32_t blo = lo0 + ((sb[p] * wbytes) >> 4) + kstep * j;      // compile-time offset, no carry out of the 14-bit field
                 if (p == 0 && j == 0) mma_ts2<false>(d, a_base + sa[p] * 64 + 8 * j, blo, hi0, idesc);
                 else mma_ts2<true>(d, a_base + sa[p] * 64 + 8 * j, blo, hi0, idesc);
             }
         }
     } else {   // timing experiments only
-        uint32_t acc = 0;
+        uint32_t acc = HALF;
         for (int p = 6 - nprod; p < 6; ++p)
-            for (int j = 0; j < K / 16; ++j) { mma_ts(d, a_base + sa[p] * 64 + 8 * j, desc0 + (uint64_t)(((sb[p] * wbytes) >> 4) + kstep * j), idesc, acc); acc = 1; }
+            for (int j = HALF; j < K / 16; j += 2) { mma_ts(d, a_base + sa[p] * 64 + 8 * j, desc0 + (uint64_t)(((sb[p] * wbytes) >> 4) + kstep * j), idesc, acc); acc = 1; }
     }
 }
 
 // Column-thread side of one Chain evaluation.  y[8]: this thread's 8 levels of the stage input (level 8 q + i).
 // Returns nn[i] = NN output n = 8 q + i - 1  (i = 0..8; nn[0] of q = 0 and nn[8] of q = 3 belong to the boundary faces).
-__device__ __forceinline__ void chain_eval(TcShared* S, const float* sbias, const float (&y)[8], float (&nn)[9], int& pd, int wq, int q) {
+__device__ __forceinline__ void chain_eval(TcShared* S, const float* sbias, const float (&y)[8], float (&nn)[9], int& pd, int wq, int q, long long* twd = nullptr) {
     const uint32_t tl = S->tmem_base + ((uint32_t)(32 * wq) << 16);     // this warp's TMEM lane window
     // ---- layer-1 A operand: levels 8q..8q+7 -> 4 cells per split at columns 4q
     {
@@ -235,47 +257,53 @@ __device__ __forceinline__ void chain_eval(TcShared* S, const float* sbias, cons
         wait_st();
         fence_before_sync();
         mbar_arrive(&S->bar_a);
+        mbar_arrive(&S->bar_a1);
     }
     // ---- hidden layers: D -> bias, relu, split -> A operand of the next layer (units 32q .. 32q+31 -> cells 16q .. 16q+15)
 #pragma unroll 1
     for (int l = 0; l < 2; ++l) {
-        mbar_wait(&S->bar_d, pd); pd ^= 1;
+        { const long long a = clock64(); mbar_wait(&S->bar_d, pd); pd ^= 1; if (twd) twd[l] += clock64() - a; }
         fence_after_sync();
         const float* b = sbias + 128 * l + 32 * q;
+        // the whole D slice of this thread first: the next layer's MMAs start overwriting D as soon as the first halves are published
+        uint32_t r[32];
+        tmem_ld16(tl + TM_D + 32 * q, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+        tmem_ld16(tl + TM_D + 32 * q + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+        wait_ld();
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
-            uint32_t r[16];
-            tmem_ld16(tl + TM_D + 32 * q + 16 * ch, r);
-            wait_ld();
             uint32_t p1[8], p2[8], p3[8];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
                 const float4 bb = *reinterpret_cast<const float4*>(b + 16 * ch + 4 * i);
-                const float v0 = fmaxf(__uint_as_float(r[4 * i]) + bb.x, 0.f), v1 = fmaxf(__uint_as_float(r[4 * i + 1]) + bb.y, 0.f);
-                const float v2 = fmaxf(__uint_as_float(r[4 * i + 2]) + bb.z, 0.f), v3 = fmaxf(__uint_as_float(r[4 * i + 3]) + bb.w, 0.f);
+                const float v0 = fmaxf(__uint_as_float(r[16 * ch + 4 * i]) + bb.x, 0.f), v1 = fmaxf(__uint_as_float(r[16 * ch + 4 * i + 1]) + bb.y, 0.f);
+                const float v2 = fmaxf(__uint_as_float(r[16 * ch + 4 * i + 2]) + bb.z, 0.f), v3 = fmaxf(__uint_as_float(r[16 * ch + 4 * i + 3]) + bb.w, 0.f);
                 split3(v0, v1, p1[2 * i], p2[2 * i], p3[2 * i]);
                 split3(v2, v3, p1[2 * i + 1], p2[2 * i + 1], p3[2 * i + 1]);
             }
             tmem_st8(tl + TM_A + 0 * 64 + 16 * q + 8 * ch, p1);
             tmem_st8(tl + TM_A + 1 * 64 + 16 * q + 8 * ch, p2);
             tmem_st8(tl + TM_A + 2 * 64 + 16 * q + 8 * ch, p3);
+            wait_st();
+            fence_before_sync();
+            mbar_arrive(ch == 0 ? &S->bar_a : &S->bar_a1);     // units 32q+16ch.. = k-step 2q+ch of the next layer
         }
-        wait_st();
-        fence_before_sync();
-        mbar_arrive(&S->bar_a);
     }
     // ---- output layer: NN[8q-1 .. 8q+7]
-    mbar_wait(&S->bar_d, pd); pd ^= 1;
+    { const long long a = clock64(); mbar_wait(&S->bar_d, pd); pd ^= 1; if (twd) twd[2] += clock64() - a; }
     fence_after_sync();
     {
-        uint32_t r[8], r0 = 0;
-        tmem_ld8(tl + TM_D + 8 * q, r);
-        if (q) tmem_ld1(tl + TM_D + 8 * q - 1, r0);
+        uint32_t ra[8], rb[8], rc[8], a0 = 0, b0 = 0, c0 = 0;
+        tmem_ld8(tl + TM_D + 8 * q, ra);
+        tmem_ld8(tl + TM_D + 32 + 8 * q, rb);
+        tmem_ld8(tl + TM_D + 64 + 8 * q, rc);
+        if (q) { tmem_ld1(tl + TM_D + 8 * q - 1, a0); tmem_ld1(tl + TM_D + 32 + 8 * q - 1, b0); tmem_ld1(tl + TM_D + 64 + 8 * q - 1, c0); }
         wait_ld();
         const float* b3 = sbias + 256;
-        nn[0] = q ? __uint_as_float(r0) + b3[8 * q - 1] : 0.f;
+        // smallest group first: (A B3 + A B2) + A B1
+        nn[0] = q ? ((__uint_as_float(c0) + __uint_as_float(b0)) + __uint_as_float(a0)) + b3[8 * q - 1] : 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) nn[i + 1] = __uint_as_float(r[i]) + b3[8 * q + i];
+        for (int i = 0; i < 8; ++i) nn[i + 1] = ((__uint_as_float(rc[i]) + __uint_as_float(rb[i])) + __uint_as_float(ra[i])) + b3[8 * q + i];
     }
     fence_before_sync();     // the next evaluation's tcgen05.st / MMA may overwrite D and A
 }
@@ -300,19 +328,33 @@ __device__ __forceinline__ void faces_to_f(const float (&y)[8], float ylo, float
 }
 
 // MMA warp main loop: three layers per Chain evaluation until the column threads raise `stop`
-__device__ __forceinline__ void mma_warp_loop(TcShared* S, uint32_t smem_img, int lane) {
+__device__ __forceinline__ void mma_warp_loop(TcShared* S, uint32_t smem_img, int lane, long long* dbg = nullptr) {
     if (lane == 0) {
         int pa = 0, layer = 0;
+        long long tw0[3] = {0, 0, 0}, ti0[3] = {0, 0, 0}, tw1[3] = {0, 0, 0}, ti1[3] = {0, 0, 0}, n[3] = {0, 0, 0};
+        long long c0 = clock64();
         while (true) {
-            mbar_wait(&S->bar_a, pa); pa ^= 1;
+            mbar_wait(&S->bar_a, pa);
             if (*reinterpret_cast<volatile int*>(&S->stop)) break;
             fence_after_sync();
-            if (layer == 0) issue_layer<0>(S->tmem_base, smem_img, S->nprod);
-            else if (layer == 1) issue_layer<1>(S->tmem_base, smem_img, S->nprod);
-            else issue_layer<2>(S->tmem_base, smem_img, S->nprod);
+            const long long c1 = clock64();
+            if (layer == 0) issue_layer<0, 0>(S->tmem_base, smem_img, S->nprod);
+            else if (layer == 1) issue_layer<1, 0>(S->tmem_base, smem_img, S->nprod);
+            else issue_layer<2, 0>(S->tmem_base, smem_img, S->nprod);
+            const long long c2 = clock64();
+            mbar_wait(&S->bar_a1, pa); pa ^= 1;
+            fence_after_sync();
+            const long long c3 = clock64();
+            if (layer == 0) issue_layer<0, 1>(S->tmem_base, smem_img, S->nprod);
+            else if (layer == 1) issue_layer<1, 1>(S->tmem_base, smem_img, S->nprod);
+            else issue_layer<2, 1>(S->tmem_base, smem_img, S->nprod);
             mma_commit(&S->bar_d);
+            const long long c4 = clock64();
+            tw0[layer] += c1 - c0; ti0[layer] += c2 - c1; tw1[layer] += c3 - c2; ti1[layer] += c4 - c3; n[layer] += 1; c0 = c4;
             layer = layer == 2 ? 0 : layer + 1;
         }
+        if (dbg && blockIdx.x == 0)
+            for (int l = 0; l < 3; ++l) { dbg[5 * l] = tw0[l]; dbg[5 * l + 1] = ti0[l]; dbg[5 * l + 2] = tw1[l]; dbg[5 * l + 3] = ti1[l]; dbg[5 * l + 4] = n[l]; }
     }
     __syncwarp();
 }
@@ -322,6 +364,7 @@ __device__ __forceinline__ void tc_prologue(TcShared* S, unsigned char* simg, co
     if (threadIdx.x == 0) {
         mbar_init(&S->bar_w, 1);
         mbar_init(&S->bar_a, NCT);
+        mbar_init(&S->bar_a1, NCT);
         mbar_init(&S->bar_d, 1);
         S->stop = 0;
         S->nprod = nprod;
@@ -439,10 +482,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
     const float* sbias = reinterpret_cast<const float*>(smem_raw + OFF_B);
     if (warp >= NCT / 32) {
         reg_dec<REGS_MMA>();
-        if (warp == NCT / 32) mma_warp_loop(&S, smem_img, lane);
+        if (warp == NCT / 32) mma_warp_loop(&S, smem_img, lane, reinterpret_cast<long long*>(P.resid));   // P.resid is unused here: debug timers
     } else {
         reg_inc<REGS_COL>();
         const int wq = warp & 3, q = warp >> 2, c = 32 * wq + lane;
+        long long twd[4] = {0, 0, 0, 0};
+        const long long tstart = clock64();
         const uint32_t tl = S.tmem_base + ((uint32_t)(32 * wq) << 16);
         int pd = 0, xb = 0, pb = 0;
         float u[8], k1[8], y[8];
@@ -533,7 +578,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
                 S.xch[xb][c][q][0] = y[0];
                 S.xch[xb][c][q][1] = y[7];
                 float nn[9], f[8];
-                chain_eval(&S, sbias, y, nn, pd, wq, q);
+                chain_eval(&S, sbias, y, nn, pd, wq, q, twd);
                 const float ylo = q > 0 ? S.xch[xb][c][q - 1][1] : 0.f, yhi = q < 3 ? S.xch[xb][c][q + 1][0] : 0.f;
                 faces_to_f(y, ylo, yhi, nn, bot, top, kk, P.pref, q, f);
                 tmem_st8f(kaddr(tl, s + 2, q), f);
@@ -613,6 +658,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
                 }
                 if (status != ST_OK) done = true;
             }
+        }
+        if (P.resid && blockIdx.x == 0 && threadIdx.x == 0) {
+            long long* dbg = reinterpret_cast<long long*>(P.resid);
+            dbg[16] = twd[0]; dbg[17] = twd[1]; dbg[18] = twd[2]; dbg[19] = clock64() - tstart;
         }
         // release the MMA warp
         cta_bar();
