@@ -111,6 +111,16 @@ int32_t nfc_loss_grad_dev(nfc_handle* h, const float* T0, const float* colp, con
                           double* loss_sum_dev, float* grad_dev, int32_t* status, int64_t B, int64_t n_total_columns,
                           void* stream);
 int32_t nfc_sync(nfc_handle* h);
+
+/* SURVEY row f1 -- the embedded path oceananigans_convective_adjustment[_with_neural_network] (src/oceananigans_nn.jl:97-282):
+ * n_steps fixed steps of dt: explicit neural-network flux step in physical units (forward Euler stands in for Oceananigans' own
+ * time stepper), then the implicit convective adjustment of convective_adjustment! (src/oceananigans_nn.jl:3-30) as one tridiagonal
+ * solve per column.  T0 [B][Nz] and Tout [B][n_steps/save_every + 1][Nz] are PHYSICAL temperatures; heat_flux [B] is the surface
+ * temperature flux; scal = (mu_T, sigma_T, mu_wT, sigma_wT) of the two ZeroMeanUnitVarianceScalings; K is the diffusivity as the
+ * reference passes it to convective_adjustment! (already multiplied by sigma_wT/sigma_T*stop_time/Lz in the NN variant, :195).
+ * Set the weights to zero for the pure convective-adjustment baseline.  Host pointers; synchronous. */
+int32_t nfc_embedded_solve(nfc_handle* h, const float* T0, const float* heat_flux, const float* scal, float Lz, float dt, float K,
+                           float bottom_gradient, int32_t n_steps, int32_t save_every, float* Tout, int64_t B);
 /* diagnostics: attempted backward (adjoint) steps per column of the last nfc_loss_grad chunk (the analogue of naccept + nreject) */
 int32_t nfc_get_adjoint_steps(nfc_handle* h, int32_t* out, int64_t n);
 

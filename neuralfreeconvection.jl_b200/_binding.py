@@ -13,7 +13,7 @@ NFC_MAX_LAYERS = 8
 
 EXPORTS = ["nfc_create", "nfc_destroy", "nfc_last_error", "nfc_n_params", "nfc_set_weights", "nfc_set_saveat",
            "nfc_get_counters", "nfc_rhs", "nfc_solve", "nfc_diagnose_flux", "nfc_loss_grad", "nfc_rhs_dev",
-           "nfc_solve_dev", "nfc_loss_grad_dev", "nfc_sync", "nfc_measure_fp32_peak", "nfc_get_adjoint_steps"]
+           "nfc_solve_dev", "nfc_loss_grad_dev", "nfc_sync", "nfc_measure_fp32_peak", "nfc_get_adjoint_steps", "nfc_embedded_solve"]
 
 
 class NfcConfig(C.Structure):
@@ -60,6 +60,7 @@ def load():
     lib.nfc_solve_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int64, vp]
     lib.nfc_loss_grad_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int64, vp]
     lib.nfc_sync.argtypes = [vp]
+    lib.nfc_embedded_solve.argtypes = [vp, fp, fp, fp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_int32, fp, C.c_int64]
     lib.nfc_get_adjoint_steps.argtypes = [vp, ip, C.c_int64]
     lib.nfc_measure_fp32_peak.argtypes = [C.c_int32, C.c_float, dp]
     for name in EXPORTS:
@@ -222,6 +223,15 @@ class Handle:
                                                status.data_ptr() if status is not None else None, B,
                                                n_total_columns if n_total_columns is not None else B, stream),
                     "nfc_loss_grad_dev")
+
+    def embedded_solve(self, T0, heat_flux, scal, Lz, dt, K, bottom_gradient, n_steps, save_every=1):
+        """nfc_embedded_solve: explicit NN flux step + implicit convective adjustment (tridiagonal solve) per fixed step."""
+        T0, heat_flux, scal = _f32(T0), _f32(heat_flux), _f32(scal)
+        B = T0.shape[0]
+        out = np.empty((B, n_steps // save_every + 1, self.Nz), dtype=np.float32)
+        self._check(self.lib.nfc_embedded_solve(self.h, _fp(T0), _fp(heat_flux), _fp(scal), Lz, dt, K, bottom_gradient, n_steps, save_every,
+                                                _fp(out), B), "nfc_embedded_solve")
+        return out
 
     def adjoint_steps(self, n):
         out = np.zeros(n, dtype=np.int32)

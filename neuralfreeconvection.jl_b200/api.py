@@ -285,3 +285,37 @@ def _inscribe_history(path, epoch, theta, loss, runtime):
     prev[f"mean_loss/{epoch}"] = np.float64(loss)
     prev[f"runtime/{epoch}"] = np.float64(runtime)
     np.savez(path, **prev)
+
+
+# ------------------------------------------------------------------------------------------------
+# the embedded (Oceananigans-style) path, src/oceananigans_nn.jl
+# ------------------------------------------------------------------------------------------------
+def oceananigans_convective_adjustment_with_neural_network(ds, NN, T_scaling, wT_scaling, dt=600.0, K=10.0, device=0, save_every=1):
+    """Fixed-step explicit NN-flux step + implicit convective adjustment (src/oceananigans_nn.jl:158-282).  Returns T [Nz, Nt]
+    in physical units.  K is non-dimensionalised exactly like the reference does (:195)."""
+    Nz, Nt = ds.T.shape
+    Lz, stop_time = abs(float(ds.zf[0])), float(ds.times[-1])
+    Knd = wT_scaling.sigma / T_scaling.sigma * stop_time / Lz * K
+    return _embedded(ds, NN, T_scaling, wT_scaling, dt, Knd, device, save_every)
+
+
+def oceananigans_convective_adjustment(ds, dt=600.0, K=10.0, device=0, save_every=1):
+    """The pure convective-adjustment baseline (src/oceananigans_nn.jl:97-156): zero network flux, surface flux, implicit CA."""
+    NN = named_chain("dense-default", Nz=ds.T.shape[0])
+    for p_ in NN.params():
+        p_ *= 0
+    ident = ZeroMeanUnitVarianceScaling(0.0, 1.0)
+    return _embedded(ds, NN, ident, ident, dt, K, device, save_every)
+
+
+def _embedded(ds, NN, T_scaling, wT_scaling, dt, K, device, save_every):
+    Nz, Nt = ds.T.shape
+    Lz, stop_time = abs(float(ds.zf[0])), float(ds.times[-1])
+    n_steps = int(round(stop_time / dt))
+    h = B_.Handle(NN.conv_width, NN.dense_spec, 1, np.float32([0.0, 1.0]), device=device, Nz=Nz)
+    theta, _ = destructure(NN)
+    h.set_weights(theta)
+    scal = [T_scaling.mu, T_scaling.sigma, wT_scaling.mu, wT_scaling.sigma]
+    out = h.embedded_solve(ds.T[None, :, 0], [ds.metadata["temperature_flux"]], scal, Lz, dt, K,
+                           float(ds.metadata.get("dθdz_deep", ds.metadata.get("dthetadz_deep", 0.0))), n_steps, save_every)
+    return out[0].T

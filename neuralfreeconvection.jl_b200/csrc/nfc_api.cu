@@ -15,6 +15,7 @@
 #include "nfc_forward.cuh"
 #include "nfc_launch.h"
 #include "nfc_tc.cuh"
+#include "nfc_embedded.cuh"
 
 using namespace nfc;
 
@@ -88,6 +89,20 @@ int do_rhs(nfc_handle* h, const float* T, const float* colp, float pref, float* 
     rhs_init_kernel<N, WS, 0><<<grid, NW * 32, smem_bytes<N>(NW), st>>>(h->d_wpack.p, T, colp, out, nullptr, B, pref,
                                                                    h->cfg.nde_type == NFC_NDE_CONVECTIVE_ADJUSTMENT, h->cfg.reltol,
                                                                    h->cfg.abstol, h->saveat.back(), h->cfg.fixed_dt);
+    NFC_CUDA(h, cudaGetLastError());
+    h->last_launches += 1;
+    return 0;
+}
+
+template <class N>
+int do_embedded(nfc_handle* h, EmbeddedParams& P, cudaStream_t st) {
+    constexpr bool WS = Launch<N>::WS;
+    constexpr int NW = Launch<N>::NW;
+    NFC_CUDA(h, cudaFuncSetAttribute(embedded_kernel<N, WS, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<N>(NW)));
+    P.wpack = h->d_wpack.p;
+    const long long groups = (P.B + CPW - 1) / CPW;
+    const int grid = (int)std::min<long long>(h->num_sms, (groups + NW - 1) / NW);
+    embedded_kernel<N, WS, NW><<<grid, NW * 32, smem_bytes<N>(NW), st>>>(P);
     NFC_CUDA(h, cudaGetLastError());
     h->last_launches += 1;
     return 0;
@@ -524,6 +539,35 @@ int32_t nfc_diagnose_flux(nfc_handle* h, const float* Tsol, const float* colp, f
     int rc = [&]() -> int { NFC_DISPATCH(h, do_diagnose, h, h->s_true.p, h->s_colp.p, h->s_out.p, B, h->stream); }();
     if (rc) return rc;
     NFC_CUDA(h, cudaMemcpyAsync(wT, h->s_out.p, sizeof(float) * nout, cudaMemcpyDeviceToHost, h->stream));
+    NFC_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int32_t nfc_embedded_solve(nfc_handle* h, const float* T0, const float* heat_flux, const float* scal, float Lz, float dt, float K,
+                           float bottom_gradient, int32_t n_steps, int32_t save_every, float* Tout, int64_t B) {
+    if (int rc = check_ready(h, B)) return rc;
+    if (B == 0) return 0;
+    if (!T0 || !heat_flux || !scal || !Tout) return fail(h, -1, "null argument");
+    if (n_steps < 1 || save_every < 1 || !(dt > 0.f) || !(Lz > 0.f) || !(scal[1] > 0.f)) return fail(h, -2, "bad step / scaling arguments");
+    EmbeddedParams P{};
+    P.B = B; P.n_steps = n_steps; P.save_every = save_every; P.n_out = n_steps / save_every + 1;
+    P.mu_T = scal[0]; P.sigma_T = scal[1]; P.mu_wT = scal[2]; P.sigma_wT = scal[3];
+    P.dz = Lz / NZ; P.dt = dt; P.K = K; P.bottom_gradient = bottom_gradient;
+    const size_t nout = (size_t)B * P.n_out * NZ;
+    NFC_CUDA(h, h->s_T0.ensure((size_t)B * NZ));
+    NFC_CUDA(h, h->s_colp.ensure((size_t)B * 3));
+    NFC_CUDA(h, h->s_out.ensure(nout));
+    NFC_CUDA(h, cudaMemcpyAsync(h->s_T0.p, T0, sizeof(float) * B * NZ, cudaMemcpyHostToDevice, h->stream));
+    NFC_CUDA(h, cudaMemcpyAsync(h->s_colp.p, heat_flux, sizeof(float) * B, cudaMemcpyHostToDevice, h->stream));
+    P.T0 = h->s_T0.p; P.heat_flux = h->s_colp.p; P.Tout = h->s_out.p;
+    h->last_launches = 0;
+    NFC_CUDA(h, cudaEventRecord(h->ev[0], h->stream));
+    int rc = [&]() -> int { NFC_DISPATCH(h, do_embedded, h, P, h->stream); }();
+    if (rc) return rc;
+    NFC_CUDA(h, cudaEventRecord(h->ev[1], h->stream));
+    h->ev_fwd_valid = true;
+    h->last_columns = B;
+    NFC_CUDA(h, cudaMemcpyAsync(Tout, h->s_out.p, sizeof(float) * nout, cudaMemcpyDeviceToHost, h->stream));
     NFC_CUDA(h, cudaStreamSynchronize(h->stream));
     return 0;
 }

@@ -402,7 +402,7 @@ static void tape_eval(const dtape_t *tp, int *pn, float t, float *u, int N) {
 
 /* backward pass of one column: g (double, un-normalised: caller scales by 2/N_total) */
 static void adjoint_continuous(const net_t *n, const float *th, const float *colp, float pref, const float *saveat, int n_save, const float *resid,
-                               const dtape_t *tape, float reltol, float abstol, float fixed_dt, double *g, double *gstep, float *lam_out,
+                               const dtape_t *tape, float reltol, float abstol, float fixed_dt, double *g, double *gstep, double *gnull, float *lam_out,
                                int *nacc, int *nrej, actbuf_t *ab) {
     int N = n->Nz; float lam[MAXW], lams[7][MAXW], kap[7][MAXW], us[7][MAXW], lnew[MAXW], tmp[MAXW];
     *nacc = 0; *nrej = 0;
@@ -430,15 +430,12 @@ static void adjoint_continuous(const net_t *n, const float *th, const float *col
                 float bw = 0.f; { float b[6]; a_row(7, b); if (s <= 6) bw = h * b[s - 1]; }
                 if (bw != 0.f) {
                     for (int i = 0; i < N; ++i) tmp[i] = bw * lams[s - 1][i];
-                    float dummy[MAXW]; for (int i = 0; i < N; ++i) dummy[i] = 0.f;
-                    rhs_vjp(n, th, us[s - 1], colp, pref, tmp, dummy, gstep, ab);
-                    for (int i = 0; i < N; ++i) kap[s - 1][i] = dummy[i] / bw;
+                    float scaled[MAXW]; for (int i = 0; i < N; ++i) scaled[i] = 0.f;
+                    rhs_vjp(n, th, us[s - 1], colp, pref, tmp, scaled, gstep, ab);
+                    for (int i = 0; i < N; ++i) kap[s - 1][i] = scaled[i] / bw;
                 } else {
-                    double *gnull = gstep; /* weight zero: evaluate J^T lam without touching the quadrature */
-                    double keep0 = 0; (void)keep0; (void)gnull;
-                    static __thread double *scratch = NULL; static __thread int64_t scratch_n = 0;
-                    if (scratch_n < n->n_params) { scratch = (double *)realloc(scratch, sizeof(double) * n->n_params); scratch_n = n->n_params; }
-                    rhs_vjp(n, th, us[s - 1], colp, pref, lams[s - 1], kap[s - 1], scratch, ab);
+                    /* stage 7 has quadrature weight 0: J^T lam is needed (error estimate), its parameter part is discarded */
+                    rhs_vjp(n, th, us[s - 1], colp, pref, lams[s - 1], kap[s - 1], gnull, ab);
                 }
             }
             memcpy(lnew, lams[6], sizeof(float) * N);
@@ -490,18 +487,19 @@ int oracle_loss_grad_continuous(int Nz, int conv_width, int n_layers, const int 
         actbuf_t *ab = (actbuf_t *)malloc(sizeof(actbuf_t));
         double *g = gall + (size_t)tid * n.n_params;
         double *gstep = (double *)malloc(sizeof(double) * n.n_params);
+        double *gnull = (double *)malloc(sizeof(double) * n.n_params);
         float *resid = (float *)malloc(sizeof(float) * n_save * Nz);
 #pragma omp for schedule(dynamic, 1)
         for (int64_t b = 0; b < B; ++b) {
             int na, nr, st, ba, br; dtape_t tape = {0, 0, 0}; float lam0[MAXW];
             sse_all += forward_record(&n, theta, T0 + b * Nz, colp + b * 3, pref, saveat, n_save, reltol, abstol, fixed_dt,
                                       Ttrue + b * (int64_t)n_save * Nz, resid, &tape, &na, &nr, &st, ab);
-            adjoint_continuous(&n, theta, colp + b * 3, pref, saveat, n_save, resid, &tape, adj_reltol, adj_abstol, fixed_dt, g, gstep, lam0, &ba, &br, ab);
+            adjoint_continuous(&n, theta, colp + b * 3, pref, saveat, n_save, resid, &tape, adj_reltol, adj_abstol, fixed_dt, g, gstep, gnull, lam0, &ba, &br, ab);
             if (dT0) for (int i = 0; i < Nz; ++i) dT0[b * Nz + i] = (float)(2.0 / ntot * lam0[i]);
             if (adj_naccept) adj_naccept[b] = ba; if (adj_nreject) adj_nreject[b] = br;
             free(tape.e);
         }
-        free(ab); free(gstep); free(resid);
+        free(ab); free(gstep); free(gnull); free(resid);
     }
     for (int64_t p = 0; p < n.n_params; ++p) { double s = 0.0; for (int t = 0; t < nthreads; ++t) s += gall[(size_t)t * n.n_params + p]; grad[p] = (float)(2.0 / ntot * s); }
     free(gall);

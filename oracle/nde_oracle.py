@@ -412,3 +412,67 @@ def loss_and_grad_autograd(T0, theta, conv_width, layers, colp, glob, saveat, Tt
     loss = total / (B * n_save * Nz)
     loss.backward()
     return float(loss.detach()), th.grad.numpy().copy(), T0_t.grad.numpy().copy()
+
+
+# ----------------------------------------------------------------------------------
+# embedded path, src/oceananigans_nn.jl:3-30 (convective_adjustment!) and :158-282
+# ----------------------------------------------------------------------------------
+def convective_adjustment_matrix(T, dt, dz, K, bottom_gradient=0.0):
+    """(ld, d, ud) of convective_adjustment! (src/oceananigans_nn.jl:10-24) for one column T[Nz] (index 0 = bottom).
+    kappa_i = K where the cell-centre dT/dz < 0; the centre gradient is the mean of the two face gradients, the bottom
+    face carries the gradient BC of base_model (:84), the top (flux BC) face is zero gradient [UPSTREAM halo filling]."""
+    T = np.asarray(T)
+    N = T.size
+    gface = np.empty(N + 1, dtype=T.dtype)
+    gface[1:N] = (T[1:] - T[:-1]) / dz
+    gface[0], gface[N] = bottom_gradient, 0
+    kap = np.where(0.5 * (gface[:-1] + gface[1:]) < 0, K, 0).astype(T.dtype)
+    a = dt / dz**2
+    ld = -a * kap[1:]                                   # ld[i] couples row i+1 to i  (Julia: ld = [-a kappa[i] for i in 2:Nz])
+    ud = -a * kap[1:]                                   # ud[i] couples row i to i+1  (Julia: ud = [-a kappa[i+1] for i in 1:Nz-1])
+    d = np.empty(N, dtype=T.dtype)
+    d[:-1] = 1 + a * (kap[:-1] + kap[1:])
+    d[-1] = 1 + a * kap[-1]
+    return ld, d, ud
+
+
+def thomas(ld, d, ud, rhs):
+    """Tridiagonal solve (what `Tridiagonal(ld, d, ud) \\ T` does, src/oceananigans_nn.jl:26-27)."""
+    n = d.size
+    c, r = np.array(ud, dtype=d.dtype), np.array(rhs, dtype=d.dtype)
+    b = np.array(d)
+    for i in range(1, n):
+        w = ld[i - 1] / b[i - 1]
+        b[i] -= w * c[i - 1]
+        r[i] -= w * r[i - 1]
+    x = np.empty(n, dtype=d.dtype)
+    x[-1] = r[-1] / b[-1]
+    for i in range(n - 2, -1, -1):
+        x[i] = (r[i] - c[i] * x[i + 1]) / b[i]
+    return x
+
+
+def embedded_solve(T0, heat_flux, theta, conv_width, layers, scal, Lz, dt, K, bottom_gradient, n_steps, save_every=1,
+                   dtype=np.float64):
+    """Batched restatement of oceananigans_convective_adjustment_with_neural_network (src/oceananigans_nn.jl:158-282):
+    forward-Euler NN flux step (stand-in for Oceananigans' own time stepper [UPSTREAM]) + implicit convective adjustment.
+    scal = (mu_T, sigma_T, mu_wT, sigma_wT).  Returns T[B, n_steps//save_every + 1, Nz] (physical units)."""
+    T = np.array(T0, dtype=dtype)
+    B, Nz = T.shape
+    muT, sT, muw, sw = [dtype(x) for x in scal]
+    dz, dt, K = dtype(Lz / Nz), dtype(dt), dtype(K)
+    Q = np.asarray(heat_flux, dtype=dtype)
+    out = np.empty((B, n_steps // save_every + 1, Nz), dtype=dtype)
+    out[:, 0] = T
+    th = np.asarray(theta, dtype=dtype)
+    for step in range(1, n_steps + 1):
+        F = np.zeros((B, Nz + 1), dtype=dtype)
+        F[:, 1:Nz] = sw * nn_forward(th, conv_width, layers, (T - muT) / sT) + muw
+        F[:, Nz] = Q
+        T = T - dt * (F[:, 1:] - F[:, :-1]) / dz
+        for b in range(B):
+            ld, d, ud = convective_adjustment_matrix(T[b], dt, dz, K, dtype(bottom_gradient))
+            T[b] = thomas(ld, d, ud, T[b])
+        if step % save_every == 0:
+            out[:, step // save_every] = T
+    return out
