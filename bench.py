@@ -227,13 +227,15 @@ def main():
     hbm = {"achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs", 6650.0),
            "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback", "algorithmic_bytes": alg_bytes}
     if use_tc:
-        # tensor-core path: every fp32 product is six bf16 tcgen05 MMAs (3-way split, terms down to 2^-16), so the ceiling for
-        # FP32-faithful work is the measured dense bf16 peak / 6 (burst figure: the kernel is timed alone)
+        # tensor-core path: every fp32 product is three fp16 (default, 2-way split) or six bf16 (3-way split) tcgen05 MMAs, so the
+        # ceiling for FP32-faithful work is the measured dense 16-bit peak / 3 (or / 6); burst figure: the kernel is timed alone
         bf16_peak = peaks.get("bf16_tflops", 1590.0)
-        roofline = {"bound": "tensor", "achieved": achieved, "peak": bf16_peak / 6.0, "unit": "TFLOP/s", "frac": achieved / (bf16_peak / 6.0),
+        nsplit = 6.0 if os.environ.get("NFC_TC_SPLIT", "fp16") == "bf16" else 3.0      # MMAs per fp32 product: BF16x3 -> 6, FP16x2 (default) -> 3
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": bf16_peak / nsplit, "unit": "TFLOP/s", "frac": achieved / (bf16_peak / nsplit),
                     "traffic": 1.06e9, "traffic_source": "ncu dram__bytes r+w per launch, profiles/r01_solve_tc_kernel_ncu.txt",
-                    "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1590") + " / 6 MMAs per fp32 product (BF16x3 split)",
-                    "tensor_tflops_bf16": 6.0 * achieved, "fp32_simt_peak_measured": fp32_peak, "frac_of_fp32_simt_peak": achieved / fp32_peak,
+                    "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1590") +
+                                   (" / 6 MMAs per fp32 product (BF16x3 split)" if nsplit == 6.0 else " / 3 MMAs per fp32 product (FP16x2 split; fp16 and bf16 MMAs run at the same rate)"),
+                    "tensor_tflops_16bit": nsplit * achieved, "fp32_simt_peak_measured": fp32_peak, "frac_of_fp32_simt_peak": achieved / fp32_peak,
                     "flops_per_column_step": FLOPS_PER_COLUMN_STEP, "kernel": "solve_tc_kernel (+ rhs_init_kernel, scheduler)", "kernel_ms": kernel_ms,
                     "hbm": hbm}
     else:
@@ -279,7 +281,7 @@ def main():
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 (bf16x3-split tcgen05 MMAs, fp32 accumulate)" if use_tc else "f32", "data": "synthetic",
+            "dtype": ("f32 (fp16x2-split tcgen05 MMAs, fp32 accumulate)" if os.environ.get("NFC_TC_SPLIT", "fp16") != "bf16" else "f32 (bf16x3-split tcgen05 MMAs, fp32 accumulate)") if use_tc else "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "kernel_path": "tcgen05" if use_tc else "simt", "columns_per_gpu": B, "column_steps_per_pass_rank0": steps_per_pass,
                        "l2": "outputs (1.08 GB/step) exceed the 126 MB L2; no explicit flush", "parallelism": f"columns sharded x{world}, no collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

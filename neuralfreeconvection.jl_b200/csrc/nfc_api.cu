@@ -77,7 +77,8 @@ int do_rhs(nfc_handle* h, const float* T, const float* colp, float pref, float* 
     if (h->use_tc && h->arch == ARCH_DEFAULT) {
         const long long ntiles = (B + tc::TILE - 1) / tc::TILE;
         const int grid = (int)std::min<long long>(h->num_sms, ntiles);
-        tc::rhs_tc_kernel<<<grid, tc::NTHREADS, tc::IMG_BYTES, st>>>(h->d_wimg.p, T, colp, out, B, pref, h->cfg.nde_type == NFC_NDE_CONVECTIVE_ADJUSTMENT);
+        if (h->tc_fp16) tc::rhs_tc_kernel<tc::SplitFP16x2><<<grid, tc::NTHREADS, tc::IMG16_BYTES, st>>>(h->d_wimg.p, T, colp, out, B, pref, h->cfg.nde_type == NFC_NDE_CONVECTIVE_ADJUSTMENT);
+        else tc::rhs_tc_kernel<tc::SplitBF16x3><<<grid, tc::NTHREADS, tc::IMG_BYTES, st>>>(h->d_wimg.p, T, colp, out, B, pref, h->cfg.nde_type == NFC_NDE_CONVECTIVE_ADJUSTMENT);
         NFC_CUDA(h, cudaGetLastError());
         h->last_launches += 1;
         return 0;
@@ -190,7 +191,8 @@ int launch_solve(nfc_handle* h, SolveParams& P, cudaStream_t st, bool reset_coun
             NFC_CUDA(h, cudaMemsetAsync(h->a_resid.p, 0, 256, st));
             P.resid = h->a_resid.p;
         }
-        tc::solve_tc_kernel<<<gridt, tc::NTHREADS, tc::IMG_BYTES, st>>>(h->d_wimg.p, P);
+        if (h->tc_fp16) tc::solve_tc_kernel<tc::SplitFP16x2><<<gridt, tc::NTHREADS, tc::IMG16_BYTES, st>>>(h->d_wimg.p, P);
+        else tc::solve_tc_kernel<tc::SplitBF16x3><<<gridt, tc::NTHREADS, tc::IMG_BYTES, st>>>(h->d_wimg.p, P);
         if (P.resid) {
             long long dbg[32];
             NFC_CUDA(h, cudaStreamSynchronize(st));
@@ -333,8 +335,12 @@ int32_t nfc_create(const nfc_config* cfg, nfc_handle** out) {
     if (rc) return bail(rc);
     if (h->arch == ARCH_DEFAULT) {
         if (h->d_wimg.ensure(tc::IMG_BYTES)) { h->err = "cudaMalloc failed"; return bail(-10); }
-        if (cudaFuncSetAttribute(tc::rhs_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::IMG_BYTES) != cudaSuccess ||
-            cudaFuncSetAttribute(tc::solve_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::IMG_BYTES) != cudaSuccess) { h->err = "cudaFuncSetAttribute(tc) failed"; return bail(-10); }
+        if (cudaFuncSetAttribute(tc::rhs_tc_kernel<tc::SplitBF16x3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::IMG_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(tc::solve_tc_kernel<tc::SplitBF16x3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::IMG_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(tc::rhs_tc_kernel<tc::SplitFP16x2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::IMG16_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(tc::solve_tc_kernel<tc::SplitFP16x2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::IMG16_BYTES) != cudaSuccess) { h->err = "cudaFuncSetAttribute(tc) failed"; return bail(-10); }
+        h->tc_fp16 = true;                                       // default split: FP16x2 (3 MMAs / product); NFC_TC_SPLIT=bf16 selects BF16x3 (6)
+        if (const char* e3 = getenv("NFC_TC_SPLIT")) h->tc_fp16 = strcmp(e3, "bf16") != 0;
         if (const char* e2 = getenv("NFC_SCHED")) h->use_sched = atoi(e2) != 0;
         const char* e = getenv("NFC_TC");          // tensor-core forward path is the default for this Chain; NFC_TC=0 selects the SIMT kernels
         h->use_tc = !(e && atoi(e) == 0);
@@ -372,9 +378,28 @@ int32_t nfc_set_weights(nfc_handle* h, const float* theta, int64_t n) {
     NFC_CUDA(h, cudaMemcpyAsync(h->d_theta.p, theta, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
     int rc = [&]() -> int { NFC_DISPATCH(h, do_pack, h); }();
     if (rc) return rc;
-    if (h->arch == ARCH_DEFAULT) {
+    if (h->arch == ARCH_DEFAULT && !h->tc_fp16) {
         const int n = 128 * 32 + 128 * 128 + 32 * 128 + 288;
         tc::pack_weights_tc_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_theta.p, h->d_wimg.p);
+        NFC_CUDA(h, cudaGetLastError());
+    } else if (h->arch == ARCH_DEFAULT) {
+        // FP16x2 split: exact power-of-two scales from the weights' max / row-sum norms and the input bound |T_scaled| <= 128
+        using N0 = NetDefault;
+        auto p2 = [](double bound) { return bound > 0 ? (float)std::exp2(std::floor(std::log2(16384.0 / bound))) : 1.0f; };
+        auto norms = [&](int woff, int K, int Nn, int boff, double& wmax, double& rowsum, double& bmax) {
+            wmax = 0; rowsum = 0; bmax = 0;
+            std::vector<double> rs(Nn, 0.0);
+            for (int k = 0; k < K; ++k) for (int nn_ = 0; nn_ < Nn; ++nn_) { const double w = std::fabs((double)theta[woff + k * Nn + nn_]); wmax = std::max(wmax, w); rs[nn_] += w; }
+            for (int nn_ = 0; nn_ < Nn; ++nn_) { rowsum = std::max(rowsum, rs[nn_]); bmax = std::max(bmax, std::fabs((double)theta[boff + nn_])); }
+        };
+        double w1, r1, b1, w2, r2, b2, w3, r3, b3;
+        norms(N0::T_W0, 32, 128, N0::T_B0, w1, r1, b1);
+        norms(N0::T_HID, 128, 128, N0::T_HID + 128 * 128, w2, r2, b2);
+        norms(N0::T_WL, 128, 31, N0::T_BL, w3, r3, b3);
+        const double x0 = 128.0, a1 = r1 * x0 + b1, a2 = r2 * a1 + b2;
+        tc::Fp16Scales sc{p2(w1), p2(w2), p2(w3), p2(x0), p2(a1), p2(a2)};
+        const int n = 128 * 32 + 128 * 128 + 32 * 128 + 296;
+        tc::pack_weights_tc16_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_theta.p, h->d_wimg.p, sc);
         NFC_CUDA(h, cudaGetLastError());
     }
     NFC_CUDA(h, cudaStreamSynchronize(h->stream));

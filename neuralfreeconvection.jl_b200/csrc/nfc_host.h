@@ -44,6 +44,7 @@ struct nfc_handle {
     nfc::DevBuf<float> d_theta, d_wpack, d_saveat, d_k1, d_dt;
     nfc::DevBuf<unsigned char> d_wimg;      // tensor-core weight image (default Chain only)
     bool use_tc = false;
+    bool tc_fp16 = false;                   // tensor-core split: false = BF16x3 (6 MMAs / product), true = FP16x2 (3 MMAs, scaled operands)
     // longest-first scheduling: per-column attempted steps of the previous forward call with the same batch size
     nfc::DevBuf<int> d_work, d_order, d_hist;
     int64_t sched_B = -1;       // batch size d_work is valid for (-1: none)

@@ -18,6 +18,7 @@
 // Only the default Chain Dense(32,128,relu) -> Dense(128,128,relu) -> Dense(128,31) is instantiated here.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "nfc_device.cuh"
 
@@ -191,6 +192,7 @@ struct TcShared {
     int nprod;             // split products issued per k-step (6 = FP32-faithful; fewer only for timing experiments)
     float xch[2][TILE][4][2]; // first / last level of every quarter, exchanged between the four threads of a column (double buffered)
     float part[2][TILE][4];   // partial error norms (double buffered)
+    float rng[2][TILE][4];    // max |u_new| of each quarter (range check of accepted states)
     int newcol[TILE];         // refill hand-off between the four threads of a column
     int any;
 };
@@ -308,6 +310,195 @@ __device__ __forceinline__ void chain_eval(TcShared* S, const float* sbias, cons
     fence_before_sync();     // the next evaluation's tcgen05.st / MMA may overwrite D and A
 }
 
+
+// =====================================================================================================================
+// Split policies.  SplitBF16x3 is the scheme above.  SplitFP16x2 halves the tensor work: x = hi + lo in FP16 (11 + 11
+// significand bits), product = lo*hi + hi*lo + hi*hi (dropped lo*lo <= 2^-22), three kind::f16 MMAs per k-step.  FP16 has only 5
+// exponent bits, so every operand tensor carries an exact power-of-two scale chosen on the host (nfc_set_weights): weights by
+// their max-norm, activations by a bound propagated through the layers from |T_scaled| <= 128 (row-sum norms).  relu commutes
+// with positive scaling, so the re-scaling is folded into the bias-add FMA: v' = max(fma(D, c_l, bias'_l), 0) is already the
+// scaled activation.  Inputs beyond the bound overflow to inf and are reported as status NaN (never silently wrong).
+// =====================================================================================================================
+struct SplitBF16x3 {
+    static constexpr int IMG = IMG_BYTES, BIAS_OFF = OFF_B;
+    static constexpr float INPUT_BOUND = 3.0e38f;              // BF16 has fp32's exponent range: no bound
+    template <int LAYER, int HALF>
+    static __device__ __forceinline__ void issue(uint32_t tb, uint32_t img, int nprod) { issue_layer<LAYER, HALF>(tb, img, nprod); }
+    static __device__ __forceinline__ void eval(TcShared* S, const float* sb, const float (&y)[8], float (&nn)[9], int& pd, int wq, int q, long long* twd, bool) {
+        chain_eval(S, sb, y, nn, pd, wq, q, twd);
+    }
+};
+
+constexpr int W1H_BYTES = 128 * 32 * 2, W2H_BYTES = 128 * 128 * 2, W3H_BYTES = 64 * 128 * 2;   // layer 3: [hi; lo] stacked along N (64 rows)
+constexpr int OFF16_W1 = 0;
+constexpr int OFF16_W2 = OFF16_W1 + 2 * W1H_BYTES;
+constexpr int OFF16_W3 = OFF16_W2 + 2 * W2H_BYTES;
+constexpr int OFF16_B = OFF16_W3 + W3H_BYTES;                  // bias1'[128] bias2'[128] bias3[32] consts[8] (fp32)
+constexpr int IMG16_BYTES = OFF16_B + (128 + 128 + 32 + 8) * 4;   // 99 488 B
+struct Fp16Scales { float s_w1, s_w2, s_w3, s_a0, s_a1, s_a2; };
+
+__host__ __device__ constexpr uint32_t make_idesc16(int M, int N) {   // kind::f16: A = B = F16 (0), C = F32 (1), both K-major
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__global__ void pack_weights_tc16_kernel(const float* __restrict__ theta, unsigned char* __restrict__ img, const Fp16Scales sc) {
+    using N = Net<128, 2, 0>;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n1 = 128 * 32, n2 = 128 * 128, n3 = 32 * 128;
+    if (i < n1 + n2 + n3) {
+        float w, s;
+        int off_hi, off_lo;
+        if (i < n1) { const int n = i % 128, k = i / 128; w = theta[N::T_W0 + k * 128 + n]; s = sc.s_w1; off_hi = OFF16_W1 + umma_off(n, k, 128); off_lo = off_hi + W1H_BYTES; }
+        else if (i < n1 + n2) { const int q = i - n1, n = q % 128, k = q / 128; w = theta[N::T_HID + k * 128 + n]; s = sc.s_w2; off_hi = OFF16_W2 + umma_off(n, k, 128); off_lo = off_hi + W2H_BYTES; }
+        else {
+            const int q = i - n1 - n2, n = q % 32, k = q / 32;
+            w = n < 31 ? theta[N::T_WL + k * 31 + n] : 0.f; s = sc.s_w3;
+            off_hi = OFF16_W3 + umma_off(n, k, 64); off_lo = OFF16_W3 + umma_off(32 + n, k, 64);
+        }
+        const float ws = w * s;
+        const __half hi = __float2half_rn(ws);
+        const __half lo = __float2half_rn(ws - __half2float(hi));
+        *reinterpret_cast<__half*>(img + off_hi) = hi;
+        *reinterpret_cast<__half*>(img + off_lo) = lo;
+    } else if (i < n1 + n2 + n3 + 296) {
+        const int q = i - n1 - n2 - n3;
+        float v = 0.f;
+        if (q < 128) v = theta[N::T_B0 + q] * sc.s_a1;                                     // bias'_1 = b1 * s_a1
+        else if (q < 256) v = theta[N::T_HID + 128 * 128 + (q - 128)] * sc.s_a2;          // bias'_2 = b2 * s_a2
+        else if (q < 288) v = (q - 256 < 31) ? theta[N::T_BL + (q - 256)] : 0.f;          // b3 (output is un-scaled)
+        else if (q == 288) v = sc.s_a1 / (sc.s_a0 * sc.s_w1);                             // c1: D1 -> scaled a1
+        else if (q == 289) v = sc.s_a2 / (sc.s_a1 * sc.s_w2);                             // c2: D2 -> scaled a2
+        else if (q == 290) v = 1.f / (sc.s_a2 * sc.s_w3);                                 // inv3: D3 -> NN output
+        else if (q == 291) v = sc.s_a0;
+        reinterpret_cast<float*>(img + OFF16_B)[q] = v;
+    }
+}
+
+// (v0, v1) -> packed fp16 (hi) and packed fp16 residual (lo); element 0 in the low half
+__device__ __forceinline__ void split2h(float v0, float v1, uint32_t& ph, uint32_t& pl) {
+    float f0, f1;
+    asm("{\n\t.reg .b16 l, h;\n\tcvt.rn.f16x2.f32 %0, %4, %3;\n\tmov.b32 {l, h}, %0;\n\tcvt.f32.f16 %1, l;\n\tcvt.f32.f16 %2, h;\n\t}"
+        : "=r"(ph), "=f"(f0), "=f"(f1) : "f"(v0), "f"(v1));
+    const float r0 = v0 - f0, r1 = v1 - f1;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pl) : "f"(r1), "f"(r0));
+}
+
+template <int LAYER, int HALF>
+__device__ __forceinline__ void issue_layer16(uint32_t tmem_base, uint32_t smem_img) {
+    constexpr int K = LAYER == 0 ? 32 : 128, Nn = LAYER == 2 ? 64 : 128;
+    constexpr uint32_t woff = LAYER == 0 ? OFF16_W1 : (LAYER == 1 ? OFF16_W2 : OFF16_W3);
+    constexpr uint32_t wbytes = LAYER == 0 ? W1H_BYTES : W2H_BYTES;
+    constexpr uint32_t idesc = make_idesc16(128, Nn);
+    constexpr uint32_t kstep = (2u * Nn * 16u) >> 4;
+    const uint32_t d = tmem_base + TM_D;
+    const uint64_t desc0 = make_bdesc(smem_img + woff, Nn);
+    const uint32_t lo0 = (uint32_t)desc0, hi0 = (uint32_t)(desc0 >> 32);
+    const uint32_t a_base = tmem_base + TM_A;
+    if (LAYER == 2) {            // stacked [B_hi; B_lo]: D[:, 0:32] + D[:, 32:64] = A (B_hi + B_lo), a split lo first
+#pragma unroll
+        for (int sA = 1; sA >= 0; --sA)
+#pragma unroll
+            for (int j = HALF; j < K / 16; j += 2) {
+                if (sA == 1 && j == 0) mma_ts2<false>(d, a_base + sA * 64 + 8 * j, lo0 + kstep * j, hi0, idesc);
+                else mma_ts2<true>(d, a_base + sA * 64 + 8 * j, lo0 + kstep * j, hi0, idesc);
+            }
+    } else {
+        constexpr int sa[3] = {1, 0, 0};      // (a split, b split): lo*hi, hi*lo, hi*hi
+        constexpr int sb[3] = {0, 1, 0};
+#pragma unroll
+        for (int p = 0; p < 3; ++p)
+#pragma unroll
+            for (int j = HALF; j < K / 16; j += 2) {
+                const uint32_t blo = lo0 + ((sb[p] * wbytes) >> 4) + kstep * j;
+                if (p == 0 && j == 0) mma_ts2<false>(d, a_base + sa[p] * 64 + 8 * j, blo, hi0, idesc);
+                else mma_ts2<true>(d, a_base + sa[p] * 64 + 8 * j, blo, hi0, idesc);
+            }
+    }
+}
+
+// FP16x2 version of chain_eval; sb points at bias1' (then bias2', bias3, consts)
+__device__ __forceinline__ void chain_eval16(TcShared* S, const float* sb, const float (&y)[8], float (&nn)[9], int& pd, int wq, int q, long long* twd) {
+    const uint32_t tl = S->tmem_base + ((uint32_t)(32 * wq) << 16);
+    const float s_a0 = sb[291];
+    {
+        uint32_t ph[4], pl[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) split2h(y[2 * i] * s_a0, y[2 * i + 1] * s_a0, ph[i], pl[i]);
+        tmem_st4(tl + TM_A + 0 * 64 + 4 * q, ph);
+        tmem_st4(tl + TM_A + 1 * 64 + 4 * q, pl);
+        wait_st();
+        fence_before_sync();
+        mbar_arrive(&S->bar_a);
+        mbar_arrive(&S->bar_a1);
+    }
+#pragma unroll 1
+    for (int l = 0; l < 2; ++l) {
+        { const long long a = clock64(); mbar_wait(&S->bar_d, pd); pd ^= 1; if (twd) twd[l] += clock64() - a; }
+        fence_after_sync();
+        const float* b = sb + 128 * l + 32 * q;
+        const float cl = sb[288 + l];
+        uint32_t r[32];
+        tmem_ld16(tl + TM_D + 32 * q, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+        tmem_ld16(tl + TM_D + 32 * q + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+        wait_ld();
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            uint32_t ph[8], pl[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float4 bb = *reinterpret_cast<const float4*>(b + 16 * ch + 4 * i);
+                const float v0 = fmaxf(fmaf(__uint_as_float(r[16 * ch + 4 * i]), cl, bb.x), 0.f), v1 = fmaxf(fmaf(__uint_as_float(r[16 * ch + 4 * i + 1]), cl, bb.y), 0.f);
+                const float v2 = fmaxf(fmaf(__uint_as_float(r[16 * ch + 4 * i + 2]), cl, bb.z), 0.f), v3 = fmaxf(fmaf(__uint_as_float(r[16 * ch + 4 * i + 3]), cl, bb.w), 0.f);
+                split2h(v0, v1, ph[2 * i], pl[2 * i]);
+                split2h(v2, v3, ph[2 * i + 1], pl[2 * i + 1]);
+            }
+            tmem_st8(tl + TM_A + 0 * 64 + 16 * q + 8 * ch, ph);
+            tmem_st8(tl + TM_A + 1 * 64 + 16 * q + 8 * ch, pl);
+            wait_st();
+            fence_before_sync();
+            mbar_arrive(ch == 0 ? &S->bar_a : &S->bar_a1);
+        }
+    }
+    { const long long a = clock64(); mbar_wait(&S->bar_d, pd); pd ^= 1; if (twd) twd[2] += clock64() - a; }
+    fence_after_sync();
+    {
+        uint32_t ra[8], rb[8], a0 = 0, b0 = 0;
+        tmem_ld8(tl + TM_D + 8 * q, ra);
+        tmem_ld8(tl + TM_D + 32 + 8 * q, rb);
+        if (q) { tmem_ld1(tl + TM_D + 8 * q - 1, a0); tmem_ld1(tl + TM_D + 32 + 8 * q - 1, b0); }
+        wait_ld();
+        const float* b3 = sb + 256;
+        const float inv3 = sb[290];
+        nn[0] = q ? fmaf(__uint_as_float(b0) + __uint_as_float(a0), inv3, b3[8 * q - 1]) : 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) nn[i + 1] = fmaf(__uint_as_float(rb[i]) + __uint_as_float(ra[i]), inv3, b3[8 * q + i]);
+    }
+    fence_before_sync();
+}
+
+struct SplitFP16x2 {
+    static constexpr int IMG = IMG16_BYTES, BIAS_OFF = OFF16_B;
+    template <int LAYER, int HALF>
+    static __device__ __forceinline__ void issue(uint32_t tb, uint32_t img, int) { issue_layer16<LAYER, HALF>(tb, img); }
+    static constexpr float INPUT_BOUND = 128.f;
+    // The operand scales assume |T_scaled| <= 128 (the hidden-layer bounds then hold rigorously).  The network input is SATURATED
+    // at the bound: inside the adaptive solver only wildly wrong trial steps get there and the error estimate rejects them exactly
+    // as in FP32 (the flux divergence itself uses the unclamped state); the solver flags a column whose ACCEPTED state leaves the
+    // range (status NaN).  With `poison` (nfc_rhs: no controller) an out-of-range or NaN input yields NaN output instead.
+    static __device__ __forceinline__ void eval(TcShared* S, const float* sb, const float (&y)[8], float (&nn)[9], int& pd, int wq, int q, long long* twd,
+                                                bool poison) {
+        float yc[8];
+        bool bad = false;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { yc[i] = fminf(fmaxf(y[i], -INPUT_BOUND), INPUT_BOUND); bad |= !(fabsf(y[i]) <= INPUT_BOUND); }
+        chain_eval16(S, sb, yc, nn, pd, wq, q, twd);
+        if (poison && bad) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) nn[i] = __int_as_float(0x7fc00000);
+        }
+    }
+};
+
 // f (8 levels of this thread) from the Chain output and the stage input: faces k = 8q .. 8q+8,
 // F_0 = bottom, F_32 = top, else NN[k-1] - min(0, K_CA (y_k - y_{k-1}) / dz);  f_k = -pref (F_{k+1} - F_k) / dz
 // ylo = y_{8q-1} (from quarter q-1), yhi = y_{8q+8} (from quarter q+1)
@@ -328,6 +519,7 @@ __device__ __forceinline__ void faces_to_f(const float (&y)[8], float ylo, float
 }
 
 // MMA warp main loop: three layers per Chain evaluation until the column threads raise `stop`
+template <class SP>
 __device__ __forceinline__ void mma_warp_loop(TcShared* S, uint32_t smem_img, int lane, long long* dbg = nullptr) {
     if (lane == 0) {
         int pa = 0, layer = 0;
@@ -338,16 +530,16 @@ __device__ __forceinline__ void mma_warp_loop(TcShared* S, uint32_t smem_img, in
             if (*reinterpret_cast<volatile int*>(&S->stop)) break;
             fence_after_sync();
             const long long c1 = clock64();
-            if (layer == 0) issue_layer<0, 0>(S->tmem_base, smem_img, S->nprod);
-            else if (layer == 1) issue_layer<1, 0>(S->tmem_base, smem_img, S->nprod);
-            else issue_layer<2, 0>(S->tmem_base, smem_img, S->nprod);
+            if (layer == 0) SP::template issue<0, 0>(S->tmem_base, smem_img, S->nprod);
+            else if (layer == 1) SP::template issue<1, 0>(S->tmem_base, smem_img, S->nprod);
+            else SP::template issue<2, 0>(S->tmem_base, smem_img, S->nprod);
             const long long c2 = clock64();
             mbar_wait(&S->bar_a1, pa); pa ^= 1;
             fence_after_sync();
             const long long c3 = clock64();
-            if (layer == 0) issue_layer<0, 1>(S->tmem_base, smem_img, S->nprod);
-            else if (layer == 1) issue_layer<1, 1>(S->tmem_base, smem_img, S->nprod);
-            else issue_layer<2, 1>(S->tmem_base, smem_img, S->nprod);
+            if (layer == 0) SP::template issue<0, 1>(S->tmem_base, smem_img, S->nprod);
+            else if (layer == 1) SP::template issue<1, 1>(S->tmem_base, smem_img, S->nprod);
+            else SP::template issue<2, 1>(S->tmem_base, smem_img, S->nprod);
             mma_commit(&S->bar_d);
             const long long c4 = clock64();
             tw0[layer] += c1 - c0; ti0[layer] += c2 - c1; tw1[layer] += c3 - c2; ti1[layer] += c4 - c3; n[layer] += 1; c0 = c4;
@@ -360,7 +552,7 @@ __device__ __forceinline__ void mma_warp_loop(TcShared* S, uint32_t smem_img, in
 }
 
 // common prologue: barriers, TMEM allocation, weight image.  Returns after everything is visible to all threads.
-__device__ __forceinline__ void tc_prologue(TcShared* S, unsigned char* simg, const unsigned char* gimg, int warp, int nprod = 6) {
+__device__ __forceinline__ void tc_prologue(TcShared* S, unsigned char* simg, const unsigned char* gimg, int warp, int img_bytes, int nprod = 6) {
     if (threadIdx.x == 0) {
         mbar_init(&S->bar_w, 1);
         mbar_init(&S->bar_a, NCT);
@@ -372,9 +564,9 @@ __device__ __forceinline__ void tc_prologue(TcShared* S, unsigned char* simg, co
     __syncthreads();
     if (warp == NCT / 32) tmem_alloc(&S->tmem_base, TM_COLS);
     if (threadIdx.x == 0) {
-        mbar_expect_tx(&S->bar_w, IMG_BYTES);
-        for (unsigned off = 0; off < (unsigned)IMG_BYTES; off += 32768u) {
-            const unsigned n = IMG_BYTES - off < 32768u ? IMG_BYTES - off : 32768u;
+        mbar_expect_tx(&S->bar_w, img_bytes);
+        for (unsigned off = 0; off < (unsigned)img_bytes; off += 32768u) {
+            const unsigned n = img_bytes - off < 32768u ? img_bytes - off : 32768u;
             bulk_g2s(simg + off, gimg + off, n, &S->bar_w);
         }
     }
@@ -386,19 +578,20 @@ __device__ __forceinline__ void tc_prologue(TcShared* S, unsigned char* simg, co
 }
 
 // ---- test / nfc_rhs kernel: f(T) for whole tiles of 128 columns ---------------------------------------------------------
+template <class SP>
 __global__ void __launch_bounds__(NTHREADS, 1)
 rhs_tc_kernel(const unsigned char* __restrict__ gimg, const float* __restrict__ T, const float* __restrict__ colp, float* __restrict__ out,
               long long B, float pref, int use_kca) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ TcShared S;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    tc_prologue(&S, smem_raw, gimg, warp);
+    tc_prologue(&S, smem_raw, gimg, warp, SP::IMG);
     const uint32_t smem_img = smem_u32(smem_raw);
-    const float* sbias = reinterpret_cast<const float*>(smem_raw + OFF_B);
+    const float* sbias = reinterpret_cast<const float*>(smem_raw + SP::BIAS_OFF);
     const long long ntiles = (B + TILE - 1) / TILE;
     if (warp >= NCT / 32) {
         reg_dec<REGS_MMA>();
-        if (warp == NCT / 32) mma_warp_loop(&S, smem_img, lane);
+        if (warp == NCT / 32) mma_warp_loop<SP>(&S, smem_img, lane);
     } else {
         reg_inc<REGS_COL>();
         const int wq = warp & 3, q = warp >> 2, c = 32 * wq + lane;
@@ -415,7 +608,7 @@ rhs_tc_kernel(const unsigned char* __restrict__ gimg, const float* __restrict__ 
             xb ^= 1;
             S.xch[xb][c][q][0] = y[0];
             S.xch[xb][c][q][1] = y[7];
-            chain_eval(&S, sbias, y, nn, pd, wq, q);          // its mbarrier traffic orders the exchange (double buffered)
+            SP::eval(&S, sbias, y, nn, pd, wq, q, nullptr, true);   // its mbarrier traffic orders the exchange (double buffered)
             const float bot = ok ? colp[col * 3 + 0] : 0.f, top = ok ? colp[col * 3 + 1] : 0.f;
             const float kk = (ok && use_kca) ? colp[col * 3 + 2] * (float)NZ : 0.f;
             const float ylo = q > 0 ? S.xch[xb][c][q - 1][1] : 0.f, yhi = q < 3 ? S.xch[xb][c][q + 1][0] : 0.f;
@@ -473,16 +666,17 @@ __device__ __forceinline__ void combine6(uint32_t tl, int q, const float (&k1)[8
     for (int i = 0; i < 8; ++i) acc[i] = fmaf(coef[5], kb[i], acc[i]);
 }
 
+template <class SP>
 __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned char* __restrict__ gimg, const SolveParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ TcShared S;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    tc_prologue(&S, smem_raw, gimg, warp, (P.tape_cap >= 1 && P.tape_cap <= 6) ? P.tape_cap : 6);   // tape_cap is unused by this kernel: timing knob
+    tc_prologue(&S, smem_raw, gimg, warp, SP::IMG, (P.tape_cap >= 1 && P.tape_cap <= 6) ? P.tape_cap : 6);   // tape_cap is unused by this kernel: timing knob
     const uint32_t smem_img = smem_u32(smem_raw);
-    const float* sbias = reinterpret_cast<const float*>(smem_raw + OFF_B);
+    const float* sbias = reinterpret_cast<const float*>(smem_raw + SP::BIAS_OFF);
     if (warp >= NCT / 32) {
         reg_dec<REGS_MMA>();
-        if (warp == NCT / 32) mma_warp_loop(&S, smem_img, lane, reinterpret_cast<long long*>(P.resid));   // P.resid is unused here: debug timers
+        if (warp == NCT / 32) mma_warp_loop<SP>(&S, smem_img, lane, reinterpret_cast<long long*>(P.resid));   // P.resid is unused here: debug timers
     } else {
         reg_inc<REGS_COL>();
         const int wq = warp & 3, q = warp >> 2, c = 32 * wq + lane;
@@ -578,7 +772,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
                 S.xch[xb][c][q][0] = y[0];
                 S.xch[xb][c][q][1] = y[7];
                 float nn[9], f[8];
-                chain_eval(&S, sbias, y, nn, pd, wq, q, twd);
+                SP::eval(&S, sbias, y, nn, pd, wq, q, twd, false);
                 const float ylo = q > 0 ? S.xch[xb][c][q - 1][1] : 0.f, yhi = q < 3 ? S.xch[xb][c][q + 1][0] : 0.f;
                 faces_to_f(y, ylo, yhi, nn, bot, top, kk, P.pref, q, f);
                 tmem_st8f(kaddr(tl, s + 2, q), f);
@@ -601,6 +795,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
             }
             pb ^= 1;
             S.part[pb][c][q] = part;
+            {
+                float m = fabsf(y[0]);
+#pragma unroll
+                for (int i = 1; i < 8; ++i) m = fmaxf(m, fabsf(y[i]));
+                S.rng[pb][c][q] = m;
+            }
             // dense output in power basis, u(t + th h) = u + h th (k1 + th (c2 + th (c3 + th c4))): computed by the whole warp
             // (tensor-memory loads are warp-collective), consumed below under lane-divergent control flow
             float c2[8], c3[8], c4[8];
@@ -627,6 +827,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
                     qq = fmaxf(0.1f, fminf(5.0f, qq / 0.9f));
                     accept = ee <= 1.0f;
                     dtnew = accept ? hs / qq : hs / fminf(5.0f, q11 / 0.9f);
+                }
+                if (accept && !(fmaxf(fmaxf(S.rng[pb][c][0], S.rng[pb][c][1]), fmaxf(S.rng[pb][c][2], S.rng[pb][c][3])) <= SP::INPUT_BOUND)) {
+                    status = ST_NAN; accept = false;             // an accepted state outside the operand range of the split: report, never guess
                 }
                 if (accept) {
                     const float tn = last ? P.tf : t + hs;

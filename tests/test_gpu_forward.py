@@ -238,3 +238,37 @@ def test_kca_sweep_ensemble(nfc, gpu_ok):
     # larger K_CA = stiffer = more steps (figure C's runtime curve)
     steps = (r["naccept"] + r["nreject"]).reshape(100, 9).sum(1)
     assert steps[-1] > 3 * steps[0]
+
+
+@pytest.mark.parametrize("split", ["fp16", "bf16"])
+def test_tensor_core_splits_are_fp32_faithful(nfc, gpu_ok, monkeypatch, split):
+    """Both tensor-core split schemes (FP16x2 with power-of-two operand scaling = default, BF16x3) meet the 1e-5 RHS bar with
+    a large margin, for O(1) weights, the reference's x1e-5 weights and x100 weights (scaling / exponent-range check)."""
+    monkeypatch.setenv("NFC_TC", "1")
+    monkeypatch.setenv("NFC_TC_SPLIT", split)
+    g = golden("rhs_dense-default.npz")
+    cw, layers = O.chain_spec()
+    for scale in (1.0, 1e-5, 100.0):
+        theta = (g["theta"] * scale).astype(np.float32)
+        h = nfc.Handle(cw, layers, 1, nfc.synthetic.saveat(9))
+        h.set_weights(theta)
+        f = h.rhs(g["T"], g["colp"], g["glob"])
+        ref = O.rhs(g["T"], theta, cw, layers, g["colp"], g["glob"], np.float64)
+        assert rel_l2(f, ref).max() < 2e-6
+
+
+def test_tensor_core_out_of_range_input_is_flagged_not_wrong(nfc, gpu_ok, monkeypatch):
+    """FP16x2 assumes |T_scaled| <= 128 (operand scaling); a column beyond that must end as status NaN, its neighbours untouched."""
+    monkeypatch.setenv("NFC_TC", "1")
+    monkeypatch.setenv("NFC_TC_SPLIT", "fp16")
+    d = nfc.synthetic.make_columns("ocean", B=200, seed=8)
+    sv = nfc.synthetic.saveat(5)
+    h, cw, layers = _handle(nfc, saveat=sv)
+    h.set_weights(O.glorot_theta(cw, layers, 0, 0.3))
+    ok = h.solve(d["T0"], d["colp"], d["glob"])
+    T0 = d["T0"].copy()
+    T0[17] *= 1.0e4
+    r = h.solve(T0, d["colp"], d["glob"])
+    assert r["status"][17] == 2
+    keep = np.arange(200) != 17
+    assert (r["status"][keep] == 0).all() and np.array_equal(r["T"][keep], ok["T"][keep])
