@@ -121,6 +121,14 @@ int32_t nfc_sync(nfc_handle* h);
  * Set the weights to zero for the pure convective-adjustment baseline.  Host pointers; synchronous. */
 int32_t nfc_embedded_solve(nfc_handle* h, const float* T0, const float* heat_flux, const float* scal, float Lz, float dt, float K,
                            float bottom_gradient, int32_t n_steps, int32_t save_every, float* Tout, int64_t B);
+/* SURVEY row f3 -- compute_nde_solution_history (src/testing.jl:42-79): every saved epoch's Chain x every simulation, which the
+ * reference runs as epochs x simulations serial solve_nde calls.  Here it is one launch over an ensemble: member e (one epoch's
+ * Flux.destructure vector theta_members[e][n_params], same Chain architecture as the handle) integrates the S columns
+ * T0[e*S .. (e+1)*S) with its own weights; Tout [E*S][n_save][Nz].  The handle's own weights (nfc_set_weights) are neither needed
+ * nor touched.  Columns follow exactly the arithmetic of nfc_solve with the FP32 kernels (NFC_TC=0).  Host pointers; synchronous. */
+int32_t nfc_solve_ensemble(nfc_handle* h, const float* theta_members, int64_t n_members, const float* T0, const float* colp,
+                           const float* glob, float* Tout, int32_t* naccept, int32_t* nreject, int32_t* status,
+                           int64_t columns_per_member);
 /* diagnostics: attempted backward (adjoint) steps per column of the last nfc_loss_grad chunk (the analogue of naccept + nreject) */
 int32_t nfc_get_adjoint_steps(nfc_handle* h, int32_t* out, int64_t n);
 

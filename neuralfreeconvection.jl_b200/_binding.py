@@ -13,7 +13,8 @@ NFC_MAX_LAYERS = 8
 
 EXPORTS = ["nfc_create", "nfc_destroy", "nfc_last_error", "nfc_n_params", "nfc_set_weights", "nfc_set_saveat",
            "nfc_get_counters", "nfc_rhs", "nfc_solve", "nfc_diagnose_flux", "nfc_loss_grad", "nfc_rhs_dev",
-           "nfc_solve_dev", "nfc_loss_grad_dev", "nfc_sync", "nfc_measure_fp32_peak", "nfc_get_adjoint_steps", "nfc_embedded_solve"]
+           "nfc_solve_dev", "nfc_loss_grad_dev", "nfc_sync", "nfc_measure_fp32_peak", "nfc_get_adjoint_steps", "nfc_embedded_solve",
+           "nfc_solve_ensemble"]
 
 
 class NfcConfig(C.Structure):
@@ -55,6 +56,7 @@ def load():
     lib.nfc_rhs.argtypes = [vp, fp, fp, fp, fp, C.c_int64]
     lib.nfc_solve.argtypes = [vp, fp, fp, fp, fp, ip, ip, ip, C.c_int64]
     lib.nfc_diagnose_flux.argtypes = [vp, fp, fp, fp, C.c_int64]
+    lib.nfc_solve_ensemble.argtypes = [vp, fp, C.c_int64, fp, fp, fp, fp, ip, ip, ip, C.c_int64]
     lib.nfc_loss_grad.argtypes = [vp, fp, fp, fp, fp, dp, fp, ip, C.c_int64]
     lib.nfc_rhs_dev.argtypes = [vp, vp, vp, vp, vp, C.c_int64, vp]
     lib.nfc_solve_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int64, vp]
@@ -179,6 +181,21 @@ class Handle:
         na, nr, st = (np.zeros(B, dtype=np.int32) for _ in range(3))
         self._check(self.lib.nfc_solve(self.h, _fp(T0), _fp(colp), _fp(glob), _fp(out), _ip(na), _ip(nr), _ip(st), B),
                     "nfc_solve")
+        return dict(T=out, naccept=na, nreject=nr, status=st)
+
+    def solve_ensemble(self, theta_members, T0, colp, glob):
+        """nfc_solve_ensemble: member e integrates T0[e] ([E][S][Nz]) with its own weights theta_members[e] (src/testing.jl:42-79)."""
+        theta_members, T0, colp, glob = _f32(theta_members), _f32(T0), _f32(colp), _f32(glob)
+        if theta_members.ndim != 2 or theta_members.shape[1] != self.n_params:
+            raise ValueError(f"theta_members must be [E][{self.n_params}], got {theta_members.shape}")
+        E = theta_members.shape[0]
+        if T0.ndim != 3 or T0.shape[0] != E or colp.shape[:2] != T0.shape[:2]:
+            raise ValueError("T0 must be [E][S][Nz] and colp [E][S][3]")
+        S = T0.shape[1]
+        out = np.empty((E, S, self.n_save, self.Nz), dtype=np.float32)
+        na, nr, st = (np.zeros((E, S), dtype=np.int32) for _ in range(3))
+        self._check(self.lib.nfc_solve_ensemble(self.h, _fp(theta_members), E, _fp(T0), _fp(colp), _fp(glob), _fp(out), _ip(na), _ip(nr),
+                                                _ip(st), S), "nfc_solve_ensemble")
         return dict(T=out, naccept=na, nreject=nr, status=st)
 
     def diagnose_flux(self, Tsol, colp):

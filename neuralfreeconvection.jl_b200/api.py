@@ -288,6 +288,47 @@ def _inscribe_history(path, epoch, theta, loss, runtime):
 
 
 # ------------------------------------------------------------------------------------------------
+# epoch-history evaluators, src/testing.jl
+# ------------------------------------------------------------------------------------------------
+def load_history(history):
+    """The `neural_network/<e>` entries of a training history (what inscribe_history wrote) as [epochs][n_params]."""
+    if isinstance(history, str):
+        history = dict(np.load(history if history.endswith(".npz") else history + ".npz"))
+    if isinstance(history, dict):
+        epochs = sorted(int(k.split("/")[1]) for k in history if k.startswith("neural_network/"))
+        return np.stack([np.asarray(history[f"neural_network/{e}"], dtype=np.float32) for e in epochs])
+    return np.asarray(history, dtype=np.float32)
+
+
+def compute_nde_solution_history(datasets, NDEType, nde_params, algorithm, NN, history, T_scaling, device=0):
+    """compute_nde_solution_history (src/testing.jl:42-79): the NDE solution of every simulation under every saved epoch's
+    network.  The reference runs epochs x simulations solve_nde calls one after the other; here all of them are one
+    nfc_solve_ensemble launch (member = epoch).  `NN` gives the architecture, `history` the per-epoch destructured weights
+    (npz path / dict as written by inscribe_history, or an [epochs][n_params] array).
+    Returns (solution_history, loss_history): {id: [epochs, Nz, Nt]} in physical units and {id: [epochs, Nt]} with
+    Flux.Losses.mse(T_true, T, agg = x -> mean(x, dims=1)), i.e. the mean over depth per saved time."""
+    _check_alg(algorithm)
+    thetas = load_history(history)
+    ids = sorted(datasets.keys())
+    ds0 = datasets[ids[0]]
+    nde = NDEType(NN, ds0, device=device)
+    P = np.stack([np.asarray(nde_params[i], dtype=np.float32) for i in ids])
+    if P.shape[-1] < 7:
+        raise IndexError("solve_nde(ds, ...) reads nde_params[7] (src/solve.jl:30): pass ConvectiveAdjustmentNDEParameters")
+    colp, glob = _split_params(nde, P if nde.nde_type == 1 else P[:, :6])
+    T0 = np.stack([T_scaling(datasets[i].T[:, 0]) for i in ids]).astype(np.float32)          # [S, Nz]
+    E = thetas.shape[0]
+    res = nde.handle.solve_ensemble(thetas, np.broadcast_to(T0, (E,) + T0.shape), np.broadcast_to(colp, (E,) + colp.shape), glob)
+    sol = T_scaling.inv(res["T"].astype(np.float64))                                           # [E, S, Nt, Nz]
+    solution_history, loss_history = {}, {}
+    for s_, i in enumerate(ids):
+        solution_history[i] = np.transpose(sol[:, s_], (0, 2, 1))                              # [E, Nz, Nt]
+        loss_history[i] = np.mean((datasets[i].T[None] - solution_history[i]) ** 2, axis=1)    # [E, Nt]
+    nde.last = res
+    return solution_history, loss_history
+
+
+# ------------------------------------------------------------------------------------------------
 # SURVEY row f1: the embedded (Oceananigans-style) path, src/oceananigans_nn.jl
 # ------------------------------------------------------------------------------------------------
 def oceananigans_convective_adjustment_with_neural_network(ds, NN, T_scaling, wT_scaling, dt=600.0, K=10.0, device=0, save_every=1):

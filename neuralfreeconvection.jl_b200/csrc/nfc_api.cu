@@ -230,6 +230,37 @@ int do_solve(nfc_handle* h, const float* T0, const float* colp, float pref, floa
 }
 
 template <class N>
+int do_solve_ensemble(nfc_handle* h, const float* theta_members, int64_t E, int S, const float* T0, const float* colp, float pref, float* Tout,
+                      int* nacc, int* nrej, int* status, cudaStream_t st) {
+    constexpr bool WS = Launch<N>::WS;
+    constexpr int NW = Launch<N>::NW;
+    const long long B = (long long)E * S;
+    NFC_CUDA(h, cudaFuncSetAttribute(solve_ensemble_kernel<N, WS, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<N>(NW)));
+    NFC_CUDA(h, h->e_theta.ensure((size_t)E * N::T_TOTAL));
+    NFC_CUDA(h, h->e_wpack.ensure((size_t)E * N::P_TOTAL));
+    NFC_CUDA(h, h->d_k1.ensure((size_t)B * NZ));
+    NFC_CUDA(h, h->d_dt.ensure((size_t)B));
+    NFC_CUDA(h, cudaMemcpyAsync(h->e_theta.p, theta_members, sizeof(float) * (size_t)E * N::T_TOTAL, cudaMemcpyHostToDevice, st));
+    pack_weights_kernel<N><<<dim3((N::P_TOTAL + 255) / 256, (unsigned)E), 256, 0, st>>>(h->e_theta.p, h->e_wpack.p);
+    NFC_CUDA(h, cudaGetLastError());
+    SolveParams P{};
+    P.wpack = h->e_wpack.p; P.T0 = T0; P.colp = colp; P.k1_init = h->d_k1.p; P.dt_init = h->d_dt.p; P.saveat = h->d_saveat.p;
+    P.Tout = Tout; P.naccept = nacc; P.nreject = nrej; P.status = status; P.counters = h->d_counters.p; P.B = B;
+    P.n_save = h->cfg.n_save; P.max_iters = h->cfg.max_iters; P.use_kca = h->cfg.nde_type == NFC_NDE_CONVECTIVE_ADJUSTMENT;
+    P.pref = pref; P.tf = h->saveat.back(); P.reltol = h->cfg.reltol; P.abstol = h->cfg.abstol; P.fixed_dt = h->cfg.fixed_dt;
+    NFC_CUDA(h, cudaMemsetAsync(h->d_counters.p, 0, sizeof(unsigned long long) * CTR_COUNT, st));
+    NFC_CUDA(h, cudaEventRecord(h->ev[0], st));
+    const int grid = (int)std::min<long long>(h->num_sms, E);
+    solve_ensemble_kernel<N, WS, NW><<<grid, NW * 32, smem_bytes<N>(NW), st>>>(P, E, S, h->d_k1.p, h->d_dt.p);
+    NFC_CUDA(h, cudaGetLastError());
+    NFC_CUDA(h, cudaEventRecord(h->ev[1], st));
+    h->ev_fwd_valid = true;
+    h->last_launches += 2;
+    h->last_columns = B;
+    return 0;
+}
+
+template <class N>
 int do_loss_grad(nfc_handle* h, const float* T0, const float* colp, float pref, const float* Ttrue, double* loss_sum_dev, float* grad_dev,
                  int* status, int64_t B, int64_t n_total_columns, cudaStream_t st) {
     return adjoint_loss_grad<N, Launch<N>::WS, Launch<N>::NW>(h, T0, colp, pref, Ttrue, loss_sum_dev, grad_dev, status, B, n_total_columns, st);
@@ -358,6 +389,7 @@ int32_t nfc_destroy(nfc_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     h->d_work.release(); h->d_order.release(); h->d_hist.release(); h->d_wimg.release(); h->d_theta.release(); h->d_wpack.release(); h->d_saveat.release(); h->d_k1.release(); h->d_dt.release(); h->d_counters.release();
+    h->e_theta.release(); h->e_wpack.release();
     h->s_T0.release(); h->s_colp.release(); h->s_out.release(); h->s_true.release(); h->s_grad.release();
     h->s_nacc.release(); h->s_nrej.release(); h->s_status.release(); h->s_loss.release();
     h->a_resid.release(); h->a_tape.release(); h->a_gacc.release(); h->a_tlen.release(); h->a_adjsteps.release(); h->a_gsum.release();
@@ -543,6 +575,42 @@ int32_t nfc_solve(nfc_handle* h, const float* T0, const float* colp, const float
                                     cudaMemcpyDeviceToHost, cs));
     }
     if (npieces > 1) NFC_CUDA(h, cudaStreamSynchronize(h->copy_stream));
+    if (naccept) NFC_CUDA(h, cudaMemcpyAsync(naccept, h->s_nacc.p, sizeof(int) * B, cudaMemcpyDeviceToHost, h->stream));
+    if (nreject) NFC_CUDA(h, cudaMemcpyAsync(nreject, h->s_nrej.p, sizeof(int) * B, cudaMemcpyDeviceToHost, h->stream));
+    if (status) NFC_CUDA(h, cudaMemcpyAsync(status, h->s_status.p, sizeof(int) * B, cudaMemcpyDeviceToHost, h->stream));
+    NFC_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int32_t nfc_solve_ensemble(nfc_handle* h, const float* theta_members, int64_t E, const float* T0, const float* colp, const float* glob,
+                           float* Tout, int32_t* naccept, int32_t* nreject, int32_t* status, int64_t S) {
+    if (!h) return -1;
+    if (E < 0 || S < 0) return fail(h, -2, "negative ensemble size");
+    if (E > 65535) return fail(h, -2, "at most 65535 ensemble members per call (got %lld)", (long long)E);
+    if (S > (1 << 20)) return fail(h, -2, "at most 2^20 columns per member (got %lld)", (long long)S);
+    if (E == 0 || S == 0) return 0;
+    if (!theta_members || !T0 || !colp || !glob || !Tout) return fail(h, -1, "null argument");
+    {
+        cudaError_t e = cudaSetDevice(h->device);
+        if (e != cudaSuccess) return fail(h, -10, "cudaSetDevice(%d): %s", h->device, cudaGetErrorString(e));
+    }
+    const int64_t B = E * S;
+    const size_t nout = (size_t)B * h->cfg.n_save * NZ;
+    NFC_CUDA(h, h->s_T0.ensure((size_t)B * NZ));
+    NFC_CUDA(h, h->s_colp.ensure((size_t)B * 3));
+    NFC_CUDA(h, h->s_out.ensure(nout));
+    NFC_CUDA(h, h->s_nacc.ensure(B));
+    NFC_CUDA(h, h->s_nrej.ensure(B));
+    NFC_CUDA(h, h->s_status.ensure(B));
+    NFC_CUDA(h, cudaMemcpyAsync(h->s_T0.p, T0, sizeof(float) * B * NZ, cudaMemcpyHostToDevice, h->stream));
+    NFC_CUDA(h, cudaMemcpyAsync(h->s_colp.p, colp, sizeof(float) * B * 3, cudaMemcpyHostToDevice, h->stream));
+    h->last_launches = 0;
+    int rc = [&]() -> int {
+        NFC_DISPATCH(h, do_solve_ensemble, h, theta_members, E, (int)S, h->s_T0.p, h->s_colp.p, prefactor(glob), h->s_out.p, h->s_nacc.p,
+                     h->s_nrej.p, h->s_status.p, h->stream);
+    }();
+    if (rc) return rc;
+    NFC_CUDA(h, cudaMemcpyAsync(Tout, h->s_out.p, sizeof(float) * nout, cudaMemcpyDeviceToHost, h->stream));
     if (naccept) NFC_CUDA(h, cudaMemcpyAsync(naccept, h->s_nacc.p, sizeof(int) * B, cudaMemcpyDeviceToHost, h->stream));
     if (nreject) NFC_CUDA(h, cudaMemcpyAsync(nreject, h->s_nrej.p, sizeof(int) * B, cudaMemcpyDeviceToHost, h->stream));
     if (status) NFC_CUDA(h, cudaMemcpyAsync(status, h->s_status.p, sizeof(int) * B, cudaMemcpyDeviceToHost, h->stream));

@@ -190,6 +190,22 @@ __device__ __forceinline__ void stage_weights(float* sW, const float* __restrict
     mbar_wait(bar, 0);
 }
 
+// The same for a barrier that is already initialised (count 1) and has completed `parity` phases mod 2: used when a CTA
+// replaces its weights (ensemble members).  The caller's __syncthreads() guarantees nobody still reads the old weights.
+__device__ __forceinline__ void restage_weights(float* sW, const float* __restrict__ gW, int nfloats, uint64_t* bar, unsigned parity) {
+    if (threadIdx.x == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads of sW before the async-proxy overwrite
+        const unsigned total = (unsigned)nfloats * 4u;
+        mbar_expect_tx(bar, total);
+        constexpr unsigned CHUNK = 32768u;
+        for (unsigned off = 0; off < total; off += CHUNK) {
+            unsigned n = total - off < CHUNK ? total - off : CHUNK;
+            bulk_g2s(reinterpret_cast<char*>(sW) + off, reinterpret_cast<const char*>(gW) + off, n, bar);
+        }
+    }
+    mbar_wait(bar, parity);
+}
+
 // ---- Dense layers on a warp tile ----------------------------------------------------------------------
 // out[n][c] = act(b[n] + sum_k W[k][n] in[k][c]),  in: [K][8], out: [32*NPL][8] (row = neuron), weights lane-permuted.
 template <int K, int NPL, int RS, bool RELU>

@@ -44,8 +44,11 @@ struct SolveParams {
 
 template <class N>
 __global__ void pack_weights_kernel(const float* __restrict__ theta, float* __restrict__ wpack) {
+    static_assert(N::P_TOTAL % 4 == 0, "ensemble members are staged with 16-byte aligned bulk copies");
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= N::P_TOTAL) return;
+    theta += (size_t)blockIdx.y * N::T_TOTAL;     // blockIdx.y = ensemble member (0 for the handle's own weights)
+    wpack += (size_t)blockIdx.y * N::P_TOTAL;
     const int t = packed_to_theta<N>(p);
     wpack[p] = t >= 0 ? theta[t] : 0.f;
 }
@@ -63,6 +66,56 @@ __device__ __forceinline__ void rhs_tile(const float* sW, float* ws, const float
     // the next nn_forward_tile writes sX/sA first and reaches sY only after several __syncwarp()s
 }
 
+// f(T) (MODE 0) or k1 = f(u0) plus the Hairer initial dt (MODE 1) for the 8 columns [col0, col0 + 8) below colEnd.
+template <class N, int MODE>
+__device__ __forceinline__ void rhs_init_group(const float* sW, float* ws, long long col0, long long colEnd, const float* __restrict__ T,
+                                               const float* __restrict__ colp, float* __restrict__ out, float* __restrict__ dt_out, float pref,
+                                               int use_kca, float reltol, float abstol, float tf, float fixed_dt, int lane) {
+    float y[CPW], f0[CPW], bot[CPW], top[CPW], kca[CPW];
+#pragma unroll
+    for (int c = 0; c < CPW; ++c) {
+        const long long col = col0 + c;
+        const bool ok = col < colEnd;
+        y[c] = ok ? T[col * NZ + lane] : 0.f;
+        bot[c] = ok ? colp[col * 3 + 0] : 0.f;
+        top[c] = ok ? colp[col * 3 + 1] : 0.f;
+        kca[c] = (ok && use_kca) ? colp[col * 3 + 2] : 0.f;
+    }
+    rhs_tile<N>(sW, ws, y, f0, bot, top, kca, pref, lane);
+#pragma unroll
+    for (int c = 0; c < CPW; ++c) {
+        const long long col = col0 + c;
+        if (col < colEnd) out[col * NZ + lane] = f0[c];
+    }
+    if (MODE == 1) {
+        // Hairer-Wanner initial step (OrdinaryDiffEq ode_determine_initdt, order 5)
+        float dt0[CPW], d1[CPW], y1[CPW], f1[CPW];
+#pragma unroll
+        for (int c = 0; c < CPW; ++c) {
+            const float sk = abstol + fabsf(y[c]) * reltol;
+            const float a = y[c] / sk, b = f0[c] / sk;
+            const float d0 = sqrtf(warp_sum(a * a) * (1.f / NZ));
+            d1[c] = sqrtf(warp_sum(b * b) * (1.f / NZ));
+            float t = (d0 < 1e-5f || d1[c] < 1e-5f) ? 1e-6f : 0.01f * d0 / d1[c];
+            dt0[c] = fminf(t, tf);
+            y1[c] = fmaf(dt0[c], f0[c], y[c]);
+        }
+        rhs_tile<N>(sW, ws, y1, f1, bot, top, kca, pref, lane);
+#pragma unroll
+        for (int c = 0; c < CPW; ++c) {
+            const float sk = abstol + fabsf(y[c]) * reltol;
+            const float a = (f1[c] - f0[c]) / sk;
+            const float d2 = sqrtf(warp_sum(a * a) * (1.f / NZ)) / dt0[c];
+            const float m = fmaxf(d1[c], d2);
+            const float dt1 = (m <= 1e-15f) ? fmaxf(1e-6f, dt0[c] * 1e-3f) : powf(10.0f, -(2.0f + log10f(m)) / 6.0f);
+            float dt = fminf(fminf(100.0f * dt0[c], dt1), tf);
+            if (fixed_dt > 0.f) dt = fixed_dt;
+            const long long col = col0 + c;
+            if (lane == 0 && col < colEnd) dt_out[col] = dt;
+        }
+    }
+}
+
 template <class N, bool WS, int MODE>
 __global__ void __launch_bounds__(256, 1)
 rhs_init_kernel(const float* __restrict__ wpack, const float* __restrict__ T, const float* __restrict__ colp, float* __restrict__ out,
@@ -74,51 +127,8 @@ rhs_init_kernel(const float* __restrict__ wpack, const float* __restrict__ T, co
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     float* ws = smem + (WS ? N::P_TOTAL : 0) + warp * N::S_TOTAL;
     const long long ngroups = (B + CPW - 1) / CPW;
-    for (long long g = (long long)blockIdx.x * nw + warp; g < ngroups; g += (long long)gridDim.x * nw) {
-        float y[CPW], f0[CPW], bot[CPW], top[CPW], kca[CPW];
-#pragma unroll
-        for (int c = 0; c < CPW; ++c) {
-            const long long col = g * CPW + c;
-            const bool ok = col < B;
-            y[c] = ok ? T[col * NZ + lane] : 0.f;
-            bot[c] = ok ? colp[col * 3 + 0] : 0.f;
-            top[c] = ok ? colp[col * 3 + 1] : 0.f;
-            kca[c] = (ok && use_kca) ? colp[col * 3 + 2] : 0.f;
-        }
-        rhs_tile<N>(sW, ws, y, f0, bot, top, kca, pref, lane);
-#pragma unroll
-        for (int c = 0; c < CPW; ++c) {
-            const long long col = g * CPW + c;
-            if (col < B) out[col * NZ + lane] = f0[c];
-        }
-        if (MODE == 1) {
-            // Hairer-Wanner initial step (OrdinaryDiffEq ode_determine_initdt, order 5)
-            float dt0[CPW], d1[CPW], y1[CPW], f1[CPW];
-#pragma unroll
-            for (int c = 0; c < CPW; ++c) {
-                const float sk = abstol + fabsf(y[c]) * reltol;
-                const float a = y[c] / sk, b = f0[c] / sk;
-                const float d0 = sqrtf(warp_sum(a * a) * (1.f / NZ));
-                d1[c] = sqrtf(warp_sum(b * b) * (1.f / NZ));
-                float t = (d0 < 1e-5f || d1[c] < 1e-5f) ? 1e-6f : 0.01f * d0 / d1[c];
-                dt0[c] = fminf(t, tf);
-                y1[c] = fmaf(dt0[c], f0[c], y[c]);
-            }
-            rhs_tile<N>(sW, ws, y1, f1, bot, top, kca, pref, lane);
-#pragma unroll
-            for (int c = 0; c < CPW; ++c) {
-                const float sk = abstol + fabsf(y[c]) * reltol;
-                const float a = (f1[c] - f0[c]) / sk;
-                const float d2 = sqrtf(warp_sum(a * a) * (1.f / NZ)) / dt0[c];
-                const float m = fmaxf(d1[c], d2);
-                const float dt1 = (m <= 1e-15f) ? fmaxf(1e-6f, dt0[c] * 1e-3f) : powf(10.0f, -(2.0f + log10f(m)) / 6.0f);
-                float dt = fminf(fminf(100.0f * dt0[c], dt1), tf);
-                if (fixed_dt > 0.f) dt = fixed_dt;
-                const long long col = g * CPW + c;
-                if (lane == 0 && col < B) dt_out[col] = dt;
-            }
-        }
-    }
+    for (long long g = (long long)blockIdx.x * nw + warp; g < ngroups; g += (long long)gridDim.x * nw)
+        rhs_init_group<N, MODE>(sW, ws, g * CPW, B, T, colp, out, dt_out, pref, use_kca, reltol, abstol, tf, fixed_dt, lane);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -192,13 +202,24 @@ __device__ __forceinline__ void tsit5_stages(const float* sW, float* ws, const W
     }
 }
 
-template <class N, bool RECORD>
-__device__ __forceinline__ void fill_slot(const SolveParams& P, WarpSlots* sl, int c, float& u, float& k1, double& lsum, int lane) {
+// Column queue of one ensemble member (solve_ensemble_kernel): the member's columns [base, base + count) are handed out
+// through a shared-memory counter.  The plain solve uses the global queue over all B columns.
+struct MemberQueue {
+    int* next;        // shared-memory counter
+    long long base;
+    int count;
+};
+
+template <class N, bool RECORD, bool ENS = false>
+__device__ __forceinline__ void fill_slot(const SolveParams& P, WarpSlots* sl, int c, float& u, float& k1, double& lsum, int lane,
+                                          const MemberQueue& mq = MemberQueue{nullptr, 0, 0}) {
     long long next = 0;
-    if (lane == 0) next = (long long)atomicAdd(&P.counters[CTR_QUEUE], 1ULL);
+    if (ENS) {
+        if (lane == 0) { const int q = atomicAdd(mq.next, 1); next = q < mq.count ? mq.base + q : P.B; }
+    } else if (lane == 0) next = (long long)atomicAdd(&P.counters[CTR_QUEUE], 1ULL);
     next = __shfl_sync(FULL, next, 0);
     if (next < P.B) {
-        if (P.order) next = P.order[next];
+        if (!ENS && P.order) next = P.order[next];
         u = P.T0[next * NZ + lane];
         k1 = P.k1_init[next * NZ + lane];
         int si = 0;
@@ -222,24 +243,16 @@ __device__ __forceinline__ void fill_slot(const SolveParams& P, WarpSlots* sl, i
     }
 }
 
-template <class N, bool WS, int NW, bool RECORD>
-__global__ void __launch_bounds__(NW * 32, 1) solve_kernel(const SolveParams P) {
-    extern __shared__ __align__(16) float smem[];
-    __shared__ uint64_t bar;
-    __shared__ WarpSlots slots[NW];
-    const float* sW = WS ? smem : P.wpack;
-    if (WS) stage_weights(smem, P.wpack, N::P_TOTAL, &bar);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* ws = smem + (WS ? N::P_TOTAL : 0) + warp * N::S_TOTAL;
-    WarpSlots* sl = &slots[warp];
-
+// One warp's share of the solve: fill its 8 slots from the queue, step until the queue is empty and the slots have drained.
+template <class N, bool RECORD, bool ENS>
+__device__ __forceinline__ void solve_warp(const SolveParams& P, const float* sW, float* ws, WarpSlots* sl, int lane, const MemberQueue& mq) {
     float u[CPW], ks[7][CPW], y[CPW];
     double lsum = 0.0;   // this warp's sum of squared residuals (RECORD mode)
 #pragma unroll
     for (int c = 0; c < CPW; ++c) {
 #pragma unroll
         for (int j = 1; j < 7; ++j) ks[j][c] = 0.f;
-        fill_slot<N, RECORD>(P, sl, c, u[c], ks[0][c], lsum, lane);
+        fill_slot<N, RECORD, ENS>(P, sl, c, u[c], ks[0][c], lsum, lane, mq);
     }
     __syncwarp();
 
@@ -372,7 +385,7 @@ __global__ void __launch_bounds__(NW * 32, 1) solve_kernel(const SolveParams P) 
                     atomicAdd(&P.counters[CTR_REJECT], (unsigned long long)sl->nrej[c]);
                 }
                 __syncwarp();
-                fill_slot<N, RECORD>(P, sl, c, u[c], ks[0][c], lsum, lane);
+                fill_slot<N, RECORD, ENS>(P, sl, c, u[c], ks[0][c], lsum, lane, mq);
 #pragma unroll
                 for (int j = 1; j < 7; ++j) ks[j][c] = 0.f;   // stale stages meet zero tableau entries: keep them finite
             }
@@ -380,6 +393,53 @@ __global__ void __launch_bounds__(NW * 32, 1) solve_kernel(const SolveParams P) 
         __syncwarp();
     }
     if (RECORD && lane == 0) atomicAdd(P.loss_sum, lsum);
+}
+
+template <class N, bool WS, int NW, bool RECORD>
+__global__ void __launch_bounds__(NW * 32, 1) solve_kernel(const SolveParams P) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ uint64_t bar;
+    __shared__ WarpSlots slots[NW];
+    const float* sW = WS ? smem : P.wpack;
+    if (WS) stage_weights(smem, P.wpack, N::P_TOTAL, &bar);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* ws = smem + (WS ? N::P_TOTAL : 0) + warp * N::S_TOTAL;
+    solve_warp<N, RECORD, false>(P, sW, ws, &slots[warp], lane, MemberQueue{nullptr, 0, 0});
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Ensemble of Chains (src/testing.jl:42-79 compute_nde_solution_history: every saved epoch's NN x every
+// simulation, serial there).  Member m has its own packed weights at wpack + m*P_TOTAL and owns the
+// columns [m*S, (m+1)*S).  A CTA takes members from a global queue: stage that member's weights,
+// k1 / initial dt for its columns, then the same slot loop as solve_kernel over the member's columns.
+// ---------------------------------------------------------------------------------------------------
+template <class N, bool WS, int NW>
+__global__ void __launch_bounds__(NW * 32, 1) solve_ensemble_kernel(const SolveParams P, long long E, int S, float* k1_buf, float* dt_buf) {
+    extern __shared__ __align__(16) float smem[];
+    __shared__ uint64_t bar;
+    __shared__ WarpSlots slots[NW];
+    __shared__ long long s_member;
+    __shared__ int s_next;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* ws = smem + (WS ? N::P_TOTAL : 0) + warp * N::S_TOTAL;
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    unsigned parity = 0;
+    for (;;) {
+        __syncthreads();   // every warp is done with the previous member's weights and queue
+        if (threadIdx.x == 0) { s_member = (long long)atomicAdd(&P.counters[CTR_QUEUE], 1ULL); s_next = 0; }
+        __syncthreads();
+        const long long m = s_member;
+        if (m >= E) break;
+        const float* gW = P.wpack + m * (long long)N::P_TOTAL;
+        const float* sW = WS ? smem : gW;
+        if (WS) { restage_weights(smem, gW, N::P_TOTAL, &bar, parity); parity ^= 1u; }
+        const long long base = m * S;
+        for (int g = warp; g * CPW < S; g += NW)
+            rhs_init_group<N, 1>(sW, ws, base + g * CPW, base + S, P.T0, P.colp, k1_buf, dt_buf, P.pref, P.use_kca, P.reltol, P.abstol, P.tf,
+                                 P.fixed_dt, lane);
+        __syncthreads();   // k1 / dt of the member's columns are visible to the whole CTA
+        solve_warp<N, false, true>(P, sW, ws, &slots[warp], lane, MemberQueue{&s_next, base, S});
+    }
 }
 
 // ---- longest-first schedule from the previous call's per-column step counts (counting sort, 1024 buckets, descending) ----
