@@ -6,7 +6,7 @@
 module FreeConvectionB200
 
 using Flux
-export FreeConvectionNDE, ConvectiveAdjustmentNDE, solve_nde, nde_loss_and_gradient
+export solve_nde_history, FreeConvectionNDE, ConvectiveAdjustmentNDE, solve_nde, nde_loss_and_gradient
 
 const LIB = get(ENV, "LIBNFC_B200", joinpath(@__DIR__, "..", "neuralfreeconvection.jl_b200", "libnfc_b200.so"))
 const NFC_MAX_LAYERS = 8
@@ -97,6 +97,25 @@ function nde_loss_and_gradient(nde::NDEHandle, θ::Vector{Float32}, T₀::Matrix
                nde.ptr, T₀, colp, glob, Ttrue, loss, grad, st, B)
     check(nde.ptr, rc, "nfc_loss_grad")
     return loss[], grad
+end
+
+"""
+The epoch x simulation loop of compute_nde_solution_history (src/testing.jl:62-73) as one call.  `thetas` is n_params x epochs
+(column e = Flux.destructure(history["neural_network/\$e"])[1]), T₀ is Nz x S (one column per dataset, T_scaling'ed),
+nde_params 7 x S.  Returns Nz x n_save x S x epochs (scaled units; apply inv(T_scaling) as src/solve.jl:50 does).
+"""
+function solve_nde_history(nde::NDEHandle, thetas::Matrix{Float32}, T₀::Matrix{Float32}, nde_params)
+    E = size(thetas, 2); S = size(T₀, 2)
+    colp, glob = split_params(nde, nde_params)
+    T0e = repeat(T₀, 1, E); colpe = repeat(colp, 1, E)                     # member e owns columns (e-1)S+1 : eS
+    out = Array{Float32}(undef, nde.Nz, length(nde.saveat), S, E)
+    na = zeros(Int32, S, E); nr = zeros(Int32, S, E); st = zeros(Int32, S, E)
+    rc = ccall((:nfc_solve_ensemble, LIB), Int32,
+               (Ptr{Cvoid}, Ptr{Float32}, Int64, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Int64),
+               nde.ptr, thetas, E, T0e, colpe, glob, out, na, nr, st, S)
+    check(nde.ptr, rc, "nfc_solve_ensemble")
+    any(!=(0), st) && @warn "solver status != 0 for $(count(!=(0), st)) (simulation, epoch) pairs"
+    return out
 end
 
 end # module
