@@ -46,6 +46,7 @@ extern "C" {
 #define NFC_NDE_FREE_CONVECTION 0      /* K_CA column of colp is ignored (treated as 0) */
 #define NFC_NDE_CONVECTIVE_ADJUSTMENT 1
 #define NFC_ALG_TSIT5 0
+#define NFC_ALG_RKC2 1   /* stabilised explicit Runge-Kutta-Chebyshev, in the role of ROCK4 (train_free_convection_nde.sh:3); nfc_solve only */
 
 typedef struct nfc_handle nfc_handle;
 
@@ -57,7 +58,7 @@ typedef struct nfc_config {
     int32_t layer_dims[NFC_MAX_LAYERS + 1];       /* in_0, out_0, out_1, ... */
     int32_t activations[NFC_MAX_LAYERS];          /* NFC_ACT_* per Dense layer */
     int32_t nde_type;                             /* NFC_NDE_* */
-    int32_t alg;                                  /* NFC_ALG_TSIT5 */
+    int32_t alg;                                  /* NFC_ALG_TSIT5 | NFC_ALG_RKC2 */
     float reltol;                                 /* src/solve.jl:4 -> 1e-4 */
     float abstol;                                 /* DiffEqBase default 1e-6 */
     float fixed_dt;                               /* > 0: adaptive=false, dt=fixed_dt (test / fixed-step use) */
@@ -80,6 +81,7 @@ typedef struct nfc_counters {
     int64_t kernel_launches;    /* kernels launched by the last call */
     float   last_kernel_ms;     /* device time of the last call's main kernel(s), CUDA events */
     float   last_adjoint_ms;
+    int64_t rhs_evals;          /* forward RHS evaluations of the last solve (Tsit5: 6 per attempted step + 2 per column) */
 } nfc_counters;
 
 int32_t nfc_create(const nfc_config* cfg, nfc_handle** out);

@@ -29,7 +29,7 @@ class NfcConfig(C.Structure):
 class NfcCounters(C.Structure):
     _fields_ = [("columns", C.c_int64), ("steps_accepted", C.c_int64), ("steps_rejected", C.c_int64),
                 ("adj_steps_accepted", C.c_int64), ("adj_steps_rejected", C.c_int64), ("kernel_launches", C.c_int64),
-                ("last_kernel_ms", C.c_float), ("last_adjoint_ms", C.c_float)]
+                ("last_kernel_ms", C.c_float), ("last_adjoint_ms", C.c_float), ("rhs_evals", C.c_int64)]
 
 
 _lib = None
@@ -102,7 +102,7 @@ class Handle:
     """Owns one nfc_handle (device buffers, stream).  Thin, 1:1 with include/nfc.h."""
 
     def __init__(self, conv_width, layers, nde_type, saveat, reltol=1e-4, abstol=1e-6, fixed_dt=0.0, device=0,
-                 max_iters=100000, adjoint_max_steps=0, adjoint_reltol=0.0, adjoint_abstol=0.0, Nz=32):
+                 max_iters=100000, adjoint_max_steps=0, adjoint_reltol=0.0, adjoint_abstol=0.0, Nz=32, alg=0):
         self.lib = load()
         cfg = NfcConfig()
         cfg.struct_size = C.sizeof(NfcConfig)
@@ -117,7 +117,7 @@ class Handle:
         for i, (_, _, a) in enumerate(layers):
             cfg.activations[i] = a
         cfg.nde_type = nde_type
-        cfg.alg = 0
+        cfg.alg = {"Tsit5": 0, "RKC2": 1, "ROCK4": 1}.get(alg, alg) if isinstance(alg, str) else int(alg)
         cfg.reltol, cfg.abstol, cfg.fixed_dt = reltol, abstol, fixed_dt
         cfg.max_iters = max_iters
         self.saveat = _f32(saveat)

@@ -127,7 +127,7 @@ class _NDE:
 
     nde_type = None
 
-    def __init__(self, NN, ds, iterations=None, device=0, reltol=1e-4, abstol=1e-6, **kw):
+    def __init__(self, NN, ds, iterations=None, device=0, reltol=1e-4, abstol=1e-6, alg=0, **kw):
         Nz, Nt = ds.T.shape
         self.Nz, self.Nt = Nz, Nt
         self.H = abs(float(ds.zf[0]))
@@ -138,8 +138,17 @@ class _NDE:
         self.iterations = iterations
         self.tspan = (np.float32(0.0), np.float32(iterations.max() / Nt))
         self.saveat = np.linspace(self.tspan[0], self.tspan[1], len(iterations)).astype(np.float32)
-        self.handle = B_.Handle(NN.conv_width, NN.dense_spec, self.nde_type, self.saveat, reltol=reltol, abstol=abstol,
-                                device=device, Nz=Nz, **kw)
+        self._mk = lambda a: B_.Handle(NN.conv_width, NN.dense_spec, self.nde_type, self.saveat, reltol=reltol, abstol=abstol,
+                                       device=device, Nz=Nz, alg=a, **kw)
+        self._handles = {}
+        self.handle = self.handle_for(alg)
+
+    def handle_for(self, alg):
+        """The solver is fixed per C handle; the reference passes it per solve call (src/solve.jl:1), so keep one handle per algorithm."""
+        a = alg if isinstance(alg, int) else _check_alg(alg)
+        if a not in self._handles:
+            self._handles[a] = self._mk(a)
+        return self._handles[a]
 
 
 class FreeConvectionNDE(_NDE):
@@ -184,13 +193,13 @@ def solve_nde(*args, **kw):
     solve_nde(ds, NN, NDEType, nde_params, algorithm, T_scaling, wT_scaling; T0=None) -> (T, wT)  (src/solve.jl:8-51)."""
     if isinstance(args[0], _NDE):
         nde, NN, T0, alg, nde_params = args
-        _check_alg(alg)
+        handle = nde.handle_for(alg)
         theta, _ = destructure(NN)
-        nde.handle.set_weights(theta)
+        handle.set_weights(theta)
         colp, glob = _split_params(nde, nde_params)
         T0 = np.asarray(T0, dtype=np.float32)
         single = T0.ndim == 1
-        res = nde.handle.solve(np.atleast_2d(T0), colp, glob)
+        res = handle.solve(np.atleast_2d(T0), colp, glob)
         nde.last = res
         return res["T"][0].T.copy() if single else res["T"]
     ds, NN, NDEType, nde_params, algorithm, T_scaling, wT_scaling = args
@@ -208,13 +217,28 @@ def solve_nde(*args, **kw):
 
 
 def _check_alg(alg):
-    name = alg if isinstance(alg, str) else type(alg).__name__
-    if name not in ("Tsit5", "Tsit5()"):
-        raise NotImplementedError(f"time stepper {name}: this build implements Tsit5 (ROCK4 is SURVEY.md row f2)")
+    """Algorithm id of the C ABI: Tsit5 -> NFC_ALG_TSIT5; RKC2 / ROCK4 -> NFC_ALG_RKC2 (stabilised explicit, see class ROCK4)."""
+    name = (alg if isinstance(alg, str) else type(alg).__name__).replace("()", "")
+    if name == "Tsit5":
+        return 0
+    if name in ("RKC2", "ROCK4"):
+        return 1
+    raise NotImplementedError(f"time stepper {name}: this build implements Tsit5 and the stabilised explicit RKC2 (ROCK4's role)")
 
 
 class Tsit5:
     pass
+
+
+class RKC2:
+    """Second-order Runge-Kutta-Chebyshev (Sommeijer, Shampine & Verwer 1998): explicit, stage count chosen per step from a
+    spectral-radius estimate, so the convective-adjustment term does not limit the step as it does for Tsit5."""
+
+
+class ROCK4(RKC2):
+    """The reference's production integrator (train_free_convection_nde.sh:3).  ROCK4's coefficient tables are OrdinaryDiffEq's
+    and not available offline; selecting it here runs RKC2, the same kind of method at lower order: trajectories agree with
+    any convergent integrator to the tolerance, step and evaluation counts differ from ROCK4's."""
 
 
 class ADAM:
@@ -242,7 +266,8 @@ def train_neural_differential_equation(NN, NDEType, nde_params, algorithm, datas
     solutions and the scaled truth of every training simulation.  One epoch = one nfc_loss_grad call (all simulations
     in one launch) + the callback's loss re-evaluation (src/training.jl:53-68).  Returns the best-loss Chain
     (GalacticOptim returns sol.minimizer, src/training.jl:74)."""
-    _check_alg(algorithm)
+    if _check_alg(algorithm) != 0:
+        raise NotImplementedError("the adjoint gradient is implemented for Tsit5 (its tape is Tsit5 dense output); train with Tsit5()")
     ids = sorted(datasets.keys())
     it = np.asarray(list(iterations)) - 1                                   # Julia 1-based -> 0-based
     T0 = np.stack([T_scaling(datasets[i].T[:, 0]) for i in ids]).astype(np.float32)
@@ -307,7 +332,8 @@ def compute_nde_solution_history(datasets, NDEType, nde_params, algorithm, NN, h
     (npz path / dict as written by inscribe_history, or an [epochs][n_params] array).
     Returns (solution_history, loss_history): {id: [epochs, Nz, Nt]} in physical units and {id: [epochs, Nt]} with
     Flux.Losses.mse(T_true, T, agg = x -> mean(x, dims=1)), i.e. the mean over depth per saved time."""
-    _check_alg(algorithm)
+    if _check_alg(algorithm) != 0:
+        raise NotImplementedError("the ensemble launch runs Tsit5")
     thetas = load_history(history)
     ids = sorted(datasets.keys())
     ds0 = datasets[ids[0]]

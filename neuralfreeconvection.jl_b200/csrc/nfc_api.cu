@@ -16,6 +16,7 @@
 #include "nfc_launch.h"
 #include "nfc_tc.cuh"
 #include "nfc_embedded.cuh"
+#include "nfc_rkc.cuh"
 
 using namespace nfc;
 
@@ -221,11 +222,61 @@ int nfc_launch_record(nfc_handle* h, nfc::SolveParams& P, cudaStream_t st, bool 
 #include "nfc_adjoint.cuh"
 namespace {
 
+// Chebyshev recurrences of the m-stage RKC formula for m = 2..MMAX in double, stored as float (oracle/nde_oracle.py:rkc_coefficients)
+std::vector<float> rkc_coefficients() {
+    using namespace rkc;
+    std::vector<float> tab((size_t)TAB_FLOATS, 0.f);
+    std::vector<double> T(MMAX + 1), dT(MMAX + 1), d2T(MMAX + 1), b(MMAX + 1);
+    for (int m = 2; m <= MMAX; ++m) {
+        const double w0 = 1.0 + (2.0 / 13.0) / ((double)m * m);
+        T[0] = 1; T[1] = w0; dT[0] = 0; dT[1] = 1; d2T[0] = 0; d2T[1] = 0;
+        for (int j = 2; j <= m; ++j) {
+            T[j] = 2 * w0 * T[j - 1] - T[j - 2];
+            dT[j] = 2 * w0 * dT[j - 1] - dT[j - 2] + 2 * T[j - 1];
+            d2T[j] = 2 * w0 * d2T[j - 1] - d2T[j - 2] + 4 * dT[j - 1];
+        }
+        const double w1 = dT[m] / d2T[m];
+        for (int j = 2; j <= m; ++j) b[j] = d2T[j] / (dT[j] * dT[j]);
+        b[0] = b[1] = b[2];
+        tab[((size_t)m * (MMAX + 1) + 1) * TAB_STRIDE + 3] = (float)(b[1] * w1);
+        for (int j = 2; j <= m; ++j) {
+            const double mu = 2 * b[j] * w0 / b[j - 1], nu = -b[j] / b[j - 2], mus = 2 * b[j] * w1 / b[j - 1];
+            float* c = &tab[((size_t)m * (MMAX + 1) + j) * TAB_STRIDE];
+            c[0] = (float)mu; c[1] = (float)nu; c[2] = (float)(1.0 - mu - nu); c[3] = (float)mus; c[4] = (float)(-(1.0 - b[j - 1] * T[j - 1]) * mus);
+        }
+    }
+    return tab;
+}
+
+template <class N>
+int launch_solve_rkc(nfc_handle* h, SolveParams& S, cudaStream_t st, bool reset_counters, bool last_piece, int* nfe) {
+    constexpr bool WS = Launch<N>::WS;
+    constexpr int NW = Launch<N>::NW;
+    NFC_CUDA(h, cudaFuncSetAttribute(rkc::solve_rkc_kernel<N, WS, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<N>(NW)));
+    S.wpack = h->d_wpack.p; S.saveat = h->d_saveat.p; S.counters = h->d_counters.p;
+    S.n_save = h->cfg.n_save; S.max_iters = h->cfg.max_iters; S.use_kca = h->cfg.nde_type == NFC_NDE_CONVECTIVE_ADJUSTMENT;
+    S.tf = h->saveat.back(); S.reltol = h->cfg.reltol; S.abstol = h->cfg.abstol; S.fixed_dt = 0.f;
+    if (reset_counters) {
+        NFC_CUDA(h, cudaMemsetAsync(h->d_counters.p, 0, sizeof(unsigned long long) * CTR_COUNT, st));
+        NFC_CUDA(h, cudaEventRecord(h->ev[0], st));
+    } else NFC_CUDA(h, cudaMemsetAsync(h->d_counters.p + CTR_QUEUE, 0, sizeof(unsigned long long), st));
+    rkc::Params P{S, h->d_rkctab.p, nfe, h->rkc_mmax};
+    const long long groups = (S.B + CPW - 1) / CPW;
+    const int grid = (int)std::min<long long>(h->num_sms, (groups + NW - 1) / NW);
+    rkc::solve_rkc_kernel<N, WS, NW><<<grid, NW * 32, smem_bytes<N>(NW), st>>>(P);
+    NFC_CUDA(h, cudaGetLastError());
+    if (last_piece) { NFC_CUDA(h, cudaEventRecord(h->ev[1], st)); h->ev_fwd_valid = true; }
+    h->last_launches += 1;
+    h->last_columns = reset_counters ? S.B : h->last_columns + S.B;
+    return 0;
+}
+
 template <class N>
 int do_solve(nfc_handle* h, const float* T0, const float* colp, float pref, float* Tout, int* nacc, int* nrej, int* status, int64_t B,
              cudaStream_t st, bool first = true, int64_t hist_total = -1, int64_t hist_off = 0, bool last_piece = true) {
     SolveParams P{};
     P.T0 = T0; P.colp = colp; P.pref = pref; P.Tout = Tout; P.naccept = nacc; P.nreject = nrej; P.status = status; P.B = B;
+    if (h->cfg.alg == NFC_ALG_RKC2) return launch_solve_rkc<N>(h, P, st, first, last_piece, nullptr);
     return launch_solve<N, false>(h, P, st, first, hist_total, hist_off, last_piece);
 }
 
@@ -330,7 +381,8 @@ int32_t nfc_create(const nfc_config* cfg, nfc_handle** out) {
     *out = nullptr;
     if (cfg->struct_size != (int32_t)sizeof(nfc_config)) return fail(nullptr, -2, "nfc_config.struct_size %d != %zu", cfg->struct_size, sizeof(nfc_config));
     if (cfg->Nz != NZ) return fail(nullptr, -3, "this build supports Nz = 32 only (got %d)", cfg->Nz);
-    if (cfg->alg != NFC_ALG_TSIT5) return fail(nullptr, -3, "unsupported algorithm id %d (Tsit5 = 0)", cfg->alg);
+    if (cfg->alg != NFC_ALG_TSIT5 && cfg->alg != NFC_ALG_RKC2) return fail(nullptr, -3, "unsupported algorithm id %d (Tsit5 = 0, RKC2 = 1)", cfg->alg);
+    if (cfg->alg == NFC_ALG_RKC2 && cfg->fixed_dt > 0.f) return fail(nullptr, -3, "fixed_dt is a Tsit5 option; RKC2 chooses step and stage count itself");
     if (cfg->nde_type != NFC_NDE_FREE_CONVECTION && cfg->nde_type != NFC_NDE_CONVECTIVE_ADJUSTMENT) return fail(nullptr, -2, "bad nde_type");
     if (cfg->n_save < 1 || !cfg->saveat) return fail(nullptr, -2, "saveat must hold at least one time");
     if (!(cfg->reltol > 0.f) || !(cfg->abstol >= 0.f)) return fail(nullptr, -2, "bad tolerances");
@@ -364,6 +416,14 @@ int32_t nfc_create(const nfc_config* cfg, nfc_handle** out) {
     for (auto& ev : h->ev) if (cudaEventCreate(&ev) != cudaSuccess) { h->err = "cudaEventCreate failed"; return bail(-10); }
     int rc = [&]() -> int { NFC_DISPATCH(h, arch_setup, h); }();
     if (rc) return bail(rc);
+    if (h->cfg.alg == NFC_ALG_RKC2) {
+        std::vector<float> tab = rkc_coefficients();
+        if (h->d_rkctab.ensure(tab.size()) || cudaMemcpy(h->d_rkctab.p, tab.data(), sizeof(float) * tab.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+            h->err = "RKC table upload failed"; return bail(-10);
+        }
+        // round-off inside an m-stage step grows like m^2 eps: m^2 <= reltol / (10 eps)   (RKC's own rule)
+        h->rkc_mmax = std::max(2, std::min(rkc::MMAX, (int)std::sqrt((double)h->cfg.reltol / (10.0 * 1.1920928955078125e-07))));
+    }
     if (h->arch == ARCH_DEFAULT) {
         if (h->d_wimg.ensure(tc::IMG_BYTES)) { h->err = "cudaMalloc failed"; return bail(-10); }
         if (cudaFuncSetAttribute(tc::rhs_tc_kernel<tc::SplitBF16x3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::IMG_BYTES) != cudaSuccess ||
@@ -389,7 +449,7 @@ int32_t nfc_destroy(nfc_handle* h) {
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     h->d_work.release(); h->d_order.release(); h->d_hist.release(); h->d_wimg.release(); h->d_theta.release(); h->d_wpack.release(); h->d_saveat.release(); h->d_k1.release(); h->d_dt.release(); h->d_counters.release();
-    h->e_theta.release(); h->e_wpack.release();
+    h->e_theta.release(); h->e_wpack.release(); h->d_rkctab.release(); h->s_nfe.release();
     h->s_T0.release(); h->s_colp.release(); h->s_out.release(); h->s_true.release(); h->s_grad.release();
     h->s_nacc.release(); h->s_nrej.release(); h->s_status.release(); h->s_loss.release();
     h->a_resid.release(); h->a_tape.release(); h->a_gacc.release(); h->a_tlen.release(); h->a_adjsteps.release(); h->a_gsum.release();
@@ -480,6 +540,7 @@ int32_t nfc_get_counters(const nfc_handle* hc, nfc_counters* out) {
     out->adj_steps_accepted = (int64_t)c[CTR_ADJ_ACCEPT];
     out->adj_steps_rejected = (int64_t)c[CTR_ADJ_REJECT];
     out->kernel_launches = h->last_launches;
+    out->rhs_evals = h->cfg.alg == NFC_ALG_RKC2 ? (int64_t)c[rkc::CTR_NFE] : 6 * (out->steps_accepted + out->steps_rejected) + 2 * out->columns;
     if (h->ev_fwd_valid) cudaEventElapsedTime(&out->last_kernel_ms, h->ev[0], h->ev[1]);
     if (h->ev_adj_valid) cudaEventElapsedTime(&out->last_adjoint_ms, h->ev[2], h->ev[3]);
     return 0;
@@ -511,6 +572,7 @@ int32_t nfc_loss_grad_dev(nfc_handle* h, const float* T0, const float* colp, con
                           float* grad_dev, int32_t* status, int64_t B, int64_t n_total_columns, void* stream) {
     if (int rc = check_ready(h, B)) return rc;
     if (!glob) return fail(h, -1, "null glob");
+    if (h->cfg.alg != NFC_ALG_TSIT5) return fail(h, -3, "nfc_loss_grad needs a Tsit5 handle (the adjoint tape is Tsit5 dense output)");
     const float* g = glob;   // glob is always a HOST pointer (4 scalars)
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     h->last_launches = 0;
@@ -586,6 +648,7 @@ int32_t nfc_solve_ensemble(nfc_handle* h, const float* theta_members, int64_t E,
                            float* Tout, int32_t* naccept, int32_t* nreject, int32_t* status, int64_t S) {
     if (!h) return -1;
     if (E < 0 || S < 0) return fail(h, -2, "negative ensemble size");
+    if (h->cfg.alg != NFC_ALG_TSIT5) return fail(h, -3, "nfc_solve_ensemble needs a Tsit5 handle");
     if (E > 65535) return fail(h, -2, "at most 65535 ensemble members per call (got %lld)", (long long)E);
     if (S > (1 << 20)) return fail(h, -2, "at most 2^20 columns per member (got %lld)", (long long)S);
     if (E == 0 || S == 0) return 0;
@@ -670,6 +733,7 @@ int32_t nfc_loss_grad(nfc_handle* h, const float* T0, const float* colp, const f
     if (int rc = check_ready(h, B)) return rc;
     if (B == 0) return fail(h, -2, "loss over zero columns is undefined");
     if (!T0 || !colp || !glob || !Ttrue || !loss || !grad_theta) return fail(h, -1, "null argument");
+    if (h->cfg.alg != NFC_ALG_TSIT5) return fail(h, -3, "nfc_loss_grad needs a Tsit5 handle (the adjoint tape is Tsit5 dense output)");
     const size_t ntraj = (size_t)B * h->cfg.n_save * NZ;
     NFC_CUDA(h, h->s_T0.ensure((size_t)B * NZ));
     NFC_CUDA(h, h->s_colp.ensure((size_t)B * 3));

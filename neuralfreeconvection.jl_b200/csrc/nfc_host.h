@@ -42,7 +42,10 @@ struct nfc_handle {
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool ev_fwd_valid = false, ev_adj_valid = false;
     nfc::DevBuf<float> d_theta, d_wpack, d_saveat, d_k1, d_dt;
-    nfc::DevBuf<float> e_theta, e_wpack;   // ensemble members (nfc_solve_ensemble)
+    nfc::DevBuf<float> e_theta, e_wpack;
+    nfc::DevBuf<float> d_rkctab;           // RKC coefficient table (alg = NFC_ALG_RKC2)
+    nfc::DevBuf<int> s_nfe;
+    int rkc_mmax = 2;   // ensemble members (nfc_solve_ensemble)
     nfc::DevBuf<unsigned char> d_wimg;      // tensor-core weight image (default Chain only)
     bool use_tc = false;
     bool tc_fp16 = false;                   // tensor-core split: false = BF16x3 (6 MMAs / product), true = FP16x2 (3 MMAs, scaled operands)

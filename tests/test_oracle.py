@@ -173,3 +173,45 @@ def test_empty_and_ragged_batches(nfc):
     r9 = CO.solve(d["T0"], theta, cw, layers, d["colp"], d["glob"], sv)
     assert np.array_equal(r1["T"][0], r9["T"][0])                 # columns are independent
     np.testing.assert_array_equal(r9["T"][:, 0], d["T0"])         # first save point is the initial condition
+
+
+# ---------------------------------------------------------------- RKC2 (stabilised explicit) oracle
+def test_rkc_coefficients_are_consistent_and_second_order():
+    """Stage 'times' c_j follow the same recurrence as the stages; consistency needs c_s = 1 and second order needs the
+    stability polynomial P(z) = 1 + z + z^2/2 + O(z^3): check P on the scalar test equation y' = lambda y."""
+    tab = O.rkc_coefficients()
+    for m in (2, 3, 5, 9, 20, 64):
+        c = tab[m]
+        cs = [0.0, c[1, 3]]
+        for j in range(2, m + 1):
+            assert abs(c[j, 0] + c[j, 1] + c[j, 2] - 1.0) < 1e-14
+            cs.append(c[j, 0] * cs[j - 1] + c[j, 1] * cs[j - 2] + c[j, 3] + c[j, 4])
+        assert abs(cs[-1] - 1.0) < 1e-12
+        for z in (-1e-3, 1e-3):
+            y0, y1 = 1.0, 1.0 + z * c[1, 3]
+            for j in range(2, m + 1):
+                y0, y1 = y1, c[j, 0] * y1 + c[j, 1] * y0 + c[j, 2] + (c[j, 3] * z * y1 + c[j, 4] * z)
+            assert abs(y1 - (1 + z + z * z / 2)) < 2e-9          # third-order remainder
+        # damped stability along the negative real axis: beta(m) ~ 0.653 (m^2 - 1), which is what the stage-count rule assumes
+        for z in np.linspace(-0.653 * (m * m - 1), -0.01, 400):
+            y0, y1 = 1.0, 1.0 + z * c[1, 3]
+            for j in range(2, m + 1):
+                y0, y1 = y1, c[j, 0] * y1 + c[j, 1] * y0 + c[j, 2] + (c[j, 3] * z * y1 + c[j, 4] * z)
+            assert abs(y1) <= 1.0 + 1e-9
+
+
+def test_rkc_oracle_converges_and_beats_tsit5_on_stiff_adjustment(nfc):
+    syn = nfc.synthetic
+    d = syn.make_columns("training9")
+    d["colp"][:, 2] = 10.0
+    sv = syn.saveat(17)
+    cw, layers = O.chain_spec()
+    theta = O.glorot_theta(cw, layers, 0, 0.3)
+    truth = O.truth_solve(d["T0"][:3], theta, cw, layers, d["colp"][:3], d["glob"], sv)
+    for dt_ in (np.float32, np.float64):
+        r = O.rkc_solve(d["T0"][:3], theta, cw, layers, d["colp"][:3], d["glob"], sv, dtype=dt_)
+        assert (r["status"] == 0).all()
+        assert rel_l2(r["T"], truth).max() < 2e-4
+    t = O.tsit5_solve(d["T0"][:3], theta, cw, layers, d["colp"][:3], d["glob"], sv, dtype=np.float32)
+    assert r["nfe"].sum() < 0.5 * 6 * (t["naccept"] + t["nreject"]).sum()
+    assert O.rkc_max_stages(1e-4, np.float32) == 9 and O.rkc_max_stages(1e-4, np.float64) == O.RKC_MMAX
