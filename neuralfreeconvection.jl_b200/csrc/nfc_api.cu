@@ -17,6 +17,7 @@
 #include "nfc_tc.cuh"
 #include "nfc_embedded.cuh"
 #include "nfc_rkc.cuh"
+#include "nfc_rkc_tc.cuh"
 
 using namespace nfc;
 
@@ -261,6 +262,21 @@ int launch_solve_rkc(nfc_handle* h, SolveParams& S, cudaStream_t st, bool reset_
         NFC_CUDA(h, cudaEventRecord(h->ev[0], st));
     } else NFC_CUDA(h, cudaMemsetAsync(h->d_counters.p + CTR_QUEUE, 0, sizeof(unsigned long long), st));
     rkc::Params P{S, h->d_rkctab.p, nfe, h->rkc_mmax};
+    if (h->use_tc && h->arch == ARCH_DEFAULT) {
+        const int gridt = (int)std::min<long long>(h->num_sms, (S.B + tc::TILE - 1) / tc::TILE);
+        if (h->tc_fp16) {
+            NFC_CUDA(h, cudaFuncSetAttribute(tc::solve_rkc_tc_kernel<tc::SplitFP16x2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::rkc_tc_smem_bytes<tc::SplitFP16x2>()));
+            tc::solve_rkc_tc_kernel<tc::SplitFP16x2><<<gridt, tc::NTHREADS, tc::rkc_tc_smem_bytes<tc::SplitFP16x2>(), st>>>(h->d_wimg.p, P);
+        } else {
+            NFC_CUDA(h, cudaFuncSetAttribute(tc::solve_rkc_tc_kernel<tc::SplitBF16x3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::rkc_tc_smem_bytes<tc::SplitBF16x3>()));
+            tc::solve_rkc_tc_kernel<tc::SplitBF16x3><<<gridt, tc::NTHREADS, tc::rkc_tc_smem_bytes<tc::SplitBF16x3>(), st>>>(h->d_wimg.p, P);
+        }
+        NFC_CUDA(h, cudaGetLastError());
+        if (last_piece) { NFC_CUDA(h, cudaEventRecord(h->ev[1], st)); h->ev_fwd_valid = true; }
+        h->last_launches += 1;
+        h->last_columns = reset_counters ? S.B : h->last_columns + S.B;
+        return 0;
+    }
     const long long groups = (S.B + CPW - 1) / CPW;
     const int grid = (int)std::min<long long>(h->num_sms, (groups + NW - 1) / NW);
     rkc::solve_rkc_kernel<N, WS, NW><<<grid, NW * 32, smem_bytes<N>(NW), st>>>(P);

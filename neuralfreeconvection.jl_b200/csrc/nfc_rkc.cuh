@@ -30,14 +30,18 @@ enum : int { PH_F0 = 0, PH_RHO = 1, PH_DT0 = 2, PH_STAGE = 3 };
 enum : int { ACT_NONE = 0, ACT_RHO_INIT = 1, ACT_RHO_CONT = 2, ACT_DT0 = 3, ACT_BEGIN = 4, ACT_STAGE = 5, ACT_REFILL = 6, ACT_MASK = 15,
              AF_ACCEPT = 16, AF_RHO_DONE = 32, AF_SETF0 = 64 };
 
-struct Slots {   // one per warp, shared memory; index = slot
-    int col[CPW], phase[CPW], act[CPW], m[CPW], j[CPW], it[CPW], nstsig[CPW], nacc[CPW], nrej[CPW], nfe[CPW], si[CPW], status[CPW];
-    int newspc[CPW], jacatt[CPW], first[CPW], last[CPW];
-    float t[CPW], tnew[CPW], absh[CPW], h[CPW], hlast[CPW], errold[CPW], sprad[CPW], ynrm2[CPW], vnrm2[CPW], dynrm[CPW];
-    float sigma[CPW], sigmal[CPW], env[CPW], smax[CPW];
-    float bot[CPW], top[CPW], kca[CPW];
-    float ca[CPW], cb[CPW], cc[CPW], cd[CPW], ce[CPW];
+template <int NS>
+struct SlotsT {   // shared memory; index = slot (SIMT kernel: 8 per warp; tensor-core kernel: 128 per CTA)
+    int col[NS], phase[NS], act[NS], m[NS], j[NS], it[NS], nstsig[NS], nacc[NS], nrej[NS], nfe[NS], si[NS], status[NS];
+    int newspc[NS], jacatt[NS], first[NS], last[NS];
+    float t[NS], absh[NS], h[NS], hlast[NS], errold[NS], sprad[NS], ynrm2[NS], vnrm2[NS], dynrm[NS];
+    float sigma[NS], env[NS], smax[NS];
+    float bot[NS], top[NS], kca[NS];
+    float ca[NS], cb[NS], cc[NS], cd[NS], ce[NS];   // coefficients of the vector action
+    float o_t0[NS], o_h[NS], o_tn[NS];              // the step just accepted (dense output): start, size, end
+    int o_si[NS];                                   //   and the first save index it may serve
 };
+using Slots = SlotsT<CPW>;
 
 struct Params {
     SolveParams S;            // T0, colp, saveat, Tout, naccept, nreject, status, counters, B, n_save, max_iters, use_kca, pref, tf, tolerances
@@ -59,7 +63,7 @@ __device__ __forceinline__ void fill(const Params& P, Slots* sl, int c, float& y
             sl->col[c] = (int)next; sl->phase[c] = PH_F0; sl->act[c] = ACT_NONE; sl->m[c] = 0; sl->j[c] = 0; sl->it[c] = 0; sl->nstsig[c] = 0;
             sl->nacc[c] = 0; sl->nrej[c] = 0; sl->nfe[c] = 0; sl->si[c] = si; sl->status[c] = ST_OK;
             sl->newspc[c] = 1; sl->jacatt[c] = 0; sl->first[c] = 1; sl->last[c] = 0;
-            sl->t[c] = 0.f; sl->tnew[c] = 0.f; sl->absh[c] = P.S.tf; sl->h[c] = 0.f; sl->hlast[c] = 0.f; sl->errold[c] = 0.f; sl->sprad[c] = 0.f;
+            sl->t[c] = 0.f; sl->absh[c] = P.S.tf; sl->h[c] = 0.f; sl->hlast[c] = 0.f; sl->errold[c] = 0.f; sl->sprad[c] = 0.f;
             sl->bot[c] = P.S.colp[next * 3 + 0]; sl->top[c] = P.S.colp[next * 3 + 1];
             sl->kca[c] = P.S.use_kca ? P.S.colp[next * 3 + 2] : 0.f;
         }
@@ -69,8 +73,10 @@ __device__ __forceinline__ void fill(const Params& P, Slots* sl, int c, float& y
     }
 }
 
-// Scalar transition of slot s (= lane) after its evaluation; r0, r1, r2 are the reductions of step (B).
-__device__ __forceinline__ void transition(const Params& P, Slots* sl, int s, float r0, float r1, float r2) {
+// Scalar transition of slot s after its evaluation; r0, r1, r2 are the reductions of step (B); xmax = max |y_{n+1}| is checked
+// against `bound` when a step is accepted (operand range of the tensor-core splits; +inf for the FP32 kernel).
+template <class SL>
+__device__ __forceinline__ void transition(const Params& P, SL* sl, int s, float r0, float r1, float r2, float xmax, float bound) {
     const float tf = P.S.tf, hmax = tf, uround = 1.1920929e-07f, hmin = 10.f * uround * tf;
     const int ph = sl->phase[s];
     int act = ACT_NONE;
@@ -90,7 +96,7 @@ __device__ __forceinline__ void transition(const Params& P, Slots* sl, int s, fl
         const float sigmal = sl->sigma[s], sigma = dfnrm / dynrm;
         const float envl = sl->env[s], env = fmaxf(sigma, sigmal);
         float smax = fmaxf(sl->smax[s], sigma);
-        sl->sigmal[s] = sigmal; sl->sigma[s] = sigma; sl->env[s] = env;
+        sl->sigma[s] = sigma; sl->env[s] = env;
         const bool conv = it >= 3 && fabsf(env - envl) <= fmaxf(env, 1.0f / hmax) * 0.01f;
         if (conv) smax = env;
         sl->smax[s] = smax;
@@ -131,12 +137,21 @@ __device__ __forceinline__ void transition(const Params& P, Slots* sl, int s, fl
                     sl->newspc[s] = newspc;
                     if (newspc) to_rho = true; else to_begin = true;
                 }
+            } else if (!(xmax <= bound)) {
+                sl->status[s] = ST_NAN; retire = true;   // an accepted state outside the operand range of the split: report, never guess
             } else {
                 const int nacc = sl->nacc[s] + 1;
                 sl->nacc[s] = nacc;
                 act |= AF_ACCEPT;
+                sl->o_t0[s] = tcur; sl->o_h[s] = h;
                 tcur = sl->last[s] ? tf : tcur + h;
-                sl->tnew[s] = tcur;
+                sl->o_tn[s] = tcur; sl->t[s] = tcur;
+                {
+                    int si = sl->si[s];
+                    sl->o_si[s] = si;
+                    while (si < P.S.n_save && P.S.saveat[si] <= tcur) ++si;
+                    sl->si[s] = si;
+                }
                 sl->ynrm2[s] = r1;
                 sl->jacatt[s] = 0;
                 const int nstsig = (sl->nstsig[s] + 1) % 25;
@@ -172,7 +187,7 @@ __device__ __forceinline__ void transition(const Params& P, Slots* sl, int s, fl
         else if (vnrm != 0.f) { dynrm = uround; ca = 0.f; cb = dynrm / vnrm; }
         else { dynrm = uround; ca = 0.f; cb = 0.f; cc = dynrm * 0.17677669529663687f; }   // 1/sqrt(32)
         sl->dynrm[s] = dynrm; sl->ca[s] = ca; sl->cb[s] = cb; sl->cc[s] = cc;
-        sl->it[s] = 0; sl->sigma[s] = 0.f; sl->sigmal[s] = 0.f; sl->env[s] = 0.f; sl->smax[s] = 0.f;
+        sl->it[s] = 0; sl->sigma[s] = 0.f; sl->env[s] = 0.f; sl->smax[s] = 0.f;
         sl->phase[s] = PH_RHO;
         act |= ACT_RHO_INIT;
     }
@@ -254,7 +269,7 @@ __global__ void __launch_bounds__(NW * 32, 1) solve_rkc_kernel(const Params P) {
         }
         __syncwarp();
         // ---- (C) scalar transitions, slot = lane ----
-        if (lane < CPW && sl->col[lane] >= 0) transition(P, sl, lane, r0, r1, r2);
+        if (lane < CPW && sl->col[lane] >= 0) transition(P, sl, lane, r0, r1, r2, 0.f, __int_as_float(0x7f800000));
         __syncwarp();
         // ---- (D) vector updates ----
 #pragma unroll
@@ -265,19 +280,15 @@ __global__ void __launch_bounds__(NW * 32, 1) solve_rkc_kernel(const Params P) {
             if (act & AF_ACCEPT) {
                 // cubic Hermite on (y_n, f_n, y_{n+1}, f_{n+1}) at every save time in (t, t+h]
                 const long long col = sl->col[c];
-                const float t0 = sl->t[c], h = sl->h[c], tn = sl->tnew[c];
+                const float t0 = sl->o_t0[c], h = sl->o_h[c], tn = sl->o_tn[c];
                 const float d = (x[c] - yn[c]) / h;
                 const float c2 = 3.f * d - 2.f * fn[c] - f[c], c3 = -2.f * d + fn[c] + f[c];
-                int si = sl->si[c];
-                while (si < P.S.n_save) {
+                for (int si = sl->o_si[c]; si < P.S.n_save; ++si) {
                     const float ts = P.S.saveat[si];
                     if (ts > tn) break;
                     const float th = fminf((ts - t0) / h, 1.0f);
                     P.S.Tout[(col * P.S.n_save + si) * NZ + lane] = fmaf(h * th, fmaf(th, fmaf(th, c3, c2), fn[c]), yn[c]);
-                    ++si;
                 }
-                __syncwarp();
-                if (lane == 0) { sl->si[c] = si; sl->t[c] = tn; }
                 yn[c] = x[c]; fn[c] = f[c];
             }
             if (act & AF_RHO_DONE) v[c] -= yn[c];

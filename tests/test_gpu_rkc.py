@@ -18,9 +18,13 @@ def _cols(nfc, B, seed, K=None):
     return d
 
 
-@pytest.mark.parametrize("arch", ["dense-default", "dense-wider", "dense-deeper", "conv-2", "conv-4"])
-def test_rkc_matches_cpu_twin_all_chains(nfc, gpu_ok, arch):
-    B = 19
+@pytest.mark.parametrize("arch,tc", [("dense-default", "1"), ("dense-default", "0"), ("dense-default", "bf16"), ("dense-wider", "0"),
+                                     ("dense-deeper", "0"), ("conv-2", "0"), ("conv-4", "0")])
+def test_rkc_matches_cpu_twin_all_chains(nfc, gpu_ok, monkeypatch, arch, tc):
+    """tc = "1": tensor-core kernel (FP16x2 split, the default for the default Chain), "bf16": its BF16x3 split, "0": FP32 kernel."""
+    monkeypatch.setenv("NFC_TC", "0" if tc == "0" else "1")
+    monkeypatch.setenv("NFC_TC_SPLIT", "bf16" if tc == "bf16" else "fp16")
+    B = 19 if tc == "0" else 150
     d = _cols(nfc, B, 21)
     sv = nfc.synthetic.saveat(17)
     cw, layers = O.chain_spec(arch)
@@ -28,14 +32,16 @@ def test_rkc_matches_cpu_twin_all_chains(nfc, gpu_ok, arch):
     h = nfc.Handle(cw, layers, 1, sv, alg="RKC2")
     h.set_weights(theta)
     r = h.solve(d["T0"], d["colp"], d["glob"])
-    c = O.rkc_solve(d["T0"], theta, cw, layers, d["colp"], d["glob"], sv, dtype=np.float32)
+    c = O.rkc_solve(d["T0"][:19], theta, cw, layers, d["colp"][:19], d["glob"], sv, dtype=np.float32)
     assert (r["status"] == 0).all() and (c["status"] == 0).all()
+    full = r
+    r = {k: v[:19] for k, v in r.items()}
     assert rel_l2(r["T"], c["T"]).max() < TRAJ_TOL
     tot_g, tot_c = int((r["naccept"] + r["nreject"]).sum()), int((c["naccept"] + c["nreject"]).sum())
     assert abs(tot_g - tot_c) <= 0.1 * tot_c
     cnt = h.counters()
-    assert cnt["steps_accepted"] == int(r["naccept"].sum()) and cnt["steps_rejected"] == int(r["nreject"].sum())
-    assert abs(cnt["rhs_evals"] - int(c["nfe"].sum())) <= 0.1 * int(c["nfe"].sum())
+    assert cnt["steps_accepted"] == int(full["naccept"].sum()) and cnt["steps_rejected"] == int(full["nreject"].sum())
+    assert abs(cnt["rhs_evals"] * 19 / B - int(c["nfe"].sum())) <= 0.1 * int(c["nfe"].sum())
 
 
 @pytest.mark.parametrize("K", [0.0, 2.0, 10.0])
@@ -78,7 +84,9 @@ def test_rkc_needs_fewer_evaluations_when_adjustment_is_stiff(nfc, gpu_ok):
     assert er < 0.5 * et, (er, et)
 
 
-def test_rkc_columns_are_independent_and_edge_cases(nfc, gpu_ok):
+@pytest.mark.parametrize("tc", ["1", "0"])
+def test_rkc_columns_are_independent_and_edge_cases(nfc, gpu_ok, monkeypatch, tc):
+    monkeypatch.setenv("NFC_TC", tc)
     B = 333
     d = _cols(nfc, B, 13)
     sv = nfc.synthetic.saveat(5)
@@ -95,14 +103,16 @@ def test_rkc_columns_are_independent_and_edge_cases(nfc, gpu_ok):
     h.set_weights(np.zeros(h.n_params, np.float32))
     colp = np.zeros((4, 3), np.float32)
     z = h.solve(d["T0"][:4], colp, d["glob"])
-    assert (z["status"] == 0).all() and np.array_equal(z["T"], np.repeat(d["T0"][:4, None, :], 5, axis=1))
+    # (to rounding: the stage recurrence mu Y_{j-1} + nu Y_{j-2} + (1 - mu - nu) y_n reproduces a constant only to an ulp)
+    assert (z["status"] == 0).all()
+    np.testing.assert_allclose(z["T"], np.repeat(d["T0"][:4, None, :], 5, axis=1), rtol=2e-6, atol=1e-6)
     # zero network with fluxes: only the boundary cells drift, linearly (closed form)
     colp[:, 0], colp[:, 1] = 0.1, 0.3
     z = h.solve(d["T0"][:4], colp, d["glob"])
     pref = d["glob"][1] / d["glob"][0] * d["glob"][3] / d["glob"][2]
     np.testing.assert_allclose(z["T"][:, -1, 31], d["T0"][:4, 31] - pref * 0.3 * 32, rtol=2e-5, atol=1e-5)
     np.testing.assert_allclose(z["T"][:, -1, 0], d["T0"][:4, 0] + pref * 0.1 * 32, rtol=2e-5, atol=1e-5)
-    assert np.array_equal(z["T"][:, :, 1:31], np.repeat(d["T0"][:4, None, 1:31], 5, axis=1))
+    np.testing.assert_allclose(z["T"][:, :, 1:31], np.repeat(d["T0"][:4, None, 1:31], 5, axis=1), rtol=2e-6, atol=1e-6)
 
 
 def test_rkc_handle_rejects_what_it_cannot_do(nfc, gpu_ok):
