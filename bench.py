@@ -245,13 +245,15 @@ def main():
 
     # ---------------- second BASELINE metric: adjoint gradient, seconds per epoch ----------------
     # epoch = one loss + gradient over the batch (src/training.jl:45-48,70): (a) BASELINE config 3, the 9 training simulations;
-    # (b) a 16384-column batch of the config-2 distribution (what a GPU-sized training set costs)
+    # (b) the config-2 batch itself (65536 columns): the throughput regime.  (A 16384-column batch is bound by the critical path of
+    # its longest backward solve -- one column with 1100 backward steps against a median of 350 -- not by throughput.)
+    # flops_per_adjoint_column_step = 6*3*2*sum(in*out) = 880128 (the kernel actually runs 7 stages: no FSAL backwards)
     adjoint = None
     if world == 1:
         try:
             syn = nfc_b200.synthetic
             adjoint = {}
-            for tag, dd in (("config3_9sims", syn.make_columns("training9")), ("ocean_16384", syn.make_columns("ocean", B=16384, seed=2))):
+            for tag, dd in (("config3_9sims", syn.make_columns("training9")), ("ocean_65536", syn.make_columns("ocean", B=65536, seed=2))):
                 nb = dd["T0"].shape[0]
                 Tt = torch.from_numpy(np.repeat(dd["T0"][:, None, :], N_SAVE, axis=1) * np.float32(0.98)).to(dev)
                 a0, ac = torch.from_numpy(dd["T0"]).to(dev), torch.from_numpy(dd["colp"]).to(dev)
@@ -268,6 +270,11 @@ def main():
                 adjoint[tag] = {"sec_per_epoch": dt_, "columns": nb, "fwd_column_steps": ca["steps_accepted"] + ca["steps_rejected"],
                                 "adjoint_column_steps": ca["adj_steps_accepted"] + ca["adj_steps_rejected"], "device_ms": ca["last_adjoint_ms"],
                                 "adjoint_column_steps_per_sec": (ca["adj_steps_accepted"] + ca["adj_steps_rejected"]) / max(ca["last_adjoint_ms"] * 1e-3, 1e-9)}
+                if nb >= 4096:
+                    tf_ = adjoint[tag]["adjoint_column_steps_per_sec"] * 880128 / 1e12
+                    adjoint[tag]["roofline"] = {"bound": "fp32_fma", "achieved": tf_, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf_ / fp32_peak,
+                                                "flops_per_adjoint_column_step": 880128, "kernel": "adjoint_kernel (+ solve_kernel<RECORD>, both inside device_ms)"}
+                del Tt
         except Exception as e:                                     # the forward metric must not die with the extra one
             adjoint = {"error": str(e)}
 

@@ -62,6 +62,7 @@ struct AdjScratch {     // per-warp shared-memory scratch of the backward pass, 
 struct AdjSlots {
     int col[CPW];
     float t[CPW], dt[CPW], h[CPW], qold[CPW], tstop[CPW], bot[CPW], top[CPW], kca[CPW], dt_retry[CPW];
+    float th[CPW], hn[CPW];      // this stage's position inside tape interval ipos: theta in [0, 1] and the interval length
     int si[CPW], nacc[CPW], nrej[CPW], flag[CPW], mode[CPW], ipos[CPW], tlen[CPW], status[CPW];
 };
 enum : int { AFL_ACCEPT = 1, AFL_LAST = 2, AFL_DONE = 4, AFL_JUMP = 8 };
@@ -314,6 +315,35 @@ __global__ void __launch_bounds__(ADJ_NW * 32, 1) adjoint_kernel(const AdjParams
 #pragma unroll
             for (int c = 0; c < CPW; ++c) { us[c] = 0.f; uca[c] = 0.f; winv[c] = 1.f; fb[c] = 0.f; }
             if (wact) {
+            // u(t_s) from the forward tape.  Lanes 0..7 locate the tape interval of their own column side by side (the search is a
+            // chain of dependent global loads), then all 40 coefficient rows of the warp's 8 columns are fetched in one batch: done
+            // column by column the exposed latency was 8 % of all stall samples.
+            if (lane < CPW) {
+                const int col = sl->col[lane];
+                float th = 0.f, hn = 0.f;
+                if (col >= 0) {
+                    const float tcur = sl->t[lane], hc = sl->h[lane];
+                    const float ts = (s == 6 && (sl->flag[lane] & AFL_LAST)) ? sl->tstop[lane] : tcur - cs * hc;
+                    const float* base = P.tape + (long long)col * P.tape_cap * TAPE_STRIDE;
+                    int n = sl->ipos[lane];
+                    const int len = sl->tlen[lane];
+                    float tn = base[(long long)n * TAPE_STRIDE + TAPE_T];
+                    hn = base[(long long)n * TAPE_STRIDE + TAPE_H];
+                    while (n > 0 && ts < tn) { --n; tn = base[(long long)n * TAPE_STRIDE + TAPE_T]; hn = base[(long long)n * TAPE_STRIDE + TAPE_H]; }
+                    while (n + 1 < len && ts > tn + hn) { ++n; tn = base[(long long)n * TAPE_STRIDE + TAPE_T]; hn = base[(long long)n * TAPE_STRIDE + TAPE_H]; }
+                    sl->ipos[lane] = n;
+                    th = fminf(fmaxf((ts - tn) / hn, 0.f), 1.f);
+                }
+                sl->th[lane] = th; sl->hn[lane] = hn;
+            }
+            __syncwarp();
+            float e0[CPW], e1[CPW], e2[CPW], e3[CPW], e4[CPW];
+#pragma unroll
+            for (int c = 0; c < CPW; ++c) {
+                const int col = sl->col[c];
+                const float* e = P.tape + (col >= 0 ? ((long long)col * P.tape_cap + sl->ipos[c]) * TAPE_STRIDE : 0LL);   // idle slot: any valid row
+                e0[c] = e[lane]; e1[c] = e[NZ + lane]; e2[c] = e[2 * NZ + lane]; e3[c] = e[3 * NZ + lane]; e4[c] = e[4 * NZ + lane];
+            }
 #pragma unroll
             for (int c = 0; c < CPW; ++c) {
                 float acc = a0 * kap[0][c];
@@ -321,24 +351,9 @@ __global__ void __launch_bounds__(ADJ_NW * 32, 1) adjoint_kernel(const AdjParams
                 acc = fmaf(a4, kap[4][c], acc); acc = fmaf(a5, kap[5][c], acc);
                 const float hc = sl->h[c];
                 ls[c] = fmaf(hc, acc, lam[c]);
-                // u(t_s) from the forward tape
                 const int col = sl->col[c];
-                float u = 0.f;
-                if (col >= 0) {
-                    const float tcur = sl->t[c];
-                    const float ts = (s == 6 && (sl->flag[c] & AFL_LAST)) ? sl->tstop[c] : tcur - cs * hc;
-                    const float* base = P.tape + (long long)col * P.tape_cap * TAPE_STRIDE;
-                    int n = sl->ipos[c];
-                    const int len = sl->tlen[c];
-                    float tn = base[(long long)n * TAPE_STRIDE + TAPE_T], hn = base[(long long)n * TAPE_STRIDE + TAPE_H];
-                    while (n > 0 && ts < tn) { --n; tn = base[(long long)n * TAPE_STRIDE + TAPE_T]; hn = base[(long long)n * TAPE_STRIDE + TAPE_H]; }
-                    while (n + 1 < len && ts > tn + hn) { ++n; tn = base[(long long)n * TAPE_STRIDE + TAPE_T]; hn = base[(long long)n * TAPE_STRIDE + TAPE_H]; }
-                    __syncwarp();
-                    if (lane == 0) sl->ipos[c] = n;
-                    const float th = fminf(fmaxf((ts - tn) / hn, 0.f), 1.f);
-                    const float* e = base + (long long)n * TAPE_STRIDE;
-                    u = fmaf(hn, th * fmaf(th, fmaf(th, fmaf(th, e[4 * NZ + lane], e[3 * NZ + lane]), e[2 * NZ + lane]), e[NZ + lane]), e[lane]);
-                }
+                const float th = sl->th[c];
+                const float u = col >= 0 ? fmaf(sl->hn[c], th * fmaf(th, fmaf(th, fmaf(th, e4[c], e3[c]), e2[c]), e1[c]), e0[c]) : 0.f;
                 us[c] = u;
                 // quadrature weight folded into the back-propagated vector (stage 7 carries weight 0: propagate unscaled, skip dW)
                 const float sgn = sl->mode[c] ? -1.f : 1.f;
@@ -613,26 +628,30 @@ int adjoint_loss_grad(nfc_handle* h, const float* T0, const float* colp, float p
         P.Ttrue = Ttrue + off * (int64_t)n_save * NZ; P.resid = h->a_resid.p; P.tape = h->a_tape.p; P.tape_len = h->a_tlen.p;
         P.loss_sum = loss_sum_dev; P.tape_cap = cap;
         if (int rc = nfc_launch_record<N>(h, P, st, first)) return rc;
-        // backward queue: columns with the longest forward solves first (their backward solves are the longest too)
+        // backward queue, longest first.  Key: the per-column backward step counts of the previous call on the same batch size (a
+        // training loop solves the same columns every epoch), else the forward tape length (a forward-stiff column is usually
+        // backward-stiff too, but outliers -- 1100 backward steps against a median of 350 -- are only known from history).
         const int* order = nullptr;
+        NFC_CUDA(h, h->a_adjsteps.ensure((size_t)B));
+        if (h->a_adjhist_B != B) { h->a_adjhist_B = B; h->a_adjhist_valid = false; }
         if (h->use_sched && nb >= 2048) {
+            const int* key = h->a_adjhist_valid ? h->a_adjsteps.p + off : h->a_tlen.p;
             NFC_CUDA(h, h->d_order.ensure((size_t)nb));
             NFC_CUDA(h, h->d_hist.ensure(SCHED_BUCKETS));
             NFC_CUDA(h, cudaMemsetAsync(h->d_hist.p, 0, sizeof(int) * SCHED_BUCKETS, st));
             const int nblk = (int)((nb + 255) / 256);
-            sched_hist_kernel<<<nblk, 256, 0, st>>>(h->a_tlen.p, h->d_hist.p, nb);
+            sched_hist_kernel<<<nblk, 256, 0, st>>>(key, h->d_hist.p, nb);
             sched_scan_kernel<<<1, SCHED_BUCKETS, 0, st>>>(h->d_hist.p);
-            sched_scatter_kernel<<<nblk, 256, 0, st>>>(h->a_tlen.p, h->d_hist.p, h->d_order.p, nb);
+            sched_scatter_kernel<<<nblk, 256, 0, st>>>(key, h->d_hist.p, h->d_order.p, nb);
             NFC_CUDA(h, cudaGetLastError());
             order = h->d_order.p;
             h->last_launches += 3;
         }
         AdjParams A{};
         A.order = order;
-        NFC_CUDA(h, h->a_adjsteps.ensure((size_t)nb));
-        NFC_CUDA(h, cudaMemsetAsync(h->a_adjsteps.p, 0, sizeof(int) * nb, st));
-        A.adj_steps = h->a_adjsteps.p;
-        h->a_adjsteps_n = nb;
+        NFC_CUDA(h, cudaMemsetAsync(h->a_adjsteps.p + off, 0, sizeof(int) * nb, st));     // after the order is built (stream order)
+        A.adj_steps = h->a_adjsteps.p + off;
+        h->a_adjsteps_n = B;
         A.wpack = h->d_wpack.p; A.colp = colp + off * 3; A.saveat = h->d_saveat.p; A.resid = h->a_resid.p; A.tape = h->a_tape.p;
         A.tape_len = h->a_tlen.p; A.status = st_all + off; A.gacc = h->a_gacc.p; A.counters = h->d_counters.p; A.B = nb; A.n_save = n_save;
         A.tape_cap = cap; A.max_iters = h->cfg.max_iters; A.use_kca = h->cfg.nde_type == NFC_NDE_CONVECTIVE_ADJUSTMENT; A.n_params = (int)h->n_params;
@@ -648,6 +667,7 @@ int adjoint_loss_grad(nfc_handle* h, const float* T0, const float* colp, float p
     NFC_CUDA(h, cudaGetLastError());
     NFC_CUDA(h, cudaEventRecord(h->ev[3], st));
     h->ev_adj_valid = true;
+    h->a_adjhist_valid = true;
     h->last_launches += 2;
     h->last_columns = B;
     return 0;

@@ -530,7 +530,7 @@ int32_t nfc_get_adjoint_steps(nfc_handle* h, int32_t* out, int64_t n) {
     if (!h || !out) return -1;
     NFC_CUDA(h, cudaSetDevice(h->device));
     NFC_CUDA(h, cudaDeviceSynchronize());
-    if (n > h->a_adjsteps_n) return fail(h, -2, "only %lld columns in the last loss_grad chunk", (long long)h->a_adjsteps_n);
+    if (n > h->a_adjsteps_n) return fail(h, -2, "only %lld columns in the last loss_grad batch", (long long)h->a_adjsteps_n);
     NFC_CUDA(h, cudaMemcpy(out, h->a_adjsteps.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
     return 0;
 }
