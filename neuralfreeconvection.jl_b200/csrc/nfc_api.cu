@@ -15,6 +15,7 @@
 #include "nfc_forward.cuh"
 #include "nfc_launch.h"
 #include "nfc_tc.cuh"
+#include "nfc_tc2.cuh"
 #include "nfc_embedded.cuh"
 #include "nfc_rkc.cuh"
 #include "nfc_rkc_tc.cuh"
@@ -193,9 +194,26 @@ int launch_solve(nfc_handle* h, SolveParams& P, cudaStream_t st, bool reset_coun
             NFC_CUDA(h, cudaMemsetAsync(h->a_resid.p, 0, 256, st));
             P.resid = h->a_resid.p;
         }
-        if (h->tc_fp16) tc::solve_tc_kernel<tc::SplitFP16x2><<<gridt, tc::NTHREADS, tc::IMG16_BYTES, st>>>(h->d_wimg.p, P);
+        // two tiles in flight per CTA (nfc_tc2.cuh): +17..25 % throughput once the batch gives every one of the 148 x 256 column slots
+        // several columns; below that the one-tile kernel's lower step latency (29 vs 42 us) wins.  NFC_TC_TILES=1|2 forces a kernel.
+        const bool two_tiles = h->tc_fp16 && (h->tc_tiles == 2 || (h->tc_tiles == 0 && B >= h->tc2_min_columns));
+        if (two_tiles) {
+            const int grid2 = (int)std::min<long long>(h->num_sms, (B + 2 * tc::TILE - 1) / (2 * tc::TILE));
+            if (P.resid) tc2::solve_tc2_kernel<true><<<grid2, tc2::NT2, tc2::SMEM2_BYTES, st>>>(h->d_wimg.p, P);
+            else tc2::solve_tc2_kernel<false><<<grid2, tc2::NT2, tc2::SMEM2_BYTES, st>>>(h->d_wimg.p, P);
+        } else if (h->tc_fp16) tc::solve_tc_kernel<tc::SplitFP16x2><<<gridt, tc::NTHREADS, tc::IMG16_BYTES, st>>>(h->d_wimg.p, P);
         else tc::solve_tc_kernel<tc::SplitBF16x3><<<gridt, tc::NTHREADS, tc::IMG_BYTES, st>>>(h->d_wimg.p, P);
-        if (P.resid) {
+        if (P.resid && two_tiles) {
+            long long dbg[12];
+            NFC_CUDA(h, cudaStreamSynchronize(st));
+            NFC_CUDA(h, cudaMemcpy(dbg, P.resid, sizeof dbg, cudaMemcpyDeviceToHost));
+            const double n = (double)std::max<long long>(dbg[7], 1);
+            fprintf(stderr, "[nfc tc2 debug] thread 0 of CTA 0, cycles per stage of BOTH tiles (%lld stages): step end %.0f | stage inputs %.0f | hidden epilogues %.0f "
+                            "(waiting for D: layer 1 %.0f, layer 2 %.0f) | output epilogues %.0f (waiting %.0f) | total %.0f\n",
+                    dbg[7], dbg[0] / n, dbg[1] / n, dbg[2] / n, dbg[4] / n, dbg[5] / n, dbg[3] / n, dbg[6] / n, (dbg[0] + dbg[1] + dbg[2] + dbg[3]) / n);
+            fprintf(stderr, "[nfc tc2 debug] step end, cycles per STEP: error estimates %.0f | barrier %.0f | control + barrier %.0f | finish %.0f\n",
+                    6 * dbg[8] / n, 6 * dbg[9] / n, 6 * dbg[10] / n, 6 * dbg[11] / n);
+        } else if (P.resid) {
             long long dbg[32];
             NFC_CUDA(h, cudaStreamSynchronize(st));
             NFC_CUDA(h, cudaMemcpy(dbg, P.resid, sizeof dbg, cudaMemcpyDeviceToHost));
@@ -445,9 +463,13 @@ int32_t nfc_create(const nfc_config* cfg, nfc_handle** out) {
         if (cudaFuncSetAttribute(tc::rhs_tc_kernel<tc::SplitBF16x3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::IMG_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(tc::solve_tc_kernel<tc::SplitBF16x3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::IMG_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(tc::rhs_tc_kernel<tc::SplitFP16x2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::IMG16_BYTES) != cudaSuccess ||
-            cudaFuncSetAttribute(tc::solve_tc_kernel<tc::SplitFP16x2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::IMG16_BYTES) != cudaSuccess) { h->err = "cudaFuncSetAttribute(tc) failed"; return bail(-10); }
+            cudaFuncSetAttribute(tc::solve_tc_kernel<tc::SplitFP16x2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::IMG16_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(tc2::solve_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM2_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(tc2::solve_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM2_BYTES) != cudaSuccess) { h->err = "cudaFuncSetAttribute(tc) failed"; return bail(-10); }
         h->tc_fp16 = true;                                       // default split: FP16x2 (3 MMAs / product); NFC_TC_SPLIT=bf16 selects BF16x3 (6)
         if (const char* e3 = getenv("NFC_TC_SPLIT")) h->tc_fp16 = strcmp(e3, "bf16") != 0;
+        if (const char* e4 = getenv("NFC_TC_TILES")) h->tc_tiles = atoi(e4);            // 0 auto, 1 / 2: force the one- / two-tile solve kernel
+        if (const char* e5 = getenv("NFC_TC2_MIN")) h->tc2_min_columns = atoll(e5);
         if (const char* e2 = getenv("NFC_SCHED")) h->use_sched = atoi(e2) != 0;
         const char* e = getenv("NFC_TC");          // tensor-core forward path is the default for this Chain; NFC_TC=0 selects the SIMT kernels
         h->use_tc = !(e && atoi(e) == 0);

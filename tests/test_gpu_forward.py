@@ -272,3 +272,35 @@ def test_tensor_core_out_of_range_input_is_flagged_not_wrong(nfc, gpu_ok, monkey
     assert r["status"][17] == 2
     keep = np.arange(200) != 17
     assert (r["status"][keep] == 0).all() and np.array_equal(r["T"][keep], ok["T"][keep])
+
+
+@pytest.mark.parametrize("B", [1, 127, 300, 5000])
+def test_two_tile_kernel_matches_one_tile_kernel_bit_for_bit(nfc, gpu_ok, monkeypatch, B):
+    """nfc_tc2.cuh (two 128-column tiles in flight per CTA, the large-batch kernel) performs the arithmetic of the one-tile
+    tensor-core kernel operation for operation: trajectories, step counts and status agree bit for bit, ragged sizes included
+    (one tile empty, both partly filled, several refills per slot), with an out-of-range column flagged as in the one-tile kernel."""
+    monkeypatch.setenv("NFC_TC", "1")
+    monkeypatch.setenv("NFC_TC_SPLIT", "fp16")
+    d = nfc.synthetic.make_columns("ocean", B=B, seed=21)
+    T0 = d["T0"].copy()
+    if B > 200:
+        T0[131] *= 1.0e4                      # |T_scaled| > 128: must end as status NaN in both kernels
+    sv = nfc.synthetic.saveat(33)
+    res = []
+    for tiles in ("1", "2"):
+        monkeypatch.setenv("NFC_TC_TILES", tiles)
+        h, cw, layers = _handle(nfc, saveat=sv)
+        h.set_weights(O.glorot_theta(cw, layers, 0, 0.3))
+        res.append(h.solve(T0, d["colp"], d["glob"]))
+    a, b = res
+    assert np.array_equal(a["status"], b["status"]) and np.array_equal(a["naccept"], b["naccept"]) and np.array_equal(a["nreject"], b["nreject"])
+    if B > 200:
+        assert b["status"][131] == 2
+    good = b["status"] == 0
+    assert good.sum() >= B - 1
+    assert np.array_equal(a["T"][good].view(np.uint32), b["T"][good].view(np.uint32))
+    # and against the oracle at the trajectory tolerance
+    k = min(B, 16)
+    theta = O.glorot_theta(cw, layers, 0, 0.3)
+    ref = CO.solve(d["T0"][:k], theta, cw, layers, d["colp"][:k], d["glob"], sv)
+    assert rel_l2(b["T"][:k], ref["T"]).max() < TRAJ_TOL

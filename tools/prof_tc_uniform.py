@@ -7,7 +7,7 @@ NN = nfc_b200.named_chain("dense-default", seed=0)
 for p in NN.params(): p *= 1e-5
 theta, _ = nfc_b200.destructure(NN)
 dev = torch.device("cuda:0")
-B = 148 * 128
+B = 148 * 128 * int(os.environ.get("NFC_TC_TILES", "1"))
 d = syn.make_columns("ocean", B=B, seed=1)
 T0, colp = torch.from_numpy(d["T0"]).to(dev), torch.from_numpy(d["colp"]).to(dev)
 Tout = torch.empty((B, 2, 32), device=dev); st = torch.zeros(B, dtype=torch.int32, device=dev)
