@@ -121,6 +121,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--columns", type=int, default=COLUMNS_PER_GPU, help="columns per GPU (default: BASELINE config 2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-large-batch", action="store_true", help="skip the 1,048,576-column forward solve (config 4) reported next to the headline")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -278,6 +279,37 @@ def main():
         except Exception as e:                                     # the forward metric must not die with the extra one
             adjoint = {"error": str(e)}
 
+    # ---------------- BASELINE config 4's forward half on this GPU: 1,048,576 columns (0.25 degree ocean), 129 saves ----------------
+    # (the throughput regime: every one of the 148 x 256 column slots of the two-tile kernel gets ~28 columns; config 2's 65,536 columns
+    #  give it 1.7 and are bound by slot quantisation: 135-step columns, each slot runs them back to back)
+    large_batch = None
+    if world == 1 and use_tc and not args.no_large_batch:
+        try:
+            del Tout, hout
+            BL = 1048576
+            dl = nfc_b200.synthetic.make_columns("ocean", B=BL, seed=2, K_CA=2.0)
+            lT0, lcolp = (torch.from_numpy(dl[k]).to(dev) for k in ("T0", "colp"))
+            lout = torch.empty((BL, N_SAVE, 32), device=dev, dtype=torch.float32)
+            lst = torch.zeros(BL, dtype=torch.int32, device=dev)
+            for _ in range(2):
+                h.solve_dev(lT0, lcolp, dl["glob"], lout, None, None, lst, stream=stream)
+            torch.cuda.synchronize()
+            e0.record()
+            h.solve_dev(lT0, lcolp, dl["glob"], lout, None, None, lst, stream=stream)
+            e1.record()
+            torch.cuda.synchronize()
+            cl = h.counters()
+            lsteps = cl["steps_accepted"] + cl["steps_rejected"]
+            lms = e0.elapsed_time(e1)
+            ltf = lsteps * FLOPS_PER_COLUMN_STEP / (lms * 1e-3) / 1e12
+            large_batch = {"workload": "config4 forward: 1048576 columns on one GPU, 129 saves, same Chain / tolerances", "ms": lms, "column_steps": lsteps,
+                           "value": lsteps / (lms * 1e-3), "unit": UNIT, "bad_status": int((lst != 0).sum()),
+                           "roofline": {"bound": "tensor", "achieved": ltf, "peak": bf16_peak / 3.0, "unit": "TFLOP/s", "frac": ltf / (bf16_peak / 3.0),
+                                        "kernel": "solve_tc2_kernel (two 128-column tiles in flight per CTA; picked from 98304 columns on)"}}
+            del lout, lT0, lcolp, lst
+        except Exception as e:
+            large_batch = {"error": str(e)}
+
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
@@ -289,10 +321,10 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": ("f32 (fp16x2-split tcgen05 MMAs, fp32 accumulate)" if os.environ.get("NFC_TC_SPLIT", "fp16") != "bf16" else "f32 (bf16x3-split tcgen05 MMAs, fp32 accumulate)") if use_tc else "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "kernel_path": "tcgen05" if use_tc else "simt", "columns_per_gpu": B, "column_steps_per_pass_rank0": steps_per_pass,
+            "config": {"workload": WORKLOAD, "kernel_path": "tcgen05" if use_tc else "simt", "tiles_in_flight_per_cta": (2 if (os.environ.get("NFC_TC_TILES", "0") == "2" or (os.environ.get("NFC_TC_TILES", "0") == "0" and B >= int(os.environ.get("NFC_TC2_MIN", "98304")))) else 1) if use_tc else None, "columns_per_gpu": B, "column_steps_per_pass_rank0": steps_per_pass,
                        "l2": "outputs (1.08 GB/step) exceed the 126 MB L2; no explicit flush", "parallelism": f"columns sharded x{world}, no collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(cnt["kernel_launches"]) * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "adjoint": adjoint}
+            "gpu_launches": int(cnt["kernel_launches"]) * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "adjoint": adjoint, "large_batch": large_batch}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -653,7 +653,7 @@ int32_t nfc_solve(nfc_handle* h, const float* T0, const float* colp, const float
     // Large batches are solved in three pieces so that the device->host copy of one piece (the trajectories dominate the
     // end-to-end time: 1.08 GB for 65 536 columns x 129 saves) overlaps the solve of the next one (second stream; measured +32 % end to end).
     int npieces = (B >= 65536) ? 3 : 1;
-    if (const char* e = getenv("NFC_E2E_PIECES")) npieces = std::max(1, std::min(4, atoi(e)));
+    if (const char* e = getenv("NFC_E2E_PIECES")) npieces = std::max(1, std::min(8, atoi(e)));
     if (B < 8192 * npieces) npieces = 1;
     const int64_t piece = ((B + npieces - 1) / npieces + 127) / 128 * 128;
     const float pref = prefactor(glob);

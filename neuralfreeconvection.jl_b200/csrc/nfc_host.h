@@ -38,7 +38,7 @@ struct nfc_handle {
     int64_t n_params = 0, n_packed = 0;
     bool weights_set = false;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t ev_chunk[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev_chunk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool ev_fwd_valid = false, ev_adj_valid = false;
     nfc::DevBuf<float> d_theta, d_wpack, d_saveat, d_k1, d_dt;
