@@ -276,6 +276,18 @@ def main():
                     adjoint[tag]["roofline"] = {"bound": "fp32_fma", "achieved": tf_, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf_ / fp32_peak,
                                                 "flops_per_adjoint_column_step": 880128, "kernel": "adjoint_kernel (+ solve_kernel<RECORD>, both inside device_ms)"}
                 del Tt
+                if tag == "config3_9sims" and not args.no_cpu_baseline:
+                    # the CPU twin of the same continuous adjoint (oracle/nde_oracle.c, OpenMP over the 9 simulations) on the box's cores
+                    from oracle import c_oracle as CO
+                    Tth = np.repeat(dd["T0"][:, None, :], N_SAVE, axis=1) * np.float32(0.98)
+                    cores = min(os.cpu_count() or 1, nb)
+                    tc_ = []
+                    for it in range(2):
+                        t0 = time.perf_counter()
+                        rc_ = CO.loss_grad_continuous(dd["T0"], theta, cw, layers, dd["colp"], dd["glob"], sv, Tth, nthreads=cores)
+                        tc_.append(time.perf_counter() - t0)
+                    adjoint[tag]["cpu_port"] = {"sec_per_epoch": min(tc_), "cores": cores, "kind": "port",
+                                                "adjoint_column_steps": int((rc_["adj_naccept"] + rc_["adj_nreject"]).sum())}
         except Exception as e:                                     # the forward metric must not die with the extra one
             adjoint = {"error": str(e)}
 

@@ -304,3 +304,43 @@ def test_two_tile_kernel_matches_one_tile_kernel_bit_for_bit(nfc, gpu_ok, monkey
     theta = O.glorot_theta(cw, layers, 0, 0.3)
     ref = CO.solve(d["T0"][:k], theta, cw, layers, d["colp"][:k], d["glob"], sv)
     assert rel_l2(b["T"][:k], ref["T"]).max() < TRAJ_TOL
+
+
+def test_two_tile_kernel_edge_cases(nfc, gpu_ok, monkeypatch):
+    """The two-tile kernel at the seams of its tiling: exactly one / two full tiles and one column more, fixed steps, the free NDE
+    (K_CA ignored), a NaN column, a tiny max_iters (status 4 for everybody) -- always the one-tile kernel's answer bit for bit."""
+    monkeypatch.setenv("NFC_TC", "1")
+    monkeypatch.setenv("NFC_TC_SPLIT", "fp16")
+    sv = nfc.synthetic.saveat(17)
+    cw, layers = O.chain_spec()
+    theta = O.glorot_theta(cw, layers, 3, 0.3)
+
+    def both(B, nde_type=1, bad=None, **kw):
+        d = nfc.synthetic.make_columns("ocean", B=B, seed=40 + B % 7)
+        T0 = d["T0"].copy()
+        if bad is not None:
+            T0[bad, 5] = np.nan
+        out = []
+        for tiles in ("1", "2"):
+            monkeypatch.setenv("NFC_TC_TILES", tiles)
+            h = nfc.Handle(cw, layers, nde_type, sv, **kw)
+            h.set_weights(theta)
+            out.append(h.solve(T0, d["colp"], d["glob"]))
+        a, b = out
+        for k in ("status", "naccept", "nreject"):
+            assert np.array_equal(a[k], b[k]), (B, k)
+        ok = b["status"] == 0
+        assert np.array_equal(a["T"][ok].view(np.uint32), b["T"][ok].view(np.uint32)), B
+        return b
+
+    for B in (128, 129, 256, 257):
+        r = both(B)
+        assert (r["status"] == 0).all()
+    r = both(200, fixed_dt=1.0 / 64)
+    ok = r["status"] == 0                      # a fixed step of 1/64 is beyond the stability limit of some columns: those end as NaN
+    assert ok.sum() > 100 and (r["naccept"][ok] == 64).all() and (r["nreject"][ok] == 0).all()
+    both(150, nde_type=0)
+    r = both(300, bad=140)
+    assert r["status"][140] == 2 and (np.delete(r["status"], 140) == 0).all()
+    r = both(140, max_iters=5)
+    assert (r["status"] == 1).sum() > 100      # ST_MAXITERS
