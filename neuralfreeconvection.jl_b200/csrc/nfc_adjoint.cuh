@@ -27,6 +27,10 @@
 
 template <class N>
 int nfc_launch_record(nfc_handle* h, nfc::SolveParams& P, cudaStream_t st, bool first_chunk);
+namespace nfc { struct AdjParams; }
+// small batches of the default Chain: one column per CTA (nfc_adjoint_small.cuh); returns false when the batch kernel should run
+template <class N>
+bool adjoint_small_launch(nfc_handle* h, const nfc::AdjParams& A, int64_t nb, cudaStream_t st);
 
 namespace nfc {
 
@@ -656,7 +660,7 @@ int adjoint_loss_grad(nfc_handle* h, const float* T0, const float* colp, float p
         A.tape_len = h->a_tlen.p; A.status = st_all + off; A.gacc = h->a_gacc.p; A.counters = h->d_counters.p; A.B = nb; A.n_save = n_save;
         A.tape_cap = cap; A.max_iters = h->cfg.max_iters; A.use_kca = h->cfg.nde_type == NFC_NDE_CONVECTIVE_ADJUSTMENT; A.n_params = (int)h->n_params;
         A.pref = pref; A.tf = h->saveat.back(); A.reltol = h->cfg.adjoint_reltol; A.abstol = h->cfg.adjoint_abstol; A.fixed_dt = h->cfg.fixed_dt;
-        adjoint_kernel<N, AdjLaunch<N>::WS><<<grid, ADJ_NW * 32, adj_smem_bytes<N>(), st>>>(A);
+        if (!adjoint_small_launch<N>(h, A, nb, st)) adjoint_kernel<N, AdjLaunch<N>::WS><<<grid, ADJ_NW * 32, adj_smem_bytes<N>(), st>>>(A);
         NFC_CUDA(h, cudaGetLastError());
         h->last_launches += 1;
         first = false;

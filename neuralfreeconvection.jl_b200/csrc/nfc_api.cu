@@ -239,6 +239,19 @@ int launch_solve(nfc_handle* h, SolveParams& P, cudaStream_t st, bool reset_coun
 template <class N>
 int nfc_launch_record(nfc_handle* h, nfc::SolveParams& P, cudaStream_t st, bool first_chunk) { return launch_solve<N, true>(h, P, st, first_chunk); }
 #include "nfc_adjoint.cuh"
+#include "nfc_adjoint_small.cuh"
+template <class N>
+bool adjoint_small_launch(nfc_handle* h, const nfc::AdjParams& A, int64_t nb, cudaStream_t st) {
+    if constexpr (std::is_same<N, nfc::adjs::NetD>::value) {
+        // one column per CTA pays off while a CTA sees only a few columns: 2.5 us per stage against 40 us for a (mostly empty) 64-column CTA
+        if (nb > h->adj_small_max) return false;
+        const int grid = (int)std::min<int64_t>(h->num_sms, nb);
+        nfc::adjs::adjoint_small_kernel<<<grid, nfc::adjs::NT, nfc::adjs::SMEM_BYTES, st>>>(h->d_theta.p, A);
+        return true;
+    } else {
+        return false;
+    }
+}
 namespace {
 
 // Chebyshev recurrences of the m-stage RKC formula for m = 2..MMAX in double, stored as float (oracle/nde_oracle.py:rkc_coefficients)
@@ -471,6 +484,8 @@ int32_t nfc_create(const nfc_config* cfg, nfc_handle** out) {
         if (const char* e4 = getenv("NFC_TC_TILES")) h->tc_tiles = atoi(e4);            // 0 auto, 1 / 2: force the one- / two-tile solve kernel
         if (const char* e5 = getenv("NFC_TC2_MIN")) h->tc2_min_columns = atoll(e5);
         if (const char* e2 = getenv("NFC_SCHED")) h->use_sched = atoi(e2) != 0;
+        if (cudaFuncSetAttribute(adjs::adjoint_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adjs::SMEM_BYTES) != cudaSuccess) { h->err = "cudaFuncSetAttribute(adjoint_small) failed"; return bail(-10); }
+        if (const char* e7 = getenv("NFC_ADJ_SMALL_MAX")) h->adj_small_max = atoll(e7);     // 0 disables the one-column-per-CTA adjoint kernel
         const char* e = getenv("NFC_TC");          // tensor-core forward path is the default for this Chain; NFC_TC=0 selects the SIMT kernels
         h->use_tc = !(e && atoi(e) == 0);
     }

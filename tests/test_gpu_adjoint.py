@@ -61,7 +61,9 @@ def test_loss_grad_vs_c_oracle_adaptive(nfc, gpu_ok, scale, K, tol):
     assert cos > 0.9999
     cnt = h.counters()
     tot_o = int(o["adj_naccept"].sum() + o["adj_nreject"].sum())
-    assert abs(cnt["adj_steps_accepted"] + cnt["adj_steps_rejected"] - tot_o) <= 0.05 * tot_o
+    # step counts: same controller, but a quarter of the backward steps are rejections at the stability limit, whose pattern follows
+    # the rounding of the (differently ordered) float32 sums: batch kernel within 5 %, one-column kernel within 7 % of the CPU twin
+    assert abs(cnt["adj_steps_accepted"] + cnt["adj_steps_rejected"] - tot_o) <= 0.10 * tot_o
 
 
 def test_loss_matches_forward_solve(nfc, gpu_ok):
@@ -134,3 +136,30 @@ def test_training_loop_reduces_loss(nfc, gpu_ok):
                                                  nfc.ADAM(), 6)
     losses = [hst["mean_loss"] for hst in NN2.history]
     assert len(losses) == 6 and losses[-1] < losses[0] and np.isfinite(losses).all()
+
+
+@pytest.mark.parametrize("B,K,scale,tol", [(9, 2.0, 1e-5, 2e-5), (200, 2.0, 1e-5, 2e-5), (9, 2.0, 0.3, 1e-3), (200, 2.0, 0.3, 1e-3), (200, 0.0, 0.3, 1e-3)])
+def test_one_column_per_cta_kernel_agrees_with_batch_kernel(nfc, gpu_ok, monkeypatch, B, K, scale, tol):
+    """Small batches (the reference's 9 training simulations) run the backward pass with one column per CTA and the weight gradient
+    accumulated in shared memory (nfc_adjoint_small.cuh); larger ones run the 64-columns-per-CTA batch kernel.  Same algorithm,
+    differently ordered float32 sums: loss identical (same forward pass), gradients equal to rounding for the reference's x1e-5
+    weights and within the north-star tolerance where the mixed layer's active set flips with rounding (weights x0.3, DESIGN.md
+    "Adjoint"), step counts within 5 % (the rejection pattern at the stability limit follows the rounding), and a failed column reported the same way."""
+    res = []
+    for small_max in ("0", "100000"):
+        monkeypatch.setenv("NFC_ADJ_SMALL_MAX", small_max)
+        d, cw, layers, theta, sv, colp, Ttrue, h = _setup(nfc, scale=scale, K=K, B=B)
+        T0 = d["T0"].copy()
+        if B > 9:
+            T0[7, 3] = np.nan                       # forward failure: status 2, contributes nothing to the gradient
+        r = h.loss_grad(T0, colp, d["glob"], Ttrue)
+        res.append((r, h.counters()))
+    (a, ca), (b, cb) = res
+    assert np.array_equal(a["status"], b["status"])
+    if B > 9:
+        assert b["status"][7] == 2 and (np.delete(b["status"], 7) == 0).all()
+    assert _rel(b["grad"], a["grad"]) < tol
+    na, nb = ca["adj_steps_accepted"] + ca["adj_steps_rejected"], cb["adj_steps_accepted"] + cb["adj_steps_rejected"]
+    assert abs(na - nb) <= 0.05 * na
+    if not np.isnan(a["loss"]):
+        assert abs(a["loss"] - b["loss"]) <= 1e-6 * abs(a["loss"])
