@@ -5,14 +5,16 @@
 // 24 735 weight-gradient accumulators of its CTA with RED.ADD -- a stage costs ~40 us whether the CTA holds 64 columns or one,
 // so a 9-column epoch (290 backward steps x 7 stages, strictly sequential per column) takes 70-80 ms.  Here all 256 threads of a
 // CTA work on ONE column: the Dense layers and their transposes are 128-wide matrix-vector products spread over the CTA, and the
-// weight gradient is accumulated in SHARED memory (the CTA's private copy, 100 KB, flushed once at the end), so a stage is a
-// handful of 0.1-0.3 us phases.  Same algorithm as adjoint_kernel / oracle adjoint_continuous: adaptive backward Tsit5 on lambda
+// weight gradient is accumulated in REGISTERS (24 735 accumulators = 96 per thread, flushed once per CTA at the end: a first
+// version kept them in shared memory and spent a third of every stage on the read-modify-write traffic), so a stage is a handful
+// of 0.1-0.3 us phases.  Same algorithm as adjoint_kernel / oracle adjoint_continuous: adaptive backward Tsit5 on lambda
 // with tstops at the save times, u(t) from the forward tape, quadrature weight h*b_s folded into the back-propagated vector,
 // a rejected step undone by a replay with negative weight.  Default Chain only (Dense 32 -> 128 -> 128 -> 31).
 //
 // Shared-memory layout: one padded copy of the weights serves both directions -- row stride 129 (33 for the output layer) makes
 // "thread = output neuron, loop over inputs" (W[k][n], n across threads) and "thread = input row, loop over outputs" (W[k][n],
-// k across threads) both bank-conflict free.  The gradient accumulators use the same layout.
+// k across threads) both bank-conflict free.  The tape interval the backward solve currently sits in is cached in shared memory
+// (7 stages of a step fall into one or two intervals).
 #pragma once
 #include "nfc_adjoint.cuh"
 
@@ -22,14 +24,14 @@ namespace adjs {
 using NetD = Net<128, 2, 0>;
 constexpr int H = 128, RS = H + 1, RS3 = 33, NT = 256;
 constexpr int O_W1 = 0, O_B1 = O_W1 + NZ * RS, O_W2 = O_B1 + H, O_B2 = O_W2 + H * RS, O_W3 = O_B2 + H, O_B3 = O_W3 + H * RS3, W_TOTAL = O_B3 + 32;
-constexpr int O_G = W_TOTAL;                                  // gradient accumulators, same layout
-constexpr int O_A0 = O_G + W_TOTAL, O_A1 = O_A0 + NZ, O_A2 = O_A1 + H, O_G3 = O_A2 + H, O_D2 = O_G3 + NZ, O_D1 = O_D2 + H, O_UB = O_D1 + H,
-              O_PART = O_UB + NZ, S_TOTAL = O_PART + NT;
-constexpr size_t SMEM_BYTES = sizeof(float) * S_TOTAL;        // 204 672 B
+constexpr int O_A0 = W_TOTAL, O_A1 = O_A0 + NZ, O_A2 = O_A1 + H, O_G3 = O_A2 + H, O_D2 = O_G3 + NZ, O_D1 = O_D2 + H, O_TAPE = O_D1 + H,
+              O_PART = O_TAPE + 5 * NZ, S_TOTAL = O_PART + NT;
+constexpr size_t SMEM_BYTES = sizeof(float) * S_TOTAL;        // 104 KB
 
 struct Slot {
     int col, si, nacc, nrej, flag, mode, ipos, tlen, status;
-    float t, dt, h, qold, tstop, bot, top, kca, dt_retry, th, hn;
+    float t, dt, h, qold, tstop, bot, top, kca, dt_retry, tn, hn;
+    int icached;          // tape row held in shared memory (-1: none)
 };
 
 // theta (Flux layout) index <-> padded shared-memory index
@@ -46,12 +48,22 @@ __global__ void __launch_bounds__(NT, 1) adjoint_small_kernel(const float* __res
     extern __shared__ __align__(16) float sm[];
     __shared__ Slot S;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < 2 * W_TOTAL; i += NT) sm[i] = 0.f;
+    for (int i = tid; i < W_TOTAL; i += NT) sm[i] = 0.f;
     __syncthreads();
     for (int p = tid; p < NetD::T_TOTAL; p += NT) sm[theta_to_smem(p)] = theta[p];
     if (tid == 0) S.col = -1;
     float* g = P.gacc + (size_t)blockIdx.x * P.n_params;
     const float c0 = P.pref * (float)NZ;
+    // weight-gradient accumulators of this thread:  gw2: layer 2, output n = tid & 127, inputs k = 64 (tid >> 7) + i;  gw1: layer 1, output
+    // n = tid & 127, inputs k = 16 (tid >> 7) + i;  gw3: output layer, output n = tid & 31 (< 31), hidden units k = 16 (tid >> 5) + i;
+    // biases: gb (threads < 128: b1 and b2 of neuron tid; threads < 31: b3)
+    float gw2[H / 2], gw1[NZ / 2], gw3[H / 8], gb1 = 0.f, gb2 = 0.f, gb3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < H / 2; ++i) gw2[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < NZ / 2; ++i) gw1[i] = 0.f;
+#pragma unroll
+    for (int i = 0; i < H / 8; ++i) gw3[i] = 0.f;
     float lam = 0.f, ls = 0.f, kap[7];
 #pragma unroll
     for (int j = 0; j < 7; ++j) kap[j] = 0.f;
@@ -79,6 +91,7 @@ __global__ void __launch_bounds__(NT, 1) adjoint_small_kernel(const float* __res
                     S.dt = P.fixed_dt > 0.f ? P.fixed_dt : last[TAPE_H]; S.qold = 1e-4f; S.nacc = 0; S.nrej = 0; S.flag = 0;
                     S.mode = 0; S.ipos = len - 1; S.tlen = len; S.status = ST_OK; S.dt_retry = 0.f;
                     S.bot = P.colp[next * 3 + 0]; S.top = P.colp[next * 3 + 1]; S.kca = P.use_kca ? P.colp[next * 3 + 2] : 0.f;
+                    S.icached = -1;
                     S.col = (int)next;
                 }
                 break;
@@ -109,19 +122,26 @@ __global__ void __launch_bounds__(NT, 1) adjoint_small_kernel(const float* __res
                 acc = fmaf(c_adj_a[s][1], kap[1], acc); acc = fmaf(c_adj_a[s][2], kap[2], acc); acc = fmaf(c_adj_a[s][3], kap[3], acc);
                 acc = fmaf(c_adj_a[s][4], kap[4], acc); acc = fmaf(c_adj_a[s][5], kap[5], acc);
                 ls = fmaf(hc, acc, lam);
-                // u(t_s) from the forward tape
+                // u(t_s) from the forward tape: the interval's five coefficient rows are cached in shared memory
                 const float ts = (s == 6 && (S.flag & AFL_LAST)) ? S.tstop : S.t - c_adj_c[s] * hc;
                 const float* base = P.tape + (long long)S.col * P.tape_cap * TAPE_STRIDE;
                 int n = S.ipos;
                 const int len = S.tlen;
-                float tn = base[(long long)n * TAPE_STRIDE + TAPE_T], hn = base[(long long)n * TAPE_STRIDE + TAPE_H];
-                while (n > 0 && ts < tn) { --n; tn = base[(long long)n * TAPE_STRIDE + TAPE_T]; hn = base[(long long)n * TAPE_STRIDE + TAPE_H]; }
-                while (n + 1 < len && ts > tn + hn) { ++n; tn = base[(long long)n * TAPE_STRIDE + TAPE_T]; hn = base[(long long)n * TAPE_STRIDE + TAPE_H]; }
-                __syncwarp();
-                if (lane == 0) S.ipos = n;
+                float tn = S.tn, hn = S.hn;
+                if (S.icached != n || (n > 0 && ts < tn) || (n + 1 < len && ts > tn + hn)) {
+                    tn = base[(long long)n * TAPE_STRIDE + TAPE_T]; hn = base[(long long)n * TAPE_STRIDE + TAPE_H];
+                    while (n > 0 && ts < tn) { --n; tn = base[(long long)n * TAPE_STRIDE + TAPE_T]; hn = base[(long long)n * TAPE_STRIDE + TAPE_H]; }
+                    while (n + 1 < len && ts > tn + hn) { ++n; tn = base[(long long)n * TAPE_STRIDE + TAPE_T]; hn = base[(long long)n * TAPE_STRIDE + TAPE_H]; }
+                    const float* e = base + (long long)n * TAPE_STRIDE;
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) sm[O_TAPE + j * NZ + lane] = e[j * NZ + lane];
+                    __syncwarp();
+                    if (lane == 0) { S.ipos = n; S.icached = n; S.tn = tn; S.hn = hn; }
+                    __syncwarp();
+                }
                 const float th = fminf(fmaxf((ts - tn) / hn, 0.f), 1.f);
-                const float* e = base + (long long)n * TAPE_STRIDE;
-                const float u = fmaf(hn, th * fmaf(th, fmaf(th, fmaf(th, e[4 * NZ + lane], e[3 * NZ + lane]), e[2 * NZ + lane]), e[NZ + lane]), e[lane]);
+                const float u = fmaf(hn, th * fmaf(th, fmaf(th, fmaf(th, sm[O_TAPE + 4 * NZ + lane], sm[O_TAPE + 3 * NZ + lane]), sm[O_TAPE + 2 * NZ + lane]),
+                                                   sm[O_TAPE + NZ + lane]), sm[O_TAPE + lane]);
                 const float sgn = S.mode ? -1.f : 1.f;
                 const float w = do_dw ? sgn * hc * c_adj_b[s] : 1.f;
                 winv = 1.f / w;
@@ -169,18 +189,20 @@ __global__ void __launch_bounds__(NT, 1) adjoint_small_kernel(const float* __res
             // ---- output layer backwards: d2[k] = [a2[k] > 0] sum_n W3[k][n] g3[n];  dW3[k][n] += a2[k] g3[n], db3 += g3
             if (tid < H) {
                 const int k = tid;
-                const float ak = sm[O_A2 + k];
                 float acc = 0.f;
 #pragma unroll
-                for (int n = 0; n < NZ - 1; ++n) {
-                    const float gn = sm[O_G3 + n];
-                    acc = fmaf(sm[O_W3 + k * RS3 + n], gn, acc);
-                    if (do_dw) sm[O_G + O_W3 + k * RS3 + n] = fmaf(ak, gn, sm[O_G + O_W3 + k * RS3 + n]);
+                for (int n = 0; n < NZ - 1; ++n) acc = fmaf(sm[O_W3 + k * RS3 + n], sm[O_G3 + n], acc);
+                sm[O_D2 + k] = sm[O_A2 + k] > 0.f ? acc : 0.f;
+            }
+            if (do_dw) {
+                const int n = tid & (NZ - 1), part = tid >> 5;
+                const float gn = sm[O_G3 + n];                      // row 31 is zero
+#pragma unroll
+                for (int i = 0; i < H / 8; i += 4) {
+                    const float4 a = *reinterpret_cast<const float4*>(&sm[O_A2 + part * (H / 8) + i]);
+                    gw3[i] = fmaf(a.x, gn, gw3[i]); gw3[i + 1] = fmaf(a.y, gn, gw3[i + 1]); gw3[i + 2] = fmaf(a.z, gn, gw3[i + 2]); gw3[i + 3] = fmaf(a.w, gn, gw3[i + 3]);
                 }
-                sm[O_D2 + k] = ak > 0.f ? acc : 0.f;
-            } else if (do_dw && tid < H + NZ - 1) {
-                const int n = tid - H;
-                sm[O_G + O_B3 + n] += sm[O_G3 + n];
+                if (part == 0) gb3 += gn;
             }
             __syncthreads();
             // ---- hidden layer backwards: d1[k] = [a1[k] > 0] sum_n W2[k][n] d2[n] (thread pair (k, half));  dW2[k][n] += a1[k] d2[n], db2 += d2
@@ -197,14 +219,13 @@ __global__ void __launch_bounds__(NT, 1) adjoint_small_kernel(const float* __res
                 }
                 sm[O_PART + tid] = (a0 + a1) + (a2 + a3);
                 if (do_dw) {
-                    const int n = tid & (H - 1);                 // thread pair (n, half of the k rows): conflict free across n
-                    const float dn = sm[O_D2 + n];
-#pragma unroll 4
-                    for (int kk2 = 0; kk2 < H / 2; ++kk2) {
-                        const int kr = half * (H / 2) + kk2;
-                        sm[O_G + O_W2 + kr * RS + n] = fmaf(sm[O_A1 + kr], dn, sm[O_G + O_W2 + kr * RS + n]);
+                    const float dn = sm[O_D2 + k];                  // this thread's neuron n = k of layer 2; its 64 input rows are 64 half + i
+#pragma unroll
+                    for (int i = 0; i < H / 2; i += 4) {
+                        const float4 a = *reinterpret_cast<const float4*>(&sm[O_A1 + half * (H / 2) + i]);
+                        gw2[i] = fmaf(a.x, dn, gw2[i]); gw2[i + 1] = fmaf(a.y, dn, gw2[i + 1]); gw2[i + 2] = fmaf(a.z, dn, gw2[i + 2]); gw2[i + 3] = fmaf(a.w, dn, gw2[i + 3]);
                     }
-                    if (half == 0) sm[O_G + O_B2 + n] += dn;
+                    if (half == 0) gb2 += dn;
                 }
             }
             __syncthreads();
@@ -220,12 +241,12 @@ __global__ void __launch_bounds__(NT, 1) adjoint_small_kernel(const float* __res
                 if (do_dw) {
                     const int n = tid & (H - 1), half = tid >> 7;
                     const float dn = sm[O_D1 + n];
-#pragma unroll 4
-                    for (int kk2 = 0; kk2 < NZ / 2; ++kk2) {
-                        const int kr = half * (NZ / 2) + kk2;
-                        sm[O_G + O_W1 + kr * RS + n] = fmaf(sm[O_A0 + kr], dn, sm[O_G + O_W1 + kr * RS + n]);
+#pragma unroll
+                    for (int i = 0; i < NZ / 2; i += 4) {
+                        const float4 a = *reinterpret_cast<const float4*>(&sm[O_A0 + half * (NZ / 2) + i]);
+                        gw1[i] = fmaf(a.x, dn, gw1[i]); gw1[i + 1] = fmaf(a.y, dn, gw1[i + 1]); gw1[i + 2] = fmaf(a.z, dn, gw1[i + 2]); gw1[i + 3] = fmaf(a.w, dn, gw1[i + 3]);
                     }
-                    if (half == 0) sm[O_G + O_B1 + n] += dn;
+                    if (half == 0) gb1 += dn;
                 }
             }
             __syncthreads();
@@ -309,8 +330,21 @@ __global__ void __launch_bounds__(NT, 1) adjoint_small_kernel(const float* __res
         }
         __syncthreads();
     }
-    // ---------------- flush the CTA's gradient accumulators (theta layout; the slice is private to this CTA) ----------------
-    for (int p = tid; p < NetD::T_TOTAL; p += NT) g[p] += sm[O_G + theta_to_smem(p)];
+    // ---------------- flush this thread's gradient accumulators (theta layout; the slice is private to this CTA) ----------------
+    {
+        const int n = tid & (H - 1), half = tid >> 7;
+#pragma unroll
+        for (int i = 0; i < H / 2; ++i) g[NetD::T_HID + (half * (H / 2) + i) * H + n] += gw2[i];
+#pragma unroll
+        for (int i = 0; i < NZ / 2; ++i) g[NetD::T_W0 + (half * (NZ / 2) + i) * H + n] += gw1[i];
+        if (half == 0) { g[NetD::T_B0 + n] += gb1; g[NetD::T_HID + H * H + n] += gb2; }
+        const int n3 = tid & (NZ - 1), part = tid >> 5;
+        if (n3 < NZ - 1) {
+#pragma unroll
+            for (int i = 0; i < H / 8; ++i) g[NetD::T_WL + (part * (H / 8) + i) * (NZ - 1) + n3] += gw3[i];
+            if (part == 0) g[NetD::T_BL + n3] += gb3;
+        }
+    }
 }
 
 }  // namespace adjs
