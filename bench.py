@@ -274,7 +274,7 @@ def main():
                 if nb >= 4096:
                     tf_ = adjoint[tag]["adjoint_column_steps_per_sec"] * 880128 / 1e12
                     adjoint[tag]["roofline"] = {"bound": "fp32_fma", "achieved": tf_, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf_ / fp32_peak,
-                                                "flops_per_adjoint_column_step": 880128, "kernel": "adjoint_kernel (+ solve_kernel<RECORD>, both inside device_ms)"}
+                                                "flops_per_adjoint_column_step": 880128, "kernel": "adjoint_kernel (+ the tensor-core RECORD forward pass, both inside device_ms)"}
                 del Tt
                 if tag == "config3_9sims" and not args.no_cpu_baseline:
                     # the CPU twin of the same continuous adjoint (oracle/nde_oracle.c, OpenMP over the 9 simulations) on the box's cores

@@ -186,24 +186,28 @@ int launch_solve(nfc_handle* h, SolveParams& P, cudaStream_t st, bool reset_coun
     rhs_init_kernel<N, WS, 1><<<grid0, NW * 32, smem_bytes<N>(NW), st>>>(h->d_wpack.p, P.T0, P.colp, h->d_k1.p, h->d_dt.p, B, P.pref, P.use_kca,
                                                                     P.reltol, P.abstol, P.tf, P.fixed_dt);
     NFC_CUDA(h, cudaGetLastError());
-    if (!RECORD && h->use_tc && h->arch == ARCH_DEFAULT) {
+    // tensor-core kernels: the forward solve always (default Chain), the RECORD pass of loss_grad with the FP16x2 split (NFC_TC_RECORD=0: SIMT)
+    if (h->use_tc && h->arch == ARCH_DEFAULT && (!RECORD || (h->tc_fp16 && h->tc_record))) {
         const int gridt = (int)std::min<long long>(h->num_sms, (B + tc::TILE - 1) / tc::TILE);
-        if (const char* e = getenv("NFC_TC_NPROD")) P.tape_cap = atoi(e);   // timing experiments only (results are wrong for < 6)
-        if (getenv("NFC_TC_DEBUG")) {                                        // phase timers of CTA 0 (clock64), printed after the kernel
-            NFC_CUDA(h, h->a_resid.ensure(64));
-            NFC_CUDA(h, cudaMemsetAsync(h->a_resid.p, 0, 256, st));
-            P.resid = h->a_resid.p;
+        if (!RECORD) {
+            if (const char* e = getenv("NFC_TC_NPROD")) P.tape_cap = atoi(e);   // timing experiments only (results are wrong for < 6)
+            if (getenv("NFC_TC_DEBUG")) {                                        // phase timers of CTA 0 (clock64), printed after the kernel
+                NFC_CUDA(h, h->a_resid.ensure(64));
+                NFC_CUDA(h, cudaMemsetAsync(h->a_resid.p, 0, 256, st));
+                P.resid = h->a_resid.p;
+            }
         }
         // two tiles in flight per CTA (nfc_tc2.cuh): +17..25 % throughput once the batch gives every one of the 148 x 256 column slots
         // several columns; below that the one-tile kernel's lower step latency (29 vs 42 us) wins.  NFC_TC_TILES=1|2 forces a kernel.
         const bool two_tiles = h->tc_fp16 && (h->tc_tiles == 2 || (h->tc_tiles == 0 && B >= h->tc2_min_columns));
+        const bool dbg = !RECORD && P.resid;
         if (two_tiles) {
             const int grid2 = (int)std::min<long long>(h->num_sms, (B + 2 * tc::TILE - 1) / (2 * tc::TILE));
-            if (P.resid) tc2::solve_tc2_kernel<true><<<grid2, tc2::NT2, tc2::SMEM2_BYTES, st>>>(h->d_wimg.p, P);
-            else tc2::solve_tc2_kernel<false><<<grid2, tc2::NT2, tc2::SMEM2_BYTES, st>>>(h->d_wimg.p, P);
-        } else if (h->tc_fp16) tc::solve_tc_kernel<tc::SplitFP16x2><<<gridt, tc::NTHREADS, tc::IMG16_BYTES, st>>>(h->d_wimg.p, P);
-        else tc::solve_tc_kernel<tc::SplitBF16x3><<<gridt, tc::NTHREADS, tc::IMG_BYTES, st>>>(h->d_wimg.p, P);
-        if (P.resid && two_tiles) {
+            if (dbg) tc2::solve_tc2_kernel<true, false><<<grid2, tc2::NT2, tc2::SMEM2_BYTES, st>>>(h->d_wimg.p, P);
+            else tc2::solve_tc2_kernel<false, RECORD><<<grid2, tc2::NT2, tc2::SMEM2_BYTES, st>>>(h->d_wimg.p, P);
+        } else if (h->tc_fp16) tc::solve_tc_kernel<tc::SplitFP16x2, RECORD><<<gridt, tc::NTHREADS, tc::IMG16_BYTES, st>>>(h->d_wimg.p, P);
+        else tc::solve_tc_kernel<tc::SplitBF16x3, false><<<gridt, tc::NTHREADS, tc::IMG_BYTES, st>>>(h->d_wimg.p, P);
+        if (dbg && two_tiles) {
             long long dbg[12];
             NFC_CUDA(h, cudaStreamSynchronize(st));
             NFC_CUDA(h, cudaMemcpy(dbg, P.resid, sizeof dbg, cudaMemcpyDeviceToHost));
@@ -213,7 +217,7 @@ int launch_solve(nfc_handle* h, SolveParams& P, cudaStream_t st, bool reset_coun
                     dbg[7], dbg[0] / n, dbg[1] / n, dbg[2] / n, dbg[4] / n, dbg[5] / n, dbg[3] / n, dbg[6] / n, (dbg[0] + dbg[1] + dbg[2] + dbg[3]) / n);
             fprintf(stderr, "[nfc tc2 debug] step end, cycles per STEP: error estimates %.0f | barrier %.0f | control + barrier %.0f | finish %.0f\n",
                     6 * dbg[8] / n, 6 * dbg[9] / n, 6 * dbg[10] / n, 6 * dbg[11] / n);
-        } else if (P.resid) {
+        } else if (dbg) {
             long long dbg[32];
             NFC_CUDA(h, cudaStreamSynchronize(st));
             NFC_CUDA(h, cudaMemcpy(dbg, P.resid, sizeof dbg, cudaMemcpyDeviceToHost));
@@ -477,12 +481,15 @@ int32_t nfc_create(const nfc_config* cfg, nfc_handle** out) {
             cudaFuncSetAttribute(tc::solve_tc_kernel<tc::SplitBF16x3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::IMG_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(tc::rhs_tc_kernel<tc::SplitFP16x2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::IMG16_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(tc::solve_tc_kernel<tc::SplitFP16x2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::IMG16_BYTES) != cudaSuccess ||
-            cudaFuncSetAttribute(tc2::solve_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM2_BYTES) != cudaSuccess ||
-            cudaFuncSetAttribute(tc2::solve_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM2_BYTES) != cudaSuccess) { h->err = "cudaFuncSetAttribute(tc) failed"; return bail(-10); }
+            cudaFuncSetAttribute(tc::solve_tc_kernel<tc::SplitFP16x2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::IMG16_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(tc2::solve_tc2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM2_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(tc2::solve_tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM2_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(tc2::solve_tc2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM2_BYTES) != cudaSuccess) { h->err = "cudaFuncSetAttribute(tc) failed"; return bail(-10); }
         h->tc_fp16 = true;                                       // default split: FP16x2 (3 MMAs / product); NFC_TC_SPLIT=bf16 selects BF16x3 (6)
         if (const char* e3 = getenv("NFC_TC_SPLIT")) h->tc_fp16 = strcmp(e3, "bf16") != 0;
         if (const char* e4 = getenv("NFC_TC_TILES")) h->tc_tiles = atoi(e4);            // 0 auto, 1 / 2: force the one- / two-tile solve kernel
         if (const char* e5 = getenv("NFC_TC2_MIN")) h->tc2_min_columns = atoll(e5);
+        if (const char* e8 = getenv("NFC_TC_RECORD")) h->tc_record = atoi(e8) != 0;         // 0: the forward pass of loss_grad stays on the FP32 SIMT kernel
         if (const char* e2 = getenv("NFC_SCHED")) h->use_sched = atoi(e2) != 0;
         if (cudaFuncSetAttribute(adjs::adjoint_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adjs::SMEM_BYTES) != cudaSuccess) { h->err = "cudaFuncSetAttribute(adjoint_small) failed"; return bail(-10); }
         if (const char* e7 = getenv("NFC_ADJ_SMALL_MAX")) h->adj_small_max = atoll(e7);     // 0 disables the one-column-per-CTA adjoint kernel

@@ -48,6 +48,7 @@ struct nfc_handle {
     int rkc_mmax = 2;   // ensemble members (nfc_solve_ensemble)
     nfc::DevBuf<unsigned char> d_wimg;      // tensor-core weight image (default Chain only)
     bool use_tc = false;
+    bool tc_record = true;                  // forward (RECORD) pass of loss_grad on the tensor-core kernels (FP16x2 split)
     int tc_tiles = 0;                       // FP16x2 solve: 0 = pick by batch size, 1 = one tile per CTA (nfc_tc.cuh), 2 = two tiles in flight (nfc_tc2.cuh)
     int64_t tc2_min_columns = 98304;        // auto: two tiles from this batch size on
     bool tc_fp16 = false;                   // tensor-core split: false = BF16x3 (6 MMAs / product), true = FP16x2 (3 MMAs, scaled operands)

@@ -666,17 +666,20 @@ __device__ __forceinline__ void combine6(uint32_t tl, int q, const float (&k1)[8
     for (int i = 0; i < 8; ++i) acc[i] = fmaf(coef[5], kb[i], acc[i]);
 }
 
-template <class SP>
+// RECORD: forward pass of nfc_loss_grad (nfc_adjoint.cuh): instead of the trajectory it writes the residuals at the save points, the
+// dense tape (u_n and the interpolant in power basis per accepted step; the row index is the column's accepted-step count) and the
+// sum of squared residuals -- the same quantities as solve_kernel<RECORD>.
+template <class SP, bool RECORD = false>
 __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned char* __restrict__ gimg, const SolveParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ TcShared S;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    tc_prologue(&S, smem_raw, gimg, warp, SP::IMG, (P.tape_cap >= 1 && P.tape_cap <= 6) ? P.tape_cap : 6);   // tape_cap is unused by this kernel: timing knob
+    tc_prologue(&S, smem_raw, gimg, warp, SP::IMG, (!RECORD && P.tape_cap >= 1 && P.tape_cap <= 6) ? P.tape_cap : 6);   // forward solve: tape_cap doubles as a timing knob
     const uint32_t smem_img = smem_u32(smem_raw);
     const float* sbias = reinterpret_cast<const float*>(smem_raw + SP::BIAS_OFF);
     if (warp >= NCT / 32) {
         reg_dec<REGS_MMA>();
-        if (warp == NCT / 32) mma_warp_loop<SP>(&S, smem_img, lane, reinterpret_cast<long long*>(P.resid));   // P.resid is unused here: debug timers
+        if (warp == NCT / 32) mma_warp_loop<SP>(&S, smem_img, lane, RECORD ? nullptr : reinterpret_cast<long long*>(P.resid));   // forward solve: P.resid carries the debug timers
     } else {
         reg_inc<REGS_COL>();
         const int wq = warp & 3, q = warp >> 2, c = 32 * wq + lane;
@@ -688,6 +691,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
         int col = -1, si = 0, nacc = 0, nrej = 0, status = ST_OK;
         float t = 0.f, dt = 0.f, qold = 1e-4f, bot = 0.f, top = 0.f, kk = 0.f;
         bool queue_empty = false, done = true;       // done => slot wants a (new) column
+        double lsum = 0.0;                           // RECORD: this thread's sum of squared residuals
         const float zero8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int i = 0; i < 8; ++i) { u[i] = 0.f; k1[i] = 0.f; }
@@ -701,6 +705,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
                         if (P.nreject) P.nreject[col] = nrej;
                         if (P.status) P.status[col] = status;
                         if (P.work) P.work[col] = nacc + nrej;
+                        if (RECORD) P.tape_len[col] = nacc < P.tape_cap ? nacc : P.tape_cap;
                         atomicAdd(&P.counters[CTR_ACCEPT], (unsigned long long)nacc);
                         atomicAdd(&P.counters[CTR_REJECT], (unsigned long long)nrej);
                     }
@@ -738,9 +743,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
                         bot = P.colp[(long long)nc * 3 + 0]; top = P.colp[(long long)nc * 3 + 1];
                         kk = P.use_kca ? P.colp[(long long)nc * 3 + 2] * (float)NZ : 0.f;
                         while (si < P.n_save && P.saveat[si] <= 0.f) {
-                            float* o2 = P.Tout + ((long long)nc * P.n_save + si) * NZ + 8 * q;
-                            *reinterpret_cast<float4*>(o2) = make_float4(u[0], u[1], u[2], u[3]);
-                            *reinterpret_cast<float4*>(o2 + 4) = make_float4(u[4], u[5], u[6], u[7]);
+                            const long long o2i = ((long long)nc * P.n_save + si) * NZ + 8 * q;
+                            if (RECORD) {
+                                const float4 ta = *reinterpret_cast<const float4*>(P.Ttrue + o2i), tb = *reinterpret_cast<const float4*>(P.Ttrue + o2i + 4);
+                                const float r[8] = {u[0] - ta.x, u[1] - ta.y, u[2] - ta.z, u[3] - ta.w, u[4] - tb.x, u[5] - tb.y, u[6] - tb.z, u[7] - tb.w};
+                                *reinterpret_cast<float4*>(P.resid + o2i) = make_float4(r[0], r[1], r[2], r[3]);
+                                *reinterpret_cast<float4*>(P.resid + o2i + 4) = make_float4(r[4], r[5], r[6], r[7]);
+                                float sse = 0.f;
+#pragma unroll
+                                for (int i = 0; i < 8; ++i) sse = fmaf(r[i], r[i], sse);
+                                lsum += (double)sse;
+                            } else {
+                                float* o2 = P.Tout + o2i;
+                                *reinterpret_cast<float4*>(o2) = make_float4(u[0], u[1], u[2], u[3]);
+                                *reinterpret_cast<float4*>(o2 + 4) = make_float4(u[4], u[5], u[6], u[7]);
+                            }
                             ++si;
                         }
                     } else {
@@ -833,16 +850,45 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
                 }
                 if (accept) {
                     const float tn = last ? P.tf : t + hs;
+                    if (RECORD) {
+                        if (nacc < P.tape_cap) {
+                            float* e = P.tape + ((long long)col * P.tape_cap + nacc) * TAPE_STRIDE + 8 * q;
+#pragma unroll
+                            for (int hlf = 0; hlf < 2; ++hlf) {
+                                const int i = 4 * hlf;
+                                *reinterpret_cast<float4*>(e + i) = make_float4(u[i], u[i + 1], u[i + 2], u[i + 3]);
+                                *reinterpret_cast<float4*>(e + NZ + i) = make_float4(k1[i], k1[i + 1], k1[i + 2], k1[i + 3]);
+                                *reinterpret_cast<float4*>(e + 2 * NZ + i) = make_float4(c2[i], c2[i + 1], c2[i + 2], c2[i + 3]);
+                                *reinterpret_cast<float4*>(e + 3 * NZ + i) = make_float4(c3[i], c3[i + 1], c3[i + 2], c3[i + 3]);
+                                *reinterpret_cast<float4*>(e + 4 * NZ + i) = make_float4(c4[i], c4[i + 1], c4[i + 2], c4[i + 3]);
+                            }
+                            if (q == 0) { e[TAPE_T] = t; e[TAPE_H] = hs; }
+                        } else {
+                            status = ST_TAPE_OVERFLOW;
+                        }
+                    }
                     while (si < P.n_save) {
                         const float ts = P.saveat[si];
                         if (ts > tn) break;
                         const float th = fminf((ts - t) / hs, 1.0f);
-                        float* o2 = P.Tout + ((long long)col * P.n_save + si) * NZ + 8 * q;
+                        const long long o2i = ((long long)col * P.n_save + si) * NZ + 8 * q;
                         float v[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) v[i] = fmaf(hs, th * fmaf(th, fmaf(th, fmaf(th, c4[i], c3[i]), c2[i]), k1[i]), u[i]);
-                        *reinterpret_cast<float4*>(o2) = make_float4(v[0], v[1], v[2], v[3]);
-                        *reinterpret_cast<float4*>(o2 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                        if (RECORD) {
+                            const float4 ta = *reinterpret_cast<const float4*>(P.Ttrue + o2i), tb = *reinterpret_cast<const float4*>(P.Ttrue + o2i + 4);
+                            const float r[8] = {v[0] - ta.x, v[1] - ta.y, v[2] - ta.z, v[3] - ta.w, v[4] - tb.x, v[5] - tb.y, v[6] - tb.z, v[7] - tb.w};
+                            *reinterpret_cast<float4*>(P.resid + o2i) = make_float4(r[0], r[1], r[2], r[3]);
+                            *reinterpret_cast<float4*>(P.resid + o2i + 4) = make_float4(r[4], r[5], r[6], r[7]);
+                            float sse = 0.f;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) sse = fmaf(r[i], r[i], sse);
+                            lsum += (double)sse;
+                        } else {
+                            float* o2 = P.Tout + o2i;
+                            *reinterpret_cast<float4*>(o2) = make_float4(v[0], v[1], v[2], v[3]);
+                            *reinterpret_cast<float4*>(o2 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                        }
                         ++si;
                     }
 #pragma unroll
@@ -862,9 +908,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
                 if (status != ST_OK) done = true;
             }
         }
-        if (P.resid && blockIdx.x == 0 && threadIdx.x == 0) {
+        if (!RECORD && P.resid && blockIdx.x == 0 && threadIdx.x == 0) {
             long long* dbg = reinterpret_cast<long long*>(P.resid);
             dbg[16] = twd[0]; dbg[17] = twd[1]; dbg[18] = twd[2]; dbg[19] = clock64() - tstart;
+        }
+        if (RECORD) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(FULL, lsum, o);
+            if (lane == 0) atomicAdd(P.loss_sum, lsum);
         }
         // release the MMA warp
         cta_bar();

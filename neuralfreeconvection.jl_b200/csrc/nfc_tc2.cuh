@@ -265,11 +265,11 @@ __device__ __forceinline__ void output_epilogue(Shared2* S, unsigned char* ks, c
 }
 
 // ---- end of a step ------------------------------------------------------------------------------------------------------------
-struct StepOld { float t, hs; int col, si, ctl; };
+struct StepOld { float t, hs; int col, si, ctl, nacc; };
 
 template <int T>
 __device__ __forceinline__ void step_error(Shared2* S, unsigned char* ks, const SolveParams& P, TileRegs& R, StepOld& o, uint32_t tl, int q, int c) {
-    o.t = S->cs[T].t[c]; o.hs = S->cs[T].hs[c]; o.col = S->cs[T].col[c]; o.si = S->cs[T].si[c]; o.ctl = S->cs[T].ctl[c];
+    o.t = S->cs[T].t[c]; o.hs = S->cs[T].hs[c]; o.col = S->cs[T].col[c]; o.si = S->cs[T].si[c]; o.ctl = S->cs[T].ctl[c]; o.nacc = S->cs[T].nacc[c];
     const float bt[6] = {NFC_BT1, NFC_BT2, NFC_BT3, NFC_BT4, NFC_BT5, NFC_BT6};
     float e[8], part = 0.f;
     combine<T>(tl, ks, q, c, R.k1, bt, 6, e);
@@ -287,7 +287,7 @@ __device__ __forceinline__ void step_error(Shared2* S, unsigned char* ks, const 
 }
 
 // quarter-0 thread of column c: controller, retire / refill, next step size (scalar state in shared memory)
-template <int T>
+template <int T, bool RECORD>
 __device__ __forceinline__ void step_control(Shared2* S, const SolveParams& P, int c) {
     Cols& C = S->cs[T];
     int col = C.col[c];
@@ -318,6 +318,7 @@ __device__ __forceinline__ void step_control(Shared2* S, const SolveParams& P, i
             C.si[c] = si;
             C.t[c] = tn;
             if (P.fixed_dt <= 0.f) C.qold[c] = fmaxf(ee, 1e-4f);
+            if (RECORD && nacc >= P.tape_cap) status = ST_TAPE_OVERFLOW;      // no tape row left for this step
             ++nacc;
             if (tn >= P.tf) done = true;
             newctl |= CTL_ACCEPT;
@@ -336,6 +337,7 @@ __device__ __forceinline__ void step_control(Shared2* S, const SolveParams& P, i
             if (P.nreject) P.nreject[col] = nrej;
             if (P.status) P.status[col] = status;
             if (P.work) P.work[col] = nacc + nrej;
+            if (RECORD) P.tape_len[col] = nacc < P.tape_cap ? nacc : P.tape_cap;
             atomicAdd(&P.counters[CTR_ACCEPT], (unsigned long long)nacc);
             atomicAdd(&P.counters[CTR_REJECT], (unsigned long long)nrej);
         }
@@ -373,8 +375,27 @@ __device__ __forceinline__ void step_control(Shared2* S, const SolveParams& P, i
 }
 
 // all four threads of a column: dense output of the accepted step, state update, load of a new column
-template <int T>
-__device__ __forceinline__ void step_finish(Shared2* S, unsigned char* ks, const SolveParams& P, TileRegs& R, const StepOld& o, uint32_t tl, int q, int c) {
+// (RECORD: residuals, tape row and squared-residual sum instead of the trajectory, as in tc::solve_tc_kernel<SP, true>)
+template <bool RECORD>
+__device__ __forceinline__ void save_point(const SolveParams& P, long long o2i, const float (&v)[8], double& lsum) {
+    if (RECORD) {
+        const float4 ta = *reinterpret_cast<const float4*>(P.Ttrue + o2i), tb = *reinterpret_cast<const float4*>(P.Ttrue + o2i + 4);
+        const float r[8] = {v[0] - ta.x, v[1] - ta.y, v[2] - ta.z, v[3] - ta.w, v[4] - tb.x, v[5] - tb.y, v[6] - tb.z, v[7] - tb.w};
+        *reinterpret_cast<float4*>(P.resid + o2i) = make_float4(r[0], r[1], r[2], r[3]);
+        *reinterpret_cast<float4*>(P.resid + o2i + 4) = make_float4(r[4], r[5], r[6], r[7]);
+        float sse = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) sse = fmaf(r[i], r[i], sse);
+        lsum += (double)sse;
+    } else {
+        float* o2 = P.Tout + o2i;
+        *reinterpret_cast<float4*>(o2) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(o2 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
+
+template <int T, bool RECORD>
+__device__ __forceinline__ void step_finish(Shared2* S, unsigned char* ks, const SolveParams& P, TileRegs& R, const StepOld& o, uint32_t tl, int q, int c, double& lsum) {
     // dense output in power basis, u(t + th h) = u + h th (k1 + th (c2 + th (c3 + th c4))): the loads are warp-collective
     float c2[8], c3[8], c4[8];
     {
@@ -406,16 +427,27 @@ __device__ __forceinline__ void step_finish(Shared2* S, unsigned char* ks, const
     if (o.col >= 0 && (ctl & CTL_ACCEPT)) {
         const float tn = (o.ctl & CTL_LAST) ? P.tf : o.t + o.hs;
         int si = o.si;
+        if (RECORD && o.nacc < P.tape_cap) {
+            float* e = P.tape + ((long long)o.col * P.tape_cap + o.nacc) * TAPE_STRIDE + 8 * q;
+#pragma unroll
+            for (int hlf = 0; hlf < 2; ++hlf) {
+                const int i = 4 * hlf;
+                *reinterpret_cast<float4*>(e + i) = make_float4(R.u[i], R.u[i + 1], R.u[i + 2], R.u[i + 3]);
+                *reinterpret_cast<float4*>(e + NZ + i) = make_float4(R.k1[i], R.k1[i + 1], R.k1[i + 2], R.k1[i + 3]);
+                *reinterpret_cast<float4*>(e + 2 * NZ + i) = make_float4(c2[i], c2[i + 1], c2[i + 2], c2[i + 3]);
+                *reinterpret_cast<float4*>(e + 3 * NZ + i) = make_float4(c3[i], c3[i + 1], c3[i + 2], c3[i + 3]);
+                *reinterpret_cast<float4*>(e + 4 * NZ + i) = make_float4(c4[i], c4[i + 1], c4[i + 2], c4[i + 3]);
+            }
+            if (q == 0) { e[TAPE_T] = o.t; e[TAPE_H] = o.hs; }
+        }
         while (si < P.n_save) {
             const float ts = P.saveat[si];
             if (ts > tn) break;
             const float th = fminf((ts - o.t) / o.hs, 1.0f);
-            float* o2 = P.Tout + ((long long)o.col * P.n_save + si) * NZ + 8 * q;
             float v[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = fmaf(o.hs, th * fmaf(th, fmaf(th, fmaf(th, c4[i], c3[i]), c2[i]), R.k1[i]), R.u[i]);
-            *reinterpret_cast<float4*>(o2) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(o2 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            save_point<RECORD>(P, ((long long)o.col * P.n_save + si) * NZ + 8 * q, v, lsum);
             ++si;
         }
 #pragma unroll
@@ -433,9 +465,7 @@ __device__ __forceinline__ void step_finish(Shared2* S, unsigned char* ks, const
             }
             int si = 0;
             while (si < P.n_save && P.saveat[si] <= 0.f) {
-                float* o2 = P.Tout + ((long long)nc * P.n_save + si) * NZ + 8 * q;
-                *reinterpret_cast<float4*>(o2) = make_float4(R.u[0], R.u[1], R.u[2], R.u[3]);
-                *reinterpret_cast<float4*>(o2 + 4) = make_float4(R.u[4], R.u[5], R.u[6], R.u[7]);
+                save_point<RECORD>(P, ((long long)nc * P.n_save + si) * NZ + 8 * q, R.u, lsum);
                 ++si;
             }
         } else {
@@ -445,7 +475,7 @@ __device__ __forceinline__ void step_finish(Shared2* S, unsigned char* ks, const
     }
 }
 
-template <bool DBG>
+template <bool DBG, bool RECORD = false>
 __global__ void __launch_bounds__(NT2, 1) solve_tc2_kernel(const unsigned char* __restrict__ gimg, const SolveParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     unsigned char* ks = smem_raw + IMG_PAD;
@@ -506,6 +536,7 @@ __global__ void __launch_bounds__(NT2, 1) solve_tc2_kernel(const unsigned char* 
         // waiting for the accumulator of layer 1 / 2 / 3, [7] stages
         long long tm[8] = {0, 0, 0, 0, 0, 0, 0, 0}, te[4] = {0, 0, 0, 0};   // te: step end = error estimate | barrier | control + barrier | finish
         bool ydead = false;
+        double lsum = 0.0;                   // RECORD: this thread's sum of squared residuals
         while (true) {
             StepOld ox, oy;
             long long c0 = tick<DBG>();
@@ -515,12 +546,12 @@ __global__ void __launch_bounds__(NT2, 1) solve_tc2_kernel(const unsigned char* 
             long long e1 = tick<DBG>(); te[0] += e1 - c0;
             cta_bar();
             long long e2 = tick<DBG>(); te[1] += e2 - e1;
-            if (q == 0) step_control<0>(S, P, c);                 // the two tiles' controllers run side by side in different warps
-            else if (q == 1 && !ydead) step_control<1>(S, P, c);
+            if (q == 0) step_control<0, RECORD>(S, P, c);         // the two tiles' controllers run side by side in different warps
+            else if (q == 1 && !ydead) step_control<1, RECORD>(S, P, c);
             cta_bar();
             e1 = tick<DBG>(); te[2] += e1 - e2;
-            step_finish<0>(S, ks, P, X, ox, tl, q, c);
-            if (!ydead) step_finish<1>(S, ks, P, Y, oy, tl, q, c);
+            step_finish<0, RECORD>(S, ks, P, X, ox, tl, q, c, lsum);
+            if (!ydead) step_finish<1, RECORD>(S, ks, P, Y, oy, tl, q, c, lsum);
             te[3] += tick<DBG>() - e1;
             const bool anyx = *reinterpret_cast<volatile int*>(&S->anyT[0]) != 0, anyy = !ydead && *reinterpret_cast<volatile int*>(&S->anyT[1]) != 0;
             if (!anyx && !anyy) break;
@@ -567,7 +598,12 @@ __global__ void __launch_bounds__(NT2, 1) solve_tc2_kernel(const unsigned char* 
                 tm[7] += 1;
             }
         }
-        if (DBG && P.resid && blockIdx.x == 0 && threadIdx.x == 0) {
+        if (RECORD) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(FULL, lsum, o);
+            if (lane == 0) atomicAdd(P.loss_sum, lsum);
+        }
+        if (DBG && !RECORD && P.resid && blockIdx.x == 0 && threadIdx.x == 0) {
             long long* dbg = reinterpret_cast<long long*>(P.resid);
 #pragma unroll
             for (int i = 0; i < 8; ++i) dbg[i] = tm[i];
