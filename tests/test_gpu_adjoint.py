@@ -163,3 +163,26 @@ def test_one_column_per_cta_kernel_agrees_with_batch_kernel(nfc, gpu_ok, monkeyp
     assert abs(na - nb) <= 0.05 * na
     if not np.isnan(a["loss"]):
         assert abs(a["loss"] - b["loss"]) <= 1e-6 * abs(a["loss"])
+
+
+def test_record_pass_kernels_agree(nfc, gpu_ok, monkeypatch):
+    """The forward (RECORD) pass of loss_grad exists three times: FP32 SIMT (`NFC_TC_RECORD=0`), the one-tile and the two-tile tensor-core
+    kernel.  The two tensor-core kernels are arithmetically identical (same tape, same residuals: loss equal to the last bits of the
+    double sum, gradients to rounding of the atomics); the SIMT pass differs by FP32-faithful rounding only."""
+    out = {}
+    for tag, env in (("simt", {"NFC_TC_RECORD": "0"}), ("tc1", {"NFC_TC_RECORD": "1", "NFC_TC_TILES": "1"}), ("tc2", {"NFC_TC_RECORD": "1", "NFC_TC_TILES": "2"})):
+        for k in ("NFC_TC_RECORD", "NFC_TC_TILES"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        d, cw, layers, theta, sv, colp, Ttrue, h = _setup(nfc, scale=1e-5, K=2.0, B=300)
+        r = h.loss_grad(d["T0"], colp, d["glob"], Ttrue)
+        out[tag] = (r, h.counters())
+    (a, ca), (b, cb), (c, cc) = out["simt"], out["tc1"], out["tc2"]
+    for r in (a, b, c):
+        assert (r["status"] == 0).all()
+    assert cb["steps_accepted"] == cc["steps_accepted"] and cb["steps_rejected"] == cc["steps_rejected"]
+    assert abs(b["loss"] - c["loss"]) <= 1e-12 * abs(b["loss"])
+    assert _rel(c["grad"], b["grad"]) < 1e-5
+    assert abs(a["loss"] - b["loss"]) <= 2e-4 * abs(a["loss"])       # small residuals of a nearly fitted model: the loss itself cancels
+    assert _rel(b["grad"], a["grad"]) < 1e-3
