@@ -530,16 +530,21 @@ __device__ __forceinline__ void mma_warp_loop(TcShared* S, uint32_t smem_img, in
             if (*reinterpret_cast<volatile int*>(&S->stop)) break;
             fence_after_sync();
             const long long c1 = clock64();
-            if (layer == 0) SP::template issue<0, 0>(S->tmem_base, smem_img, S->nprod);
-            else if (layer == 1) SP::template issue<1, 0>(S->tmem_base, smem_img, S->nprod);
-            else SP::template issue<2, 0>(S->tmem_base, smem_img, S->nprod);
+            // The operand addresses must be re-derived inside the loop (an add on a uniform register per MMA): as loop invariants the
+            // compiler hoists them all and, with the 32 registers this warp keeps, spills them -- a local-memory load in front of the MMA.
+            uint32_t tb = S->tmem_base, img = smem_img;
+            asm volatile("" : "+r"(tb), "+r"(img));
+            if (layer == 0) SP::template issue<0, 0>(tb, img, S->nprod);
+            else if (layer == 1) SP::template issue<1, 0>(tb, img, S->nprod);
+            else SP::template issue<2, 0>(tb, img, S->nprod);
             const long long c2 = clock64();
             mbar_wait(&S->bar_a1, pa); pa ^= 1;
             fence_after_sync();
             const long long c3 = clock64();
-            if (layer == 0) SP::template issue<0, 1>(S->tmem_base, smem_img, S->nprod);
-            else if (layer == 1) SP::template issue<1, 1>(S->tmem_base, smem_img, S->nprod);
-            else SP::template issue<2, 1>(S->tmem_base, smem_img, S->nprod);
+            asm volatile("" : "+r"(tb), "+r"(img));
+            if (layer == 0) SP::template issue<0, 1>(tb, img, S->nprod);
+            else if (layer == 1) SP::template issue<1, 1>(tb, img, S->nprod);
+            else SP::template issue<2, 1>(tb, img, S->nprod);
             mma_commit(&S->bar_d);
             const long long c4 = clock64();
             tw0[layer] += c1 - c0; ti0[layer] += c2 - c1; tw1[layer] += c3 - c2; ti1[layer] += c4 - c3; n[layer] += 1; c0 = c4;

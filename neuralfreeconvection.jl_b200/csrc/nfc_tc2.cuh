@@ -113,14 +113,16 @@ __device__ __forceinline__ void mma_warp_loop2(Shared2* S, uint32_t smem_img, in
             // The operand addresses are re-derived from a base that is re-read in every iteration: as loop invariants the compiler
             // hoisted all 184 of them out of the loop and, with the 32 registers this warp keeps, spilled them -- one local-memory
             // load in front of every MMA made the issue slower than the tensor pipe.
-            uint32_t tb = *reinterpret_cast<volatile uint32_t*>(&S->tmem_base);
-            issue_tile_layer<0>(layer, tb, smem_img);
+            uint32_t tb = *reinterpret_cast<volatile uint32_t*>(&S->tmem_base), img = smem_img;
+            asm volatile("" : "+r"(img));
+            issue_tile_layer<0>(layer, tb, img);
             mma_commit(&S->bar_d[0]);
             if (!*reinterpret_cast<volatile int*>(&S->ydead)) {       // set before the arrival that starts a step, never cleared
                 mbar_wait(&S->bar_a[1], pa1); pa1 ^= 1;
                 fence_after_sync();
                 tb = *reinterpret_cast<volatile uint32_t*>(&S->tmem_base);
-                issue_tile_layer<1>(layer, tb, smem_img);
+                asm volatile("" : "+r"(img));
+                issue_tile_layer<1>(layer, tb, img);
                 mma_commit(&S->bar_d[1]);
             }
             layer = layer == 2 ? 0 : layer + 1;
