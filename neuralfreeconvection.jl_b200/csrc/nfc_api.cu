@@ -19,6 +19,7 @@
 #include "nfc_embedded.cuh"
 #include "nfc_rkc.cuh"
 #include "nfc_rkc_tc.cuh"
+#include "nfc_embedded_tc.cuh"
 
 using namespace nfc;
 
@@ -104,6 +105,19 @@ int do_embedded(nfc_handle* h, EmbeddedParams& P, cudaStream_t st) {
     constexpr int NW = Launch<N>::NW;
     NFC_CUDA(h, cudaFuncSetAttribute(embedded_kernel<N, WS, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<N>(NW)));
     P.wpack = h->d_wpack.p;
+    if (h->use_tc && h->arch == ARCH_DEFAULT) {       // default Chain: Chain evaluations on the tensor cores (nfc_embedded_tc.cuh)
+        const int gridt = (int)std::min<long long>(h->num_sms, (P.B + tc::TILE - 1) / tc::TILE);
+        if (h->tc_fp16) {
+            NFC_CUDA(h, cudaFuncSetAttribute(tc::embedded_tc_kernel<tc::SplitFP16x2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::emb_tc_smem_bytes<tc::SplitFP16x2>()));
+            tc::embedded_tc_kernel<tc::SplitFP16x2><<<gridt, tc::NTHREADS, tc::emb_tc_smem_bytes<tc::SplitFP16x2>(), st>>>(h->d_wimg.p, P);
+        } else {
+            NFC_CUDA(h, cudaFuncSetAttribute(tc::embedded_tc_kernel<tc::SplitBF16x3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::emb_tc_smem_bytes<tc::SplitBF16x3>()));
+            tc::embedded_tc_kernel<tc::SplitBF16x3><<<gridt, tc::NTHREADS, tc::emb_tc_smem_bytes<tc::SplitBF16x3>(), st>>>(h->d_wimg.p, P);
+        }
+        NFC_CUDA(h, cudaGetLastError());
+        h->last_launches += 1;
+        return 0;
+    }
     const long long groups = (P.B + CPW - 1) / CPW;
     const int grid = (int)std::min<long long>(h->num_sms, (groups + NW - 1) / NW);
     embedded_kernel<N, WS, NW><<<grid, NW * 32, smem_bytes<N>(NW), st>>>(P);

@@ -38,13 +38,16 @@ __device__ __forceinline__ float pcr32(float a, float b, float c, float d, int l
         float ap = __shfl_down_sync(FULL, a, s), bp = __shfl_down_sync(FULL, b, s), cp = __shfl_down_sync(FULL, c, s), dp = __shfl_down_sync(FULL, d, s);
         if (lane < s) { am = 0.f; bm = 1.f; cm = 0.f; dm = 0.f; }
         if (lane + s >= NZ) { ap = 0.f; bp = 1.f; cp = 0.f; dp = 0.f; }
-        const float al = -a / bm, ga = -c / bp;
+        // fast division (reciprocal + multiply, 2 ulp): the diagonals are 1 + a (kappa_i + kappa_{i+1}) >= 1, far from the range limits,
+        // and the off-diagonals are zero wherever the column is stable -- the IEEE sequence took its slow path for every zero numerator
+        // and the solve cost three times the Chain evaluation
+        const float al = -__fdividef(a, bm), ga = -__fdividef(c, bp);
         b = b + al * cm + ga * ap;
         d = d + al * dm + ga * dp;
         a = al * am;
         c = ga * cp;
     }
-    return d / b;
+    return __fdividef(d, b);
 }
 
 template <class N, bool WS, int NW>

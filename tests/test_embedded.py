@@ -78,3 +78,25 @@ def test_gpu_embedded_api_mirror(nfc, gpu_ok):
         p *= 1e-5
     T2 = nfc.oceananigans_convective_adjustment_with_neural_network(ds, NN, Ts, wTs, save_every=9)
     assert T2.shape == (32, 129) and np.isfinite(T2).all()
+
+
+@pytest.mark.gpu
+def test_gpu_embedded_tensor_core_matches_simt(nfc, gpu_ok, monkeypatch):
+    """Default Chain: the Chain of the embedded path runs on the tensor cores (nfc_embedded_tc.cuh); the explicit step and the
+    tridiagonal solve are the FP32 SIMT kernel's code, so the two paths differ only by the FP32-faithful rounding of the network
+    output.  Ragged tile (300 columns = 2 full tiles + 44), several saves."""
+    B = 300
+    T0, Q, scal = _columns(nfc, B, seed=9)
+    cw, layers = O.chain_spec()
+    theta = O.glorot_theta(cw, layers, 1, 0.3)
+    K = scal[3] / scal[1] * 691200.0 / 256.0 * 10.0
+    out = {}
+    for tc in ("0", "1"):
+        monkeypatch.setenv("NFC_TC", tc)
+        h = nfc.Handle(cw, layers, 1, np.float32([0, 1]))
+        h.set_weights(theta)
+        out[tc] = h.embedded_solve(T0, Q, scal, 256.0, 600.0, K, 1e-3, 288, save_every=24)
+    a, b = out["0"], out["1"]
+    assert a.shape == b.shape == (B, 13, 32) and np.isfinite(b).all()
+    np.testing.assert_array_equal(b[:, 0], T0)
+    assert rel_l2(b[:, 1:] - T0[:, None], a[:, 1:] - T0[:, None]).max() < 1e-4
