@@ -264,7 +264,8 @@ __device__ __forceinline__ void chain_eval(TcShared* S, const float* sbias, cons
     // ---- hidden layers: D -> bias, relu, split -> A operand of the next layer (units 32q .. 32q+31 -> cells 16q .. 16q+15)
 #pragma unroll 1
     for (int l = 0; l < 2; ++l) {
-        { const long long a = clock64(); mbar_wait(&S->bar_d, pd); pd ^= 1; if (twd) twd[l] += clock64() - a; }
+        if (twd) { const long long a = clock64(); mbar_wait(&S->bar_d, pd); twd[l] += clock64() - a; } else mbar_wait(&S->bar_d, pd);
+        pd ^= 1;
         fence_after_sync();
         const float* b = sbias + 128 * l + 32 * q;
         // the whole D slice of this thread first: the next layer's MMAs start overwriting D as soon as the first halves are published
@@ -292,7 +293,8 @@ __device__ __forceinline__ void chain_eval(TcShared* S, const float* sbias, cons
         }
     }
     // ---- output layer: NN[8q-1 .. 8q+7]
-    { const long long a = clock64(); mbar_wait(&S->bar_d, pd); pd ^= 1; if (twd) twd[2] += clock64() - a; }
+    if (twd) { const long long a = clock64(); mbar_wait(&S->bar_d, pd); twd[2] += clock64() - a; } else mbar_wait(&S->bar_d, pd);
+    pd ^= 1;
     fence_after_sync();
     {
         uint32_t ra[8], rb[8], rc[8], a0 = 0, b0 = 0, c0 = 0;
@@ -433,7 +435,8 @@ __device__ __forceinline__ void chain_eval16(TcShared* S, const float* sb, const
     }
 #pragma unroll 1
     for (int l = 0; l < 2; ++l) {
-        { const long long a = clock64(); mbar_wait(&S->bar_d, pd); pd ^= 1; if (twd) twd[l] += clock64() - a; }
+        if (twd) { const long long a = clock64(); mbar_wait(&S->bar_d, pd); twd[l] += clock64() - a; } else mbar_wait(&S->bar_d, pd);
+        pd ^= 1;
         fence_after_sync();
         const float* b = sb + 128 * l + 32 * q;
         const float cl = sb[288 + l];
@@ -459,7 +462,8 @@ __device__ __forceinline__ void chain_eval16(TcShared* S, const float* sb, const
             mbar_arrive(ch == 0 ? &S->bar_a : &S->bar_a1);
         }
     }
-    { const long long a = clock64(); mbar_wait(&S->bar_d, pd); pd ^= 1; if (twd) twd[2] += clock64() - a; }
+    if (twd) { const long long a = clock64(); mbar_wait(&S->bar_d, pd); twd[2] += clock64() - a; } else mbar_wait(&S->bar_d, pd);
+    pd ^= 1;
     fence_after_sync();
     {
         uint32_t ra[8], rb[8], a0 = 0, b0 = 0;
@@ -689,6 +693,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
         reg_inc<REGS_COL>();
         const int wq = warp & 3, q = warp >> 2, c = 32 * wq + lane;
         long long twd[4] = {0, 0, 0, 0};
+        long long* const twdp = (!RECORD && P.resid) ? twd : nullptr;      // phase timers only with NFC_TC_DEBUG=1
         const long long tstart = clock64();
         const uint32_t tl = S.tmem_base + ((uint32_t)(32 * wq) << 16);
         int pd = 0, xb = 0, pb = 0;
@@ -794,7 +799,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
                 S.xch[xb][c][q][0] = y[0];
                 S.xch[xb][c][q][1] = y[7];
                 float nn[9], f[8];
-                SP::eval(&S, sbias, y, nn, pd, wq, q, twd, false);
+                SP::eval(&S, sbias, y, nn, pd, wq, q, twdp, false);
                 const float ylo = q > 0 ? S.xch[xb][c][q - 1][1] : 0.f, yhi = q < 3 ? S.xch[xb][c][q + 1][0] : 0.f;
                 faces_to_f(y, ylo, yhi, nn, bot, top, kk, P.pref, q, f);
                 tmem_st8f(kaddr(tl, s + 2, q), f);
@@ -844,8 +849,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
                 if (!isfinite(ee)) { status = ST_NAN; accept = false; dtnew = hs; }
                 else if (P.fixed_dt > 0.f) { accept = true; dtnew = P.fixed_dt; }
                 else {
-                    const float q11 = powf(ee, 0.14f);
-                    float qq = q11 / powf(qold, 0.08f);
+                    // PI controller exponents: the fast power (2 ulp) is ample for the trajectory, whose accept test is on ee itself; the RECORD
+                    // pass keeps powf so that its step sequence stays the CPU twin's (gradients of two step sequences differ by ~1e-3)
+                    const float q11 = RECORD ? powf(ee, 0.14f) : __powf(ee, 0.14f);
+                    float qq = q11 / (RECORD ? powf(qold, 0.08f) : __powf(qold, 0.08f));
                     qq = fmaxf(0.1f, fminf(5.0f, qq / 0.9f));
                     accept = ee <= 1.0f;
                     dtnew = accept ? hs / qq : hs / fminf(5.0f, q11 / 0.9f);

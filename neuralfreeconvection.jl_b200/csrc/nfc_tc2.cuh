@@ -306,8 +306,8 @@ __device__ __forceinline__ void step_control(Shared2* S, const SolveParams& P, i
         if (!isfinite(ee)) { status = ST_NAN; accept = false; dtnew = hs; }
         else if (P.fixed_dt > 0.f) { accept = true; dtnew = P.fixed_dt; }
         else {
-            const float q11 = powf(ee, 0.14f);
-            float qq = q11 / powf(C.qold[c], 0.08f);
+            const float q11 = RECORD ? powf(ee, 0.14f) : __powf(ee, 0.14f);      // as in tc::solve_tc_kernel
+            float qq = q11 / (RECORD ? powf(C.qold[c], 0.08f) : __powf(C.qold[c], 0.08f));
             qq = fmaxf(0.1f, fminf(5.0f, qq / 0.9f));
             accept = ee <= 1.0f;
             dtnew = accept ? hs / qq : hs / fminf(5.0f, q11 / 0.9f);
