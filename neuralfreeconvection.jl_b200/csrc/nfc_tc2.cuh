@@ -203,7 +203,7 @@ __device__ __forceinline__ void stage_input(Shared2* S, unsigned char* ks, const
 }
 
 // ---- E1 / E2: hidden-layer epilogue, in place ---------------------------------------------------------------------------------
-template <int T, bool DBG>
+template <int T, bool DBG, bool FOLD>
 __device__ __forceinline__ void hidden_epilogue(Shared2* S, const float* sb, int l, int& pd, uint32_t tl, int q, long long& tw) {
     { const long long a = tick<DBG>(); mbar_wait(&S->bar_d[T], pd); pd ^= 1; tw += tick<DBG>() - a; }
     fence_after_sync();
@@ -220,10 +220,15 @@ __device__ __forceinline__ void hidden_epilogue(Shared2* S, const float* sb, int
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const float4 bb = *reinterpret_cast<const float4*>(b + 16 * ch + 4 * i);
-            const float v0 = fmaxf(fmaf(__uint_as_float(r[16 * ch + 4 * i]), cl, bb.x), 0.f), v1 = fmaxf(fmaf(__uint_as_float(r[16 * ch + 4 * i + 1]), cl, bb.y), 0.f);
-            const float v2 = fmaxf(fmaf(__uint_as_float(r[16 * ch + 4 * i + 2]), cl, bb.z), 0.f), v3 = fmaxf(fmaf(__uint_as_float(r[16 * ch + 4 * i + 3]), cl, bb.w), 0.f);
-            split2h(v0, v1, ph[2 * i], pl[2 * i]);
-            split2h(v2, v3, ph[2 * i + 1], pl[2 * i + 1]);
+            const float v0 = fmaf(__uint_as_float(r[16 * ch + 4 * i]), cl, bb.x), v1 = fmaf(__uint_as_float(r[16 * ch + 4 * i + 1]), cl, bb.y);
+            const float v2 = fmaf(__uint_as_float(r[16 * ch + 4 * i + 2]), cl, bb.z), v3 = fmaf(__uint_as_float(r[16 * ch + 4 * i + 3]), cl, bb.w);
+            if (FOLD) {                                              // relu folded into the conversions (tc::split2h_relu); not in the RECORD pass
+                split2h_relu(v0, v1, ph[2 * i], pl[2 * i]);
+                split2h_relu(v2, v3, ph[2 * i + 1], pl[2 * i + 1]);
+            } else {
+                split2h(fmaxf(v0, 0.f), fmaxf(v1, 0.f), ph[2 * i], pl[2 * i]);
+                split2h(fmaxf(v2, 0.f), fmaxf(v3, 0.f), ph[2 * i + 1], pl[2 * i + 1]);
+            }
         }
         tmem_st8(d + 8 * ch, ph);              // units 32q + 16ch .. : k-step 2q + ch of the next layer, hi
         tmem_st8(d + 16 + 8 * ch, pl);         //                                                        lo
@@ -583,8 +588,8 @@ __global__ void __launch_bounds__(NT2, 1) solve_tc2_kernel(const unsigned char* 
             for (int s = 0; s < 6; ++s) {
 #pragma unroll 1
                 for (int l = 0; l < 2; ++l) {
-                    hidden_epilogue<0, DBG>(S, sb, l, pdx, tl, q, tm[4 + l]);
-                    if (!ydead) hidden_epilogue<1, DBG>(S, sb, l, pdy, tl, q, tm[4 + l]);
+                    hidden_epilogue<0, DBG, !RECORD>(S, sb, l, pdx, tl, q, tm[4 + l]);
+                    if (!ydead) hidden_epilogue<1, DBG, !RECORD>(S, sb, l, pdy, tl, q, tm[4 + l]);
                 }
                 c1 = tick<DBG>(); tm[2] += c1 - c0; c0 = c1;
                 output_epilogue<0, DBG>(S, ks, sb, X, s, pdx, tl, q, c, P.pref, tm[6]);
