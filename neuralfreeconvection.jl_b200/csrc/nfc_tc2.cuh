@@ -16,9 +16,11 @@
 //     one otherwise; with the strict X/Y alternation THREE regions serve both tiles (tile T, layer l: A = R[(l + 2T) % 3],
 //     D = R[(l + 1 + 2T) % 3]; the region an MMA frees is the next MMA's accumulator -- the tensor pipe executes in issue order);
 //   * of the ten stored stage vectors (k2..k6 of two tiles) four live in the remaining 128 tensor-memory columns (k2, k3) and
-//     six in shared memory (k4..k6, 96 KB); the per-column scalars live in shared memory, owned by the quarter-0 thread.
-// Arithmetic is the one of solve_tc_kernel<SplitFP16x2>, operation for operation (same MMA order, same combination order), so the
-// two kernels agree bit for bit -- tests/test_gpu_forward.py compares them.
+//     six in shared memory (k4..k6, 96 KB); the per-column scalars live in shared memory, owned by one thread per column (tile X: the
+//     quarter-0 thread, tile Y: the quarter-1 thread, so the two tiles' controllers run side by side in different warps).
+// Arithmetic is the one of solve_tc_kernel<SplitFP16x2, RECORD>, operation for operation (same MMA order, same combination order, same
+// split and controller variants per mode), so the two kernels agree bit for bit -- tests/test_gpu_forward.py and
+// tests/test_gpu_adjoint.py::test_record_pass_kernels_agree compare them.
 #pragma once
 #include "nfc_tc.cuh"
 
