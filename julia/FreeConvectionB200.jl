@@ -6,7 +6,8 @@
 module FreeConvectionB200
 
 using Flux
-export solve_nde_history, FreeConvectionNDE, ConvectiveAdjustmentNDE, solve_nde, nde_loss_and_gradient
+export solve_nde_history, FreeConvectionNDE, ConvectiveAdjustmentNDE, solve_nde, nde_loss_and_gradient, diagnose_flux,
+       oceananigans_convective_adjustment_with_neural_network
 
 const LIB = get(ENV, "LIBNFC_B200", joinpath(@__DIR__, "..", "neuralfreeconvection.jl_b200", "libnfc_b200.so"))
 const NFC_MAX_LAYERS = 8
@@ -115,6 +116,40 @@ function solve_nde_history(nde::NDEHandle, thetas::Matrix{Float32}, T₀::Matrix
                nde.ptr, thetas, E, T0e, colpe, glob, out, na, nr, st, S)
     check(nde.ptr, rc, "nfc_solve_ensemble")
     any(!=(0), st) && @warn "solver status != 0 for $(count(!=(0), st)) (simulation, epoch) pairs"
+    return out
+end
+
+"""
+The flux diagnosis loop of solve_nde(ds, ...) (src/solve.jl:32-48) for a solution `T` (Nz x n_save x B, scaled units):
+wT[:, n] = [bottom; NN(T[:, n]); top] - min(0, K_CA dT/dz), returned as (Nz+1) x n_save x B (scaled units; apply inv(wT_scaling)).
+"""
+function diagnose_flux(nde::NDEHandle, NN, T::Array{Float32,3}, nde_params)
+    θ, _ = Flux.destructure(NN)
+    check(nde.ptr, ccall((:nfc_set_weights, LIB), Int32, (Ptr{Cvoid}, Ptr{Float32}, Int64), nde.ptr, θ, length(θ)), "nfc_set_weights")
+    colp, _ = split_params(nde, nde_params); B = size(T, 3)
+    wT = Array{Float32}(undef, nde.Nz + 1, size(T, 2), B)
+    rc = ccall((:nfc_diagnose_flux, LIB), Int32, (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Int64), nde.ptr, T, colp, wT, B)
+    check(nde.ptr, rc, "nfc_diagnose_flux")
+    return wT
+end
+
+"""
+oceananigans_convective_adjustment_with_neural_network (src/oceananigans_nn.jl:158-282) for B columns at once: explicit neural-network flux
+step + implicit convective adjustment per fixed step `Δt`.  `T₀` is Nz x B (physical temperatures), `heat_flux` the B surface temperature
+fluxes; `K` is non-dimensionalised as the reference does (:195).  Returns Nz x (n_steps ÷ save_every + 1) x B in physical units.
+"""
+function oceananigans_convective_adjustment_with_neural_network(nde::NDEHandle, NN, T₀::Matrix{Float32}, heat_flux::Vector{Float32},
+                                                                T_scaling, wT_scaling; Lz, stop_time, Δt=600.0, K=10.0, ∂T∂z_deep=0.0, save_every=1)
+    θ, _ = Flux.destructure(NN)
+    check(nde.ptr, ccall((:nfc_set_weights, LIB), Int32, (Ptr{Cvoid}, Ptr{Float32}, Int64), nde.ptr, θ, length(θ)), "nfc_set_weights")
+    B = size(T₀, 2); n_steps = round(Int, stop_time / Δt)
+    Knd = wT_scaling.σ / T_scaling.σ * stop_time / Lz * K
+    scal = Float32[T_scaling.μ, T_scaling.σ, wT_scaling.μ, wT_scaling.σ]
+    out = Array{Float32}(undef, nde.Nz, n_steps ÷ save_every + 1, B)
+    rc = ccall((:nfc_embedded_solve, LIB), Int32,
+               (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Float32, Float32, Float32, Float32, Int32, Int32, Ptr{Float32}, Int64),
+               nde.ptr, T₀, heat_flux, scal, Lz, Δt, Knd, ∂T∂z_deep, n_steps, save_every, out, B)
+    check(nde.ptr, rc, "nfc_embedded_solve")
     return out
 end
 
