@@ -1,13 +1,14 @@
 // nfc_embedded_tc.cuh -- the embedded fixed-step path (nfc_embedded.cuh) with the Chain on the tensor cores.
 //
-// One CTA owns a tile of 128 columns for all n_steps.  Per step the 512 column threads play two roles:
-//   role A (nfc_tc.cuh layout: thread = column c, quarter q): the Chain evaluation of the tile -- tc::SplitFP16x2 / SplitBF16x3 ::eval,
-//           the tcgen05 MMAs issued by the MMA warp, exactly as in rhs_tc_kernel;
-//   role B (nfc_embedded.cuh layout: warp w owns columns 8w..8w+7, lane = level): the explicit flux step and the implicit
-//           convective adjustment -- the per-level code and the 32-unknown parallel-cyclic-reduction solve of embedded_kernel, verbatim.
-// The state lives in role B's registers; it crosses to role A (scaled temperatures) and back (network output) through two
-// [128][33] shared-memory arrays, one CTA barrier each way.  Everything except the network output (FP32-faithful to 1e-7) is
-// therefore bit-identical to the FP32 SIMT kernel.
+// One CTA owns a tile of 128 columns for all n_steps.  The scaled state lives in shared memory, one padded row per column; per step
+//   (A) all 512 column threads (nfc_tc.cuh layout: thread = column c, quarter q) evaluate the Chain of the tile -- tc::SplitFP16x2 /
+//       SplitBF16x3 ::eval, the tcgen05 MMAs issued by the MMA warp, exactly as in rhs_tc_kernel -- and leave the network output in a
+//       second [128][33] array;
+//   (B) the quarter-0 thread of every column (4 warps, one per SM sub-partition) does the explicit flux step and the implicit
+//       convective adjustment of its column with the Thomas algorithm on 32 unknowns in registers.  (A first version transposed to
+//       the SIMT kernel's lane = level layout and ran its parallel cyclic reduction: 19 K warp-instructions per tile and step against
+//       1.8 K for the sequential sweeps, and as long as the Chain evaluation itself.)
+// Coefficients follow convective_adjustment! (src/oceananigans_nn.jl:3-30) as in nfc_embedded.cuh; oracle: nde_oracle.py:embedded_solve.
 #pragma once
 #include "nfc_embedded.cuh"
 #include "nfc_tc.cuh"
@@ -40,21 +41,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) embedded_tc_kernel(const unsigned
         const float fscale = P.dt * inv_dz * inv_sT, gbot = P.bottom_gradient * inv_sT * P.dz;
         int pd = 0;
         for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            // role B state: columns tile * 128 + 8 warp + c, lane = level
-            float T[CPW], Q[CPW];
+            const long long col = tile * TILE + cA;
+            const bool own = q == 0, live = own && col < P.B;      // role B: the quarter-0 thread owns column cA
+            float Q = 0.f;
+            cta_bar();                                             // the previous tile's last reads of sT are done
+            if (own) {
+                float* row = sT + cA * EMB_ROW;
 #pragma unroll
-            for (int c = 0; c < CPW; ++c) {
-                const long long col = tile * TILE + 8 * warp + c;
-                const float t0 = col < P.B ? P.T0[col * NZ + lane] : P.mu_T;
-                T[c] = (t0 - P.mu_T) * inv_sT;
-                Q[c] = col < P.B ? P.heat_flux[col] : 0.f;
-                if (col < P.B) P.Tout[(col * P.n_out) * NZ + lane] = t0;
+                for (int k = 0; k < NZ; ++k) {
+                    const float t0 = live ? P.T0[col * NZ + k] : P.mu_T;
+                    row[k] = (t0 - P.mu_T) * inv_sT;
+                    if (live) P.Tout[(col * P.n_out) * NZ + k] = t0;
+                }
+                Q = live ? P.heat_flux[col] : 0.f;
             }
             for (int step = 1; step <= P.n_steps; ++step) {
-#pragma unroll
-                for (int c = 0; c < CPW; ++c) sT[(8 * warp + c) * EMB_ROW + lane] = T[c];
                 cta_bar();
-                {   // role A: Chain evaluation of the tile
+                {   // (A) Chain evaluation of the tile
                     float y[8], nn[9];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) y[i] = sT[cA * EMB_ROW + 8 * q + i];
@@ -63,31 +66,50 @@ __global__ void __launch_bounds__(NTHREADS, 1) embedded_tc_kernel(const unsigned
                     for (int i = 1; i <= 8; ++i) sN[cA * EMB_ROW + 8 * q + i - 1] = nn[i];     // neuron n = 8q + i - 1 (n = 31 is not used)
                 }
                 cta_bar();
+                if (own) {   // (B) explicit flux step + implicit convective adjustment of column cA
+                    float* row = sT + cA * EMB_ROW;
+                    const float* sY = sN + cA * EMB_ROW;
+                    float t[NZ], cp[NZ];
+                    // faces: F_0 = 0, F_k = sigma_wT NN[k-1] + mu_wT, F_32 = Q
+                    float Flo = 0.f;
 #pragma unroll
-                for (int c = 0; c < CPW; ++c) {
-                    const float* sY = sN + (8 * warp + c) * EMB_ROW;
-                    // faces: F_0 = 0, F_k = sigma_wT NN[k-1] + mu_wT, F_32 = Q   (nfc_embedded.cuh, same operations)
-                    const float Flo = lane > 0 ? fmaf(P.sigma_wT, sY[lane - 1], P.mu_wT) : 0.f;
-                    float Fhi = __shfl_down_sync(FULL, Flo, 1);
-                    if (lane == NZ - 1) Fhi = Q[c];
-                    float t = T[c] - fscale * (Fhi - Flo);
-                    const float tlo = __shfl_up_sync(FULL, t, 1), thi = __shfl_down_sync(FULL, t, 1);
-                    const float glo = lane > 0 ? (t - tlo) : gbot;
-                    const float ghi = lane < NZ - 1 ? (thi - t) : 0.f;
-                    const float kap = (glo + ghi < 0.f) ? P.K : 0.f;
-                    float kap_hi = __shfl_down_sync(FULL, kap, 1);
-                    if (lane == NZ - 1) kap_hi = 0.f;
-                    const float ld = lane > 0 ? -a * kap : 0.f;
-                    const float ud = lane < NZ - 1 ? -a * kap_hi : 0.f;
-                    const float dd = 1.f + a * (kap + kap_hi);
-                    T[c] = pcr32(ld, dd, ud, t, lane);
-                }
-                if (step % P.save_every == 0) {
-                    const int so = step / P.save_every;
+                    for (int k = 0; k < NZ; ++k) {
+                        const float Fhi = k < NZ - 1 ? fmaf(P.sigma_wT, sY[k], P.mu_wT) : Q;
+                        t[k] = row[k] - fscale * (Fhi - Flo);
+                        Flo = Fhi;
+                    }
+                    // kappa_k = K where the centre gradient (mean of the face gradients; bottom: gradient BC, top: zero) is negative
+                    float kap_lo = ((gbot) + (t[1] - t[0]) < 0.f) ? P.K : 0.f;      // kappa_0
+                    float dprev = 0.f, cprev = 0.f;
 #pragma unroll
-                    for (int c = 0; c < CPW; ++c) {
-                        const long long col = tile * TILE + 8 * warp + c;
-                        if (col < P.B) P.Tout[(col * P.n_out + so) * NZ + lane] = fmaf(P.sigma_T, T[c], P.mu_T);
+                    for (int k = 0; k < NZ; ++k) {
+                        float kap_hi = 0.f;                                          // kappa_{k+1}
+                        if (k < NZ - 1) {
+                            const float glo = t[k + 1] - t[k];
+                            const float ghi = k + 1 < NZ - 1 ? (t[k + 2] - t[k + 1]) : 0.f;
+                            kap_hi = (glo + ghi < 0.f) ? P.K : 0.f;
+                        }
+                        const float ld = k > 0 ? -a * kap_lo : 0.f;
+                        const float ud = k < NZ - 1 ? -a * kap_hi : 0.f;
+                        const float dd = 1.f + a * (kap_lo + kap_hi);
+                        // Thomas forward sweep (dd >= 1, off-diagonals <= 0: diagonally dominant, no pivoting)
+                        const float m = fmaf(-ld, cprev, dd);
+                        const float im = __fdividef(1.f, m);
+                        cprev = ud * im;
+                        dprev = fmaf(-ld, dprev, t[k]) * im;
+                        cp[k] = cprev; t[k] = dprev;
+                        kap_lo = kap_hi;
+                    }
+#pragma unroll
+                    for (int k = NZ - 2; k >= 0; --k) t[k] = fmaf(-cp[k], t[k + 1], t[k]);
+#pragma unroll
+                    for (int k = 0; k < NZ; ++k) row[k] = t[k];
+                    if (live && step % P.save_every == 0) {
+                        float* o = P.Tout + (col * P.n_out + step / P.save_every) * NZ;
+#pragma unroll
+                        for (int k = 0; k < NZ; k += 4)
+                            *reinterpret_cast<float4*>(o + k) = make_float4(fmaf(P.sigma_T, t[k], P.mu_T), fmaf(P.sigma_T, t[k + 1], P.mu_T),
+                                                                            fmaf(P.sigma_T, t[k + 2], P.mu_T), fmaf(P.sigma_T, t[k + 3], P.mu_T));
                     }
                 }
             }

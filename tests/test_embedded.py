@@ -82,9 +82,11 @@ def test_gpu_embedded_api_mirror(nfc, gpu_ok):
 
 @pytest.mark.gpu
 def test_gpu_embedded_tensor_core_matches_simt(nfc, gpu_ok, monkeypatch):
-    """Default Chain: the Chain of the embedded path runs on the tensor cores (nfc_embedded_tc.cuh); the explicit step and the
-    tridiagonal solve are the FP32 SIMT kernel's code, so the two paths differ only by the FP32-faithful rounding of the network
-    output.  Ragged tile (300 columns = 2 full tiles + 44), several saves."""
+    """Default Chain: the Chain of the embedded path runs on the tensor cores (nfc_embedded_tc.cuh) and the tridiagonal systems are
+    solved by a per-column Thomas sweep; the FP32 SIMT kernel uses parallel cyclic reduction.  Two float32 tridiagonal algorithms
+    and the FP32-faithful rounding of the network output over 288 steps (with the adjustment's active set flipping at neutral
+    stratification): a few 1e-4 of the profile CHANGE; both are within 2e-3 of the float64 oracle (test above).  Ragged tile
+    (300 columns = 2 full tiles + 44), several saves."""
     B = 300
     T0, Q, scal = _columns(nfc, B, seed=9)
     cw, layers = O.chain_spec()
@@ -99,4 +101,4 @@ def test_gpu_embedded_tensor_core_matches_simt(nfc, gpu_ok, monkeypatch):
     a, b = out["0"], out["1"]
     assert a.shape == b.shape == (B, 13, 32) and np.isfinite(b).all()
     np.testing.assert_array_equal(b[:, 0], T0)
-    assert rel_l2(b[:, 1:] - T0[:, None], a[:, 1:] - T0[:, None]).max() < 1e-4
+    assert rel_l2(b[:, 1:] - T0[:, None], a[:, 1:] - T0[:, None]).max() < 5e-4
