@@ -71,7 +71,7 @@ struct AdjSlots {
 };
 enum : int { AFL_ACCEPT = 1, AFL_LAST = 2, AFL_DONE = 4, AFL_JUMP = 8 };
 
-__constant__ float c_adj_a[7][6] = {
+static __constant__ float c_adj_a[7][6] = {
     {0.f, 0.f, 0.f, 0.f, 0.f, 0.f},
     {NFC_A21, 0.f, 0.f, 0.f, 0.f, 0.f},
     {NFC_A31, NFC_A32, 0.f, 0.f, 0.f, 0.f},
@@ -79,8 +79,8 @@ __constant__ float c_adj_a[7][6] = {
     {NFC_A51, NFC_A52, NFC_A53, NFC_A54, 0.f, 0.f},
     {NFC_A61, NFC_A62, NFC_A63, NFC_A64, NFC_A65, 0.f},
     {NFC_B1, NFC_B2, NFC_B3, NFC_B4, NFC_B5, NFC_B6}};
-__constant__ float c_adj_c[7] = {0.f, 0.161f, 0.327f, 0.9f, 0.9800255409045097f, 1.f, 1.f};
-__constant__ float c_adj_b[7] = {NFC_B1, NFC_B2, NFC_B3, NFC_B4, NFC_B5, NFC_B6, 0.f};
+static __constant__ float c_adj_c[7] = {0.f, 0.161f, 0.327f, 0.9f, 0.9800255409045097f, 1.f, 1.f};
+static __constant__ float c_adj_b[7] = {NFC_B1, NFC_B2, NFC_B3, NFC_B4, NFC_B5, NFC_B6, 0.f};
 
 // ---- transposed products on a warp tile: out[k][c] = mask(k,c) * sum_n W[k][pos(n)] din[n][c], lane owns rows k = lane + 32 i ----
 // hidden layer: W is [K][RS] with columns in packed order (position NPL*fl + j  <->  neuron fl + 32 j)
@@ -579,7 +579,7 @@ __global__ void __launch_bounds__(ADJ_NW * 32, 1) adjoint_kernel(const AdjParams
     }
 }
 
-__global__ void grad_reduce_kernel(const float* __restrict__ gacc, int ncta, int n_params, double scale, float* __restrict__ grad) {
+static __global__ void grad_reduce_kernel(const float* __restrict__ gacc, int ncta, int n_params, double scale, float* __restrict__ grad) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n_params) return;
     double s = 0.0;
@@ -587,7 +587,7 @@ __global__ void grad_reduce_kernel(const float* __restrict__ gacc, int ncta, int
     grad[p] = (float)(scale * s);
 }
 
-__global__ void set_loss_count_kernel(double* loss_sum, double count) { loss_sum[1] = count; }
+static __global__ void set_loss_count_kernel(double* loss_sum, double count) { loss_sum[1] = count; }
 
 // ------------------------------------------------ host side ------------------------------------------------
 template <class N> struct AdjLaunch { static constexpr bool WS = sizeof(float) * (N::P_TOTAL + ADJ_NW * AdjScratch<N>::TOTAL) + 4096 <= 232448; };
@@ -660,7 +660,12 @@ int adjoint_loss_grad(nfc_handle* h, const float* T0, const float* colp, float p
         A.tape_len = h->a_tlen.p; A.status = st_all + off; A.gacc = h->a_gacc.p; A.counters = h->d_counters.p; A.B = nb; A.n_save = n_save;
         A.tape_cap = cap; A.max_iters = h->cfg.max_iters; A.use_kca = h->cfg.nde_type == NFC_NDE_CONVECTIVE_ADJUSTMENT; A.n_params = (int)h->n_params;
         A.pref = pref; A.tf = h->saveat.back(); A.reltol = h->cfg.adjoint_reltol; A.abstol = h->cfg.adjoint_abstol; A.fixed_dt = h->cfg.fixed_dt;
-        if (!adjoint_small_launch<N>(h, A, nb, st)) adjoint_kernel<N, AdjLaunch<N>::WS><<<grid, ADJ_NW * 32, adj_smem_bytes<N>(), st>>>(A);
+        if (!adjoint_small_launch<N>(h, A, nb, st)) {
+            // default Chain, FP16x2 operand scales available: the tensor-core backward kernel (nfc_adjoint_tc.cuh); else FP32 SIMT
+            if (h->arch == ARCH_DEFAULT && h->use_tc && h->tc_fp16 && h->adj_tc && cap <= 32767) {
+                if (int rc = adjoint_tc_launch(h, A, h->atc_scales, nb, st)) return rc;
+            } else adjoint_kernel<N, AdjLaunch<N>::WS><<<grid, ADJ_NW * 32, adj_smem_bytes<N>(), st>>>(A);
+        }
         NFC_CUDA(h, cudaGetLastError());
         h->last_launches += 1;
         first = false;

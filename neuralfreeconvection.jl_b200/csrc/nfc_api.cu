@@ -507,6 +507,8 @@ int32_t nfc_create(const nfc_config* cfg, nfc_handle** out) {
         if (const char* e2 = getenv("NFC_SCHED")) h->use_sched = atoi(e2) != 0;
         if (cudaFuncSetAttribute(adjs::adjoint_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adjs::SMEM_BYTES) != cudaSuccess) { h->err = "cudaFuncSetAttribute(adjoint_small) failed"; return bail(-10); }
         if (const char* e7 = getenv("NFC_ADJ_SMALL_MAX")) h->adj_small_max = atoll(e7);     // 0 disables the one-column-per-CTA adjoint kernel
+        if (adjoint_tc_setup(h)) return bail(-10);
+        if (const char* e9 = getenv("NFC_ADJ_TC")) h->adj_tc = atoi(e9) != 0;               // 0: batch backward pass on the FP32 SIMT kernel
         const char* e = getenv("NFC_TC");          // tensor-core forward path is the default for this Chain; NFC_TC=0 selects the SIMT kernels
         h->use_tc = !(e && atoi(e) == 0);
     }
@@ -552,18 +554,34 @@ int32_t nfc_set_weights(nfc_handle* h, const float* theta, int64_t n) {
         // FP16x2 split: exact power-of-two scales from the weights' max / row-sum norms and the input bound |T_scaled| <= 128
         using N0 = NetDefault;
         auto p2 = [](double bound) { return bound > 0 ? (float)std::exp2(std::floor(std::log2(16384.0 / bound))) : 1.0f; };
-        auto norms = [&](int woff, int K, int Nn, int boff, double& wmax, double& rowsum, double& bmax) {
-            wmax = 0; rowsum = 0; bmax = 0;
+        // rowsum: max over output neurons of sum_k |W[n][k]| (bounds the forward activations); colsum: max over inputs of sum_n |W[n][k]|
+        // (bounds the back-propagated vectors of the tensor-core backward kernel, nfc_adjoint_tc.cuh)
+        auto norms = [&](int woff, int K, int Nn, int boff, double& wmax, double& rowsum, double& bmax, double& colsum) {
+            wmax = 0; rowsum = 0; bmax = 0; colsum = 0;
             std::vector<double> rs(Nn, 0.0);
-            for (int k = 0; k < K; ++k) for (int nn_ = 0; nn_ < Nn; ++nn_) { const double w = std::fabs((double)theta[woff + k * Nn + nn_]); wmax = std::max(wmax, w); rs[nn_] += w; }
+            for (int k = 0; k < K; ++k) {
+                double cs = 0.0;
+                for (int nn_ = 0; nn_ < Nn; ++nn_) { const double w = std::fabs((double)theta[woff + k * Nn + nn_]); wmax = std::max(wmax, w); rs[nn_] += w; cs += w; }
+                colsum = std::max(colsum, cs);
+            }
             for (int nn_ = 0; nn_ < Nn; ++nn_) { rowsum = std::max(rowsum, rs[nn_]); bmax = std::max(bmax, std::fabs((double)theta[boff + nn_])); }
         };
-        double w1, r1, b1, w2, r2, b2, w3, r3, b3;
-        norms(N0::T_W0, 32, 128, N0::T_B0, w1, r1, b1);
-        norms(N0::T_HID, 128, 128, N0::T_HID + 128 * 128, w2, r2, b2);
-        norms(N0::T_WL, 128, 31, N0::T_BL, w3, r3, b3);
+        double w1, r1, b1, k1, w2, r2, b2, k2, w3, r3, b3, k3;
+        norms(N0::T_W0, 32, 128, N0::T_B0, w1, r1, b1, k1);
+        norms(N0::T_HID, 128, 128, N0::T_HID + 128 * 128, w2, r2, b2, k2);
+        norms(N0::T_WL, 128, 31, N0::T_BL, w3, r3, b3, k3);
         const double x0 = 128.0, a1 = r1 * x0 + b1, a2 = r2 * a1 + b2;
         tc::Fp16Scales sc{p2(w1), p2(w2), p2(w3), p2(x0), p2(a1), p2(a2)};
+        {   // backward chain: |d3 * scol| <= 1 per column, |g2| <= colsum(W3), |g1| <= colsum(W2) colsum(W3)
+            const double s_d3 = 16384.0, s_d2 = p2(k3), s_d1 = p2(k2 * k3);
+            atc::AtcScales& a = h->atc_scales;
+            a.s_d3 = (float)s_d3;
+            a.c_g2 = (float)(s_d2 / (s_d3 * (double)sc.s_w3));
+            a.c_g1 = (float)(s_d1 / (s_d2 * (double)sc.s_w2));
+            a.inv_u = (float)(1.0 / (s_d1 * (double)sc.s_w1));
+            a.inv_sd2 = (float)(1.0 / s_d2); a.inv_sd1 = (float)(1.0 / s_d1);
+            a.inv_sa0 = 1.f / sc.s_a0; a.inv_sa1 = 1.f / sc.s_a1; a.inv_sa2 = 1.f / sc.s_a2;
+        }
         const int n = 128 * 32 + 128 * 128 + 32 * 128 + 296;
         tc::pack_weights_tc16_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_theta.p, h->d_wimg.p, sc);
         NFC_CUDA(h, cudaGetLastError());

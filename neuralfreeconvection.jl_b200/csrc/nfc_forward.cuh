@@ -164,7 +164,7 @@ __device__ __forceinline__ void tsit5_power_basis(const float (&ks)[7][CPW], int
 
 // Tsit5 a-matrix rows for stages 2..7 (row 7 == b), zero padded so that one runtime loop serves every stage:
 // the Dense-layer code then exists once in the kernel (instruction-cache resident) instead of six times.
-__constant__ float c_tsit5_a[6][6] = {
+static __constant__ float c_tsit5_a[6][6] = {
     {NFC_A21, 0.f, 0.f, 0.f, 0.f, 0.f},
     {NFC_A31, NFC_A32, 0.f, 0.f, 0.f, 0.f},
     {NFC_A41, NFC_A42, NFC_A43, 0.f, 0.f, 0.f},
@@ -444,11 +444,11 @@ __global__ void __launch_bounds__(NW * 32, 1) solve_ensemble_kernel(const SolveP
 
 // ---- longest-first schedule from the previous call's per-column step counts (counting sort, 1024 buckets, descending) ----
 constexpr int SCHED_BUCKETS = 1024;
-__global__ void sched_hist_kernel(const int* __restrict__ work, int* __restrict__ hist, long long B) {
+static __global__ void sched_hist_kernel(const int* __restrict__ work, int* __restrict__ hist, long long B) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < B) atomicAdd(&hist[min(max(work[i], 0), SCHED_BUCKETS - 1)], 1);
 }
-__global__ void sched_scan_kernel(int* __restrict__ hist) {   // in place: hist[b] = number of columns in longer buckets (b' > b)
+static __global__ void sched_scan_kernel(int* __restrict__ hist) {   // in place: hist[b] = number of columns in longer buckets (b' > b)
     __shared__ int s[SCHED_BUCKETS];
     const int t = threadIdx.x;
     s[t] = hist[SCHED_BUCKETS - 1 - t];
@@ -456,7 +456,7 @@ __global__ void sched_scan_kernel(int* __restrict__ hist) {   // in place: hist[
     for (int off = 1; off < SCHED_BUCKETS; off <<= 1) { const int v = t >= off ? s[t - off] : 0; __syncthreads(); s[t] += v; __syncthreads(); }
     hist[SCHED_BUCKETS - 1 - t] = t ? s[t - 1] : 0;
 }
-__global__ void sched_scatter_kernel(const int* __restrict__ work, int* __restrict__ hist, int* __restrict__ order, long long B) {
+static __global__ void sched_scatter_kernel(const int* __restrict__ work, int* __restrict__ hist, int* __restrict__ order, long long B) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < B) order[atomicAdd(&hist[min(max(work[i], 0), SCHED_BUCKETS - 1)], 1)] = (int)i;
 }

@@ -28,6 +28,24 @@ struct DevBuf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+namespace atc {
+// operand scales of the tensor-core backward kernel (nfc_adjoint_tc.cuh): exact powers of two chosen in nfc_set_weights
+struct AtcScales {
+    float c_g2, c_g1;                 // accumulator -> next A operand of the transposed chain
+    float inv_u;                      // ubar accumulator -> ubar (times 1/sc of the column)
+    float s_d3;                       // scale of the output-layer delta operand (2^14)
+    float inv_sd2, inv_sd1;           // operand scale -> true delta (times 1/sc of the column)
+    float inv_sa0, inv_sa1, inv_sa2;  // the staged activations carry the forward operand scales: undone when the accumulators are flushed
+};
+}  // namespace atc
+
+struct AdjParams;
+}  // namespace nfc
+
+struct nfc_handle;
+namespace nfc {
+int adjoint_tc_setup(nfc_handle* h);
+int adjoint_tc_launch(nfc_handle* h, const AdjParams& A, const atc::AtcScales& sc, int64_t nb, cudaStream_t st);
 }  // namespace nfc
 
 struct nfc_handle {
@@ -51,6 +69,8 @@ struct nfc_handle {
     bool tc_record = true;                  // forward (RECORD) pass of loss_grad on the tensor-core kernels (FP16x2 split)
     int tc_tiles = 0;                       // FP16x2 solve: 0 = pick by batch size, 1 = one tile per CTA (nfc_tc.cuh), 2 = two tiles in flight (nfc_tc2.cuh)
     int64_t tc2_min_columns = 98304;        // auto: two tiles from this batch size on
+    bool adj_tc = true;                     // batch backward pass of loss_grad on the tensor cores (default Chain, FP16x2; NFC_ADJ_TC=0: FP32 SIMT kernel)
+    nfc::atc::AtcScales atc_scales{};
     bool tc_fp16 = false;                   // tensor-core split: false = BF16x3 (6 MMAs / product), true = FP16x2 (3 MMAs, scaled operands)
     // longest-first scheduling: per-column attempted steps of the previous forward call with the same batch size
     nfc::DevBuf<int> d_work, d_order, d_hist;

@@ -143,7 +143,7 @@ __device__ __forceinline__ void split3(float v0, float v1, uint32_t& p1, uint32_
 }
 
 // ---- weight image: theta (Flux layout) -> three bf16 splits per layer in UMMA layout + fp32 biases ----------------------
-__global__ void pack_weights_tc_kernel(const float* __restrict__ theta, unsigned char* __restrict__ img) {
+static __global__ void pack_weights_tc_kernel(const float* __restrict__ theta, unsigned char* __restrict__ img) {
     using N = Net<128, 2, 0>;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int n1 = 128 * 32, n2 = 128 * 128, n3 = 32 * 128;
@@ -344,7 +344,7 @@ __host__ __device__ constexpr uint32_t make_idesc16(int M, int N) {   // kind::f
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__global__ void pack_weights_tc16_kernel(const float* __restrict__ theta, unsigned char* __restrict__ img, const Fp16Scales sc) {
+static __global__ void pack_weights_tc16_kernel(const float* __restrict__ theta, unsigned char* __restrict__ img, const Fp16Scales sc) {
     using N = Net<128, 2, 0>;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int n1 = 128 * 32, n2 = 128 * 128, n3 = 32 * 128;
