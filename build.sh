@@ -1,16 +1,22 @@
 #!/bin/bash
-# Builds libnfc_b200.so (sm_100a only) in-tree: two translation units compiled side by side, then linked.  Usage: ./build.sh [-v]
+# Builds libnfc_b200.so (sm_100a only) in-tree: two translation units compiled side by side, then linked.
+# Usage: ./build.sh [-v] [-f]     -v: ptxas resource usage, -f: rebuild everything (default: only objects older than their sources)
 set -e
 cd "$(dirname "$0")"
 PKG="neuralfreeconvection.jl_b200"
-EXTRA=""
-[ "$1" = "-v" ] && EXTRA="-Xptxas -v"
+EXTRA=""; FORCE=0
+for a in "$@"; do [ "$a" = "-v" ] && EXTRA="-Xptxas -v"; [ "$a" = "-f" ] && FORCE=1; done
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -diag-suppress 128 $EXTRA -Xcompiler -fPIC"
 mkdir -p build
-nvcc $FLAGS -c -o build/nfc_api.o "$PKG/csrc/nfc_api.cu" &
-P1=$!
-nvcc $FLAGS -c -o build/nfc_adjoint_tc.o "$PKG/csrc/nfc_adjoint_tc.cu" &
-P2=$!
-wait $P1
-wait $P2
+stale() {   # $1 object, rest: sources
+    local o="$1"; shift
+    [ "$FORCE" = 1 ] || [ ! -f "$o" ] && return 0
+    for s in "$@"; do [ "$s" -nt "$o" ] && return 0; done
+    return 1
+}
+COMMON=$(ls $PKG/csrc/*.cuh $PKG/csrc/*.h include/nfc.h | grep -v nfc_adjoint_tc)
+PIDS=""
+if stale build/nfc_api.o $PKG/csrc/nfc_api.cu $COMMON; then nvcc $FLAGS -c -o build/nfc_api.o "$PKG/csrc/nfc_api.cu" & PIDS="$PIDS $!"; fi
+if stale build/nfc_adjoint_tc.o $PKG/csrc/nfc_adjoint_tc.cu $PKG/csrc/nfc_adjoint_tc.cuh $COMMON; then nvcc $FLAGS -c -o build/nfc_adjoint_tc.o "$PKG/csrc/nfc_adjoint_tc.cu" & PIDS="$PIDS $!"; fi
+for p in $PIDS; do wait $p; done
 nvcc -gencode arch=compute_100a,code=sm_100a --shared -o "$PKG/libnfc_b200.so" build/nfc_api.o build/nfc_adjoint_tc.o

@@ -55,8 +55,8 @@ struct AtcShared {
     uint64_t bar_w, bar_a, bar_d, bar_x;
     uint32_t tmem_base;
     int stop, any;
-    float xu[TILE][4][2], xl[TILE][4][2], xm[TILE][4];      // boundary levels of u and w*lambda_s, max |w lambda_s| of every quarter
-    float part[TILE][4];
+    float xu[4][2][TILE], xl[4][2][TILE], xm[4][TILE];      // boundary levels of u and w*lambda_s, max |w lambda_s| of every quarter
+    float part[4][TILE];
     int bad[TILE];
     // per-column slot state, owned by the quarter-0 thread of the column
     int col[TILE], si[TILE], nacc[TILE], nrej[TILE], mode[TILE], tlen[TILE], status[TILE], flag[TILE], jsi[TILE], ipos[TILE];
@@ -226,7 +226,7 @@ __device__ __forceinline__ void atc_control(const AdjParams& P, AtcShared& S, in
             S.mode[c] = 0;
             S.dt[c] = S.dt_retry[c];
         } else {
-            const float ee = sqrtf(((S.part[c][0] + S.part[c][1]) + (S.part[c][2] + S.part[c][3])) * (1.f / NZ));
+            const float ee = sqrtf(((S.part[0][c] + S.part[1][c]) + (S.part[2][c] + S.part[3][c])) * (1.f / NZ));
             const float h = S.h[c];
             bool accept;
             float dtnew;
@@ -423,6 +423,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) adjoint_tc_kernel(const unsigned 
                     for (int i = 0; i < 8; ++i) { kr[0][i] = 0.f; kr[1][i] = 0.f; kr[2][i] = 0.f; kr[3][i] = 0.f; }
                 }
                 h = S.h[c]; sgn = S.mode[c] ? -1.f : 1.f; kk = S.kk[c];
+                // the backward solve walks down the tape: pull the two rows below this step's last interval into L2 now (a row is 6 lines;
+                // the four threads of a column share them out), so that the next step's stage loads do not wait for HBM
+                if (col >= 0) {
+                    const int n6 = S.ivp[6][c];
+                    const char* r0 = reinterpret_cast<const char*>(P.tape + ((long long)col * P.tape_cap + (n6 > 0 ? n6 - 1 : 0)) * TAPE_STRIDE);
+                    const char* r1 = reinterpret_cast<const char*>(P.tape + ((long long)col * P.tape_cap + (n6 > 1 ? n6 - 2 : 0)) * TAPE_STRIDE);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(r0 + 128 * q));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(r1 + 128 * q));
+                    if (q < 2) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(r0 + 128 * (q + 4)));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(r1 + 128 * (q + 4)));
+                    }
+                }
             }
             const int any = S.any;
             cta_bar();
@@ -439,6 +452,36 @@ __global__ void __launch_bounds__(NTHREADS, 1) adjoint_tc_kernel(const unsigned 
                 uint32_t ph3[4], pl3[4];
                 // ---- E0: stage input lambda_s, u(t_s) from the tape, layer-1 operand ----
                 {
+                    // u(t_s) of the CTA's 128 columns from the forward tape, loaded COOPERATIVELY: warp w evaluates columns 8w..8w+7 with
+                    // lane == level, so every load is one coalesced 128-B line (768 line requests per stage).  Loading with thread == column
+                    // (each lane its own row: 6 144 sector requests per stage) saturated the L1 miss queue: 40 % of all stall samples.
+                    // The result goes through shared memory (the X staging buffer is free between dW1 of the previous stage and E2).
+                    if (s > 0) { mbar_wait(&S.bar_x, px); px ^= 1; }      // dW1 of the previous stage has read the X and u staging buffers
+                    {
+                        float* xu32 = reinterpret_cast<float*>(smem + SO_X);
+                        const float cs = c_adj_c[s];
+#pragma unroll
+                        for (int b = 0; b < 2; ++b) {
+                            float e[4][5], tn[4], hn[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int cc = 8 * warp + 4 * b + j, colx = S.col[cc];
+                                const float* row = P.tape + ((long long)(colx >= 0 ? colx : 0) * P.tape_cap + S.ivp[s][cc]) * TAPE_STRIDE;
+                                tn[j] = __ldg(row + TAPE_T); hn[j] = __ldg(row + TAPE_H);
+#pragma unroll
+                                for (int k = 0; k < 5; ++k) e[j][k] = __ldg(row + k * NZ + lane);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const int cc = 8 * warp + 4 * b + j;
+                                const float hc = S.h[cc];
+                                const float ts = (s == 6 && (S.flag[cc] & AFL_LAST)) ? S.tstop[cc] : S.t[cc] - cs * hc;
+                                const float th = fminf(fmaxf((ts - tn[j]) / hn[j], 0.f), 1.f);
+                                const float uv = fmaf(hn[j], th * fmaf(th, fmaf(th, fmaf(th, e[j][4], e[j][3]), e[j][2]), e[j][1]), e[j][0]);
+                                xu32[cc * 36 + lane] = S.col[cc] >= 0 ? uv : 0.f;
+                            }
+                        }
+                    }
                     float acc[8], kv[8];
                     tmem_ld8f(tl + TA_K1 + 8 * q, kv);
                     const float4 ka = *reinterpret_cast<const float4*>(k2p), kb = *reinterpret_cast<const float4*>(k2p + 4 * TILE * 4);
@@ -449,39 +492,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) adjoint_tc_kernel(const unsigned 
                     for (int i = 0; i < 8; ++i) {
                         float a = a0 * kv[i];
                         a = fmaf(a1, k2v[i], a); a = fmaf(a2, kr[0][i], a); a = fmaf(a3, kr[1][i], a); a = fmaf(a4, kr[2][i], a); a = fmaf(a5, kr[3][i], a);
-                        acc[i] = a;
+                        acc[i] = fmaf(h, a, lam[i]);            // lambda_s
                     }
-                    const float* row = P.tape + ((long long)(col >= 0 ? col : 0) * P.tape_cap + S.ivp[s][c]) * TAPE_STRIDE;
+                    cta_bar();
                     float u[8], lw[8];
                     {
-                        const float tn = row[TAPE_T], hn = row[TAPE_H];
-                        const float tcur = S.t[c];
-                        const float ts = (s == 6 && (S.flag[c] & AFL_LAST)) ? S.tstop[c] : tcur - c_adj_c[s] * h;
-                        const float th = fminf(fmaxf((ts - tn) / hn, 0.f), 1.f);
-                        const float* e = row + 8 * q;
-#pragma unroll
-                        for (int hf = 0; hf < 2; ++hf) {
-                            const float4 e0 = *reinterpret_cast<const float4*>(e + 4 * hf), e1 = *reinterpret_cast<const float4*>(e + NZ + 4 * hf),
-                                         e2 = *reinterpret_cast<const float4*>(e + 2 * NZ + 4 * hf), e3 = *reinterpret_cast<const float4*>(e + 3 * NZ + 4 * hf),
-                                         e4 = *reinterpret_cast<const float4*>(e + 4 * NZ + 4 * hf);
-                            u[4 * hf + 0] = fmaf(hn, th * fmaf(th, fmaf(th, fmaf(th, e4.x, e3.x), e2.x), e1.x), e0.x);
-                            u[4 * hf + 1] = fmaf(hn, th * fmaf(th, fmaf(th, fmaf(th, e4.y, e3.y), e2.y), e1.y), e0.y);
-                            u[4 * hf + 2] = fmaf(hn, th * fmaf(th, fmaf(th, fmaf(th, e4.z, e3.z), e2.z), e1.z), e0.z);
-                            u[4 * hf + 3] = fmaf(hn, th * fmaf(th, fmaf(th, fmaf(th, e4.w, e3.w), e2.w), e1.w), e0.w);
-                        }
+                        const float* xu32 = reinterpret_cast<const float*>(smem + SO_X) + c * 36 + 8 * q;
+                        const float4 ua = *reinterpret_cast<const float4*>(xu32), ub = *reinterpret_cast<const float4*>(xu32 + 4);
+                        u[0] = ua.x; u[1] = ua.y; u[2] = ua.z; u[3] = ua.w; u[4] = ub.x; u[5] = ub.y; u[6] = ub.z; u[7] = ub.w;
                     }
                     float m = 0.f, nanacc = 0.f;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
-                        if (col < 0) u[i] = 0.f;
-                        const float ls = fmaf(h, acc[i], lam[i]);
-                        lw[i] = w * ls;
+                        lw[i] = w * acc[i];
                         m = fmaxf(m, fabsf(lw[i]));
                         nanacc = fmaf(lw[i], 0.f, nanacc);
                     }
-                    S.xu[c][q][0] = u[0]; S.xu[c][q][1] = u[7];
-                    S.xl[c][q][0] = lw[0]; S.xl[c][q][1] = lw[7];
-                    S.xm[c][q] = nanacc == 0.f ? m : __int_as_float(0x7fc00000);
+                    S.xu[q][0][c] = u[0]; S.xu[q][1][c] = u[7];
+                    S.xl[q][0][c] = lw[0]; S.xl[q][1][c] = lw[7];
+                    S.xm[q][c] = nanacc == 0.f ? m : __int_as_float(0x7fc00000);
                     // layer-1 A operand (the network input saturates at the operand bound like in the forward solve)
                     uint32_t ph[4], pl[4], pb[4];
 #pragma unroll
@@ -491,7 +520,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) adjoint_tc_kernel(const unsigned 
                         split2h(v0, v1, ph[i], pl[i]);
                         pb[i] = pack_bf16(v0, v1);
                     }
-                    if (s > 0) { mbar_wait(&S.bar_x, px); px ^= 1; }      // dW1 of the previous stage has read the u staging buffer
                     tmem_st4(tl + TA_A + 4 * q, ph);
                     tmem_st4(tl + TA_A + 64 + 4 * q, pl);
                     if (dw) *reinterpret_cast<uint4*>(smem + SO_U + q * CH + c * 16) = make_uint4(pb[0], pb[1], pb[2], pb[3]);
@@ -508,9 +536,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) adjoint_tc_kernel(const unsigned 
                 fence_after_sync();
                 {
                     // the exchange buffers were written before the barrier traffic of the layer-1 MMAs
-                    const float ulo = q > 0 ? S.xu[c][q - 1][1] : 0.f, uhi = q < 3 ? S.xu[c][q + 1][0] : 0.f;
-                    const float llo = q > 0 ? S.xl[c][q - 1][1] : 0.f, lhi = q < 3 ? S.xl[c][q + 1][0] : 0.f;
-                    const float m0 = S.xm[c][0], m1 = S.xm[c][1], m2 = S.xm[c][2], m3 = S.xm[c][3];
+                    const float ulo = q > 0 ? S.xu[q > 0 ? q - 1 : 0][1][c] : 0.f, uhi = q < 3 ? S.xu[q < 3 ? q + 1 : 3][0][c] : 0.f;
+                    const float llo = q > 0 ? S.xl[q > 0 ? q - 1 : 0][1][c] : 0.f, lhi = q < 3 ? S.xl[q < 3 ? q + 1 : 3][0][c] : 0.f;
+                    const float m0 = S.xm[0][c], m1 = S.xm[1][c], m2 = S.xm[2][c], m3 = S.xm[3][c];
                     const float M = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
                     const bool isbad = !(m0 == m0 && m1 == m1 && m2 == m2 && m3 == m3) || !(M < 1e30f);
                     {
@@ -681,7 +709,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) adjoint_tc_kernel(const unsigned 
                     const float r = e / (P.abstol + fmaxf(fabsf(lam[i]), fabsf(lnew[i])) * P.reltol);
                     part = fmaf(r, r, part);
                 }
-                S.part[c][q] = part;
+                S.part[q][c] = part;
             }
             cta_bar();
         }
