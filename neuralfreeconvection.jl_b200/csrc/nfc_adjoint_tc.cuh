@@ -47,8 +47,8 @@ constexpr int SO_ONES = SO_U + 4 * CH;       // ones       2 chunks  } B operand
 constexpr int SO_A1 = SO_ONES + 2 * CH;      // a1        16 chunks  }
 constexpr int SO_X = SO_A1 + 16 * CH;        // a2, then d2, then d1 (A operands of the three contractions), 16 chunks
 constexpr int SO_D3 = SO_X + 16 * CH;        // d3         4 chunks  (B operand of dW3^T, N = 32)
-constexpr int SO_K2 = SO_D3 + 4 * CH;        // kappa_2 [2][4][128][4] fp32
-constexpr int SO_ST = SO_K2 + 16384;
+constexpr int SO_UB = SO_D3 + 4 * CH;        // u(t_s) of the NEXT stage, fp32 [column][32 levels], 16-byte groups XOR-swizzled by the column
+constexpr int SO_ST = SO_UB + 16384;
 static_assert(IMG16_BYTES <= SO_U, "weight image overlaps the staging buffers");
 
 struct AtcShared {
@@ -325,6 +325,33 @@ __device__ __forceinline__ void atc_control(const AdjParams& P, AtcShared& S, in
     S.bad[c] = 0;
 }
 
+// u(t_s) of the CTA's 128 columns from the forward tape, loaded COOPERATIVELY and one stage ahead: warp w evaluates columns 8w..8w+7 with
+// lane == level, so every load is one coalesced 128-B line (768 line requests per stage) and its latency hides under the MMAs of the
+// stage before.  Loading with thread == column (each lane its own row: 6 144 sector requests per stage) saturated the L1 miss queue: 40 %
+// of all stall samples.  Batch b = columns 8w + 4b .. 8w + 4b + 3.
+__device__ __forceinline__ void coop_load(const AdjParams& P, AtcShared& S, unsigned char* smem, int s, int b, int warp, int lane) {
+    float* ub = reinterpret_cast<float*>(smem + SO_UB);
+    const float cs = c_adj_c[s];
+    float e[4][5], tn[4], hn[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int cc = 8 * warp + 4 * b + j, colx = S.col[cc];
+        const float* row = P.tape + ((long long)(colx >= 0 ? colx : 0) * P.tape_cap + S.ivp[s][cc]) * TAPE_STRIDE;
+        tn[j] = __ldg(row + TAPE_T); hn[j] = __ldg(row + TAPE_H);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) e[j][k] = __ldg(row + k * NZ + lane);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int cc = 8 * warp + 4 * b + j;
+        const float hc = S.h[cc];
+        const float ts = (s == 6 && (S.flag[cc] & AFL_LAST)) ? S.tstop[cc] : S.t[cc] - cs * hc;
+        const float th = fminf(fmaxf((ts - tn[j]) / hn[j], 0.f), 1.f);
+        const float uv = fmaf(hn[j], th * fmaf(th, fmaf(th, fmaf(th, e[j][4], e[j][3]), e[j][2]), e[j][1]), e[j][0]);
+        ub[cc * 32 + ((((lane >> 2) ^ (cc & 7)) << 2) | (lane & 3))] = S.col[cc] >= 0 ? uv : 0.f;
+    }
+}
+
 __global__ void __launch_bounds__(NTHREADS, 1) adjoint_tc_kernel(const unsigned char* __restrict__ gimg, const AdjParams P, const AtcScales sc) {
     extern __shared__ __align__(1024) unsigned char smem[];
     AtcShared& S = *reinterpret_cast<AtcShared*>(smem + SO_ST);
@@ -346,7 +373,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) adjoint_tc_kernel(const unsigned 
         }
     }
     // staging buffers: zero (idle slots and the stage-7 pass never write them), constant-one rows of the bias gradients
-    for (int i = threadIdx.x; i < (SO_K2 + 16384 - SO_U) / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem + SO_U)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (int i = threadIdx.x; i < (SO_UB + 16384 - SO_U) / 16; i += NTHREADS) reinterpret_cast<uint4*>(smem + SO_U)[i] = make_uint4(0u, 0u, 0u, 0u);
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * CH / 4; i += NTHREADS) reinterpret_cast<uint32_t*>(smem + SO_ONES)[i] = 0x3f803f80u;
     for (int i = threadIdx.x; i < TILE; i += NTHREADS) { S.col[i] = -1; S.bad[i] = 0; S.flag[i] = 0; S.mode[i] = 0; S.status[i] = ST_OK; }
@@ -368,7 +395,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) adjoint_tc_kernel(const unsigned 
         const uint32_t tl = S.tmem_base + ((uint32_t)(32 * wq) << 16);
         const float c0 = P.pref * (float)NZ;
         const float c1 = sb[288], c2 = sb[289], s_a0 = sb[291];
-        float* const k2p = reinterpret_cast<float*>(smem + SO_K2) + (q * TILE + c) * 4;      // second half at + 4 * TILE * 4 floats
         {   // clear the persistent accumulators and kappa_1
             const uint32_t z8[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
 #pragma unroll
@@ -377,12 +403,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) adjoint_tc_kernel(const unsigned 
             wait_st();
         }
         int pd = 0, px = 0, col = -1;
-        float lam[8], kr[4][8], uca[8], k7[8], lnew[8];
+        float lam[8], kr[5][8], uca[8], k7[8], lnew[8];
         float h = 0.f, sgn = 1.f, kk = 0.f, db3 = 0.f;
         uint32_t mask1 = 0u, mask2 = 0u;
         bool queue_empty = false;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { lam[i] = 0.f; uca[i] = 0.f; k7[i] = 0.f; lnew[i] = 0.f; kr[0][i] = 0.f; kr[1][i] = 0.f; kr[2][i] = 0.f; kr[3][i] = 0.f; }
+        for (int i = 0; i < 8; ++i) { lam[i] = 0.f; uca[i] = 0.f; k7[i] = 0.f; lnew[i] = 0.f; kr[0][i] = 0.f; kr[1][i] = 0.f; kr[2][i] = 0.f; kr[3][i] = 0.f; kr[4][i] = 0.f; }
         fence_before_sync();
         cta_bar();
         while (true) {
@@ -417,10 +443,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) adjoint_tc_kernel(const unsigned 
 #pragma unroll
                         for (int i = 0; i < 8; ++i) lam[i] = 0.f;
                     }
-                    *reinterpret_cast<float4*>(k2p) = make_float4(0.f, 0.f, 0.f, 0.f);
-                    *reinterpret_cast<float4*>(k2p + 4 * TILE * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) { kr[0][i] = 0.f; kr[1][i] = 0.f; kr[2][i] = 0.f; kr[3][i] = 0.f; }
+                    for (int i = 0; i < 8; ++i) { kr[0][i] = 0.f; kr[1][i] = 0.f; kr[2][i] = 0.f; kr[3][i] = 0.f; kr[4][i] = 0.f; }
                 }
                 h = S.h[c]; sgn = S.mode[c] ? -1.f : 1.f; kk = S.kk[c];
                 // the backward solve walks down the tape: pull the two rows below this step's last interval into L2 now (a row is 6 lines;
@@ -438,6 +462,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) adjoint_tc_kernel(const unsigned 
                 }
             }
             const int any = S.any;
+            if (any) { coop_load(P, S, smem, 0, 0, warp, lane); coop_load(P, S, smem, 0, 1, warp, lane); }
             cta_bar();
             if (threadIdx.x == 0) S.any = 0;          // re-armed for the next control phase (two barriers away)
             if (!any) break;
@@ -452,54 +477,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) adjoint_tc_kernel(const unsigned 
                 uint32_t ph3[4], pl3[4];
                 // ---- E0: stage input lambda_s, u(t_s) from the tape, layer-1 operand ----
                 {
-                    // u(t_s) of the CTA's 128 columns from the forward tape, loaded COOPERATIVELY: warp w evaluates columns 8w..8w+7 with
-                    // lane == level, so every load is one coalesced 128-B line (768 line requests per stage).  Loading with thread == column
-                    // (each lane its own row: 6 144 sector requests per stage) saturated the L1 miss queue: 40 % of all stall samples.
-                    // The result goes through shared memory (the X staging buffer is free between dW1 of the previous stage and E2).
-                    if (s > 0) { mbar_wait(&S.bar_x, px); px ^= 1; }      // dW1 of the previous stage has read the X and u staging buffers
-                    {
-                        float* xu32 = reinterpret_cast<float*>(smem + SO_X);
-                        const float cs = c_adj_c[s];
-#pragma unroll
-                        for (int b = 0; b < 2; ++b) {
-                            float e[4][5], tn[4], hn[4];
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int cc = 8 * warp + 4 * b + j, colx = S.col[cc];
-                                const float* row = P.tape + ((long long)(colx >= 0 ? colx : 0) * P.tape_cap + S.ivp[s][cc]) * TAPE_STRIDE;
-                                tn[j] = __ldg(row + TAPE_T); hn[j] = __ldg(row + TAPE_H);
-#pragma unroll
-                                for (int k = 0; k < 5; ++k) e[j][k] = __ldg(row + k * NZ + lane);
-                            }
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const int cc = 8 * warp + 4 * b + j;
-                                const float hc = S.h[cc];
-                                const float ts = (s == 6 && (S.flag[cc] & AFL_LAST)) ? S.tstop[cc] : S.t[cc] - cs * hc;
-                                const float th = fminf(fmaxf((ts - tn[j]) / hn[j], 0.f), 1.f);
-                                const float uv = fmaf(hn[j], th * fmaf(th, fmaf(th, fmaf(th, e[j][4], e[j][3]), e[j][2]), e[j][1]), e[j][0]);
-                                xu32[cc * 36 + lane] = S.col[cc] >= 0 ? uv : 0.f;
-                            }
-                        }
-                    }
                     float acc[8], kv[8];
                     tmem_ld8f(tl + TA_K1 + 8 * q, kv);
-                    const float4 ka = *reinterpret_cast<const float4*>(k2p), kb = *reinterpret_cast<const float4*>(k2p + 4 * TILE * 4);
                     const float a0 = c_adj_a[s][0], a1 = c_adj_a[s][1], a2 = c_adj_a[s][2], a3 = c_adj_a[s][3], a4 = c_adj_a[s][4], a5 = c_adj_a[s][5];
-                    const float k2v[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
+                    float u[8], lw[8];
+                    {   // u(t_s): put into the u buffer one stage ahead by coop_load (below)
+                        const float* ub = reinterpret_cast<const float*>(smem + SO_UB) + c * 32;
+                        const float4 ua = *reinterpret_cast<const float4*>(ub + (((2 * q) ^ (c & 7)) << 2)), uc = *reinterpret_cast<const float4*>(ub + (((2 * q + 1) ^ (c & 7)) << 2));
+                        u[0] = ua.x; u[1] = ua.y; u[2] = ua.z; u[3] = ua.w; u[4] = uc.x; u[5] = uc.y; u[6] = uc.z; u[7] = uc.w;
+                    }
                     wait_ld();
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         float a = a0 * kv[i];
-                        a = fmaf(a1, k2v[i], a); a = fmaf(a2, kr[0][i], a); a = fmaf(a3, kr[1][i], a); a = fmaf(a4, kr[2][i], a); a = fmaf(a5, kr[3][i], a);
+                        a = fmaf(a1, kr[0][i], a); a = fmaf(a2, kr[1][i], a); a = fmaf(a3, kr[2][i], a); a = fmaf(a4, kr[3][i], a); a = fmaf(a5, kr[4][i], a);
                         acc[i] = fmaf(h, a, lam[i]);            // lambda_s
-                    }
-                    cta_bar();
-                    float u[8], lw[8];
-                    {
-                        const float* xu32 = reinterpret_cast<const float*>(smem + SO_X) + c * 36 + 8 * q;
-                        const float4 ua = *reinterpret_cast<const float4*>(xu32), ub = *reinterpret_cast<const float4*>(xu32 + 4);
-                        u[0] = ua.x; u[1] = ua.y; u[2] = ua.z; u[3] = ua.w; u[4] = ub.x; u[5] = ub.y; u[6] = ub.z; u[7] = ub.w;
                     }
                     float m = 0.f, nanacc = 0.f;
 #pragma unroll
@@ -522,6 +514,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) adjoint_tc_kernel(const unsigned 
                     }
                     tmem_st4(tl + TA_A + 4 * q, ph);
                     tmem_st4(tl + TA_A + 64 + 4 * q, pl);
+                    if (s > 0) { mbar_wait(&S.bar_x, px); px ^= 1; }      // dW1 of the previous stage has read the u staging buffer
                     if (dw) *reinterpret_cast<uint4*>(smem + SO_U + q * CH + c * 16) = make_uint4(pb[0], pb[1], pb[2], pb[3]);
                     wait_st();
                     fence_before_sync();
@@ -599,6 +592,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) adjoint_tc_kernel(const unsigned 
                 fence_before_sync();
                 fence_async_smem();
                 mbar_arrive(&S.bar_a);
+                if (s < 6) coop_load(P, S, smem, s + 1, 0, warp, lane);      // under the layer-2 MMAs
                 // ---- E2: z2 -> a2 (staged for dW3^T, relu mask); output-layer delta -> A operand ----
                 mbar_wait(&S.bar_d, pd); pd ^= 1;
                 fence_after_sync();
@@ -633,13 +627,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) adjoint_tc_kernel(const unsigned 
                 for (int l = 0; l < 2; ++l) {
                     mbar_wait(&S.bar_d, pd); pd ^= 1;
                     fence_after_sync();
-                    if (dw) { mbar_wait(&S.bar_x, px); px ^= 1; }          // the previous contraction has read the X staging buffer
                     const float cg = l == 0 ? sc.c_g2 : sc.c_g1;
                     const float cst = (l == 0 ? sc.inv_sd2 : sc.inv_sd1) / scol;
                     const uint32_t mk = l == 0 ? mask2 : mask1;
+                    uint32_t pb[16];
 #pragma unroll
                     for (int ch = 0; ch < 2; ++ch) {
-                        uint32_t r[16], ph[8], pl[8], pb[8];
+                        uint32_t r[16], ph[8], pl[8];
                         tmem_ld16(tl + TA_D + 32 * q + 16 * ch, r);
                         wait_ld();
 #pragma unroll
@@ -647,19 +641,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) adjoint_tc_kernel(const unsigned 
                             const float v0 = ((mk >> (16 * ch + 2 * i)) & 1u) ? __uint_as_float(r[2 * i]) * cg : 0.f;
                             const float v1 = ((mk >> (16 * ch + 2 * i + 1)) & 1u) ? __uint_as_float(r[2 * i + 1]) * cg : 0.f;
                             split2h(v0, v1, ph[i], pl[i]);
-                            pb[i] = pack_bf16(v0 * cst, v1 * cst);
+                            pb[8 * ch + i] = pack_bf16(v0 * cst, v1 * cst);
                         }
                         tmem_st8(tl + TA_A + 16 * q + 8 * ch, ph);
                         tmem_st8(tl + TA_A + 64 + 16 * q + 8 * ch, pl);
-                        if (dw) {
-                            *reinterpret_cast<uint4*>(smem + SO_X + (4 * q + 2 * ch) * CH + c * 16) = make_uint4(pb[0], pb[1], pb[2], pb[3]);
-                            *reinterpret_cast<uint4*>(smem + SO_X + (4 * q + 2 * ch + 1) * CH + c * 16) = make_uint4(pb[4], pb[5], pb[6], pb[7]);
-                        }
+                    }
+                    if (dw) {
+                        mbar_wait(&S.bar_x, px); px ^= 1;          // the previous contraction (issued behind this layer's MMAs) has read the X staging buffer
+#pragma unroll
+                        for (int g4 = 0; g4 < 4; ++g4)
+                            *reinterpret_cast<uint4*>(smem + SO_X + (4 * q + g4) * CH + c * 16) = make_uint4(pb[4 * g4], pb[4 * g4 + 1], pb[4 * g4 + 2], pb[4 * g4 + 3]);
                     }
                     wait_st();
                     fence_before_sync();
                     fence_async_smem();
                     mbar_arrive(&S.bar_a);
+                    if (l == 0 && s < 6) coop_load(P, S, smem, s + 1, 1, warp, lane);      // under the g1 MMAs
                 }
                 // ---- E6: kappa_s = (W1^T d1 + K_CA part) / w ----
                 mbar_wait(&S.bar_d, pd); pd ^= 1;
@@ -673,16 +670,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) adjoint_tc_kernel(const unsigned 
 #pragma unroll
                     for (int i = 0; i < 8; ++i) kap[i] = fmaf(a[i] + b[i], cu, uca[i]) * winv;
                     if (s == 0) { tmem_st8f(tl + TA_K1 + 8 * q, kap); wait_st(); }
-                    else if (s == 1) {
-                        *reinterpret_cast<float4*>(k2p) = make_float4(kap[0], kap[1], kap[2], kap[3]);
-                        *reinterpret_cast<float4*>(k2p + 4 * TILE * 4) = make_float4(kap[4], kap[5], kap[6], kap[7]);
-                    } else {
+                    else {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
-                            if (s == 2) kr[0][i] = kap[i];
-                            else if (s == 3) kr[1][i] = kap[i];
-                            else if (s == 4) kr[2][i] = kap[i];
-                            else if (s == 5) kr[3][i] = kap[i];
+                            if (s == 1) kr[0][i] = kap[i];
+                            else if (s == 2) kr[1][i] = kap[i];
+                            else if (s == 3) kr[2][i] = kap[i];
+                            else if (s == 4) kr[3][i] = kap[i];
+                            else if (s == 5) kr[4][i] = kap[i];
                             else k7[i] = kap[i];
                         }
                     }
@@ -693,18 +688,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) adjoint_tc_kernel(const unsigned 
             {
                 float kv[8];
                 tmem_ld8f(tl + TA_K1 + 8 * q, kv);
-                const float4 ka = *reinterpret_cast<const float4*>(k2p), kb = *reinterpret_cast<const float4*>(k2p + 4 * TILE * 4);
-                const float k2v[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
                 wait_ld();
                 float part = 0.f;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     float b = NFC_B1 * kv[i];
-                    b = fmaf(NFC_B2, k2v[i], b); b = fmaf(NFC_B3, kr[0][i], b); b = fmaf(NFC_B4, kr[1][i], b); b = fmaf(NFC_B5, kr[2][i], b); b = fmaf(NFC_B6, kr[3][i], b);
+                    b = fmaf(NFC_B2, kr[0][i], b); b = fmaf(NFC_B3, kr[1][i], b); b = fmaf(NFC_B4, kr[2][i], b); b = fmaf(NFC_B5, kr[3][i], b); b = fmaf(NFC_B6, kr[4][i], b);
                     lnew[i] = fmaf(h, b, lam[i]);
                     float e = NFC_BT1 * kv[i];
-                    e = fmaf(NFC_BT2, k2v[i], e); e = fmaf(NFC_BT3, kr[0][i], e); e = fmaf(NFC_BT4, kr[1][i], e); e = fmaf(NFC_BT5, kr[2][i], e);
-                    e = fmaf(NFC_BT6, kr[3][i], e); e = fmaf(NFC_BT7, k7[i], e);
+                    e = fmaf(NFC_BT2, kr[0][i], e); e = fmaf(NFC_BT3, kr[1][i], e); e = fmaf(NFC_BT4, kr[2][i], e); e = fmaf(NFC_BT5, kr[3][i], e);
+                    e = fmaf(NFC_BT6, kr[4][i], e); e = fmaf(NFC_BT7, k7[i], e);
                     e *= h;
                     const float r = e / (P.abstol + fmaxf(fabsf(lam[i]), fabsf(lnew[i])) * P.reltol);
                     part = fmaf(r, r, part);
