@@ -13,7 +13,7 @@
 //   weight gradient     dW3^T += a2^T d3       dW2 += d2^T [1 a1]  dW1 += d1^T [u 1]   SS form with K = the 128 ocean columns: both
 //                                                                                   operands are staged by the epilogue threads as BF16 in
 //                                                                                   MN-major layout, the accumulators (224 TMEM columns)
-//                                                                                   persist for the whole kernel; the constant-one rows
+//                                                                                   collect one Runge-Kutta step and are flushed in stage 7; the constant-one rows
 //                                                                                   make the bias gradients fall out of the same MMAs.
 //
 // Arithmetic: the chain (forward and transposed) is FP32-faithful like the forward solve (FP16 hi + lo, three products per k-step,
@@ -83,6 +83,10 @@ __device__ __forceinline__ void mma_ss2(uint32_t d_tmem, uint32_t a_lo, uint32_t
         asm volatile("{\n\t.reg .b64 ad, bd;\n\t.reg .pred p;\n\tsetp.ne.u32 p, 1, 1;\n\tmov.b64 ad, {%1, %2};\n\tmov.b64 bd, {%3, %4};\n\t"
                      "tcgen05.mma.cta_group::1.kind::f16 [%0], ad, bd, %5, p;\n\t}" ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(id) : "memory");
 }
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t id, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem), "l"(a_desc),
+                 "l"(b_desc), "r"(id), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // TS-form product over NK k-steps: D (+)= A[cells a + 8 j] x B[desc + kadv j]
@@ -94,12 +98,16 @@ __device__ __forceinline__ void issue_ts(uint32_t d, uint32_t a, uint32_t blo, u
         else mma_ts2<true>(d, a + 8 * j, blo + kadv * j, bhi, id);
     }
 }
-// SS-form contraction over the 128 columns (8 k-steps of 16 columns = 256 B in both staging buffers): always accumulates
-__device__ __forceinline__ void issue_dw(uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t id) {
+// SS-form contraction over the 128 columns (8 k-steps of 16 columns = 256 B in both staging buffers).  The accumulators collect ONE
+// Runge-Kutta step (first = stage 0 overwrites) and are flushed to the CTA's fp32 gradient row in stage 7: the tensor core adds with
+// truncation, and an accumulator that lived for the whole kernel (17 000 additions of increments far below its own magnitude) drifted
+// by 1e-3 relative -- growing with the number of steps, which is how it was found (tight tolerances made the gradient WORSE).
+__device__ __forceinline__ void issue_dw(uint32_t d, uint32_t a_addr, uint32_t b_addr, uint32_t id, bool first) {
     const uint64_t ad = make_desc(a_addr, 128, CH), bd = make_desc(b_addr, 128, CH);
     const uint32_t alo = (uint32_t)ad, ahi = (uint32_t)(ad >> 32), blo = (uint32_t)bd, bhi = (uint32_t)(bd >> 32);
+    mma_ss(d, ad, bd, id, first ? 0u : 1u);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) mma_ss2<true>(d, alo + 16 * j, ahi, blo + 16 * j, bhi, id);
+    for (int j = 1; j < 8; ++j) mma_ss2<true>(d, alo + 16 * j, ahi, blo + 16 * j, bhi, id);
 }
 
 // ---- MMA issuer: per stage five batches, each released by the 512 column threads through bar_a -----------------------------------------
@@ -153,7 +161,7 @@ __device__ __forceinline__ void atc_mma_loop(AtcShared* S, uint32_t sbase) {
             mma_commit(&S->bar_d);
             if (dw) {
                 asm volatile("" : "+r"(tb), "+r"(img));
-                issue_dw(tb + TA_ACC3, img + SO_X, img + SO_D3, ID_W32);
+                issue_dw(tb + TA_ACC3, img + SO_X, img + SO_D3, ID_W32, s == 0);
                 mma_commit(&S->bar_x);
             }
             // (4) g1 = d2 W2, then dW2 += d2^T [1 a1]
@@ -170,7 +178,7 @@ __device__ __forceinline__ void atc_mma_loop(AtcShared* S, uint32_t sbase) {
             mma_commit(&S->bar_d);
             if (dw) {
                 asm volatile("" : "+r"(tb), "+r"(img));
-                issue_dw(tb + TA_ACC2, img + SO_X, img + SO_ONES, ID_W144);
+                issue_dw(tb + TA_ACC2, img + SO_X, img + SO_ONES, ID_W144, s == 0);
                 mma_commit(&S->bar_x);
             }
             // (5) ubar = d1 W1 (hi and lo images are adjacent along the transposed N: one N = 64 operand), then dW1 += d1^T [u 1]
@@ -186,7 +194,7 @@ __device__ __forceinline__ void atc_mma_loop(AtcShared* S, uint32_t sbase) {
             mma_commit(&S->bar_d);
             if (dw) {
                 asm volatile("" : "+r"(tb), "+r"(img));
-                issue_dw(tb + TA_ACC1, img + SO_X, img + SO_U, ID_W48);
+                issue_dw(tb + TA_ACC1, img + SO_X, img + SO_U, ID_W48, s == 0);
                 mma_commit(&S->bar_x);
             }
         }
@@ -325,6 +333,26 @@ __device__ __forceinline__ void atc_control(const AdjParams& P, AtcShared& S, in
     S.bad[c] = 0;
 }
 
+// Flush this step's weight-gradient accumulators (224 TMEM columns, lane = unit) into the CTA's gradient row with fire-and-forget RED.ADD
+__device__ __forceinline__ void flush_acc(float* __restrict__ g, uint32_t tl, int c, int q, const AtcScales& sc) {
+    using N0 = Net<128, 2, 0>;
+#pragma unroll 1
+    for (int gidx = q; gidx < 28; gidx += 4) {
+        float v[8];
+        tmem_ld8f(tl + 8 * gidx, v);
+        wait_ld();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int ci = 8 * gidx + e;        // accumulator column; TMEM lane c = unit j
+            if (ci < 16) { if (ci == 0) atomicAdd(g + N0::T_HID + 128 * 128 + c, v[e]); }
+            else if (ci < 144) atomicAdd(g + N0::T_HID + (ci - 16) * 128 + c, v[e] * sc.inv_sa1);
+            else if (ci < 176) atomicAdd(g + N0::T_W0 + (ci - 144) * 128 + c, v[e] * sc.inv_sa0);
+            else if (ci < 192) { if (ci == 176) atomicAdd(g + N0::T_B0 + c, v[e]); }
+            else if (ci - 192 < 31) atomicAdd(g + N0::T_WL + c * 31 + (ci - 192), v[e] * sc.inv_sa2);
+        }
+    }
+}
+
 // u(t_s) of the CTA's 128 columns from the forward tape, loaded COOPERATIVELY and one stage ahead: warp w evaluates columns 8w..8w+7 with
 // lane == level, so every load is one coalesced 128-B line (768 line requests per stage) and its latency hides under the MMAs of the
 // stage before.  Loading with thread == column (each lane its own row: 6 144 sector requests per stage) saturated the L1 miss queue: 40 %
@@ -395,13 +423,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) adjoint_tc_kernel(const unsigned 
         const uint32_t tl = S.tmem_base + ((uint32_t)(32 * wq) << 16);
         const float c0 = P.pref * (float)NZ;
         const float c1 = sb[288], c2 = sb[289], s_a0 = sb[291];
-        {   // clear the persistent accumulators and kappa_1
+        {   // clear kappa_1 (stale stage vectors meet zero tableau entries and must be finite)
             const uint32_t z8[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-#pragma unroll
-            for (int g = 0; g < 7; ++g) tmem_st8(tl + TA_ACC2 + 8 * (7 * q + g), z8);
             tmem_st8(tl + TA_K1 + 8 * q, z8);
             wait_st();
         }
+        float* const g = P.gacc + (size_t)blockIdx.x * P.n_params;
         int pd = 0, px = 0, col = -1;
         float lam[8], kr[5][8], uca[8], k7[8], lnew[8];
         float h = 0.f, sgn = 1.f, kk = 0.f, db3 = 0.f;
@@ -593,6 +620,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) adjoint_tc_kernel(const unsigned 
                 fence_async_smem();
                 mbar_arrive(&S.bar_a);
                 if (s < 6) coop_load(P, S, smem, s + 1, 0, warp, lane);      // under the layer-2 MMAs
+                else flush_acc(g, tl, c, q, sc);                             // every contraction of this step has completed (bar_x at E0)
                 // ---- E2: z2 -> a2 (staged for dW3^T, relu mask); output-layer delta -> A operand ----
                 mbar_wait(&S.bar_d, pd); pd ^= 1;
                 fence_after_sync();
@@ -707,27 +735,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) adjoint_tc_kernel(const unsigned 
             cta_bar();
         }
         // ---- flush: bias gradient of the output layer (registers), then the persistent accumulators ----
-        float* g = P.gacc + (size_t)blockIdx.x * P.n_params;
         using N0 = Net<128, 2, 0>;
         if ((lane & 3) == 0) {
             const int n = 8 * q + ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
             if (n < 31) atomicAdd(g + N0::T_BL + n, db3);
-        }
-        fence_after_sync();
-#pragma unroll 1
-        for (int gidx = q; gidx < 28; gidx += 4) {
-            float v[8];
-            tmem_ld8f(tl + 8 * gidx, v);
-            wait_ld();
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int ci = 8 * gidx + e;        // accumulator column; TMEM lane c = unit j
-                if (ci < 16) { if (ci == 0) atomicAdd(g + N0::T_HID + 128 * 128 + c, v[e]); }
-                else if (ci < 144) atomicAdd(g + N0::T_HID + (ci - 16) * 128 + c, v[e] * sc.inv_sa1);
-                else if (ci < 176) atomicAdd(g + N0::T_W0 + (ci - 144) * 128 + c, v[e] * sc.inv_sa0);
-                else if (ci < 192) { if (ci == 176) atomicAdd(g + N0::T_B0 + c, v[e]); }
-                else if (ci - 192 < 31) atomicAdd(g + N0::T_WL + c * 31 + (ci - 192), v[e] * sc.inv_sa2);
-            }
         }
         // release the MMA warp
         cta_bar();

@@ -146,6 +146,7 @@ def test_one_column_per_cta_kernel_agrees_with_batch_kernel(nfc, gpu_ok, monkeyp
     weights and within the north-star tolerance where the mixed layer's active set flips with rounding (weights x0.3, DESIGN.md
     "Adjoint"), step counts within 5 % (the rejection pattern at the stability limit follows the rounding), and a failed column reported the same way."""
     res = []
+    monkeypatch.setenv("NFC_ADJ_TC", "0")           # the FP32 batch kernel; the tensor-core one has its own file (test_gpu_adjoint_tc.py)
     for small_max in ("0", "100000"):
         monkeypatch.setenv("NFC_ADJ_SMALL_MAX", small_max)
         d, cw, layers, theta, sv, colp, Ttrue, h = _setup(nfc, scale=scale, K=K, B=B)

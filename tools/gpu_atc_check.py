@@ -26,7 +26,12 @@ def run(B, scale, K, n_save=33, oracle=True):
     out = {}
     for tag, env in (("simt", "0"), ("tc", "1")):
         os.environ["NFC_ADJ_TC"] = env
-        h = nfc_b200.Handle(cw, layers, 1, sv)
+        kw = {}
+        if os.environ.get("ATC_ADJ_RTOL"):
+            kw = dict(adjoint_reltol=float(os.environ["ATC_ADJ_RTOL"]), adjoint_abstol=float(os.environ["ATC_ADJ_RTOL"]) * 1e-2)
+        if os.environ.get("ATC_FIXED_DT"):
+            kw = dict(fixed_dt=float(os.environ["ATC_FIXED_DT"]), adjoint_max_steps=int(1.0 / float(os.environ["ATC_FIXED_DT"])) + 8)
+        h = nfc_b200.Handle(cw, layers, 1, sv, **kw)
         h.set_weights(theta)
         r = h.loss_grad(d["T0"], colp, d["glob"], Ttrue)
         out[tag] = (r, h.counters())
@@ -36,7 +41,12 @@ def run(B, scale, K, n_save=33, oracle=True):
     msg += f" | steps simt {ca['adj_steps_accepted']}+{ca['adj_steps_rejected']} tc {cb['adj_steps_accepted']}+{cb['adj_steps_rejected']}"
     msg += f" | status simt {np.unique(a['status']).tolist()} tc {np.unique(b['status']).tolist()} | ms simt {ca['last_adjoint_ms']:.1f} tc {cb['last_adjoint_ms']:.1f}"
     if oracle:
-        o = CO.loss_grad_continuous(d["T0"], theta, cw, layers, colp, d["glob"], sv, Ttrue, nthreads=8)
+        okw = {}
+        if os.environ.get("ATC_ADJ_RTOL"):
+            okw = dict(adj_reltol=float(os.environ["ATC_ADJ_RTOL"]), adj_abstol=float(os.environ["ATC_ADJ_RTOL"]) * 1e-2)
+        if os.environ.get("ATC_FIXED_DT"):
+            okw = dict(fixed_dt=float(os.environ["ATC_FIXED_DT"]))
+        o = CO.loss_grad_continuous(d["T0"], theta, cw, layers, colp, d["glob"], sv, Ttrue, nthreads=8, **okw)
         msg += f" | vs C twin: simt {rel(a['grad'], o['grad']):.2e} tc {rel(b['grad'], o['grad']):.2e}"
         # per-block errors (which accumulator is off, if any)
         N = [("W1", 0, 4096), ("b1", 4096, 4224), ("W2", 4224, 20608), ("b2", 20608, 20736), ("W3", 20736, 24704), ("b3", 24704, 24735)]
