@@ -19,4 +19,4 @@ PIDS=""
 if stale build/nfc_api.o $PKG/csrc/nfc_api.cu $COMMON; then nvcc $FLAGS -c -o build/nfc_api.o "$PKG/csrc/nfc_api.cu" & PIDS="$PIDS $!"; fi
 if stale build/nfc_adjoint_tc.o $PKG/csrc/nfc_adjoint_tc.cu $PKG/csrc/nfc_adjoint_tc.cuh $COMMON; then nvcc $FLAGS -c -o build/nfc_adjoint_tc.o "$PKG/csrc/nfc_adjoint_tc.cu" & PIDS="$PIDS $!"; fi
 for p in $PIDS; do wait $p; done
-nvcc -gencode arch=compute_100a,code=sm_100a --shared -o "$PKG/libnfc_b200.so" build/nfc_api.o build/nfc_adjoint_tc.o
+nvcc -gencode arch=compute_100a,code=sm_100a --shared -ldl -o "$PKG/libnfc_b200.so" build/nfc_api.o build/nfc_adjoint_tc.o

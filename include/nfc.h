@@ -82,6 +82,8 @@ typedef struct nfc_counters {
     float   last_kernel_ms;     /* device time of the last call's main kernel(s), CUDA events */
     float   last_adjoint_ms;
     int64_t rhs_evals;          /* forward RHS evaluations of the last solve (Tsit5: 6 per attempted step + 2 per column) */
+    float   last_allreduce_ms;  /* device time of the [grad; loss] all-reduce of the last nfc_loss_grad (0 without a communicator) */
+    int32_t comm_world;         /* ranks of the attached communicator (1: none) */
 } nfc_counters;
 
 int32_t nfc_create(const nfc_config* cfg, nfc_handle** out);
@@ -108,11 +110,27 @@ int32_t nfc_solve_dev(nfc_handle* h, const float* T0, const float* colp, const f
                       int32_t* naccept, int32_t* nreject, int32_t* status, int64_t B, void* stream);
 /* loss_sum_dev: double[2] = (sum of squared residuals, number of residuals) of this rank's columns;
  * grad_dev: float[n_params] = d(sum of squared residuals / n_total)/dtheta with n_total = n_total_columns*n_save*Nz,
- * so that a SUM all-reduce over ranks yields the global-batch gradient (src/training.jl:47 mean over all sims). */
+ * so that a SUM all-reduce over ranks yields the global-batch gradient (src/training.jl:47 mean over all sims).
+ * With a communicator attached (nfc_comm_init) the all-reduce happens inside the call: loss_sum_dev and grad_dev then hold the GLOBAL
+ * sums / gradient on every rank and n_total_columns is ignored. */
 int32_t nfc_loss_grad_dev(nfc_handle* h, const float* T0, const float* colp, const float* glob, const float* Ttrue,
                           double* loss_sum_dev, float* grad_dev, int32_t* status, int64_t B, int64_t n_total_columns,
                           void* stream);
 int32_t nfc_sync(nfc_handle* h);
+
+/* Multi-GPU (the reference has none): one handle per GPU (one process per GPU, or several handles in one process), columns
+ * sharded over the ranks by the host, NO data-path collective in the forward solve.  A handle with a communicator performs the ONE
+ * collective of a training step itself: nfc_loss_grad / nfc_loss_grad_dev then take this rank's columns and return the loss and the
+ * gradient of the GLOBAL batch on every rank (src/training.jl:45-48,70 over all ranks' simulations) -- one grouped ncclAllReduce of
+ * [dL/dtheta (n_params floats); sum of squared residuals, residual count (2 doubles)] over NVLink, enqueued behind the backward kernel.
+ * NCCL is loaded at run time (dlopen "libnccl.so.2": the library the host process already uses, else the system one).
+ *   nfc_comm_unique_id  rank 0 creates the 128-byte rendezvous id; the HOST ships it to the other ranks (MPI, a file, a socket)
+ *   nfc_comm_init       collective over all ranks: attaches rank `rank` of `world` to the handle (world = 1 is allowed)
+ *   nfc_comm_destroy    detaches (nfc_destroy does it too) */
+#define NFC_UNIQUE_ID_BYTES 128
+int32_t nfc_comm_unique_id(void* id128);
+int32_t nfc_comm_init(nfc_handle* h, const void* id128, int32_t rank, int32_t world);
+int32_t nfc_comm_destroy(nfc_handle* h);
 
 /* SURVEY row f1 -- the embedded path oceananigans_convective_adjustment[_with_neural_network] (src/oceananigans_nn.jl:97-282):
  * n_steps fixed steps of dt: explicit neural-network flux step in physical units (forward Euler stands in for Oceananigans' own

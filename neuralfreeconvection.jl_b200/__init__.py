@@ -4,13 +4,13 @@ The directory name contains a dot, so it is imported through the root-level `nfc
 (`import nfc_b200`), which loads this package with importlib.
 """
 from . import _binding, api, distributed, synthetic
-from ._binding import Handle, NfcError, load, LIB_PATH, EXPORTS, measure_fp32_peak
+from ._binding import Handle, NfcError, load, LIB_PATH, EXPORTS, measure_fp32_peak, comm_unique_id
 from .api import (ADAM, Chain, ColumnDataset, Conv, ConvectiveAdjustmentNDE, ConvectiveAdjustmentNDEParameters, Dense,
                   FreeConvectionNDE, FreeConvectionNDEParameters, Tsit5, RKC2, ROCK4, ZeroMeanUnitVarianceScaling, destructure,
                   named_chain, compute_nde_solution_history, load_history, oceananigans_convective_adjustment, oceananigans_convective_adjustment_with_neural_network, solve_nde,
                   train_neural_differential_equation)
 
-__all__ = ["measure_fp32_peak", "Handle", "NfcError", "load", "LIB_PATH", "EXPORTS", "ADAM", "Chain", "ColumnDataset", "Conv",
+__all__ = ["measure_fp32_peak", "comm_unique_id", "Handle", "NfcError", "load", "LIB_PATH", "EXPORTS", "ADAM", "Chain", "ColumnDataset", "Conv",
            "ConvectiveAdjustmentNDE", "ConvectiveAdjustmentNDEParameters", "Dense", "FreeConvectionNDE",
            "FreeConvectionNDEParameters", "Tsit5", "RKC2", "ROCK4", "ZeroMeanUnitVarianceScaling", "destructure", "named_chain",
            "solve_nde", "train_neural_differential_equation", "oceananigans_convective_adjustment",

@@ -14,7 +14,7 @@ NFC_MAX_LAYERS = 8
 EXPORTS = ["nfc_create", "nfc_destroy", "nfc_last_error", "nfc_n_params", "nfc_set_weights", "nfc_set_saveat",
            "nfc_get_counters", "nfc_rhs", "nfc_solve", "nfc_diagnose_flux", "nfc_loss_grad", "nfc_rhs_dev",
            "nfc_solve_dev", "nfc_loss_grad_dev", "nfc_sync", "nfc_measure_fp32_peak", "nfc_get_adjoint_steps", "nfc_embedded_solve",
-           "nfc_solve_ensemble"]
+           "nfc_solve_ensemble", "nfc_comm_unique_id", "nfc_comm_init", "nfc_comm_destroy"]
 
 
 class NfcConfig(C.Structure):
@@ -29,7 +29,8 @@ class NfcConfig(C.Structure):
 class NfcCounters(C.Structure):
     _fields_ = [("columns", C.c_int64), ("steps_accepted", C.c_int64), ("steps_rejected", C.c_int64),
                 ("adj_steps_accepted", C.c_int64), ("adj_steps_rejected", C.c_int64), ("kernel_launches", C.c_int64),
-                ("last_kernel_ms", C.c_float), ("last_adjoint_ms", C.c_float), ("rhs_evals", C.c_int64)]
+                ("last_kernel_ms", C.c_float), ("last_adjoint_ms", C.c_float), ("rhs_evals", C.c_int64),
+                ("last_allreduce_ms", C.c_float), ("comm_world", C.c_int32)]
 
 
 _lib = None
@@ -65,6 +66,9 @@ def load():
     lib.nfc_embedded_solve.argtypes = [vp, fp, fp, fp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_int32, fp, C.c_int64]
     lib.nfc_get_adjoint_steps.argtypes = [vp, ip, C.c_int64]
     lib.nfc_measure_fp32_peak.argtypes = [C.c_int32, C.c_float, dp]
+    lib.nfc_comm_unique_id.argtypes = [vp]
+    lib.nfc_comm_init.argtypes = [vp, vp, C.c_int32, C.c_int32]
+    lib.nfc_comm_destroy.argtypes = [vp]
     for name in EXPORTS:
         if name not in ("nfc_last_error", "nfc_n_params"):
             getattr(lib, name).restype = C.c_int32
@@ -96,6 +100,18 @@ def measure_fp32_peak(device=0, ms_target=50.0):
     if rc != 0:
         raise NfcError(f"nfc_measure_fp32_peak failed ({rc}): {load().nfc_last_error(None).decode()}")
     return out.value
+
+
+NFC_UNIQUE_ID_BYTES = 128
+
+
+def comm_unique_id() -> bytes:
+    """nfc_comm_unique_id: rank 0 creates the NCCL rendezvous id; the host ships these 128 bytes to the other ranks."""
+    buf = C.create_string_buffer(NFC_UNIQUE_ID_BYTES)
+    rc = load().nfc_comm_unique_id(buf)
+    if rc != 0:
+        raise NfcError(f"nfc_comm_unique_id failed ({rc}): {load().nfc_last_error(None).decode()}")
+    return buf.raw
 
 
 class Handle:
@@ -209,7 +225,7 @@ class Handle:
         T0, colp, glob, Ttrue = _f32(T0), _f32(colp), _f32(glob), _f32(Ttrue)
         B = T0.shape[0]
         grad = np.zeros(self.n_params, dtype=np.float32)
-        st = np.zeros(B, dtype=np.int32)
+        st = np.zeros(max(B, 1), dtype=np.int32)[:B]
         loss = C.c_double(0.0)
         self._check(self.lib.nfc_loss_grad(self.h, _fp(T0), _fp(colp), _fp(glob), _fp(Ttrue), C.byref(loss), _fp(grad),
                                            _ip(st), B), "nfc_loss_grad")
@@ -257,3 +273,13 @@ class Handle:
 
     def sync(self):
         self._check(self.lib.nfc_sync(self.h), "nfc_sync")
+
+    def comm_init(self, unique_id: bytes, rank: int, world: int):
+        """nfc_comm_init (collective): from now on loss_grad / loss_grad_dev return the loss and gradient of the GLOBAL batch."""
+        if len(unique_id) != NFC_UNIQUE_ID_BYTES:
+            raise ValueError("the rendezvous id has 128 bytes")
+        buf = C.create_string_buffer(unique_id, NFC_UNIQUE_ID_BYTES)
+        self._check(self.lib.nfc_comm_init(self.h, buf, rank, world), "nfc_comm_init")
+
+    def comm_destroy(self):
+        self._check(self.lib.nfc_comm_destroy(self.h), "nfc_comm_destroy")

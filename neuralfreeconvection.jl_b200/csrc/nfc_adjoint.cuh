@@ -607,8 +607,9 @@ int adjoint_loss_grad(nfc_handle* h, const float* T0, const float* colp, float p
     NFC_CUDA(h, cudaMemsetAsync(loss_sum_dev, 0, 2 * sizeof(double), st));
     NFC_CUDA(h, h->a_gacc.ensure((size_t)grid * h->n_params));
     NFC_CUDA(h, cudaMemsetAsync(h->a_gacc.p, 0, sizeof(float) * (size_t)grid * h->n_params, st));
-    if (B == 0) {
+    if (B == 0) {          // a rank without columns still takes part in the collective
         NFC_CUDA(h, cudaMemsetAsync(grad_dev, 0, sizeof(float) * h->n_params, st));
+        if (h->nccl_comm) return comm_allreduce_grad(h, grad_dev, loss_sum_dev, st);
         return 0;
     }
     // chunk the batch so that tape + residuals stay inside the scratch budget (default 48 GiB of the 180 GB, NFC_TAPE_GIB overrides)
@@ -670,10 +671,12 @@ int adjoint_loss_grad(nfc_handle* h, const float* T0, const float* colp, float p
         h->last_launches += 1;
         first = false;
     }
-    const double ntot = (double)n_total_columns * n_save * NZ;
+    // with a communicator the sums stay un-normalised until the all-reduce has produced the global residual count
+    const double ntot = h->nccl_comm ? 1.0 : (double)n_total_columns * n_save * NZ;
     grad_reduce_kernel<<<((int)h->n_params + 255) / 256, 256, 0, st>>>(h->a_gacc.p, grid, (int)h->n_params, 2.0 / ntot, grad_dev);
     set_loss_count_kernel<<<1, 1, 0, st>>>(loss_sum_dev, (double)B * n_save * NZ);
     NFC_CUDA(h, cudaGetLastError());
+    if (h->nccl_comm) { if (int rc = comm_allreduce_grad(h, grad_dev, loss_sum_dev, st)) return rc; }
     NFC_CUDA(h, cudaEventRecord(h->ev[3], st));
     h->ev_adj_valid = true;
     h->a_adjhist_valid = true;

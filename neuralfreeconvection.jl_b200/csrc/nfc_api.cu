@@ -1,5 +1,6 @@
 // nfc_api.cu -- the C ABI of libnfc_b200.so (declared in include/nfc.h).  sm_100a only, no CPU fallback.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cmath>
@@ -408,6 +409,71 @@ __global__ void __launch_bounds__(256) fma_peak_kernel(float* out, int iters, fl
     if (s == 123.456f) out[0] = s;   // never true; keeps the chains alive
 }
 
+
+// ------------------------------------------ NCCL, loaded at run time ------------------------------------------
+struct NcclId { char internal[NFC_UNIQUE_ID_BYTES]; };       // ncclUniqueId (passed by value to ncclCommInitRank)
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    std::string err;
+};
+NcclApi& nccl_api() {
+    static NcclApi a;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        // RTLD_NOLOAD first: the copy the host process (e.g. torch) already loaded; else the system library
+        a.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!a.lib) a.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!a.lib) a.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (!a.lib) { a.err = std::string("cannot load libnccl.so.2: ") + dlerror(); return; }
+        auto sym = [&](const char* n) { void* p = dlsym(a.lib, n); if (!p) a.err = std::string("libnccl lacks ") + n; return p; };
+        a.GetUniqueId = (int (*)(void*))sym("ncclGetUniqueId");
+        a.CommInitRank = (int (*)(void**, int, NcclId, int))sym("ncclCommInitRank");
+        a.CommDestroy = (int (*)(void*))sym("ncclCommDestroy");
+        a.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))sym("ncclAllReduce");
+        a.GroupStart = (int (*)())sym("ncclGroupStart");
+        a.GroupEnd = (int (*)())sym("ncclGroupEnd");
+        a.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+    });
+    return a;
+}
+constexpr int NCCL_FLOAT32 = 7, NCCL_FLOAT64 = 8, NCCL_SUM = 0;       // nccl.h: ncclDataType_t / ncclRedOp_t
+#define NFC_NCCL(h, call)                                                                                         \
+    do {                                                                                                          \
+        int r__ = (call);                                                                                         \
+        if (r__ != 0) return nfc::fail(h, -12, "NCCL error %d at %s:%d (%s)", r__, __FILE__, __LINE__, nccl_api().GetErrorString ? nccl_api().GetErrorString(r__) : "?"); \
+    } while (0)
+
+__global__ void grad_normalise_kernel(float* __restrict__ grad, const double* __restrict__ loss_sum, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) grad[i] = (float)((double)grad[i] / loss_sum[1]);     // grad holds 2 * sum over all ranks; loss_sum[1] = global residual count
+}
+}  // namespace
+
+namespace nfc {
+int comm_allreduce_grad(nfc_handle* h, float* grad_dev, double* loss_sum_dev, cudaStream_t st) {
+    NcclApi& a = nccl_api();
+    if (!a.err.empty()) return fail(h, -12, "%s", a.err.c_str());
+    NFC_CUDA(h, cudaEventRecord(h->ev_ar[0], st));
+    NFC_NCCL(h, a.GroupStart());
+    NFC_NCCL(h, a.AllReduce(grad_dev, grad_dev, (size_t)h->n_params, NCCL_FLOAT32, NCCL_SUM, h->nccl_comm, st));
+    NFC_NCCL(h, a.AllReduce(loss_sum_dev, loss_sum_dev, 2, NCCL_FLOAT64, NCCL_SUM, h->nccl_comm, st));
+    NFC_NCCL(h, a.GroupEnd());
+    NFC_CUDA(h, cudaEventRecord(h->ev_ar[1], st));
+    grad_normalise_kernel<<<((int)h->n_params + 255) / 256, 256, 0, st>>>(grad_dev, loss_sum_dev, (int)h->n_params);
+    NFC_CUDA(h, cudaGetLastError());
+    h->last_launches += 2;
+    return 0;
+}
+}  // namespace nfc
+
 extern "C" {
 
 int32_t nfc_measure_fp32_peak(int32_t device, float ms_target, double* tflops) {
@@ -524,6 +590,8 @@ int32_t nfc_destroy(nfc_handle* h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->nccl_comm) nfc_comm_destroy(h);
+    for (auto& ev : h->ev_ar) if (ev) cudaEventDestroy(ev);
     h->d_work.release(); h->d_order.release(); h->d_hist.release(); h->d_wimg.release(); h->d_theta.release(); h->d_wpack.release(); h->d_saveat.release(); h->d_k1.release(); h->d_dt.release(); h->d_counters.release();
     h->e_theta.release(); h->e_wpack.release(); h->d_rkctab.release(); h->s_nfe.release();
     h->s_T0.release(); h->s_colp.release(); h->s_out.release(); h->s_true.release(); h->s_grad.release();
@@ -611,6 +679,40 @@ int32_t nfc_get_adjoint_steps(nfc_handle* h, int32_t* out, int64_t n) {
     return 0;
 }
 
+int32_t nfc_comm_unique_id(void* id128) {
+    if (!id128) return -1;
+    NcclApi& a = nccl_api();
+    if (!a.err.empty()) return fail(nullptr, -12, "%s", a.err.c_str());
+    NFC_NCCL(nullptr, a.GetUniqueId(id128));
+    return 0;
+}
+
+int32_t nfc_comm_init(nfc_handle* h, const void* id128, int32_t rank, int32_t world) {
+    if (!h || !id128) return -1;
+    if (world < 1 || rank < 0 || rank >= world) return fail(h, -2, "bad rank %d of %d", rank, world);
+    if (h->nccl_comm) return fail(h, -2, "the handle already has a communicator");
+    NcclApi& a = nccl_api();
+    if (!a.err.empty()) return fail(h, -12, "%s", a.err.c_str());
+    NFC_CUDA(h, cudaSetDevice(h->device));
+    NcclId id;
+    memcpy(id.internal, id128, NFC_UNIQUE_ID_BYTES);
+    void* comm = nullptr;
+    NFC_NCCL(h, a.CommInitRank(&comm, world, id, rank));
+    for (auto& ev : h->ev_ar) if (!ev) NFC_CUDA(h, cudaEventCreate(&ev));
+    h->nccl_comm = comm; h->comm_rank = rank; h->comm_world = world;
+    return 0;
+}
+
+int32_t nfc_comm_destroy(nfc_handle* h) {
+    if (!h) return -1;
+    if (!h->nccl_comm) return 0;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    NFC_NCCL(h, nccl_api().CommDestroy(h->nccl_comm));
+    h->nccl_comm = nullptr; h->comm_rank = 0; h->comm_world = 1;
+    return 0;
+}
+
 int32_t nfc_sync(nfc_handle* h) {
     if (!h) return -1;
     NFC_CUDA(h, cudaSetDevice(h->device));
@@ -635,6 +737,9 @@ int32_t nfc_get_counters(const nfc_handle* hc, nfc_counters* out) {
     out->rhs_evals = h->cfg.alg == NFC_ALG_RKC2 ? (int64_t)c[rkc::CTR_NFE] : 6 * (out->steps_accepted + out->steps_rejected) + 2 * out->columns;
     if (h->ev_fwd_valid) cudaEventElapsedTime(&out->last_kernel_ms, h->ev[0], h->ev[1]);
     if (h->ev_adj_valid) cudaEventElapsedTime(&out->last_adjoint_ms, h->ev[2], h->ev[3]);
+    if (h->nccl_comm && h->ev_adj_valid) cudaEventElapsedTime(&h->last_allreduce_ms, h->ev_ar[0], h->ev_ar[1]);
+    out->last_allreduce_ms = h->nccl_comm ? h->last_allreduce_ms : 0.f;
+    out->comm_world = h->comm_world;
     return 0;
 }
 
@@ -823,19 +928,21 @@ int32_t nfc_embedded_solve(nfc_handle* h, const float* T0, const float* heat_flu
 int32_t nfc_loss_grad(nfc_handle* h, const float* T0, const float* colp, const float* glob, const float* Ttrue, double* loss, float* grad_theta,
                       int32_t* status, int64_t B) {
     if (int rc = check_ready(h, B)) return rc;
-    if (B == 0) return fail(h, -2, "loss over zero columns is undefined");
-    if (!T0 || !colp || !glob || !Ttrue || !loss || !grad_theta) return fail(h, -1, "null argument");
+    if (B == 0 && !h->nccl_comm) return fail(h, -2, "loss over zero columns is undefined");
+    if ((B > 0 && (!T0 || !colp || !Ttrue)) || !glob || !loss || !grad_theta) return fail(h, -1, "null argument");
     if (h->cfg.alg != NFC_ALG_TSIT5) return fail(h, -3, "nfc_loss_grad needs a Tsit5 handle (the adjoint tape is Tsit5 dense output)");
     const size_t ntraj = (size_t)B * h->cfg.n_save * NZ;
-    NFC_CUDA(h, h->s_T0.ensure((size_t)B * NZ));
-    NFC_CUDA(h, h->s_colp.ensure((size_t)B * 3));
-    NFC_CUDA(h, h->s_true.ensure(ntraj));
+    NFC_CUDA(h, h->s_T0.ensure((size_t)std::max<int64_t>(B, 1) * NZ));
+    NFC_CUDA(h, h->s_colp.ensure((size_t)std::max<int64_t>(B, 1) * 3));
+    NFC_CUDA(h, h->s_true.ensure(std::max<size_t>(ntraj, 1)));
     NFC_CUDA(h, h->s_grad.ensure(h->n_params));
     NFC_CUDA(h, h->s_loss.ensure(2));
-    NFC_CUDA(h, h->s_status.ensure(B));
-    NFC_CUDA(h, cudaMemcpyAsync(h->s_T0.p, T0, sizeof(float) * B * NZ, cudaMemcpyHostToDevice, h->stream));
-    NFC_CUDA(h, cudaMemcpyAsync(h->s_colp.p, colp, sizeof(float) * B * 3, cudaMemcpyHostToDevice, h->stream));
-    NFC_CUDA(h, cudaMemcpyAsync(h->s_true.p, Ttrue, sizeof(float) * ntraj, cudaMemcpyHostToDevice, h->stream));
+    NFC_CUDA(h, h->s_status.ensure(std::max<int64_t>(B, 1)));
+    if (B > 0) {
+        NFC_CUDA(h, cudaMemcpyAsync(h->s_T0.p, T0, sizeof(float) * B * NZ, cudaMemcpyHostToDevice, h->stream));
+        NFC_CUDA(h, cudaMemcpyAsync(h->s_colp.p, colp, sizeof(float) * B * 3, cudaMemcpyHostToDevice, h->stream));
+        NFC_CUDA(h, cudaMemcpyAsync(h->s_true.p, Ttrue, sizeof(float) * ntraj, cudaMemcpyHostToDevice, h->stream));
+    }
     h->last_launches = 0;
     int rc = [&]() -> int {
         NFC_DISPATCH(h, do_loss_grad, h, h->s_T0.p, h->s_colp.p, prefactor(glob), h->s_true.p, h->s_loss.p, h->s_grad.p, h->s_status.p, B, B, h->stream);
@@ -844,8 +951,9 @@ int32_t nfc_loss_grad(nfc_handle* h, const float* T0, const float* colp, const f
     double ls[2];
     NFC_CUDA(h, cudaMemcpyAsync(ls, h->s_loss.p, sizeof ls, cudaMemcpyDeviceToHost, h->stream));
     NFC_CUDA(h, cudaMemcpyAsync(grad_theta, h->s_grad.p, sizeof(float) * h->n_params, cudaMemcpyDeviceToHost, h->stream));
-    if (status) NFC_CUDA(h, cudaMemcpyAsync(status, h->s_status.p, sizeof(int) * B, cudaMemcpyDeviceToHost, h->stream));
+    if (status && B > 0) NFC_CUDA(h, cudaMemcpyAsync(status, h->s_status.p, sizeof(int) * B, cudaMemcpyDeviceToHost, h->stream));
     NFC_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (h->nccl_comm) cudaEventElapsedTime(&h->last_allreduce_ms, h->ev_ar[0], h->ev_ar[1]);
     *loss = ls[0] / ls[1];
     return 0;
 }

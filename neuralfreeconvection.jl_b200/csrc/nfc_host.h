@@ -44,6 +44,8 @@ struct AdjParams;
 
 struct nfc_handle;
 namespace nfc {
+// [grad; loss sums] all-reduce over the handle's communicator + normalisation by the global residual count (nfc_api.cu)
+int comm_allreduce_grad(nfc_handle* h, float* grad_dev, double* loss_sum_dev, cudaStream_t st);
 int adjoint_tc_setup(nfc_handle* h);
 int adjoint_tc_launch(nfc_handle* h, const AdjParams& A, const atc::AtcScales& sc, int64_t nb, cudaStream_t st);
 }  // namespace nfc
@@ -90,6 +92,11 @@ struct nfc_handle {
     int64_t a_adjhist_B = -1;      // batch size that history belongs to; it is the next call's longest-first key
     bool a_adjhist_valid = false;
     nfc::DevBuf<double> a_gsum;
+    // multi-GPU: NCCL communicator attached by nfc_comm_init (null: single GPU); the all-reduce of nfc_loss_grad runs on it
+    void* nccl_comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
+    float last_allreduce_ms = 0.f;
+    cudaEvent_t ev_ar[2] = {nullptr, nullptr};
     int64_t last_columns = 0, last_launches = 0;
     std::string err;
 };
