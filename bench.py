@@ -9,6 +9,9 @@ A "step" is one pass of the hot path over one batch: the batched Tsit5 solve of 
 129 save points = the training `iterations = 1:9:1153`), weights random-init as the reference (Glorot x 1e-5).
 One column-step = one attempted Tsit5 step of one column (6 new RHS evaluations) -- SURVEY.md 8d.
 Columns shard across ranks with no data-path collective (weak scaling: 65,536 columns per GPU).
+Next to the headline the line carries BASELINE's second metric and config 4: `adjoint` (seconds per loss+gradient epoch) and `config4`
+(1,048,576 columns sharded over the N ranks: forward solve, then loss + gradient with the NCCL all-reduce of [grad; loss] INSIDE the
+timed region -- the collective runs inside nfc_loss_grad on the handle's own communicator, include/nfc.h nfc_comm_init).
 """
 import argparse
 import json
@@ -28,6 +31,8 @@ UNIT = "column-steps/s"
 COLUMNS_PER_GPU = 65536
 N_SAVE = 129
 FLOPS_PER_COLUMN_STEP = 6 * 2 * (32 * 128 + 128 * 128 + 128 * 31)      # 293,376 (default Chain)
+FLOPS_PER_ADJOINT_COLUMN_STEP = 3 * FLOPS_PER_COLUMN_STEP               # 880,128 (the kernel runs 7 stages: no FSAL backwards)
+CONFIG4_COLUMNS = 1048576
 WORKLOAD = ("config2: 65536 columns/GPU, ConvectiveAdjustmentNDE K_CA=2, dense-default Chain (24735 params, Glorot x1e-5), "
             "Tsit5 reltol 1e-4 abstol 1e-6, saveat 129 points on [0,1]")
 
@@ -78,6 +83,25 @@ class ClockSampler:
         pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
                 "power_w_max": max(pw) if pw else None, "samples": len(sm)}
+
+
+def bind_to_gpu_numa_node(index):
+    """Pin this rank to the CPUs next to its GPU (the host-buffer path copies 1 GB per step through that root complex)."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(index).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(index), "pci_domain_id", 0)
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:00.0/local_cpulist"
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{min(cpus)}-{max(cpus)} ({len(cpus)} cpus, {path})"
+    except Exception as e:      # best effort
+        return f"unchanged ({type(e).__name__})"
+    return "unchanged"
 
 
 def cpu_reference_run(steps, warmup, sample_columns, nthreads):
@@ -142,6 +166,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     warmup = max(args.warmup, 3)
     B = args.columns
+    affinity = bind_to_gpu_numa_node(local_rank)
 
     d, cw, layers, theta, sv = make_inputs(B, seed=1 + rank)
     h = nfc_b200.Handle(cw, layers, 1, sv, device=local_rank)
@@ -210,47 +235,89 @@ def main():
     h2d = hT0.numel() * 4 + hcolp.numel() * 4
     d2h = hout.numel() * 4 + 3 * B * 4
 
-    if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return 0
-
-    # ---------------- roofline of the dominant kernel (solve_kernel) ----------------
+    # ---------------- roofline of the dominant kernel (solve_tc_kernel) ----------------
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except OSError:
         pass
-    fp32_peak = nfc_b200.measure_fp32_peak(local_rank, 50.0)                   # TFLOP/s, measured on this GPU now
-    achieved = FLOPS_PER_COLUMN_STEP * steps_per_pass / (kernel_ms * 1e-3) / 1e12   # algorithmic (FP32-equivalent) TFLOP/s
-    alg_bytes = B * (128 + 12 + N_SAVE * 128 + 12)
+    bf16_peak = peaks.get("bf16_tflops", 1590.0)
     use_tc = os.environ.get("NFC_TC", "1") != "0"
-    hbm = {"achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs", 6650.0),
-           "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback", "algorithmic_bytes": alg_bytes}
-    if use_tc:
-        # tensor-core path: every fp32 product is three fp16 (default, 2-way split) or six bf16 (3-way split) tcgen05 MMAs, so the
-        # ceiling for FP32-faithful work is the measured dense 16-bit peak / 3 (or / 6); burst figure: the kernel is timed alone
-        bf16_peak = peaks.get("bf16_tflops", 1590.0)
-        nsplit = 6.0 if os.environ.get("NFC_TC_SPLIT", "fp16") == "bf16" else 3.0      # MMAs per fp32 product: BF16x3 -> 6, FP16x2 (default) -> 3
-        roofline = {"bound": "tensor", "achieved": achieved, "peak": bf16_peak / nsplit, "unit": "TFLOP/s", "frac": achieved / (bf16_peak / nsplit),
-                    "traffic": 1.06e9, "traffic_source": "ncu dram__bytes r+w per launch, profiles/r01_solve_tc_kernel_ncu.txt",
-                    "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1590") +
-                                   (" / 6 MMAs per fp32 product (BF16x3 split)" if nsplit == 6.0 else " / 3 MMAs per fp32 product (FP16x2 split; fp16 and bf16 MMAs run at the same rate)"),
-                    "tensor_tflops_16bit": nsplit * achieved, "fp32_simt_peak_measured": fp32_peak, "frac_of_fp32_simt_peak": achieved / fp32_peak,
-                    "flops_per_column_step": FLOPS_PER_COLUMN_STEP, "kernel": "solve_tc_kernel (+ rhs_init_kernel, scheduler)", "kernel_ms": kernel_ms,
-                    "hbm": hbm}
-    else:
-        roofline = {"bound": "fp32_fma", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": 1.06e9,
-                    "peak_source": "measured in this run: pure-FFMA kernel in libnfc_b200 (nominal 148x128x2x1.965GHz = 74.4)",
-                    "flops_per_column_step": FLOPS_PER_COLUMN_STEP, "kernel": "solve_kernel (+ rhs_init_kernel)", "kernel_ms": kernel_ms, "hbm": hbm}
+    roofline = fp32_peak = None
+    if rank == 0:
+        fp32_peak = nfc_b200.measure_fp32_peak(local_rank, 50.0)                   # TFLOP/s, measured on this GPU now
+        achieved = FLOPS_PER_COLUMN_STEP * steps_per_pass / (kernel_ms * 1e-3) / 1e12   # algorithmic (FP32-equivalent) TFLOP/s
+        alg_bytes = B * (128 + 12 + N_SAVE * 128 + 12)
+        hbm = {"achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs", 6650.0),
+               "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback", "algorithmic_bytes": alg_bytes}
+        # DRAM traffic of the dominant kernel: from the ncu capture of the SAME kernel build (tools/ncu_traffic.py writes the file), else null
+        traffic, traffic_source = None, "no ncu capture of this build under profiles/"
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r02_solve_tc_traffic.json")))
+            traffic, traffic_source = tj["dram_bytes_per_launch"], tj["source"]
+        except (OSError, KeyError, ValueError):
+            pass
+        if use_tc:
+            # tensor-core path: every fp32 product is three fp16 (default, 2-way split) or six bf16 (3-way split) tcgen05 MMAs, so the
+            # ceiling for FP32-faithful work is the measured dense 16-bit peak / 3 (or / 6); burst figure: the kernel is timed alone
+            nsplit = 6.0 if os.environ.get("NFC_TC_SPLIT", "fp16") == "bf16" else 3.0      # MMAs per fp32 product: BF16x3 -> 6, FP16x2 (default) -> 3
+            roofline = {"bound": "tensor", "achieved": achieved, "peak": bf16_peak / nsplit, "unit": "TFLOP/s", "frac": achieved / (bf16_peak / nsplit),
+                        "traffic": traffic, "traffic_source": traffic_source,
+                        "peak_source": ("MEASURED_PEAKS.json bf16_tflops (burst)" if peaks else "fallback 1590") +
+                                       (" / 6 MMAs per fp32 product (BF16x3 split)" if nsplit == 6.0 else " / 3 MMAs per fp32 product (FP16x2 split; fp16 and bf16 MMAs run at the same rate)"),
+                        "tensor_tflops_16bit": nsplit * achieved, "fp32_simt_peak_measured": fp32_peak, "frac_of_fp32_simt_peak": achieved / fp32_peak,
+                        "flops_per_column_step": FLOPS_PER_COLUMN_STEP, "kernel": "solve_tc_kernel (+ rhs_init_kernel, scheduler)", "kernel_ms": kernel_ms,
+                        "hbm": hbm}
+        else:
+            roofline = {"bound": "fp32_fma", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak, "traffic": traffic,
+                        "peak_source": "measured in this run: pure-FFMA kernel in libnfc_b200 (nominal 148x128x2x1.965GHz = 74.4)",
+                        "flops_per_column_step": FLOPS_PER_COLUMN_STEP, "kernel": "solve_kernel (+ rhs_init_kernel)", "kernel_ms": kernel_ms, "hbm": hbm}
 
-    # ---------------- second BASELINE metric: adjoint gradient, seconds per epoch ----------------
-    # epoch = one loss + gradient over the batch (src/training.jl:45-48,70): (a) BASELINE config 3, the 9 training simulations;
-    # (b) the config-2 batch itself (65536 columns): the throughput regime.  (A 16384-column batch is bound by the critical path of
-    # its longest backward solve -- one column with 1100 backward steps against a median of 350 -- not by throughput.)
-    # flops_per_adjoint_column_step = 6*3*2*sum(in*out) = 880128 (the kernel actually runs 7 stages: no FSAL backwards)
+    # ---------------- the schedule does not flatter the number: a handle without step history, and the first call of a fresh handle ----------------
+    cold = None
+    if rank == 0:
+        try:
+            os.environ["NFC_SCHED"] = "0"
+            h2 = nfc_b200.Handle(cw, layers, 1, sv, device=local_rank)
+            del os.environ["NFC_SCHED"]
+            h2.set_weights(theta)
+            torch.cuda.synchronize()
+            e0.record()
+            h2.solve_dev(T0, colp, glob, Tout, na, nr, st, stream=stream)          # first call of a fresh handle: scratch allocations inside
+            e1.record()
+            torch.cuda.synchronize()
+            first_ms = e0.elapsed_time(e1)
+            for _ in range(2):
+                h2.solve_dev(T0, colp, glob, Tout, na, nr, st, stream=stream)
+            torch.cuda.synchronize()
+            e0.record()
+            h2.solve_dev(T0, colp, glob, Tout, na, nr, st, stream=stream)
+            e1.record()
+            torch.cuda.synchronize()
+            ns_ms = e0.elapsed_time(e1)
+            cold = {"first_call_of_a_fresh_handle": {"ms": first_ms, "value": steps_per_pass / (first_ms * 1e-3)},
+                    "no_longest_first_schedule": {"ms": ns_ms, "value": steps_per_pass / (ns_ms * 1e-3), "how": "NFC_SCHED=0: columns served in input order"},
+                    "unit": UNIT}
+            h2.close()
+        except Exception as e:
+            cold = {"error": str(e)}
+
+    # ---------------- second BASELINE metric: adjoint gradient, seconds per epoch (rank 0, one GPU) ----------------
+    # epoch = one loss + gradient over the batch (src/training.jl:45-48,70): (a) BASELINE config 3, the 9 training simulations (one column per
+    # CTA, FP32); (b) the config-2 batch (65536 columns): the tensor-core backward kernel (csrc/nfc_adjoint_tc.cuh).
+    def adjoint_roofline(ca, ms):
+        tf_ = (ca["adj_steps_accepted"] + ca["adj_steps_rejected"]) * FLOPS_PER_ADJOINT_COLUMN_STEP / (ms * 1e-3) / 1e12
+        if use_tc and os.environ.get("NFC_ADJ_TC", "1") != "0":
+            return {"bound": "tensor", "achieved": tf_, "peak": bf16_peak / 3.0, "unit": "TFLOP/s", "frac": tf_ / (bf16_peak / 3.0),
+                    "flops_per_adjoint_column_step": FLOPS_PER_ADJOINT_COLUMN_STEP, "frac_of_fp32_simt_peak": tf_ / fp32_peak if fp32_peak else None,
+                    "kernel": "adjoint_tc_kernel (tcgen05: forward recompute + transposed chain FP16x2, dW contraction BF16) + the tensor-core RECORD "
+                              "forward pass, both inside device_ms",
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst) / 3 MMAs per fp32 product" if peaks else "fallback 1590 / 3"}
+        return {"bound": "fp32_fma", "achieved": tf_, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf_ / fp32_peak if fp32_peak else None,
+                "flops_per_adjoint_column_step": FLOPS_PER_ADJOINT_COLUMN_STEP, "kernel": "adjoint_kernel (FP32 SIMT) + RECORD forward pass"}
+
     adjoint = None
-    if world == 1:
+    if rank == 0:
         try:
             syn = nfc_b200.synthetic
             adjoint = {}
@@ -270,11 +337,10 @@ def main():
                 ca = h.counters()
                 adjoint[tag] = {"sec_per_epoch": dt_, "columns": nb, "fwd_column_steps": ca["steps_accepted"] + ca["steps_rejected"],
                                 "adjoint_column_steps": ca["adj_steps_accepted"] + ca["adj_steps_rejected"], "device_ms": ca["last_adjoint_ms"],
+                                "record_pass_ms": ca["last_kernel_ms"], "bad_status": int((sta != 0).sum()),
                                 "adjoint_column_steps_per_sec": (ca["adj_steps_accepted"] + ca["adj_steps_rejected"]) / max(ca["last_adjoint_ms"] * 1e-3, 1e-9)}
-                if nb >= 4096:
-                    tf_ = adjoint[tag]["adjoint_column_steps_per_sec"] * 880128 / 1e12
-                    adjoint[tag]["roofline"] = {"bound": "fp32_fma", "achieved": tf_, "peak": fp32_peak, "unit": "TFLOP/s", "frac": tf_ / fp32_peak,
-                                                "flops_per_adjoint_column_step": 880128, "kernel": "adjoint_kernel (+ the tensor-core RECORD forward pass, both inside device_ms)"}
+                if nb >= 8192:
+                    adjoint[tag]["roofline"] = adjoint_roofline(ca, ca["last_adjoint_ms"])
                 del Tt
                 if tag == "config3_9sims" and not args.no_cpu_baseline:
                     # the CPU twin of the same continuous adjoint (oracle/nde_oracle.c, OpenMP over the 9 simulations) on the box's cores
@@ -291,44 +357,95 @@ def main():
         except Exception as e:                                     # the forward metric must not die with the extra one
             adjoint = {"error": str(e)}
 
-    # ---------------- BASELINE config 4's forward half on this GPU: 1,048,576 columns (0.25 degree ocean), 129 saves ----------------
-    # (the throughput regime: every one of the 148 x 256 column slots of the two-tile kernel gets ~28 columns; config 2's 65,536 columns
-    #  give it 1.7 and are bound by slot quantisation: 135-step columns, each slot runs them back to back)
-    large_batch = None
-    if world == 1 and use_tc and not args.no_large_batch:
+    # ---------------- BASELINE config 4: 1,048,576 columns (0.25 degree ocean), 129 saves, sharded over the N ranks (STRONG scaling) ----------------
+    # forward solve (no collective), then loss + gradient with the all-reduce of [grad; loss sums] inside the timed region: the collective runs
+    # inside nfc_loss_grad_dev on the handle's own NCCL communicator (torch.distributed only ships the 128-byte rendezvous id).
+    config4 = None
+    if use_tc and not args.no_large_batch:
         try:
             del Tout, hout
-            BL = 1048576
-            dl = nfc_b200.synthetic.make_columns("ocean", B=BL, seed=2, K_CA=2.0)
-            lT0, lcolp = (torch.from_numpy(dl[k]).to(dev) for k in ("T0", "colp"))
-            lout = torch.empty((BL, N_SAVE, 32), device=dev, dtype=torch.float32)
-            lst = torch.zeros(BL, dtype=torch.int32, device=dev)
+            lo, hi = nfc_b200.distributed.shard_range(CONFIG4_COLUMNS, rank, world)
+            nb = hi - lo
+            # every rank generates the same 1M-column set in pieces and keeps its shard (identical columns whatever N is)
+            dl = nfc_b200.synthetic.make_columns("ocean", B=CONFIG4_COLUMNS, seed=2, K_CA=2.0)
+            lT0, lcolp = (torch.from_numpy(np.ascontiguousarray(dl[k][lo:hi])).to(dev) for k in ("T0", "colp"))
+            lglob = dl["glob"]
+            del dl
+            lout = torch.empty((nb, N_SAVE, 32), device=dev, dtype=torch.float32)
+            lst = torch.zeros(nb, dtype=torch.int32, device=dev)
             for _ in range(2):
-                h.solve_dev(lT0, lcolp, dl["glob"], lout, None, None, lst, stream=stream)
-            torch.cuda.synchronize()
+                h.solve_dev(lT0, lcolp, lglob, lout, None, None, lst, stream=stream)
+            barrier()
             e0.record()
-            h.solve_dev(lT0, lcolp, dl["glob"], lout, None, None, lst, stream=stream)
+            h.solve_dev(lT0, lcolp, lglob, lout, None, None, lst, stream=stream)
             e1.record()
-            torch.cuda.synchronize()
+            barrier()
             cl = h.counters()
-            lsteps = cl["steps_accepted"] + cl["steps_rejected"]
-            lms = e0.elapsed_time(e1)
-            ltf = lsteps * FLOPS_PER_COLUMN_STEP / (lms * 1e-3) / 1e12
-            large_batch = {"workload": "config4 forward: 1048576 columns on one GPU, 129 saves, same Chain / tolerances", "ms": lms, "column_steps": lsteps,
-                           "value": lsteps / (lms * 1e-3), "unit": UNIT, "bad_status": int((lst != 0).sum()),
-                           "roofline": {"bound": "tensor", "achieved": ltf, "peak": bf16_peak / 3.0, "unit": "TFLOP/s", "frac": ltf / (bf16_peak / 3.0),
-                                        "kernel": "solve_tc2_kernel (two 128-column tiles in flight per CTA; picked from 98304 columns on)"}}
-            del lout, lT0, lcolp, lst
+            fms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+            fst = torch.tensor([float(cl["steps_accepted"] + cl["steps_rejected"]), float((lst != 0).sum())], device=dev, dtype=torch.float64)
+            if dist is not None:
+                dist.all_reduce(fms, op=dist.ReduceOp.MAX)
+                dist.all_reduce(fst, op=dist.ReduceOp.SUM)
+            fwd_ms, fwd_steps = float(fms.item()), float(fst[0].item())
+            ftf = fwd_steps * FLOPS_PER_COLUMN_STEP / (fwd_ms * 1e-3) / 1e12
+            config4 = {"workload": f"config4: {CONFIG4_COLUMNS} columns sharded over {world} GPU(s) ({nb} on rank 0), 129 saves, same Chain / tolerances",
+                       "scaling": "strong", "columns_per_rank": nb,
+                       "forward": {"ms": fwd_ms, "column_steps": fwd_steps, "value": fwd_steps / (fwd_ms * 1e-3), "unit": UNIT, "bad_status": int(fst[1].item()),
+                                   "roofline": {"bound": "tensor", "achieved": ftf, "peak": world * bf16_peak / 3.0, "unit": "TFLOP/s", "frac": ftf / (world * bf16_peak / 3.0),
+                                                "kernel": "solve_tc2_kernel (two 128-column tiles in flight per CTA; picked from 98304 columns per call on)"}}}
+            # loss + gradient: truth = the forward solution perturbed in closed form on the device (no 17 GB host read)
+            lTt = lout.mul_(0.99).add_(0.01)
+            del lout
+            if dist is not None:
+                nfc_b200.distributed.attach_communicator(h)
+            g = torch.empty(h.n_params, device=dev)
+            ls = torch.zeros(2, dtype=torch.float64, device=dev)
+            times = []
+            for it in range(2):
+                barrier()
+                e0.record()
+                h.loss_grad_dev(lT0, lcolp, lglob, lTt, ls, g, lst, n_total_columns=CONFIG4_COLUMNS, stream=stream)
+                e1.record()
+                barrier()
+                times.append(e0.elapsed_time(e1))
+            ca = h.counters()
+            ams = torch.tensor([times[-1], ca["last_allreduce_ms"]], device=dev, dtype=torch.float64)
+            ast = torch.tensor([float(ca["adj_steps_accepted"] + ca["adj_steps_rejected"]), float(ca["steps_accepted"] + ca["steps_rejected"]),
+                                float((lst != 0).sum())], device=dev, dtype=torch.float64)
+            if dist is not None:
+                dist.all_reduce(ams, op=dist.ReduceOp.MAX)
+                dist.all_reduce(ast, op=dist.ReduceOp.SUM)
+            lsh = ls.cpu()
+            atf = float(ast[0].item()) * FLOPS_PER_ADJOINT_COLUMN_STEP / (float(ams[0].item()) * 1e-3) / 1e12
+            config4["loss_grad"] = {"sec_per_epoch": float(ams[0].item()) * 1e-3, "first_call_sec": times[0] * 1e-3,
+                                    "allreduce_us_max_over_ranks": float(ams[1].item()) * 1e3 if dist is not None else 0.0,
+                                    "collective": ("one grouped ncclAllReduce of 24735 floats + 2 doubles inside nfc_loss_grad_dev (C-ABI communicator), inside the timed region"
+                                                   if dist is not None else "none (one GPU)"),
+                                    "adjoint_column_steps": float(ast[0].item()), "fwd_column_steps": float(ast[1].item()), "bad_status": int(ast[2].item()),
+                                    "adjoint_column_steps_per_sec": float(ast[0].item()) / (float(ams[0].item()) * 1e-3),
+                                    "loss": float(lsh[0] / lsh[1]) if dist is not None else float(lsh[0] / lsh[1]),
+                                    "grad_norm": float(g.double().norm().item()),
+                                    "roofline": {"bound": "tensor", "achieved": atf, "peak": world * bf16_peak / 3.0, "unit": "TFLOP/s", "frac": atf / (world * bf16_peak / 3.0),
+                                                 "flops_per_adjoint_column_step": FLOPS_PER_ADJOINT_COLUMN_STEP,
+                                                 "note": "whole loss+gradient call (RECORD forward pass, backward kernel, tape chunking, all-reduce) against the tensor ceiling of all ranks"}}
+            del lTt, lT0, lcolp, lst
         except Exception as e:
-            large_batch = {"error": str(e)}
+            config4 = {"error": f"{type(e).__name__}: {e}"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
         sample = 2048
         v, ms, nst = cpu_reference_run(1, 1, sample, cores)
+        v1, ms1, nst1 = cpu_reference_run(1, 0, 256, 1)          # the reference's actual mode: one thread (train_free_convection_nde.jl:23)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"{sample} of the {B} columns, {nst} column-steps, {ms:.0f} ms, C port of the reference path (OpenMP over columns)"}
+                        "sample": f"{sample} of the {B} columns, {nst} column-steps, {ms:.0f} ms, C port of the reference path (OpenMP over columns)",
+                        "single_thread": {"value": v1, "unit": UNIT, "cores": 1, "sample": f"256 of the {B} columns, {nst1} column-steps, {ms1:.0f} ms"}}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -336,7 +453,8 @@ def main():
             "config": {"workload": WORKLOAD, "kernel_path": "tcgen05" if use_tc else "simt", "tiles_in_flight_per_cta": (2 if (os.environ.get("NFC_TC_TILES", "0") == "2" or (os.environ.get("NFC_TC_TILES", "0") == "0" and B >= int(os.environ.get("NFC_TC2_MIN", "98304")))) else 1) if use_tc else None, "columns_per_gpu": B, "column_steps_per_pass_rank0": steps_per_pass,
                        "l2": "outputs (1.08 GB/step) exceed the 126 MB L2; no explicit flush", "parallelism": f"columns sharded x{world}, no collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(cnt["kernel_launches"]) * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "adjoint": adjoint, "large_batch": large_batch}
+            "gpu_launches": int(cnt["kernel_launches"]) * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "adjoint": adjoint,
+            "config4": config4, "cold_call": cold, "cpu_affinity": affinity}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

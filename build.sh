@@ -6,7 +6,7 @@ cd "$(dirname "$0")"
 PKG="neuralfreeconvection.jl_b200"
 EXTRA=""; FORCE=0
 for a in "$@"; do [ "$a" = "-v" ] && EXTRA="-Xptxas -v"; [ "$a" = "-f" ] && FORCE=1; done
-FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -diag-suppress 128 $EXTRA -Xcompiler -fPIC"
+FLAGS="$NFC_EXTRA_FLAGS -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -diag-suppress 128 $EXTRA -Xcompiler -fPIC"
 mkdir -p build
 stale() {   # $1 object, rest: sources
     local o="$1"; shift

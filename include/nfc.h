@@ -103,8 +103,9 @@ int32_t nfc_loss_grad(nfc_handle* h, const float* T0, const float* colp, const f
                       double* loss, float* grad_theta, int32_t* status, int64_t B);
 
 /* device-buffer calls: same semantics, array pointers are device memory on cfg.device (glob stays a HOST pointer:
- * four scalars), work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = the handle's own stream)
- * and NOT synchronised. */
+ * four scalars), work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = the handle's own stream, which is
+ * non-blocking and therefore NOT ordered with the legacy default stream: a host whose buffers are produced on the default
+ * stream passes cudaStreamLegacy, (void*)0x1, or cudaStreamPerThread, (void*)0x2) and NOT synchronised. */
 int32_t nfc_rhs_dev(nfc_handle* h, const float* T, const float* colp, const float* glob, float* dTdt, int64_t B, void* stream);
 int32_t nfc_solve_dev(nfc_handle* h, const float* T0, const float* colp, const float* glob, float* Tout,
                       int32_t* naccept, int32_t* nreject, int32_t* status, int64_t B, void* stream);
@@ -151,6 +152,10 @@ int32_t nfc_solve_ensemble(nfc_handle* h, const float* theta_members, int64_t n_
                            int64_t columns_per_member);
 /* diagnostics: attempted backward (adjoint) steps per column of the last nfc_loss_grad chunk (the analogue of naccept + nreject) */
 int32_t nfc_get_adjoint_steps(nfc_handle* h, int32_t* out, int64_t n);
+
+/* diagnostics: the forward tape of one column of the last nfc_loss_grad chunk -- per accepted step 168 floats: u_n[32], then the Tsit5
+ * dense output in power basis c1..c4 [4][32] (u(t_n + th h) = u_n + h th (c1 + th (c2 + th (c3 + th c4)))), t_n, h_n, 6 unused. */
+int32_t nfc_get_tape(nfc_handle* h, int64_t column, float* rows, int32_t max_rows, int32_t* n_rows);
 
 /* Roofline denominator for this path: sustained FP32 FMA throughput of `device`, measured with a
  * pure-FFMA kernel (16 independent chains per thread, full occupancy) over ~`ms_target` milliseconds. */

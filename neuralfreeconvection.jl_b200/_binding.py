@@ -14,7 +14,7 @@ NFC_MAX_LAYERS = 8
 EXPORTS = ["nfc_create", "nfc_destroy", "nfc_last_error", "nfc_n_params", "nfc_set_weights", "nfc_set_saveat",
            "nfc_get_counters", "nfc_rhs", "nfc_solve", "nfc_diagnose_flux", "nfc_loss_grad", "nfc_rhs_dev",
            "nfc_solve_dev", "nfc_loss_grad_dev", "nfc_sync", "nfc_measure_fp32_peak", "nfc_get_adjoint_steps", "nfc_embedded_solve",
-           "nfc_solve_ensemble", "nfc_comm_unique_id", "nfc_comm_init", "nfc_comm_destroy"]
+           "nfc_solve_ensemble", "nfc_comm_unique_id", "nfc_comm_init", "nfc_comm_destroy", "nfc_get_tape"]
 
 
 class NfcConfig(C.Structure):
@@ -66,6 +66,7 @@ def load():
     lib.nfc_embedded_solve.argtypes = [vp, fp, fp, fp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_int32, fp, C.c_int64]
     lib.nfc_get_adjoint_steps.argtypes = [vp, ip, C.c_int64]
     lib.nfc_measure_fp32_peak.argtypes = [C.c_int32, C.c_float, dp]
+    lib.nfc_get_tape.argtypes = [vp, C.c_int64, fp, C.c_int32, ip]
     lib.nfc_comm_unique_id.argtypes = [vp]
     lib.nfc_comm_init.argtypes = [vp, vp, C.c_int32, C.c_int32]
     lib.nfc_comm_destroy.argtypes = [vp]
@@ -150,6 +151,7 @@ class Handle:
         if rc != 0:
             raise NfcError(f"nfc_create failed ({rc}): {self.lib.nfc_last_error(None).decode()}")
         self.h = h
+        self.comm_world = 1
         self.n_params = int(self.lib.nfc_n_params(h))
 
     def _check(self, rc, what):
@@ -274,12 +276,21 @@ class Handle:
     def sync(self):
         self._check(self.lib.nfc_sync(self.h), "nfc_sync")
 
+    def tape(self, column, max_rows=4096):
+        """nfc_get_tape: [n_rows][168] forward tape of one column of the last loss_grad chunk (u, c1..c4, t, h per accepted step)."""
+        rows = np.zeros((max_rows, 168), dtype=np.float32)
+        n = C.c_int32(0)
+        self._check(self.lib.nfc_get_tape(self.h, column, _fp(rows), max_rows, C.byref(n)), "nfc_get_tape")
+        return rows[:min(n.value, max_rows)]
+
     def comm_init(self, unique_id: bytes, rank: int, world: int):
         """nfc_comm_init (collective): from now on loss_grad / loss_grad_dev return the loss and gradient of the GLOBAL batch."""
         if len(unique_id) != NFC_UNIQUE_ID_BYTES:
             raise ValueError("the rendezvous id has 128 bytes")
         buf = C.create_string_buffer(unique_id, NFC_UNIQUE_ID_BYTES)
         self._check(self.lib.nfc_comm_init(self.h, buf, rank, world), "nfc_comm_init")
+        self.comm_world = world
 
     def comm_destroy(self):
         self._check(self.lib.nfc_comm_destroy(self.h), "nfc_comm_destroy")
+        self.comm_world = 1

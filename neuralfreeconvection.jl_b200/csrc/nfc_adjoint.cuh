@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(ADJ_NW * 32, 1) adjoint_kernel(const AdjParams
                 const float t = sl->t[lane], ts = sl->tstop[lane];
                 float h = fminf(sl->dt[lane], t - ts);
                 int fl = 0;
-                if (t - h <= ts + 1e-6f * P.tf) { h = t - ts; fl = AFL_LAST; }
+                if (t - h <= ts + 1e-6f * P.tf && (t - h) - ts <= 0.05f * fabsf(h)) { h = t - ts; fl = AFL_LAST; } // snap to the save time only when that stretches the step by < 5 %: a wider window re-stretched a rejected step for ever (livelock at t - tstop = 4e-6, 2 of 10^6 columns)
                 sl->h[lane] = h; sl->flag[lane] = fl;
             } else {
                 sl->flag[lane] &= AFL_LAST;          // cancel pass replays the rejected step (same h, same tstop logic)

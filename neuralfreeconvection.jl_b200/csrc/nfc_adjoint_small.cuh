@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(NT, 1) adjoint_small_kernel(const float* __res
             if (S.mode == 0) {
                 float h = fminf(S.dt, S.t - S.tstop);
                 int fl = 0;
-                if (S.t - h <= S.tstop + 1e-6f * P.tf) { h = S.t - S.tstop; fl = AFL_LAST; }
+                if (S.t - h <= S.tstop + 1e-6f * P.tf && (S.t - h) - S.tstop <= 0.05f * fabsf(h)) { h = S.t - S.tstop; fl = AFL_LAST; } // snap to the save time only when that stretches the step by < 5 %: a wider window re-stretched a rejected step for ever (livelock at t - tstop = 4e-6, 2 of 10^6 columns)
                 S.h = h; S.flag = fl;
             } else {
                 S.flag &= AFL_LAST;
@@ -300,6 +300,9 @@ __global__ void __launch_bounds__(NT, 1) adjoint_small_kernel(const float* __res
                             if (S.si >= 1) fl |= AFL_JUMP; else fl |= AFL_DONE;
                         }
                     } else {
+#ifdef NFC_DEBUG_STUCK
+                        if (S.nrej > 400 && S.nrej < 412) printf("stuck col %d: t %.9g tstop %.9g h %.9g dt %.9g ee %g dtnew %g si %d ipos %d fl %d\n", S.col, S.t, S.tstop, h, S.dt, ee, dtnew, S.si, S.ipos, fl);
+#endif
                         S.nrej += 1;
                         S.mode = 1;                             // undo this step's quadrature contribution next iteration
                         S.dt_retry = dtnew;

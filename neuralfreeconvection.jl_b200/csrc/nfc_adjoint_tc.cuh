@@ -306,7 +306,7 @@ __device__ __forceinline__ void atc_control(const AdjParams& P, AtcShared& S, in
             const float t = S.t[c], ts = S.tstop[c];
             h = fminf(S.dt[c], t - ts);
             fl &= ~AFL_LAST;
-            if (t - h <= ts + 1e-6f * P.tf) { h = t - ts; fl |= AFL_LAST; }
+            if (t - h <= ts + 1e-6f * P.tf && (t - h) - ts <= 0.05f * fabsf(h)) { h = t - ts; fl |= AFL_LAST; } // snap to the save time only when that stretches the step by < 5 %: a wider window re-stretched a rejected step for ever (livelock at t - tstop = 4e-6, 2 of 10^6 columns)
             S.h[c] = h;
         }
         const float* base = P.tape + (long long)col * P.tape_cap * TAPE_STRIDE;

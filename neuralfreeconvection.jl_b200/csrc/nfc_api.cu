@@ -679,6 +679,20 @@ int32_t nfc_get_adjoint_steps(nfc_handle* h, int32_t* out, int64_t n) {
     return 0;
 }
 
+int32_t nfc_get_tape(nfc_handle* h, int64_t column, float* rows, int32_t max_rows, int32_t* n_rows) {
+    if (!h || !rows || !n_rows) return -1;
+    NFC_CUDA(h, cudaSetDevice(h->device));
+    NFC_CUDA(h, cudaDeviceSynchronize());
+    const int cap = h->cfg.adjoint_max_steps;
+    if (column < 0 || (size_t)(column + 1) * cap * TAPE_STRIDE > h->a_tape.cap || (size_t)column >= h->a_tlen.cap) return fail(h, -2, "column %lld is not in the last loss_grad chunk", (long long)column);
+    int len = 0;
+    NFC_CUDA(h, cudaMemcpy(&len, h->a_tlen.p + column, sizeof(int), cudaMemcpyDeviceToHost));
+    *n_rows = len;
+    const int n = std::min(len, max_rows);
+    if (n > 0) NFC_CUDA(h, cudaMemcpy(rows, h->a_tape.p + (size_t)column * cap * TAPE_STRIDE, sizeof(float) * (size_t)n * TAPE_STRIDE, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 int32_t nfc_comm_unique_id(void* id128) {
     if (!id128) return -1;
     NcclApi& a = nccl_api();

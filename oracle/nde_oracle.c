@@ -417,7 +417,7 @@ static void adjoint_continuous(const net_t *n, const float *th, const float *col
         float tstop = saveat[si - 1];
         for (int iter = 0; iter < 100000 && t > tstop; ++iter) {
             float h = fminf(dt, t - tstop);
-            int last = (t - h) <= tstop + 1e-6f * saveat[n_save - 1];
+            int last = (t - h) <= tstop + 1e-6f * saveat[n_save - 1] && (t - h) - tstop <= 0.05f * fabsf(h);   /* snap only when it stretches the step by < 5 %: no livelock on rejection */
             if (last) h = t - tstop;
             for (int p = 0; p < n->n_params; ++p) gstep[p] = 0.0;
             for (int s = 1; s <= 7; ++s) {
