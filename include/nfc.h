@@ -94,7 +94,8 @@ int32_t nfc_set_weights(nfc_handle* h, const float* theta, int64_t n);
 int32_t nfc_set_saveat(nfc_handle* h, const float* saveat, int32_t n_save);
 int32_t nfc_get_counters(const nfc_handle* h, nfc_counters* out);
 
-/* host-buffer calls (the drop-in boundary) */
+/* host-buffer calls (the drop-in boundary).  A column whose status is not 0 stops saving where it failed: nfc_solve returns NaN in the
+ * remaining rows of its trajectory (the *_dev calls leave those rows of the caller's buffer untouched). */
 int32_t nfc_rhs(nfc_handle* h, const float* T, const float* colp, const float* glob, float* dTdt, int64_t B);
 int32_t nfc_solve(nfc_handle* h, const float* T0, const float* colp, const float* glob, float* Tout,
                   int32_t* naccept, int32_t* nreject, int32_t* status, int64_t B);

@@ -138,8 +138,8 @@ class _NDE:
         self.iterations = iterations
         self.tspan = (np.float32(0.0), np.float32(iterations.max() / Nt))
         self.saveat = np.linspace(self.tspan[0], self.tspan[1], len(iterations)).astype(np.float32)
-        self._mk = lambda a: B_.Handle(NN.conv_width, NN.dense_spec, self.nde_type, self.saveat, reltol=reltol, abstol=abstol,
-                                       device=device, Nz=Nz, alg=a, **kw)
+        self._mk = lambda a, **kw2: B_.Handle(NN.conv_width, NN.dense_spec, self.nde_type, self.saveat, reltol=reltol, abstol=abstol,
+                                              device=device, Nz=Nz, alg=a, **{**kw, **kw2})
         self._handles = {}
         self.handle = self.handle_for(alg)
 
@@ -201,6 +201,7 @@ def solve_nde(*args, **kw):
         single = T0.ndim == 1
         res = handle.solve(np.atleast_2d(T0), colp, glob)
         nde.last = res
+        _warn_status(res["status"], "solve_nde")
         return res["T"][0].T.copy() if single else res["T"]
     ds, NN, NDEType, nde_params, algorithm, T_scaling, wT_scaling = args
     T0 = kw.get("T0")
@@ -212,8 +213,21 @@ def solve_nde(*args, **kw):
     p = np.asarray(nde_params, dtype=np.float32)
     T = solve_nde(nde, NN, T0, algorithm, p if nde.nde_type == 1 else p[:6])          # [Nz, Nt]
     colp, _ = _split_params(nde, p if nde.nde_type == 1 else p[:6])
-    wT = nde.handle.diagnose_flux(T.T[None], colp)[0].T                                 # [Nz+1, Nt]
+    wT = nde.handle_for(algorithm).diagnose_flux(T.T[None], colp)[0].T                  # [Nz+1, Nt]; the handle that holds the weights
     return dict(T=T_scaling.inv(T), wT=wT_scaling.inv(wT))
+
+
+STATUS_NAMES = {1: "maxiters", 2: "NaN / operand range", 3: "dt underflow", 4: "adjoint tape overflow"}
+
+
+def _warn_status(status, what):
+    """The reference treats solver retcodes as warnings, never exceptions: so does the host side here -- but it says so.
+    Failed columns return NaN after the failure (nfc_solve) and contribute nothing to the gradient (nfc_loss_grad)."""
+    status = np.asarray(status)
+    if status.any():
+        import warnings
+        kinds = {STATUS_NAMES.get(int(k), str(k)): int((status == k).sum()) for k in np.unique(status) if k != 0}
+        warnings.warn(f"{what}: {int((status != 0).sum())} of {status.size} columns failed ({kinds}); their results are NaN / excluded", RuntimeWarning, stacklevel=3)
 
 
 def _check_alg(alg):
@@ -264,8 +278,9 @@ def train_neural_differential_equation(NN, NDEType, nde_params, algorithm, datas
                                        history_filepath=None, device=0, callback=None):
     """train_neural_differential_equation!(...) (src/training.jl:34-78): full-batch ADAM on the MSE between the NDE
     solutions and the scaled truth of every training simulation.  One epoch = one nfc_loss_grad call (all simulations
-    in one launch) + the callback's loss re-evaluation (src/training.jl:53-68).  Returns the best-loss Chain
-    (GalacticOptim returns sol.minimizer, src/training.jl:74)."""
+    in one launch) + one ADAM update.  The loss recorded for an epoch is the loss of the weights its gradient was taken at (the
+    reference's callback re-solves every simulation for that number, src/training.jl:53-54; nfc_loss_grad already has it).
+    Returns the best-loss Chain (GalacticOptim returns sol.minimizer, src/training.jl:74)."""
     if _check_alg(algorithm) != 0:
         raise NotImplementedError("the adjoint gradient is implemented for Tsit5 (its tape is Tsit5 dense output); train with Tsit5()")
     ids = sorted(datasets.keys())
@@ -279,10 +294,18 @@ def train_neural_differential_equation(NN, NDEType, nde_params, algorithm, datas
     theta, reconstruct = destructure(NN)
     best = (np.inf, theta.copy())
     history = []
+    tape_steps = 512                                                        # the C library's default adjoint_max_steps
     t0 = time.time()
     for epoch in range(1, epochs + 1):
         nde.handle.set_weights(theta)
         res = nde.handle.loss_grad(T0, colp, glob, true_sols)
+        while (res["status"] == 4).any() and tape_steps < 65536:
+            # adjoint tape overflow: the column's residuals are in the loss but its gradient is missing -- never train on that; keep more steps
+            tape_steps *= 2
+            nde._handles[0] = nde.handle = nde._mk(0, adjoint_max_steps=tape_steps)
+            nde.handle.set_weights(theta)
+            res = nde.handle.loss_grad(T0, colp, glob, true_sols)
+        _warn_status(res["status"], f"train_neural_differential_equation epoch {epoch}")
         if res["loss"] < best[0]:
             best = (res["loss"], theta.copy())
         runtime = time.time() - t0

@@ -822,6 +822,8 @@ int32_t nfc_solve(nfc_handle* h, const float* T0, const float* colp, const float
     NFC_CUDA(h, h->s_status.ensure(B));
     NFC_CUDA(h, cudaMemcpyAsync(h->s_T0.p, T0, sizeof(float) * B * NZ, cudaMemcpyHostToDevice, h->stream));
     NFC_CUDA(h, cudaMemcpyAsync(h->s_colp.p, colp, sizeof(float) * B * 3, cudaMemcpyHostToDevice, h->stream));
+    // a column that fails (status != 0) stops saving: its remaining rows must read NaN, not the previous call's trajectories (0xFFFFFFFF is a NaN)
+    NFC_CUDA(h, cudaMemsetAsync(h->s_out.p, 0xFF, sizeof(float) * nout, h->stream));
     h->last_launches = 0;
     // Large batches are solved in three pieces so that the device->host copy of one piece (the trajectories dominate the
     // end-to-end time: 1.08 GB for 65 536 columns x 129 saves) overlaps the solve of the next one (second stream; measured +32 % end to end).
@@ -878,6 +880,7 @@ int32_t nfc_solve_ensemble(nfc_handle* h, const float* theta_members, int64_t E,
     NFC_CUDA(h, h->s_status.ensure(B));
     NFC_CUDA(h, cudaMemcpyAsync(h->s_T0.p, T0, sizeof(float) * B * NZ, cudaMemcpyHostToDevice, h->stream));
     NFC_CUDA(h, cudaMemcpyAsync(h->s_colp.p, colp, sizeof(float) * B * 3, cudaMemcpyHostToDevice, h->stream));
+    NFC_CUDA(h, cudaMemsetAsync(h->s_out.p, 0xFF, sizeof(float) * nout, h->stream));      // unsaved rows of failed columns read NaN
     h->last_launches = 0;
     int rc = [&]() -> int {
         NFC_DISPATCH(h, do_solve_ensemble, h, theta_members, E, (int)S, h->s_T0.p, h->s_colp.p, prefactor(glob), h->s_out.p, h->s_nacc.p,
