@@ -281,8 +281,7 @@ def train_neural_differential_equation(NN, NDEType, nde_params, algorithm, datas
     in one launch) + one ADAM update.  The loss recorded for an epoch is the loss of the weights its gradient was taken at (the
     reference's callback re-solves every simulation for that number, src/training.jl:53-54; nfc_loss_grad already has it).
     Returns the best-loss Chain (GalacticOptim returns sol.minimizer, src/training.jl:74)."""
-    if _check_alg(algorithm) != 0:
-        raise NotImplementedError("the adjoint gradient is implemented for Tsit5 (its tape is Tsit5 dense output); train with Tsit5()")
+    alg = _check_alg(algorithm)          # Tsit5, or the stabilised explicit integrator (ROCK4's role): the continuous adjoint reads either tape
     ids = sorted(datasets.keys())
     it = np.asarray(list(iterations)) - 1                                   # Julia 1-based -> 0-based
     T0 = np.stack([T_scaling(datasets[i].T[:, 0]) for i in ids]).astype(np.float32)
@@ -297,14 +296,15 @@ def train_neural_differential_equation(NN, NDEType, nde_params, algorithm, datas
     tape_steps = 512                                                        # the C library's default adjoint_max_steps
     t0 = time.time()
     for epoch in range(1, epochs + 1):
-        nde.handle.set_weights(theta)
-        res = nde.handle.loss_grad(T0, colp, glob, true_sols)
-        while (res["status"] == 4).any() and tape_steps < 65536:
+        handle = nde.handle_for(alg)
+        handle.set_weights(theta)
+        res = handle.loss_grad(T0, colp, glob, true_sols)
+        while (res["status"] == 4).any() and tape_steps < 32768:
             # adjoint tape overflow: the column's residuals are in the loss but its gradient is missing -- never train on that; keep more steps
             tape_steps *= 2
-            nde._handles[0] = nde.handle = nde._mk(0, adjoint_max_steps=tape_steps)
-            nde.handle.set_weights(theta)
-            res = nde.handle.loss_grad(T0, colp, glob, true_sols)
+            handle = nde._handles[alg] = nde._mk(alg, adjoint_max_steps=tape_steps)
+            handle.set_weights(theta)
+            res = handle.loss_grad(T0, colp, glob, true_sols)
         _warn_status(res["status"], f"train_neural_differential_equation epoch {epoch}")
         if res["loss"] < best[0]:
             best = (res["loss"], theta.copy())

@@ -254,9 +254,13 @@ int launch_solve(nfc_handle* h, SolveParams& P, cudaStream_t st, bool reset_coun
 }
 
 }  // namespace
-// the adjoint's host code reuses launch_solve<N, true> (forward pass in RECORD mode)
+// the adjoint's host code reuses the forward solves in RECORD mode: Tsit5 (launch_solve<N, true>) or the stabilised integrator
+namespace { template <class N> int launch_record_rkc(nfc_handle* h, nfc::SolveParams& P, cudaStream_t st, bool first_chunk); }
 template <class N>
-int nfc_launch_record(nfc_handle* h, nfc::SolveParams& P, cudaStream_t st, bool first_chunk) { return launch_solve<N, true>(h, P, st, first_chunk); }
+int nfc_launch_record(nfc_handle* h, nfc::SolveParams& P, cudaStream_t st, bool first_chunk) {
+    if (h->cfg.alg == NFC_ALG_RKC2) return launch_record_rkc<N>(h, P, st, first_chunk);
+    return launch_solve<N, true>(h, P, st, first_chunk);
+}
 #include "nfc_adjoint.cuh"
 #include "nfc_adjoint_small.cuh"
 template <class N>
@@ -299,27 +303,30 @@ std::vector<float> rkc_coefficients() {
     return tab;
 }
 
-template <class N>
+template <class N, bool RECORD = false>
 int launch_solve_rkc(nfc_handle* h, SolveParams& S, cudaStream_t st, bool reset_counters, bool last_piece, int* nfe) {
     constexpr bool WS = Launch<N>::WS;
     constexpr int NW = Launch<N>::NW;
-    NFC_CUDA(h, cudaFuncSetAttribute(rkc::solve_rkc_kernel<N, WS, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<N>(NW)));
+    NFC_CUDA(h, cudaFuncSetAttribute(rkc::solve_rkc_kernel<N, WS, NW, RECORD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<N>(NW)));
     S.wpack = h->d_wpack.p; S.saveat = h->d_saveat.p; S.counters = h->d_counters.p;
     S.n_save = h->cfg.n_save; S.max_iters = h->cfg.max_iters; S.use_kca = h->cfg.nde_type == NFC_NDE_CONVECTIVE_ADJUSTMENT;
     S.tf = h->saveat.back(); S.reltol = h->cfg.reltol; S.abstol = h->cfg.abstol; S.fixed_dt = 0.f;
     if (reset_counters) {
         NFC_CUDA(h, cudaMemsetAsync(h->d_counters.p, 0, sizeof(unsigned long long) * CTR_COUNT, st));
         NFC_CUDA(h, cudaEventRecord(h->ev[0], st));
-    } else NFC_CUDA(h, cudaMemsetAsync(h->d_counters.p + CTR_QUEUE, 0, sizeof(unsigned long long), st));
+    } else {
+        NFC_CUDA(h, cudaMemsetAsync(h->d_counters.p + CTR_QUEUE, 0, sizeof(unsigned long long), st));
+        NFC_CUDA(h, cudaMemsetAsync(h->d_counters.p + CTR_ADJ_QUEUE, 0, sizeof(unsigned long long), st));
+    }
     rkc::Params P{S, h->d_rkctab.p, nfe, h->rkc_mmax};
     if (h->use_tc && h->arch == ARCH_DEFAULT) {
         const int gridt = (int)std::min<long long>(h->num_sms, (S.B + tc::TILE - 1) / tc::TILE);
         if (h->tc_fp16) {
-            NFC_CUDA(h, cudaFuncSetAttribute(tc::solve_rkc_tc_kernel<tc::SplitFP16x2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::rkc_tc_smem_bytes<tc::SplitFP16x2>()));
-            tc::solve_rkc_tc_kernel<tc::SplitFP16x2><<<gridt, tc::NTHREADS, tc::rkc_tc_smem_bytes<tc::SplitFP16x2>(), st>>>(h->d_wimg.p, P);
+            NFC_CUDA(h, cudaFuncSetAttribute(tc::solve_rkc_tc_kernel<tc::SplitFP16x2, RECORD>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::rkc_tc_smem_bytes<tc::SplitFP16x2>()));
+            tc::solve_rkc_tc_kernel<tc::SplitFP16x2, RECORD><<<gridt, tc::NTHREADS, tc::rkc_tc_smem_bytes<tc::SplitFP16x2>(), st>>>(h->d_wimg.p, P);
         } else {
-            NFC_CUDA(h, cudaFuncSetAttribute(tc::solve_rkc_tc_kernel<tc::SplitBF16x3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::rkc_tc_smem_bytes<tc::SplitBF16x3>()));
-            tc::solve_rkc_tc_kernel<tc::SplitBF16x3><<<gridt, tc::NTHREADS, tc::rkc_tc_smem_bytes<tc::SplitBF16x3>(), st>>>(h->d_wimg.p, P);
+            NFC_CUDA(h, cudaFuncSetAttribute(tc::solve_rkc_tc_kernel<tc::SplitBF16x3, RECORD>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::rkc_tc_smem_bytes<tc::SplitBF16x3>()));
+            tc::solve_rkc_tc_kernel<tc::SplitBF16x3, RECORD><<<gridt, tc::NTHREADS, tc::rkc_tc_smem_bytes<tc::SplitBF16x3>(), st>>>(h->d_wimg.p, P);
         }
         NFC_CUDA(h, cudaGetLastError());
         if (last_piece) { NFC_CUDA(h, cudaEventRecord(h->ev[1], st)); h->ev_fwd_valid = true; }
@@ -329,12 +336,17 @@ int launch_solve_rkc(nfc_handle* h, SolveParams& S, cudaStream_t st, bool reset_
     }
     const long long groups = (S.B + CPW - 1) / CPW;
     const int grid = (int)std::min<long long>(h->num_sms, (groups + NW - 1) / NW);
-    rkc::solve_rkc_kernel<N, WS, NW><<<grid, NW * 32, smem_bytes<N>(NW), st>>>(P);
+    rkc::solve_rkc_kernel<N, WS, NW, RECORD><<<grid, NW * 32, smem_bytes<N>(NW), st>>>(P);
     NFC_CUDA(h, cudaGetLastError());
     if (last_piece) { NFC_CUDA(h, cudaEventRecord(h->ev[1], st)); h->ev_fwd_valid = true; }
     h->last_launches += 1;
     h->last_columns = reset_counters ? S.B : h->last_columns + S.B;
     return 0;
+}
+
+template <class N>
+int launch_record_rkc(nfc_handle* h, nfc::SolveParams& P, cudaStream_t st, bool first_chunk) {
+    return launch_solve_rkc<N, true>(h, P, st, first_chunk, true, nullptr);
 }
 
 template <class N>
@@ -783,7 +795,6 @@ int32_t nfc_loss_grad_dev(nfc_handle* h, const float* T0, const float* colp, con
                           float* grad_dev, int32_t* status, int64_t B, int64_t n_total_columns, void* stream) {
     if (int rc = check_ready(h, B)) return rc;
     if (!glob) return fail(h, -1, "null glob");
-    if (h->cfg.alg != NFC_ALG_TSIT5) return fail(h, -3, "nfc_loss_grad needs a Tsit5 handle (the adjoint tape is Tsit5 dense output)");
     const float* g = glob;   // glob is always a HOST pointer (4 scalars)
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     h->last_launches = 0;
@@ -947,7 +958,6 @@ int32_t nfc_loss_grad(nfc_handle* h, const float* T0, const float* colp, const f
     if (int rc = check_ready(h, B)) return rc;
     if (B == 0 && !h->nccl_comm) return fail(h, -2, "loss over zero columns is undefined");
     if ((B > 0 && (!T0 || !colp || !Ttrue)) || !glob || !loss || !grad_theta) return fail(h, -1, "null argument");
-    if (h->cfg.alg != NFC_ALG_TSIT5) return fail(h, -3, "nfc_loss_grad needs a Tsit5 handle (the adjoint tape is Tsit5 dense output)");
     const size_t ntraj = (size_t)B * h->cfg.n_save * NZ;
     NFC_CUDA(h, h->s_T0.ensure((size_t)std::max<int64_t>(B, 1) * NZ));
     NFC_CUDA(h, h->s_colp.ensure((size_t)std::max<int64_t>(B, 1) * 3));

@@ -40,6 +40,7 @@ struct SlotsT {   // shared memory; index = slot (SIMT kernel: 8 per warp; tenso
     float ca[NS], cb[NS], cc[NS], cd[NS], ce[NS];   // coefficients of the vector action
     float o_t0[NS], o_h[NS], o_tn[NS];              // the step just accepted (dense output): start, size, end
     int o_si[NS];                                   //   and the first save index it may serve
+    int o_row[NS];                                  //   and its tape row (RECORD mode: accepted-step index)
 };
 using Slots = SlotsT<CPW>;
 
@@ -50,7 +51,8 @@ struct Params {
     int mmax;
 };
 
-__device__ __forceinline__ void fill(const Params& P, Slots* sl, int c, float& yn, float& x, int lane) {
+template <bool RECORD = false>
+__device__ __forceinline__ void fill(const Params& P, Slots* sl, int c, float& yn, float& x, int lane, double* lsum = nullptr) {
     long long next = 0;
     if (lane == 0) next = (long long)atomicAdd(&P.S.counters[CTR_QUEUE], 1ULL);
     next = __shfl_sync(FULL, next, 0);
@@ -58,7 +60,12 @@ __device__ __forceinline__ void fill(const Params& P, Slots* sl, int c, float& y
         yn = P.S.T0[next * NZ + lane];
         x = yn;
         int si = 0;
-        while (si < P.S.n_save && P.S.saveat[si] <= 0.f) { P.S.Tout[(next * P.S.n_save + si) * NZ + lane] = yn; ++si; }
+        while (si < P.S.n_save && P.S.saveat[si] <= 0.f) {
+            const long long o = (next * P.S.n_save + si) * NZ + lane;
+            if (RECORD) { const float r = yn - P.S.Ttrue[o]; P.S.resid[o] = r; *lsum += (double)warp_sum(r * r); }
+            else P.S.Tout[o] = yn;
+            ++si;
+        }
         if (lane == 0) {
             sl->col[c] = (int)next; sl->phase[c] = PH_F0; sl->act[c] = ACT_NONE; sl->m[c] = 0; sl->j[c] = 0; sl->it[c] = 0; sl->nstsig[c] = 0;
             sl->nacc[c] = 0; sl->nrej[c] = 0; sl->nfe[c] = 0; sl->si[c] = si; sl->status[c] = ST_OK;
@@ -143,7 +150,7 @@ __device__ __forceinline__ void transition(const Params& P, SL* sl, int s, float
                 const int nacc = sl->nacc[s] + 1;
                 sl->nacc[s] = nacc;
                 act |= AF_ACCEPT;
-                sl->o_t0[s] = tcur; sl->o_h[s] = h;
+                sl->o_t0[s] = tcur; sl->o_h[s] = h; sl->o_row[s] = nacc - 1;
                 tcur = sl->last[s] ? tf : tcur + h;
                 sl->o_tn[s] = tcur; sl->t[s] = tcur;
                 {
@@ -218,7 +225,10 @@ __device__ __forceinline__ void transition(const Params& P, SL* sl, int s, float
     sl->act[s] = act;
 }
 
-template <class N, bool WS, int NW>
+// RECORD: forward pass of nfc_loss_grad with the stabilised integrator -- residuals at the save points, their squared sum, and the
+// adjoint tape: per accepted step u_n and the cubic-Hermite dense output in the power basis of the Tsit5 tape (c1 = f_n, c2, c3, c4 = 0),
+// so the backward kernels (continuous adjoint: integrator-agnostic by construction) read it unchanged.
+template <class N, bool WS, int NW, bool RECORD = false>
 __global__ void __launch_bounds__(NW * 32, 1) solve_rkc_kernel(const Params P) {
     extern __shared__ __align__(16) float smem[];
     __shared__ uint64_t bar;
@@ -231,10 +241,11 @@ __global__ void __launch_bounds__(NW * 32, 1) solve_rkc_kernel(const Params P) {
     const float reltol = P.S.reltol, abstol = P.S.abstol;
 
     float yn[CPW], fn[CPW], v[CPW], yjm2[CPW], x[CPW], f[CPW];
+    double lsum = 0.0;
 #pragma unroll
     for (int c = 0; c < CPW; ++c) {
         fn[c] = 0.f; v[c] = 0.f; yjm2[c] = 0.f;
-        fill(P, sl, c, yn[c], x[c], lane);
+        fill<RECORD>(P, sl, c, yn[c], x[c], lane, &lsum);
     }
     __syncwarp();
 
@@ -283,12 +294,25 @@ __global__ void __launch_bounds__(NW * 32, 1) solve_rkc_kernel(const Params P) {
                 const float t0 = sl->o_t0[c], h = sl->o_h[c], tn = sl->o_tn[c];
                 const float d = (x[c] - yn[c]) / h;
                 const float c2 = 3.f * d - 2.f * fn[c] - f[c], c3 = -2.f * d + fn[c] + f[c];
+                if (RECORD) {
+                    const int n = sl->o_row[c];
+                    if (n < P.S.tape_cap) {
+                        float* e = P.S.tape + ((long long)col * P.S.tape_cap + n) * TAPE_STRIDE;
+                        e[lane] = yn[c]; e[NZ + lane] = fn[c]; e[2 * NZ + lane] = c2; e[3 * NZ + lane] = c3; e[4 * NZ + lane] = 0.f;
+                        if (lane == 0) { e[TAPE_T] = t0; e[TAPE_H] = h; }
+                    }
+                }
+                float sse = 0.f;
                 for (int si = sl->o_si[c]; si < P.S.n_save; ++si) {
                     const float ts = P.S.saveat[si];
                     if (ts > tn) break;
                     const float th = fminf((ts - t0) / h, 1.0f);
-                    P.S.Tout[(col * P.S.n_save + si) * NZ + lane] = fmaf(h * th, fmaf(th, fmaf(th, c3, c2), fn[c]), yn[c]);
+                    const long long o = (col * P.S.n_save + si) * NZ + lane;
+                    const float val = fmaf(h * th, fmaf(th, fmaf(th, c3, c2), fn[c]), yn[c]);
+                    if (RECORD) { const float r = val - P.S.Ttrue[o]; P.S.resid[o] = r; sse = fmaf(r, r, sse); }
+                    else P.S.Tout[o] = val;
                 }
+                if (RECORD) lsum += (double)warp_sum(sse);
                 yn[c] = x[c]; fn[c] = f[c];
             }
             if (act & AF_RHO_DONE) v[c] -= yn[c];
@@ -305,6 +329,10 @@ __global__ void __launch_bounds__(NW * 32, 1) solve_rkc_kernel(const Params P) {
                     const int col = sl->col[c];
                     if (P.S.naccept) P.S.naccept[col] = sl->nacc[c];
                     if (P.S.nreject) P.S.nreject[col] = sl->nrej[c];
+                    if (RECORD) {
+                        if (sl->nacc[c] > P.S.tape_cap && sl->status[c] == ST_OK) sl->status[c] = ST_TAPE_OVERFLOW;
+                        P.S.tape_len[col] = sl->nacc[c] < P.S.tape_cap ? sl->nacc[c] : P.S.tape_cap;
+                    }
                     if (P.S.status) P.S.status[col] = sl->status[c];
                     if (P.nfe) P.nfe[col] = sl->nfe[c];
                     atomicAdd(&P.S.counters[CTR_ACCEPT], (unsigned long long)sl->nacc[c]);
@@ -313,11 +341,12 @@ __global__ void __launch_bounds__(NW * 32, 1) solve_rkc_kernel(const Params P) {
                 }
                 __syncwarp();
                 fn[c] = 0.f; v[c] = 0.f; yjm2[c] = 0.f;
-                fill(P, sl, c, yn[c], x[c], lane);
+                fill<RECORD>(P, sl, c, yn[c], x[c], lane, &lsum);
             }
         }
         __syncwarp();
     }
+    if (RECORD && lane == 0) atomicAdd(P.S.loss_sum, lsum);
 }
 
 }  // namespace rkc

@@ -24,7 +24,7 @@ struct RkcShared {
 template <class SP>
 constexpr int rkc_tc_smem_bytes() { return ((SP::IMG + 127) / 128) * 128 + (int)sizeof(RkcShared); }
 
-template <class SP>
+template <class SP, bool RECORD = false>
 __global__ void __launch_bounds__(NTHREADS, 1) solve_rkc_tc_kernel(const unsigned char* __restrict__ gimg, const rkc::Params P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ TcShared S;
@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_rkc_tc_kernel(const unsigne
         auto* sl = &R.sl;
         int pd = 0, xb = 0, pb = 0;
         float yn[8], fn[8], x[8];
+        double lsum = 0.0;          // RECORD: this thread's sum of squared residuals
         const float zero8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 
         // scalar part of a refill (quarter-0 thread): next column from the queue, fresh controller state
@@ -76,9 +77,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_rkc_tc_kernel(const unsigne
 #pragma unroll
                 for (int i = 0; i < 8; ++i) x[i] = yn[i];
                 for (int si = 0; si < P.S.n_save && P.S.saveat[si] <= 0.f; ++si) {
-                    float* o = P.S.Tout + ((long long)nc * P.S.n_save + si) * NZ + 8 * q;
-                    *reinterpret_cast<float4*>(o) = a;
-                    *reinterpret_cast<float4*>(o + 4) = b;
+                    const long long oi = ((long long)nc * P.S.n_save + si) * NZ + 8 * q;
+                    if (RECORD) {
+                        const float4 ta = *reinterpret_cast<const float4*>(P.S.Ttrue + oi), tb = *reinterpret_cast<const float4*>(P.S.Ttrue + oi + 4);
+                        const float r[8] = {a.x - ta.x, a.y - ta.y, a.z - ta.z, a.w - ta.w, b.x - tb.x, b.y - tb.y, b.z - tb.z, b.w - tb.w};
+                        *reinterpret_cast<float4*>(P.S.resid + oi) = make_float4(r[0], r[1], r[2], r[3]);
+                        *reinterpret_cast<float4*>(P.S.resid + oi + 4) = make_float4(r[4], r[5], r[6], r[7]);
+                        float sse = 0.f;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) sse = fmaf(r[i], r[i], sse);
+                        lsum += (double)sse;
+                    } else {
+                        float* o = P.S.Tout + oi;
+                        *reinterpret_cast<float4*>(o) = a;
+                        *reinterpret_cast<float4*>(o + 4) = b;
+                    }
                 }
             }
         };
@@ -147,6 +160,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_rkc_tc_kernel(const unsigne
                     if ((sl->act[c] & ACT_MASK) == ACT_REFILL) {
                         if (P.S.naccept) P.S.naccept[colc] = sl->nacc[c];
                         if (P.S.nreject) P.S.nreject[colc] = sl->nrej[c];
+                        if (RECORD) {
+                            if (sl->nacc[c] > P.S.tape_cap && sl->status[c] == ST_OK) sl->status[c] = ST_TAPE_OVERFLOW;
+                            P.S.tape_len[colc] = sl->nacc[c] < P.S.tape_cap ? sl->nacc[c] : P.S.tape_cap;
+                        }
                         if (P.S.status) P.S.status[colc] = sl->status[c];
                         if (P.nfe) P.nfe[colc] = sl->nfe[c];
                         atomicAdd(&P.S.counters[CTR_ACCEPT], (unsigned long long)sl->nacc[c]);
@@ -175,6 +192,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_rkc_tc_kernel(const unsigne
                         const float d = (x[i] - yn[i]) / h;
                         c2[i] = 3.f * d - 2.f * fn[i] - f[i]; c3[i] = -2.f * d + fn[i] + f[i];
                     }
+                    if (RECORD) {          // tape row in the Tsit5 tape's power basis: u_n, c1 = f_n, c2, c3, c4 = 0, (t_n, h_n)
+                        const int n = sl->o_row[c];
+                        if (n < P.S.tape_cap) {
+                            float* e = P.S.tape + ((long long)colc * P.S.tape_cap + n) * TAPE_STRIDE + 8 * q;
+#pragma unroll
+                            for (int hf = 0; hf < 2; ++hf) {
+                                const int i = 4 * hf;
+                                *reinterpret_cast<float4*>(e + i) = make_float4(yn[i], yn[i + 1], yn[i + 2], yn[i + 3]);
+                                *reinterpret_cast<float4*>(e + NZ + i) = make_float4(fn[i], fn[i + 1], fn[i + 2], fn[i + 3]);
+                                *reinterpret_cast<float4*>(e + 2 * NZ + i) = make_float4(c2[i], c2[i + 1], c2[i + 2], c2[i + 3]);
+                                *reinterpret_cast<float4*>(e + 3 * NZ + i) = make_float4(c3[i], c3[i + 1], c3[i + 2], c3[i + 3]);
+                                *reinterpret_cast<float4*>(e + 4 * NZ + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+                            }
+                            if (q == 0) { e[TAPE_T] = t0; e[TAPE_H] = h; }
+                        }
+                    }
                     for (int si = sl->o_si[c]; si < P.S.n_save; ++si) {
                         const float ts = P.S.saveat[si];
                         if (ts > tn) break;
@@ -182,9 +215,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_rkc_tc_kernel(const unsigne
                         float o[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) o[i] = fmaf(h * th, fmaf(th, fmaf(th, c3[i], c2[i]), fn[i]), yn[i]);
-                        float* dst = P.S.Tout + ((long long)colc * P.S.n_save + si) * NZ + 8 * q;
-                        *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
-                        *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                        const long long oi = ((long long)colc * P.S.n_save + si) * NZ + 8 * q;
+                        if (RECORD) {
+                            const float4 ta = *reinterpret_cast<const float4*>(P.S.Ttrue + oi), tb = *reinterpret_cast<const float4*>(P.S.Ttrue + oi + 4);
+                            const float r[8] = {o[0] - ta.x, o[1] - ta.y, o[2] - ta.z, o[3] - ta.w, o[4] - tb.x, o[5] - tb.y, o[6] - tb.z, o[7] - tb.w};
+                            *reinterpret_cast<float4*>(P.S.resid + oi) = make_float4(r[0], r[1], r[2], r[3]);
+                            *reinterpret_cast<float4*>(P.S.resid + oi + 4) = make_float4(r[4], r[5], r[6], r[7]);
+                            float sse = 0.f;
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) sse = fmaf(r[i], r[i], sse);
+                            lsum += (double)sse;
+                        } else {
+                            float* dst = P.S.Tout + oi;
+                            *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+                            *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+                        }
                     }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) { yn[i] = x[i]; fn[i] = f[i]; }
@@ -223,6 +268,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_rkc_tc_kernel(const unsigne
             tmem_st8f(tv, v);
             tmem_st8f(ty, yj);
             wait_st();
+        }
+        if (RECORD) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(FULL, lsum, o);
+            if (lane == 0) atomicAdd(P.S.loss_sum, lsum);
         }
         // release the MMA warp
         cta_bar();

@@ -120,11 +120,8 @@ def test_rkc_handle_rejects_what_it_cannot_do(nfc, gpu_ok):
     sv = nfc.synthetic.saveat(5)
     with pytest.raises(nfc.NfcError):
         nfc.Handle(cw, layers, 1, sv, alg="RKC2", fixed_dt=0.01)
-    h = nfc.Handle(cw, layers, 1, sv, alg="RKC2")
-    h.set_weights(O.glorot_theta(cw, layers, 2, 0.3))
-    d = nfc.synthetic.make_columns("training9")
     with pytest.raises(nfc.NfcError):
-        h.loss_grad(d["T0"], d["colp"], d["glob"], np.zeros((9, 5, 32), np.float32))
+        nfc.Handle(cw, layers, 1, sv, alg=7)
 
 
 def test_reference_api_selects_the_stabilised_method(nfc, gpu_ok):
@@ -145,3 +142,49 @@ def test_reference_api_selects_the_stabilised_method(nfc, gpu_ok):
     b = nfc.solve_nde(nde, NN, Ts(ds.T[:, 0]), nfc.Tsit5(), p)
     assert a.shape == (32, 129)
     assert rel_l2(a.T[None], b.T[None]).max() < TRAJ_TOL
+    # the 7-argument form (src/solve.jl:8-51) with the production integrator: the flux diagnosis must use the handle that holds the weights
+    full = nfc.solve_nde(ds, NN, nfc.ConvectiveAdjustmentNDE, p, nfc.ROCK4(), Ts, wTs)
+    ref = nfc.solve_nde(ds, NN, nfc.ConvectiveAdjustmentNDE, p, nfc.Tsit5(), Ts, wTs)
+    assert full["T"].shape == (32, 1153) and full["wT"].shape == (33, 1153)
+    assert rel_l2(full["T"].T[None], ref["T"].T[None]).max() < TRAJ_TOL
+    assert np.isfinite(full["wT"]).all()
+
+
+def test_loss_grad_through_the_stabilised_integrator(nfc, gpu_ok):
+    """nfc_loss_grad on an RKC2 handle (the production configuration trains with ROCK4, train_free_convection_nde.sh:3): the forward pass
+    records residuals and a cubic-Hermite tape, the continuous adjoint reads it like the Tsit5 tape.  Same continuous problem as with
+    Tsit5, so loss and gradient agree to the integrators' tolerance; both against the C twin (Tsit5) of the oracle."""
+    from oracle import c_oracle as CO
+    syn = nfc.synthetic
+    d = syn.make_columns("training9")
+    cw, layers = O.chain_spec("dense-default")
+    sv = syn.saveat(33)
+    cp10 = d["colp"].copy(); cp10[:, 2] = 10.0
+    for scale, K, tol in ((1.0, 2.0, 5e-3), (0.3, 0.0, 3e-3)):
+        theta = O.glorot_theta(cw, layers, 0, scale)
+        colp = d["colp"].copy(); colp[:, 2] = K
+        Ttrue = CO.solve(d["T0"], np.zeros_like(theta), cw, layers, cp10, d["glob"], sv, reltol=1e-6, abstol=1e-8, nthreads=8)["T"]
+        res = {}
+        for alg in ("Tsit5", "RKC2"):
+            h = nfc.Handle(cw, layers, 1, sv, alg=alg, reltol=1e-5, abstol=1e-7, adjoint_reltol=1e-5, adjoint_abstol=1e-7)
+            h.set_weights(theta)
+            res[alg] = h.loss_grad(d["T0"], colp, d["glob"], Ttrue)
+            assert (res[alg]["status"] == 0).all()
+        a, b = res["Tsit5"], res["RKC2"]
+        assert abs(a["loss"] - b["loss"]) / a["loss"] < 1e-3
+        rel = float(np.linalg.norm(a["grad"].astype(np.float64) - b["grad"]) / np.linalg.norm(a["grad"]))
+        assert rel < tol, rel
+    # default tolerances, larger batch (tensor-core RKC2 RECORD pass + batch backward kernel): finite, status clean, close to Tsit5
+    d = syn.make_columns("ocean", B=300, seed=5)
+    theta = O.glorot_theta(cw, layers, 0, 0.3)
+    colp = d["colp"].copy(); colp[:, 2] = 2.0
+    Ttrue = np.repeat(d["T0"][:, None, :], 33, axis=1) * np.float32(0.98)
+    out = {}
+    for alg in ("Tsit5", "RKC2"):
+        h = nfc.Handle(cw, layers, 1, sv, alg=alg)
+        h.set_weights(theta)
+        out[alg] = h.loss_grad(d["T0"], colp, d["glob"], Ttrue)
+        assert (out[alg]["status"] == 0).all() and np.isfinite(out[alg]["grad"]).all()
+    assert abs(out["Tsit5"]["loss"] - out["RKC2"]["loss"]) / out["Tsit5"]["loss"] < 2e-3
+    cos = float(out["Tsit5"]["grad"].astype(np.float64) @ out["RKC2"]["grad"] / np.linalg.norm(out["Tsit5"]["grad"]) / np.linalg.norm(out["RKC2"]["grad"]))
+    assert cos > 0.999
