@@ -820,7 +820,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
                 S.xch[xb][c][q][0] = y[0];
                 S.xch[xb][c][q][1] = y[7];
                 float nn[9], f[8];
-                SP::template eval<!RECORD>(&S, sbias, y, nn, pd, wq, q, twdp, false);
+                SP::template eval<true>(&S, sbias, y, nn, pd, wq, q, twdp, false);      // nfc_solve and the RECORD pass of nfc_loss_grad share ONE arithmetic
                 const float ylo = q > 0 ? S.xch[xb][c][q - 1][1] : 0.f, yhi = q < 3 ? S.xch[xb][c][q + 1][0] : 0.f;
                 faces_to_f(y, ylo, yhi, nn, bot, top, kk, P.pref, q, f);
                 tmem_st8f(kaddr(tl, s + 2, q), f);
@@ -870,10 +870,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
                 if (!isfinite(ee)) { status = ST_NAN; accept = false; dtnew = hs; }
                 else if (P.fixed_dt > 0.f) { accept = true; dtnew = P.fixed_dt; }
                 else {
-                    // PI controller exponents: the fast power (2 ulp) is ample for the trajectory, whose accept test is on ee itself; the RECORD
-                    // pass keeps powf so that its step sequence stays the CPU twin's (gradients of two step sequences differ by ~1e-3)
-                    const float q11 = RECORD ? powf(ee, 0.14f) : __powf(ee, 0.14f);
-                    float qq = q11 / (RECORD ? powf(qold, 0.08f) : __powf(qold, 0.08f));
+                    // PI controller exponents: the fast power (2 ulp) is ample for the trajectory, whose accept test is on ee itself.  The RECORD
+                    // pass uses the same arithmetic, so that mse(nfc_solve(...), truth) and the loss nfc_loss_grad reports are the same number
+                    const float q11 = __powf(ee, 0.14f);
+                    float qq = q11 / __powf(qold, 0.08f);
                     qq = fmaxf(0.1f, fminf(5.0f, qq / 0.9f));
                     accept = ee <= 1.0f;
                     dtnew = accept ? hs / qq : hs / fminf(5.0f, q11 / 0.9f);

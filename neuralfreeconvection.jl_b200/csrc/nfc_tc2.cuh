@@ -313,8 +313,8 @@ __device__ __forceinline__ void step_control(Shared2* S, const SolveParams& P, i
         if (!isfinite(ee)) { status = ST_NAN; accept = false; dtnew = hs; }
         else if (P.fixed_dt > 0.f) { accept = true; dtnew = P.fixed_dt; }
         else {
-            const float q11 = RECORD ? powf(ee, 0.14f) : __powf(ee, 0.14f);      // as in tc::solve_tc_kernel
-            float qq = q11 / (RECORD ? powf(C.qold[c], 0.08f) : __powf(C.qold[c], 0.08f));
+            const float q11 = __powf(ee, 0.14f);      // as in tc::solve_tc_kernel (solve and RECORD pass: one arithmetic)
+            float qq = q11 / __powf(C.qold[c], 0.08f);
             qq = fmaxf(0.1f, fminf(5.0f, qq / 0.9f));
             accept = ee <= 1.0f;
             dtnew = accept ? hs / qq : hs / fminf(5.0f, q11 / 0.9f);
@@ -590,8 +590,8 @@ __global__ void __launch_bounds__(NT2, 1) solve_tc2_kernel(const unsigned char* 
             for (int s = 0; s < 6; ++s) {
 #pragma unroll 1
                 for (int l = 0; l < 2; ++l) {
-                    hidden_epilogue<0, DBG, !RECORD>(S, sb, l, pdx, tl, q, tm[4 + l]);
-                    if (!ydead) hidden_epilogue<1, DBG, !RECORD>(S, sb, l, pdy, tl, q, tm[4 + l]);
+                    hidden_epilogue<0, DBG, true>(S, sb, l, pdx, tl, q, tm[4 + l]);
+                    if (!ydead) hidden_epilogue<1, DBG, true>(S, sb, l, pdy, tl, q, tm[4 + l]);
                 }
                 c1 = tick<DBG>(); tm[2] += c1 - c0; c0 = c1;
                 output_epilogue<0, DBG>(S, ks, sb, X, s, pdx, tl, q, c, P.pref, tm[6]);

@@ -48,9 +48,13 @@ def test_gradient_golden_fixed_step(nfc, gpu_ok, K):
     assert _rel(r["grad"], g["grad"]) < (1e-3 if K == 0 else 5e-3)
 
 
-@pytest.mark.parametrize("scale,K,tol", [(1.0, 0.0, 1e-3), (1.0, 2.0, 1e-3), (0.3, 0.0, 1e-3), (0.3, 2.0, 5e-3)])
+@pytest.mark.parametrize("scale,K,tol", [(1.0, 0.0, 1e-3), (1.0, 2.0, 1.5e-3), (0.3, 0.0, 1e-3), (0.3, 2.0, 5e-3)])
 def test_loss_grad_vs_c_oracle_adaptive(nfc, gpu_ok, scale, K, tol):
-    """Same float32 algorithm on CPU and GPU, adaptive steps in both passes."""
+    """Same float32 algorithm on CPU and GPU, adaptive steps in both passes.  With convective adjustment (K = 2) the two runs take
+    different -- equally valid -- step sequences (the GPU forward pass is the tensor-core kernel with the fast power function in its
+    controller, the C twin uses powf), and at reltol 1e-4 two valid step sequences give gradients 1e-3 apart: the band is measured in
+    test_gradient_converges_to_the_float64_truth below (both sides sit about 1e-3 from the truth at the default tolerance and converge
+    to it together as the tolerance tightens)."""
     d, cw, layers, theta, sv, colp, Ttrue, h = _setup(nfc, scale=scale, K=K)
     r = h.loss_grad(d["T0"], colp, d["glob"], Ttrue)
     o = CO.loss_grad_continuous(d["T0"], theta, cw, layers, colp, d["glob"], sv, Ttrue, nthreads=8)
@@ -70,8 +74,8 @@ def test_loss_matches_forward_solve(nfc, gpu_ok):
     d, cw, layers, theta, sv, colp, Ttrue, h = _setup(nfc, scale=0.3, K=2.0, B=300)
     r = h.loss_grad(d["T0"], colp, d["glob"], Ttrue)
     s = h.solve(d["T0"], colp, d["glob"])
-    # the record pass runs the SIMT kernel, nfc_solve the tensor-core kernel: different (equally valid) adaptive step sequences
-    assert abs(r["loss"] - O.mse(s["T"], Ttrue)) / r["loss"] < 2e-3
+    # the RECORD pass and nfc_solve run the same kernels with the same arithmetic: the loss IS the mse of the solve's trajectories
+    assert abs(r["loss"] - O.mse(s["T"], Ttrue)) / r["loss"] < 1e-5
 
 
 def test_gradient_vs_float64_truth(nfc, gpu_ok):
@@ -82,6 +86,31 @@ def test_gradient_vs_float64_truth(nfc, gpu_ok):
     L, g, _ = O.loss_and_grad_autograd(d["T0"][:B], theta, cw, layers, colp[:B], d["glob"], sv, Ttrue[:B], fixed_dt=1 / 1024)
     assert abs(r["loss"] - L) / L < 1e-3
     assert _rel(r["grad"], g) < 1e-3
+
+
+def test_gradient_converges_to_the_float64_truth(nfc, gpu_ok):
+    """The measured band behind the tolerances above: GPU and C twin against the converged float64 gradient (autograd on a fine fixed
+    grid) at reltol = abstol*100 = 1e-4 (the reference's setting, src/solve.jl:4), 1e-5 and 1e-6.  Both converge to the truth; at the
+    default tolerance each is within 3e-3 of it, which bounds their mutual distance (triangle inequality) -- any two correct float32
+    implementations of solve(...; reltol=1e-4) + adjoint, the Julia one included, can differ by that much."""
+    d, cw, layers, theta, sv, colp, Ttrue, _ = _setup(nfc, scale=1.0, K=2.0)
+    B = 3
+    L, g, _ = O.loss_and_grad_autograd(d["T0"][:B], theta, cw, layers, colp[:B], d["glob"], sv, Ttrue[:B], fixed_dt=1 / 1024)
+    err_gpu, err_c, dist = [], [], []
+    for rt in (1e-4, 1e-5, 1e-6):
+        h = nfc.Handle(cw, layers, 1, sv, reltol=rt, abstol=rt * 1e-2, adjoint_max_steps=4096)
+        h.set_weights(theta)
+        r = h.loss_grad(d["T0"][:B], colp[:B], d["glob"], Ttrue[:B])
+        o = CO.loss_grad_continuous(d["T0"][:B], theta, cw, layers, colp[:B], d["glob"], sv, Ttrue[:B], reltol=rt, abstol=rt * 1e-2, nthreads=3)
+        assert (r["status"] == 0).all()
+        err_gpu.append(_rel(r["grad"], g)); err_c.append(_rel(o["grad"], g)); dist.append(_rel(r["grad"], o["grad"]))
+        assert abs(r["loss"] - L) / L < 10 * rt + 1e-5
+    print("gradient error vs float64 truth at reltol 1e-4 / 1e-5 / 1e-6: GPU", err_gpu, "C twin", err_c, "GPU vs C twin", dist)
+    assert err_gpu[0] < 3e-3 and err_c[0] < 3e-3                       # the band at the reference's tolerance
+    assert err_gpu[2] < 1e-3 and err_c[2] < 1e-3                       # converged: north_star's 1e-3
+    assert err_gpu[2] < err_gpu[0] and err_c[2] < err_c[0]
+    for k in range(3):
+        assert dist[k] <= err_gpu[k] + err_c[k] + 1e-6
 
 
 def test_batch_split_and_chunking(nfc, gpu_ok, monkeypatch):
@@ -186,4 +215,6 @@ def test_record_pass_kernels_agree(nfc, gpu_ok, monkeypatch):
     assert abs(b["loss"] - c["loss"]) <= 1e-12 * abs(b["loss"])
     assert _rel(c["grad"], b["grad"]) < 1e-5
     assert abs(a["loss"] - b["loss"]) <= 2e-4 * abs(a["loss"])       # small residuals of a nearly fitted model: the loss itself cancels
-    assert _rel(b["grad"], a["grad"]) < 1e-3
+    # FP32 SIMT record pass (powf, FP32 FMA) vs tensor-core record pass (the arithmetic of nfc_solve): two valid step sequences; for these
+    # x1e-5 weights with K_CA = 2 the problem is ill-conditioned (the C twin differs from either by 1.5e-2)
+    assert _rel(b["grad"], a["grad"]) < 3e-3
