@@ -52,7 +52,7 @@ constexpr int SO_ST = SO_UB + 16384;
 static_assert(IMG16_BYTES <= SO_U, "weight image overlaps the staging buffers");
 
 struct AtcShared {
-    uint64_t bar_w, bar_a, bar_d, bar_x;
+    uint64_t bar_w, bar_a, bar_a1, bar_d, bar_x;     // bar_a / bar_a1: first / second half of an A operand published (even / odd k-steps)
     uint32_t tmem_base;
     int stop, any;
     float xu[4][2][TILE], xl[4][2][TILE], xm[4][TILE];      // boundary levels of u and w*lambda_s, max |w lambda_s| of every quarter
@@ -98,6 +98,15 @@ __device__ __forceinline__ void issue_ts(uint32_t d, uint32_t a, uint32_t blo, u
         else mma_ts2<true>(d, a + 8 * j, blo + kadv * j, bhi, id);
     }
 }
+// the k-steps of one parity (HALF 0: even = the first halves of the quarters' operand slices, published first)
+template <int NK, int HALF, bool FIRST>
+__device__ __forceinline__ void issue_ts_half(uint32_t d, uint32_t a, uint32_t blo, uint32_t bhi, uint32_t kadv, uint32_t id) {
+#pragma unroll
+    for (int j = HALF; j < NK; j += 2) {
+        if (FIRST && j == 0) mma_ts2<false>(d, a + 8 * j, blo + kadv * j, bhi, id);
+        else mma_ts2<true>(d, a + 8 * j, blo + kadv * j, bhi, id);
+    }
+}
 // SS-form contraction over the 128 columns (8 k-steps of 16 columns = 256 B in both staging buffers).  The accumulators collect ONE
 // Runge-Kutta step (first = stage 0 overwrites) and are flushed to the CTA's fp32 gradient row in stage 7: the tensor core adds with
 // truncation, and an accumulator that lived for the whole kernel (17 000 additions of increments far below its own magnitude) drifted
@@ -123,8 +132,9 @@ __device__ __forceinline__ void atc_mma_loop(AtcShared* S, uint32_t sbase) {
             const bool dw = s < 6;
             uint32_t tb, img;
             // (1) z1 = u W1^T
-            mbar_wait(&S->bar_a, pa); pa ^= 1;
+            mbar_wait(&S->bar_a, pa);
             if (s == 0 && *reinterpret_cast<volatile int*>(&S->stop)) return;
+            mbar_wait(&S->bar_a1, pa); pa ^= 1;
             fence_after_sync();
             tb = S->tmem_base; img = sbase; asm volatile("" : "+r"(tb), "+r"(img));
             {
@@ -135,20 +145,31 @@ __device__ __forceinline__ void atc_mma_loop(AtcShared* S, uint32_t sbase) {
                 issue_ts<2, false>(tb + TA_D, tb + TA_A, lo, hi, 256, ID_F);                            // a_hi W_hi
             }
             mma_commit(&S->bar_d);
-            // (2) z2 = a1 W2^T
-            mbar_wait(&S->bar_a, pa); pa ^= 1;
+            // (2) z2 = a1 W2^T: the even k-steps start as soon as the first halves of the operand are published
+            mbar_wait(&S->bar_a, pa);
             fence_after_sync();
             tb = S->tmem_base; img = sbase; asm volatile("" : "+r"(tb), "+r"(img));
             {
                 const uint64_t b = make_desc(img + OFF16_W2, 128 * 16, 128);
                 const uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32);
-                issue_ts<8, true>(tb + TA_D, tb + TA_A + 64, lo, hi, 256, ID_F);
-                issue_ts<8, false>(tb + TA_D, tb + TA_A, lo + (W2H_BYTES >> 4), hi, 256, ID_F);
-                issue_ts<8, false>(tb + TA_D, tb + TA_A, lo, hi, 256, ID_F);
+                issue_ts_half<8, 0, true>(tb + TA_D, tb + TA_A + 64, lo, hi, 256, ID_F);
+                issue_ts_half<8, 0, false>(tb + TA_D, tb + TA_A, lo + (W2H_BYTES >> 4), hi, 256, ID_F);
+                issue_ts_half<8, 0, false>(tb + TA_D, tb + TA_A, lo, hi, 256, ID_F);
+            }
+            mbar_wait(&S->bar_a1, pa); pa ^= 1;
+            fence_after_sync();
+            tb = S->tmem_base; img = sbase; asm volatile("" : "+r"(tb), "+r"(img));
+            {
+                const uint64_t b = make_desc(img + OFF16_W2, 128 * 16, 128);
+                const uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32);
+                issue_ts_half<8, 1, false>(tb + TA_D, tb + TA_A + 64, lo, hi, 256, ID_F);
+                issue_ts_half<8, 1, false>(tb + TA_D, tb + TA_A, lo + (W2H_BYTES >> 4), hi, 256, ID_F);
+                issue_ts_half<8, 1, false>(tb + TA_D, tb + TA_A, lo, hi, 256, ID_F);
             }
             mma_commit(&S->bar_d);
             // (3) g2 = d3 W3 (image: [hi rows 0..31; lo rows 32..63] x K = 128, i.e. transposed: k' 0..31 hi, 32..63 lo), then dW3^T += a2^T d3
-            mbar_wait(&S->bar_a, pa); pa ^= 1;
+            mbar_wait(&S->bar_a, pa);
+            mbar_wait(&S->bar_a1, pa); pa ^= 1;
             fence_after_sync();
             tb = S->tmem_base; img = sbase; asm volatile("" : "+r"(tb), "+r"(img));
             {
@@ -165,15 +186,25 @@ __device__ __forceinline__ void atc_mma_loop(AtcShared* S, uint32_t sbase) {
                 mma_commit(&S->bar_x);
             }
             // (4) g1 = d2 W2, then dW2 += d2^T [1 a1]
-            mbar_wait(&S->bar_a, pa); pa ^= 1;
+            mbar_wait(&S->bar_a, pa);
             fence_after_sync();
             tb = S->tmem_base; img = sbase; asm volatile("" : "+r"(tb), "+r"(img));
             {
                 const uint64_t b = make_desc(img + OFF16_W2, 128, 128 * 16);
                 const uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32);
-                issue_ts<8, true>(tb + TA_D, tb + TA_A + 64, lo, hi, 16, ID_T128);
-                issue_ts<8, false>(tb + TA_D, tb + TA_A, lo + (W2H_BYTES >> 4), hi, 16, ID_T128);
-                issue_ts<8, false>(tb + TA_D, tb + TA_A, lo, hi, 16, ID_T128);
+                issue_ts_half<8, 0, true>(tb + TA_D, tb + TA_A + 64, lo, hi, 16, ID_T128);
+                issue_ts_half<8, 0, false>(tb + TA_D, tb + TA_A, lo + (W2H_BYTES >> 4), hi, 16, ID_T128);
+                issue_ts_half<8, 0, false>(tb + TA_D, tb + TA_A, lo, hi, 16, ID_T128);
+            }
+            mbar_wait(&S->bar_a1, pa); pa ^= 1;
+            fence_after_sync();
+            tb = S->tmem_base; img = sbase; asm volatile("" : "+r"(tb), "+r"(img));
+            {
+                const uint64_t b = make_desc(img + OFF16_W2, 128, 128 * 16);
+                const uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32);
+                issue_ts_half<8, 1, false>(tb + TA_D, tb + TA_A + 64, lo, hi, 16, ID_T128);
+                issue_ts_half<8, 1, false>(tb + TA_D, tb + TA_A, lo + (W2H_BYTES >> 4), hi, 16, ID_T128);
+                issue_ts_half<8, 1, false>(tb + TA_D, tb + TA_A, lo, hi, 16, ID_T128);
             }
             mma_commit(&S->bar_d);
             if (dw) {
@@ -182,14 +213,23 @@ __device__ __forceinline__ void atc_mma_loop(AtcShared* S, uint32_t sbase) {
                 mma_commit(&S->bar_x);
             }
             // (5) ubar = d1 W1 (hi and lo images are adjacent along the transposed N: one N = 64 operand), then dW1 += d1^T [u 1]
-            mbar_wait(&S->bar_a, pa); pa ^= 1;
+            mbar_wait(&S->bar_a, pa);
             fence_after_sync();
             tb = S->tmem_base; img = sbase; asm volatile("" : "+r"(tb), "+r"(img));
             {
                 const uint64_t b = make_desc(img + OFF16_W1, 128, 128 * 16);
                 const uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32);
-                issue_ts<8, true>(tb + TA_D, tb + TA_A + 64, lo, hi, 16, ID_T64);
-                issue_ts<8, false>(tb + TA_D, tb + TA_A, lo, hi, 16, ID_T64);
+                issue_ts_half<8, 0, true>(tb + TA_D, tb + TA_A + 64, lo, hi, 16, ID_T64);
+                issue_ts_half<8, 0, false>(tb + TA_D, tb + TA_A, lo, hi, 16, ID_T64);
+            }
+            mbar_wait(&S->bar_a1, pa); pa ^= 1;
+            fence_after_sync();
+            tb = S->tmem_base; img = sbase; asm volatile("" : "+r"(tb), "+r"(img));
+            {
+                const uint64_t b = make_desc(img + OFF16_W1, 128, 128 * 16);
+                const uint32_t lo = (uint32_t)b, hi = (uint32_t)(b >> 32);
+                issue_ts_half<8, 1, false>(tb + TA_D, tb + TA_A + 64, lo, hi, 16, ID_T64);
+                issue_ts_half<8, 1, false>(tb + TA_D, tb + TA_A, lo, hi, 16, ID_T64);
             }
             mma_commit(&S->bar_d);
             if (dw) {
@@ -201,6 +241,21 @@ __device__ __forceinline__ void atc_mma_loop(AtcShared* S, uint32_t sbase) {
     }
 }
 
+// (max(lo,0), max(hi,0)) -> packed bf16
+__device__ __forceinline__ uint32_t pack_bf16_relu(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+// packed bf16 pair times a packed power of two (exact): the per-column scale of the staged deltas costs one instruction per pair
+__device__ __forceinline__ uint32_t mul_bf16x2(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+// relu mask, one instruction per activation: shift the sign bit of the pre-activation into m (MSB first: after 32 calls element e sits at
+// bit 31 - e and m holds "v < 0"; the caller inverts it once).  v == +0 counts as active, harmlessly: its delta meets a zero activation
+__device__ __forceinline__ void mask_push(uint32_t& m, float v) { m = __funnelshift_l(__float_as_uint(v), m, 1); }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     uint32_t r;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
@@ -387,6 +442,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) adjoint_tc_kernel(const unsigned 
     if (threadIdx.x == 0) {
         mbar_init(&S.bar_w, 1);
         mbar_init(&S.bar_a, NCT);
+        mbar_init(&S.bar_a1, NCT);
         mbar_init(&S.bar_d, 1);
         mbar_init(&S.bar_x, 1);
         S.stop = 0; S.any = 0;
@@ -547,6 +603,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) adjoint_tc_kernel(const unsigned 
                     fence_before_sync();
                     fence_async_smem();
                     mbar_arrive(&S.bar_a);
+                    mbar_arrive(&S.bar_a1);
                     // keep w*lambda_s and u for the face quantities (computed after the exchange, below)
 #pragma unroll
                     for (int i = 0; i < 8; ++i) { uca[i] = u[i]; lnew[i] = lw[i]; }
@@ -593,86 +650,102 @@ __global__ void __launch_bounds__(NTHREADS, 1) adjoint_tc_kernel(const unsigned 
                     for (int i = 0; i < 4; ++i) split2h(d3[2 * i] * s3, d3[2 * i + 1] * s3, ph3[i], pl3[i]);
                 }
                 mask1 = 0u;
-#pragma unroll
-                for (int ch = 0; ch < 2; ++ch) {
-                    uint32_t r[16], ph[8], pl[8], pb[8];
-                    tmem_ld16(tl + TA_D + 32 * q + 16 * ch, r);
+                {
+                    // the whole D slice first: the layer-2 MMAs of the even k-steps overwrite D as soon as the first halves are published
+                    uint32_t r[32];
+                    tmem_ld16(tl + TA_D + 32 * q, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+                    tmem_ld16(tl + TA_D + 32 * q + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
                     wait_ld();
-                    const float* b = sb + 32 * q + 16 * ch;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float2 bb = *reinterpret_cast<const float2*>(b + 2 * i);
-                        const float v0 = fmaf(__uint_as_float(r[2 * i]), c1, bb.x), v1 = fmaf(__uint_as_float(r[2 * i + 1]), c1, bb.y);
-                        mask1 |= (v0 > 0.f ? 1u : 0u) << (16 * ch + 2 * i);
-                        mask1 |= (v1 > 0.f ? 1u : 0u) << (16 * ch + 2 * i + 1);
-                        split2h_relu(v0, v1, ph[i], pl[i]);
-                        pb[i] = pack_bf16(fmaxf(v0, 0.f), fmaxf(v1, 0.f));
-                    }
-                    tmem_st8(tl + TA_A + 16 * q + 8 * ch, ph);
-                    tmem_st8(tl + TA_A + 64 + 16 * q + 8 * ch, pl);
-                    if (dw) {
-                        *reinterpret_cast<uint4*>(smem + SO_A1 + (4 * q + 2 * ch) * CH + c * 16) = make_uint4(pb[0], pb[1], pb[2], pb[3]);
-                        *reinterpret_cast<uint4*>(smem + SO_A1 + (4 * q + 2 * ch + 1) * CH + c * 16) = make_uint4(pb[4], pb[5], pb[6], pb[7]);
+                    for (int ch = 0; ch < 2; ++ch) {
+                        uint32_t ph[8], pl[8], pb[8];
+                        const float* b = sb + 32 * q + 16 * ch;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float2 bb = *reinterpret_cast<const float2*>(b + 2 * i);
+                            const float v0 = fmaf(__uint_as_float(r[16 * ch + 2 * i]), c1, bb.x), v1 = fmaf(__uint_as_float(r[16 * ch + 2 * i + 1]), c1, bb.y);
+                            mask_push(mask1, v0); mask_push(mask1, v1);
+                            split2h_relu(v0, v1, ph[i], pl[i]);
+                            pb[i] = pack_bf16_relu(v0, v1);
+                        }
+                        tmem_st8(tl + TA_A + 16 * q + 8 * ch, ph);
+                        tmem_st8(tl + TA_A + 64 + 16 * q + 8 * ch, pl);
+                        if (dw) {
+                            *reinterpret_cast<uint4*>(smem + SO_A1 + (4 * q + 2 * ch) * CH + c * 16) = make_uint4(pb[0], pb[1], pb[2], pb[3]);
+                            *reinterpret_cast<uint4*>(smem + SO_A1 + (4 * q + 2 * ch + 1) * CH + c * 16) = make_uint4(pb[4], pb[5], pb[6], pb[7]);
+                        }
+                        wait_st();
+                        fence_before_sync();
+                        if (ch == 0) mbar_arrive(&S.bar_a);
+                        else { fence_async_smem(); mbar_arrive(&S.bar_a1); }
                     }
                 }
-                wait_st();
-                fence_before_sync();
-                fence_async_smem();
-                mbar_arrive(&S.bar_a);
+                mask1 = ~mask1;
                 if (s < 6) coop_load(P, S, smem, s + 1, 0, warp, lane);      // under the layer-2 MMAs
                 else flush_acc(g, tl, c, q, sc);                             // every contraction of this step has completed (bar_x at E0)
                 // ---- E2: z2 -> a2 (staged for dW3^T, relu mask); output-layer delta -> A operand ----
                 mbar_wait(&S.bar_d, pd); pd ^= 1;
                 fence_after_sync();
                 mask2 = 0u;
-#pragma unroll
-                for (int ch = 0; ch < 2; ++ch) {
-                    uint32_t r[16], pb[8];
-                    tmem_ld16(tl + TA_D + 32 * q + 16 * ch, r);
+                {
+                    uint32_t r[32];
+                    tmem_ld16(tl + TA_D + 32 * q, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+                    tmem_ld16(tl + TA_D + 32 * q + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
                     wait_ld();
-                    const float* b = sb + 128 + 32 * q + 16 * ch;
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float2 bb = *reinterpret_cast<const float2*>(b + 2 * i);
-                        const float v0 = fmaf(__uint_as_float(r[2 * i]), c2, bb.x), v1 = fmaf(__uint_as_float(r[2 * i + 1]), c2, bb.y);
-                        mask2 |= (v0 > 0.f ? 1u : 0u) << (16 * ch + 2 * i);
-                        mask2 |= (v1 > 0.f ? 1u : 0u) << (16 * ch + 2 * i + 1);
-                        pb[i] = pack_bf16(fmaxf(v0, 0.f), fmaxf(v1, 0.f));
-                    }
-                    if (dw) {
-                        *reinterpret_cast<uint4*>(smem + SO_X + (4 * q + 2 * ch) * CH + c * 16) = make_uint4(pb[0], pb[1], pb[2], pb[3]);
-                        *reinterpret_cast<uint4*>(smem + SO_X + (4 * q + 2 * ch + 1) * CH + c * 16) = make_uint4(pb[4], pb[5], pb[6], pb[7]);
+                    for (int ch = 0; ch < 2; ++ch) {
+                        uint32_t pb[8];
+                        const float* b = sb + 128 + 32 * q + 16 * ch;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float2 bb = *reinterpret_cast<const float2*>(b + 2 * i);
+                            const float v0 = fmaf(__uint_as_float(r[16 * ch + 2 * i]), c2, bb.x), v1 = fmaf(__uint_as_float(r[16 * ch + 2 * i + 1]), c2, bb.y);
+                            mask_push(mask2, v0); mask_push(mask2, v1);
+                            pb[i] = pack_bf16_relu(v0, v1);
+                        }
+                        if (dw) {
+                            *reinterpret_cast<uint4*>(smem + SO_X + (4 * q + 2 * ch) * CH + c * 16) = make_uint4(pb[0], pb[1], pb[2], pb[3]);
+                            *reinterpret_cast<uint4*>(smem + SO_X + (4 * q + 2 * ch + 1) * CH + c * 16) = make_uint4(pb[4], pb[5], pb[6], pb[7]);
+                        }
                     }
                 }
+                mask2 = ~mask2;
                 tmem_st4(tl + TA_A + 4 * q, ph3);
                 tmem_st4(tl + TA_A + 64 + 4 * q, pl3);
                 wait_st();
                 fence_before_sync();
                 fence_async_smem();
                 mbar_arrive(&S.bar_a);
+                mbar_arrive(&S.bar_a1);
                 // ---- E4 / E5: g2 -> d2 = g2 . relu'(z2), g1 -> d1 = g1 . relu'(z1): next operand + staged (true scale) for dW2 / dW1 ----
 #pragma unroll 1
                 for (int l = 0; l < 2; ++l) {
                     mbar_wait(&S.bar_d, pd); pd ^= 1;
                     fence_after_sync();
                     const float cg = l == 0 ? sc.c_g2 : sc.c_g1;
-                    const float cst = (l == 0 ? sc.inv_sd2 : sc.inv_sd1) / scol;
+                    const float cst = (l == 0 ? sc.inv_sd2 : sc.inv_sd1) / scol;      // a power of two: exact in bf16
+                    const uint32_t cst2 = pack_bf16(cst, cst);
                     const uint32_t mk = l == 0 ? mask2 : mask1;
                     uint32_t pb[16];
-#pragma unroll
-                    for (int ch = 0; ch < 2; ++ch) {
-                        uint32_t r[16], ph[8], pl[8];
-                        tmem_ld16(tl + TA_D + 32 * q + 16 * ch, r);
+                    {
+                        uint32_t r[32];
+                        tmem_ld16(tl + TA_D + 32 * q, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
+                        tmem_ld16(tl + TA_D + 32 * q + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
                         wait_ld();
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const float v0 = ((mk >> (16 * ch + 2 * i)) & 1u) ? __uint_as_float(r[2 * i]) * cg : 0.f;
-                            const float v1 = ((mk >> (16 * ch + 2 * i + 1)) & 1u) ? __uint_as_float(r[2 * i + 1]) * cg : 0.f;
-                            split2h(v0, v1, ph[i], pl[i]);
-                            pb[8 * ch + i] = pack_bf16(v0 * cst, v1 * cst);
+                        for (int ch = 0; ch < 2; ++ch) {
+                            uint32_t ph[8], pl[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float v0 = ((mk >> (31 - (16 * ch + 2 * i))) & 1u) ? __uint_as_float(r[16 * ch + 2 * i]) * cg : 0.f;
+                                const float v1 = ((mk >> (31 - (16 * ch + 2 * i + 1))) & 1u) ? __uint_as_float(r[16 * ch + 2 * i + 1]) * cg : 0.f;
+                                split2h(v0, v1, ph[i], pl[i]);
+                                pb[8 * ch + i] = mul_bf16x2(pack_bf16(v0, v1), cst2);
+                            }
+                            tmem_st8(tl + TA_A + 16 * q + 8 * ch, ph);
+                            tmem_st8(tl + TA_A + 64 + 16 * q + 8 * ch, pl);
+                            if (ch == 0) { wait_st(); fence_before_sync(); mbar_arrive(&S.bar_a); }
                         }
-                        tmem_st8(tl + TA_A + 16 * q + 8 * ch, ph);
-                        tmem_st8(tl + TA_A + 64 + 16 * q + 8 * ch, pl);
                     }
                     if (dw) {
                         mbar_wait(&S.bar_x, px); px ^= 1;          // the previous contraction (issued behind this layer's MMAs) has read the X staging buffer
@@ -683,7 +756,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) adjoint_tc_kernel(const unsigned 
                     wait_st();
                     fence_before_sync();
                     fence_async_smem();
-                    mbar_arrive(&S.bar_a);
+                    mbar_arrive(&S.bar_a1);
                     if (l == 0 && s < 6) coop_load(P, S, smem, s + 1, 1, warp, lane);      // under the g1 MMAs
                 }
                 // ---- E6: kappa_s = (W1^T d1 + K_CA part) / w ----
