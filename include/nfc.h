@@ -154,6 +154,19 @@ int32_t nfc_solve_ensemble(nfc_handle* h, const float* theta_members, int64_t n_
 /* diagnostics: attempted backward (adjoint) steps per column of the last nfc_loss_grad chunk (the analogue of naccept + nreject) */
 int32_t nfc_get_adjoint_steps(nfc_handle* h, int32_t* out, int64_t n);
 
+/* Kernel selection and scratch budgets (defaults are chosen by batch size; the same names in upper case with the prefix NFC_ are read
+ * from the environment at nfc_create / call time and win over the defaults):
+ *   tc               0: FP32 SIMT kernels; 1: tensor-core kernels (default Chain only, the default there)
+ *   tc_tiles         0: pick by batch size; 1 / 2: one / two 128-column tiles in flight per CTA in the forward solve
+ *   tc2_min_columns  batch size from which tc_tiles = 0 picks two tiles (default 98304)
+ *   tc_record        0: forward (RECORD) pass of nfc_loss_grad on the FP32 SIMT kernel
+ *   sched            0: columns served in input order; 1 (default): longest first from the previous call's step counts
+ *   adj_small_max    batches up to this many columns run the one-column-per-CTA backward kernel (default 7400; 0 = never)
+ *   adj_tc           0: batch backward pass on the FP32 SIMT kernel instead of the tensor-core kernel
+ *   e2e_pieces       nfc_solve: pieces whose device->host copy overlaps the next piece's solve (0 = auto: 3 from 65536 columns)
+ *   tape_gib         tape budget of nfc_loss_grad in GiB; larger batches are processed in chunks (0 = default 48) */
+int32_t nfc_set_option(nfc_handle* h, const char* name, int64_t value);
+
 /* diagnostics: the forward tape of one column of the last nfc_loss_grad chunk -- per accepted step 168 floats: u_n[32], then the Tsit5
  * dense output in power basis c1..c4 [4][32] (u(t_n + th h) = u_n + h th (c1 + th (c2 + th (c3 + th c4)))), t_n, h_n, 6 unused. */
 int32_t nfc_get_tape(nfc_handle* h, int64_t column, float* rows, int32_t max_rows, int32_t* n_rows);

@@ -14,7 +14,7 @@ NFC_MAX_LAYERS = 8
 EXPORTS = ["nfc_create", "nfc_destroy", "nfc_last_error", "nfc_n_params", "nfc_set_weights", "nfc_set_saveat",
            "nfc_get_counters", "nfc_rhs", "nfc_solve", "nfc_diagnose_flux", "nfc_loss_grad", "nfc_rhs_dev",
            "nfc_solve_dev", "nfc_loss_grad_dev", "nfc_sync", "nfc_measure_fp32_peak", "nfc_get_adjoint_steps", "nfc_embedded_solve",
-           "nfc_solve_ensemble", "nfc_comm_unique_id", "nfc_comm_init", "nfc_comm_destroy", "nfc_get_tape"]
+           "nfc_solve_ensemble", "nfc_comm_unique_id", "nfc_comm_init", "nfc_comm_destroy", "nfc_get_tape", "nfc_set_option"]
 
 
 class NfcConfig(C.Structure):
@@ -67,6 +67,7 @@ def load():
     lib.nfc_get_adjoint_steps.argtypes = [vp, ip, C.c_int64]
     lib.nfc_measure_fp32_peak.argtypes = [C.c_int32, C.c_float, dp]
     lib.nfc_get_tape.argtypes = [vp, C.c_int64, fp, C.c_int32, ip]
+    lib.nfc_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     lib.nfc_comm_unique_id.argtypes = [vp]
     lib.nfc_comm_init.argtypes = [vp, vp, C.c_int32, C.c_int32]
     lib.nfc_comm_destroy.argtypes = [vp]
@@ -275,6 +276,10 @@ class Handle:
 
     def sync(self):
         self._check(self.lib.nfc_sync(self.h), "nfc_sync")
+
+    def set_option(self, name, value):
+        """nfc_set_option: kernel selection / scratch budgets (include/nfc.h lists the names)."""
+        self._check(self.lib.nfc_set_option(self.h, name.encode(), int(value)), "nfc_set_option")
 
     def tape(self, column, max_rows=4096):
         """nfc_get_tape: [n_rows][168] forward tape of one column of the last loss_grad chunk (u, c1..c4, t, h per accepted step)."""

@@ -613,7 +613,7 @@ int adjoint_loss_grad(nfc_handle* h, const float* T0, const float* colp, float p
         return 0;
     }
     // chunk the batch so that tape + residuals stay inside the scratch budget (default 48 GiB of the 180 GB, NFC_TAPE_GIB overrides)
-    double budget = 48.0;
+    double budget = h->tape_gib > 0 ? h->tape_gib : 48.0;
     if (const char* e = getenv("NFC_TAPE_GIB")) budget = atof(e) > 0 ? atof(e) : budget;
     const size_t per_col = sizeof(float) * ((size_t)cap * TAPE_STRIDE + (size_t)n_save * NZ);
     int64_t chunk = (int64_t)(budget * 1073741824.0 / (double)per_col);

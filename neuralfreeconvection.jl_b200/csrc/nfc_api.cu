@@ -204,6 +204,7 @@ int launch_solve(nfc_handle* h, SolveParams& P, cudaStream_t st, bool reset_coun
     // tensor-core kernels: the forward solve always (default Chain), the RECORD pass of loss_grad with the FP16x2 split (NFC_TC_RECORD=0: SIMT)
     if (h->use_tc && h->arch == ARCH_DEFAULT && (!RECORD || (h->tc_fp16 && h->tc_record))) {
         const int gridt = (int)std::min<long long>(h->num_sms, (B + tc::TILE - 1) / tc::TILE);
+#ifdef NFC_DEBUG_TIMERS          // debug build only: phase timers of CTA 0 (clock64) and the timing-experiment knob; the release kernels ignore both
         if (!RECORD) {
             if (const char* e = getenv("NFC_TC_NPROD")) P.tape_cap = atoi(e);   // timing experiments only (results are wrong for < 6)
             if (getenv("NFC_TC_DEBUG")) {                                        // phase timers of CTA 0 (clock64), printed after the kernel
@@ -212,14 +213,22 @@ int launch_solve(nfc_handle* h, SolveParams& P, cudaStream_t st, bool reset_coun
                 P.resid = h->a_resid.p;
             }
         }
+#endif
         // two tiles in flight per CTA (nfc_tc2.cuh): +17..25 % throughput once the batch gives every one of the 148 x 256 column slots
         // several columns; below that the one-tile kernel's lower step latency (29 vs 42 us) wins.  NFC_TC_TILES=1|2 forces a kernel.
         const bool two_tiles = h->tc_fp16 && (h->tc_tiles == 2 || (h->tc_tiles == 0 && B >= h->tc2_min_columns));
+#ifdef NFC_DEBUG_TIMERS
         const bool dbg = !RECORD && P.resid;
+#else
+        const bool dbg = false;
+#endif
         if (two_tiles) {
             const int grid2 = (int)std::min<long long>(h->num_sms, (B + 2 * tc::TILE - 1) / (2 * tc::TILE));
+#ifdef NFC_DEBUG_TIMERS
             if (dbg) tc2::solve_tc2_kernel<true, false><<<grid2, tc2::NT2, tc2::SMEM2_BYTES, st>>>(h->d_wimg.p, P);
-            else tc2::solve_tc2_kernel<false, RECORD><<<grid2, tc2::NT2, tc2::SMEM2_BYTES, st>>>(h->d_wimg.p, P);
+            else
+#endif
+            tc2::solve_tc2_kernel<false, RECORD><<<grid2, tc2::NT2, tc2::SMEM2_BYTES, st>>>(h->d_wimg.p, P);
         } else if (h->tc_fp16) tc::solve_tc_kernel<tc::SplitFP16x2, RECORD><<<gridt, tc::NTHREADS, tc::IMG16_BYTES, st>>>(h->d_wimg.p, P);
         else tc::solve_tc_kernel<tc::SplitBF16x3, false><<<gridt, tc::NTHREADS, tc::IMG_BYTES, st>>>(h->d_wimg.p, P);
         if (dbg && two_tiles) {
@@ -576,7 +585,10 @@ int32_t nfc_create(const nfc_config* cfg, nfc_handle** out) {
             cudaFuncSetAttribute(tc::solve_tc_kernel<tc::SplitFP16x2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::IMG16_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(tc2::solve_tc2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM2_BYTES) != cudaSuccess ||
             cudaFuncSetAttribute(tc2::solve_tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM2_BYTES) != cudaSuccess ||
-            cudaFuncSetAttribute(tc2::solve_tc2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM2_BYTES) != cudaSuccess) { h->err = "cudaFuncSetAttribute(tc) failed"; return bail(-10); }
+#ifdef NFC_DEBUG_TIMERS
+            cudaFuncSetAttribute(tc2::solve_tc2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM2_BYTES) != cudaSuccess ||
+#endif
+            false) { h->err = "cudaFuncSetAttribute(tc) failed"; return bail(-10); }
         h->tc_fp16 = true;                                       // default split: FP16x2 (3 MMAs / product); NFC_TC_SPLIT=bf16 selects BF16x3 (6)
         if (const char* e3 = getenv("NFC_TC_SPLIT")) h->tc_fp16 = strcmp(e3, "bf16") != 0;
         if (const char* e4 = getenv("NFC_TC_TILES")) h->tc_tiles = atoi(e4);            // 0 auto, 1 / 2: force the one- / two-tile solve kernel
@@ -688,6 +700,23 @@ int32_t nfc_get_adjoint_steps(nfc_handle* h, int32_t* out, int64_t n) {
     NFC_CUDA(h, cudaDeviceSynchronize());
     if (n > h->a_adjsteps_n) return fail(h, -2, "only %lld columns in the last loss_grad batch", (long long)h->a_adjsteps_n);
     NFC_CUDA(h, cudaMemcpy(out, h->a_adjsteps.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int32_t nfc_set_option(nfc_handle* h, const char* name, int64_t value) {
+    if (!h || !name) return -1;
+    const std::string n(name);
+    const bool def = h->arch == ARCH_DEFAULT;
+    if (n == "tc") { if (value && !def) return fail(h, -3, "the tensor-core kernels exist for the default Chain only"); h->use_tc = value != 0; }
+    else if (n == "tc_tiles") { if (value < 0 || value > 2) return fail(h, -2, "tc_tiles: 0 (auto), 1 or 2"); h->tc_tiles = (int)value; }
+    else if (n == "tc2_min_columns") h->tc2_min_columns = value;
+    else if (n == "tc_record") h->tc_record = value != 0;
+    else if (n == "sched") h->use_sched = value != 0;
+    else if (n == "adj_small_max") h->adj_small_max = value;
+    else if (n == "adj_tc") h->adj_tc = value != 0;
+    else if (n == "e2e_pieces") { if (value < 0 || value > 8) return fail(h, -2, "e2e_pieces: 0 (auto) .. 8"); h->e2e_pieces = (int)value; }
+    else if (n == "tape_gib") { if (value < 0) return fail(h, -2, "tape_gib: >= 0 (0 = default 48)"); h->tape_gib = (double)value; }
+    else return fail(h, -2, "unknown option '%s' (tc, tc_tiles, tc2_min_columns, tc_record, sched, adj_small_max, adj_tc, e2e_pieces, tape_gib)", name);
     return 0;
 }
 
@@ -839,6 +868,7 @@ int32_t nfc_solve(nfc_handle* h, const float* T0, const float* colp, const float
     // Large batches are solved in three pieces so that the device->host copy of one piece (the trajectories dominate the
     // end-to-end time: 1.08 GB for 65 536 columns x 129 saves) overlaps the solve of the next one (second stream; measured +32 % end to end).
     int npieces = (B >= 65536) ? 3 : 1;
+    if (h->e2e_pieces > 0) npieces = h->e2e_pieces;
     if (const char* e = getenv("NFC_E2E_PIECES")) npieces = std::max(1, std::min(8, atoi(e)));
     if (B < 8192 * npieces) npieces = 1;
     const int64_t piece = ((B + npieces - 1) / npieces + 127) / 128 * 128;

@@ -71,6 +71,8 @@ struct nfc_handle {
     bool tc_record = true;                  // forward (RECORD) pass of loss_grad on the tensor-core kernels (FP16x2 split)
     int tc_tiles = 0;                       // FP16x2 solve: 0 = pick by batch size, 1 = one tile per CTA (nfc_tc.cuh), 2 = two tiles in flight (nfc_tc2.cuh)
     int64_t tc2_min_columns = 98304;        // auto: two tiles from this batch size on
+    int e2e_pieces = 0;                     // nfc_solve: pieces whose device->host copies overlap the next piece's solve (0 = pick by batch size)
+    double tape_gib = 0.0;                  // scratch budget of nfc_loss_grad's tape in GiB (0 = default 48)
     bool adj_tc = true;                     // batch backward pass of loss_grad on the tensor cores (default Chain, FP16x2; NFC_ADJ_TC=0: FP32 SIMT kernel)
     nfc::atc::AtcScales atc_scales{};
     bool tc_fp16 = false;                   // tensor-core split: false = BF16x3 (6 MMAs / product), true = FP16x2 (3 MMAs, scaled operands)

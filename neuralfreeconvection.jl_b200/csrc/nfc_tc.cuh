@@ -704,17 +704,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ TcShared S;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    tc_prologue(&S, smem_raw, gimg, warp, SP::IMG, (!RECORD && P.tape_cap >= 1 && P.tape_cap <= 6) ? P.tape_cap : 6);   // forward solve: tape_cap doubles as a timing knob
+#ifdef NFC_DEBUG_TIMERS
+    tc_prologue(&S, smem_raw, gimg, warp, SP::IMG, (!RECORD && P.tape_cap >= 1 && P.tape_cap <= 6) ? P.tape_cap : 6);   // debug build: tape_cap doubles as a timing knob
+    long long* const dbgbuf = RECORD ? nullptr : reinterpret_cast<long long*>(P.resid);                                  //              P.resid carries the phase timers
+#else
+    tc_prologue(&S, smem_raw, gimg, warp, SP::IMG);
+    long long* const dbgbuf = nullptr;
+#endif
     const uint32_t smem_img = smem_u32(smem_raw);
     const float* sbias = reinterpret_cast<const float*>(smem_raw + SP::BIAS_OFF);
     if (warp >= NCT / 32) {
         reg_dec<REGS_MMA>();
-        if (warp == NCT / 32) mma_warp_loop<SP>(&S, smem_img, lane, RECORD ? nullptr : reinterpret_cast<long long*>(P.resid));   // forward solve: P.resid carries the debug timers
+        if (warp == NCT / 32) mma_warp_loop<SP>(&S, smem_img, lane, dbgbuf);
     } else {
         reg_inc<REGS_COL>();
         const int wq = warp & 3, q = warp >> 2, c = 32 * wq + lane;
         long long twd[4] = {0, 0, 0, 0};
-        long long* const twdp = (!RECORD && P.resid) ? twd : nullptr;      // phase timers only with NFC_TC_DEBUG=1
+        long long* const twdp = dbgbuf ? twd : nullptr;      // phase timers: debug build with NFC_TC_DEBUG=1 only
         const long long tstart = clock64();
         const uint32_t tl = S.tmem_base + ((uint32_t)(32 * wq) << 16);
         int pd = 0, xb = 0, pb = 0;
@@ -941,8 +947,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
                 if (status != ST_OK) done = true;
             }
         }
-        if (!RECORD && P.resid && blockIdx.x == 0 && threadIdx.x == 0) {
-            long long* dbg = reinterpret_cast<long long*>(P.resid);
+        if (dbgbuf && blockIdx.x == 0 && threadIdx.x == 0) {
+            long long* dbg = dbgbuf;
             dbg[16] = twd[0]; dbg[17] = twd[1]; dbg[18] = twd[2]; dbg[19] = clock64() - tstart;
         }
         if (RECORD) {

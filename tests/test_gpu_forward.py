@@ -344,3 +344,26 @@ def test_two_tile_kernel_edge_cases(nfc, gpu_ok, monkeypatch):
     assert r["status"][140] == 2 and (np.delete(r["status"], 140) == 0).all()
     r = both(140, max_iters=5)
     assert (r["status"] == 1).sum() > 100      # ST_MAXITERS
+
+
+def test_set_option_selects_kernels(nfc, gpu_ok):
+    """nfc_set_option (include/nfc.h): the kernel-selection knobs have an API surface, not only environment variables."""
+    syn = nfc.synthetic
+    d = syn.make_columns("ocean", B=300, seed=9)
+    cw, layers = O.chain_spec("dense-default")
+    theta = O.glorot_theta(cw, layers, 0, 0.3)
+    h = nfc.Handle(cw, layers, 1, syn.saveat(17))
+    h.set_weights(theta)
+    a = h.solve(d["T0"], d["colp"], d["glob"])
+    h.set_option("tc", 0)                      # FP32 SIMT kernels
+    b = h.solve(d["T0"], d["colp"], d["glob"])
+    h.set_option("tc", 1)
+    h.set_option("tc_tiles", 2)                # two tiles in flight: bit-identical to one tile
+    c = h.solve(d["T0"], d["colp"], d["glob"])
+    assert (a["status"] == 0).all() and (b["status"] == 0).all()
+    assert rel_l2(a["T"], b["T"]).max() < TRAJ_TOL and not np.array_equal(a["T"], b["T"])
+    assert np.array_equal(a["T"], c["T"])
+    with pytest.raises(nfc.NfcError):
+        h.set_option("no_such_option", 1)
+    with pytest.raises(nfc.NfcError):
+        h.set_option("tc_tiles", 3)
