@@ -10,7 +10,8 @@
 //      T <- Tridiagonal(ld, d, ud) \ T.
 //      The centre gradient is the mean of the two face gradients; the bottom face carries the gradient boundary condition
 //      (base_model, oceananigans_nn.jl:84), the top face of a flux boundary condition is filled with zero gradient [UPSTREAM].
-// The state is carried in SCALED units x = (T - mu_T)/sigma_T (the update is linear and the sign test is scale invariant), so
+// The state is carried in SCALED units x = (T - mu_T)/sigma_T (the update is affine -- the reference's matrix preserves constants except
+// in its first row, which gets the corresponding affine term below -- and the sign test is scale invariant), so
 // Float32 resolves the O(0.01 K) changes of a 20 C profile; temperatures are un-scaled on output only.
 // One warp = 8 columns, lane == level; the 32-unknown tridiagonal systems are solved by parallel cyclic reduction in
 // registers (5 rounds of shuffles) -- no sequential Thomas sweep across lanes.
@@ -91,6 +92,9 @@ __global__ void __launch_bounds__(NW * 32, 1) embedded_kernel(const EmbeddedPara
                 const float ld = lane > 0 ? -a * kap : 0.f;
                 const float ud = lane < NZ - 1 ? -a * kap_hi : 0.f;
                 const float dd = 1.f + a * (kap + kap_hi);
+                // first row: d_1 keeps kappa_1 although there is no sub-diagonal (src/oceananigans_nn.jl:19-22), row sum 1 + a kappa_1: in scaled
+                // units x = (T - mu)/sigma the reference's solve reads  L x' = x - (mu/sigma) a kappa_1 e_1
+                if (lane == 0) t -= P.mu_T * inv_sT * a * kap;
                 T[c] = pcr32(ld, dd, ud, t, lane);
             }
             __syncwarp();

@@ -80,6 +80,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) embedded_tc_kernel(const unsigned
                     }
                     // kappa_k = K where the centre gradient (mean of the face gradients; bottom: gradient BC, top: zero) is negative
                     float kap_lo = ((gbot) + (t[1] - t[0]) < 0.f) ? P.K : 0.f;      // kappa_0
+                    // The reference's first row has no sub-diagonal but keeps kappa_1 on its diagonal (d_1 = 1 + a (kappa_1 + kappa_2),
+                    // src/oceananigans_nn.jl:19-22): its row sum is 1 + a kappa_1, so the operator does not preserve constants when the deepest
+                    // cell is unstable, and the solve in scaled units x = (T - mu)/sigma needs the affine term  L x' = x - (mu/sigma) a kappa_1 e_1
+                    const float aff = P.mu_T * inv_sT * a * kap_lo;                 // right-hand side of row 0 only (the sign tests use the state itself)
                     float dprev = 0.f, cprev = 0.f;
 #pragma unroll
                     for (int k = 0; k < NZ; ++k) {
@@ -96,7 +100,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) embedded_tc_kernel(const unsigned
                         const float m = fmaf(-ld, cprev, dd);
                         const float im = __fdividef(1.f, m);
                         cprev = ud * im;
-                        dprev = fmaf(-ld, dprev, t[k]) * im;
+                        dprev = fmaf(-ld, dprev, k == 0 ? t[k] - aff : t[k]) * im;
                         cp[k] = cprev; t[k] = dprev;
                         kap_lo = kap_hi;
                     }

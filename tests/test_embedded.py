@@ -63,6 +63,29 @@ def test_gpu_embedded_matches_oracle(nfc, gpu_ok, arch, scale):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("tc", ["0", "1"])
+def test_gpu_embedded_unstable_bottom_cell(nfc, gpu_ok, monkeypatch, tc):
+    """The reference's matrix keeps kappa_1 on the diagonal of its first row without a sub-diagonal (src/oceananigans_nn.jl:19-22): when the
+    deepest cell is unstable the operator does not preserve constants, and a solve carried in scaled units must add the affine term.
+    Columns with a warm bottom cell against the float64 oracle, which solves in physical units like the reference."""
+    monkeypatch.setenv("NFC_TC", tc)
+    B = 133
+    T0, Q, scal = _columns(nfc, B, seed=11)
+    T0 = T0.copy()
+    T0[:, 0] += 0.5                                                   # deepest cell warmer than the one above: kappa_1 = K
+    cw, layers = O.chain_spec()
+    theta = O.glorot_theta(cw, layers, 1, 0.3)
+    h = nfc.Handle(cw, layers, 1, np.float32([0, 1]))
+    h.set_weights(theta)
+    K = scal[3] / scal[1] * 691200.0 / 256.0 * 10.0
+    out = h.embedded_solve(T0, Q, scal, 256.0, 600.0, K, -1e-3, 48, save_every=12)
+    ref = O.embedded_solve(T0, Q, theta, cw, layers, scal, 256.0, 600.0, K, -1e-3, 48, save_every=12)
+    assert rel_l2(out[:, 1:] - T0[:, None], ref[:, 1:] - T0[:, None]).max() < 2e-3
+    # without the affine term the deep cells are off by O(mu a kappa_1) ~ kelvins: make sure the test would see it
+    assert np.abs(ref[:, 1, 0] - T0[:, 0]).min() > 1e-3
+
+
+@pytest.mark.gpu
 def test_gpu_embedded_api_mirror(nfc, gpu_ok):
     syn = nfc.synthetic
     Ts, wTs = syn.reference_scalings()
