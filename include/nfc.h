@@ -18,7 +18,9 @@
  *     duration of the call only; the handle owns device memory, streams, scratch.
  *   - every call returns 0 on success, negative on usage / CUDA error (text via nfc_last_error).
  *     Per-column numerical trouble is reported in status[] (0 ok, 1 maxiters, 2 NaN/Inf, 3 dt underflow,
- *     4 adjoint tape overflow), never as a call failure -- the reference treats solver retcodes as warnings.
+ *     4 adjoint tape overflow, 5 operand range of the FP16x2 tensor-core split left: |T_scaled| > 128 -- the host-buffer
+ *     calls re-solve such columns without that bound, see `range_fallback`), never as a call failure -- the reference
+ *     treats solver retcodes as warnings.
  *   - calls on one handle are serialised by the caller; host-pointer calls are synchronous.
  *   - there is NO CPU fallback: without a CUDA device nfc_create fails.
  *
@@ -164,6 +166,9 @@ int32_t nfc_get_adjoint_steps(nfc_handle* h, int32_t* out, int64_t n);
  *   adj_small_max    batches up to this many columns run the one-column-per-CTA backward kernel (default 7400; 0 = never)
  *   adj_tc           0: batch backward pass on the FP32 SIMT kernel instead of the tensor-core kernel
  *   e2e_pieces       nfc_solve: pieces whose device->host copy overlaps the next piece's solve (0 = auto: 3 from 65536 columns)
+ *   tc_split         0 = FP16x2 operands (3 MMAs per fp32 product, needs |T_scaled| <= 128; default), 1 = BF16x3 (6 MMAs, fp32's range)
+ *   range_fallback   1 (default): nfc_solve re-solves columns that ended with status 5 on the BF16x3 split, nfc_loss_grad (no communicator)
+ *                    repeats a call that had such a column on the FP32 kernels; 0: status 5 is returned as it is (the *_dev calls always do)
  *   tape_gib         tape budget of nfc_loss_grad in GiB; larger batches are processed in chunks (0 = default 48) */
 int32_t nfc_set_option(nfc_handle* h, const char* name, int64_t value);
 

@@ -217,7 +217,7 @@ def solve_nde(*args, **kw):
     return dict(T=T_scaling.inv(T), wT=wT_scaling.inv(wT))
 
 
-STATUS_NAMES = {1: "maxiters", 2: "NaN / operand range", 3: "dt underflow", 4: "adjoint tape overflow"}
+STATUS_NAMES = {1: "maxiters", 2: "NaN", 3: "dt underflow", 4: "adjoint tape overflow", 5: "FP16x2 operand range"}
 
 
 def _warn_status(status, what):

@@ -404,6 +404,25 @@ int do_loss_grad(nfc_handle* h, const float* T0, const float* colp, float pref, 
     return adjoint_loss_grad<N, Launch<N>::WS, Launch<N>::NW>(h, T0, colp, pref, Ttrue, loss_sum_dev, grad_dev, status, B, n_total_columns, st);
 }
 
+// Re-pack the tensor-core weight image for the other operand split (default Chain).  Used by the host-buffer calls to re-solve columns
+// that left the FP16x2 operand range (status ST_RANGE) on the BF16x3 split, which has fp32's exponent range.
+int switch_split(nfc_handle* h, bool fp16) {
+    if (h->arch != ARCH_DEFAULT || h->tc_fp16 == fp16) return 0;
+    if (fp16) {
+        tc::Fp16Scales sc;
+        memcpy(&sc, h->fp16_scales, sizeof sc);
+        const int n = 128 * 32 + 128 * 128 + 32 * 128 + 296;
+        tc::pack_weights_tc16_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_theta.p, h->d_wimg.p, sc);
+    } else {
+        const int n = 128 * 32 + 128 * 128 + 32 * 128 + 288;
+        tc::pack_weights_tc_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_theta.p, h->d_wimg.p);
+    }
+    NFC_CUDA(h, cudaGetLastError());
+    NFC_CUDA(h, cudaStreamSynchronize(h->stream));
+    h->tc_fp16 = fp16;
+    return 0;
+}
+
 int check_ready(nfc_handle* h, int64_t B) {
     if (!h) return -1;
     if (B < 0) return fail(h, -2, "negative column count");
@@ -638,11 +657,7 @@ int32_t nfc_set_weights(nfc_handle* h, const float* theta, int64_t n) {
     NFC_CUDA(h, cudaMemcpyAsync(h->d_theta.p, theta, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
     int rc = [&]() -> int { NFC_DISPATCH(h, do_pack, h); }();
     if (rc) return rc;
-    if (h->arch == ARCH_DEFAULT && !h->tc_fp16) {
-        const int n = 128 * 32 + 128 * 128 + 32 * 128 + 288;
-        tc::pack_weights_tc_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_theta.p, h->d_wimg.p);
-        NFC_CUDA(h, cudaGetLastError());
-    } else if (h->arch == ARCH_DEFAULT) {
+    if (h->arch == ARCH_DEFAULT) {
         // FP16x2 split: exact power-of-two scales from the weights' max / row-sum norms and the input bound |T_scaled| <= 128
         using N0 = NetDefault;
         auto p2 = [](double bound) { return bound > 0 ? (float)std::exp2(std::floor(std::log2(16384.0 / bound))) : 1.0f; };
@@ -664,6 +679,7 @@ int32_t nfc_set_weights(nfc_handle* h, const float* theta, int64_t n) {
         norms(N0::T_WL, 128, 31, N0::T_BL, w3, r3, b3, k3);
         const double x0 = 128.0, a1 = r1 * x0 + b1, a2 = r2 * a1 + b2;
         tc::Fp16Scales sc{p2(w1), p2(w2), p2(w3), p2(x0), p2(a1), p2(a2)};
+        memcpy(h->fp16_scales, &sc, sizeof sc);
         {   // backward chain: |d3 * scol| <= 1 per column, |g2| <= colsum(W3), |g1| <= colsum(W2) colsum(W3)
             const double s_d3 = 16384.0, s_d2 = p2(k3), s_d1 = p2(k2 * k3);
             atc::AtcScales& a = h->atc_scales;
@@ -674,8 +690,13 @@ int32_t nfc_set_weights(nfc_handle* h, const float* theta, int64_t n) {
             a.inv_sd2 = (float)(1.0 / s_d2); a.inv_sd1 = (float)(1.0 / s_d1);
             a.inv_sa0 = 1.f / sc.s_a0; a.inv_sa1 = 1.f / sc.s_a1; a.inv_sa2 = 1.f / sc.s_a2;
         }
-        const int n = 128 * 32 + 128 * 128 + 32 * 128 + 296;
-        tc::pack_weights_tc16_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_theta.p, h->d_wimg.p, sc);
+        if (h->tc_fp16) {
+            const int n = 128 * 32 + 128 * 128 + 32 * 128 + 296;
+            tc::pack_weights_tc16_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_theta.p, h->d_wimg.p, sc);
+        } else {
+            const int n = 128 * 32 + 128 * 128 + 32 * 128 + 288;
+            tc::pack_weights_tc_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_theta.p, h->d_wimg.p);
+        }
         NFC_CUDA(h, cudaGetLastError());
     }
     NFC_CUDA(h, cudaStreamSynchronize(h->stream));
@@ -715,8 +736,15 @@ int32_t nfc_set_option(nfc_handle* h, const char* name, int64_t value) {
     else if (n == "adj_small_max") h->adj_small_max = value;
     else if (n == "adj_tc") h->adj_tc = value != 0;
     else if (n == "e2e_pieces") { if (value < 0 || value > 8) return fail(h, -2, "e2e_pieces: 0 (auto) .. 8"); h->e2e_pieces = (int)value; }
+    else if (n == "range_fallback") h->range_fallback = value != 0;
+    else if (n == "tc_split") {                 // 0: FP16x2 (3 MMAs per product, |T_scaled| <= 128), 1: BF16x3 (6 MMAs, fp32's range)
+        if (!def) return fail(h, -3, "the tensor-core kernels exist for the default Chain only");
+        if (!h->weights_set) { h->tc_fp16 = value == 0; return 0; }
+        NFC_CUDA(h, cudaSetDevice(h->device));
+        return switch_split(h, value == 0);
+    }
     else if (n == "tape_gib") { if (value < 0) return fail(h, -2, "tape_gib: >= 0 (0 = default 48)"); h->tape_gib = (double)value; }
-    else return fail(h, -2, "unknown option '%s' (tc, tc_tiles, tc2_min_columns, tc_record, sched, adj_small_max, adj_tc, e2e_pieces, tape_gib)", name);
+    else return fail(h, -2, "unknown option '%s' (tc, tc_tiles, tc_split, range_fallback, tc2_min_columns, tc_record, sched, adj_small_max, adj_tc, e2e_pieces, tape_gib)", name);
     return 0;
 }
 
@@ -893,8 +921,51 @@ int32_t nfc_solve(nfc_handle* h, const float* T0, const float* colp, const float
     if (npieces > 1) NFC_CUDA(h, cudaStreamSynchronize(h->copy_stream));
     if (naccept) NFC_CUDA(h, cudaMemcpyAsync(naccept, h->s_nacc.p, sizeof(int) * B, cudaMemcpyDeviceToHost, h->stream));
     if (nreject) NFC_CUDA(h, cudaMemcpyAsync(nreject, h->s_nrej.p, sizeof(int) * B, cudaMemcpyDeviceToHost, h->stream));
-    if (status) NFC_CUDA(h, cudaMemcpyAsync(status, h->s_status.p, sizeof(int) * B, cudaMemcpyDeviceToHost, h->stream));
+    // FP16x2 operand range: a column whose accepted state left |T_scaled| <= 128 comes back as ST_RANGE; it is re-solved here on the BF16x3
+    // split (fp32's exponent range, same kernel), so the caller sees what the reference would have integrated (nfc_set_option "range_fallback")
+    const bool may_fall_back = h->range_fallback && h->use_tc && h->arch == ARCH_DEFAULT && h->tc_fp16 && h->cfg.alg == NFC_ALG_TSIT5;
+    std::vector<int> hstat;
+    int* st_host = status;
+    if (!st_host && may_fall_back) { hstat.resize(B); st_host = hstat.data(); }
+    if (st_host) NFC_CUDA(h, cudaMemcpyAsync(st_host, h->s_status.p, sizeof(int) * B, cudaMemcpyDeviceToHost, h->stream));
     NFC_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (may_fall_back) {
+        std::vector<int64_t> redo;
+        for (int64_t c = 0; c < B; ++c) if (st_host[c] == ST_RANGE) redo.push_back(c);
+        if (!redo.empty()) {
+            const int64_t nr = (int64_t)redo.size();
+            const size_t row = (size_t)h->cfg.n_save * NZ;
+            std::vector<float> t0c((size_t)nr * NZ), cpc((size_t)nr * 3), outc((size_t)nr * row);
+            std::vector<int> nac(nr), nrc(nr), stc(nr);
+            for (int64_t i = 0; i < nr; ++i) {
+                memcpy(&t0c[i * NZ], T0 + redo[i] * NZ, sizeof(float) * NZ);
+                memcpy(&cpc[i * 3], colp + redo[i] * 3, sizeof(float) * 3);
+            }
+            NFC_CUDA(h, cudaMemcpyAsync(h->s_T0.p, t0c.data(), sizeof(float) * nr * NZ, cudaMemcpyHostToDevice, h->stream));
+            NFC_CUDA(h, cudaMemcpyAsync(h->s_colp.p, cpc.data(), sizeof(float) * nr * 3, cudaMemcpyHostToDevice, h->stream));
+            NFC_CUDA(h, cudaMemsetAsync(h->s_out.p, 0xFF, sizeof(float) * nr * row, h->stream));
+            if (int rc = switch_split(h, false)) return rc;
+            const bool sched = h->use_sched;
+            h->use_sched = false;                                       // keep the batch's longest-first history
+            int rc = [&]() -> int {
+                NFC_DISPATCH(h, do_solve, h, h->s_T0.p, h->s_colp.p, pref, h->s_out.p, h->s_nacc.p, h->s_nrej.p, h->s_status.p, nr, h->stream, false);
+            }();
+            h->use_sched = sched;
+            if (rc) { switch_split(h, true); return rc; }
+            NFC_CUDA(h, cudaMemcpyAsync(outc.data(), h->s_out.p, sizeof(float) * nr * row, cudaMemcpyDeviceToHost, h->stream));
+            NFC_CUDA(h, cudaMemcpyAsync(nac.data(), h->s_nacc.p, sizeof(int) * nr, cudaMemcpyDeviceToHost, h->stream));
+            NFC_CUDA(h, cudaMemcpyAsync(nrc.data(), h->s_nrej.p, sizeof(int) * nr, cudaMemcpyDeviceToHost, h->stream));
+            NFC_CUDA(h, cudaMemcpyAsync(stc.data(), h->s_status.p, sizeof(int) * nr, cudaMemcpyDeviceToHost, h->stream));
+            if (int rc2 = switch_split(h, true)) return rc2;            // synchronises the stream
+            for (int64_t i = 0; i < nr; ++i) {
+                memcpy(Tout + redo[i] * row, &outc[i * row], sizeof(float) * row);
+                if (naccept) naccept[redo[i]] = nac[i];
+                if (nreject) nreject[redo[i]] = nrc[i];
+                if (status) status[redo[i]] = stc[i];
+            }
+            h->range_resolved = nr;
+        } else h->range_resolved = 0;
+    }
     return 0;
 }
 
@@ -1008,8 +1079,27 @@ int32_t nfc_loss_grad(nfc_handle* h, const float* T0, const float* colp, const f
     double ls[2];
     NFC_CUDA(h, cudaMemcpyAsync(ls, h->s_loss.p, sizeof ls, cudaMemcpyDeviceToHost, h->stream));
     NFC_CUDA(h, cudaMemcpyAsync(grad_theta, h->s_grad.p, sizeof(float) * h->n_params, cudaMemcpyDeviceToHost, h->stream));
-    if (status && B > 0) NFC_CUDA(h, cudaMemcpyAsync(status, h->s_status.p, sizeof(int) * B, cudaMemcpyDeviceToHost, h->stream));
+    // a column outside the FP16x2 operand range contributes no gradient (status ST_RANGE): single-GPU calls repeat the whole call on the FP32
+    // kernels instead (with a communicator the ranks would have to agree on it first: the status is returned as it is)
+    const bool may_fall_back = h->range_fallback && !h->nccl_comm && B > 0 && h->use_tc && h->arch == ARCH_DEFAULT && h->tc_fp16;
+    std::vector<int> hstat;
+    int* st_host = status;
+    if (!st_host && may_fall_back) { hstat.resize(B); st_host = hstat.data(); }
+    if (st_host && B > 0) NFC_CUDA(h, cudaMemcpyAsync(st_host, h->s_status.p, sizeof(int) * B, cudaMemcpyDeviceToHost, h->stream));
     NFC_CUDA(h, cudaStreamSynchronize(h->stream));
+    if (may_fall_back && std::find(st_host, st_host + B, (int)ST_RANGE) != st_host + B) {
+        h->use_tc = false;
+        int rc2 = [&]() -> int {
+            NFC_DISPATCH(h, do_loss_grad, h, h->s_T0.p, h->s_colp.p, prefactor(glob), h->s_true.p, h->s_loss.p, h->s_grad.p, h->s_status.p, B, B, h->stream);
+        }();
+        h->use_tc = true;
+        if (rc2) return rc2;
+        NFC_CUDA(h, cudaMemcpyAsync(ls, h->s_loss.p, sizeof ls, cudaMemcpyDeviceToHost, h->stream));
+        NFC_CUDA(h, cudaMemcpyAsync(grad_theta, h->s_grad.p, sizeof(float) * h->n_params, cudaMemcpyDeviceToHost, h->stream));
+        if (status) NFC_CUDA(h, cudaMemcpyAsync(status, h->s_status.p, sizeof(int) * B, cudaMemcpyDeviceToHost, h->stream));
+        NFC_CUDA(h, cudaStreamSynchronize(h->stream));
+        h->range_resolved = B;
+    } else h->range_resolved = 0;
     if (h->nccl_comm) cudaEventElapsedTime(&h->last_allreduce_ms, h->ev_ar[0], h->ev_ar[1]);
     *loss = ls[0] / ls[1];
     return 0;

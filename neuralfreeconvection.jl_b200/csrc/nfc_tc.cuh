@@ -885,7 +885,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
                     dtnew = accept ? hs / qq : hs / fminf(5.0f, q11 / 0.9f);
                 }
                 if (accept && !(fmaxf(fmaxf(S.rng[pb][c][0], S.rng[pb][c][1]), fmaxf(S.rng[pb][c][2], S.rng[pb][c][3])) <= SP::INPUT_BOUND)) {
-                    status = ST_NAN; accept = false;             // an accepted state outside the operand range of the split: report, never guess
+                    status = ST_RANGE; accept = false;           // an accepted state outside the operand range of the split: report, never guess (the host calls re-solve it on the BF16x3 split)
                 }
                 if (accept) {
                     const float tn = last ? P.tf : t + hs;

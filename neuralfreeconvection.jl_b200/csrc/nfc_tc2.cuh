@@ -319,7 +319,7 @@ __device__ __forceinline__ void step_control(Shared2* S, const SolveParams& P, i
             accept = ee <= 1.0f;
             dtnew = accept ? hs / qq : hs / fminf(5.0f, q11 / 0.9f);
         }
-        if (accept && (ctl & CTL_RANGE)) { status = ST_NAN; accept = false; }     // accepted state outside the operand range of the split
+        if (accept && (ctl & CTL_RANGE)) { status = ST_RANGE; accept = false; }     // accepted state outside the operand range of the split
         if (accept) {
             const float tn = last ? P.tf : t + hs;
             int si = C.si[c];

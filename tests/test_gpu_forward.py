@@ -257,8 +257,10 @@ def test_tensor_core_splits_are_fp32_faithful(nfc, gpu_ok, monkeypatch, split):
         assert rel_l2(f, ref).max() < 2e-6
 
 
-def test_tensor_core_out_of_range_input_is_flagged_not_wrong(nfc, gpu_ok, monkeypatch):
-    """FP16x2 assumes |T_scaled| <= 128 (operand scaling); a column beyond that must end as status NaN, its neighbours untouched."""
+def test_tensor_core_out_of_range_input_is_flagged_or_resolved(nfc, gpu_ok, monkeypatch):
+    """FP16x2 assumes |T_scaled| <= 128 (operand scaling).  The kernel never guesses: a column beyond that ends as status 5 (ST_RANGE), its
+    neighbours untouched (`range_fallback` 0).  By default the host-buffer call re-solves such a column on the BF16x3 split (fp32's
+    exponent range), so the caller sees what the FP32 kernel integrates, as the reference would."""
     monkeypatch.setenv("NFC_TC", "1")
     monkeypatch.setenv("NFC_TC_SPLIT", "fp16")
     d = nfc.synthetic.make_columns("ocean", B=200, seed=8)
@@ -267,11 +269,32 @@ def test_tensor_core_out_of_range_input_is_flagged_not_wrong(nfc, gpu_ok, monkey
     h.set_weights(O.glorot_theta(cw, layers, 0, 0.3))
     ok = h.solve(d["T0"], d["colp"], d["glob"])
     T0 = d["T0"].copy()
-    T0[17] *= 1.0e4
-    r = h.solve(T0, d["colp"], d["glob"])
-    assert r["status"][17] == 2
+    T0[17] *= 120.0                            # |T_scaled| up to ~ 167: outside the FP16x2 operand range, harmless in fp32
+    assert np.abs(T0[17]).max() > 128
     keep = np.arange(200) != 17
+    h.set_option("range_fallback", 0)
+    r = h.solve(T0, d["colp"], d["glob"])
+    assert r["status"][17] == 5
     assert (r["status"][keep] == 0).all() and np.array_equal(r["T"][keep], ok["T"][keep])
+    h.set_option("range_fallback", 1)
+    r = h.solve(T0, d["colp"], d["glob"])
+    assert (r["status"][keep] == 0).all() and np.array_equal(r["T"][keep], ok["T"][keep])
+    h.set_option("tc", 0)                      # the FP32 SIMT kernel on the same inputs
+    s = h.solve(T0, d["colp"], d["glob"])
+    assert r["status"][17] == s["status"][17] == 0
+    assert rel_l2(r["T"][17:18], s["T"][17:18]).max() < TRAJ_TOL
+    assert abs(int(r["naccept"][17]) - int(s["naccept"][17])) <= 0.05 * s["naccept"][17] + 2
+    # loss + gradient: the whole call is repeated on the FP32 kernels when a column left the range
+    h.set_option("tc", 1)
+    Ttrue = np.ascontiguousarray(ok["T"] + 0.05, dtype=np.float32)
+    g = h.loss_grad(T0[:32], d["colp"][:32], d["glob"], Ttrue[:32])
+    h.set_option("tc", 0)
+    g0 = h.loss_grad(T0[:32], d["colp"][:32], d["glob"], Ttrue[:32])
+    assert (g["status"] == 0).all() and g["loss"] == g0["loss"] and np.array_equal(g["grad"], g0["grad"])
+    h.set_option("tc", 1)
+    h.set_option("range_fallback", 0)
+    g1 = h.loss_grad(T0[:32], d["colp"][:32], d["glob"], Ttrue[:32])
+    assert g1["status"][17] == 5 and (np.delete(g1["status"], 17) == 0).all()
 
 
 @pytest.mark.parametrize("B", [1, 127, 300, 5000])
@@ -284,18 +307,19 @@ def test_two_tile_kernel_matches_one_tile_kernel_bit_for_bit(nfc, gpu_ok, monkey
     d = nfc.synthetic.make_columns("ocean", B=B, seed=21)
     T0 = d["T0"].copy()
     if B > 200:
-        T0[131] *= 1.0e4                      # |T_scaled| > 128: must end as status NaN in both kernels
+        T0[131] *= 1.0e4                      # |T_scaled| > 128: must end as status 5 (ST_RANGE) in both kernels
     sv = nfc.synthetic.saveat(33)
     res = []
     for tiles in ("1", "2"):
         monkeypatch.setenv("NFC_TC_TILES", tiles)
         h, cw, layers = _handle(nfc, saveat=sv)
+        h.set_option("range_fallback", 0)     # the kernels' own answer, not the host call's BF16x3 re-solve
         h.set_weights(O.glorot_theta(cw, layers, 0, 0.3))
         res.append(h.solve(T0, d["colp"], d["glob"]))
     a, b = res
     assert np.array_equal(a["status"], b["status"]) and np.array_equal(a["naccept"], b["naccept"]) and np.array_equal(a["nreject"], b["nreject"])
     if B > 200:
-        assert b["status"][131] == 2
+        assert b["status"][131] == 5
     good = b["status"] == 0
     assert good.sum() >= B - 1
     assert np.array_equal(a["T"][good].view(np.uint32), b["T"][good].view(np.uint32))
