@@ -7,7 +7,8 @@ PKG="neuralfreeconvection.jl_b200"
 EXTRA=""; FORCE=0
 for a in "$@"; do [ "$a" = "-v" ] && EXTRA="-Xptxas -v"; [ "$a" = "-f" ] && FORCE=1; done
 FLAGS="$NFC_EXTRA_FLAGS -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -diag-suppress 128 $EXTRA -Xcompiler -fPIC"
-mkdir -p build
+BUILD=${NFC_BUILD_DIR:-build}; SO=${NFC_SO:-libnfc_b200.so}     # debug builds: NFC_EXTRA_FLAGS=-DNFC_DEBUG_TIMERS NFC_BUILD_DIR=build_dbg NFC_SO=libnfc_b200_dbg.so
+mkdir -p $BUILD
 stale() {   # $1 object, rest: sources
     local o="$1"; shift
     [ "$FORCE" = 1 ] || [ ! -f "$o" ] && return 0
@@ -16,7 +17,7 @@ stale() {   # $1 object, rest: sources
 }
 COMMON=$(ls $PKG/csrc/*.cuh $PKG/csrc/*.h include/nfc.h | grep -v nfc_adjoint_tc)
 PIDS=""
-if stale build/nfc_api.o $PKG/csrc/nfc_api.cu $COMMON; then nvcc $FLAGS -c -o build/nfc_api.o "$PKG/csrc/nfc_api.cu" & PIDS="$PIDS $!"; fi
-if stale build/nfc_adjoint_tc.o $PKG/csrc/nfc_adjoint_tc.cu $PKG/csrc/nfc_adjoint_tc.cuh $COMMON; then nvcc $FLAGS -c -o build/nfc_adjoint_tc.o "$PKG/csrc/nfc_adjoint_tc.cu" & PIDS="$PIDS $!"; fi
+if stale $BUILD/nfc_api.o $PKG/csrc/nfc_api.cu $COMMON; then nvcc $FLAGS -c -o $BUILD/nfc_api.o "$PKG/csrc/nfc_api.cu" & PIDS="$PIDS $!"; fi
+if stale $BUILD/nfc_adjoint_tc.o $PKG/csrc/nfc_adjoint_tc.cu $PKG/csrc/nfc_adjoint_tc.cuh $COMMON; then nvcc $FLAGS -c -o $BUILD/nfc_adjoint_tc.o "$PKG/csrc/nfc_adjoint_tc.cu" & PIDS="$PIDS $!"; fi
 for p in $PIDS; do wait $p; done
-nvcc -gencode arch=compute_100a,code=sm_100a --shared -ldl -o "$PKG/libnfc_b200.so" build/nfc_api.o build/nfc_adjoint_tc.o
+nvcc -gencode arch=compute_100a,code=sm_100a --shared -ldl -o "$PKG/$SO" $BUILD/nfc_api.o $BUILD/nfc_adjoint_tc.o

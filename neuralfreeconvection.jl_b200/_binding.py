@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnfc_b200.so")
+LIB_PATH = os.environ.get("NFC_B200_LIB") or os.path.join(_HERE, "libnfc_b200.so")   # NFC_B200_LIB: a debug build of the same library (build.sh)
 NFC_MAX_LAYERS = 8
 
 EXPORTS = ["nfc_create", "nfc_destroy", "nfc_last_error", "nfc_n_params", "nfc_set_weights", "nfc_set_saveat",

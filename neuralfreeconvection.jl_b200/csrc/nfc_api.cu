@@ -249,7 +249,14 @@ int launch_solve(nfc_handle* h, SolveParams& P, cudaStream_t st, bool reset_coun
                 fprintf(stderr, "[nfc tc debug] layer %d: n %lld | MMA thread: wait A0 %.0f, issue half0 %.0f, wait A1 %.0f, issue half1+commit %.0f cycles | column thread 0 waits for D %.0f\n",
                         l, dbg[5 * l + 4], (double)dbg[5 * l] / dbg[5 * l + 4], (double)dbg[5 * l + 1] / dbg[5 * l + 4], (double)dbg[5 * l + 2] / dbg[5 * l + 4],
                         (double)dbg[5 * l + 3] / dbg[5 * l + 4], (double)dbg[16 + l] / dbg[5 * l + 4]);
-            fprintf(stderr, "[nfc tc debug] column thread 0 total %lld cycles, %.0f per Chain evaluation\n", dbg[19], (double)dbg[19] / dbg[4]);
+            fprintf(stderr, "[nfc tc debug] column thread 0 total %lld cycles, %.0f per Chain evaluation; %lld steps: %.0f cycles per step in the six stages, %.0f at the step boundary\n",
+                    dbg[19], (double)dbg[19] / dbg[4], dbg[21], (double)dbg[20] / std::max<long long>(dbg[21], 1), (double)(dbg[19] - dbg[20]) / std::max<long long>(dbg[21], 1));
+            {
+                const double n = (double)std::max<long long>(dbg[21], 1);
+                fprintf(stderr, "[nfc tc debug] step boundary, cycles per step: error estimate + dense output + barrier %.0f | controller + saves %.0f | retire + queue pop + barrier %.0f | new-column loads + barrier %.0f\n",
+                        dbg[24] / n, dbg[25] / n, dbg[22] / n, dbg[23] / n);
+                fprintf(stderr, "[nfc tc debug]   controller + saves: decision known after %.0f, saves written after %.0f (accepted steps only, per step)\n", dbg[26] / n, dbg[27] / n);
+            }
         }
     } else {
         const int grid = (int)std::min<long long>(h->num_sms, (groups + NW - 1) / NW);

@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) embedded_tc_kernel(const unsigned
         cta_bar();
         if (threadIdx.x == 0) S.stop = 1;
         cta_bar();
-        mbar_arrive(&S.bar_a);
+        warp_arrive(&S.bar_a);
     }
     fence_before_sync();
     __syncthreads();

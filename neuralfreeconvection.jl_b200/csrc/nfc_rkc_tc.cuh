@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_rkc_tc_kernel(const unsigne
         cta_bar();
         if (threadIdx.x == 0) S.stop = 1;
         cta_bar();
-        mbar_arrive(&S.bar_a);
+        warp_arrive(&S.bar_a);
     }
     fence_before_sync();
     __syncthreads();

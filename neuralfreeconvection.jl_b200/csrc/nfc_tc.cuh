@@ -67,6 +67,14 @@ __device__ __forceinline__ void wait_st() { asm volatile("tcgen05.wait::st.sync.
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// one arrival per WARP (the barriers of the A operand count the 16 column warps): 512 per-thread arrivals on one shared-memory word
+// serialise and sat on the critical path of every hand-off to the MMA warp.  Each lane has completed its tcgen05.st (wait::st) and issued
+// tcgen05.fence::before_thread_sync; the warp barrier orders the lanes before lane 0 arrives for all of them.
+constexpr int NCW = 16;                   // column warps
+__device__ __forceinline__ void warp_arrive(uint64_t* bar) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
 // D[tmem] (+)= A[tmem] * B[smem desc]   (kind::f16, bf16 inputs, fp32 accumulate)
 __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -133,6 +141,48 @@ __device__ __forceinline__ uint64_t make_bdesc(uint32_t smem_addr, int N) {   //
     return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(((uint32_t)N * 16) >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
 }
 
+// ---- packed fp32 (sm_100: FFMA2 / FADD2 / FMUL2, two IEEE fp32 operations per instruction, results identical to the scalar forms).
+// The column threads are bound by instruction issue and dependent-issue latency, not by the FP32 pipe, so halving the number of FMA / ADD
+// instructions of the 8-level vectors is a direct gain.  Pairs are (even, odd) elements; ptxas keeps them in adjacent registers.
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(unsigned long long v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+// (d0, d1) = (a0, a1) * s + (c0, c1)
+__device__ __forceinline__ void fma2s(float& d0, float& d1, float a0, float a1, float s, float c0, float c1) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk2(a0, a1)), "l"(pk2(s, s)), "l"(pk2(c0, c1)));
+    upk2(r, d0, d1);
+}
+// (d0, d1) = (a0, a1) * (b0, b1) + (c0, c1)
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk2(a0, a1)), "l"(pk2(b0, b1)), "l"(pk2(c0, c1)));
+    upk2(r, d0, d1);
+}
+__device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a0, a1)), "l"(pk2(b0, b1)));
+    upk2(r, d0, d1);
+}
+__device__ __forceinline__ void sub2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+    unsigned long long r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a0, a1)), "l"(pk2(b0, b1)));
+    upk2(r, d0, d1);
+}
+__device__ __forceinline__ void mul2s(float& d0, float& d1, float a0, float a1, float s) {
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a0, a1)), "l"(pk2(s, s)));
+    upk2(r, d0, d1);
+}
+// acc[0..8) = coef * k[0..8) + acc[0..8)   /   acc = coef * k
+__device__ __forceinline__ void axpy8(float (&acc)[8], float coef, const float (&k)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) fma2s(acc[i], acc[i + 1], k[i], k[i + 1], coef, acc[i], acc[i + 1]);
+}
+__device__ __forceinline__ void scal8(float (&acc)[8], float coef, const float (&k)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) mul2s(acc[i], acc[i + 1], k[i], k[i + 1], coef);
+}
+
 // x = x1 + x2 + x3 in bf16; the pair (even, odd) is packed as (low, high) half of one 32-bit cell
 __device__ __forceinline__ void split3(float v0, float v1, uint32_t& p1, uint32_t& p2, uint32_t& p3) {
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(p1) : "f"(v1), "f"(v0));
@@ -184,8 +234,8 @@ static __global__ void pack_weights_tc_kernel(const float* __restrict__ theta, u
 // ---- shared state of one CTA ------------------------------------------------------------------------------------------
 struct TcShared {
     uint64_t bar_w;        // weight image landed
-    uint64_t bar_a;        // first half of the A operand written by all column threads (even k-steps of the next layer)
-    uint64_t bar_a1;       // second half written (odd k-steps)
+    uint64_t bar_a;        // A operand, sub-chunk 0 written by all column threads: the whole layer-1 operand / k-steps 0, 1 of a later layer
+    uint64_t bar_q[3];     // sub-chunks 1..3 of a hidden or output layer's operand (k-steps 2s, 2s+1)
     uint64_t bar_d;        // accumulator ready (tcgen05.commit)
     uint32_t tmem_base;
     int stop;
@@ -197,13 +247,14 @@ struct TcShared {
     int any;
 };
 
-// MMA issuer: all six split products of one Dense layer, fully unrolled: per MMA one 32-bit add on the descriptor's
+// MMA issuer: the split products of one Dense layer, fully unrolled: per MMA one 32-bit add on the descriptor's
 // address field (k-step stride 2*LBO), one add on the TMEM column, the tcgen05.mma itself.  (A first version built every
 // descriptor in a runtime loop and was issue-bound at ~98 cycles per MMA against 64 / 16 cycles of tensor-pipe time.)
-// HALF selects the k-steps whose A cells are published first (even) or second (odd); the very first MMA of a layer overwrites D
-template <int LAYER, int HALF>
+// SUB selects the k-steps 2 SUB, 2 SUB + 1, whose A cells the column threads publish as their sub-chunk SUB (layer 0: K = 32, one
+// sub-chunk); the very first MMA of a layer overwrites D
+template <int LAYER, int SUB>
 __device__ __forceinline__ void issue_layer(uint32_t tmem_base, uint32_t smem_img, int nprod) {
-    constexpr int K = LAYER == 0 ? 32 : 128, Nn = LAYER == 2 ? 96 : 128;
+    constexpr int Nn = LAYER == 2 ? 96 : 128;
     constexpr uint32_t woff = LAYER == 0 ? OFF_W1 : (LAYER == 1 ? OFF_W2 : OFF_W3);
     constexpr uint32_t wbytes = LAYER == 0 ? W1_BYTES : (LAYER == 1 ? W2_BYTES : W3_BYTES);
     constexpr uint32_t idesc = make_idesc(128, Nn);
@@ -222,7 +273,7 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem_base, uint32_t smem_im
 #pragma unroll
         for (int sA = 2; sA >= 0; --sA) {
 #pragma unroll
-            for (int j = HALF; j < K / 16; j += 2) {
+            for (int j = 2 * SUB; j < 2 * SUB + 2; ++j) {
                 if (sA == 2 && j == 0) mma_ts2<false>(d, a_base + sA * 64 + 8 * j, lo0 + kstep * j, hi0, idesc);
                 else mma_ts2<true>(d, a_base + sA * 64 + 8 * j, lo0 + kstep * j, hi0, idesc);
             }
@@ -231,22 +282,27 @@ __device__ __forceinline__ void issue_layer(uint32_t tmem_base, uint32_t smem_im
 #pragma unroll
         for (int p = 0; p < 6; ++p) {
 #pragma unroll
-            for (int j = HALF; j < K / 16; j += 2) {
+            for (int j = 2 * SUB; j < 2 * SUB + 2; ++j) {
                 const uint32_t blo = lo0 + ((sb[p] * wbytes) >> 4) + kstep * j;      // compile-time offset, no carry out of the 14-bit field
                 if (p == 0 && j == 0) mma_ts2<false>(d, a_base + sa[p] * 64 + 8 * j, blo, hi0, idesc);
                 else mma_ts2<true>(d, a_base + sa[p] * 64 + 8 * j, blo, hi0, idesc);
             }
         }
     } else {   // timing experiments only
-        uint32_t acc = HALF;
+        uint32_t acc = SUB != 0;
         for (int p = 6 - nprod; p < 6; ++p)
-            for (int j = HALF; j < K / 16; j += 2) { mma_ts(d, a_base + sa[p] * 64 + 8 * j, desc0 + (uint64_t)(((sb[p] * wbytes) >> 4) + kstep * j), idesc, acc); acc = 1; }
+            for (int j = 2 * SUB; j < 2 * SUB + 2; ++j) { mma_ts(d, a_base + sa[p] * 64 + 8 * j, desc0 + (uint64_t)(((sb[p] * wbytes) >> 4) + kstep * j), idesc, acc); acc = 1; }
     }
 }
 
+// hooks of a Chain evaluation: work the column threads do while the tensor pipe runs layer 2 (H1) / the output layer (H2)
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
+
 // Column-thread side of one Chain evaluation.  y[8]: this thread's 8 levels of the stage input (level 8 q + i).
 // Returns nn[i] = NN output n = 8 q + i - 1  (i = 0..8; nn[0] of q = 0 and nn[8] of q = 3 belong to the boundary faces).
-__device__ __forceinline__ void chain_eval(TcShared* S, const float* sbias, const float (&y)[8], float (&nn)[9], int& pd, int wq, int q, long long* twd = nullptr) {
+template <class H1 = NoHook, class H2 = NoHook>
+__device__ __forceinline__ void chain_eval(TcShared* S, const float* sbias, const float (&y)[8], float (&nn)[9], int& pd, int wq, int q, long long* twd = nullptr,
+                                           H1 hook1 = H1(), H2 hook2 = H2()) {
     const uint32_t tl = S->tmem_base + ((uint32_t)(32 * wq) << 16);     // this warp's TMEM lane window
     // ---- layer-1 A operand: levels 8q..8q+7 -> 4 cells per split at columns 4q
     {
@@ -258,39 +314,41 @@ __device__ __forceinline__ void chain_eval(TcShared* S, const float* sbias, cons
         tmem_st4(tl + TM_A + 2 * 64 + 4 * q, p3);
         wait_st();
         fence_before_sync();
-        mbar_arrive(&S->bar_a);
-        mbar_arrive(&S->bar_a1);
+        warp_arrive(&S->bar_a);
     }
-    // ---- hidden layers: D -> bias, relu, split -> A operand of the next layer (units 32q .. 32q+31 -> cells 16q .. 16q+15)
+    // ---- hidden layers: D -> bias, relu, split -> A operand of the next layer.  Thread (column, quarter q) converts the units
+    //      32 s + 8 q .. + 7 in its sub-chunk s = 0..3, so that after sub-chunk s of all four quarters the k-steps 2s, 2s+1 of the next
+    //      layer are complete and their MMAs start under the conversion of the following sub-chunk
 #pragma unroll 1
     for (int l = 0; l < 2; ++l) {
         if (twd) { const long long a = clock64(); mbar_wait(&S->bar_d, pd); twd[l] += clock64() - a; } else mbar_wait(&S->bar_d, pd);
         pd ^= 1;
         fence_after_sync();
-        const float* b = sbias + 128 * l + 32 * q;
-        // the whole D slice of this thread first: the next layer's MMAs start overwriting D as soon as the first halves are published
+        const float* b = sbias + 128 * l + 8 * q;
+        // the whole D slice of this thread first: the next layer's MMAs overwrite D as soon as the first sub-chunks are published
         uint32_t r[32];
-        tmem_ld16(tl + TM_D + 32 * q, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
-        tmem_ld16(tl + TM_D + 32 * q + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+#pragma unroll
+        for (int sc = 0; sc < 4; ++sc) tmem_ld8(tl + TM_D + 32 * sc + 8 * q, *reinterpret_cast<uint32_t(*)[8]>(&r[8 * sc]));
         wait_ld();
 #pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-            uint32_t p1[8], p2[8], p3[8];
+        for (int sc = 0; sc < 4; ++sc) {
+            uint32_t p1[4], p2[4], p3[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 bb = *reinterpret_cast<const float4*>(b + 16 * ch + 4 * i);
-                const float v0 = fmaxf(__uint_as_float(r[16 * ch + 4 * i]) + bb.x, 0.f), v1 = fmaxf(__uint_as_float(r[16 * ch + 4 * i + 1]) + bb.y, 0.f);
-                const float v2 = fmaxf(__uint_as_float(r[16 * ch + 4 * i + 2]) + bb.z, 0.f), v3 = fmaxf(__uint_as_float(r[16 * ch + 4 * i + 3]) + bb.w, 0.f);
+            for (int i = 0; i < 2; ++i) {
+                const float4 bb = *reinterpret_cast<const float4*>(b + 32 * sc + 4 * i);
+                const float v0 = fmaxf(__uint_as_float(r[8 * sc + 4 * i]) + bb.x, 0.f), v1 = fmaxf(__uint_as_float(r[8 * sc + 4 * i + 1]) + bb.y, 0.f);
+                const float v2 = fmaxf(__uint_as_float(r[8 * sc + 4 * i + 2]) + bb.z, 0.f), v3 = fmaxf(__uint_as_float(r[8 * sc + 4 * i + 3]) + bb.w, 0.f);
                 split3(v0, v1, p1[2 * i], p2[2 * i], p3[2 * i]);
                 split3(v2, v3, p1[2 * i + 1], p2[2 * i + 1], p3[2 * i + 1]);
             }
-            tmem_st8(tl + TM_A + 0 * 64 + 16 * q + 8 * ch, p1);
-            tmem_st8(tl + TM_A + 1 * 64 + 16 * q + 8 * ch, p2);
-            tmem_st8(tl + TM_A + 2 * 64 + 16 * q + 8 * ch, p3);
+            tmem_st4(tl + TM_A + 0 * 64 + 16 * sc + 4 * q, p1);
+            tmem_st4(tl + TM_A + 1 * 64 + 16 * sc + 4 * q, p2);
+            tmem_st4(tl + TM_A + 2 * 64 + 16 * sc + 4 * q, p3);
             wait_st();
             fence_before_sync();
-            mbar_arrive(ch == 0 ? &S->bar_a : &S->bar_a1);     // units 32q+16ch.. = k-step 2q+ch of the next layer
+            warp_arrive(sc == 0 ? &S->bar_a : &S->bar_q[sc - 1]);
         }
+        if (l == 0) hook1(); else hook2();
     }
     // ---- output layer: NN[8q-1 .. 8q+7]
     if (twd) { const long long a = clock64(); mbar_wait(&S->bar_d, pd); twd[2] += clock64() - a; } else mbar_wait(&S->bar_d, pd);
@@ -324,11 +382,14 @@ __device__ __forceinline__ void chain_eval(TcShared* S, const float* sbias, cons
 struct SplitBF16x3 {
     static constexpr int IMG = IMG_BYTES, BIAS_OFF = OFF_B;
     static constexpr float INPUT_BOUND = 3.0e38f;              // BF16 has fp32's exponent range: no bound
-    template <int LAYER, int HALF>
-    static __device__ __forceinline__ void issue(uint32_t tb, uint32_t img, int nprod) { issue_layer<LAYER, HALF>(tb, img, nprod); }
-    template <bool FOLD = true>
-    static __device__ __forceinline__ void eval(TcShared* S, const float* sb, const float (&y)[8], float (&nn)[9], int& pd, int wq, int q, long long* twd, bool) {
-        chain_eval(S, sb, y, nn, pd, wq, q, twd);
+    static constexpr bool SPARE_TMEM = false;                  // all 512 tensor-memory columns are in use (three operand splits)
+    static __device__ __forceinline__ uint32_t spare(uint32_t tl, int, int q) { return tl + TM_K + 160 + 8 * q; }
+    template <int LAYER, int SUB>
+    static __device__ __forceinline__ void issue(uint32_t tb, uint32_t img, int nprod) { issue_layer<LAYER, SUB>(tb, img, nprod); }
+    template <bool FOLD = true, class H1 = NoHook, class H2 = NoHook>
+    static __device__ __forceinline__ void eval(TcShared* S, const float* sb, const float (&y)[8], float (&nn)[9], int& pd, int wq, int q, long long* twd, bool,
+                                                H1 h1 = H1(), H2 h2 = H2()) {
+        chain_eval(S, sb, y, nn, pd, wq, q, twd, h1, h2);
     }
 };
 
@@ -382,7 +443,8 @@ __device__ __forceinline__ void split2h(float v0, float v1, uint32_t& ph, uint32
     float f0, f1;
     asm("{\n\t.reg .b16 l, h;\n\tcvt.rn.f16x2.f32 %0, %4, %3;\n\tmov.b32 {l, h}, %0;\n\tcvt.f32.f16 %1, l;\n\tcvt.f32.f16 %2, h;\n\t}"
         : "=r"(ph), "=f"(f0), "=f"(f1) : "f"(v0), "f"(v1));
-    const float r0 = v0 - f0, r1 = v1 - f1;
+    float r0, r1;
+    sub2(r0, r1, v0, v1, f0, f1);
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(pl) : "f"(r1), "f"(r0));
 }
 
@@ -394,13 +456,14 @@ __device__ __forceinline__ void split2h_relu(float v0, float v1, uint32_t& ph, u
     float f0, f1;
     asm("{\n\t.reg .b16 l, h;\n\tcvt.rz.relu.f16x2.f32 %0, %4, %3;\n\tmov.b32 {l, h}, %0;\n\tcvt.f32.f16 %1, l;\n\tcvt.f32.f16 %2, h;\n\t}"
         : "=r"(ph), "=f"(f0), "=f"(f1) : "f"(v0), "f"(v1));
-    const float r0 = v0 - f0, r1 = v1 - f1;
+    float r0, r1;
+    sub2(r0, r1, v0, v1, f0, f1);
     asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(pl) : "f"(r1), "f"(r0));
 }
 
-template <int LAYER, int HALF>
+template <int LAYER, int SUB>
 __device__ __forceinline__ void issue_layer16(uint32_t tmem_base, uint32_t smem_img) {
-    constexpr int K = LAYER == 0 ? 32 : 128, Nn = LAYER == 2 ? 64 : 128;
+    constexpr int Nn = LAYER == 2 ? 64 : 128;
     constexpr uint32_t woff = LAYER == 0 ? OFF16_W1 : (LAYER == 1 ? OFF16_W2 : OFF16_W3);
     constexpr uint32_t wbytes = LAYER == 0 ? W1H_BYTES : W2H_BYTES;
     constexpr uint32_t idesc = make_idesc16(128, Nn);
@@ -413,7 +476,7 @@ __device__ __forceinline__ void issue_layer16(uint32_t tmem_base, uint32_t smem_
 #pragma unroll
         for (int sA = 1; sA >= 0; --sA)
 #pragma unroll
-            for (int j = HALF; j < K / 16; j += 2) {
+            for (int j = 2 * SUB; j < 2 * SUB + 2; ++j) {
                 if (sA == 1 && j == 0) mma_ts2<false>(d, a_base + sA * 64 + 8 * j, lo0 + kstep * j, hi0, idesc);
                 else mma_ts2<true>(d, a_base + sA * 64 + 8 * j, lo0 + kstep * j, hi0, idesc);
             }
@@ -423,7 +486,7 @@ __device__ __forceinline__ void issue_layer16(uint32_t tmem_base, uint32_t smem_
 #pragma unroll
         for (int p = 0; p < 3; ++p)
 #pragma unroll
-            for (int j = HALF; j < K / 16; j += 2) {
+            for (int j = 2 * SUB; j < 2 * SUB + 2; ++j) {
                 const uint32_t blo = lo0 + ((sb[p] * wbytes) >> 4) + kstep * j;
                 if (p == 0 && j == 0) mma_ts2<false>(d, a_base + sa[p] * 64 + 8 * j, blo, hi0, idesc);
                 else mma_ts2<true>(d, a_base + sa[p] * 64 + 8 * j, blo, hi0, idesc);
@@ -433,40 +496,46 @@ __device__ __forceinline__ void issue_layer16(uint32_t tmem_base, uint32_t smem_
 
 // FP16x2 version of chain_eval; sb points at bias1' (then bias2', bias3, consts).  FOLD: relu folded into the conversions (split2h_relu);
 // the RECORD pass of loss_grad keeps the round-to-nearest split so that its trajectories stay those the gradient tests were pinned with
-template <bool FOLD>
-__device__ __forceinline__ void chain_eval16(TcShared* S, const float* sb, const float (&y)[8], float (&nn)[9], int& pd, int wq, int q, long long* twd) {
+template <bool FOLD, class H1 = NoHook, class H2 = NoHook>
+__device__ __forceinline__ void chain_eval16(TcShared* S, const float* sb, const float (&y)[8], float (&nn)[9], int& pd, int wq, int q, long long* twd,
+                                             H1 hook1 = H1(), H2 hook2 = H2()) {
     const uint32_t tl = S->tmem_base + ((uint32_t)(32 * wq) << 16);
     const float s_a0 = sb[291];
     {
         uint32_t ph[4], pl[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) split2h(y[2 * i] * s_a0, y[2 * i + 1] * s_a0, ph[i], pl[i]);
+        for (int i = 0; i < 4; ++i) {
+            float s0, s1;
+            mul2s(s0, s1, y[2 * i], y[2 * i + 1], s_a0);
+            split2h(s0, s1, ph[i], pl[i]);
+        }
         tmem_st4(tl + TM_A + 0 * 64 + 4 * q, ph);
         tmem_st4(tl + TM_A + 1 * 64 + 4 * q, pl);
         wait_st();
         fence_before_sync();
-        mbar_arrive(&S->bar_a);
-        mbar_arrive(&S->bar_a1);
+        warp_arrive(&S->bar_a);
     }
+    // hidden layers: thread (column, quarter q) converts the units 32 s + 8 q .. + 7 in its sub-chunk s = 0..3 (see chain_eval)
 #pragma unroll 1
     for (int l = 0; l < 2; ++l) {
         if (twd) { const long long a = clock64(); mbar_wait(&S->bar_d, pd); twd[l] += clock64() - a; } else mbar_wait(&S->bar_d, pd);
         pd ^= 1;
         fence_after_sync();
-        const float* b = sb + 128 * l + 32 * q;
+        const float* b = sb + 128 * l + 8 * q;
         const float cl = sb[288 + l];
         uint32_t r[32];
-        tmem_ld16(tl + TM_D + 32 * q, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
-        tmem_ld16(tl + TM_D + 32 * q + 16, *reinterpret_cast<uint32_t(*)[16]>(&r[16]));
+#pragma unroll
+        for (int sc = 0; sc < 4; ++sc) tmem_ld8(tl + TM_D + 32 * sc + 8 * q, *reinterpret_cast<uint32_t(*)[8]>(&r[8 * sc]));
         wait_ld();
 #pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-            uint32_t ph[8], pl[8];
+        for (int sc = 0; sc < 4; ++sc) {
+            uint32_t ph[4], pl[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float4 bb = *reinterpret_cast<const float4*>(b + 16 * ch + 4 * i);
-                const float v0 = fmaf(__uint_as_float(r[16 * ch + 4 * i]), cl, bb.x), v1 = fmaf(__uint_as_float(r[16 * ch + 4 * i + 1]), cl, bb.y);
-                const float v2 = fmaf(__uint_as_float(r[16 * ch + 4 * i + 2]), cl, bb.z), v3 = fmaf(__uint_as_float(r[16 * ch + 4 * i + 3]), cl, bb.w);
+            for (int i = 0; i < 2; ++i) {
+                const float4 bb = *reinterpret_cast<const float4*>(b + 32 * sc + 4 * i);
+                float v0, v1, v2, v3;
+                fma2s(v0, v1, __uint_as_float(r[8 * sc + 4 * i]), __uint_as_float(r[8 * sc + 4 * i + 1]), cl, bb.x, bb.y);
+                fma2s(v2, v3, __uint_as_float(r[8 * sc + 4 * i + 2]), __uint_as_float(r[8 * sc + 4 * i + 3]), cl, bb.z, bb.w);
                 if (FOLD) {
                     split2h_relu(v0, v1, ph[2 * i], pl[2 * i]);
                     split2h_relu(v2, v3, ph[2 * i + 1], pl[2 * i + 1]);
@@ -475,12 +544,13 @@ __device__ __forceinline__ void chain_eval16(TcShared* S, const float* sb, const
                     split2h(fmaxf(v2, 0.f), fmaxf(v3, 0.f), ph[2 * i + 1], pl[2 * i + 1]);
                 }
             }
-            tmem_st8(tl + TM_A + 0 * 64 + 16 * q + 8 * ch, ph);
-            tmem_st8(tl + TM_A + 1 * 64 + 16 * q + 8 * ch, pl);
+            tmem_st4(tl + TM_A + 0 * 64 + 16 * sc + 4 * q, ph);
+            tmem_st4(tl + TM_A + 1 * 64 + 16 * sc + 4 * q, pl);
             wait_st();
             fence_before_sync();
-            mbar_arrive(ch == 0 ? &S->bar_a : &S->bar_a1);
+            warp_arrive(sc == 0 ? &S->bar_a : &S->bar_q[sc - 1]);
         }
+        if (l == 0) hook1(); else hook2();
     }
     if (twd) { const long long a = clock64(); mbar_wait(&S->bar_d, pd); twd[2] += clock64() - a; } else mbar_wait(&S->bar_d, pd);
     pd ^= 1;
@@ -495,28 +565,35 @@ __device__ __forceinline__ void chain_eval16(TcShared* S, const float* sb, const
         const float inv3 = sb[290];
         nn[0] = q ? fmaf(__uint_as_float(b0) + __uint_as_float(a0), inv3, b3[8 * q - 1]) : 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) nn[i + 1] = fmaf(__uint_as_float(rb[i]) + __uint_as_float(ra[i]), inv3, b3[8 * q + i]);
+        for (int i = 0; i < 8; i += 2) {
+            float t0, t1;
+            add2(t0, t1, __uint_as_float(rb[i]), __uint_as_float(rb[i + 1]), __uint_as_float(ra[i]), __uint_as_float(ra[i + 1]));
+            fma2s(nn[i + 1], nn[i + 2], t0, t1, inv3, b3[8 * q + i], b3[8 * q + i + 1]);
+        }
     }
     fence_before_sync();
 }
 
 struct SplitFP16x2 {
     static constexpr int IMG = IMG16_BYTES, BIAS_OFF = OFF16_B;
-    template <int LAYER, int HALF>
-    static __device__ __forceinline__ void issue(uint32_t tb, uint32_t img, int) { issue_layer16<LAYER, HALF>(tb, img); }
+    template <int LAYER, int SUB>
+    static __device__ __forceinline__ void issue(uint32_t tb, uint32_t img, int) { issue_layer16<LAYER, SUB>(tb, img); }
     static constexpr float INPUT_BOUND = 128.f;
+    // free 32-column vector slots in tensor memory: the third operand-split region (two slots) and the k7 slot (k7 stays in registers)
+    static constexpr bool SPARE_TMEM = true;
+    static __device__ __forceinline__ uint32_t spare(uint32_t tl, int i, int q) { return tl + (i < 2 ? TM_A + 128 + 32 * i : TM_K + 160) + 8 * q; }
     // The operand scales assume |T_scaled| <= 128 (the hidden-layer bounds then hold rigorously).  The network input is SATURATED
     // at the bound: inside the adaptive solver only wildly wrong trial steps get there and the error estimate rejects them exactly
     // as in FP32 (the flux divergence itself uses the unclamped state); the solver flags a column whose ACCEPTED state leaves the
     // range (status NaN).  With `poison` (nfc_rhs: no controller) an out-of-range or NaN input yields NaN output instead.
-    template <bool FOLD = true>
+    template <bool FOLD = true, class H1 = NoHook, class H2 = NoHook>
     static __device__ __forceinline__ void eval(TcShared* S, const float* sb, const float (&y)[8], float (&nn)[9], int& pd, int wq, int q, long long* twd,
-                                                bool poison) {
+                                                bool poison, H1 h1 = H1(), H2 h2 = H2()) {
         float yc[8];
         bool bad = false;
 #pragma unroll
         for (int i = 0; i < 8; ++i) { yc[i] = fminf(fmaxf(y[i], -INPUT_BOUND), INPUT_BOUND); bad |= !(fabsf(y[i]) <= INPUT_BOUND); }
-        chain_eval16<FOLD>(S, sb, yc, nn, pd, wq, q, twd);
+        chain_eval16<FOLD>(S, sb, yc, nn, pd, wq, q, twd, h1, h2);
         if (poison && bad) {
 #pragma unroll
             for (int i = 0; i < 9; ++i) nn[i] = __int_as_float(0x7fc00000);
@@ -543,40 +620,61 @@ __device__ __forceinline__ void faces_to_f(const float (&y)[8], float ylo, float
     }
 }
 
-// MMA warp main loop: three layers per Chain evaluation until the column threads raise `stop`
+// MMA warp main loop: three layers per Chain evaluation until the column threads raise `stop`.  Layer 1 (K = 32) is issued in one go;
+// the hidden-to-hidden and the output layer in four sub-batches (k-steps 2s, 2s+1) as the column threads publish their sub-chunks.
+template <class SP, int LAYER>
+__device__ __forceinline__ void mma_issue_subs(TcShared* S, uint32_t smem_img, int& pa, int (&pq)[3], long long& t_wait) {
+    const long long c0 = clock64();
+    mbar_wait(&S->bar_a, pa); pa ^= 1;
+    fence_after_sync();
+    t_wait += clock64() - c0;
+    // The operand addresses must be re-derived inside the loop (an add on a uniform register per MMA): as loop invariants the
+    // compiler hoists them all and, with the 32 registers this warp keeps, spills them -- a local-memory load in front of the MMA.
+    uint32_t tb = *reinterpret_cast<volatile uint32_t*>(&S->tmem_base), img = smem_img;
+    asm volatile("" : "+r"(tb), "+r"(img));
+    SP::template issue<LAYER, 0>(tb, img, S->nprod);
+    mbar_wait(&S->bar_q[0], pq[0]); pq[0] ^= 1;
+    fence_after_sync();
+    asm volatile("" : "+r"(tb), "+r"(img));
+    SP::template issue<LAYER, 1>(tb, img, S->nprod);
+    mbar_wait(&S->bar_q[1], pq[1]); pq[1] ^= 1;
+    fence_after_sync();
+    asm volatile("" : "+r"(tb), "+r"(img));
+    SP::template issue<LAYER, 2>(tb, img, S->nprod);
+    mbar_wait(&S->bar_q[2], pq[2]); pq[2] ^= 1;
+    fence_after_sync();
+    asm volatile("" : "+r"(tb), "+r"(img));
+    SP::template issue<LAYER, 3>(tb, img, S->nprod);
+    mma_commit(&S->bar_d);
+}
+
 template <class SP>
 __device__ __forceinline__ void mma_warp_loop(TcShared* S, uint32_t smem_img, int lane, long long* dbg = nullptr) {
     if (lane == 0) {
-        int pa = 0, layer = 0;
-        long long tw0[3] = {0, 0, 0}, ti0[3] = {0, 0, 0}, tw1[3] = {0, 0, 0}, ti1[3] = {0, 0, 0}, n[3] = {0, 0, 0};
-        long long c0 = clock64();
+        int pa = 0, pq[3] = {0, 0, 0};
+        long long tw[3] = {0, 0, 0}, ti[3] = {0, 0, 0}, n = 0;
         while (true) {
-            mbar_wait(&S->bar_a, pa);
+            long long c0 = clock64();
+            mbar_wait(&S->bar_a, pa); pa ^= 1;
             if (*reinterpret_cast<volatile int*>(&S->stop)) break;
             fence_after_sync();
-            const long long c1 = clock64();
-            // The operand addresses must be re-derived inside the loop (an add on a uniform register per MMA): as loop invariants the
-            // compiler hoists them all and, with the 32 registers this warp keeps, spills them -- a local-memory load in front of the MMA.
-            uint32_t tb = S->tmem_base, img = smem_img;
+            long long c1 = clock64();
+            uint32_t tb = *reinterpret_cast<volatile uint32_t*>(&S->tmem_base), img = smem_img;
             asm volatile("" : "+r"(tb), "+r"(img));
-            if (layer == 0) SP::template issue<0, 0>(tb, img, S->nprod);
-            else if (layer == 1) SP::template issue<1, 0>(tb, img, S->nprod);
-            else SP::template issue<2, 0>(tb, img, S->nprod);
-            const long long c2 = clock64();
-            mbar_wait(&S->bar_a1, pa); pa ^= 1;
-            fence_after_sync();
-            const long long c3 = clock64();
-            asm volatile("" : "+r"(tb), "+r"(img));
-            if (layer == 0) SP::template issue<0, 1>(tb, img, S->nprod);
-            else if (layer == 1) SP::template issue<1, 1>(tb, img, S->nprod);
-            else SP::template issue<2, 1>(tb, img, S->nprod);
+            SP::template issue<0, 0>(tb, img, S->nprod);
             mma_commit(&S->bar_d);
-            const long long c4 = clock64();
-            tw0[layer] += c1 - c0; ti0[layer] += c2 - c1; tw1[layer] += c3 - c2; ti1[layer] += c4 - c3; n[layer] += 1; c0 = c4;
-            layer = layer == 2 ? 0 : layer + 1;
+            long long c2 = clock64();
+            tw[0] += c1 - c0; ti[0] += c2 - c1;
+            long long w = 0;
+            mma_issue_subs<SP, 1>(S, smem_img, pa, pq, w);
+            c1 = clock64(); tw[1] += w; ti[1] += c1 - c2 - w;
+            w = 0;
+            mma_issue_subs<SP, 2>(S, smem_img, pa, pq, w);
+            c2 = clock64(); tw[2] += w; ti[2] += c2 - c1 - w;
+            n += 1;
         }
-        if (dbg && blockIdx.x == 0)
-            for (int l = 0; l < 3; ++l) { dbg[5 * l] = tw0[l]; dbg[5 * l + 1] = ti0[l]; dbg[5 * l + 2] = tw1[l]; dbg[5 * l + 3] = ti1[l]; dbg[5 * l + 4] = n[l]; }
+        if (dbg && blockIdx.x == 0)      // per layer: waiting for the first sub-chunk | everything up to the commit (issue + later sub-chunks)
+            for (int l = 0; l < 3; ++l) { dbg[5 * l] = tw[l]; dbg[5 * l + 1] = ti[l]; dbg[5 * l + 2] = 0; dbg[5 * l + 3] = 0; dbg[5 * l + 4] = n; }
     }
     __syncwarp();
 }
@@ -585,8 +683,8 @@ __device__ __forceinline__ void mma_warp_loop(TcShared* S, uint32_t smem_img, in
 __device__ __forceinline__ void tc_prologue(TcShared* S, unsigned char* simg, const unsigned char* gimg, int warp, int img_bytes, int nprod = 6) {
     if (threadIdx.x == 0) {
         mbar_init(&S->bar_w, 1);
-        mbar_init(&S->bar_a, NCT);
-        mbar_init(&S->bar_a1, NCT);
+        mbar_init(&S->bar_a, NCW);
+        mbar_init(&S->bar_q[0], NCW); mbar_init(&S->bar_q[1], NCW); mbar_init(&S->bar_q[2], NCW);
         mbar_init(&S->bar_d, 1);
         S->stop = 0;
         S->nprod = nprod;
@@ -652,7 +750,7 @@ rhs_tc_kernel(const unsigned char* __restrict__ gimg, const float* __restrict__ 
         asm volatile("bar.sync 1, 512;" ::: "memory");
         if (threadIdx.x == 0) S.stop = 1;
         asm volatile("bar.sync 1, 512;" ::: "memory");
-        mbar_arrive(&S.bar_a);
+        warp_arrive(&S.bar_a);
     }
     fence_before_sync();
     __syncthreads();
@@ -677,23 +775,82 @@ __device__ __forceinline__ void cta_bar() { asm volatile("bar.sync 1, 512;" ::: 
 // k_j (j = 2..7) chunk of this thread in tensor memory: column TM_K + 32 (j-2) + 8 q, 8 cells
 __device__ __forceinline__ uint32_t kaddr(uint32_t tl, int j, int q) { return tl + TM_K + 32 * (j - 2) + 8 * q; }
 
-// acc[i] = sum_j coef[j] * k_j[i] over j = 1..6 (k1 in registers, k2..k6 from tensor memory)
-__device__ __forceinline__ void combine6(uint32_t tl, int q, const float (&k1)[8], const float* coef, float (&acc)[8]) {
-    float kb[8], kc[8];
-    tmem_ld8f(kaddr(tl, 2, q), kb);
-    tmem_ld8f(kaddr(tl, 3, q), kc);
+// Step-boundary arithmetic shared by the one- and the two-tile kernel (they agree bit for bit).  Divisions and the square root of the
+// controller are the fast approximations (MUFU.RCP / MUFU.SQRT + one multiply, <= 2 ulp): the step-size sequence does not need more, the
+// accept test compares the error norm itself, and the position inside a step (theta of the dense output) is good to 1e-7.  The IEEE
+// sequences they replace were ~10 instructions each on the serial path every thread walks between two barriers.
+__device__ __forceinline__ float fast_div(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// squared scaled error of one level: (h * sum btilde_j k_j / (abstol + max(|u|, |u_new|) reltol))^2 accumulated into `part`
+__device__ __forceinline__ float err_term(float part, float e6, float k7, float hs, float u, float y, float abstol, float reltol) {
+    const float ei = fmaf(NFC_BT7, k7, e6) * hs;
+    const float r = fast_div(ei, fmaf(fmaxf(fabsf(u), fabsf(y)), reltol, abstol));
+    return fmaf(r, r, part);
+}
+// OrdinaryDiffEq's PI controller (beta1 = 7/50, beta2 = 2/25, gamma = 9/10, qmin = 1/5, qmax = 10; reject: dt / min(1/qmin, q11 / gamma))
+__device__ __forceinline__ void pi_controller(float ee, float qold, float hs, bool& accept, float& dtnew) {
+    const float q11 = __powf(ee, 0.14f);
+    float qq = fast_div(q11, __powf(qold, 0.08f));
+    qq = fmaxf(0.1f, fminf(5.0f, qq * (1.0f / 0.9f)));
+    accept = ee <= 1.0f;
+    dtnew = accept ? fast_div(hs, qq) : fast_div(hs, fminf(5.0f, q11 * (1.0f / 0.9f)));
+}
+constexpr int SAVE_SMEM = 2048;           // save times kept in shared memory by the one-tile kernel (longer lists are read from global memory)
+
+// acc[i] = sum_j coef[j-1] * k_j[i] over j = 1..nk (k1 in registers, k2..k6 from tensor memory), one fma chain in the order of j.
+// nk is uniform over the CTA (tcgen05.ld is warp-collective); all loads are in flight before the first use
+__device__ __forceinline__ void combine_n(uint32_t tl, int q, const float (&k1)[8], const float* coef, int nk, float (&acc)[8]) {
+    float ka[8], kb[8], kc[8], kd[8], ke[8];
+    if (nk >= 2) tmem_ld8f(kaddr(tl, 2, q), ka);
+    if (nk >= 3) tmem_ld8f(kaddr(tl, 3, q), kb);
+    if (nk >= 4) tmem_ld8f(kaddr(tl, 4, q), kc);
+    if (nk >= 5) tmem_ld8f(kaddr(tl, 5, q), kd);
+    if (nk >= 6) tmem_ld8f(kaddr(tl, 6, q), ke);
+    scal8(acc, coef[0], k1);
+    if (nk >= 2) { wait_ld(); axpy8(acc, coef[1], ka); }
+    if (nk >= 3) axpy8(acc, coef[2], kb);
+    if (nk >= 4) axpy8(acc, coef[3], kc);
+    if (nk >= 5) axpy8(acc, coef[4], kd);
+    if (nk >= 6) axpy8(acc, coef[5], ke);
+}
+
+// Tsit5 dense output in power basis, u(t + th h) = u + h th (k1 + th (c2 + th (c3 + th c4))): the k1..k6 part of c2, c3, c4 (each one fma
+// chain in the order of j; every stage vector is loaded once for the three); the k7 terms are added by dense_k7
+__device__ __forceinline__ void dense_partial(uint32_t tl, int q, const float (&k1)[8], float (&c2)[8], float (&c3)[8], float (&c4)[8]) {
+    const float r2[6] = {-2.763706197274826f, 0.13169999999999998f, 3.9302962368947516f, -12.411077166933676f, 37.50931341651104f, -27.896526289197286f};
+    const float r3[6] = {2.9132554618219126f, -0.2234f, -5.941033872131505f, 30.33818863028232f, -88.1789048947664f, 65.09189467479366f};
+    const float r4[6] = {-1.0530884977290216f, 0.1017f, 2.490627285651253f, -16.548102889244902f, 47.37952196281928f, -34.87065786149661f};
+    float ka[8], kb[8];
+    tmem_ld8f(kaddr(tl, 2, q), ka);
+    tmem_ld8f(kaddr(tl, 3, q), kb);
+    scal8(c2, r2[0], k1); scal8(c3, r3[0], k1); scal8(c4, r4[0], k1);
     wait_ld();
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { acc[i] = coef[0] * k1[i]; acc[i] = fmaf(coef[1], kb[i], acc[i]); acc[i] = fmaf(coef[2], kc[i], acc[i]); }
-    tmem_ld8f(kaddr(tl, 4, q), kb);
-    tmem_ld8f(kaddr(tl, 5, q), kc);
+    axpy8(c2, r2[1], ka); axpy8(c3, r3[1], ka); axpy8(c4, r4[1], ka);
+    axpy8(c2, r2[2], kb); axpy8(c3, r3[2], kb); axpy8(c4, r4[2], kb);
+    tmem_ld8f(kaddr(tl, 4, q), ka);
+    tmem_ld8f(kaddr(tl, 5, q), kb);
     wait_ld();
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { acc[i] = fmaf(coef[3], kb[i], acc[i]); acc[i] = fmaf(coef[4], kc[i], acc[i]); }
-    tmem_ld8f(kaddr(tl, 6, q), kb);
+    axpy8(c2, r2[3], ka); axpy8(c3, r3[3], ka); axpy8(c4, r4[3], ka);
+    axpy8(c2, r2[4], kb); axpy8(c3, r3[4], kb); axpy8(c4, r4[4], kb);
+    tmem_ld8f(kaddr(tl, 6, q), ka);
     wait_ld();
+    axpy8(c2, r2[5], ka); axpy8(c3, r3[5], ka); axpy8(c4, r4[5], ka);
+}
+__device__ __forceinline__ void dense_k7(const float (&k7)[8], float (&c2)[8], float (&c3)[8], float (&c4)[8]) {
+    axpy8(c2, 1.5f, k7); axpy8(c3, -4.0f, k7); axpy8(c4, 2.5f, k7);
+}
+// v = u + h th (k1 + th (c2 + th (c3 + th c4)))  (the dense output at th in [0, 1])
+__device__ __forceinline__ void dense_eval(float (&v)[8], float hs, float th, const float (&u)[8], const float (&k1)[8], const float (&c2)[8],
+                                           const float (&c3)[8], const float (&c4)[8]) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = fmaf(coef[5], kb[i], acc[i]);
+    for (int i = 0; i < 8; i += 2) {
+        float a0, a1;
+        fma2s(a0, a1, c4[i], c4[i + 1], th, c3[i], c3[i + 1]);
+        fma2s(a0, a1, a0, a1, th, c2[i], c2[i + 1]);
+        fma2s(a0, a1, a0, a1, th, k1[i], k1[i + 1]);
+        mul2s(a0, a1, a0, a1, th);
+        fma2s(v[i], v[i + 1], a0, a1, hs, u[i], u[i + 1]);
+    }
 }
 
 // RECORD: forward pass of nfc_loss_grad (nfc_adjoint.cuh): instead of the trajectory it writes the residuals at the save points, the
@@ -703,7 +860,10 @@ template <class SP, bool RECORD = false>
 __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned char* __restrict__ gimg, const SolveParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ TcShared S;
+    __shared__ float s_save[SAVE_SMEM];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* const sv = P.n_save <= SAVE_SMEM ? s_save : P.saveat;       // read by every thread at every accepted step
+    if (P.n_save <= SAVE_SMEM) for (int i = threadIdx.x; i < P.n_save; i += NTHREADS) s_save[i] = P.saveat[i];      // visible after the prologue's __syncthreads
 #ifdef NFC_DEBUG_TIMERS
     tc_prologue(&S, smem_raw, gimg, warp, SP::IMG, (!RECORD && P.tape_cap >= 1 && P.tape_cap <= 6) ? P.tape_cap : 6);   // debug build: tape_cap doubles as a timing knob
     long long* const dbgbuf = RECORD ? nullptr : reinterpret_cast<long long*>(P.resid);                                  //              P.resid carries the phase timers
@@ -719,7 +879,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
     } else {
         reg_inc<REGS_COL>();
         const int wq = warp & 3, q = warp >> 2, c = 32 * wq + lane;
-        long long twd[4] = {0, 0, 0, 0};
+        long long twd[4] = {0, 0, 0, 0}, tstage = 0, nsteps = 0, tb[6] = {0, 0, 0, 0, 0, 0}, tmark = 0;     // tstage: cycles inside the six-stage loop; the rest of the kernel's time is step boundaries
         long long* const twdp = dbgbuf ? twd : nullptr;      // phase timers: debug build with NFC_TC_DEBUG=1 only
         const long long tstart = clock64();
         const uint32_t tl = S.tmem_base + ((uint32_t)(32 * wq) << 16);
@@ -733,6 +893,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
 #pragma unroll
         for (int i = 0; i < 8; ++i) { u[i] = 0.f; k1[i] = 0.f; }
         while (true) {
+            if (twdp) { const long long n = clock64(); if (tmark) tb[3] += n - tmark; tmark = n; }
             // ---------------- retire / refill ----------------
             if (q == 0) {
                 int nc = -2;                                    // -2: keep the current column
@@ -756,6 +917,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
             }
             if (threadIdx.x == 0) S.any = 0;
             cta_bar();
+            if (twdp) { const long long n = clock64(); tb[0] += n - tmark; tmark = n; }
             {
                 const int nc = S.newcol[c];
                 // tcgen05.ld/st are warp-collective: NEVER issue them under a lane-dependent branch.  k2..k7 are dead at a
@@ -779,7 +941,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
                         dt = P.dt_init[nc];
                         bot = P.colp[(long long)nc * 3 + 0]; top = P.colp[(long long)nc * 3 + 1];
                         kk = P.use_kca ? P.colp[(long long)nc * 3 + 2] * (float)NZ : 0.f;
-                        while (si < P.n_save && P.saveat[si] <= 0.f) {
+                        while (si < P.n_save && sv[si] <= 0.f) {
                             const long long o2i = ((long long)nc * P.n_save + si) * NZ + 8 * q;
                             if (RECORD) {
                                 const float4 ta = *reinterpret_cast<const float4*>(P.Ttrue + o2i), tb = *reinterpret_cast<const float4*>(P.Ttrue + o2i + 4);
@@ -791,9 +953,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
                                 for (int i = 0; i < 8; ++i) sse = fmaf(r[i], r[i], sse);
                                 lsum += (double)sse;
                             } else {
-                                float* o2 = P.Tout + o2i;
-                                *reinterpret_cast<float4*>(o2) = make_float4(u[0], u[1], u[2], u[3]);
-                                *reinterpret_cast<float4*>(o2 + 4) = make_float4(u[4], u[5], u[6], u[7]);
+                                float* o2 = P.Tout + o2i;          // streaming stores: 1 GB of trajectories must not evict the inputs of later columns from L2
+                                __stcs(reinterpret_cast<float4*>(o2), make_float4(u[0], u[1], u[2], u[3]));
+                                __stcs(reinterpret_cast<float4*>(o2 + 4), make_float4(u[4], u[5], u[6], u[7]));
                             }
                             ++si;
                         }
@@ -807,6 +969,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
                 if (col >= 0) S.any = 1;
             }
             cta_bar();
+            if (twdp) { const long long n = clock64(); tb[1] += n - tmark; tmark = n; }
             if (!S.any) break;
             // ---------------- one attempted Tsit5 step ----------------
             float hs = 0.f;
@@ -815,37 +978,52 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
                 hs = fminf(dt, P.tf - t);
                 if (t + hs >= P.tf * (1.0f - 1e-6f)) { hs = P.tf - t; last = true; }
             }
-            float k7[8];
+            // The linear combination a stage needs, sum_j a_sj k_j, is formed ahead of time: its k1 .. k_{s+1} part while the tensor pipe runs
+            // layer 2 of stage s (hook of the Chain evaluation), its last term when f(y_s) = k_{s+2} arrives.  After the last stage the hooks
+            // form the error estimate's and the dense output's k1..k6 parts instead.  Same fma chains, term by term, as a combination
+            // computed in one go.
+            float k7[8], pre[8];
+            const long long tloop = twdp ? clock64() : 0;
+            scal8(pre, c_tsit5_a[0][0], k1);
+            const float bt[6] = {NFC_BT1, NFC_BT2, NFC_BT3, NFC_BT4, NFC_BT5, NFC_BT6};
 #pragma unroll 1
             for (int s = 0; s < 6; ++s) {
-                float acc[8];
-                combine6(tl, q, k1, c_tsit5_a[s], acc);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) y[i] = fmaf(hs, acc[i], u[i]);
+                for (int i = 0; i < 8; i += 2) fma2s(y[i], y[i + 1], pre[i], pre[i + 1], hs, u[i], u[i + 1]);
                 xb ^= 1;
                 S.xch[xb][c][q][0] = y[0];
                 S.xch[xb][c][q][1] = y[7];
                 float nn[9], f[8];
-                SP::template eval<true>(&S, sbias, y, nn, pd, wq, q, twdp, false);      // nfc_solve and the RECORD pass of nfc_loss_grad share ONE arithmetic
+                auto h1 = [&]() {       // two calls: the coefficient tables live in different address spaces (constant bank / immediates)
+                    if (s < 5) combine_n(tl, q, k1, c_tsit5_a[s + 1], s + 1, pre);
+                    else combine_n(tl, q, k1, bt, 6, pre);
+                };
+                auto h2 = [&]() {
+                    if (SP::SPARE_TMEM && s == 5) {      // dense-output partial sums, parked in free tensor-memory columns until the step is judged
+                        float d2[8], d3[8], d4[8];
+                        dense_partial(tl, q, k1, d2, d3, d4);
+                        tmem_st8f(SP::spare(tl, 0, q), d2);
+                        tmem_st8f(SP::spare(tl, 1, q), d3);
+                        tmem_st8f(SP::spare(tl, 2, q), d4);
+                        wait_st();
+                    }
+                };
+                SP::template eval<true>(&S, sbias, y, nn, pd, wq, q, twdp, false, h1, h2);      // nfc_solve and the RECORD pass of nfc_loss_grad share ONE arithmetic
                 const float ylo = q > 0 ? S.xch[xb][c][q - 1][1] : 0.f, yhi = q < 3 ? S.xch[xb][c][q + 1][0] : 0.f;
                 faces_to_f(y, ylo, yhi, nn, bot, top, kk, P.pref, q, f);
-                tmem_st8f(kaddr(tl, s + 2, q), f);
-                wait_st();
+                if (s < 5) {
+                    tmem_st8f(kaddr(tl, s + 2, q), f);       // completed by the wait::st of the next evaluation's operand stores, long before a hook reads it
+                    axpy8(pre, c_tsit5_a[s + 1][s + 1], f);
+                }
 #pragma unroll
                 for (int i = 0; i < 8; ++i) k7[i] = f[i];          // after s == 5 this is k7 = f(u_new) (FSAL)
             }
-            // y == u_new, k7 == f(u_new); error estimate = h * sum btilde_j k_j
+            if (twdp) { tmark = clock64(); tstage += tmark - tloop; nsteps += 1; }
+            // y == u_new, k7 == f(u_new), pre == sum_{j<=6} btilde_j k_j; error estimate = h * sum btilde_j k_j
             float part = 0.f;
             {
-                const float bt[6] = {NFC_BT1, NFC_BT2, NFC_BT3, NFC_BT4, NFC_BT5, NFC_BT6};
-                float e[8];
-                combine6(tl, q, k1, bt, e);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float ei = fmaf(NFC_BT7, k7[i], e[i]) * hs;
-                    const float r = ei / (P.abstol + fmaxf(fabsf(u[i]), fabsf(y[i])) * P.reltol);
-                    part = fmaf(r, r, part);
-                }
+                for (int i = 0; i < 8; ++i) part = err_term(part, pre[i], k7[i], hs, u[i], y[i], P.abstol, P.reltol);
             }
             pb ^= 1;
             S.part[pb][c][q] = part;
@@ -855,38 +1033,31 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
                 for (int i = 1; i < 8; ++i) m = fmaxf(m, fabsf(y[i]));
                 S.rng[pb][c][q] = m;
             }
-            // dense output in power basis, u(t + th h) = u + h th (k1 + th (c2 + th (c3 + th c4))): computed by the whole warp
-            // (tensor-memory loads are warp-collective), consumed below under lane-divergent control flow
+            // dense output: computed / fetched by the whole warp (tensor-memory loads are warp-collective), consumed below under
+            // lane-divergent control flow
             float c2[8], c3[8], c4[8];
-            {
-                const float r2[6] = {-2.763706197274826f, 0.13169999999999998f, 3.9302962368947516f, -12.411077166933676f, 37.50931341651104f, -27.896526289197286f};
-                const float r3[6] = {2.9132554618219126f, -0.2234f, -5.941033872131505f, 30.33818863028232f, -88.1789048947664f, 65.09189467479366f};
-                const float r4[6] = {-1.0530884977290216f, 0.1017f, 2.490627285651253f, -16.548102889244902f, 47.37952196281928f, -34.87065786149661f};
-                combine6(tl, q, k1, r2, c2);
-                combine6(tl, q, k1, r3, c3);
-                combine6(tl, q, k1, r4, c4);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { c2[i] = fmaf(1.5f, k7[i], c2[i]); c3[i] = fmaf(-4.0f, k7[i], c3[i]); c4[i] = fmaf(2.5f, k7[i], c4[i]); }
+            if (SP::SPARE_TMEM) {
+                tmem_ld8f(SP::spare(tl, 0, q), c2);
+                tmem_ld8f(SP::spare(tl, 1, q), c3);
+                tmem_ld8f(SP::spare(tl, 2, q), c4);
+                wait_ld();
+            } else {
+                dense_partial(tl, q, k1, c2, c3, c4);
             }
+            dense_k7(k7, c2, c3, c4);
             cta_bar();
+            if (twdp) { const long long n = clock64(); tb[2] += n - tmark; tmark = n; }
             if (col >= 0) {
-                const float ee = sqrtf(((S.part[pb][c][0] + S.part[pb][c][1]) + (S.part[pb][c][2] + S.part[pb][c][3])) * (1.f / NZ));
+                const float ee = fast_sqrt(((S.part[pb][c][0] + S.part[pb][c][1]) + (S.part[pb][c][2] + S.part[pb][c][3])) * (1.f / NZ));
                 bool accept;
                 float dtnew;
                 if (!isfinite(ee)) { status = ST_NAN; accept = false; dtnew = hs; }
                 else if (P.fixed_dt > 0.f) { accept = true; dtnew = P.fixed_dt; }
-                else {
-                    // PI controller exponents: the fast power (2 ulp) is ample for the trajectory, whose accept test is on ee itself.  The RECORD
-                    // pass uses the same arithmetic, so that mse(nfc_solve(...), truth) and the loss nfc_loss_grad reports are the same number
-                    const float q11 = __powf(ee, 0.14f);
-                    float qq = q11 / __powf(qold, 0.08f);
-                    qq = fmaxf(0.1f, fminf(5.0f, qq / 0.9f));
-                    accept = ee <= 1.0f;
-                    dtnew = accept ? hs / qq : hs / fminf(5.0f, q11 / 0.9f);
-                }
+                else pi_controller(ee, qold, hs, accept, dtnew);      // the RECORD pass uses the same arithmetic: mse(nfc_solve(...), truth) and the loss nfc_loss_grad reports are the same number
                 if (accept && !(fmaxf(fmaxf(S.rng[pb][c][0], S.rng[pb][c][1]), fmaxf(S.rng[pb][c][2], S.rng[pb][c][3])) <= SP::INPUT_BOUND)) {
                     status = ST_RANGE; accept = false;           // an accepted state outside the operand range of the split: report, never guess (the host calls re-solve it on the BF16x3 split)
                 }
+                if (twdp) { const long long n = clock64(); tb[4] += n - tmark; }
                 if (accept) {
                     const float tn = last ? P.tf : t + hs;
                     if (RECORD) {
@@ -907,13 +1078,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
                         }
                     }
                     while (si < P.n_save) {
-                        const float ts = P.saveat[si];
+                        const float ts = sv[si];
                         if (ts > tn) break;
-                        const float th = fminf((ts - t) / hs, 1.0f);
+                        const float th = fminf(fast_div(ts - t, hs), 1.0f);
                         const long long o2i = ((long long)col * P.n_save + si) * NZ + 8 * q;
                         float v[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) v[i] = fmaf(hs, th * fmaf(th, fmaf(th, fmaf(th, c4[i], c3[i]), c2[i]), k1[i]), u[i]);
+                        dense_eval(v, hs, th, u, k1, c2, c3, c4);
                         if (RECORD) {
                             const float4 ta = *reinterpret_cast<const float4*>(P.Ttrue + o2i), tb = *reinterpret_cast<const float4*>(P.Ttrue + o2i + 4);
                             const float r[8] = {v[0] - ta.x, v[1] - ta.y, v[2] - ta.z, v[3] - ta.w, v[4] - tb.x, v[5] - tb.y, v[6] - tb.z, v[7] - tb.w};
@@ -925,11 +1095,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
                             lsum += (double)sse;
                         } else {
                             float* o2 = P.Tout + o2i;
-                            *reinterpret_cast<float4*>(o2) = make_float4(v[0], v[1], v[2], v[3]);
-                            *reinterpret_cast<float4*>(o2 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                            __stcs(reinterpret_cast<float4*>(o2), make_float4(v[0], v[1], v[2], v[3]));
+                            __stcs(reinterpret_cast<float4*>(o2 + 4), make_float4(v[4], v[5], v[6], v[7]));
                         }
                         ++si;
                     }
+                    if (twdp) { const long long n = clock64(); tb[5] += n - tmark; }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) { u[i] = y[i]; k1[i] = k7[i]; }
                     t = tn;
@@ -949,7 +1120,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
         }
         if (dbgbuf && blockIdx.x == 0 && threadIdx.x == 0) {
             long long* dbg = dbgbuf;
-            dbg[16] = twd[0]; dbg[17] = twd[1]; dbg[18] = twd[2]; dbg[19] = clock64() - tstart;
+            dbg[16] = twd[0]; dbg[17] = twd[1]; dbg[18] = twd[2]; dbg[19] = clock64() - tstart; dbg[20] = tstage; dbg[21] = nsteps; dbg[22] = tb[0]; dbg[23] = tb[1]; dbg[24] = tb[2]; dbg[25] = tb[3]; dbg[26] = tb[4]; dbg[27] = tb[5];
         }
         if (RECORD) {
 #pragma unroll
@@ -960,7 +1131,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
         cta_bar();
         if (threadIdx.x == 0) S.stop = 1;
         cta_bar();
-        mbar_arrive(&S.bar_a);
+        warp_arrive(&S.bar_a);
     }
     fence_before_sync();
     __syncthreads();

@@ -61,7 +61,8 @@ template <bool DBG> __device__ __forceinline__ long long tick() { return DBG ? c
 // accumulator / operand regions: tile T, layer l reads A from region (l + 2T) % 3 and writes D to region (l + 1 + 2T) % 3
 __host__ __device__ constexpr uint32_t region(int i) { return 128u * (uint32_t)(i % 3); }
 
-// all MMAs of one Dense layer of one tile, in the order of tc::issue_layer16<LAYER, 0> followed by <LAYER, 1>
+// all MMAs of one Dense layer of one tile, in the order of tc::issue_layer16<LAYER, 0>, <LAYER, 1>, ... (sub-batches of two k-steps):
+// the accumulation order decides the rounding, and the two kernels agree bit for bit
 template <int LAYER>
 __device__ __forceinline__ void issue2(uint32_t a_reg, uint32_t d_reg, uint32_t smem_img) {
     constexpr int K = LAYER == 0 ? 32 : 128, Nn = LAYER == 2 ? 64 : 128;
@@ -72,14 +73,14 @@ __device__ __forceinline__ void issue2(uint32_t a_reg, uint32_t d_reg, uint32_t 
     const uint64_t desc0 = make_bdesc(smem_img + woff, Nn);
     const uint32_t lo0 = (uint32_t)desc0, hi0 = (uint32_t)(desc0 >> 32);
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
+    for (int sub = 0; sub < K / 32; ++sub) {
         if (LAYER == 2) {
 #pragma unroll
             for (int sA = 1; sA >= 0; --sA)
 #pragma unroll
-                for (int j = half; j < K / 16; j += 2) {
+                for (int j = 2 * sub; j < 2 * sub + 2; ++j) {
                     const uint32_t a = a_reg + 32 * (j >> 1) + 16 * sA + 8 * (j & 1);
-                    if (half == 0 && sA == 1 && j == 0) mma_ts2<false>(d_reg, a, lo0 + kstep * j, hi0, idesc);
+                    if (sA == 1 && j == 0) mma_ts2<false>(d_reg, a, lo0 + kstep * j, hi0, idesc);
                     else mma_ts2<true>(d_reg, a, lo0 + kstep * j, hi0, idesc);
                 }
         } else {
@@ -88,10 +89,10 @@ __device__ __forceinline__ void issue2(uint32_t a_reg, uint32_t d_reg, uint32_t 
 #pragma unroll
             for (int p = 0; p < 3; ++p)
 #pragma unroll
-                for (int j = half; j < K / 16; j += 2) {
+                for (int j = 2 * sub; j < 2 * sub + 2; ++j) {
                     const uint32_t a = LAYER == 0 ? a_reg + 64 + 32 * sa[p] + 8 * j : a_reg + 32 * (j >> 1) + 16 * sa[p] + 8 * (j & 1);
                     const uint32_t blo = lo0 + ((sb[p] * wbytes) >> 4) + kstep * j;
-                    if (half == 0 && p == 0 && j == 0) mma_ts2<false>(d_reg, a, blo, hi0, idesc);
+                    if (p == 0 && j == 0) mma_ts2<false>(d_reg, a, blo, hi0, idesc);
                     else mma_ts2<true>(d_reg, a, blo, hi0, idesc);
                 }
         }
@@ -144,38 +145,21 @@ template <int T> __device__ __forceinline__ void ks_load(unsigned char* ks, int 
     k[0] = a.x; k[1] = a.y; k[2] = a.z; k[3] = a.w; k[4] = b.x; k[5] = b.y; k[6] = b.z; k[7] = b.w;
 }
 
-// acc = sum_{j = 1 .. nk} coef[j-1] k_j in the operation order of tc::combine6 (terms j > nk have a zero coefficient there)
+// acc = sum_{j = 1 .. nk} coef[j-1] k_j in the operation order of tc::combine_n
 template <int T>
 __device__ __forceinline__ void combine(uint32_t tl, unsigned char* ks, int q, int c, const float (&k1)[8], const float* coef, int nk, float (&acc)[8]) {
     float kb[8], kc[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = coef[0] * k1[i];
+    scal8(acc, coef[0], k1);
     if (nk >= 2) {                                   // nk is uniform over the CTA: tcgen05.ld is warp-collective
         tmem_ld8f(kt_addr<T>(tl, 2, q), kb);
         if (nk >= 3) tmem_ld8f(kt_addr<T>(tl, 3, q), kc);
         wait_ld();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(coef[1], kb[i], acc[i]);
-        if (nk >= 3) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) acc[i] = fmaf(coef[2], kc[i], acc[i]);
-        }
+        axpy8(acc, coef[1], kb);
+        if (nk >= 3) axpy8(acc, coef[2], kc);
     }
-    if (nk >= 4) {
-        ks_load<T>(ks, 4, q, c, kb);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(coef[3], kb[i], acc[i]);
-    }
-    if (nk >= 5) {
-        ks_load<T>(ks, 5, q, c, kb);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(coef[4], kb[i], acc[i]);
-    }
-    if (nk >= 6) {
-        ks_load<T>(ks, 6, q, c, kb);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = fmaf(coef[5], kb[i], acc[i]);
-    }
+    if (nk >= 4) { ks_load<T>(ks, 4, q, c, kb); axpy8(acc, coef[3], kb); }
+    if (nk >= 5) { ks_load<T>(ks, 5, q, c, kb); axpy8(acc, coef[4], kb); }
+    if (nk >= 6) { ks_load<T>(ks, 6, q, c, kb); axpy8(acc, coef[5], kb); }
 }
 
 // ---- P0: stage input y = u + h sum a_sj k_j, published as the layer-1 A operand ------------------------------------------------
@@ -185,7 +169,7 @@ __device__ __forceinline__ void stage_input(Shared2* S, unsigned char* ks, const
     combine<T>(tl, ks, q, c, R.k1, c_tsit5_a[s], s + 1, acc);
     const float hs = S->cs[T].hs[c];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) R.y[i] = fmaf(hs, acc[i], R.u[i]);
+    for (int i = 0; i < 8; i += 2) fma2s(R.y[i], R.y[i + 1], acc[i], acc[i + 1], hs, R.u[i], R.u[i + 1]);
     S->xch[T][s & 1][c][q][0] = R.y[0];
     S->xch[T][s & 1][c][q][1] = R.y[7];
     const float s_a0 = sb[291];
@@ -194,14 +178,16 @@ __device__ __forceinline__ void stage_input(Shared2* S, unsigned char* ks, const
     for (int i = 0; i < 4; ++i) {
         const float v0 = fminf(fmaxf(R.y[2 * i], -SplitFP16x2::INPUT_BOUND), SplitFP16x2::INPUT_BOUND);
         const float v1 = fminf(fmaxf(R.y[2 * i + 1], -SplitFP16x2::INPUT_BOUND), SplitFP16x2::INPUT_BOUND);
-        split2h(v0 * s_a0, v1 * s_a0, ph[i], pl[i]);
+        float s0, s1;
+        mul2s(s0, s1, v0, v1, s_a0);
+        split2h(s0, s1, ph[i], pl[i]);
     }
     const uint32_t a = tl + region(2 * T) + 64 + 4 * q;
     tmem_st4(a, ph);
     tmem_st4(a + 32, pl);
     wait_st();
     fence_before_sync();
-    mbar_arrive(&S->bar_a[T]);
+    warp_arrive(&S->bar_a[T]);
 }
 
 // ---- E1 / E2: hidden-layer epilogue, in place ---------------------------------------------------------------------------------
@@ -222,8 +208,9 @@ __device__ __forceinline__ void hidden_epilogue(Shared2* S, const float* sb, int
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const float4 bb = *reinterpret_cast<const float4*>(b + 16 * ch + 4 * i);
-            const float v0 = fmaf(__uint_as_float(r[16 * ch + 4 * i]), cl, bb.x), v1 = fmaf(__uint_as_float(r[16 * ch + 4 * i + 1]), cl, bb.y);
-            const float v2 = fmaf(__uint_as_float(r[16 * ch + 4 * i + 2]), cl, bb.z), v3 = fmaf(__uint_as_float(r[16 * ch + 4 * i + 3]), cl, bb.w);
+            float v0, v1, v2, v3;
+            fma2s(v0, v1, __uint_as_float(r[16 * ch + 4 * i]), __uint_as_float(r[16 * ch + 4 * i + 1]), cl, bb.x, bb.y);
+            fma2s(v2, v3, __uint_as_float(r[16 * ch + 4 * i + 2]), __uint_as_float(r[16 * ch + 4 * i + 3]), cl, bb.z, bb.w);
             if (FOLD) {                                              // relu folded into the conversions (tc::split2h_relu); not in the RECORD pass
                 split2h_relu(v0, v1, ph[2 * i], pl[2 * i]);
                 split2h_relu(v2, v3, ph[2 * i + 1], pl[2 * i + 1]);
@@ -237,7 +224,7 @@ __device__ __forceinline__ void hidden_epilogue(Shared2* S, const float* sb, int
     }
     wait_st();
     fence_before_sync();
-    mbar_arrive(&S->bar_a[T]);
+    warp_arrive(&S->bar_a[T]);
 }
 
 // ---- E3: output layer -> f(y) -> k_{s+2} ------------------------------------------------------------------------------------------
@@ -259,7 +246,11 @@ __device__ __forceinline__ void output_epilogue(Shared2* S, unsigned char* ks, c
         const float inv3 = sb[290];
         nn[0] = q ? fmaf(__uint_as_float(b0) + __uint_as_float(a0), inv3, b3[8 * q - 1]) : 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) nn[i + 1] = fmaf(__uint_as_float(rb[i]) + __uint_as_float(ra[i]), inv3, b3[8 * q + i]);
+        for (int i = 0; i < 8; i += 2) {
+            float t0, t1;
+            add2(t0, t1, __uint_as_float(rb[i]), __uint_as_float(rb[i + 1]), __uint_as_float(ra[i]), __uint_as_float(ra[i + 1]));
+            fma2s(nn[i + 1], nn[i + 2], t0, t1, inv3, b3[8 * q + i], b3[8 * q + i + 1]);
+        }
     }
     fence_before_sync();
     faces_to_f(R.y, ylo, yhi, nn, bot, top, kk, pref, q, R.k7);
@@ -283,11 +274,7 @@ __device__ __forceinline__ void step_error(Shared2* S, unsigned char* ks, const 
     float e[8], part = 0.f;
     combine<T>(tl, ks, q, c, R.k1, bt, 6, e);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const float ei = fmaf(NFC_BT7, R.k7[i], e[i]) * o.hs;
-        const float r = ei / (P.abstol + fmaxf(fabsf(R.u[i]), fabsf(R.y[i])) * P.reltol);
-        part = fmaf(r, r, part);
-    }
+    for (int i = 0; i < 8; ++i) part = err_term(part, e[i], R.k7[i], o.hs, R.u[i], R.y[i], P.abstol, P.reltol);
     S->part[T][c][q] = part;
     float m = fabsf(R.y[0]);
 #pragma unroll
@@ -307,18 +294,12 @@ __device__ __forceinline__ void step_control(Shared2* S, const SolveParams& P, i
         const float t = C.t[c], hs = C.hs[c];
         int status = C.status[c], nacc = C.nacc[c], nrej = C.nrej[c];
         const bool last = ctl & CTL_LAST;
-        const float ee = sqrtf(((S->part[T][c][0] + S->part[T][c][1]) + (S->part[T][c][2] + S->part[T][c][3])) * (1.f / NZ));
+        const float ee = fast_sqrt(((S->part[T][c][0] + S->part[T][c][1]) + (S->part[T][c][2] + S->part[T][c][3])) * (1.f / NZ));
         bool accept;
         float dtnew;
         if (!isfinite(ee)) { status = ST_NAN; accept = false; dtnew = hs; }
         else if (P.fixed_dt > 0.f) { accept = true; dtnew = P.fixed_dt; }
-        else {
-            const float q11 = __powf(ee, 0.14f);      // as in tc::solve_tc_kernel (solve and RECORD pass: one arithmetic)
-            float qq = q11 / __powf(C.qold[c], 0.08f);
-            qq = fmaxf(0.1f, fminf(5.0f, qq / 0.9f));
-            accept = ee <= 1.0f;
-            dtnew = accept ? hs / qq : hs / fminf(5.0f, q11 / 0.9f);
-        }
+        else pi_controller(ee, C.qold[c], hs, accept, dtnew);      // as in tc::solve_tc_kernel (solve and RECORD pass: one arithmetic)
         if (accept && (ctl & CTL_RANGE)) { status = ST_RANGE; accept = false; }     // accepted state outside the operand range of the split
         if (accept) {
             const float tn = last ? P.tf : t + hs;
@@ -397,9 +378,9 @@ __device__ __forceinline__ void save_point(const SolveParams& P, long long o2i, 
         for (int i = 0; i < 8; ++i) sse = fmaf(r[i], r[i], sse);
         lsum += (double)sse;
     } else {
-        float* o2 = P.Tout + o2i;
-        *reinterpret_cast<float4*>(o2) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(o2 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+        float* o2 = P.Tout + o2i;          // streaming stores (see tc::solve_tc_kernel)
+        __stcs(reinterpret_cast<float4*>(o2), make_float4(v[0], v[1], v[2], v[3]));
+        __stcs(reinterpret_cast<float4*>(o2 + 4), make_float4(v[4], v[5], v[6], v[7]));
     }
 }
 
@@ -411,26 +392,20 @@ __device__ __forceinline__ void step_finish(Shared2* S, unsigned char* ks, const
         const float r2[6] = {-2.763706197274826f, 0.13169999999999998f, 3.9302962368947516f, -12.411077166933676f, 37.50931341651104f, -27.896526289197286f};
         const float r3[6] = {2.9132554618219126f, -0.2234f, -5.941033872131505f, 30.33818863028232f, -88.1789048947664f, 65.09189467479366f};
         const float r4[6] = {-1.0530884977290216f, 0.1017f, 2.490627285651253f, -16.548102889244902f, 47.37952196281928f, -34.87065786149661f};
-        // every stage vector is loaded once for the three combinations (each in the operation order of tc::combine6)
+        // every stage vector is loaded once for the three combinations (each in the operation order of tc::dense_partial)
         float kb[8], kc[8];
         tmem_ld8f(kt_addr<T>(tl, 2, q), kb);
         tmem_ld8f(kt_addr<T>(tl, 3, q), kc);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { c2[i] = r2[0] * R.k1[i]; c3[i] = r3[0] * R.k1[i]; c4[i] = r4[0] * R.k1[i]; }
+        scal8(c2, r2[0], R.k1); scal8(c3, r3[0], R.k1); scal8(c4, r4[0], R.k1);
         wait_ld();
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            c2[i] = fmaf(r2[1], kb[i], c2[i]); c3[i] = fmaf(r3[1], kb[i], c3[i]); c4[i] = fmaf(r4[1], kb[i], c4[i]);
-            c2[i] = fmaf(r2[2], kc[i], c2[i]); c3[i] = fmaf(r3[2], kc[i], c3[i]); c4[i] = fmaf(r4[2], kc[i], c4[i]);
-        }
+        axpy8(c2, r2[1], kb); axpy8(c3, r3[1], kb); axpy8(c4, r4[1], kb);
+        axpy8(c2, r2[2], kc); axpy8(c3, r3[2], kc); axpy8(c4, r4[2], kc);
 #pragma unroll
         for (int j = 4; j <= 6; ++j) {
             ks_load<T>(ks, j, q, c, kb);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { c2[i] = fmaf(r2[j - 1], kb[i], c2[i]); c3[i] = fmaf(r3[j - 1], kb[i], c3[i]); c4[i] = fmaf(r4[j - 1], kb[i], c4[i]); }
+            axpy8(c2, r2[j - 1], kb); axpy8(c3, r3[j - 1], kb); axpy8(c4, r4[j - 1], kb);
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { c2[i] = fmaf(1.5f, R.k7[i], c2[i]); c3[i] = fmaf(-4.0f, R.k7[i], c3[i]); c4[i] = fmaf(2.5f, R.k7[i], c4[i]); }
+        dense_k7(R.k7, c2, c3, c4);
     }
     const int ctl = S->cs[T].ctl[c];
     if (o.col >= 0 && (ctl & CTL_ACCEPT)) {
@@ -452,10 +427,9 @@ __device__ __forceinline__ void step_finish(Shared2* S, unsigned char* ks, const
         while (si < P.n_save) {
             const float ts = P.saveat[si];
             if (ts > tn) break;
-            const float th = fminf((ts - o.t) / o.hs, 1.0f);
+            const float th = fminf(fast_div(ts - o.t, o.hs), 1.0f);
             float v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = fmaf(o.hs, th * fmaf(th, fmaf(th, fmaf(th, c4[i], c3[i]), c2[i]), R.k1[i]), R.u[i]);
+            dense_eval(v, o.hs, th, R.u, R.k1, c2, c3, c4);
             save_point<RECORD>(P, ((long long)o.col * P.n_save + si) * NZ + 8 * q, v, lsum);
             ++si;
         }
@@ -492,7 +466,7 @@ __global__ void __launch_bounds__(NT2, 1) solve_tc2_kernel(const unsigned char* 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         mbar_init(&S->bar_w, 1);
-        mbar_init(&S->bar_a[0], NCT); mbar_init(&S->bar_a[1], NCT);
+        mbar_init(&S->bar_a[0], NCW); mbar_init(&S->bar_a[1], NCW);
         mbar_init(&S->bar_d[0], 1); mbar_init(&S->bar_d[1], 1);
         S->stop = 0; S->qempty = 0; S->ydead = 0; S->anyT[0] = 0; S->anyT[1] = 0;
     }
@@ -623,7 +597,7 @@ __global__ void __launch_bounds__(NT2, 1) solve_tc2_kernel(const unsigned char* 
         cta_bar();
         if (threadIdx.x == 0) S->stop = 1;
         cta_bar();
-        mbar_arrive(&S->bar_a[0]);
+        warp_arrive(&S->bar_a[0]);
     }
     fence_before_sync();
     __syncthreads();
