@@ -312,7 +312,7 @@ def train_neural_differential_equation(NN, NDEType, nde_params, algorithm, datas
         history.append(dict(epoch=epoch, mean_loss=res["loss"], runtime=runtime))
         if callback is not None:
             callback(epoch, theta, res["loss"])
-        _inscribe_history(history_filepath, epoch, theta, res["loss"], runtime)
+        _inscribe_history(history_filepath, epoch, theta, res["loss"], runtime, NN)
         t0 = time.time()
         theta = opt.update(theta, res["grad"]).astype(np.float32)
     NN_final = reconstruct(best[1])
@@ -320,19 +320,11 @@ def train_neural_differential_equation(NN, NDEType, nde_params, algorithm, datas
     return NN_final
 
 
-def _inscribe_history(path, epoch, theta, loss, runtime):
-    """inscribe_history (src/training.jl:3-12) -- keys neural_network/<e>, mean_loss/<e>, runtime/<e>; stored as .npz
-    because JLD2 is a Julia format."""
-    if path is None:
-        return
-    import os
-    if not path.endswith(".npz"):
-        path += ".npz"
-    prev = dict(np.load(path)) if os.path.exists(path) else {}
-    prev[f"neural_network/{epoch}"] = theta
-    prev[f"mean_loss/{epoch}"] = np.float64(loss)
-    prev[f"runtime/{epoch}"] = np.float64(runtime)
-    np.savez(path, **prev)
+def _inscribe_history(path, epoch, theta, loss, runtime, NN=None):
+    """inscribe_history (src/training.jl:3-12) -- keys neural_network/<e>, mean_loss/<e>, runtime/<e>; the container is .npz and
+    `julia/convert_formats.jl` turns it into the reference's JLD2 file (formats.py)."""
+    from . import formats
+    formats.inscribe_history(path, epoch, theta, loss, runtime, NN)
 
 
 # ------------------------------------------------------------------------------------------------

@@ -104,3 +104,36 @@ def test_adam_matches_flux_update_rule(nfc):
     th1 = opt.update(th, g)
     # first step of ADAM moves every non-zero-gradient coordinate by ~eta
     np.testing.assert_allclose(th1, th - 1e-3 * np.sign(g) * (np.abs(g) / (np.abs(g) + 1e-8)), rtol=1e-6)
+
+
+def test_on_disk_formats_round_trip(tmp_path):
+    """the training driver's files carry the reference's keys (src/training.jl:3-12, train_free_convection_nde.jl:259-266,
+    :376-390) as plain arrays in .npz; julia/convert_formats.jl rebuilds the JLD2 files from them."""
+    import nfc_b200
+    F, syn = nfc_b200.formats, nfc_b200.synthetic
+    NN = nfc_b200.named_chain("conv-2", seed=3)
+    theta, _ = nfc_b200.destructure(NN)
+    Ts, wTs = syn.Scaling(19.6, 0.5), syn.Scaling(0.0, 1e-5)
+    hist = str(tmp_path / "history")
+    for e in (1, 2, 3):
+        F.inscribe_history(hist, e, theta * e, 0.5 / e, 0.1 * e, NN)
+    h = F.read_history(hist)
+    assert list(h["epochs"]) == [1, 2, 3] and np.allclose(h["mean_loss"], [0.5, 0.25, 0.5 / 3]) and np.array_equal(h["neural_network"][2], theta * 3)
+    assert list(h["arch"]) == [2, 31, 128, 128, 31]
+    assert np.array_equal(nfc_b200.load_history(hist), h["neural_network"])           # what compute_nde_solution_history reads
+    raw = dict(np.load(hist + ".npz"))
+    assert {k.split("/")[0] for k in raw} == set(F.HISTORY_KEYS) | {"arch"}
+    net = str(tmp_path / "neural_network_trained_on_timeseries")
+    F.save_neural_network(net, NN, Ts, wTs)
+    assert set(k.split("/")[0] for k in np.load(net + ".npz")) == set(F.NETWORK_FILE_KEYS)
+    NN2, Ts2, wTs2, Nz = F.load_neural_network(net)
+    assert Nz == 32 and (Ts2.mu, Ts2.sigma, wTs2.sigma) == (19.6, 0.5, 1e-5) and np.array_equal(nfc_b200.destructure(NN2)[0], theta)
+    assert NN2.conv_width == 2 and [s[:2] for s in NN2.dense_spec] == [s[:2] for s in NN.dense_spec]
+    sol = str(tmp_path / "solutions_and_history")
+    T = np.arange(32 * 5, dtype=np.float64).reshape(32, 5)
+    F.save_solutions(sol, NN, Ts, wTs, {"true": {1: {"T": T, "wT": T[:, :4]}}, "nde": {1: {"T": T + 1}, 2: {"T": T + 2}}},
+                     solution_history={1: np.zeros((3, 32, 5))}, solution_loss_history={1: np.ones((3, 5))})
+    s = F.load_solutions(sol)
+    assert np.array_equal(s["nde"][2]["T"], T + 2) and np.array_equal(s["true"][1]["wT"], T[:, :4]) and s["solution_loss_history"][1].shape == (3, 5)
+    with pytest.raises(ValueError):
+        F.save_solutions(sol, NN, Ts, wTs, {"les": {}})
