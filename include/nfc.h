@@ -145,6 +145,11 @@ int32_t nfc_comm_destroy(nfc_handle* h);
  * Set the weights to zero for the pure convective-adjustment baseline.  Host pointers; synchronous. */
 int32_t nfc_embedded_solve(nfc_handle* h, const float* T0, const float* heat_flux, const float* scal, float Lz, float dt, float K,
                            float bottom_gradient, int32_t n_steps, int32_t save_every, float* Tout, int64_t B);
+/* second output of the embedded path, diagnose_wT_NN (src/oceananigans_nn.jl:200-218): for saved PHYSICAL profiles Tsol [B][n_out][Nz]
+ * (what nfc_embedded_solve returned) wT [B][n_out][Nz+1] = [0; wT_scaling^-1(NN(T_scaling(T))); heat_flux] - kappa dT/dz on the interior
+ * faces, kappa = K where dT/dz < 0 (K as passed to nfc_embedded_solve). */
+int32_t nfc_embedded_diagnose_flux(nfc_handle* h, const float* Tsol, const float* heat_flux, const float* scal, float Lz, float K,
+                                   int32_t n_out, float* wT, int64_t B);
 /* SURVEY row f3 -- compute_nde_solution_history (src/testing.jl:42-79): every saved epoch's Chain x every simulation, which the
  * reference runs as epochs x simulations serial solve_nde calls.  Here it is one launch over an ensemble: member e (one epoch's
  * Flux.destructure vector theta_members[e][n_params], same Chain architecture as the handle) integrates the S columns

@@ -253,7 +253,8 @@ end
 """
 oceananigans_convective_adjustment_with_neural_network (src/oceananigans_nn.jl:158-282) for B columns at once: explicit neural-network flux
 step + implicit convective adjustment per fixed step `Δt`.  `T₀` is Nz x B (physical temperatures), `heat_flux` the B surface temperature
-fluxes; `K` is non-dimensionalised as the reference does (:195).  Returns Nz x (n_steps ÷ save_every + 1) x B in physical units.
+fluxes; `K` is non-dimensionalised as the reference does (:195).  Returns the reference's `(T, wT)`: Nz x n_out x B and (Nz+1) x n_out x B
+(n_out = n_steps ÷ save_every + 1) in physical units.
 """
 function oceananigans_convective_adjustment_with_neural_network(nde::NDEHandle, NN, T₀::Matrix{Float32}, heat_flux::Vector{Float32},
                                                                 T_scaling, wT_scaling; Lz, stop_time, Δt=600.0, K=10.0, ∂T∂z_deep=0.0, save_every=1)
@@ -267,7 +268,13 @@ function oceananigans_convective_adjustment_with_neural_network(nde::NDEHandle, 
                (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Float32, Float32, Float32, Float32, Int32, Int32, Ptr{Float32}, Int64),
                nde.ptr, T₀, heat_flux, scal, Lz, Δt, Knd, ∂T∂z_deep, n_steps, save_every, out, B)
     check(nde.ptr, rc, "nfc_embedded_solve")
-    return out
+    # second output of the reference, diagnose_wT_NN (src/oceananigans_nn.jl:200-218): (Nz+1) x n_out x B
+    wT = Array{Float32}(undef, nde.Nz + 1, size(out, 2), B)
+    rc = ccall((:nfc_embedded_diagnose_flux, LIB), Int32,
+               (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Float32, Float32, Int32, Ptr{Float32}, Int64),
+               nde.ptr, out, heat_flux, scal, Lz, Knd, size(out, 2), wT, B)
+    check(nde.ptr, rc, "nfc_embedded_diagnose_flux")
+    return (T=out, wT=wT)
 end
 
 end # module

@@ -14,7 +14,7 @@ NFC_MAX_LAYERS = 8
 EXPORTS = ["nfc_create", "nfc_destroy", "nfc_last_error", "nfc_n_params", "nfc_set_weights", "nfc_set_saveat",
            "nfc_get_counters", "nfc_rhs", "nfc_solve", "nfc_diagnose_flux", "nfc_loss_grad", "nfc_rhs_dev",
            "nfc_solve_dev", "nfc_loss_grad_dev", "nfc_sync", "nfc_measure_fp32_peak", "nfc_get_adjoint_steps", "nfc_embedded_solve",
-           "nfc_solve_ensemble", "nfc_comm_unique_id", "nfc_comm_init", "nfc_comm_destroy", "nfc_get_tape", "nfc_set_option"]
+           "nfc_embedded_diagnose_flux", "nfc_solve_ensemble", "nfc_comm_unique_id", "nfc_comm_init", "nfc_comm_destroy", "nfc_get_tape", "nfc_set_option"]
 
 
 class NfcConfig(C.Structure):
@@ -64,6 +64,8 @@ def load():
     lib.nfc_loss_grad_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int64, vp]
     lib.nfc_sync.argtypes = [vp]
     lib.nfc_embedded_solve.argtypes = [vp, fp, fp, fp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_int32, fp, C.c_int64]
+    lib.nfc_embedded_diagnose_flux.argtypes = [vp, fp, fp, fp, C.c_float, C.c_float, C.c_int32, fp, C.c_int64]
+    lib.nfc_embedded_diagnose_flux.restype = C.c_int32
     lib.nfc_get_adjoint_steps.argtypes = [vp, ip, C.c_int64]
     lib.nfc_measure_fp32_peak.argtypes = [C.c_int32, C.c_float, dp]
     lib.nfc_get_tape.argtypes = [vp, C.c_int64, fp, C.c_int32, ip]
@@ -276,6 +278,15 @@ class Handle:
 
     def sync(self):
         self._check(self.lib.nfc_sync(self.h), "nfc_sync")
+
+    def embedded_diagnose_flux(self, Tsol, heat_flux, scal, Lz, K):
+        """nfc_embedded_diagnose_flux: wT [B][n_out][Nz+1] (physical units) of saved physical profiles Tsol [B][n_out][Nz]."""
+        Tsol, heat_flux, scal = _f32(Tsol), _f32(heat_flux), _f32(scal)
+        B, n_out = Tsol.shape[0], Tsol.shape[1]
+        wT = np.empty((B, n_out, self.Nz + 1), dtype=np.float32)
+        self._check(self.lib.nfc_embedded_diagnose_flux(self.h, _fp(Tsol), _fp(heat_flux), _fp(scal), Lz, K, n_out,
+                                                        _fp(wT), B), "nfc_embedded_diagnose_flux")
+        return wT
 
     def set_option(self, name, value):
         """nfc_set_option: kernel selection / scratch budgets (include/nfc.h lists the names)."""

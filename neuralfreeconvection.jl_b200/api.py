@@ -17,6 +17,8 @@ from __future__ import annotations
 import time
 from dataclasses import dataclass, field
 
+from typing import NamedTuple
+
 import numpy as np
 
 from . import _binding as B_
@@ -390,6 +392,11 @@ def oceananigans_convective_adjustment(ds, dt=600.0, K=10.0, device=0, save_ever
     return _embedded(ds, NN, ident, ident, dt, K, device, save_every)
 
 
+class EmbeddedSolution(NamedTuple):
+    T: np.ndarray
+    wT: np.ndarray
+
+
 def _embedded(ds, NN, T_scaling, wT_scaling, dt, K, device, save_every):
     Nz, Nt = ds.T.shape
     Lz, stop_time = abs(float(ds.zf[0])), float(ds.times[-1])
@@ -398,6 +405,8 @@ def _embedded(ds, NN, T_scaling, wT_scaling, dt, K, device, save_every):
     theta, _ = destructure(NN)
     h.set_weights(theta)
     scal = [T_scaling.mu, T_scaling.sigma, wT_scaling.mu, wT_scaling.sigma]
-    out = h.embedded_solve(ds.T[None, :, 0], [ds.metadata["temperature_flux"]], scal, Lz, dt, K,
+    Q = [ds.metadata["temperature_flux"]]
+    out = h.embedded_solve(ds.T[None, :, 0], Q, scal, Lz, dt, K,
                            float(ds.metadata.get("dθdz_deep", ds.metadata.get("dthetadz_deep", 0.0))), n_steps, save_every)
-    return out[0].T
+    wT = h.embedded_diagnose_flux(out, Q, scal, Lz, K)               # diagnose_wT_NN, src/oceananigans_nn.jl:200-218
+    return EmbeddedSolution(T=out[0].T, wT=wT[0].T)                   # the reference's (T=T_nn, wT=wT_nn): Nz x Nt and (Nz+1) x Nt

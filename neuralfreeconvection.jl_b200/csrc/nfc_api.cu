@@ -128,13 +128,14 @@ int do_embedded(nfc_handle* h, EmbeddedParams& P, cudaStream_t st) {
 }
 
 template <class N>
-int do_diagnose(nfc_handle* h, const float* Tsol, const float* colp, float* wT, int64_t B, cudaStream_t st) {
+int do_diagnose(nfc_handle* h, const float* Tsol, const float* colp, float* wT, int64_t B, cudaStream_t st, int n_prof = 0, int use_kca = -1) {
     constexpr bool WS = Launch<N>::WS;
     constexpr int NW = Launch<N>::NW;
-    const long long groups = (B * h->cfg.n_save + CPW - 1) / CPW;
+    if (n_prof <= 0) n_prof = h->cfg.n_save;                 // profiles per column (nfc_embedded_diagnose_flux: the saved steps of that call)
+    if (use_kca < 0) use_kca = h->cfg.nde_type == NFC_NDE_CONVECTIVE_ADJUSTMENT;
+    const long long groups = (B * n_prof + CPW - 1) / CPW;
     const int grid = (int)std::min<long long>(h->num_sms, (groups + NW - 1) / NW);
-    diagnose_flux_kernel<N, WS><<<grid, NW * 32, smem_bytes<N>(NW), st>>>(h->d_wpack.p, Tsol, colp, wT, B, h->cfg.n_save,
-                                                                     h->cfg.nde_type == NFC_NDE_CONVECTIVE_ADJUSTMENT);
+    diagnose_flux_kernel<N, WS><<<grid, NW * 32, smem_bytes<N>(NW), st>>>(h->d_wpack.p, Tsol, colp, wT, B, n_prof, use_kca);
     NFC_CUDA(h, cudaGetLastError());
     h->last_launches += 1;
     return 0;
@@ -1058,6 +1059,38 @@ int32_t nfc_embedded_solve(nfc_handle* h, const float* T0, const float* heat_flu
     h->last_columns = B;
     NFC_CUDA(h, cudaMemcpyAsync(Tout, h->s_out.p, sizeof(float) * nout, cudaMemcpyDeviceToHost, h->stream));
     NFC_CUDA(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+// The reference's second output of the embedded path, diagnose_wT_NN (src/oceananigans_nn.jl:200-218), for saved profiles in PHYSICAL units:
+// wT = [0; wT_scaling^-1(NN(T_scaling(T))); heat_flux] - kappa dT/dz on the interior faces, kappa = K where dT/dz < 0.  Evaluated by the flux
+// diagnosis kernel of nfc_diagnose_flux in scaled units (boundary rows and the diffusivity re-expressed in them), un-scaled on the host.
+int32_t nfc_embedded_diagnose_flux(nfc_handle* h, const float* Tsol, const float* heat_flux, const float* scal, float Lz, float K, int32_t n_out,
+                                   float* wT, int64_t B) {
+    if (int rc = check_ready(h, B)) return rc;
+    if (B == 0) return 0;
+    if (!Tsol || !heat_flux || !scal || !wT) return fail(h, -1, "null argument");
+    if (n_out < 1 || !(Lz > 0.f) || !(scal[1] > 0.f) || !(scal[3] > 0.f)) return fail(h, -2, "bad profile count / scaling arguments");
+    const double muT = scal[0], sT = scal[1], muW = scal[2], sW = scal[3];
+    const size_t nin = (size_t)B * n_out * NZ, nout = (size_t)B * n_out * (NZ + 1);
+    std::vector<float> ts(nin), cp((size_t)B * 3), w(nout);
+    for (size_t i = 0; i < nin; ++i) ts[i] = (float)(((double)Tsol[i] - muT) / sT);
+    for (int64_t b = 0; b < B; ++b) {
+        cp[b * 3 + 0] = (float)((0.0 - muW) / sW);                         // bottom face: zero flux
+        cp[b * 3 + 1] = (float)(((double)heat_flux[b] - muW) / sW);        // top face: the surface temperature flux
+        cp[b * 3 + 2] = (float)((double)K * sT / ((double)Lz * sW));       // K dT/dz in scaled units: K sigma_T / (Lz sigma_wT) * Nz dT_scaled
+    }
+    NFC_CUDA(h, h->s_true.ensure(nin));
+    NFC_CUDA(h, h->s_colp.ensure((size_t)B * 3));
+    NFC_CUDA(h, h->s_out.ensure(nout));
+    NFC_CUDA(h, cudaMemcpyAsync(h->s_true.p, ts.data(), sizeof(float) * nin, cudaMemcpyHostToDevice, h->stream));
+    NFC_CUDA(h, cudaMemcpyAsync(h->s_colp.p, cp.data(), sizeof(float) * B * 3, cudaMemcpyHostToDevice, h->stream));
+    h->last_launches = 0;
+    int rc = [&]() -> int { NFC_DISPATCH(h, do_diagnose, h, h->s_true.p, h->s_colp.p, h->s_out.p, B, h->stream, n_out, 1); }();
+    if (rc) return rc;
+    NFC_CUDA(h, cudaMemcpyAsync(w.data(), h->s_out.p, sizeof(float) * nout, cudaMemcpyDeviceToHost, h->stream));
+    NFC_CUDA(h, cudaStreamSynchronize(h->stream));
+    for (size_t i = 0; i < nout; ++i) wT[i] = (float)(sW * (double)w[i] + muW);
     return 0;
 }
 

@@ -93,14 +93,28 @@ def test_gpu_embedded_api_mirror(nfc, gpu_ok):
     zf = -256.0 + np.arange(33) * 8.0
     ds = nfc.ColumnDataset(T=np.repeat(Ts.inv(d["T0"][0])[:, None], 1153, axis=1), wT=np.zeros((33, 1153)), zc=syn.cell_centres(), zf=zf,
                            times=np.arange(1153) * 600.0, metadata={"temperature_flux": 2.5e-5, "dθdz_deep": 1e-3})
-    T = nfc.oceananigans_convective_adjustment(ds, dt=600.0, K=10.0)
+    sol = nfc.oceananigans_convective_adjustment(ds, dt=600.0, K=10.0)
+    T = sol.T
     assert T.shape == (32, 1153) and np.isfinite(T).all()
     assert T[-1, -1] < T[-1, 0] and np.diff(T[:, -1]).min() > -1e-3      # surface cooled, column adjusted to (near) neutral
+    # the reference's second output (diagnose_wT_NN): zero network => wT = [0; 0...; Q] - min(0, K dT/dz) on the interior faces
+    assert sol.wT.shape == (33, 1153)
+    dTdz = np.diff(T.astype(np.float64), axis=0) / 8.0
+    ref = np.zeros((33, 1153)); ref[-1] = 2.5e-5; ref[1:-1] -= np.minimum(0.0, 10.0 * dTdz)
+    assert np.abs(sol.wT - ref).max() <= 1e-5 * max(np.abs(ref).max(), 2.5e-5) + 1e-9
     NN = nfc.named_chain("dense-default", seed=0)
     for p in NN.params():
         p *= 1e-5
-    T2 = nfc.oceananigans_convective_adjustment_with_neural_network(ds, NN, Ts, wTs, save_every=9)
-    assert T2.shape == (32, 129) and np.isfinite(T2).all()
+    sol2 = nfc.oceananigans_convective_adjustment_with_neural_network(ds, NN, Ts, wTs, save_every=9)
+    assert sol2.T.shape == (32, 129) and np.isfinite(sol2.T).all() and sol2.wT.shape == (33, 129) and np.isfinite(sol2.wT).all()
+    # against the oracle's flux (scaled units) for a few saved profiles
+    cw, layers = O.chain_spec()
+    theta, _ = nfc.destructure(NN)
+    Knd = wTs.sigma / Ts.sigma * 691200.0 / 256.0 * 10.0
+    Tsc = Ts(sol2.T[:, ::32].T)
+    colp = np.float64([[(0.0 - wTs.mu) / wTs.sigma, (2.5e-5 - wTs.mu) / wTs.sigma, Knd * Ts.sigma / (256.0 * wTs.sigma)]] * Tsc.shape[0])
+    wref = wTs.inv(O.total_flux(Tsc, theta, cw, layers, colp, np.float64))
+    assert np.abs(sol2.wT[:, ::32].T - wref).max() <= 2e-4 * np.abs(wref).max()
 
 
 @pytest.mark.gpu

@@ -45,7 +45,8 @@ for l in lines[start + 1:]:
             chain, pending = pending, []
         insts.append((int(m.group(1), 16), m.group(2).strip(), chain))
 
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+# REPORT may also be the text of `ncu -i X.ncu-rep --page source --csv` (exported on the GPU box: reports are ~28 MB each)
+txt = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
 hi_ = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
 hdr = rows[hi_]

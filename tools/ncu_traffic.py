@@ -3,7 +3,7 @@ usage: python tools/ncu_traffic.py REPORT.ncu-rep OUT.json [label]      (reads w
 import csv, io, json, subprocess, sys
 rep, out = sys.argv[1], sys.argv[2]
 label = sys.argv[3] if len(sys.argv) > 3 else rep
-txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+txt = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
 hdr, units, r = rows[0], rows[1], rows[2]
 d = {h: (v, u) for h, v, u in zip(hdr, r, units)}
