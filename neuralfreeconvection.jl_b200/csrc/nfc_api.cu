@@ -44,6 +44,19 @@ Arch classify(const nfc_config& c) {
     return ARCH_NONE;
 }
 
+// Chains with a tensor-core forward path (nfc_tc.cuh): the default Chain (every kernel), conv-2 / conv-4 / deeper (nfc_rhs and the Tsit5
+// forward solve, FP16x2 split; their other entry points and the wider Chain run the FP32 SIMT kernels)
+#define NFC_COMMA ,
+inline bool tc_forward_arch(Arch a) { return a == ARCH_DEFAULT || a == ARCH_CONV2 || a == ARCH_CONV4 || a == ARCH_DEEPER; }
+#define NFC_TC_ARCH_DISPATCH(h, EXPR_DEFAULT, EXPR_CONV2, EXPR_CONV4, EXPR_DEEPER) \
+    switch ((h)->arch) {                                                          \
+        case ARCH_DEFAULT: EXPR_DEFAULT; break;                                   \
+        case ARCH_CONV2: EXPR_CONV2; break;                                       \
+        case ARCH_CONV4: EXPR_CONV4; break;                                       \
+        case ARCH_DEEPER: EXPR_DEEPER; break;                                     \
+        default: break;                                                           \
+    }
+
 #define NFC_DISPATCH(h, FN, ...)                                      \
     switch ((h)->arch) {                                              \
         case ARCH_DEFAULT: return FN<NetDefault>(__VA_ARGS__);        \
@@ -79,11 +92,14 @@ inline float prefactor(const float* glob) { return glob[1] / glob[0] * glob[3] /
 
 template <class N>
 int do_rhs(nfc_handle* h, const float* T, const float* colp, float pref, float* out, int64_t B, cudaStream_t st) {
-    if (h->use_tc && h->arch == ARCH_DEFAULT) {
+    if (h->use_tc && tc_forward_arch(h->arch)) {
         const long long ntiles = (B + tc::TILE - 1) / tc::TILE;
         const int grid = (int)std::min<long long>(h->num_sms, ntiles);
-        if (h->tc_fp16) tc::rhs_tc_kernel<tc::SplitFP16x2><<<grid, tc::NTHREADS, tc::IMG16_BYTES, st>>>(h->d_wimg.p, T, colp, out, B, pref, h->cfg.nde_type == NFC_NDE_CONVECTIVE_ADJUSTMENT);
-        else tc::rhs_tc_kernel<tc::SplitBF16x3><<<grid, tc::NTHREADS, tc::IMG_BYTES, st>>>(h->d_wimg.p, T, colp, out, B, pref, h->cfg.nde_type == NFC_NDE_CONVECTIVE_ADJUSTMENT);
+        const int kca = h->cfg.nde_type == NFC_NDE_CONVECTIVE_ADJUSTMENT;
+#define NFC_RHS_TC(SP) tc::rhs_tc_kernel<SP><<<grid, tc::NTHREADS, SP::IMG, st>>>(h->d_wimg.p, T, colp, out, B, pref, kca)
+        if (!h->tc_fp16) NFC_RHS_TC(tc::SplitBF16x3);
+        else NFC_TC_ARCH_DISPATCH(h, NFC_RHS_TC(tc::SplitFP16x2), NFC_RHS_TC(tc::SplitFP16x2T<2 NFC_COMMA 2>), NFC_RHS_TC(tc::SplitFP16x2T<2 NFC_COMMA 4>), NFC_RHS_TC(tc::SplitFP16x2T<3 NFC_COMMA 0>))
+#undef NFC_RHS_TC
         NFC_CUDA(h, cudaGetLastError());
         h->last_launches += 1;
         return 0;
@@ -203,7 +219,13 @@ int launch_solve(nfc_handle* h, SolveParams& P, cudaStream_t st, bool reset_coun
                                                                     P.reltol, P.abstol, P.tf, P.fixed_dt);
     NFC_CUDA(h, cudaGetLastError());
     // tensor-core kernels: the forward solve always (default Chain), the RECORD pass of loss_grad with the FP16x2 split (NFC_TC_RECORD=0: SIMT)
-    if (h->use_tc && h->arch == ARCH_DEFAULT && (!RECORD || (h->tc_fp16 && h->tc_record))) {
+    if (h->use_tc && h->arch != ARCH_DEFAULT && tc_forward_arch(h->arch) && !RECORD && h->tc_fp16) {
+        // conv-2 / conv-4 / deeper Chain: one-tile tensor-core forward solve (the RECORD pass of loss_grad stays on the FP32 SIMT kernel)
+        const int gridt = (int)std::min<long long>(h->num_sms, (B + tc::TILE - 1) / tc::TILE);
+#define NFC_SOLVE_TC(SP) tc::solve_tc_kernel<SP, false><<<gridt, tc::NTHREADS, SP::IMG, st>>>(h->d_wimg.p, P)
+        NFC_TC_ARCH_DISPATCH(h, (void)0, NFC_SOLVE_TC(tc::SplitFP16x2T<2 NFC_COMMA 2>), NFC_SOLVE_TC(tc::SplitFP16x2T<2 NFC_COMMA 4>), NFC_SOLVE_TC(tc::SplitFP16x2T<3 NFC_COMMA 0>))
+#undef NFC_SOLVE_TC
+    } else if (h->use_tc && h->arch == ARCH_DEFAULT && (!RECORD || (h->tc_fp16 && h->tc_record))) {
         const int gridt = (int)std::min<long long>(h->num_sms, (B + tc::TILE - 1) / tc::TILE);
 #ifdef NFC_DEBUG_TIMERS          // debug build only: phase timers of CTA 0 (clock64) and the timing-experiment knob; the release kernels ignore both
         if (!RECORD) {
@@ -419,8 +441,8 @@ int switch_split(nfc_handle* h, bool fp16) {
     if (fp16) {
         tc::Fp16Scales sc;
         memcpy(&sc, h->fp16_scales, sizeof sc);
-        const int n = 128 * 32 + 128 * 128 + 32 * 128 + 296;
-        tc::pack_weights_tc16_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_theta.p, h->d_wimg.p, sc);
+        const int n = 128 * 32 + 128 * 128 + 32 * 128 + tc::TcDefault::CB + 16;
+        tc::pack_weights_tc16_kernel<2, 0><<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_theta.p, h->d_wimg.p, sc);
     } else {
         const int n = 128 * 32 + 128 * 128 + 32 * 128 + 288;
         tc::pack_weights_tc_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_theta.p, h->d_wimg.p);
@@ -629,6 +651,19 @@ int32_t nfc_create(const nfc_config* cfg, nfc_handle** out) {
         const char* e = getenv("NFC_TC");          // tensor-core forward path is the default for this Chain; NFC_TC=0 selects the SIMT kernels
         h->use_tc = !(e && atoi(e) == 0);
     }
+    if (h->arch != ARCH_DEFAULT && tc_forward_arch(h->arch)) {       // conv-2 / conv-4 / deeper: tensor-core nfc_rhs and forward solve (FP16x2)
+        if (h->d_wimg.ensure(tc::IMG16_MAX)) { h->err = "cudaMalloc failed"; return bail(-10); }
+        bool ok = true;
+#define NFC_TC_ATTR(SP) ok = ok && cudaFuncSetAttribute(tc::rhs_tc_kernel<SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP::IMG) == cudaSuccess && \
+                          cudaFuncSetAttribute(tc::solve_tc_kernel<SP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP::IMG) == cudaSuccess
+        NFC_TC_ARCH_DISPATCH(h, (void)0, NFC_TC_ATTR(tc::SplitFP16x2T<2 NFC_COMMA 2>), NFC_TC_ATTR(tc::SplitFP16x2T<2 NFC_COMMA 4>), NFC_TC_ATTR(tc::SplitFP16x2T<3 NFC_COMMA 0>))
+#undef NFC_TC_ATTR
+        if (!ok) { h->err = "cudaFuncSetAttribute(tc) failed"; return bail(-10); }
+        h->tc_fp16 = true;
+        if (const char* e2 = getenv("NFC_SCHED")) h->use_sched = atoi(e2) != 0;
+        const char* e = getenv("NFC_TC");
+        h->use_tc = !(e && atoi(e) == 0);
+    }
     if (h->d_theta.ensure(h->n_params) || h->d_wpack.ensure(h->n_packed) || h->d_saveat.ensure(h->saveat.size()) ||
         h->d_counters.ensure(CTR_COUNT)) { h->err = "cudaMalloc failed"; return bail(-10); }
     if (cudaMemcpy(h->d_saveat.p, h->saveat.data(), sizeof(float) * h->saveat.size(), cudaMemcpyHostToDevice) != cudaSuccess) { h->err = "saveat upload failed"; return bail(-10); }
@@ -665,9 +700,12 @@ int32_t nfc_set_weights(nfc_handle* h, const float* theta, int64_t n) {
     NFC_CUDA(h, cudaMemcpyAsync(h->d_theta.p, theta, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
     int rc = [&]() -> int { NFC_DISPATCH(h, do_pack, h); }();
     if (rc) return rc;
-    if (h->arch == ARCH_DEFAULT) {
+    if (tc_forward_arch(h->arch)) {
         // FP16x2 split: exact power-of-two scales from the weights' max / row-sum norms and the input bound |T_scaled| <= 128
-        using N0 = NetDefault;
+        const int NH = h->arch == ARCH_DEEPER ? 3 : 2, CW = h->arch == ARCH_CONV2 ? 2 : (h->arch == ARCH_CONV4 ? 4 : 0);
+        const int IN0 = NZ - (CW ? CW - 1 : 0);
+        const int T_W0 = CW ? CW + 1 : 0, T_B0 = T_W0 + IN0 * 128, T_HID = T_B0 + 128, HID_STRIDE = 128 * 128 + 128;
+        const int T_WL = T_HID + (NH - 1) * HID_STRIDE, T_BL = T_WL + 128 * 31;                 // Net<128, NH, CW> (nfc_device.cuh)
         auto p2 = [](double bound) { return bound > 0 ? (float)std::exp2(std::floor(std::log2(16384.0 / bound))) : 1.0f; };
         // rowsum: max over output neurons of sum_k |W[n][k]| (bounds the forward activations); colsum: max over inputs of sum_n |W[n][k]|
         // (bounds the back-propagated vectors of the tensor-core backward kernel, nfc_adjoint_tc.cuh)
@@ -681,26 +719,36 @@ int32_t nfc_set_weights(nfc_handle* h, const float* theta, int64_t n) {
             }
             for (int nn_ = 0; nn_ < Nn; ++nn_) { rowsum = std::max(rowsum, rs[nn_]); bmax = std::max(bmax, std::fabs((double)theta[boff + nn_])); }
         };
-        double w1, r1, b1, k1, w2, r2, b2, k2, w3, r3, b3, k3;
-        norms(N0::T_W0, 32, 128, N0::T_B0, w1, r1, b1, k1);
-        norms(N0::T_HID, 128, 128, N0::T_HID + 128 * 128, w2, r2, b2, k2);
-        norms(N0::T_WL, 128, 31, N0::T_BL, w3, r3, b3, k3);
-        const double x0 = 128.0, a1 = r1 * x0 + b1, a2 = r2 * a1 + b2;
-        tc::Fp16Scales sc{p2(w1), p2(w2), p2(w3), p2(x0), p2(a1), p2(a2)};
+        double wm[4], rsum[4], bm[4], csum[4], abound[4];
+        norms(T_W0, IN0, 128, T_B0, wm[0], rsum[0], bm[0], csum[0]);
+        for (int l = 1; l < NH; ++l) norms(T_HID + (l - 1) * HID_STRIDE, 128, 128, T_HID + (l - 1) * HID_STRIDE + 128 * 128, wm[l], rsum[l], bm[l], csum[l]);
+        norms(T_WL, 128, 31, T_BL, wm[NH], rsum[NH], bm[NH], csum[NH]);
+        abound[0] = 128.0;                                                   // network input; behind a Conv front-end: 128 sum|w| + |b|
+        if (CW) {
+            double sw = 0.0;
+            for (int j = 0; j < CW; ++j) sw += std::fabs((double)theta[j]);
+            abound[0] = 128.0 * sw + std::fabs((double)theta[CW]);
+        }
+        for (int l = 1; l <= NH; ++l) abound[l] = rsum[l - 1] * abound[l - 1] + bm[l - 1];
+        tc::Fp16Scales sc{};
+        for (int l = 0; l <= NH; ++l) { sc.s_w[l] = p2(wm[l]); sc.s_a[l] = p2(abound[l]); }
+        for (int l = NH + 1; l < 4; ++l) { sc.s_w[l] = 1.f; sc.s_a[l] = 1.f; }
         memcpy(h->fp16_scales, &sc, sizeof sc);
-        {   // backward chain: |d3 * scol| <= 1 per column, |g2| <= colsum(W3), |g1| <= colsum(W2) colsum(W3)
-            const double s_d3 = 16384.0, s_d2 = p2(k3), s_d1 = p2(k2 * k3);
+        if (h->arch == ARCH_DEFAULT) {   // backward chain: |d3 * scol| <= 1 per column, |g2| <= colsum(W3), |g1| <= colsum(W2) colsum(W3)
+            const double s_d3 = 16384.0, s_d2 = p2(csum[2]), s_d1 = p2(csum[1] * csum[2]);
             atc::AtcScales& a = h->atc_scales;
             a.s_d3 = (float)s_d3;
-            a.c_g2 = (float)(s_d2 / (s_d3 * (double)sc.s_w3));
-            a.c_g1 = (float)(s_d1 / (s_d2 * (double)sc.s_w2));
-            a.inv_u = (float)(1.0 / (s_d1 * (double)sc.s_w1));
+            a.c_g2 = (float)(s_d2 / (s_d3 * (double)sc.s_w[2]));
+            a.c_g1 = (float)(s_d1 / (s_d2 * (double)sc.s_w[1]));
+            a.inv_u = (float)(1.0 / (s_d1 * (double)sc.s_w[0]));
             a.inv_sd2 = (float)(1.0 / s_d2); a.inv_sd1 = (float)(1.0 / s_d1);
-            a.inv_sa0 = 1.f / sc.s_a0; a.inv_sa1 = 1.f / sc.s_a1; a.inv_sa2 = 1.f / sc.s_a2;
+            a.inv_sa0 = 1.f / sc.s_a[0]; a.inv_sa1 = 1.f / sc.s_a[1]; a.inv_sa2 = 1.f / sc.s_a[2];
         }
         if (h->tc_fp16) {
-            const int n = 128 * 32 + 128 * 128 + 32 * 128 + 296;
-            tc::pack_weights_tc16_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_theta.p, h->d_wimg.p, sc);
+            const int n = 128 * 32 + (NH - 1) * 128 * 128 + 32 * 128 + NH * 128 + 32 + 16;
+#define NFC_PACK16(NHv, CWv) tc::pack_weights_tc16_kernel<NHv, CWv><<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_theta.p, h->d_wimg.p, sc)
+            NFC_TC_ARCH_DISPATCH(h, NFC_PACK16(2, 0), NFC_PACK16(2, 2), NFC_PACK16(2, 4), NFC_PACK16(3, 0))
+#undef NFC_PACK16
         } else {
             const int n = 128 * 32 + 128 * 128 + 32 * 128 + 288;
             tc::pack_weights_tc_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(h->d_theta.p, h->d_wimg.p);
@@ -736,7 +784,7 @@ int32_t nfc_set_option(nfc_handle* h, const char* name, int64_t value) {
     if (!h || !name) return -1;
     const std::string n(name);
     const bool def = h->arch == ARCH_DEFAULT;
-    if (n == "tc") { if (value && !def) return fail(h, -3, "the tensor-core kernels exist for the default Chain only"); h->use_tc = value != 0; }
+    if (n == "tc") { if (value && !tc_forward_arch(h->arch)) return fail(h, -3, "no tensor-core kernels for the wider Chain"); h->use_tc = value != 0; }
     else if (n == "tc_tiles") { if (value < 0 || value > 2) return fail(h, -2, "tc_tiles: 0 (auto), 1 or 2"); h->tc_tiles = (int)value; }
     else if (n == "tc2_min_columns") h->tc2_min_columns = value;
     else if (n == "tc_record") h->tc_record = value != 0;
@@ -931,7 +979,8 @@ int32_t nfc_solve(nfc_handle* h, const float* T0, const float* colp, const float
     if (nreject) NFC_CUDA(h, cudaMemcpyAsync(nreject, h->s_nrej.p, sizeof(int) * B, cudaMemcpyDeviceToHost, h->stream));
     // FP16x2 operand range: a column whose accepted state left |T_scaled| <= 128 comes back as ST_RANGE; it is re-solved here on the BF16x3
     // split (fp32's exponent range, same kernel), so the caller sees what the reference would have integrated (nfc_set_option "range_fallback")
-    const bool may_fall_back = h->range_fallback && h->use_tc && h->arch == ARCH_DEFAULT && h->tc_fp16 && h->cfg.alg == NFC_ALG_TSIT5;
+    const bool may_fall_back = h->range_fallback && h->use_tc && tc_forward_arch(h->arch) && h->tc_fp16 && h->cfg.alg == NFC_ALG_TSIT5;
+    const bool fb_simt = h->arch != ARCH_DEFAULT;                           // no BF16x3 kernels for these Chains: the FP32 SIMT kernel re-solves
     std::vector<int> hstat;
     int* st_host = status;
     if (!st_host && may_fall_back) { hstat.resize(B); st_host = hstat.data(); }
@@ -952,19 +1001,22 @@ int32_t nfc_solve(nfc_handle* h, const float* T0, const float* colp, const float
             NFC_CUDA(h, cudaMemcpyAsync(h->s_T0.p, t0c.data(), sizeof(float) * nr * NZ, cudaMemcpyHostToDevice, h->stream));
             NFC_CUDA(h, cudaMemcpyAsync(h->s_colp.p, cpc.data(), sizeof(float) * nr * 3, cudaMemcpyHostToDevice, h->stream));
             NFC_CUDA(h, cudaMemsetAsync(h->s_out.p, 0xFF, sizeof(float) * nr * row, h->stream));
-            if (int rc = switch_split(h, false)) return rc;
+            if (fb_simt) h->use_tc = false;
+            else if (int rc = switch_split(h, false)) return rc;
             const bool sched = h->use_sched;
             h->use_sched = false;                                       // keep the batch's longest-first history
             int rc = [&]() -> int {
                 NFC_DISPATCH(h, do_solve, h, h->s_T0.p, h->s_colp.p, pref, h->s_out.p, h->s_nacc.p, h->s_nrej.p, h->s_status.p, nr, h->stream, false);
             }();
             h->use_sched = sched;
-            if (rc) { switch_split(h, true); return rc; }
+            if (fb_simt) h->use_tc = true;
+            if (rc) { if (!fb_simt) switch_split(h, true); return rc; }
             NFC_CUDA(h, cudaMemcpyAsync(outc.data(), h->s_out.p, sizeof(float) * nr * row, cudaMemcpyDeviceToHost, h->stream));
             NFC_CUDA(h, cudaMemcpyAsync(nac.data(), h->s_nacc.p, sizeof(int) * nr, cudaMemcpyDeviceToHost, h->stream));
             NFC_CUDA(h, cudaMemcpyAsync(nrc.data(), h->s_nrej.p, sizeof(int) * nr, cudaMemcpyDeviceToHost, h->stream));
             NFC_CUDA(h, cudaMemcpyAsync(stc.data(), h->s_status.p, sizeof(int) * nr, cudaMemcpyDeviceToHost, h->stream));
-            if (int rc2 = switch_split(h, true)) return rc2;            // synchronises the stream
+            if (fb_simt) NFC_CUDA(h, cudaStreamSynchronize(h->stream));
+            else if (int rc2 = switch_split(h, true)) return rc2;       // synchronises the stream
             for (int64_t i = 0; i < nr; ++i) {
                 memcpy(Tout + redo[i] * row, &outc[i * row], sizeof(float) * row);
                 if (naccept) naccept[redo[i]] = nac[i];

@@ -75,7 +75,7 @@ struct nfc_handle {
     double tape_gib = 0.0;                  // scratch budget of nfc_loss_grad's tape in GiB (0 = default 48)
     bool adj_tc = true;                     // batch backward pass of loss_grad on the tensor cores (default Chain, FP16x2; NFC_ADJ_TC=0: FP32 SIMT kernel)
     nfc::atc::AtcScales atc_scales{};
-    float fp16_scales[6] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f};   // tc::Fp16Scales of the current weights (nfc_set_weights), for re-packing the image
+    float fp16_scales[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};   // tc::Fp16Scales of the current weights (nfc_set_weights), for re-packing the image
     bool range_fallback = true;             // host-buffer calls re-solve ST_RANGE columns on a split / kernel without the FP16 range bound
     int64_t range_resolved = 0;             // columns the last host-buffer call re-solved that way
     bool tc_fp16 = false;                   // tensor-core split: false = BF16x3 (6 MMAs / product), true = FP16x2 (3 MMAs, scaled operands)

@@ -243,6 +243,7 @@ struct TcShared {
     float xch[2][TILE][4][2]; // first / last level of every quarter, exchanged between the four threads of a column (double buffered)
     float part[2][TILE][4];   // partial error norms (double buffered)
     float rng[2][TILE][4];    // max |u_new| of each quarter (range check of accepted states)
+    float hal[2][TILE][4][3]; // first three levels of every quarter: the halo of the Conv front-end (conv-2 / conv-4 Chains)
     int newcol[TILE];         // refill hand-off between the four threads of a column
     int any;
 };
@@ -380,6 +381,7 @@ __device__ __forceinline__ void chain_eval(TcShared* S, const float* sbias, cons
 // scaled activation.  Inputs beyond the bound overflow to inf and are reported as status NaN (never silently wrong).
 // =====================================================================================================================
 struct SplitBF16x3 {
+    static constexpr int NH = 2, CW = 0;                       // default Chain only
     static constexpr int IMG = IMG_BYTES, BIAS_OFF = OFF_B;
     static constexpr float INPUT_BOUND = 3.0e38f;              // BF16 has fp32's exponent range: no bound
     static constexpr bool SPARE_TMEM = false;                  // all 512 tensor-memory columns are in use (three operand splits)
@@ -393,48 +395,74 @@ struct SplitBF16x3 {
     }
 };
 
-constexpr int W1H_BYTES = 128 * 32 * 2, W2H_BYTES = 128 * 128 * 2, W3H_BYTES = 64 * 128 * 2;   // layer 3: [hi; lo] stacked along N (64 rows)
-constexpr int OFF16_W1 = 0;
-constexpr int OFF16_W2 = OFF16_W1 + 2 * W1H_BYTES;
-constexpr int OFF16_W3 = OFF16_W2 + 2 * W2H_BYTES;
-constexpr int OFF16_B = OFF16_W3 + W3H_BYTES;                  // bias1'[128] bias2'[128] bias3[32] consts[8] (fp32)
-constexpr int IMG16_BYTES = OFF16_B + (128 + 128 + 32 + 8) * 4;   // 99 488 B
-struct Fp16Scales { float s_w1, s_w2, s_w3, s_a0, s_a1, s_a2; };
+constexpr int W1H_BYTES = 128 * 32 * 2, W2H_BYTES = 128 * 128 * 2, W3H_BYTES = 64 * 128 * 2;   // output layer: [hi; lo] stacked along N (64 rows)
+// FP16x2 weight image of a Chain [Conv((CW,1),1=>1,relu)] -> Dense(IN0,128,relu) -> (NH-1) x Dense(128,128,relu) -> Dense(128,31):
+// the default Chain (NH = 2, CW = 0), conv-2 / conv-4 (NH = 2, CW = 2 / 4; the first Dense layer's K is zero-padded to 32) and the deeper
+// Chain (NH = 3).  (The wider Chain, H = 256, needs 256 KB for its hidden matrix alone and stays on the FP32 SIMT kernels.)
+template <int NH_, int CW_>
+struct TcLayout {
+    static constexpr int NH = NH_, CW = CW_;
+    using N = Net<128, NH_, CW_>;
+    static constexpr int OFF_W1 = 0;                                          // [hi | lo], K = 32
+    static constexpr int OFF_WH = OFF_W1 + 2 * W1H_BYTES;                     // NH - 1 hidden-to-hidden matrices, [hi | lo] each
+    static constexpr int OFF_W3 = OFF_WH + (NH_ - 1) * 2 * W2H_BYTES;
+    static constexpr int OFF_B = OFF_W3 + W3H_BYTES;                          // fp32: NH x bias'[128], b3[32], consts[16]
+    static constexpr int CB = NH_ * 128 + 32;                                 // consts: c_1 .. c_NH, inv3, s_a0, conv w[0..3], conv bias
+    static constexpr int C_INV3 = CB + NH_, C_SA0 = CB + NH_ + 1, C_CONVW = CB + NH_ + 2, C_CONVB = CB + NH_ + 6;
+    static constexpr int IMG = OFF_B + (CB + 16) * 4;
+};
+using TcDefault = TcLayout<2, 0>;
+constexpr int OFF16_W1 = TcDefault::OFF_W1, OFF16_W2 = TcDefault::OFF_WH, OFF16_W3 = TcDefault::OFF_W3, OFF16_B = TcDefault::OFF_B;
+constexpr int IMG16_BYTES = TcDefault::IMG;                                   // 99 520 B
+constexpr int IMG16_MAX = TcLayout<3, 0>::IMG;                                // the largest image (deeper Chain): 165 568 B
+// exact power-of-two operand scales: s_w[l] of the l-th weight matrix (l = 0 .. NH), s_a[l] of its input (s_a[0]: the network input
+// after the Conv front-end, s_a[l]: hidden activations l)
+struct Fp16Scales { float s_w[4], s_a[4]; };
 
 __host__ __device__ constexpr uint32_t make_idesc16(int M, int N) {   // kind::f16: A = B = F16 (0), C = F32 (1), both K-major
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+template <int NH, int CW>
 static __global__ void pack_weights_tc16_kernel(const float* __restrict__ theta, unsigned char* __restrict__ img, const Fp16Scales sc) {
-    using N = Net<128, 2, 0>;
+    using L = TcLayout<NH, CW>;
+    using N = typename L::N;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n1 = 128 * 32, n2 = 128 * 128, n3 = 32 * 128;
+    const int n1 = 128 * 32, n2 = (NH - 1) * 128 * 128, n3 = 32 * 128;
     if (i < n1 + n2 + n3) {
         float w, s;
         int off_hi, off_lo;
-        if (i < n1) { const int n = i % 128, k = i / 128; w = theta[N::T_W0 + k * 128 + n]; s = sc.s_w1; off_hi = OFF16_W1 + umma_off(n, k, 128); off_lo = off_hi + W1H_BYTES; }
-        else if (i < n1 + n2) { const int q = i - n1, n = q % 128, k = q / 128; w = theta[N::T_HID + k * 128 + n]; s = sc.s_w2; off_hi = OFF16_W2 + umma_off(n, k, 128); off_lo = off_hi + W2H_BYTES; }
-        else {
+        if (i < n1) {
+            const int n = i % 128, k = i / 128;
+            w = k < N::IN0 ? theta[N::T_W0 + k * 128 + n] : 0.f; s = sc.s_w[0];
+            off_hi = L::OFF_W1 + umma_off(n, k, 128); off_lo = off_hi + W1H_BYTES;
+        } else if (i < n1 + n2) {
+            const int q = i - n1, l = q / (128 * 128), r = q % (128 * 128), n = r % 128, k = r / 128;
+            w = theta[N::T_HID + l * N::HID_STRIDE + k * 128 + n]; s = sc.s_w[1 + l];
+            off_hi = L::OFF_WH + l * 2 * W2H_BYTES + umma_off(n, k, 128); off_lo = off_hi + W2H_BYTES;
+        } else {
             const int q = i - n1 - n2, n = q % 32, k = q / 32;
-            w = n < 31 ? theta[N::T_WL + k * 31 + n] : 0.f; s = sc.s_w3;
-            off_hi = OFF16_W3 + umma_off(n, k, 64); off_lo = OFF16_W3 + umma_off(32 + n, k, 64);
+            w = n < 31 ? theta[N::T_WL + k * 31 + n] : 0.f; s = sc.s_w[NH];
+            off_hi = L::OFF_W3 + umma_off(n, k, 64); off_lo = L::OFF_W3 + umma_off(32 + n, k, 64);
         }
         const float ws = w * s;
         const __half hi = __float2half_rn(ws);
         const __half lo = __float2half_rn(ws - __half2float(hi));
         *reinterpret_cast<__half*>(img + off_hi) = hi;
         *reinterpret_cast<__half*>(img + off_lo) = lo;
-    } else if (i < n1 + n2 + n3 + 296) {
+    } else if (i < n1 + n2 + n3 + L::CB + 16) {
         const int q = i - n1 - n2 - n3;
         float v = 0.f;
-        if (q < 128) v = theta[N::T_B0 + q] * sc.s_a1;                                     // bias'_1 = b1 * s_a1
-        else if (q < 256) v = theta[N::T_HID + 128 * 128 + (q - 128)] * sc.s_a2;          // bias'_2 = b2 * s_a2
-        else if (q < 288) v = (q - 256 < 31) ? theta[N::T_BL + (q - 256)] : 0.f;          // b3 (output is un-scaled)
-        else if (q == 288) v = sc.s_a1 / (sc.s_a0 * sc.s_w1);                             // c1: D1 -> scaled a1
-        else if (q == 289) v = sc.s_a2 / (sc.s_a1 * sc.s_w2);                             // c2: D2 -> scaled a2
-        else if (q == 290) v = 1.f / (sc.s_a2 * sc.s_w3);                                 // inv3: D3 -> NN output
-        else if (q == 291) v = sc.s_a0;
-        reinterpret_cast<float*>(img + OFF16_B)[q] = v;
+        if (q < NH * 128) {                                                                     // bias'_l = b_l * s_a[l]   (l = 1 .. NH)
+            const int l = q / 128, j = q % 128;
+            v = (l == 0 ? theta[N::T_B0 + j] : theta[N::T_HID + (l - 1) * N::HID_STRIDE + 128 * 128 + j]) * sc.s_a[l + 1];
+        } else if (q < L::CB) v = (q - NH * 128 < 31) ? theta[N::T_BL + (q - NH * 128)] : 0.f;   // b3 (the output is un-scaled)
+        else if (q < L::CB + NH) { const int l = q - L::CB; v = sc.s_a[l + 1] / (sc.s_a[l] * sc.s_w[l]); }   // c_{l+1}: D -> scaled activation
+        else if (q == L::C_INV3) v = 1.f / (sc.s_a[NH] * sc.s_w[NH]);                          // D_out -> NN output
+        else if (q == L::C_SA0) v = sc.s_a[0];
+        else if (q >= L::C_CONVW && q < L::C_CONVW + 4) v = (q - L::C_CONVW) < CW ? theta[N::T_CONV + (q - L::C_CONVW)] : 0.f;
+        else if (q == L::C_CONVB) v = CW ? theta[N::T_CONV + CW] : 0.f;
+        reinterpret_cast<float*>(img + L::OFF_B)[q] = v;
     }
 }
 
@@ -461,10 +489,12 @@ __device__ __forceinline__ void split2h_relu(float v0, float v1, uint32_t& ph, u
     asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(pl) : "f"(r1), "f"(r0));
 }
 
-template <int LAYER, int SUB>
+// LAYER 0: Dense(32, 128) in one go; 1 .. NH-1: hidden-to-hidden; NH: the output layer
+template <class L, int LAYER, int SUB>
 __device__ __forceinline__ void issue_layer16(uint32_t tmem_base, uint32_t smem_img) {
-    constexpr int Nn = LAYER == 2 ? 64 : 128;
-    constexpr uint32_t woff = LAYER == 0 ? OFF16_W1 : (LAYER == 1 ? OFF16_W2 : OFF16_W3);
+    constexpr bool OUT = LAYER == L::NH;
+    constexpr int Nn = OUT ? 64 : 128;
+    constexpr uint32_t woff = LAYER == 0 ? L::OFF_W1 : (OUT ? L::OFF_W3 : L::OFF_WH + (LAYER - 1) * 2 * W2H_BYTES);
     constexpr uint32_t wbytes = LAYER == 0 ? W1H_BYTES : W2H_BYTES;
     constexpr uint32_t idesc = make_idesc16(128, Nn);
     constexpr uint32_t kstep = (2u * Nn * 16u) >> 4;
@@ -472,7 +502,7 @@ __device__ __forceinline__ void issue_layer16(uint32_t tmem_base, uint32_t smem_
     const uint64_t desc0 = make_bdesc(smem_img + woff, Nn);
     const uint32_t lo0 = (uint32_t)desc0, hi0 = (uint32_t)(desc0 >> 32);
     const uint32_t a_base = tmem_base + TM_A;
-    if (LAYER == 2) {            // stacked [B_hi; B_lo]: D[:, 0:32] + D[:, 32:64] = A (B_hi + B_lo), a split lo first
+    if (OUT) {                   // stacked [B_hi; B_lo]: D[:, 0:32] + D[:, 32:64] = A (B_hi + B_lo), a split lo first
 #pragma unroll
         for (int sA = 1; sA >= 0; --sA)
 #pragma unroll
@@ -496,11 +526,12 @@ __device__ __forceinline__ void issue_layer16(uint32_t tmem_base, uint32_t smem_
 
 // FP16x2 version of chain_eval; sb points at bias1' (then bias2', bias3, consts).  FOLD: relu folded into the conversions (split2h_relu);
 // the RECORD pass of loss_grad keeps the round-to-nearest split so that its trajectories stay those the gradient tests were pinned with
-template <bool FOLD, class H1 = NoHook, class H2 = NoHook>
+// y: the network input of this thread's 8 levels (after the Conv front-end, if the Chain has one)
+template <class L, bool FOLD, class H1 = NoHook, class H2 = NoHook>
 __device__ __forceinline__ void chain_eval16(TcShared* S, const float* sb, const float (&y)[8], float (&nn)[9], int& pd, int wq, int q, long long* twd,
                                              H1 hook1 = H1(), H2 hook2 = H2()) {
     const uint32_t tl = S->tmem_base + ((uint32_t)(32 * wq) << 16);
-    const float s_a0 = sb[291];
+    const float s_a0 = sb[L::C_SA0];
     {
         uint32_t ph[4], pl[4];
 #pragma unroll
@@ -517,12 +548,12 @@ __device__ __forceinline__ void chain_eval16(TcShared* S, const float* sb, const
     }
     // hidden layers: thread (column, quarter q) converts the units 32 s + 8 q .. + 7 in its sub-chunk s = 0..3 (see chain_eval)
 #pragma unroll 1
-    for (int l = 0; l < 2; ++l) {
+    for (int l = 0; l < L::NH; ++l) {
         if (twd) { const long long a = clock64(); mbar_wait(&S->bar_d, pd); twd[l] += clock64() - a; } else mbar_wait(&S->bar_d, pd);
         pd ^= 1;
         fence_after_sync();
         const float* b = sb + 128 * l + 8 * q;
-        const float cl = sb[288 + l];
+        const float cl = sb[L::CB + l];
         uint32_t r[32];
 #pragma unroll
         for (int sc = 0; sc < 4; ++sc) tmem_ld8(tl + TM_D + 32 * sc + 8 * q, *reinterpret_cast<uint32_t(*)[8]>(&r[8 * sc]));
@@ -550,9 +581,9 @@ __device__ __forceinline__ void chain_eval16(TcShared* S, const float* sb, const
             fence_before_sync();
             warp_arrive(sc == 0 ? &S->bar_a : &S->bar_q[sc - 1]);
         }
-        if (l == 0) hook1(); else hook2();
+        if (l == 0) hook1(); else if (l == L::NH - 1) hook2();
     }
-    if (twd) { const long long a = clock64(); mbar_wait(&S->bar_d, pd); twd[2] += clock64() - a; } else mbar_wait(&S->bar_d, pd);
+    if (twd) { const long long a = clock64(); mbar_wait(&S->bar_d, pd); twd[L::NH] += clock64() - a; } else mbar_wait(&S->bar_d, pd);
     pd ^= 1;
     fence_after_sync();
     {
@@ -561,8 +592,8 @@ __device__ __forceinline__ void chain_eval16(TcShared* S, const float* sb, const
         tmem_ld8(tl + TM_D + 32 + 8 * q, rb);
         if (q) { tmem_ld1(tl + TM_D + 8 * q - 1, a0); tmem_ld1(tl + TM_D + 32 + 8 * q - 1, b0); }
         wait_ld();
-        const float* b3 = sb + 256;
-        const float inv3 = sb[290];
+        const float* b3 = sb + 128 * L::NH;
+        const float inv3 = sb[L::C_INV3];
         nn[0] = q ? fmaf(__uint_as_float(b0) + __uint_as_float(a0), inv3, b3[8 * q - 1]) : 0.f;
 #pragma unroll
         for (int i = 0; i < 8; i += 2) {
@@ -574,10 +605,13 @@ __device__ __forceinline__ void chain_eval16(TcShared* S, const float* sb, const
     fence_before_sync();
 }
 
-struct SplitFP16x2 {
-    static constexpr int IMG = IMG16_BYTES, BIAS_OFF = OFF16_B;
+template <int NH_, int CW_>
+struct SplitFP16x2T {
+    using L = TcLayout<NH_, CW_>;
+    static constexpr int NH = NH_, CW = CW_;
+    static constexpr int IMG = L::IMG, BIAS_OFF = L::OFF_B;
     template <int LAYER, int SUB>
-    static __device__ __forceinline__ void issue(uint32_t tb, uint32_t img, int) { issue_layer16<LAYER, SUB>(tb, img); }
+    static __device__ __forceinline__ void issue(uint32_t tb, uint32_t img, int) { issue_layer16<L, LAYER, SUB>(tb, img); }
     static constexpr float INPUT_BOUND = 128.f;
     // free 32-column vector slots in tensor memory: the third operand-split region (two slots) and the k7 slot (k7 stays in registers)
     static constexpr bool SPARE_TMEM = true;
@@ -591,15 +625,19 @@ struct SplitFP16x2 {
                                                 bool poison, H1 h1 = H1(), H2 h2 = H2()) {
         float yc[8];
         bool bad = false;
+        // with a Conv front-end `y` is its output, whose bound (128 sum|w| + |b|) went into the scale s_a0: saturate where the scaled operand
+        // reaches 16384
+        const float bound = CW ? 16384.f / sb[L::C_SA0] : INPUT_BOUND;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { yc[i] = fminf(fmaxf(y[i], -INPUT_BOUND), INPUT_BOUND); bad |= !(fabsf(y[i]) <= INPUT_BOUND); }
-        chain_eval16<FOLD>(S, sb, yc, nn, pd, wq, q, twd, h1, h2);
+        for (int i = 0; i < 8; ++i) { yc[i] = fminf(fmaxf(y[i], -bound), bound); bad |= !(fabsf(y[i]) <= bound); }
+        chain_eval16<L, FOLD>(S, sb, yc, nn, pd, wq, q, twd, h1, h2);
         if (poison && bad) {
 #pragma unroll
             for (int i = 0; i < 9; ++i) nn[i] = __int_as_float(0x7fc00000);
         }
     }
 };
+using SplitFP16x2 = SplitFP16x2T<2, 0>;      // the default Chain
 
 // f (8 levels of this thread) from the Chain output and the stage input: faces k = 8q .. 8q+8,
 // F_0 = bottom, F_32 = top, else NN[k-1] - min(0, K_CA (y_k - y_{k-1}) / dz);  f_k = -pref (F_{k+1} - F_k) / dz
@@ -617,6 +655,32 @@ __device__ __forceinline__ void faces_to_f(const float (&y)[8], float ylo, float
         if (k == NZ) F = top;
         if (i > 0) f[i - 1] = -pref * ((F - Fprev) * (float)NZ);
         Fprev = F;
+    }
+}
+
+__device__ __forceinline__ void cta_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }      // the 512 column threads
+
+// Conv((CW,1),1=>1,relu) front-end of the conv-2 / conv-4 Chains on this thread's 8 levels (train_free_convection_nde.jl:138-153; a true
+// convolution: x_i = relu(b + sum_j w_j y_{i+CW-1-j})).  The CW-1 levels beyond this quarter come from the next quarter's thread through
+// shared memory (one barrier of the column threads per evaluation); outputs beyond Nz-CW+1 are zero (their rows of the first Dense layer are
+// zero padding).  cw: w[0..3], bias at cw[4] (consts of the weight image).
+template <int CW>
+__device__ __forceinline__ void conv_front(TcShared* S, const float* cw, const float (&y)[8], float (&x)[8], int xb, int c, int q) {
+#pragma unroll
+    for (int j = 0; j < CW - 1; ++j) S->hal[xb][c][q][j] = y[j];
+    cta_bar();
+    float ext[8 + 3];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) ext[i] = y[i];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) ext[8 + j] = (j < CW - 1 && q < 3) ? S->hal[xb][c][q + 1][j < CW - 1 ? j : 0] : 0.f;
+    const float b = cw[4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float acc = 0.f;
+#pragma unroll
+        for (int j = 0; j < CW; ++j) acc = fmaf(cw[j], ext[i + CW - 1 - j], acc);
+        x[i] = (8 * q + i < NZ - CW + 1) ? fmaxf(acc + b, 0.f) : 0.f;
     }
 }
 
@@ -667,9 +731,10 @@ __device__ __forceinline__ void mma_warp_loop(TcShared* S, uint32_t smem_img, in
             tw[0] += c1 - c0; ti[0] += c2 - c1;
             long long w = 0;
             mma_issue_subs<SP, 1>(S, smem_img, pa, pq, w);
+            if constexpr (SP::NH == 3) mma_issue_subs<SP, 2>(S, smem_img, pa, pq, w);      // third hidden layer (deeper Chain)
             c1 = clock64(); tw[1] += w; ti[1] += c1 - c2 - w;
             w = 0;
-            mma_issue_subs<SP, 2>(S, smem_img, pa, pq, w);
+            mma_issue_subs<SP, SP::NH>(S, smem_img, pa, pq, w);                            // output layer
             c2 = clock64(); tw[2] += w; ti[2] += c2 - c1 - w;
             n += 1;
         }
@@ -736,7 +801,20 @@ rhs_tc_kernel(const unsigned char* __restrict__ gimg, const float* __restrict__ 
             xb ^= 1;
             S.xch[xb][c][q][0] = y[0];
             S.xch[xb][c][q][1] = y[7];
-            SP::eval(&S, sbias, y, nn, pd, wq, q, nullptr, true);   // its mbarrier traffic orders the exchange (double buffered)
+            if constexpr (SP::CW > 0) {
+                float xin[8];
+                bool bad = false;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) bad |= !(fabsf(y[i]) <= SP::INPUT_BOUND);
+                conv_front<SP::CW>(&S, sbias + SP::L::C_CONVW, y, xin, xb, c, q);
+                SP::eval(&S, sbias, xin, nn, pd, wq, q, nullptr, false);
+                if (bad) {
+#pragma unroll
+                    for (int i = 0; i < 9; ++i) nn[i] = __int_as_float(0x7fc00000);
+                }
+            } else {
+                SP::eval(&S, sbias, y, nn, pd, wq, q, nullptr, true);   // its mbarrier traffic orders the exchange (double buffered)
+            }
             const float bot = ok ? colp[col * 3 + 0] : 0.f, top = ok ? colp[col * 3 + 1] : 0.f;
             const float kk = (ok && use_kca) ? colp[col * 3 + 2] * (float)NZ : 0.f;
             const float ylo = q > 0 ? S.xch[xb][c][q - 1][1] : 0.f, yhi = q < 3 ? S.xch[xb][c][q + 1][0] : 0.f;
@@ -769,8 +847,6 @@ rhs_tc_kernel(const unsigned char* __restrict__ gimg, const float* __restrict__ 
 
 namespace nfc {
 namespace tc {
-
-__device__ __forceinline__ void cta_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 // k_j (j = 2..7) chunk of this thread in tensor memory: column TM_K + 32 (j-2) + 8 q, 8 cells
 __device__ __forceinline__ uint32_t kaddr(uint32_t tl, int j, int q) { return tl + TM_K + 32 * (j - 2) + 8 * q; }
@@ -1008,7 +1084,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
                         wait_st();
                     }
                 };
-                SP::template eval<true>(&S, sbias, y, nn, pd, wq, q, twdp, false, h1, h2);      // nfc_solve and the RECORD pass of nfc_loss_grad share ONE arithmetic
+                float xin[8];
+                if constexpr (SP::CW > 0) conv_front<SP::CW>(&S, sbias + SP::L::C_CONVW, y, xin, xb, c, q);
+                const float (&xi)[8] = SP::CW > 0 ? xin : y;
+                SP::template eval<true>(&S, sbias, xi, nn, pd, wq, q, twdp, false, h1, h2);      // nfc_solve and the RECORD pass of nfc_loss_grad share ONE arithmetic
                 const float ylo = q > 0 ? S.xch[xb][c][q - 1][1] : 0.f, yhi = q < 3 ? S.xch[xb][c][q + 1][0] : 0.f;
                 faces_to_f(y, ylo, yhi, nn, bot, top, kk, P.pref, q, f);
                 if (s < 5) {

@@ -391,3 +391,35 @@ def test_set_option_selects_kernels(nfc, gpu_ok):
         h.set_option("no_such_option", 1)
     with pytest.raises(nfc.NfcError):
         h.set_option("tc_tiles", 3)
+
+
+@pytest.mark.parametrize("arch", ["conv-2", "conv-4", "dense-deeper"])
+def test_other_chains_run_on_the_tensor_cores(nfc, gpu_ok, arch):
+    """conv-2 / conv-4 / deeper Chains: nfc_rhs and the Tsit5 forward solve run on the tensor-core kernels (templated weight-image layout,
+    Conv front-end evaluated by the column threads, third hidden layer as one more MMA layer); `tc` 0 selects the FP32 SIMT kernels.
+    Both against the float64 / C oracle at the north-star tolerances, ragged batch (2 full tiles + 44 columns)."""
+    syn = nfc.synthetic
+    d = syn.make_columns("ocean", B=300, seed=12)
+    cw, layers = O.chain_spec(arch)
+    sv = syn.saveat(9)
+    for scale in (0.3, 1e-5):
+        theta = O.glorot_theta(cw, layers, 5, scale)
+        h = nfc.Handle(cw, layers, 1, sv)
+        h.set_weights(theta)
+        rng = np.random.default_rng(3)
+        T = (d["T0"] + 0.3 * rng.standard_normal(d["T0"].shape)).astype(np.float32)
+        ref = O.rhs(T, theta, cw, layers, d["colp"], d["glob"], np.float64)
+        f_tc = h.rhs(T, d["colp"], d["glob"])
+        r_tc = h.solve(d["T0"], d["colp"], d["glob"])
+        assert h.counters()["kernel_launches"] >= 1
+        h.set_option("tc", 0)
+        f_simt = h.rhs(T, d["colp"], d["glob"])
+        r_simt = h.solve(d["T0"], d["colp"], d["glob"])
+        assert rel_l2(f_tc, ref).max() < 1e-5 and rel_l2(f_simt, ref).max() < 1e-5
+        assert not np.array_equal(f_tc, f_simt)                                # two different kernels
+        assert (r_tc["status"] == 0).all() and (r_simt["status"] == 0).all()
+        # two float32 adaptive solves with different rounding (and therefore step sequences): each within the tolerance of the oracle,
+        # up to twice that between them
+        assert rel_l2(r_tc["T"], r_simt["T"]).max() < 2 * TRAJ_TOL
+        c = CO.solve(d["T0"][:48], theta, cw, layers, d["colp"][:48], d["glob"], sv)
+        assert rel_l2(r_tc["T"][:48], c["T"]).max() < TRAJ_TOL and rel_l2(r_simt["T"][:48], c["T"]).max() < TRAJ_TOL
