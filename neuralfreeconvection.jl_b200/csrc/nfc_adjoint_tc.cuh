@@ -289,18 +289,14 @@ __device__ __forceinline__ void atc_control(const AdjParams& P, AtcShared& S, in
             S.mode[c] = 0;
             S.dt[c] = S.dt_retry[c];
         } else {
-            const float ee = sqrtf(((S.part[0][c] + S.part[1][c]) + (S.part[2][c] + S.part[3][c])) * (1.f / NZ));
+            const float ee = fast_sqrt(((S.part[0][c] + S.part[1][c]) + (S.part[2][c] + S.part[3][c])) * (1.f / NZ));      // fast controller arithmetic as in the forward kernels (nfc_tc.cuh)
             const float h = S.h[c];
             bool accept;
             float dtnew;
             if (P.fixed_dt > 0.f) { accept = true; dtnew = P.fixed_dt; }
             else if (!isfinite(ee)) { accept = false; dtnew = 0.2f * h; }
             else {
-                const float q11 = powf(ee, 0.14f);
-                float qq = q11 / powf(S.qold[c], 0.08f);
-                qq = fmaxf(0.1f, fminf(5.0f, qq / 0.9f));
-                accept = ee <= 1.0f;
-                dtnew = accept ? h / qq : h / fminf(5.0f, q11 / 0.9f);
+                pi_controller(ee, S.qold[c], h, accept, dtnew);
             }
             if (accept) {
                 fl |= AFL_ACCEPT;
@@ -429,7 +425,7 @@ __device__ __forceinline__ void coop_load(const AdjParams& P, AtcShared& S, unsi
         const int cc = 8 * warp + 4 * b + j;
         const float hc = S.h[cc];
         const float ts = (s == 6 && (S.flag[cc] & AFL_LAST)) ? S.tstop[cc] : S.t[cc] - cs * hc;
-        const float th = fminf(fmaxf((ts - tn[j]) / hn[j], 0.f), 1.f);
+        const float th = fminf(fmaxf(fast_div(ts - tn[j], hn[j]), 0.f), 1.f);
         const float uv = fmaf(hn[j], th * fmaf(th, fmaf(th, fmaf(th, e[j][4], e[j][3]), e[j][2]), e[j][1]), e[j][0]);
         ub[cc * 32 + ((((lane >> 2) ^ (cc & 7)) << 2) | (lane & 3))] = S.col[cc] >= 0 ? uv : 0.f;
     }
@@ -800,7 +796,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) adjoint_tc_kernel(const unsigned 
                     e = fmaf(NFC_BT2, kr[0][i], e); e = fmaf(NFC_BT3, kr[1][i], e); e = fmaf(NFC_BT4, kr[2][i], e); e = fmaf(NFC_BT5, kr[3][i], e);
                     e = fmaf(NFC_BT6, kr[4][i], e); e = fmaf(NFC_BT7, k7[i], e);
                     e *= h;
-                    const float r = e / (P.abstol + fmaxf(fabsf(lam[i]), fabsf(lnew[i])) * P.reltol);
+                    const float r = fast_div(e, fmaf(fmaxf(fabsf(lam[i]), fabsf(lnew[i])), P.reltol, P.abstol));
                     part = fmaf(r, r, part);
                 }
                 S.part[q][c] = part;
