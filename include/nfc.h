@@ -163,14 +163,15 @@ int32_t nfc_get_adjoint_steps(nfc_handle* h, int32_t* out, int64_t n);
 
 /* Kernel selection and scratch budgets (defaults are chosen by batch size; the same names in upper case with the prefix NFC_ are read
  * from the environment at nfc_create / call time and win over the defaults):
- *   tc               0: FP32 SIMT kernels; 1: tensor-core kernels (default Chain only, the default there)
+ *   tc               0: FP32 SIMT kernels; 1: tensor-core kernels (the default where they exist: every call for the default Chain; nfc_rhs and
+ *                    the Tsit5 forward solve for conv-2 / conv-4 / deeper; none for the wider Chain)
  *   tc_tiles         0: pick by batch size; 1 / 2: one / two 128-column tiles in flight per CTA in the forward solve
  *   tc2_min_columns  batch size from which tc_tiles = 0 picks two tiles (default 98304)
  *   tc_record        0: forward (RECORD) pass of nfc_loss_grad on the FP32 SIMT kernel
  *   sched            0: columns served in input order; 1 (default): longest first from the previous call's step counts
  *   adj_small_max    batches up to this many columns run the one-column-per-CTA backward kernel (default 7400; 0 = never)
  *   adj_tc           0: batch backward pass on the FP32 SIMT kernel instead of the tensor-core kernel
- *   e2e_pieces       nfc_solve: pieces whose device->host copy overlaps the next piece's solve (0 = auto: 3 from 65536 columns)
+ *   e2e_pieces       nfc_solve: pieces whose device->host copy overlaps the next piece's solve (0 = auto: 2 from 16384, 3 from 49152 columns)
  *   tc_split         0 = FP16x2 operands (3 MMAs per fp32 product, needs |T_scaled| <= 128; default), 1 = BF16x3 (6 MMAs, fp32's range)
  *   range_fallback   1 (default): nfc_solve re-solves columns that ended with status 5 on the BF16x3 split, nfc_loss_grad (no communicator)
  *                    repeats a call that had such a column on the FP32 kernels; 0: status 5 is returned as it is (the *_dev calls always do)

@@ -951,7 +951,7 @@ int32_t nfc_solve(nfc_handle* h, const float* T0, const float* colp, const float
     h->last_launches = 0;
     // Large batches are solved in three pieces so that the device->host copy of one piece (the trajectories dominate the
     // end-to-end time: 1.08 GB for 65 536 columns x 129 saves) overlaps the solve of the next one (second stream; measured +32 % end to end).
-    int npieces = (B >= 65536) ? 3 : 1;
+    int npieces = B >= 49152 ? 3 : (B >= 16384 ? 2 : 1);
     if (h->e2e_pieces > 0) npieces = h->e2e_pieces;
     if (const char* e = getenv("NFC_E2E_PIECES")) npieces = std::max(1, std::min(8, atoi(e)));
     if (B < 8192 * npieces) npieces = 1;

@@ -88,7 +88,7 @@ __device__ __forceinline__ void rhs_init_group(const float* sW, float* ws, long 
         if (col < colEnd) out[col * NZ + lane] = f0[c];
     }
     if (MODE == 1) {
-        // Hairer-Wanner initial step (OrdinaryDiffEq ode_determine_initdt, order 5)
+        // Hairer-Wanner initial step as OrdinaryDiffEq codes it (ode_determine_initdt: exponent 1 / alg_order = 1/5 for Tsit5, not 1/(order+1))
         float dt0[CPW], d1[CPW], y1[CPW], f1[CPW];
 #pragma unroll
         for (int c = 0; c < CPW; ++c) {
@@ -107,7 +107,7 @@ __device__ __forceinline__ void rhs_init_group(const float* sW, float* ws, long 
             const float a = (f1[c] - f0[c]) / sk;
             const float d2 = sqrtf(warp_sum(a * a) * (1.f / NZ)) / dt0[c];
             const float m = fmaxf(d1[c], d2);
-            const float dt1 = (m <= 1e-15f) ? fmaxf(1e-6f, dt0[c] * 1e-3f) : powf(10.0f, -(2.0f + log10f(m)) / 6.0f);
+            const float dt1 = (m <= 1e-15f) ? fmaxf(1e-6f, dt0[c] * 1e-3f) : powf(10.0f, -(2.0f + log10f(m)) / 5.0f);
             float dt = fminf(fminf(100.0f * dt0[c], dt1), tf);
             if (fixed_dt > 0.f) dt = fixed_dt;
             const long long col = col0 + c;

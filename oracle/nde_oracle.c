@@ -178,7 +178,7 @@ static float initial_dt(const net_t *n, const float *th, const float *u0, const 
     for (int i = 0; i < N; ++i) { float sk = abstol + fabsf(u0[i]) * reltol; a[i] = (f1[i] - f0[i]) / sk; }
     float d2 = rmsf(a, N) / dt0;
     float m = fmaxf(d1, d2);
-    float dt1 = (m <= 1e-15f) ? fmaxf(1e-6f, dt0 * 1e-3f) : powf(10.0f, -(2.0f + log10f(m)) / 6.0f);
+    float dt1 = (m <= 1e-15f) ? fmaxf(1e-6f, dt0 * 1e-3f) : powf(10.0f, -(2.0f + log10f(m)) / 5.0f);
     return fminf(fminf(100.0f * dt0, dt1), dtmax);
 }
 

@@ -175,7 +175,7 @@ def _rms(x):
 
 
 def initial_dt(f, u0, f0, reltol, abstol, dtmax, dtype):
-    """Hairer-Wanner initial step as in OrdinaryDiffEq `ode_determine_initdt` (order 5) [UPSTREAM]."""
+    """Hairer-Wanner initial step as in OrdinaryDiffEq `ode_determine_initdt` [UPSTREAM]: the exponent divides by the algorithm order (get_current_alg_order = 5 for Tsit5), not by order + 1 as in Hairer's book."""
     sk = abstol + np.abs(u0) * reltol
     d0 = _rms(u0 / sk)
     d1 = _rms(f0 / sk)
@@ -187,7 +187,7 @@ def initial_dt(f, u0, f0, reltol, abstol, dtmax, dtype):
     m = np.maximum(d1, d2)
     tiny = m <= 1e-15
     dt1 = np.where(tiny, np.maximum(dtype(1e-6), dt0 * dtype(1e-3)),
-                   np.power(dtype(10.0), -(2 + np.log10(np.where(tiny, 1, m))) / 6)).astype(dtype)
+                   np.power(dtype(10.0), -(2 + np.log10(np.where(tiny, 1, m))) / 5)).astype(dtype)
     return np.minimum(np.minimum(100 * dt0, dt1), dtmax).astype(dtype)
 
 
