@@ -1,8 +1,8 @@
 """Per-source-line executed-instruction / stall histogram of one kernel: joins `ncu --page source --csv` (per SASS instruction, in
 address order) with `nvdisasm -g -gi` of the same build (source line + inlining chain per SASS instruction).
 
-usage: python tools/ncu_line_hist.py REPORT.ncu-rep MANGLED_KERNEL_SUBSTRING [lo hi] [--so path/to/libnfc_b200.so]
-  lo hi: attribute every instruction to the OUTERMOST line inside [lo, hi] of nfc_tc.cuh (i.e. the statement of the kernel body that the
+usage: python tools/ncu_line_hist.py REPORT.ncu-rep MANGLED_KERNEL_SUBSTRING [lo hi] [--so path/to/libnfc_b200.so] [--file nfc_tc.cuh]
+  lo hi: attribute every instruction to the OUTERMOST line inside [lo, hi] of --file (i.e. the statement of the kernel body that the
          inlined helpers were called from); without them the innermost line is used.
 Prints lines sorted by executed warp-instructions with their share and stall samples."""
 import collections, csv, io, os, re, subprocess, sys, tempfile
@@ -11,9 +11,13 @@ args = [a for a in sys.argv[1:] if not a.startswith("--")]
 rep, kname = args[0], args[1]
 lo, hi = (int(args[2]), int(args[3])) if len(args) >= 4 else (None, None)
 so = "neuralfreeconvection.jl_b200/libnfc_b200.so"
+srcfile = "nfc_tc.cuh"
 for i, a in enumerate(sys.argv):
     if a == "--so":
         so = sys.argv[i + 1]
+    if a == "--file":
+        srcfile = sys.argv[i + 1]
+args = [a for a in args if a not in (so, srcfile) or a == args[0] or a == args[1]]
 per_n = float(os.environ.get("PER", "0")) or None          # divide counts by this (e.g. warp-steps) for per-unit numbers
 
 tmp = tempfile.mkdtemp()
@@ -58,7 +62,7 @@ def key(ch):
     if lo is None:
         return ch[0] if ch else ("?", 0)
     for f, n in reversed(ch):       # outermost first
-        if f == "nfc_tc.cuh" and lo <= n <= hi:
+        if f == srcfile and lo <= n <= hi:
             return (f, n)
     return ch[-1] if ch else ("?", 0)
 
