@@ -302,6 +302,34 @@ def main():
         except Exception as e:
             cold = {"error": str(e)}
 
+    # ---------------- BASELINE config 5 (architecture sweep): the other Chains' forward solve on the same 65 536 columns ----------------
+    other_chains = None
+    if rank == 0 and world == 1:
+        other_chains = {}
+        for arch in ("conv-2", "conv-4", "dense-deeper", "dense-wider"):
+            try:
+                NNa = nfc_b200.named_chain(arch, seed=0)
+                for p_ in NNa.params():
+                    p_ *= 1e-5
+                tha, _ = nfc_b200.destructure(NNa)
+                ha = nfc_b200.Handle(NNa.conv_width, NNa.dense_spec, 1, sv, device=local_rank)
+                ha.set_weights(tha)
+                for _ in range(2):
+                    ha.solve_dev(T0, colp, glob, Tout, na, nr, st, stream=stream)
+                torch.cuda.synchronize()
+                e0.record()
+                ha.solve_dev(T0, colp, glob, Tout, na, nr, st, stream=stream)
+                e1.record()
+                torch.cuda.synchronize()
+                ca = ha.counters()
+                ms_a = e0.elapsed_time(e1)
+                nsteps_a = int(ca["steps_accepted"] + ca["steps_rejected"])
+                other_chains[arch] = {"ms": ms_a, "value": nsteps_a / (ms_a * 1e-3), "unit": UNIT,
+                                      "kernel_path": "tcgen05" if (use_tc and arch != "dense-wider") else "simt", "bad_status": int((st != 0).sum().item())}
+                ha.close()
+            except Exception as e:
+                other_chains[arch] = {"error": str(e)}
+
     # ---------------- second BASELINE metric: adjoint gradient, seconds per epoch (rank 0, one GPU) ----------------
     # epoch = one loss + gradient over the batch (src/training.jl:45-48,70): (a) BASELINE config 3, the 9 training simulations (one column per
     # CTA, FP32); (b) the config-2 batch (65536 columns): the tensor-core backward kernel (csrc/nfc_adjoint_tc.cuh).
@@ -454,7 +482,7 @@ def main():
                        "l2": "outputs (1.08 GB/step) exceed the 126 MB L2; no explicit flush", "parallelism": f"columns sharded x{world}, no collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(cnt["kernel_launches"]) * args.steps, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline, "adjoint": adjoint,
-            "config4": config4, "cold_call": cold, "cpu_affinity": affinity}
+            "config4": config4, "cold_call": cold, "other_chains": other_chains, "cpu_affinity": affinity}
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()

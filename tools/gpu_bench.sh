@@ -17,5 +17,6 @@ print("value %.4g e2e %.4g ms/step %.3f frac %.3f" % (d["value"], d["e2e"]["valu
 print("cold", d.get("cold_call"))
 print("adjoint", json.dumps(d.get("adjoint"))[:1500])
 print("config4", json.dumps(d.get("config4"))[:2500])
+print("other chains", json.dumps(d.get("other_chains")))
 print("cpu", d.get("cpu_baseline"), d.get("cpu_affinity"))
 PY
