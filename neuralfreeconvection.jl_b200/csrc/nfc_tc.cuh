@@ -687,14 +687,14 @@ __device__ __forceinline__ void conv_front(TcShared* S, const float* cw, const f
 // MMA warp main loop: three layers per Chain evaluation until the column threads raise `stop`.  Layer 1 (K = 32) is issued in one go;
 // the hidden-to-hidden and the output layer in four sub-batches (k-steps 2s, 2s+1) as the column threads publish their sub-chunks.
 template <class SP, int LAYER>
-__device__ __forceinline__ void mma_issue_subs(TcShared* S, uint32_t smem_img, int& pa, int (&pq)[3], long long& t_wait) {
+__device__ __forceinline__ void mma_issue_subs(TcShared* S, uint32_t tb0, uint32_t smem_img, int& pa, int (&pq)[3], long long& t_wait) {
     const long long c0 = clock64();
     mbar_wait(&S->bar_a, pa); pa ^= 1;
     fence_after_sync();
     t_wait += clock64() - c0;
     // The operand addresses must be re-derived inside the loop (an add on a uniform register per MMA): as loop invariants the
     // compiler hoists them all and, with the 32 registers this warp keeps, spills them -- a local-memory load in front of the MMA.
-    uint32_t tb = *reinterpret_cast<volatile uint32_t*>(&S->tmem_base), img = smem_img;
+    uint32_t tb = tb0, img = smem_img;
     asm volatile("" : "+r"(tb), "+r"(img));
     SP::template issue<LAYER, 0>(tb, img, S->nprod);
     mbar_wait(&S->bar_q[0], pq[0]); pq[0] ^= 1;
@@ -717,24 +717,25 @@ __device__ __forceinline__ void mma_warp_loop(TcShared* S, uint32_t smem_img, in
     if (lane == 0) {
         int pa = 0, pq[3] = {0, 0, 0};
         long long tw[3] = {0, 0, 0}, ti[3] = {0, 0, 0}, n = 0;
+        const uint32_t tb0 = S->tmem_base;          // read once; the empty asm statements below keep the derived operand addresses inside the loop
         while (true) {
             long long c0 = clock64();
             mbar_wait(&S->bar_a, pa); pa ^= 1;
             if (*reinterpret_cast<volatile int*>(&S->stop)) break;
             fence_after_sync();
             long long c1 = clock64();
-            uint32_t tb = *reinterpret_cast<volatile uint32_t*>(&S->tmem_base), img = smem_img;
+            uint32_t tb = tb0, img = smem_img;
             asm volatile("" : "+r"(tb), "+r"(img));
             SP::template issue<0, 0>(tb, img, S->nprod);
             mma_commit(&S->bar_d);
             long long c2 = clock64();
             tw[0] += c1 - c0; ti[0] += c2 - c1;
             long long w = 0;
-            mma_issue_subs<SP, 1>(S, smem_img, pa, pq, w);
-            if constexpr (SP::NH == 3) mma_issue_subs<SP, 2>(S, smem_img, pa, pq, w);      // third hidden layer (deeper Chain)
+            mma_issue_subs<SP, 1>(S, tb0, smem_img, pa, pq, w);
+            if constexpr (SP::NH == 3) mma_issue_subs<SP, 2>(S, tb0, smem_img, pa, pq, w);      // third hidden layer (deeper Chain)
             c1 = clock64(); tw[1] += w; ti[1] += c1 - c2 - w;
             w = 0;
-            mma_issue_subs<SP, SP::NH>(S, smem_img, pa, pq, w);                            // output layer
+            mma_issue_subs<SP, SP::NH>(S, tb0, smem_img, pa, pq, w);                            // output layer
             c2 = clock64(); tw[2] += w; ti[2] += c2 - c1 - w;
             n += 1;
         }

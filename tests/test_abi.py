@@ -137,3 +137,67 @@ def test_on_disk_formats_round_trip(tmp_path):
     assert np.array_equal(s["nde"][2]["T"], T + 2) and np.array_equal(s["true"][1]["wT"], T[:, :4]) and s["solution_loss_history"][1].shape == (3, 5)
     with pytest.raises(ValueError):
         F.save_solutions(sol, NN, Ts, wTs, {"les": {}})
+
+
+def _c_prototypes():
+    """{name: [C parameter types]} of every function include/nfc.h declares."""
+    import re
+    src = open(os.path.join(ROOT, "include", "nfc.h")).read()
+    src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int32_t|int64_t|const char\*)\s+(nfc_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+        params = [p.strip() for p in m.group(2).replace("\n", " ").split(",") if p.strip() and p.strip() != "void"]
+        protos[m.group(1)] = [re.sub(r"\s+\w+$", "", p).replace("const ", "").strip() for p in params]      # drop the parameter name
+    return protos
+
+
+def _julia_ccalls():
+    """[(name, [Julia argument types])] of every ccall in julia/FreeConvectionB200.jl."""
+    import re
+    src = open(os.path.join(ROOT, "julia", "FreeConvectionB200.jl")).read()
+    out = []
+    for m in re.finditer(r"ccall\(\(:(nfc_\w+), LIB\),\s*\w+,\s*\(", src):
+        i, depth = m.end(), 1
+        while depth:                                   # the type tuple, with nested braces / parentheses
+            depth += src[i] in "({"
+            depth -= src[i] in ")}"
+            i += 1
+        tup = src[m.end():i - 1]
+        types, cur, d = [], "", 0
+        for ch in tup:
+            if ch == "," and d == 0:
+                types.append(cur.strip()); cur = ""
+            else:
+                d += ch in "({"; d -= ch in ")}"; cur += ch
+        if cur.strip():
+            types.append(cur.strip())
+        out.append((m.group(1), types))
+    return out
+
+
+def test_julia_ccalls_match_the_header():
+    """The Julia host cannot run in this image: at least every ccall in julia/FreeConvectionB200.jl must name a function of include/nfc.h
+    with the same number of arguments and ABI-compatible types (pointer <-> Ptr / Ref, int32_t <-> Int32, int64_t <-> Int64, float <-> Float32)."""
+    protos = _c_prototypes()
+    calls = _julia_ccalls()
+    assert len(calls) >= 12 and len(protos) >= 25
+    kind = lambda c: "ptr" if c.endswith("*") else {"int32_t": "Int32", "int64_t": "Int64", "float": "Float32", "double": "Float64"}[c]
+    for name, jt in calls:
+        assert name in protos, f"{name} is not declared in include/nfc.h"
+        ct = protos[name]
+        assert len(ct) == len(jt), (name, ct, jt)
+        for c, j in zip(ct, jt):
+            k = kind(c)
+            if k == "ptr":
+                assert j.startswith(("Ptr{", "Ref{")) or j == "Cstring", (name, c, j)
+            else:
+                assert j == k, (name, c, j)
+    # the struct the shim passes to nfc_create has the header's field order
+    import re
+    jl = open(os.path.join(ROOT, "julia", "FreeConvectionB200.jl")).read()
+    body = re.search(r"struct NfcConfig\n(.*?)\nend", jl, flags=re.S).group(1)
+    jfields = [f.split("::")[0].strip() for l in body.split("\n") for f in l.split(";") if "::" in f]
+    hdr = re.sub(r"/\*.*?\*/", " ", open(os.path.join(ROOT, "include", "nfc.h")).read(), flags=re.S)
+    cbody = re.search(r"typedef struct nfc_config \{(.*?)\} nfc_config;", hdr, flags=re.S).group(1)
+    cfields = [re.sub(r"\[.*?\]", "", f).strip().split()[-1].lstrip("*") for f in cbody.split(";") if f.strip()]
+    assert jfields == cfields, (jfields, cfields)
