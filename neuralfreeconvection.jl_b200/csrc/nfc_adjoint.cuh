@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(ADJ_NW * 32, 1) adjoint_kernel(const AdjParams
                     while (n > 0 && ts < tn) { --n; tn = base[(long long)n * TAPE_STRIDE + TAPE_T]; hn = base[(long long)n * TAPE_STRIDE + TAPE_H]; }
                     while (n + 1 < len && ts > tn + hn) { ++n; tn = base[(long long)n * TAPE_STRIDE + TAPE_T]; hn = base[(long long)n * TAPE_STRIDE + TAPE_H]; }
                     sl->ipos[lane] = n;
-                    th = fminf(fmaxf((ts - tn) / hn, 0.f), 1.f);
+                    th = fminf(fmaxf(fast_div(ts - tn, hn), 0.f), 1.f);
                 }
                 sl->th[lane] = th; sl->hn[lane] = hn;
             }
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__(ADJ_NW * 32, 1) adjoint_kernel(const AdjParams
                 // quadrature weight folded into the back-propagated vector (stage 7 carries weight 0: propagate unscaled, skip dW)
                 const float sgn = sl->mode[c] ? -1.f : 1.f;
                 const float w = (s < 6 && col >= 0) ? sgn * hc * bs : 1.f;
-                winv[c] = 1.f / w;
+                winv[c] = fast_div(1.f, w);
                 const float lw = w * ls[c];
                 const float lwlo = __shfl_up_sync(FULL, lw, 1);
                 const float ulo = __shfl_up_sync(FULL, u, 1);
@@ -494,10 +494,9 @@ __global__ void __launch_bounds__(ADJ_NW * 32, 1) adjoint_kernel(const AdjParams
             e = fmaf(NFC_BT2, kap[1][c], e); e = fmaf(NFC_BT3, kap[2][c], e); e = fmaf(NFC_BT4, kap[3][c], e);
             e = fmaf(NFC_BT5, kap[4][c], e); e = fmaf(NFC_BT6, kap[5][c], e); e = fmaf(NFC_BT7, kap[6][c], e);
             e *= sl->h[c];
-            const float sc = P.abstol + fmaxf(fabsf(lam[c]), fabsf(ls[c])) * P.reltol;
-            const float r = e / sc;
+            const float r = fast_div(e, fmaf(fmaxf(fabsf(lam[c]), fabsf(ls[c])), P.reltol, P.abstol));      // fast controller arithmetic: one for the three backward kernels
             const float ss = warp_sum(r * r);
-            if (lane == c) ee = sqrtf(ss * (1.f / NZ));
+            if (lane == c) ee = fast_sqrt(ss * (1.f / NZ));
         }
         if (lane < CPW && sl->col[lane] >= 0) {
             int fl = sl->flag[lane];
@@ -511,11 +510,7 @@ __global__ void __launch_bounds__(ADJ_NW * 32, 1) adjoint_kernel(const AdjParams
                 if (P.fixed_dt > 0.f) { accept = true; dtnew = P.fixed_dt; }
                 else if (!isfinite(ee)) { accept = false; dtnew = 0.2f * h; }
                 else {
-                    const float q11 = powf(ee, 0.14f);
-                    float q = q11 / powf(sl->qold[lane], 0.08f);
-                    q = fmaxf(0.1f, fminf(5.0f, q / 0.9f));
-                    accept = ee <= 1.0f;
-                    dtnew = accept ? h / q : h / fminf(5.0f, q11 / 0.9f);
+                    pi_controller(ee, sl->qold[lane], h, accept, dtnew);
                 }
                 if (accept) {
                     fl |= AFL_ACCEPT;

@@ -139,12 +139,12 @@ __global__ void __launch_bounds__(NT, 1) adjoint_small_kernel(const float* __res
                     if (lane == 0) { S.ipos = n; S.icached = n; S.tn = tn; S.hn = hn; }
                     __syncwarp();
                 }
-                const float th = fminf(fmaxf((ts - tn) / hn, 0.f), 1.f);
+                const float th = fminf(fmaxf(fast_div(ts - tn, hn), 0.f), 1.f);
                 const float u = fmaf(hn, th * fmaf(th, fmaf(th, fmaf(th, sm[O_TAPE + 4 * NZ + lane], sm[O_TAPE + 3 * NZ + lane]), sm[O_TAPE + 2 * NZ + lane]),
                                                    sm[O_TAPE + NZ + lane]), sm[O_TAPE + lane]);
                 const float sgn = S.mode ? -1.f : 1.f;
                 const float w = do_dw ? sgn * hc * c_adj_b[s] : 1.f;
-                winv = 1.f / w;
+                winv = fast_div(1.f, w);
                 const float lw = w * ls;
                 const float lwlo = __shfl_up_sync(FULL, lw, 1);
                 const float ulo = __shfl_up_sync(FULL, u, 1);
@@ -268,9 +268,8 @@ __global__ void __launch_bounds__(NT, 1) adjoint_small_kernel(const float* __res
             e = fmaf(NFC_BT2, kap[1], e); e = fmaf(NFC_BT3, kap[2], e); e = fmaf(NFC_BT4, kap[3], e);
             e = fmaf(NFC_BT5, kap[4], e); e = fmaf(NFC_BT6, kap[5], e); e = fmaf(NFC_BT7, kap[6], e);
             e *= S.h;
-            const float sc = P.abstol + fmaxf(fabsf(lam), fabsf(ls)) * P.reltol;
-            const float r = e / sc;
-            const float ee = sqrtf(warp_sum(r * r) * (1.f / NZ));
+            const float r = fast_div(e, fmaf(fmaxf(fabsf(lam), fabsf(ls)), P.reltol, P.abstol));
+            const float ee = fast_sqrt(warp_sum(r * r) * (1.f / NZ));
             __syncwarp();
             if (lane == 0) {
                 int fl = S.flag;
@@ -284,11 +283,7 @@ __global__ void __launch_bounds__(NT, 1) adjoint_small_kernel(const float* __res
                     if (P.fixed_dt > 0.f) { accept = true; dtnew = P.fixed_dt; }
                     else if (!isfinite(ee)) { accept = false; dtnew = 0.2f * h; }
                     else {
-                        const float q11 = powf(ee, 0.14f);
-                        float q = q11 / powf(S.qold, 0.08f);
-                        q = fmaxf(0.1f, fminf(5.0f, q / 0.9f));
-                        accept = ee <= 1.0f;
-                        dtnew = accept ? h / q : h / fminf(5.0f, q11 / 0.9f);
+                        pi_controller(ee, S.qold, h, accept, dtnew);
                     }
                     if (accept) {
                         fl |= AFL_ACCEPT;

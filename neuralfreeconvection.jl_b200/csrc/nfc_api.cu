@@ -157,6 +157,12 @@ int do_diagnose(nfc_handle* h, const float* Tsol, const float* colp, float* wT, 
     return 0;
 }
 
+// small batches of the default Chain: one column per CTA (nfc_forward_small.cuh; defined below, after the kernel's header)
+int launch_small_forward(nfc_handle* h, const SolveParams& P, cudaStream_t st, bool record);
+inline bool small_forward_batch(const nfc_handle* h, long long B) {
+    return h->arch == ARCH_DEFAULT && h->use_tc && h->tc_tiles == 0 && h->fwd_small_max > 0 && B <= h->fwd_small_max;
+}
+
 // forward solve (RECORD=false) or forward pass of loss_grad (RECORD=true)
 // hist_total / hist_off: the per-column step history (longest-first schedule) is kept for the whole host-level batch; a call that
 // solves the batch in pieces passes the batch size and this piece's offset
@@ -219,7 +225,10 @@ int launch_solve(nfc_handle* h, SolveParams& P, cudaStream_t st, bool reset_coun
                                                                     P.reltol, P.abstol, P.tf, P.fixed_dt);
     NFC_CUDA(h, cudaGetLastError());
     // tensor-core kernels: the forward solve always (default Chain), the RECORD pass of loss_grad with the FP16x2 split (NFC_TC_RECORD=0: SIMT)
-    if (h->use_tc && h->arch != ARCH_DEFAULT && tc_forward_arch(h->arch) && !RECORD && h->tc_fp16) {
+    if (small_forward_batch(h, B)) {
+        P.wpack = nullptr;
+        if (int rc = launch_small_forward(h, P, st, RECORD)) return rc;
+    } else if (h->use_tc && h->arch != ARCH_DEFAULT && tc_forward_arch(h->arch) && !RECORD && h->tc_fp16) {
         // conv-2 / conv-4 / deeper Chain: one-tile tensor-core forward solve (the RECORD pass of loss_grad stays on the FP32 SIMT kernel)
         const int gridt = (int)std::min<long long>(h->num_sms, (B + tc::TILE - 1) / tc::TILE);
 #define NFC_SOLVE_TC(SP) tc::solve_tc_kernel<SP, false><<<gridt, tc::NTHREADS, SP::IMG, st>>>(h->d_wimg.p, P)
@@ -302,6 +311,15 @@ int nfc_launch_record(nfc_handle* h, nfc::SolveParams& P, cudaStream_t st, bool 
 }
 #include "nfc_adjoint.cuh"
 #include "nfc_adjoint_small.cuh"
+#include "nfc_forward_small.cuh"
+namespace {
+int launch_small_forward(nfc_handle* h, const SolveParams& P, cudaStream_t st, bool record) {
+    const int grid = (int)std::min<long long>(h->num_sms, P.B);
+    if (record) nfc::fws::solve_small_kernel<true><<<grid, nfc::fws::NT, nfc::fws::SMEM_BYTES, st>>>(h->d_theta.p, P);
+    else nfc::fws::solve_small_kernel<false><<<grid, nfc::fws::NT, nfc::fws::SMEM_BYTES, st>>>(h->d_theta.p, P);
+    return 0;
+}
+}  // namespace
 template <class N>
 bool adjoint_small_launch(nfc_handle* h, const nfc::AdjParams& A, int64_t nb, cudaStream_t st) {
     if constexpr (std::is_same<N, nfc::adjs::NetD>::value) {
@@ -645,6 +663,9 @@ int32_t nfc_create(const nfc_config* cfg, nfc_handle** out) {
         if (const char* e8 = getenv("NFC_TC_RECORD")) h->tc_record = atoi(e8) != 0;         // 0: the forward pass of loss_grad stays on the FP32 SIMT kernel
         if (const char* e2 = getenv("NFC_SCHED")) h->use_sched = atoi(e2) != 0;
         if (cudaFuncSetAttribute(adjs::adjoint_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)adjs::SMEM_BYTES) != cudaSuccess) { h->err = "cudaFuncSetAttribute(adjoint_small) failed"; return bail(-10); }
+        if (cudaFuncSetAttribute(fws::solve_small_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fws::SMEM_BYTES) != cudaSuccess ||
+            cudaFuncSetAttribute(fws::solve_small_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fws::SMEM_BYTES) != cudaSuccess) { h->err = "cudaFuncSetAttribute(solve_small) failed"; return bail(-10); }
+        if (const char* e10 = getenv("NFC_FWD_SMALL_MAX")) h->fwd_small_max = atoll(e10);   // 0 disables the one-column-per-CTA forward kernel
         if (const char* e7 = getenv("NFC_ADJ_SMALL_MAX")) h->adj_small_max = atoll(e7);     // 0 disables the one-column-per-CTA adjoint kernel
         if (adjoint_tc_setup(h)) return bail(-10);
         if (const char* e9 = getenv("NFC_ADJ_TC")) h->adj_tc = atoi(e9) != 0;               // 0: batch backward pass on the FP32 SIMT kernel
@@ -790,6 +811,7 @@ int32_t nfc_set_option(nfc_handle* h, const char* name, int64_t value) {
     else if (n == "tc_record") h->tc_record = value != 0;
     else if (n == "sched") h->use_sched = value != 0;
     else if (n == "adj_small_max") h->adj_small_max = value;
+    else if (n == "fwd_small_max") h->fwd_small_max = value;
     else if (n == "adj_tc") h->adj_tc = value != 0;
     else if (n == "e2e_pieces") { if (value < 0 || value > 8) return fail(h, -2, "e2e_pieces: 0 (auto) .. 8"); h->e2e_pieces = (int)value; }
     else if (n == "range_fallback") h->range_fallback = value != 0;
@@ -800,7 +822,7 @@ int32_t nfc_set_option(nfc_handle* h, const char* name, int64_t value) {
         return switch_split(h, value == 0);
     }
     else if (n == "tape_gib") { if (value < 0) return fail(h, -2, "tape_gib: >= 0 (0 = default 48)"); h->tape_gib = (double)value; }
-    else return fail(h, -2, "unknown option '%s' (tc, tc_tiles, tc_split, range_fallback, tc2_min_columns, tc_record, sched, adj_small_max, adj_tc, e2e_pieces, tape_gib)", name);
+    else return fail(h, -2, "unknown option '%s' (tc, tc_tiles, tc_split, range_fallback, tc2_min_columns, tc_record, sched, adj_small_max, fwd_small_max, adj_tc, e2e_pieces, tape_gib)", name);
     return 0;
 }
 

@@ -80,6 +80,28 @@ __device__ __forceinline__ void tsit5_btheta(float th, float (&b)[7]) {
     b[6] = 1.5f * t2 + (-4.0f) * t3 + 2.5f * t4;
 }
 
+// Step-boundary arithmetic shared by the adaptive kernels of the default path (one- / two-tile / small forward kernels agree with their
+// RECORD instantiations; the three backward kernels with each other).  Divisions and the square root of the
+// controller are the fast approximations (MUFU.RCP / MUFU.SQRT + one multiply, <= 2 ulp): the step-size sequence does not need more, the
+// accept test compares the error norm itself, and the position inside a step (theta of the dense output) is good to 1e-7.  The IEEE
+// sequences they replace were ~10 instructions each on the serial path every thread walks between two barriers.
+__device__ __forceinline__ float fast_div(float a, float b) { return __fdividef(a, b); }
+__device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// squared scaled error of one level: (h * sum btilde_j k_j / (abstol + max(|u|, |u_new|) reltol))^2 accumulated into `part`
+__device__ __forceinline__ float err_term(float part, float e6, float k7, float hs, float u, float y, float abstol, float reltol) {
+    const float ei = fmaf(NFC_BT7, k7, e6) * hs;
+    const float r = fast_div(ei, fmaf(fmaxf(fabsf(u), fabsf(y)), reltol, abstol));
+    return fmaf(r, r, part);
+}
+// OrdinaryDiffEq's PI controller (beta1 = 7/50, beta2 = 2/25, gamma = 9/10, qmin = 1/5, qmax = 10; reject: dt / min(1/qmin, q11 / gamma))
+__device__ __forceinline__ void pi_controller(float ee, float qold, float hs, bool& accept, float& dtnew) {
+    const float q11 = __powf(ee, 0.14f);
+    float qq = fast_div(q11, __powf(qold, 0.08f));
+    qq = fmaxf(0.1f, fminf(5.0f, qq * (1.0f / 0.9f)));
+    accept = ee <= 1.0f;
+    dtnew = accept ? fast_div(hs, qq) : fast_div(hs, fminf(5.0f, q11 * (1.0f / 0.9f)));
+}
+
 // ---- network shapes ---------------------------------------------------------------------------------
 // All five reference Chains (train_free_convection_nde.jl:125-153) are
 //   [Conv((CONVW,1),1=>1,relu)] -> Dense(IN0,H,relu) -> (NHID-1) x Dense(H,H,relu) -> Dense(H,Nz-1)

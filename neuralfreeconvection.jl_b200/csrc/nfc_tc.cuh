@@ -852,26 +852,11 @@ namespace tc {
 // k_j (j = 2..7) chunk of this thread in tensor memory: column TM_K + 32 (j-2) + 8 q, 8 cells
 __device__ __forceinline__ uint32_t kaddr(uint32_t tl, int j, int q) { return tl + TM_K + 32 * (j - 2) + 8 * q; }
 
-// Step-boundary arithmetic shared by the one- and the two-tile kernel (they agree bit for bit).  Divisions and the square root of the
-// controller are the fast approximations (MUFU.RCP / MUFU.SQRT + one multiply, <= 2 ulp): the step-size sequence does not need more, the
-// accept test compares the error norm itself, and the position inside a step (theta of the dense output) is good to 1e-7.  The IEEE
-// sequences they replace were ~10 instructions each on the serial path every thread walks between two barriers.
-__device__ __forceinline__ float fast_div(float a, float b) { return __fdividef(a, b); }
-__device__ __forceinline__ float fast_sqrt(float x) { float r; asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-// squared scaled error of one level: (h * sum btilde_j k_j / (abstol + max(|u|, |u_new|) reltol))^2 accumulated into `part`
-__device__ __forceinline__ float err_term(float part, float e6, float k7, float hs, float u, float y, float abstol, float reltol) {
-    const float ei = fmaf(NFC_BT7, k7, e6) * hs;
-    const float r = fast_div(ei, fmaf(fmaxf(fabsf(u), fabsf(y)), reltol, abstol));
-    return fmaf(r, r, part);
-}
-// OrdinaryDiffEq's PI controller (beta1 = 7/50, beta2 = 2/25, gamma = 9/10, qmin = 1/5, qmax = 10; reject: dt / min(1/qmin, q11 / gamma))
-__device__ __forceinline__ void pi_controller(float ee, float qold, float hs, bool& accept, float& dtnew) {
-    const float q11 = __powf(ee, 0.14f);
-    float qq = fast_div(q11, __powf(qold, 0.08f));
-    qq = fmaxf(0.1f, fminf(5.0f, qq * (1.0f / 0.9f)));
-    accept = ee <= 1.0f;
-    dtnew = accept ? fast_div(hs, qq) : fast_div(hs, fminf(5.0f, q11 * (1.0f / 0.9f)));
-}
+// step-boundary arithmetic (fast_div, fast_sqrt, err_term, pi_controller): nfc_device.cuh, shared by every adaptive kernel
+using nfc::err_term;
+using nfc::fast_div;
+using nfc::fast_sqrt;
+using nfc::pi_controller;
 constexpr int SAVE_SMEM = 2048;           // save times kept in shared memory by the one-tile kernel (longer lists are read from global memory)
 
 // acc[i] = sum_j coef[j-1] * k_j[i] over j = 1..nk (k1 in registers, k2..k6 from tensor memory), one fma chain in the order of j.

@@ -122,8 +122,20 @@ def test_solve_columns_are_independent_and_order_free(nfc, gpu_ok):
     rp = h.solve(d["T0"][perm], d["colp"][perm], d["glob"])
     assert np.array_equal(rp["T"], r["T"][perm])
     assert np.array_equal(rp["naccept"], r["naccept"][perm])
+    h.set_option("fwd_small_max", 0)                     # same (tensor-core) kernel for a batch of one
     r1 = h.solve(d["T0"][5:6], d["colp"][5:6], d["glob"])
     assert np.array_equal(r1["T"][0], r["T"][5])
+    # small batches run one column per CTA (nfc_forward_small.cuh, FP32): its own arithmetic, order-free as well, and within the
+    # trajectory tolerance of the tensor-core kernel and of the oracle
+    h.set_option("fwd_small_max", 148)
+    sub = np.arange(100)
+    s1 = h.solve(d["T0"][sub], d["colp"][sub], d["glob"])
+    s2 = h.solve(d["T0"][sub[::-1]], d["colp"][sub[::-1]], d["glob"])
+    assert np.array_equal(s2["T"], s1["T"][::-1]) and np.array_equal(s2["naccept"], s1["naccept"][::-1])
+    assert not np.array_equal(s1["T"], r["T"][sub]) and (s1["status"] == 0).all()
+    assert rel_l2(s1["T"], r["T"][sub]).max() < 2 * TRAJ_TOL
+    c = CO.solve(d["T0"][:24], O.glorot_theta(cw, layers, 2, 0.3), cw, layers, d["colp"][:24], d["glob"], sv)
+    assert rel_l2(s1["T"][:24], c["T"]).max() < TRAJ_TOL
 
 
 def test_solve_edge_cases(nfc, gpu_ok):
@@ -284,8 +296,10 @@ def test_tensor_core_out_of_range_input_is_flagged_or_resolved(nfc, gpu_ok, monk
     assert r["status"][17] == s["status"][17] == 0
     assert rel_l2(r["T"][17:18], s["T"][17:18]).max() < TRAJ_TOL
     assert abs(int(r["naccept"][17]) - int(s["naccept"][17])) <= 0.05 * s["naccept"][17] + 2
-    # loss + gradient: the whole call is repeated on the FP32 kernels when a column left the range
+    # loss + gradient: the whole call is repeated on the FP32 kernels when a column left the range (a batch this small would run the FP32
+    # one-column-per-CTA forward kernel anyway, which has no range bound: switched off to reach the tensor-core RECORD pass)
     h.set_option("tc", 1)
+    h.set_option("fwd_small_max", 0)
     Ttrue = np.ascontiguousarray(ok["T"] + 0.05, dtype=np.float32)
     g = h.loss_grad(T0[:32], d["colp"][:32], d["glob"], Ttrue[:32])
     h.set_option("tc", 0)

@@ -16,7 +16,11 @@ for arch, split in (("dense-default", "fp16"), ("dense-default", "bf16"), ("conv
     f = h.rhs(d["T0"], d["colp"], d["glob"])
     r = h.solve(d["T0"], d["colp"], d["glob"])
     w = h.diagnose_flux(r["T"], d["colp"])
-    g = h.loss_grad(d["T0"][:70], d["colp"][:70], d["glob"], r["T"][:70] * 0.99)
+    g = h.loss_grad(d["T0"][:70], d["colp"][:70], d["glob"], r["T"][:70] * 0.99)      # <= 148 columns: one-column-per-CTA forward + backward kernels (default Chain)
+    h.set_option("adj_small_max", 0)
+    if arch == "dense-default":
+        h.set_option("fwd_small_max", 0)
+    g2 = h.loss_grad(d["T0"][:70], d["colp"][:70], d["glob"], r["T"][:70] * 0.99)    # batch kernels on the same columns
     Ts, wTs = syn.reference_scalings()
     e = h.embedded_solve(Ts.inv(d["T0"][:20]), wTs.inv(d["colp"][:20, 1]), [Ts.mu, Ts.sigma, wTs.mu, wTs.sigma], 256.0, 600.0, 1.0, 1e-3, 6, 2)
     print(arch, split, "ok", float(np.abs(f).max()), int(r["status"].max()), float(g["loss"]), e.shape, flush=True)
