@@ -447,7 +447,12 @@ def main():
             g = torch.empty(h.n_params, device=dev)
             ls = torch.zeros(2, dtype=torch.float64, device=dev)
             times = []
-            for it in range(2):
+            # adjoint tape: 344 KB per column as a dense tape (360 GB for this batch on one GPU) -> compact layout (tape_mode 0 picks it when the
+            # dense tape exceeds the budget): ~ 87 KB per column, three chunks inside the default 48 GiB budget on one GPU (one chunk with
+            # tape_gib = 100 is 0.5 % faster: profiles/r02_tape_layouts.txt)
+            tape_gib = 48
+            free_before = torch.cuda.mem_get_info(dev)[0]
+            for it in range(3):
                 barrier()
                 e0.record()
                 h.loss_grad_dev(lT0, lcolp, lglob, lTt, ls, g, lst, n_total_columns=CONFIG4_COLUMNS, stream=stream)
@@ -464,6 +469,9 @@ def main():
             lsh = ls.cpu()
             atf = float(ast[0].item()) * FLOPS_PER_ADJOINT_COLUMN_STEP / (float(ams[0].item()) * 1e-3) / 1e12
             config4["loss_grad"] = {"sec_per_epoch": float(ams[0].item()) * 1e-3, "first_call_sec": times[0] * 1e-3,
+                                    "tape": {"layout": "compact (rows per column from the previous call's step counts; first call: counting pass)" if nb * 512 * 672 > tape_gib * 2**30 else "dense",
+                                             "budget_gib": tape_gib, "scratch_gib_rank0": (free_before - torch.cuda.mem_get_info(dev)[0]) / 2**30,
+                                             "dense_tape_would_need_gib": nb * (512 * 672 + N_SAVE * 128) / 2**30},
                                     "allreduce_us_max_over_ranks": float(ams[1].item()) * 1e3 if dist is not None else 0.0,
                                     "collective": ("one grouped ncclAllReduce of 24735 floats + 2 doubles inside nfc_loss_grad_dev (C-ABI communicator), inside the timed region"
                                                    if dist is not None else "none (one GPU)"),

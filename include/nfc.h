@@ -177,7 +177,12 @@ int32_t nfc_get_adjoint_steps(nfc_handle* h, int32_t* out, int64_t n);
  *   tc_split         0 = FP16x2 operands (3 MMAs per fp32 product, needs |T_scaled| <= 128; default), 1 = BF16x3 (6 MMAs, fp32's range)
  *   range_fallback   1 (default): nfc_solve re-solves columns that ended with status 5 on the BF16x3 split, nfc_loss_grad (no communicator)
  *                    repeats a call that had such a column on the FP32 kernels; 0: status 5 is returned as it is (the *_dev calls always do)
- *   tape_gib         tape budget of nfc_loss_grad in GiB; larger batches are processed in chunks (0 = default 48) */
+ *   tape_gib         tape budget of nfc_loss_grad in GiB; larger batches are processed in chunks (0 = default 48)
+ *   tape_mode        layout of the adjoint tape: 1 = dense (every column owns adjoint_max_steps rows of 672 B: 344 KB at the default 512),
+ *                    2 = compact (a counting pass -- the forward solve on the RECORD pass's kernels, no outputs -- sizes every column's
+ *                    share: accepted steps + 2 rows, ~ 75 KB per column at 110 steps; adjoint_max_steps does not apply; the call
+ *                    synchronises its stream once to read the counts), 0 (default) = compact when the dense tape of the whole batch
+ *                    exceeds tape_gib, else dense */
 int32_t nfc_set_option(nfc_handle* h, const char* name, int64_t value);
 
 /* diagnostics: the forward tape of one column of the last nfc_loss_grad chunk -- per accepted step 168 floats: u_n[32], then the Tsit5

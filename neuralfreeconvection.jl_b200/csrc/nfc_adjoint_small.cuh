@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(NT, 1) adjoint_small_kernel(const float* __res
 #pragma unroll
                 for (int j = 0; j < 7; ++j) kap[j] = 0.f;
                 if (lane == 0) {
-                    const float* last = P.tape + ((long long)next * P.tape_cap + (len - 1)) * TAPE_STRIDE;
+                    const float* last = P.tape + (tape_row0(P, next) + (len - 1)) * TAPE_STRIDE;
                     S.t = P.tf; S.tstop = P.saveat[P.n_save - 2]; S.si = P.n_save - 2;
                     S.dt = P.fixed_dt > 0.f ? P.fixed_dt : last[TAPE_H]; S.qold = 1e-4f; S.nacc = 0; S.nrej = 0; S.flag = 0;
                     S.mode = 0; S.ipos = len - 1; S.tlen = len; S.status = ST_OK; S.dt_retry = 0.f;
@@ -124,7 +124,7 @@ __global__ void __launch_bounds__(NT, 1) adjoint_small_kernel(const float* __res
                 ls = fmaf(hc, acc, lam);
                 // u(t_s) from the forward tape: the interval's five coefficient rows are cached in shared memory
                 const float ts = (s == 6 && (S.flag & AFL_LAST)) ? S.tstop : S.t - c_adj_c[s] * hc;
-                const float* base = P.tape + (long long)S.col * P.tape_cap * TAPE_STRIDE;
+                const float* base = P.tape + tape_row0(P, S.col) * TAPE_STRIDE;
                 int n = S.ipos;
                 const int len = S.tlen;
                 float tn = S.tn, hn = S.hn;

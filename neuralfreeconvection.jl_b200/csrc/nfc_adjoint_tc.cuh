@@ -62,6 +62,7 @@ struct AtcShared {
     int col[TILE], si[TILE], nacc[TILE], nrej[TILE], mode[TILE], tlen[TILE], status[TILE], flag[TILE], jsi[TILE], ipos[TILE];
     float t[TILE], dt[TILE], h[TILE], qold[TILE], tstop[TILE], dt_retry[TILE], kk[TILE];
     short ivp[7][TILE];                                     // tape interval of every stage of the current step
+    long long row0[TILE];                                   // first tape row of the slot's column (dense or compact tape)
 };
 constexpr int ATC_SMEM = SO_ST + (int)sizeof(AtcShared);
 static_assert(ATC_SMEM <= 232448, "shared memory budget");
@@ -341,8 +342,10 @@ __device__ __forceinline__ void atc_control(const AdjParams& P, AtcShared& S, in
             const int len = P.tape_len[next];
             const int st = P.status ? P.status[next] : 0;
             if (st != ST_OK || len <= 0 || P.n_save < 2) continue;      // nothing to differentiate (or forward failed: reported in status[])
-            const float* last = P.tape + ((long long)next * P.tape_cap + (len - 1)) * TAPE_STRIDE;
+            const long long r0 = tape_row0(P, next);
+            const float* last = P.tape + (r0 + (len - 1)) * TAPE_STRIDE;
             col = (int)next;
+            S.row0[c] = r0;
             S.col[c] = col; S.t[c] = P.tf; S.tstop[c] = P.saveat[P.n_save - 2]; S.si[c] = P.n_save - 2;
             S.dt[c] = P.fixed_dt > 0.f ? P.fixed_dt : last[TAPE_H]; S.qold[c] = 1e-4f; S.nacc[c] = 0; S.nrej[c] = 0;
             S.mode[c] = 0; S.ipos[c] = len - 1; S.tlen[c] = len; S.status[c] = ST_OK; S.dt_retry[c] = 0.f;
@@ -360,7 +363,7 @@ __device__ __forceinline__ void atc_control(const AdjParams& P, AtcShared& S, in
             if (t - h <= ts + 1e-6f * P.tf && (t - h) - ts <= 0.05f * fabsf(h)) { h = t - ts; fl |= AFL_LAST; } // snap to the save time only when that stretches the step by < 5 %: a wider window re-stretched a rejected step for ever (livelock at t - tstop = 4e-6, 2 of 10^6 columns)
             S.h[c] = h;
         }
-        const float* base = P.tape + (long long)col * P.tape_cap * TAPE_STRIDE;
+        const float* base = P.tape + S.row0[c] * TAPE_STRIDE;
         int n = S.ipos[c];
         const int len = S.tlen[c];
         float tn = base[(long long)n * TAPE_STRIDE + TAPE_T], hn = base[(long long)n * TAPE_STRIDE + TAPE_H];
@@ -415,7 +418,7 @@ __device__ __forceinline__ void coop_load(const AdjParams& P, AtcShared& S, unsi
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int cc = 8 * warp + 4 * b + j, colx = S.col[cc];
-        const float* row = P.tape + ((long long)(colx >= 0 ? colx : 0) * P.tape_cap + S.ivp[s][cc]) * TAPE_STRIDE;
+        const float* row = P.tape + ((colx >= 0 ? S.row0[cc] : 0LL) + S.ivp[s][cc]) * TAPE_STRIDE;
         tn[j] = __ldg(row + TAPE_T); hn[j] = __ldg(row + TAPE_H);
 #pragma unroll
         for (int k = 0; k < 5; ++k) e[j][k] = __ldg(row + k * NZ + lane);
@@ -530,8 +533,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) adjoint_tc_kernel(const unsigned 
                 // the four threads of a column share them out), so that the next step's stage loads do not wait for HBM
                 if (col >= 0) {
                     const int n6 = S.ivp[6][c];
-                    const char* r0 = reinterpret_cast<const char*>(P.tape + ((long long)col * P.tape_cap + (n6 > 0 ? n6 - 1 : 0)) * TAPE_STRIDE);
-                    const char* r1 = reinterpret_cast<const char*>(P.tape + ((long long)col * P.tape_cap + (n6 > 1 ? n6 - 2 : 0)) * TAPE_STRIDE);
+                    const long long rb = S.row0[c];
+                    const char* r0 = reinterpret_cast<const char*>(P.tape + (rb + (n6 > 0 ? n6 - 1 : 0)) * TAPE_STRIDE);
+                    const char* r1 = reinterpret_cast<const char*>(P.tape + (rb + (n6 > 1 ? n6 - 2 : 0)) * TAPE_STRIDE);
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(r0 + 128 * q));
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(r1 + 128 * q));
                     if (q < 2) {

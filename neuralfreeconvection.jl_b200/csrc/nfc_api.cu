@@ -195,6 +195,7 @@ int launch_solve(nfc_handle* h, SolveParams& P, cudaStream_t st, bool reset_coun
     // Schedule: columns that took the most steps in the previous call of this batch size go first, so the queue drains with short
     // columns and the persistent CTAs finish together (the same columns are re-solved every epoch).  Results do not depend on it.
     P.order = nullptr; P.work = nullptr;
+    const bool rec_sel = RECORD || h->count_pass;      // counting pass of the compact tape: the RECORD pass's kernel choice, so its step counts
     if (!RECORD && h->use_sched && B >= 4096) {
         if (h->sched_B != hist_total) {                      // new batch size: forget the history
             NFC_CUDA(h, cudaStreamSynchronize(st));
@@ -228,13 +229,13 @@ int launch_solve(nfc_handle* h, SolveParams& P, cudaStream_t st, bool reset_coun
     if (small_forward_batch(h, B)) {
         P.wpack = nullptr;
         if (int rc = launch_small_forward(h, P, st, RECORD)) return rc;
-    } else if (h->use_tc && h->arch != ARCH_DEFAULT && tc_forward_arch(h->arch) && !RECORD && h->tc_fp16) {
+    } else if (h->use_tc && h->arch != ARCH_DEFAULT && tc_forward_arch(h->arch) && !rec_sel && h->tc_fp16) {
         // conv-2 / conv-4 / deeper Chain: one-tile tensor-core forward solve (the RECORD pass of loss_grad stays on the FP32 SIMT kernel)
         const int gridt = (int)std::min<long long>(h->num_sms, (B + tc::TILE - 1) / tc::TILE);
 #define NFC_SOLVE_TC(SP) tc::solve_tc_kernel<SP, false><<<gridt, tc::NTHREADS, SP::IMG, st>>>(h->d_wimg.p, P)
         NFC_TC_ARCH_DISPATCH(h, (void)0, NFC_SOLVE_TC(tc::SplitFP16x2T<2 NFC_COMMA 2>), NFC_SOLVE_TC(tc::SplitFP16x2T<2 NFC_COMMA 4>), NFC_SOLVE_TC(tc::SplitFP16x2T<3 NFC_COMMA 0>))
 #undef NFC_SOLVE_TC
-    } else if (h->use_tc && h->arch == ARCH_DEFAULT && (!RECORD || (h->tc_fp16 && h->tc_record))) {
+    } else if (h->use_tc && h->arch == ARCH_DEFAULT && (!rec_sel || (h->tc_fp16 && h->tc_record))) {
         const int gridt = (int)std::min<long long>(h->num_sms, (B + tc::TILE - 1) / tc::TILE);
 #ifdef NFC_DEBUG_TIMERS          // debug build only: phase timers of CTA 0 (clock64) and the timing-experiment knob; the release kernels ignore both
         if (!RECORD) {
@@ -308,6 +309,15 @@ template <class N>
 int nfc_launch_record(nfc_handle* h, nfc::SolveParams& P, cudaStream_t st, bool first_chunk) {
     if (h->cfg.alg == NFC_ALG_RKC2) return launch_record_rkc<N>(h, P, st, first_chunk);
     return launch_solve<N, true>(h, P, st, first_chunk);
+}
+namespace { template <class N> int launch_count_rkc(nfc_handle* h, nfc::SolveParams& P, cudaStream_t st); }
+template <class N>
+int nfc_launch_count(nfc_handle* h, nfc::SolveParams& P, cudaStream_t st) {
+    if (h->cfg.alg == NFC_ALG_RKC2) return launch_count_rkc<N>(h, P, st);
+    h->count_pass = true;
+    const int rc = launch_solve<N, false>(h, P, st, true);
+    h->count_pass = false;
+    return rc;
 }
 #include "nfc_adjoint.cuh"
 #include "nfc_adjoint_small.cuh"
@@ -404,6 +414,10 @@ int launch_solve_rkc(nfc_handle* h, SolveParams& S, cudaStream_t st, bool reset_
 template <class N>
 int launch_record_rkc(nfc_handle* h, nfc::SolveParams& P, cudaStream_t st, bool first_chunk) {
     return launch_solve_rkc<N, true>(h, P, st, first_chunk, true, nullptr);
+}
+template <class N>
+int launch_count_rkc(nfc_handle* h, nfc::SolveParams& P, cudaStream_t st) {
+    return launch_solve_rkc<N, false>(h, P, st, true, true, nullptr);
 }
 
 template <class N>
@@ -685,6 +699,7 @@ int32_t nfc_create(const nfc_config* cfg, nfc_handle** out) {
         const char* e = getenv("NFC_TC");
         h->use_tc = !(e && atoi(e) == 0);
     }
+    if (const char* e = getenv("NFC_TAPE_MODE")) h->tape_mode = std::max(0, std::min(2, atoi(e)));     // adjoint tape: 0 auto, 1 dense, 2 compact
     if (h->d_theta.ensure(h->n_params) || h->d_wpack.ensure(h->n_packed) || h->d_saveat.ensure(h->saveat.size()) ||
         h->d_counters.ensure(CTR_COUNT)) { h->err = "cudaMalloc failed"; return bail(-10); }
     if (cudaMemcpy(h->d_saveat.p, h->saveat.data(), sizeof(float) * h->saveat.size(), cudaMemcpyHostToDevice) != cudaSuccess) { h->err = "saveat upload failed"; return bail(-10); }
@@ -703,7 +718,7 @@ int32_t nfc_destroy(nfc_handle* h) {
     h->e_theta.release(); h->e_wpack.release(); h->d_rkctab.release(); h->s_nfe.release();
     h->s_T0.release(); h->s_colp.release(); h->s_out.release(); h->s_true.release(); h->s_grad.release();
     h->s_nacc.release(); h->s_nrej.release(); h->s_status.release(); h->s_loss.release();
-    h->a_resid.release(); h->a_tape.release(); h->a_gacc.release(); h->a_tlen.release(); h->a_adjsteps.release(); h->a_gsum.release();
+    h->a_resid.release(); h->a_tape.release(); h->a_gacc.release(); h->a_tlen.release(); h->a_adjsteps.release(); h->a_gsum.release(); h->a_count.release(); h->a_off.release(); h->a_flag.release();
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : h->ev_chunk) if (ev) cudaEventDestroy(ev);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
@@ -821,8 +836,9 @@ int32_t nfc_set_option(nfc_handle* h, const char* name, int64_t value) {
         NFC_CUDA(h, cudaSetDevice(h->device));
         return switch_split(h, value == 0);
     }
+    else if (n == "tape_mode") { if (value < 0 || value > 2) return fail(h, -2, "tape_mode: 0 = compact tape when the dense one exceeds the budget, 1 = dense, 2 = compact"); h->tape_mode = (int)value; }
     else if (n == "tape_gib") { if (value < 0) return fail(h, -2, "tape_gib: >= 0 (0 = default 48)"); h->tape_gib = (double)value; }
-    else return fail(h, -2, "unknown option '%s' (tc, tc_tiles, tc_split, range_fallback, tc2_min_columns, tc_record, sched, adj_small_max, fwd_small_max, adj_tc, e2e_pieces, tape_gib)", name);
+    else return fail(h, -2, "unknown option '%s' (tc, tc_tiles, tc_split, range_fallback, tc2_min_columns, tc_record, sched, adj_small_max, fwd_small_max, adj_tc, e2e_pieces, tape_gib, tape_mode)", name);
     return 0;
 }
 
@@ -831,12 +847,15 @@ int32_t nfc_get_tape(nfc_handle* h, int64_t column, float* rows, int32_t max_row
     NFC_CUDA(h, cudaSetDevice(h->device));
     NFC_CUDA(h, cudaDeviceSynchronize());
     const int cap = h->cfg.adjoint_max_steps;
-    if (column < 0 || (size_t)(column + 1) * cap * TAPE_STRIDE > h->a_tape.cap || (size_t)column >= h->a_tlen.cap) return fail(h, -2, "column %lld is not in the last loss_grad chunk", (long long)column);
+    const bool compact = !h->a_off_host.empty();
+    if (column < 0 || (size_t)column >= h->a_tlen.cap || (compact ? (size_t)column + 1 >= h->a_off_host.size() : (size_t)(column + 1) * cap * TAPE_STRIDE > h->a_tape.cap))
+        return fail(h, -2, "column %lld is not in the last loss_grad chunk", (long long)column);
     int len = 0;
     NFC_CUDA(h, cudaMemcpy(&len, h->a_tlen.p + column, sizeof(int), cudaMemcpyDeviceToHost));
     *n_rows = len;
     const int n = std::min(len, max_rows);
-    if (n > 0) NFC_CUDA(h, cudaMemcpy(rows, h->a_tape.p + (size_t)column * cap * TAPE_STRIDE, sizeof(float) * (size_t)n * TAPE_STRIDE, cudaMemcpyDeviceToHost));
+    const size_t row0 = compact ? (size_t)h->a_off_host[(size_t)column] : (size_t)column * cap;
+    if (n > 0) NFC_CUDA(h, cudaMemcpy(rows, h->a_tape.p + row0 * TAPE_STRIDE, sizeof(float) * (size_t)n * TAPE_STRIDE, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -36,11 +36,18 @@ struct SolveParams {
     // record mode (loss / adjoint tape), see nfc_adjoint.cuh
     const float* Ttrue;        // [B][n_save][32]
     float* resid;              // [B][n_save][32]  u(t_i) - Ttrue
-    float* tape;               // [B][tape_cap][TAPE_STRIDE]
+    float* tape;               // dense: [B][tape_cap][TAPE_STRIDE]; compact: rows [tape_off[c], tape_off[c + 1]) belong to column c
     int* tape_len;             // [B]
     double* loss_sum;          // [1]
     int tape_cap;
+    const long long* tape_off; // [B + 1] first tape row of every column (compact tape: a counting pass sized every column's share) or null
 };
+
+// Tape addressing shared by the RECORD and the backward kernels (SolveParams / AdjParams).
+template <class PP> __device__ __forceinline__ long long tape_row0(const PP& P, long long col) { return P.tape_off ? P.tape_off[col] : col * P.tape_cap; }
+template <class PP> __device__ __forceinline__ int tape_capacity(const PP& P, long long col) {
+    return P.tape_off ? (int)(P.tape_off[col + 1] - P.tape_off[col]) : P.tape_cap;
+}
 
 template <class N>
 __global__ void pack_weights_kernel(const float* __restrict__ theta, float* __restrict__ wpack) {
@@ -227,7 +234,7 @@ __device__ __forceinline__ void fill_slot(const SolveParams& P, WarpSlots* sl, i
         while (si < P.n_save && P.saveat[si] <= 0.f) {
             const long long o = (next * P.n_save + si) * NZ + lane;
             if (RECORD) { const float r = u - P.Ttrue[o]; P.resid[o] = r; sse = fmaf(r, r, sse); }
-            else P.Tout[o] = u;
+            else if (P.Tout) P.Tout[o] = u;
             ++si;
         }
         if (RECORD && si > 0) lsum += (double)warp_sum(sse);
@@ -334,8 +341,8 @@ __device__ __forceinline__ void solve_warp(const SolveParams& P, const float* sW
                 if (RECORD) {
                     tsit5_power_basis(ks, c, pc1, pc2, pc3, pc4);
                     const int n = sl->tlen[c];
-                    if (n < P.tape_cap) {
-                        float* e = P.tape + ((long long)col * P.tape_cap + n) * TAPE_STRIDE;
+                    if (n < tape_capacity(P, col)) {
+                        float* e = P.tape + (tape_row0(P, col) + n) * TAPE_STRIDE;
                         e[lane] = u[c]; e[NZ + lane] = pc1; e[2 * NZ + lane] = pc2; e[3 * NZ + lane] = pc3; e[4 * NZ + lane] = pc4;
                         if (lane == 0) { e[TAPE_T] = t0; e[TAPE_H] = h; }
                     }
@@ -354,7 +361,7 @@ __device__ __forceinline__ void solve_warp(const SolveParams& P, const float* sW
                         float inc = b[0] * ks[0][c];
 #pragma unroll
                         for (int j = 1; j < 7; ++j) inc = fmaf(b[j], ks[j][c], inc);
-                        P.Tout[o] = fmaf(h, inc, u[c]);
+                        if (P.Tout) P.Tout[o] = fmaf(h, inc, u[c]);      // null: counting pass of the compact tape (nfc_adjoint.cuh)
                     }
                     ++si;
                 }
@@ -367,7 +374,7 @@ __device__ __forceinline__ void solve_warp(const SolveParams& P, const float* sW
         __syncwarp();
         if (lane < CPW && (sl->flag[lane] & FL_ACCEPT)) {
             sl->t[lane] = sl->tnew[lane]; sl->si[lane] = mysi;
-            if (RECORD) { if (sl->tlen[lane] >= P.tape_cap) sl->status[lane] = ST_TAPE_OVERFLOW; sl->tlen[lane] += 1; }
+            if (RECORD) { if (sl->tlen[lane] >= tape_capacity(P, sl->col[lane])) sl->status[lane] = ST_TAPE_OVERFLOW; sl->tlen[lane] += 1; }
         }
         __syncwarp();
         // ---- retire finished columns and refill their slots from the queue ----
@@ -380,7 +387,7 @@ __device__ __forceinline__ void solve_warp(const SolveParams& P, const float* sW
                     if (P.nreject) P.nreject[col] = sl->nrej[c];
                     if (P.status) P.status[col] = sl->status[c];
                     if (P.work) P.work[col] = sl->nacc[c] + sl->nrej[c];
-                    if (RECORD) P.tape_len[col] = sl->tlen[c] < P.tape_cap ? sl->tlen[c] : P.tape_cap;
+                    if (RECORD) P.tape_len[col] = min(sl->tlen[c], tape_capacity(P, col));
                     atomicAdd(&P.counters[CTR_ACCEPT], (unsigned long long)sl->nacc[c]);
                     atomicAdd(&P.counters[CTR_REJECT], (unsigned long long)sl->nrej[c]);
                 }

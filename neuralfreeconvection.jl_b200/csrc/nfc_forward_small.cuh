@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(NT, 1) solve_small_kernel(const float* __restr
                     while (si < P.n_save && P.saveat[si] <= 0.f) {
                         const long long o = (next * P.n_save + si) * NZ + lane;
                         if (RECORD) { const float r = u - P.Ttrue[o]; P.resid[o] = r; sse = fmaf(r, r, sse); }
-                        else __stcs(P.Tout + o, u);
+                        else if (P.Tout) __stcs(P.Tout + o, u);
                         ++si;
                     }
                     if (RECORD) lsum += (double)warp_sum(sse);
@@ -179,8 +179,8 @@ __global__ void __launch_bounds__(NT, 1) solve_small_kernel(const float* __restr
                 c2 = fmaf(-27.896526289197286f, k[5], c2); c3 = fmaf(65.09189467479366f, k[5], c3); c4 = fmaf(-34.87065786149661f, k[5], c4);
                 c2 = fmaf(1.5f, k[6], c2); c3 = fmaf(-4.0f, k[6], c3); c4 = fmaf(2.5f, k[6], c4);
                 if (RECORD) {
-                    if (nacc < P.tape_cap) {
-                        float* row = P.tape + ((long long)col * P.tape_cap + nacc) * TAPE_STRIDE;
+                    if (nacc < tape_capacity(P, col)) {
+                        float* row = P.tape + (tape_row0(P, col) + nacc) * TAPE_STRIDE;
                         row[lane] = u; row[NZ + lane] = k[0]; row[2 * NZ + lane] = c2; row[3 * NZ + lane] = c3; row[4 * NZ + lane] = c4;
                         if (lane == 0) { row[TAPE_T] = t; row[TAPE_H] = hs; }
                     } else status = ST_TAPE_OVERFLOW;
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(NT, 1) solve_small_kernel(const float* __restr
                     const float v = fmaf(hs, th * fmaf(th, fmaf(th, fmaf(th, c4, c3), c2), k[0]), u);
                     const long long o = ((long long)col * P.n_save + si) * NZ + lane;
                     if (RECORD) { const float r = v - P.Ttrue[o]; P.resid[o] = r; sse = fmaf(r, r, sse); }
-                    else __stcs(P.Tout + o, v);
+                    else if (P.Tout) __stcs(P.Tout + o, v);
                     ++si;
                 }
                 if (RECORD) lsum += (double)warp_sum(sse);
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(NT, 1) solve_small_kernel(const float* __restr
                     if (P.nreject) P.nreject[col] = nrej;
                     if (P.status) P.status[col] = status;
                     if (P.work) P.work[col] = nacc + nrej;
-                    if (RECORD) P.tape_len[col] = nacc < P.tape_cap ? nacc : P.tape_cap;
+                    if (RECORD) P.tape_len[col] = min(nacc, tape_capacity(P, col));
                     atomicAdd(&P.counters[CTR_ACCEPT], (unsigned long long)nacc);
                     atomicAdd(&P.counters[CTR_REJECT], (unsigned long long)nrej);
                 }

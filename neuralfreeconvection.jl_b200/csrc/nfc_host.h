@@ -91,7 +91,14 @@ struct nfc_handle {
     nfc::DevBuf<double> s_loss;
     // adjoint scratch
     nfc::DevBuf<float> a_resid, a_tape, a_gacc;
-    nfc::DevBuf<int> a_tlen, a_adjsteps;
+    nfc::DevBuf<int> a_tlen, a_adjsteps, a_count, a_flag;
+    int64_t a_count_B = -1;                    // compact tape: a_count holds the accepted steps per column of the last call on this batch size
+    bool a_count_valid = false;
+    nfc::DevBuf<long long> a_off;              // compact tape: first row of every column, per chunk (nfc_adjoint.cuh)
+    std::vector<long long> a_off_host;         // the last chunk's offsets (nfc_get_tape); empty: dense tape
+    int64_t a_tape_rows = 0;                   // rows of the tape buffer the last call used
+    int tape_mode = 0;                         // 0 = compact tape when the dense one exceeds the budget, 1 = dense, 2 = compact
+    bool count_pass = false;                   // launch_solve: pick the kernels of the RECORD pass for a non-RECORD solve
     int64_t a_adjsteps_n = 0;      // a_adjsteps: attempted backward steps per column of the last nfc_loss_grad batch (all chunks)
     int64_t fwd_small_max = 148;   // forward solves / RECORD passes of at most this many columns (default Chain) run one column per CTA (nfc_forward_small.cuh)
     int64_t adj_small_max = 7400;  // loss_grad chunks of at most this many columns (default Chain) use the one-column-per-CTA backward kernel

@@ -63,7 +63,7 @@ __device__ __forceinline__ void fill(const Params& P, Slots* sl, int c, float& y
         while (si < P.S.n_save && P.S.saveat[si] <= 0.f) {
             const long long o = (next * P.S.n_save + si) * NZ + lane;
             if (RECORD) { const float r = yn - P.S.Ttrue[o]; P.S.resid[o] = r; *lsum += (double)warp_sum(r * r); }
-            else P.S.Tout[o] = yn;
+            else if (P.S.Tout) P.S.Tout[o] = yn;
             ++si;
         }
         if (lane == 0) {
@@ -296,8 +296,8 @@ __global__ void __launch_bounds__(NW * 32, 1) solve_rkc_kernel(const Params P) {
                 const float c2 = 3.f * d - 2.f * fn[c] - f[c], c3 = -2.f * d + fn[c] + f[c];
                 if (RECORD) {
                     const int n = sl->o_row[c];
-                    if (n < P.S.tape_cap) {
-                        float* e = P.S.tape + ((long long)col * P.S.tape_cap + n) * TAPE_STRIDE;
+                    if (n < tape_capacity(P.S, col)) {
+                        float* e = P.S.tape + (tape_row0(P.S, col) + n) * TAPE_STRIDE;
                         e[lane] = yn[c]; e[NZ + lane] = fn[c]; e[2 * NZ + lane] = c2; e[3 * NZ + lane] = c3; e[4 * NZ + lane] = 0.f;
                         if (lane == 0) { e[TAPE_T] = t0; e[TAPE_H] = h; }
                     }
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(NW * 32, 1) solve_rkc_kernel(const Params P) {
                     const long long o = (col * P.S.n_save + si) * NZ + lane;
                     const float val = fmaf(h * th, fmaf(th, fmaf(th, c3, c2), fn[c]), yn[c]);
                     if (RECORD) { const float r = val - P.S.Ttrue[o]; P.S.resid[o] = r; sse = fmaf(r, r, sse); }
-                    else P.S.Tout[o] = val;
+                    else if (P.S.Tout) P.S.Tout[o] = val;
                 }
                 if (RECORD) lsum += (double)warp_sum(sse);
                 yn[c] = x[c]; fn[c] = f[c];
@@ -330,8 +330,8 @@ __global__ void __launch_bounds__(NW * 32, 1) solve_rkc_kernel(const Params P) {
                     if (P.S.naccept) P.S.naccept[col] = sl->nacc[c];
                     if (P.S.nreject) P.S.nreject[col] = sl->nrej[c];
                     if (RECORD) {
-                        if (sl->nacc[c] > P.S.tape_cap && sl->status[c] == ST_OK) sl->status[c] = ST_TAPE_OVERFLOW;
-                        P.S.tape_len[col] = sl->nacc[c] < P.S.tape_cap ? sl->nacc[c] : P.S.tape_cap;
+                        if (sl->nacc[c] > tape_capacity(P.S, col) && sl->status[c] == ST_OK) sl->status[c] = ST_TAPE_OVERFLOW;
+                        P.S.tape_len[col] = min(sl->nacc[c], tape_capacity(P.S, col));
                     }
                     if (P.S.status) P.S.status[col] = sl->status[c];
                     if (P.nfe) P.nfe[col] = sl->nfe[c];

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_rkc_tc_kernel(const unsigne
 #pragma unroll
                         for (int i = 0; i < 8; ++i) sse = fmaf(r[i], r[i], sse);
                         lsum += (double)sse;
-                    } else {
+                    } else if (P.S.Tout) {
                         float* o = P.S.Tout + oi;
                         *reinterpret_cast<float4*>(o) = a;
                         *reinterpret_cast<float4*>(o + 4) = b;
@@ -161,8 +161,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_rkc_tc_kernel(const unsigne
                         if (P.S.naccept) P.S.naccept[colc] = sl->nacc[c];
                         if (P.S.nreject) P.S.nreject[colc] = sl->nrej[c];
                         if (RECORD) {
-                            if (sl->nacc[c] > P.S.tape_cap && sl->status[c] == ST_OK) sl->status[c] = ST_TAPE_OVERFLOW;
-                            P.S.tape_len[colc] = sl->nacc[c] < P.S.tape_cap ? sl->nacc[c] : P.S.tape_cap;
+                            if (sl->nacc[c] > tape_capacity(P.S, colc) && sl->status[c] == ST_OK) sl->status[c] = ST_TAPE_OVERFLOW;
+                            P.S.tape_len[colc] = min(sl->nacc[c], tape_capacity(P.S, colc));
                         }
                         if (P.S.status) P.S.status[colc] = sl->status[c];
                         if (P.nfe) P.nfe[colc] = sl->nfe[c];
@@ -194,8 +194,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_rkc_tc_kernel(const unsigne
                     }
                     if (RECORD) {          // tape row in the Tsit5 tape's power basis: u_n, c1 = f_n, c2, c3, c4 = 0, (t_n, h_n)
                         const int n = sl->o_row[c];
-                        if (n < P.S.tape_cap) {
-                            float* e = P.S.tape + ((long long)colc * P.S.tape_cap + n) * TAPE_STRIDE + 8 * q;
+                        if (n < tape_capacity(P.S, colc)) {
+                            float* e = P.S.tape + (tape_row0(P.S, colc) + n) * TAPE_STRIDE + 8 * q;
 #pragma unroll
                             for (int hf = 0; hf < 2; ++hf) {
                                 const int i = 4 * hf;
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_rkc_tc_kernel(const unsigne
 #pragma unroll
                             for (int i = 0; i < 8; ++i) sse = fmaf(r[i], r[i], sse);
                             lsum += (double)sse;
-                        } else {
+                        } else if (P.S.Tout) {
                             float* dst = P.S.Tout + oi;
                             *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
                             *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);

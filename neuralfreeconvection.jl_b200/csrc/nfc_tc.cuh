@@ -965,7 +965,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
                         if (P.nreject) P.nreject[col] = nrej;
                         if (P.status) P.status[col] = status;
                         if (P.work) P.work[col] = nacc + nrej;
-                        if (RECORD) P.tape_len[col] = nacc < P.tape_cap ? nacc : P.tape_cap;
+                        if (RECORD) P.tape_len[col] = min(nacc, tape_capacity(P, col));
                         atomicAdd(&P.counters[CTR_ACCEPT], (unsigned long long)nacc);
                         atomicAdd(&P.counters[CTR_REJECT], (unsigned long long)nrej);
                     }
@@ -1014,7 +1014,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
 #pragma unroll
                                 for (int i = 0; i < 8; ++i) sse = fmaf(r[i], r[i], sse);
                                 lsum += (double)sse;
-                            } else {
+                            } else if (P.Tout) {                   // null: counting pass of the compact tape (nfc_adjoint.cuh)
                                 float* o2 = P.Tout + o2i;          // streaming stores: 1 GB of trajectories must not evict the inputs of later columns from L2
                                 __stcs(reinterpret_cast<float4*>(o2), make_float4(u[0], u[1], u[2], u[3]));
                                 __stcs(reinterpret_cast<float4*>(o2 + 4), make_float4(u[4], u[5], u[6], u[7]));
@@ -1126,8 +1126,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
                 if (accept) {
                     const float tn = last ? P.tf : t + hs;
                     if (RECORD) {
-                        if (nacc < P.tape_cap) {
-                            float* e = P.tape + ((long long)col * P.tape_cap + nacc) * TAPE_STRIDE + 8 * q;
+                        if (nacc < tape_capacity(P, col)) {
+                            float* e = P.tape + (tape_row0(P, col) + nacc) * TAPE_STRIDE + 8 * q;
 #pragma unroll
                             for (int hlf = 0; hlf < 2; ++hlf) {
                                 const int i = 4 * hlf;
@@ -1158,7 +1158,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) solve_tc_kernel(const unsigned ch
 #pragma unroll
                             for (int i = 0; i < 8; ++i) sse = fmaf(r[i], r[i], sse);
                             lsum += (double)sse;
-                        } else {
+                        } else if (P.Tout) {
                             float* o2 = P.Tout + o2i;
                             __stcs(reinterpret_cast<float4*>(o2), make_float4(v[0], v[1], v[2], v[3]));
                             __stcs(reinterpret_cast<float4*>(o2 + 4), make_float4(v[4], v[5], v[6], v[7]));

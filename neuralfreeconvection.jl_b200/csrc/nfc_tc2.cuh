@@ -308,7 +308,7 @@ __device__ __forceinline__ void step_control(Shared2* S, const SolveParams& P, i
             C.si[c] = si;
             C.t[c] = tn;
             if (P.fixed_dt <= 0.f) C.qold[c] = fmaxf(ee, 1e-4f);
-            if (RECORD && nacc >= P.tape_cap) status = ST_TAPE_OVERFLOW;      // no tape row left for this step
+            if (RECORD && nacc >= tape_capacity(P, col)) status = ST_TAPE_OVERFLOW;      // no tape row left for this step
             ++nacc;
             if (tn >= P.tf) done = true;
             newctl |= CTL_ACCEPT;
@@ -327,7 +327,7 @@ __device__ __forceinline__ void step_control(Shared2* S, const SolveParams& P, i
             if (P.nreject) P.nreject[col] = nrej;
             if (P.status) P.status[col] = status;
             if (P.work) P.work[col] = nacc + nrej;
-            if (RECORD) P.tape_len[col] = nacc < P.tape_cap ? nacc : P.tape_cap;
+            if (RECORD) P.tape_len[col] = min(nacc, tape_capacity(P, col));
             atomicAdd(&P.counters[CTR_ACCEPT], (unsigned long long)nacc);
             atomicAdd(&P.counters[CTR_REJECT], (unsigned long long)nrej);
         }
@@ -377,7 +377,7 @@ __device__ __forceinline__ void save_point(const SolveParams& P, long long o2i, 
 #pragma unroll
         for (int i = 0; i < 8; ++i) sse = fmaf(r[i], r[i], sse);
         lsum += (double)sse;
-    } else {
+    } else if (P.Tout) {
         float* o2 = P.Tout + o2i;          // streaming stores (see tc::solve_tc_kernel)
         __stcs(reinterpret_cast<float4*>(o2), make_float4(v[0], v[1], v[2], v[3]));
         __stcs(reinterpret_cast<float4*>(o2 + 4), make_float4(v[4], v[5], v[6], v[7]));
@@ -411,8 +411,8 @@ __device__ __forceinline__ void step_finish(Shared2* S, unsigned char* ks, const
     if (o.col >= 0 && (ctl & CTL_ACCEPT)) {
         const float tn = (o.ctl & CTL_LAST) ? P.tf : o.t + o.hs;
         int si = o.si;
-        if (RECORD && o.nacc < P.tape_cap) {
-            float* e = P.tape + ((long long)o.col * P.tape_cap + o.nacc) * TAPE_STRIDE + 8 * q;
+        if (RECORD && o.nacc < tape_capacity(P, o.col)) {
+            float* e = P.tape + (tape_row0(P, o.col) + o.nacc) * TAPE_STRIDE + 8 * q;
 #pragma unroll
             for (int hlf = 0; hlf < 2; ++hlf) {
                 const int i = 4 * hlf;

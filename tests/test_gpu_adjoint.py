@@ -224,3 +224,110 @@ def test_record_pass_kernels_agree(nfc, gpu_ok, monkeypatch):
     # FP32 SIMT record pass (powf, FP32 FMA) vs tensor-core record pass (the arithmetic of nfc_solve): two valid step sequences; for these
     # x1e-5 weights with K_CA = 2 the problem is ill-conditioned (the C twin differs from either by 1.5e-2)
     assert _rel(b["grad"], a["grad"]) < 1.5e-2
+
+
+# ---------------------------------------------------------------------------------------------------------------------------------
+# compact tape (option tape_mode, csrc/nfc_adjoint.cuh): a counting pass sizes every column's share of the tape
+# ---------------------------------------------------------------------------------------------------------------------------------
+def _tape_problem(nfc, B, arch="dense-default", n_save=17, K=2.0):
+    syn = nfc.synthetic
+    d = syn.make_columns("ocean", B=B, seed=5)
+    cw, layers = O.chain_spec(arch)
+    theta = O.glorot_theta(cw, layers, 0, 1.0)
+    sv = syn.saveat(n_save)
+    colp = d["colp"].copy()
+    colp[:, 2] = K
+    rng = np.random.default_rng(3)
+    Ttrue = (d["T0"][:, None, :] + 0.05 * rng.standard_normal((B, n_save, 32))).astype(np.float32)
+    return d, cw, layers, theta, sv, colp, Ttrue
+
+
+@pytest.mark.parametrize("B,env", [(9, {}), (300, {"NFC_ADJ_SMALL_MAX": "0"}), (300, {"NFC_ADJ_SMALL_MAX": "0", "NFC_ADJ_TC": "0", "NFC_TC_RECORD": "0"}),
+                                   (2500, {"NFC_ADJ_SMALL_MAX": "0"})])
+def test_compact_tape_matches_dense_tape(nfc, gpu_ok, monkeypatch, B, env):
+    """Same loss (bit for bit: same RECORD arithmetic), same tape rows, same gradient whatever the tape layout; every kernel family."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    d, cw, layers, theta, sv, colp, Ttrue = _tape_problem(nfc, B)
+    out = {}
+    for mode in (1, 2):
+        h = nfc.Handle(cw, layers, 1, sv)
+        h.set_weights(theta)
+        h.set_option("tape_mode", mode)
+        r = h.loss_grad(d["T0"], colp, d["glob"], Ttrue)
+        assert (r["status"] == 0).all()
+        out[mode] = (r, h.tape(B - 1), h.tape(0))
+    a, b = out[1], out[2]
+    assert a[0]["loss"] == b[0]["loss"]
+    assert np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and len(a[1]) > 10
+    assert _rel(b[0]["grad"], a[0]["grad"]) < 1e-5         # accumulation order of the per-CTA sums differs from run to run
+
+
+def test_compact_tape_has_no_step_cap_and_chunks_by_budget(nfc, gpu_ok, monkeypatch):
+    """adjoint_max_steps = 16 overflows the dense tape (status 4); the compact tape takes the steps a column needs.  A tiny budget forces
+    several chunks of unequal size: same gradient."""
+    d, cw, layers, theta, sv, colp, Ttrue = _tape_problem(nfc, 3000, n_save=9)
+    h = nfc.Handle(cw, layers, 1, sv, adjoint_max_steps=16)
+    h.set_weights(theta)
+    h.set_option("tape_mode", 1)
+    r = h.loss_grad(d["T0"], colp, d["glob"], Ttrue)
+    assert (r["status"] == 4).any()                      # dense tape: 16 rows per column are not enough
+    h2 = nfc.Handle(cw, layers, 1, sv, adjoint_max_steps=16)
+    h2.set_weights(theta)
+    h2.set_option("tape_mode", 2)
+    c = h2.loss_grad(d["T0"], colp, d["glob"], Ttrue)
+    assert (c["status"] == 0).all()
+    h3 = nfc.Handle(cw, layers, 1, sv)
+    h3.set_weights(theta)
+    h3.set_option("tape_mode", 1)
+    ref = h3.loss_grad(d["T0"], colp, d["glob"], Ttrue)
+    assert c["loss"] == ref["loss"] and _rel(c["grad"], ref["grad"]) < 1e-5
+    monkeypatch.setenv("NFC_TAPE_GIB", "0.05")             # 51 MiB (the environment takes fractions): chunks of >= 1024 columns, unequal sizes
+    h4 = nfc.Handle(cw, layers, 1, sv)
+    h4.set_weights(theta)
+    h4.set_option("tape_mode", 2)
+    e = h4.loss_grad(d["T0"], colp, d["glob"], Ttrue)
+    assert (e["status"] == 0).all()
+    assert abs(e["loss"] - ref["loss"]) <= 1e-6 * ref["loss"] and _rel(e["grad"], ref["grad"]) < 1e-5
+    assert h4.counters()["kernel_launches"] > h2.counters()["kernel_launches"]          # more than one chunk
+
+
+def test_compact_tape_other_chain_and_stabilised_integrator(nfc, gpu_ok):
+    """conv-2 Chain (FP32 RECORD pass: the counting pass must take the same kernel, not the tensor-core forward solve) and RKC2."""
+    for arch, alg in (("conv-2", 0), ("dense-default", 1), ("dense-deeper", 0)):
+        d, cw, layers, theta, sv, colp, Ttrue = _tape_problem(nfc, 400, arch=arch, n_save=9)
+        res = {}
+        for mode in (1, 2):
+            h = nfc.Handle(cw, layers, 1, sv, alg=alg)
+            h.set_weights(theta)
+            h.set_option("tape_mode", mode)
+            res[mode] = h.loss_grad(d["T0"], colp, d["glob"], Ttrue)
+            assert (res[mode]["status"] == 0).all(), (arch, alg, mode)
+        assert res[1]["loss"] == res[2]["loss"] and _rel(res[2]["grad"], res[1]["grad"]) < 1e-5, (arch, alg)
+
+
+def test_compact_tape_history_and_restart(nfc, gpu_ok, monkeypatch):
+    """Second and later calls size the tape from the previous call's step counts (no counting pass); when the weights change so much
+    that a column outgrows its share, the call notices after the RECORD pass and restarts with exact counts: same result as the dense tape."""
+    monkeypatch.setenv("NFC_ADJ_SMALL_MAX", "0")
+    d, cw, layers, theta, sv, colp, Ttrue = _tape_problem(nfc, 600, n_save=9, K=0.0)
+    hd = nfc.Handle(cw, layers, 1, sv)
+    hd.set_weights(theta)
+    hd.set_option("tape_mode", 1)
+    ref = hd.loss_grad(d["T0"], colp, d["glob"], Ttrue)
+    n_ref = hd.counters()["steps_accepted"]
+    h = nfc.Handle(cw, layers, 1, sv)
+    h.set_option("tape_mode", 2)
+    h.set_weights(theta * np.float32(1e-3))                 # a nearly static column: a handful of steps
+    r0 = h.loss_grad(d["T0"], colp, d["glob"], Ttrue)
+    l0, n0 = h.counters()["kernel_launches"], h.counters()["steps_accepted"]
+    assert (r0["status"] == 0).all() and n_ref > 1.5 * n0   # the full-strength network needs many more steps
+    r1 = h.loss_grad(d["T0"], colp, d["glob"], Ttrue)       # from history: no counting pass
+    l1 = h.counters()["kernel_launches"]
+    assert r1["loss"] == r0["loss"] and _rel(r1["grad"], r0["grad"]) < 1e-5 and l1 < l0
+    h.set_weights(theta)
+    r2 = h.loss_grad(d["T0"], colp, d["glob"], Ttrue)       # history too short -> restart inside the call
+    l2 = h.counters()["kernel_launches"]
+    assert (r2["status"] == 0).all() and r2["loss"] == ref["loss"] and _rel(r2["grad"], ref["grad"]) < 1e-5
+    r3 = h.loss_grad(d["T0"], colp, d["glob"], Ttrue)
+    assert r3["loss"] == ref["loss"] and _rel(r3["grad"], ref["grad"]) < 1e-5 and h.counters()["kernel_launches"] < l2
