@@ -54,7 +54,10 @@ typedef struct nfc_handle nfc_handle;
 
 typedef struct nfc_config {
     int32_t struct_size;                          /* = sizeof(nfc_config), ABI guard */
-    int32_t Nz;                                   /* grid points; this build: 32 */
+    int32_t Nz;                                   /* grid points (--grid-points, train_free_convection_nde.jl:29,90): 4 .. 32.  32 = every kernel.
+                                                   * Nz < 32: the same five Chains built on Nz (Dense(Nz, 4 Nz) ... Dense(4 Nz, Nz - 1)) through the
+                                                   * host-buffer calls nfc_rhs / nfc_solve / nfc_diagnose_flux / nfc_loss_grad (Tsit5, FP32 kernels: the
+                                                   * Chain is embedded zero-padded in its 32-level version); all shapes and theta are the Nz-level ones */
     int32_t conv_width;                           /* 0 = none, else Conv((k,1),1=>1,relu) front-end (2 or 4) */
     int32_t n_layers;                             /* Dense layers */
     int32_t layer_dims[NFC_MAX_LAYERS + 1];       /* in_0, out_0, out_1, ... */

@@ -54,6 +54,7 @@ struct AdjParams {
     unsigned long long* counters;
     long long B;
     int n_save, tape_cap, max_iters, use_kca, n_params;
+    int nz;                     // vertical levels in use (<= 32; 0 means 32): adjoint_kernel only
     float pref, tf, reltol, abstol, fixed_dt;
 };
 
@@ -282,7 +283,9 @@ __global__ void __launch_bounds__(ADJ_NW * 32, 1) adjoint_kernel(const AdjParams
     float* ws = scratch0 + warp * S::TOTAL;
     AdjSlots* sl = &slots[warp];
     float* g = P.gacc + (size_t)blockIdx.x * P.n_params;
-    const float c0 = P.pref * (float)NZ;
+    const int nz = P.nz > 0 ? P.nz : NZ;
+    const float fnz = (float)nz, inz = 1.f / fnz;
+    const float c0 = P.pref * fnz;
 
     float lam[CPW], kap[7][CPW], ls[CPW];
 #pragma unroll
@@ -370,11 +373,11 @@ __global__ void __launch_bounds__(ADJ_NW * 32, 1) adjoint_kernel(const AdjParams
                 const float lw = w * ls[c];
                 const float lwlo = __shfl_up_sync(FULL, lw, 1);
                 const float ulo = __shfl_up_sync(FULL, u, 1);
-                const float Fb = lane > 0 ? c0 * (lw - lwlo) : 0.f;                 // dL/dF_k, faces k = 1..31
-                const float kk = sl->kca[c] * (float)NZ;
-                const float sca = (lane > 0 && kk * (u - ulo) < 0.f) ? kk * Fb : 0.f;
+                const float Fb = (lane > 0 && lane < nz) ? c0 * (lw - lwlo) : 0.f;  // dL/dF_k, faces k = 1..nz-1 (31)
+                const float kk = sl->kca[c] * fnz;
+                const float sca = (lane > 0 && lane < nz && kk * (u - ulo) < 0.f) ? kk * Fb : 0.f;
                 float shi = __shfl_down_sync(FULL, sca, 1);
-                if (lane == NZ - 1) shi = 0.f;
+                if (lane >= nz - 1) shi = 0.f;
                 uca[c] = shi - sca;
                 fb[c] = Fb;          // delta of the output layer: row n = k - 1  (row 31 = 0)
             }
@@ -500,7 +503,7 @@ __global__ void __launch_bounds__(ADJ_NW * 32, 1) adjoint_kernel(const AdjParams
             e *= sl->h[c];
             const float r = fast_div(e, fmaf(fmaxf(fabsf(lam[c]), fabsf(ls[c])), P.reltol, P.abstol));      // fast controller arithmetic: one for the three backward kernels
             const float ss = warp_sum(r * r);
-            if (lane == c) ee = fast_sqrt(ss * (1.f / NZ));
+            if (lane == c) ee = fast_sqrt(ss * inz);
         }
         if (lane < CPW && sl->col[lane] >= 0) {
             int fl = sl->flag[lane];
@@ -739,7 +742,7 @@ int adjoint_loss_grad(nfc_handle* h, const float* T0, const float* colp, float p
         A.adj_steps = h->a_adjsteps.p + off;
         h->a_adjsteps_n = B;
         A.wpack = h->d_wpack.p; A.colp = colp + off * 3; A.saveat = h->d_saveat.p; A.resid = h->a_resid.p; A.tape = h->a_tape.p;
-        A.tape_off = tape_off;
+        A.tape_off = tape_off; A.nz = h->nz;
         A.tape_len = h->a_tlen.p; A.status = st_all + off; A.gacc = h->a_gacc.p; A.counters = h->d_counters.p; A.B = nb; A.n_save = n_save;
         A.tape_cap = cap; A.max_iters = h->cfg.max_iters; A.use_kca = h->cfg.nde_type == NFC_NDE_CONVECTIVE_ADJUSTMENT; A.n_params = (int)h->n_params;
         A.pref = pref; A.tf = h->saveat.back(); A.reltol = h->cfg.adjoint_reltol; A.abstol = h->cfg.adjoint_abstol; A.fixed_dt = h->cfg.fixed_dt;
@@ -758,9 +761,9 @@ int adjoint_loss_grad(nfc_handle* h, const float* T0, const float* colp, float p
     }   // attempt
     if (compact) h->a_count_valid = true;
     // with a communicator the sums stay un-normalised until the all-reduce has produced the global residual count
-    const double ntot = h->nccl_comm ? 1.0 : (double)n_total_columns * n_save * NZ;
+    const double ntot = h->nccl_comm ? 1.0 : (double)n_total_columns * n_save * h->nz;
     grad_reduce_kernel<<<((int)h->n_params + 255) / 256, 256, 0, st>>>(h->a_gacc.p, grid, (int)h->n_params, 2.0 / ntot, grad_dev);
-    set_loss_count_kernel<<<1, 1, 0, st>>>(loss_sum_dev, (double)B * n_save * NZ);
+    set_loss_count_kernel<<<1, 1, 0, st>>>(loss_sum_dev, (double)B * n_save * h->nz);
     NFC_CUDA(h, cudaGetLastError());
     if (h->nccl_comm) { if (int rc = comm_allreduce_grad(h, grad_dev, loss_sum_dev, st)) return rc; }
     NFC_CUDA(h, cudaEventRecord(h->ev[3], st));

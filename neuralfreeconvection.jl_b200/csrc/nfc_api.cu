@@ -110,7 +110,7 @@ int do_rhs(nfc_handle* h, const float* T, const float* colp, float pref, float* 
     const int grid = (int)std::min<long long>(h->num_sms, (groups + NW - 1) / NW);
     rhs_init_kernel<N, WS, 0><<<grid, NW * 32, smem_bytes<N>(NW), st>>>(h->d_wpack.p, T, colp, out, nullptr, B, pref,
                                                                    h->cfg.nde_type == NFC_NDE_CONVECTIVE_ADJUSTMENT, h->cfg.reltol,
-                                                                   h->cfg.abstol, h->saveat.back(), h->cfg.fixed_dt);
+                                                                   h->cfg.abstol, h->saveat.back(), h->cfg.fixed_dt, h->nz);
     NFC_CUDA(h, cudaGetLastError());
     h->last_launches += 1;
     return 0;
@@ -151,7 +151,7 @@ int do_diagnose(nfc_handle* h, const float* Tsol, const float* colp, float* wT, 
     if (use_kca < 0) use_kca = h->cfg.nde_type == NFC_NDE_CONVECTIVE_ADJUSTMENT;
     const long long groups = (B * n_prof + CPW - 1) / CPW;
     const int grid = (int)std::min<long long>(h->num_sms, (groups + NW - 1) / NW);
-    diagnose_flux_kernel<N, WS><<<grid, NW * 32, smem_bytes<N>(NW), st>>>(h->d_wpack.p, Tsol, colp, wT, B, n_prof, use_kca);
+    diagnose_flux_kernel<N, WS><<<grid, NW * 32, smem_bytes<N>(NW), st>>>(h->d_wpack.p, Tsol, colp, wT, B, n_prof, use_kca, h->nz);
     NFC_CUDA(h, cudaGetLastError());
     h->last_launches += 1;
     return 0;
@@ -184,6 +184,7 @@ int launch_solve(nfc_handle* h, SolveParams& P, cudaStream_t st, bool reset_coun
     P.use_kca = h->cfg.nde_type == NFC_NDE_CONVECTIVE_ADJUSTMENT;
     P.tf = h->saveat.back();
     P.reltol = h->cfg.reltol; P.abstol = h->cfg.abstol; P.fixed_dt = h->cfg.fixed_dt;
+    P.nz = h->nz;
     if (reset_counters) {
         NFC_CUDA(h, cudaMemsetAsync(h->d_counters.p, 0, sizeof(unsigned long long) * CTR_COUNT, st));
     } else {   // later chunks of one loss_grad call: only the two work-queue heads restart
@@ -223,7 +224,7 @@ int launch_solve(nfc_handle* h, SolveParams& P, cudaStream_t st, bool reset_coun
     const long long groups = (B + CPW - 1) / CPW;
     const int grid0 = (int)std::min<long long>(h->num_sms, (groups + NW - 1) / NW);
     rhs_init_kernel<N, WS, 1><<<grid0, NW * 32, smem_bytes<N>(NW), st>>>(h->d_wpack.p, P.T0, P.colp, h->d_k1.p, h->d_dt.p, B, P.pref, P.use_kca,
-                                                                    P.reltol, P.abstol, P.tf, P.fixed_dt);
+                                                                    P.reltol, P.abstol, P.tf, P.fixed_dt, h->nz);
     NFC_CUDA(h, cudaGetLastError());
     // tensor-core kernels: the forward solve always (default Chain), the RECORD pass of loss_grad with the FP16x2 split (NFC_TC_RECORD=0: SIMT)
     if (small_forward_batch(h, B)) {
@@ -613,7 +614,36 @@ int32_t nfc_create(const nfc_config* cfg, nfc_handle** out) {
     if (!cfg || !out) return fail(nullptr, -1, "null argument");
     *out = nullptr;
     if (cfg->struct_size != (int32_t)sizeof(nfc_config)) return fail(nullptr, -2, "nfc_config.struct_size %d != %zu", cfg->struct_size, sizeof(nfc_config));
-    if (cfg->Nz != NZ) return fail(nullptr, -3, "this build supports Nz = 32 only (got %d)", cfg->Nz);
+    if (cfg->Nz < 4 || cfg->Nz > NZ) return fail(nullptr, -3, "Nz must be in [4, 32] (got %d): every kernel maps the levels of a column onto one warp", cfg->Nz);
+    nfc_config padded = *cfg;
+    std::vector<int64_t> theta_map;
+    const int user_nz = cfg->Nz;
+    if (cfg->Nz < NZ) {
+        // --grid-points < 32 (train_free_convection_nde.jl:29,90): the same five Chains built on Nz (Dense(Nz, 4Nz) ... Dense(4Nz, Nz - 1)) are
+        // embedded in their 32-level versions: weights zero-padded (a padded hidden unit is relu(0) = 0, a padded input level meets a zero
+        // column of W1), the column lives in levels [0, Nz) and the kernels put the top flux on face Nz.  FP32 SIMT kernels, Tsit5, host-buffer calls.
+        if (cfg->alg != NFC_ALG_TSIT5) return fail(nullptr, -3, "Nz < 32 is supported with Tsit5 only");
+        const int nzu = cfg->Nz, cw = cfg->conv_width, nl = cfg->n_layers;
+        if (nl < 2 || nl > NFC_MAX_LAYERS || (cw != 0 && cw != 2 && cw != 4)) return fail(nullptr, -3, "unsupported Chain");
+        const int Hs = cfg->layer_dims[1], Hp = Hs == 4 * nzu ? 128 : (Hs == 8 * nzu ? 256 : -1);
+        if (Hp < 0 || cfg->layer_dims[0] != nzu - (cw ? cw - 1 : 0) || cfg->layer_dims[nl] != nzu - 1)
+            return fail(nullptr, -3, "unsupported Chain for Nz = %d: need [Conv(2|4)] -> Dense(in, H, relu) -> Dense(H, H, relu)x(1|2) -> Dense(H, Nz - 1), H in {4 Nz, 8 Nz}", nzu);
+        for (int l = 1; l < nl; ++l) if (cfg->layer_dims[l] != Hs) return fail(nullptr, -3, "unsupported Chain: hidden widths differ");
+        padded.Nz = NZ;
+        padded.layer_dims[0] = NZ - (cw ? cw - 1 : 0);
+        for (int l = 1; l < nl; ++l) padded.layer_dims[l] = Hp;
+        padded.layer_dims[nl] = NZ - 1;
+        // Flux.destructure order: [conv weights (k), conv bias], then per Dense layer W (out x in, column-major) and b (out)
+        int64_t pu = 0, pp = 0;
+        if (cw) { for (int j = 0; j <= cw; ++j) theta_map.push_back(pp + j); pu += cw + 1; pp += cw + 1; }
+        for (int l = 0; l < nl; ++l) {
+            const int is = cfg->layer_dims[l], os = cfg->layer_dims[l + 1], ip = padded.layer_dims[l], op = padded.layer_dims[l + 1];
+            for (int i = 0; i < is; ++i) for (int o = 0; o < os; ++o) theta_map.push_back(pp + (int64_t)i * op + o);
+            for (int o = 0; o < os; ++o) theta_map.push_back(pp + (int64_t)ip * op + o);
+            pu += (int64_t)is * os + os; pp += (int64_t)ip * op + op;
+        }
+        cfg = &padded;
+    }
     if (cfg->alg != NFC_ALG_TSIT5 && cfg->alg != NFC_ALG_RKC2) return fail(nullptr, -3, "unsupported algorithm id %d (Tsit5 = 0, RKC2 = 1)", cfg->alg);
     if (cfg->alg == NFC_ALG_RKC2 && cfg->fixed_dt > 0.f) return fail(nullptr, -3, "fixed_dt is a Tsit5 option; RKC2 chooses step and stage count itself");
     if (cfg->nde_type != NFC_NDE_FREE_CONVECTION && cfg->nde_type != NFC_NDE_CONVECTIVE_ADJUSTMENT) return fail(nullptr, -2, "bad nde_type");
@@ -639,6 +669,9 @@ int32_t nfc_create(const nfc_config* cfg, nfc_handle** out) {
     h->saveat.assign(cfg->saveat, cfg->saveat + cfg->n_save);
     h->cfg.saveat = nullptr;
     h->arch = a;
+    h->nz = user_nz;
+    h->n_params_user = (int64_t)theta_map.size();
+    h->theta_map = std::move(theta_map);
     h->device = cfg->device;
     h->num_sms = prop.multiProcessorCount;
     auto bail = [&](int code) { create_error() = h->err; nfc_destroy(h); return code; };
@@ -699,6 +732,10 @@ int32_t nfc_create(const nfc_config* cfg, nfc_handle** out) {
         const char* e = getenv("NFC_TC");
         h->use_tc = !(e && atoi(e) == 0);
     }
+    if (h->nz < NZ) {       // embedded Chain: FP32 SIMT kernels (the tensor-core and one-column-per-CTA kernels place the top flux on face 32)
+        h->use_tc = false; h->fwd_small_max = 0; h->adj_small_max = 0;
+        for (int64_t m : h->theta_map) if (m < 0 || m >= h->n_params) { h->err = "internal: parameter map out of range"; return bail(-3); }
+    }
     if (const char* e = getenv("NFC_TAPE_MODE")) h->tape_mode = std::max(0, std::min(2, atoi(e)));     // adjoint tape: 0 auto, 1 dense, 2 compact
     if (h->d_theta.ensure(h->n_params) || h->d_wpack.ensure(h->n_packed) || h->d_saveat.ensure(h->saveat.size()) ||
         h->d_counters.ensure(CTR_COUNT)) { h->err = "cudaMalloc failed"; return bail(-10); }
@@ -727,10 +764,34 @@ int32_t nfc_destroy(nfc_handle* h) {
     return 0;
 }
 
-int64_t nfc_n_params(const nfc_handle* h) { return h ? h->n_params : -1; }
+int64_t nfc_n_params(const nfc_handle* h) { return h ? (h->nz < NZ ? h->n_params_user : h->n_params) : -1; }
+
+namespace {
+// Nz < 32: host-buffer calls run on padded copies of the caller's arrays ([..][nz] rows -> [..][32] rows, zeros above level nz)
+struct PadGuard { nfc_handle* h; explicit PadGuard(nfc_handle* hh) : h(hh) { h->in_pad = true; } ~PadGuard() { h->in_pad = false; } };
+inline bool needs_pad(const nfc_handle* h) { return h && h->nz < NZ && !h->in_pad; }
+std::vector<float> pad_rows(const float* src, size_t rows, int w_in, int w_out) {
+    std::vector<float> out(rows * (size_t)w_out, 0.f);
+    for (size_t r = 0; r < rows; ++r) memcpy(&out[r * w_out], src + r * w_in, sizeof(float) * w_in);
+    return out;
+}
+void unpad_rows(const std::vector<float>& src, float* dst, size_t rows, int w_in, int w_out) {
+    for (size_t r = 0; r < rows; ++r) memcpy(dst + r * w_out, &src[r * w_in], sizeof(float) * w_out);
+}
+int no_dev_calls(nfc_handle* h, const char* what) {
+    return fail(h, -3, "%s: not available for Nz = %d (Nz < 32 runs through the host-buffer calls nfc_rhs / nfc_solve / nfc_diagnose_flux / nfc_loss_grad)", what, h->nz);
+}
+}  // namespace
 
 int32_t nfc_set_weights(nfc_handle* h, const float* theta, int64_t n) {
     if (!h || !theta) return -1;
+    if (needs_pad(h)) {
+        if (n != h->n_params_user) return fail(h, -2, "theta has %lld elements, the Chain needs %lld", (long long)n, (long long)h->n_params_user);
+        std::vector<float> full((size_t)h->n_params, 0.f);
+        for (int64_t i = 0; i < n; ++i) full[(size_t)h->theta_map[(size_t)i]] = theta[i];
+        PadGuard g(h);
+        return nfc_set_weights(h, full.data(), h->n_params);
+    }
     if (n != h->n_params) return fail(h, -2, "theta has %lld elements, the Chain needs %lld", (long long)n, (long long)h->n_params);
     NFC_CUDA(h, cudaSetDevice(h->device));
     NFC_CUDA(h, cudaMemcpyAsync(h->d_theta.p, theta, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
@@ -820,6 +881,7 @@ int32_t nfc_set_option(nfc_handle* h, const char* name, int64_t value) {
     if (!h || !name) return -1;
     const std::string n(name);
     const bool def = h->arch == ARCH_DEFAULT;
+    if (h->nz < NZ && (n == "tc" || n == "fwd_small_max" || n == "adj_small_max")) return fail(h, -3, "option '%s' is fixed for Nz < 32 (FP32 SIMT kernels)", name);
     if (n == "tc") { if (value && !tc_forward_arch(h->arch)) return fail(h, -3, "no tensor-core kernels for the wider Chain"); h->use_tc = value != 0; }
     else if (n == "tc_tiles") { if (value < 0 || value > 2) return fail(h, -2, "tc_tiles: 0 (auto), 1 or 2"); h->tc_tiles = (int)value; }
     else if (n == "tc2_min_columns") h->tc2_min_columns = value;
@@ -926,6 +988,7 @@ int32_t nfc_get_counters(const nfc_handle* hc, nfc_counters* out) {
 // ------------------------------------------ device-pointer calls ------------------------------------------
 int32_t nfc_rhs_dev(nfc_handle* h, const float* T, const float* colp, const float* glob, float* dTdt, int64_t B, void* stream) {
     if (int rc = check_ready(h, B)) return rc;
+    if (h->nz < NZ) return no_dev_calls(h, "nfc_rhs_dev");
     if (B == 0) return 0;
     if (!glob) return fail(h, -1, "null glob");
     const float* g = glob;   // glob is always a HOST pointer (4 scalars)
@@ -937,6 +1000,7 @@ int32_t nfc_rhs_dev(nfc_handle* h, const float* T, const float* colp, const floa
 int32_t nfc_solve_dev(nfc_handle* h, const float* T0, const float* colp, const float* glob, float* Tout, int32_t* naccept, int32_t* nreject,
                       int32_t* status, int64_t B, void* stream) {
     if (int rc = check_ready(h, B)) return rc;
+    if (h->nz < NZ) return no_dev_calls(h, "nfc_solve_dev");
     if (B == 0) return 0;
     if (!glob) return fail(h, -1, "null glob");
     const float* g = glob;   // glob is always a HOST pointer (4 scalars)
@@ -948,6 +1012,7 @@ int32_t nfc_solve_dev(nfc_handle* h, const float* T0, const float* colp, const f
 int32_t nfc_loss_grad_dev(nfc_handle* h, const float* T0, const float* colp, const float* glob, const float* Ttrue, double* loss_sum_dev,
                           float* grad_dev, int32_t* status, int64_t B, int64_t n_total_columns, void* stream) {
     if (int rc = check_ready(h, B)) return rc;
+    if (h->nz < NZ) return no_dev_calls(h, "nfc_loss_grad_dev");
     if (!glob) return fail(h, -1, "null glob");
     const float* g = glob;   // glob is always a HOST pointer (4 scalars)
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
@@ -960,6 +1025,13 @@ int32_t nfc_rhs(nfc_handle* h, const float* T, const float* colp, const float* g
     if (int rc = check_ready(h, B)) return rc;
     if (B == 0) return 0;
     if (!T || !colp || !glob || !dTdt) return fail(h, -1, "null argument");
+    if (needs_pad(h)) {
+        std::vector<float> Tp = pad_rows(T, (size_t)B, h->nz, NZ), out((size_t)B * NZ);
+        PadGuard g(h);
+        if (int rc = nfc_rhs(h, Tp.data(), colp, glob, out.data(), B)) return rc;
+        unpad_rows(out, dTdt, (size_t)B, NZ, h->nz);
+        return 0;
+    }
     NFC_CUDA(h, h->s_T0.ensure((size_t)B * NZ));
     NFC_CUDA(h, h->s_colp.ensure((size_t)B * 3));
     NFC_CUDA(h, h->s_out.ensure((size_t)B * NZ));
@@ -978,6 +1050,14 @@ int32_t nfc_solve(nfc_handle* h, const float* T0, const float* colp, const float
     if (int rc = check_ready(h, B)) return rc;
     if (B == 0) return 0;
     if (!T0 || !colp || !glob || !Tout) return fail(h, -1, "null argument");
+    if (needs_pad(h)) {
+        const size_t rows = (size_t)B * h->cfg.n_save;
+        std::vector<float> Tp = pad_rows(T0, (size_t)B, h->nz, NZ), out(rows * NZ);
+        PadGuard g(h);
+        if (int rc = nfc_solve(h, Tp.data(), colp, glob, out.data(), naccept, nreject, status, B)) return rc;
+        unpad_rows(out, Tout, rows, NZ, h->nz);
+        return 0;
+    }
     const size_t nout = (size_t)B * h->cfg.n_save * NZ;
     NFC_CUDA(h, h->s_T0.ensure((size_t)B * NZ));
     NFC_CUDA(h, h->s_colp.ensure((size_t)B * 3));
@@ -1073,6 +1153,7 @@ int32_t nfc_solve(nfc_handle* h, const float* T0, const float* colp, const float
 int32_t nfc_solve_ensemble(nfc_handle* h, const float* theta_members, int64_t E, const float* T0, const float* colp, const float* glob,
                            float* Tout, int32_t* naccept, int32_t* nreject, int32_t* status, int64_t S) {
     if (!h) return -1;
+    if (h->nz < NZ) return no_dev_calls(h, "nfc_solve_ensemble");
     if (E < 0 || S < 0) return fail(h, -2, "negative ensemble size");
     if (h->cfg.alg != NFC_ALG_TSIT5) return fail(h, -3, "nfc_solve_ensemble needs a Tsit5 handle");
     if (E > 65535) return fail(h, -2, "at most 65535 ensemble members per call (got %lld)", (long long)E);
@@ -1112,6 +1193,14 @@ int32_t nfc_diagnose_flux(nfc_handle* h, const float* Tsol, const float* colp, f
     if (int rc = check_ready(h, B)) return rc;
     if (B == 0) return 0;
     if (!Tsol || !colp || !wT) return fail(h, -1, "null argument");
+    if (needs_pad(h)) {
+        const size_t rows = (size_t)B * h->cfg.n_save;
+        std::vector<float> Tp = pad_rows(Tsol, rows, h->nz, NZ), out(rows * (NZ + 1));
+        PadGuard g(h);
+        if (int rc = nfc_diagnose_flux(h, Tp.data(), colp, out.data(), B)) return rc;
+        unpad_rows(out, wT, rows, NZ + 1, h->nz + 1);
+        return 0;
+    }
     const size_t nin = (size_t)B * h->cfg.n_save * NZ, nout = (size_t)B * h->cfg.n_save * (NZ + 1);
     NFC_CUDA(h, h->s_true.ensure(nin));
     NFC_CUDA(h, h->s_colp.ensure((size_t)B * 3));
@@ -1129,6 +1218,7 @@ int32_t nfc_diagnose_flux(nfc_handle* h, const float* Tsol, const float* colp, f
 int32_t nfc_embedded_solve(nfc_handle* h, const float* T0, const float* heat_flux, const float* scal, float Lz, float dt, float K,
                            float bottom_gradient, int32_t n_steps, int32_t save_every, float* Tout, int64_t B) {
     if (int rc = check_ready(h, B)) return rc;
+    if (h->nz < NZ) return no_dev_calls(h, "nfc_embedded_solve");
     if (B == 0) return 0;
     if (!T0 || !heat_flux || !scal || !Tout) return fail(h, -1, "null argument");
     if (n_steps < 1 || save_every < 1 || !(dt > 0.f) || !(Lz > 0.f) || !(scal[1] > 0.f)) return fail(h, -2, "bad step / scaling arguments");
@@ -1161,6 +1251,7 @@ int32_t nfc_embedded_solve(nfc_handle* h, const float* T0, const float* heat_flu
 int32_t nfc_embedded_diagnose_flux(nfc_handle* h, const float* Tsol, const float* heat_flux, const float* scal, float Lz, float K, int32_t n_out,
                                    float* wT, int64_t B) {
     if (int rc = check_ready(h, B)) return rc;
+    if (h->nz < NZ) return no_dev_calls(h, "nfc_embedded_diagnose_flux");
     if (B == 0) return 0;
     if (!Tsol || !heat_flux || !scal || !wT) return fail(h, -1, "null argument");
     if (n_out < 1 || !(Lz > 0.f) || !(scal[1] > 0.f) || !(scal[3] > 0.f)) return fail(h, -2, "bad profile count / scaling arguments");
@@ -1192,6 +1283,15 @@ int32_t nfc_loss_grad(nfc_handle* h, const float* T0, const float* colp, const f
     if (int rc = check_ready(h, B)) return rc;
     if (B == 0 && !h->nccl_comm) return fail(h, -2, "loss over zero columns is undefined");
     if ((B > 0 && (!T0 || !colp || !Ttrue)) || !glob || !loss || !grad_theta) return fail(h, -1, "null argument");
+    if (needs_pad(h)) {
+        if (h->nccl_comm) return fail(h, -3, "Nz < 32 with a communicator is not supported");
+        const size_t rows = (size_t)B * h->cfg.n_save;
+        std::vector<float> T0p = pad_rows(T0, (size_t)B, h->nz, NZ), Ttp = pad_rows(Ttrue, rows, h->nz, NZ), gfull((size_t)h->n_params);
+        PadGuard g(h);
+        if (int rc = nfc_loss_grad(h, T0p.data(), colp, glob, Ttp.data(), loss, gfull.data(), status, B)) return rc;
+        for (int64_t i = 0; i < h->n_params_user; ++i) grad_theta[i] = gfull[(size_t)h->theta_map[(size_t)i]];
+        return 0;
+    }
     const size_t ntraj = (size_t)B * h->cfg.n_save * NZ;
     NFC_CUDA(h, h->s_T0.ensure((size_t)std::max<int64_t>(B, 1) * NZ));
     NFC_CUDA(h, h->s_colp.ensure((size_t)std::max<int64_t>(B, 1) * 3));

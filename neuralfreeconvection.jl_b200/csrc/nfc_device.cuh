@@ -337,16 +337,21 @@ __device__ __forceinline__ void nn_forward_tile(const float* __restrict__ sW, fl
 
 // Flux divergence + convective adjustment for one column (lane == level k):
 //   F_lo = k==0 ? bottom : NN[k-1] - min(0, K_CA * (T_k - T_{k-1}) / dz),   f_k = -pref * (F_hi - F_lo) / dz,  1/dz = Nz
-__device__ __forceinline__ float flux_divergence(float yk, const float* __restrict__ sYc, float bottom, float top, float kca, float pref, int lane) {
+// nz < 32 (--grid-points, train_free_convection_nde.jl:29,90): the column lives in levels [0, nz) of the 32-level layout (the Chain is
+// zero-padded on the host, nfc_api.cu); the top flux sits on face nz and the levels above do not move.
+__device__ __forceinline__ float flux_divergence(float yk, const float* __restrict__ sYc, float bottom, float top, float kca, float pref, int lane,
+                                                 int nz = NZ) {
     const float ylo = __shfl_up_sync(FULL, yk, 1);
+    const float fnz = (float)nz;
     float Flo = bottom;
     if (lane > 0) {
-        const float d = kca * ((yk - ylo) * (float)NZ);
+        const float d = kca * ((yk - ylo) * fnz);
         Flo = sYc[lane - 1] - fminf(d, 0.f);
     }
     float Fhi = __shfl_down_sync(FULL, Flo, 1);
-    if (lane == NZ - 1) Fhi = top;
-    return -pref * ((Fhi - Flo) * (float)NZ);
+    if (lane == nz - 1) Fhi = top;
+    const float f = -pref * ((Fhi - Flo) * fnz);
+    return lane < nz ? f : 0.f;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -40,6 +40,7 @@ struct SolveParams {
     int* tape_len;             // [B]
     double* loss_sum;          // [1]
     int tape_cap;
+    int nz;                    // vertical levels in use (<= 32; 0 means 32): FP32 SIMT kernels only
     const long long* tape_off; // [B + 1] first tape row of every column (compact tape: a counting pass sized every column's share) or null
 };
 
@@ -65,11 +66,11 @@ __global__ void pack_weights_kernel(const float* __restrict__ theta, float* __re
 // ---------------------------------------------------------------------------------------------------
 template <class N>
 __device__ __forceinline__ void rhs_tile(const float* sW, float* ws, const float (&y)[CPW], float (&f)[CPW], const float* bot,
-                                         const float* top, const float* kca, float pref, int lane) {
+                                         const float* top, const float* kca, float pref, int lane, int nz = NZ) {
     nn_forward_tile<N>(sW, ws, y, lane);
     const float* sY = ws + N::S_Y;
 #pragma unroll
-    for (int c = 0; c < CPW; ++c) f[c] = flux_divergence(y[c], sY + c * YS, bot[c], top[c], kca[c], pref, lane);
+    for (int c = 0; c < CPW; ++c) f[c] = flux_divergence(y[c], sY + c * YS, bot[c], top[c], kca[c], pref, lane, nz);
     // the next nn_forward_tile writes sX/sA first and reaches sY only after several __syncwarp()s
 }
 
@@ -77,7 +78,8 @@ __device__ __forceinline__ void rhs_tile(const float* sW, float* ws, const float
 template <class N, int MODE>
 __device__ __forceinline__ void rhs_init_group(const float* sW, float* ws, long long col0, long long colEnd, const float* __restrict__ T,
                                                const float* __restrict__ colp, float* __restrict__ out, float* __restrict__ dt_out, float pref,
-                                               int use_kca, float reltol, float abstol, float tf, float fixed_dt, int lane) {
+                                               int use_kca, float reltol, float abstol, float tf, float fixed_dt, int lane, int nz = NZ) {
+    const float inz = 1.f / (float)nz;          // RMS norms run over the nz real levels (the padded ones hold zeros)
     float y[CPW], f0[CPW], bot[CPW], top[CPW], kca[CPW];
 #pragma unroll
     for (int c = 0; c < CPW; ++c) {
@@ -88,7 +90,7 @@ __device__ __forceinline__ void rhs_init_group(const float* sW, float* ws, long 
         top[c] = ok ? colp[col * 3 + 1] : 0.f;
         kca[c] = (ok && use_kca) ? colp[col * 3 + 2] : 0.f;
     }
-    rhs_tile<N>(sW, ws, y, f0, bot, top, kca, pref, lane);
+    rhs_tile<N>(sW, ws, y, f0, bot, top, kca, pref, lane, nz);
 #pragma unroll
     for (int c = 0; c < CPW; ++c) {
         const long long col = col0 + c;
@@ -101,18 +103,18 @@ __device__ __forceinline__ void rhs_init_group(const float* sW, float* ws, long 
         for (int c = 0; c < CPW; ++c) {
             const float sk = abstol + fabsf(y[c]) * reltol;
             const float a = y[c] / sk, b = f0[c] / sk;
-            const float d0 = sqrtf(warp_sum(a * a) * (1.f / NZ));
-            d1[c] = sqrtf(warp_sum(b * b) * (1.f / NZ));
+            const float d0 = sqrtf(warp_sum(a * a) * inz);
+            d1[c] = sqrtf(warp_sum(b * b) * inz);
             float t = (d0 < 1e-5f || d1[c] < 1e-5f) ? 1e-6f : 0.01f * d0 / d1[c];
             dt0[c] = fminf(t, tf);
             y1[c] = fmaf(dt0[c], f0[c], y[c]);
         }
-        rhs_tile<N>(sW, ws, y1, f1, bot, top, kca, pref, lane);
+        rhs_tile<N>(sW, ws, y1, f1, bot, top, kca, pref, lane, nz);
 #pragma unroll
         for (int c = 0; c < CPW; ++c) {
             const float sk = abstol + fabsf(y[c]) * reltol;
             const float a = (f1[c] - f0[c]) / sk;
-            const float d2 = sqrtf(warp_sum(a * a) * (1.f / NZ)) / dt0[c];
+            const float d2 = sqrtf(warp_sum(a * a) * inz) / dt0[c];
             const float m = fmaxf(d1[c], d2);
             const float dt1 = (m <= 1e-15f) ? fmaxf(1e-6f, dt0[c] * 1e-3f) : powf(10.0f, -(2.0f + log10f(m)) / 5.0f);
             float dt = fminf(fminf(100.0f * dt0[c], dt1), tf);
@@ -126,7 +128,7 @@ __device__ __forceinline__ void rhs_init_group(const float* sW, float* ws, long 
 template <class N, bool WS, int MODE>
 __global__ void __launch_bounds__(256, 1)
 rhs_init_kernel(const float* __restrict__ wpack, const float* __restrict__ T, const float* __restrict__ colp, float* __restrict__ out,
-                float* __restrict__ dt_out, long long B, float pref, int use_kca, float reltol, float abstol, float tf, float fixed_dt) {
+                float* __restrict__ dt_out, long long B, float pref, int use_kca, float reltol, float abstol, float tf, float fixed_dt, int nz) {
     extern __shared__ __align__(16) float smem[];
     __shared__ uint64_t bar;
     const float* sW = WS ? smem : wpack;
@@ -135,7 +137,7 @@ rhs_init_kernel(const float* __restrict__ wpack, const float* __restrict__ T, co
     float* ws = smem + (WS ? N::P_TOTAL : 0) + warp * N::S_TOTAL;
     const long long ngroups = (B + CPW - 1) / CPW;
     for (long long g = (long long)blockIdx.x * nw + warp; g < ngroups; g += (long long)gridDim.x * nw)
-        rhs_init_group<N, MODE>(sW, ws, g * CPW, B, T, colp, out, dt_out, pref, use_kca, reltol, abstol, tf, fixed_dt, lane);
+        rhs_init_group<N, MODE>(sW, ws, g * CPW, B, T, colp, out, dt_out, pref, use_kca, reltol, abstol, tf, fixed_dt, lane, nz);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -183,7 +185,7 @@ static __constant__ float c_tsit5_a[6][6] = {
 // ks[j] of not-yet-computed stages must be finite (they are multiplied by the zero padding).
 template <class N>
 __device__ __forceinline__ void tsit5_stages(const float* sW, float* ws, const WarpSlots* sl, const float (&u)[CPW], float (&ks)[7][CPW],
-                                             float (&y)[CPW], float pref, int lane) {
+                                             float (&y)[CPW], float pref, int lane, int nz = NZ) {
 #pragma unroll 1
     for (int s = 0; s < 6; ++s) {
         const float a0 = c_tsit5_a[s][0], a1 = c_tsit5_a[s][1], a2 = c_tsit5_a[s][2], a3 = c_tsit5_a[s][3], a4 = c_tsit5_a[s][4],
@@ -196,7 +198,7 @@ __device__ __forceinline__ void tsit5_stages(const float* sW, float* ws, const W
             y[c] = fmaf(sl->h[c], acc, u[c]);
         }
         float f[CPW];
-        rhs_tile<N>(sW, ws, y, f, sl->bot, sl->top, sl->kca, pref, lane);
+        rhs_tile<N>(sW, ws, y, f, sl->bot, sl->top, sl->kca, pref, lane, nz);
 #pragma unroll
         for (int c = 0; c < CPW; ++c) {
             if (s == 0) ks[1][c] = f[c];
@@ -255,6 +257,8 @@ template <class N, bool RECORD, bool ENS>
 __device__ __forceinline__ void solve_warp(const SolveParams& P, const float* sW, float* ws, WarpSlots* sl, int lane, const MemberQueue& mq) {
     float u[CPW], ks[7][CPW], y[CPW];
     double lsum = 0.0;   // this warp's sum of squared residuals (RECORD mode)
+    const int nz = (!ENS && P.nz > 0) ? P.nz : NZ;
+    const float inz = 1.f / (float)nz;
 #pragma unroll
     for (int c = 0; c < CPW; ++c) {
 #pragma unroll
@@ -277,7 +281,7 @@ __device__ __forceinline__ void solve_warp(const SolveParams& P, const float* sW
             sl->h[lane] = h; sl->flag[lane] = fl;
         }
         __syncwarp();
-        tsit5_stages<N>(sW, ws, sl, u, ks, y, P.pref, lane);   // y == u_new, ks[6] == f(u_new) (FSAL)
+        tsit5_stages<N>(sW, ws, sl, u, ks, y, P.pref, lane, nz);   // y == u_new, ks[6] == f(u_new) (FSAL)
 
         // ---- error estimate (RMS of err/(abstol + max(|u|,|unew|) reltol)), every lane gets all 8 ----
         float ee = 0.f;
@@ -290,7 +294,7 @@ __device__ __forceinline__ void solve_warp(const SolveParams& P, const float* sW
             const float sc = P.abstol + fmaxf(fabsf(u[c]), fabsf(y[c])) * P.reltol;
             const float r = e / sc;
             const float ss = warp_sum(r * r);
-            if (lane == c) ee = sqrtf(ss * (1.f / NZ));
+            if (lane == c) ee = sqrtf(ss * inz);
         }
         // ---- PI controller (OrdinaryDiffEq defaults for Tsit5), lane c handles column c ----
         if (lane < CPW && sl->col[lane] >= 0) {
@@ -472,7 +476,7 @@ static __global__ void sched_scatter_kernel(const int* __restrict__ work, int* _
 template <class N, bool WS>
 __global__ void __launch_bounds__(256, 1)
 diagnose_flux_kernel(const float* __restrict__ wpack, const float* __restrict__ Tsol, const float* __restrict__ colp, float* __restrict__ wT,
-                     long long B, int n_save, int use_kca) {
+                     long long B, int n_save, int use_kca, int nz) {
     extern __shared__ __align__(16) float smem[];
     __shared__ uint64_t bar;
     const float* sW = WS ? smem : wpack;
@@ -494,9 +498,10 @@ diagnose_flux_kernel(const float* __restrict__ wpack, const float* __restrict__ 
             const float kca = use_kca ? colp[col * 3 + 2] : 0.f;
             const float ylo = __shfl_up_sync(FULL, y[c], 1);
             float F = colp[col * 3 + 0];
-            if (lane > 0) F = sY[c * YS + lane - 1] - fminf(kca * ((y[c] - ylo) * (float)NZ), 0.f);
-            wT[p * (NZ + 1) + lane] = F;
-            if (lane == 0) wT[p * (NZ + 1) + NZ] = colp[col * 3 + 1];
+            if (lane > 0) F = sY[c * YS + lane - 1] - fminf(kca * ((y[c] - ylo) * (float)nz), 0.f);
+            if (lane < nz) wT[p * (NZ + 1) + lane] = F;
+            else if (lane > nz) wT[p * (NZ + 1) + lane] = 0.f;
+            if (lane == 0) wT[p * (NZ + 1) + nz] = colp[col * 3 + 1];        // top flux on face nz
         }
         __syncwarp();
     }

@@ -56,6 +56,12 @@ struct nfc_handle {
     nfc::Arch arch = nfc::ARCH_NONE;
     int device = 0, num_sms = 0;
     int64_t n_params = 0, n_packed = 0;
+    // Nz < 32 (--grid-points): the caller's Chain and columns are embedded in the 32-level kernels (zero-padded weights, levels [0, nz));
+    // cfg holds the PADDED Chain, theta_map[user index] = index in the padded parameter vector (nfc_api.cu)
+    int nz = 32;
+    int64_t n_params_user = 0;
+    std::vector<int64_t> theta_map;
+    bool in_pad = false;                    // a host-buffer call is running on padded copies of the caller's arrays
     bool weights_set = false;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev_chunk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
