@@ -71,6 +71,7 @@ struct AdjScratch {     // per-warp shared-memory scratch of the backward pass, 
 struct AdjSlots {
     int col[CPW];
     float t[CPW], dt[CPW], h[CPW], qold[CPW], tstop[CPW], bot[CPW], top[CPW], kca[CPW], dt_retry[CPW];
+    int rejrow[CPW];             // rejections in a row (adj_reject_dt)
     float th[CPW], hn[CPW];      // this stage's position inside tape interval ipos: theta in [0, 1] and the interval length
     int si[CPW], nacc[CPW], nrej[CPW], flag[CPW], mode[CPW], ipos[CPW], tlen[CPW], status[CPW];
 };
@@ -261,7 +262,7 @@ __device__ __forceinline__ bool adj_fill_slot(const AdjParams& P, AdjSlots* sl, 
         if (lane == 0) {
             const float* last = P.tape + (tape_row0(P, next) + (len - 1)) * TAPE_STRIDE;
             sl->col[c] = (int)next; sl->t[c] = P.tf; sl->tstop[c] = P.saveat[P.n_save - 2]; sl->si[c] = P.n_save - 2;
-            sl->dt[c] = P.fixed_dt > 0.f ? P.fixed_dt : last[TAPE_H]; sl->qold[c] = 1e-4f; sl->nacc[c] = 0; sl->nrej[c] = 0; sl->flag[c] = 0;
+            sl->dt[c] = P.fixed_dt > 0.f ? P.fixed_dt : last[TAPE_H]; sl->qold[c] = 1e-4f; sl->nacc[c] = 0; sl->nrej[c] = 0; sl->flag[c] = 0; sl->rejrow[c] = 0;
             sl->mode[c] = 0; sl->ipos[c] = len - 1; sl->tlen[c] = len; sl->status[c] = ST_OK; sl->dt_retry[c] = 0.f;
             sl->bot[c] = P.colp[next * 3 + 0]; sl->top[c] = P.colp[next * 3 + 1]; sl->kca[c] = P.use_kca ? P.colp[next * 3 + 2] : 0.f;
         }
@@ -522,9 +523,9 @@ __global__ void __launch_bounds__(ADJ_NW * 32, 1) adjoint_kernel(const AdjParams
                 if (accept) {
                     fl |= AFL_ACCEPT;
                     sl->t[lane] = (fl & AFL_LAST) ? sl->tstop[lane] : sl->t[lane] - h;
-                    if (P.fixed_dt <= 0.f) sl->qold[lane] = fmaxf(ee, 1e-4f);
+                    adj_accept_update(ee, h, sl->dt[lane], dtnew, P.fixed_dt <= 0.f, sl->qold[lane], sl->dt[lane]);
                     sl->nacc[lane] += 1;
-                    sl->dt[lane] = dtnew;
+                    sl->rejrow[lane] = 0;
                     if (fl & AFL_LAST) {
                         if (sl->si[lane] >= 1) { fl |= AFL_JUMP; }
                         else fl |= AFL_DONE;
@@ -532,7 +533,8 @@ __global__ void __launch_bounds__(ADJ_NW * 32, 1) adjoint_kernel(const AdjParams
                 } else {
                     sl->nrej[lane] += 1;
                     sl->mode[lane] = 1;                        // undo this step's quadrature contribution next iteration
-                    sl->dt_retry[lane] = dtnew;
+                    sl->dt_retry[lane] = dtnew = adj_reject_dt(ee, h, dtnew, sl->rejrow[lane]);
+                    sl->rejrow[lane] += 1;
                     if (dtnew < 1e-12f || sl->nacc[lane] + sl->nrej[lane] >= P.max_iters) { sl->status[lane] = dtnew < 1e-12f ? ST_DT_UNDERFLOW : ST_MAXITERS; }
                 }
                 if (sl->nacc[lane] + sl->nrej[lane] >= P.max_iters && !(fl & AFL_DONE)) sl->status[lane] = ST_MAXITERS;

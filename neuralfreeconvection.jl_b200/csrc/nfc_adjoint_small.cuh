@@ -31,6 +31,7 @@ constexpr size_t SMEM_BYTES = sizeof(float) * S_TOTAL;        // 104 KB
 struct Slot {
     int col, si, nacc, nrej, flag, mode, ipos, tlen, status;
     float t, dt, h, qold, tstop, bot, top, kca, dt_retry, tn, hn;
+    int rejrow;
     int icached;          // tape row held in shared memory (-1: none)
 };
 
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(NT, 1) adjoint_small_kernel(const float* __res
                 if (lane == 0) {
                     const float* last = P.tape + (tape_row0(P, next) + (len - 1)) * TAPE_STRIDE;
                     S.t = P.tf; S.tstop = P.saveat[P.n_save - 2]; S.si = P.n_save - 2;
-                    S.dt = P.fixed_dt > 0.f ? P.fixed_dt : last[TAPE_H]; S.qold = 1e-4f; S.nacc = 0; S.nrej = 0; S.flag = 0;
+                    S.dt = P.fixed_dt > 0.f ? P.fixed_dt : last[TAPE_H]; S.qold = 1e-4f; S.nacc = 0; S.nrej = 0; S.flag = 0; S.rejrow = 0;
                     S.mode = 0; S.ipos = len - 1; S.tlen = len; S.status = ST_OK; S.dt_retry = 0.f;
                     S.bot = P.colp[next * 3 + 0]; S.top = P.colp[next * 3 + 1]; S.kca = P.use_kca ? P.colp[next * 3 + 2] : 0.f;
                     S.icached = -1;
@@ -288,9 +289,9 @@ __global__ void __launch_bounds__(NT, 1) adjoint_small_kernel(const float* __res
                     if (accept) {
                         fl |= AFL_ACCEPT;
                         S.t = (fl & AFL_LAST) ? S.tstop : S.t - h;
-                        if (P.fixed_dt <= 0.f) S.qold = fmaxf(ee, 1e-4f);
+                        adj_accept_update(ee, h, S.dt, dtnew, P.fixed_dt <= 0.f, S.qold, S.dt);
                         S.nacc += 1;
-                        S.dt = dtnew;
+                        S.rejrow = 0;
                         if (fl & AFL_LAST) {
                             if (S.si >= 1) fl |= AFL_JUMP; else fl |= AFL_DONE;
                         }
@@ -300,7 +301,8 @@ __global__ void __launch_bounds__(NT, 1) adjoint_small_kernel(const float* __res
 #endif
                         S.nrej += 1;
                         S.mode = 1;                             // undo this step's quadrature contribution next iteration
-                        S.dt_retry = dtnew;
+                        S.dt_retry = dtnew = adj_reject_dt(ee, h, dtnew, S.rejrow);
+                        S.rejrow += 1;
                         if (dtnew < 1e-12f || S.nacc + S.nrej >= P.max_iters) S.status = dtnew < 1e-12f ? ST_DT_UNDERFLOW : ST_MAXITERS;
                     }
                     if (S.nacc + S.nrej >= P.max_iters && !(fl & AFL_DONE)) S.status = ST_MAXITERS;

@@ -61,6 +61,7 @@ struct AtcShared {
     // per-column slot state, owned by the quarter-0 thread of the column
     int col[TILE], si[TILE], nacc[TILE], nrej[TILE], mode[TILE], tlen[TILE], status[TILE], flag[TILE], jsi[TILE], ipos[TILE];
     float t[TILE], dt[TILE], h[TILE], qold[TILE], tstop[TILE], dt_retry[TILE], kk[TILE];
+    int rejrow[TILE];                                       // rejections in a row (adj_reject_dt)
     short ivp[7][TILE];                                     // tape interval of every stage of the current step
     long long row0[TILE];                                   // first tape row of the slot's column (dense or compact tape)
 };
@@ -302,9 +303,9 @@ __device__ __forceinline__ void atc_control(const AdjParams& P, AtcShared& S, in
             if (accept) {
                 fl |= AFL_ACCEPT;
                 S.t[c] = (fl & AFL_LAST) ? S.tstop[c] : S.t[c] - h;
-                if (P.fixed_dt <= 0.f) S.qold[c] = fmaxf(ee, 1e-4f);
+                adj_accept_update(ee, h, S.dt[c], dtnew, P.fixed_dt <= 0.f, S.qold[c], S.dt[c]);
                 S.nacc[c] += 1;
-                S.dt[c] = dtnew;
+                S.rejrow[c] = 0;
                 if (fl & AFL_LAST) {
                     if (S.si[c] >= 1) {
                         fl |= AFL_JUMP;
@@ -317,6 +318,8 @@ __device__ __forceinline__ void atc_control(const AdjParams& P, AtcShared& S, in
             } else {
                 S.nrej[c] += 1;
                 S.mode[c] = 1;
+                dtnew = adj_reject_dt(ee, h, dtnew, S.rejrow[c]);
+                S.rejrow[c] += 1;
                 S.dt_retry[c] = dtnew;
                 if (dtnew < 1e-12f) status = ST_DT_UNDERFLOW;
             }
@@ -347,7 +350,7 @@ __device__ __forceinline__ void atc_control(const AdjParams& P, AtcShared& S, in
             col = (int)next;
             S.row0[c] = r0;
             S.col[c] = col; S.t[c] = P.tf; S.tstop[c] = P.saveat[P.n_save - 2]; S.si[c] = P.n_save - 2;
-            S.dt[c] = P.fixed_dt > 0.f ? P.fixed_dt : last[TAPE_H]; S.qold[c] = 1e-4f; S.nacc[c] = 0; S.nrej[c] = 0;
+            S.dt[c] = P.fixed_dt > 0.f ? P.fixed_dt : last[TAPE_H]; S.qold[c] = 1e-4f; S.nacc[c] = 0; S.nrej[c] = 0; S.rejrow[c] = 0;
             S.mode[c] = 0; S.ipos[c] = len - 1; S.tlen[c] = len; S.status[c] = ST_OK; S.dt_retry[c] = 0.f;
             S.kk[c] = P.use_kca ? P.colp[next * 3 + 2] * (float)NZ : 0.f;
             break;

@@ -335,6 +335,24 @@ __device__ __forceinline__ void nn_forward_tile(const float* __restrict__ sW, fl
     __syncwarp();
 }
 
+// Backward solve, accepted step: a step cut short by a save time (h below the controller's proposal dtp) says nothing about the step
+// size the problem allows, so it neither enters the controller's error history nor replaces the proposal (growth capped at 10 h, the
+// controller's own qmax).  Otherwise the PI controller sees "tiny error, then normal error" at every one of the 128 save times and keeps
+// the steps ~ 25 % shorter than the tolerance asks for (oracle/nde_oracle.c:adjoint_continuous does the same).
+__device__ __forceinline__ void adj_accept_update(float ee, float h, float dtp, float dtnew, bool adaptive, float& qold, float& dt) {
+    const bool cut = adaptive && h < dtp;
+    if (adaptive && !cut) qold = fmaxf(ee, 1e-4f);
+    dt = cut ? fmaxf(dtnew, fminf(dtp, 10.f * h)) : dtnew;
+}
+
+// Backward solve, rejected step: lambda' = -J(u(t))^T lambda has a right-hand side that JUMPS in time wherever a temperature gradient
+// crosses zero (the active set of min(0, K dT/dz)), so across such a time the error estimate falls like h, not h^5, and the controller's
+// own shrink (~ 15 % per rejection at EEst ~ 2) needs 6-7 rejections in a row -- each one costs a cancel pass on top.  From the second
+// rejection in a row on, the new step assumes first-order behaviour: 0.9 h / EEst (at most 5 x shorter, the controller's qmin).
+__device__ __forceinline__ float adj_reject_dt(float ee, float h, float dtnew, int rejected_in_a_row) {
+    return (rejected_in_a_row >= 1 && isfinite(ee)) ? fminf(dtnew, fmaxf(0.2f * h, 0.9f * h / ee)) : dtnew;
+}
+
 // Flux divergence + convective adjustment for one column (lane == level k):
 //   F_lo = k==0 ? bottom : NN[k-1] - min(0, K_CA * (T_k - T_{k-1}) / dz),   f_k = -pref * (F_hi - F_lo) / dz,  1/dz = Nz
 // nz < 32 (--grid-points, train_free_convection_nde.jl:29,90): the column lives in levels [0, nz) of the 32-level layout (the Chain is

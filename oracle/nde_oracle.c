@@ -412,6 +412,7 @@ static void adjoint_continuous(const net_t *n, const float *th, const float *col
     float t = saveat[n_save - 1];
     float dt = fixed_dt > 0.f ? fixed_dt : tape->e[in].h;
     float qold = 1e-4f;
+    int rejrow = 0;      /* rejections in a row */
     for (int si = n_save - 1; si >= 1; --si) {
         for (int i = 0; i < N; ++i) lam[i] += resid[(int64_t)si * N + i];
         float tstop = saveat[si - 1];
@@ -419,6 +420,7 @@ static void adjoint_continuous(const net_t *n, const float *th, const float *col
             float h = fminf(dt, t - tstop);
             int last = (t - h) <= tstop + 1e-6f * saveat[n_save - 1] && (t - h) - tstop <= 0.05f * fabsf(h);   /* snap only when it stretches the step by < 5 %: no livelock on rejection */
             if (last) h = t - tstop;
+            const float dt_prop = dt;
             for (int p = 0; p < n->n_params; ++p) gstep[p] = 0.0;
             for (int s = 1; s <= 7; ++s) {
                 float a[6]; if (s > 1) a_row(s, a);
@@ -458,9 +460,20 @@ static void adjoint_continuous(const net_t *n, const float *th, const float *col
                 for (int p = 0; p < n->n_params; ++p) g[p] += gstep[p];
                 memcpy(lam, lnew, sizeof(float) * N);
                 t = last ? tstop : t - h;
-                if (fixed_dt <= 0.f) qold = fmaxf(EEst, 1e-4f);
+                /* a step cut short by the save time (h < the controller's proposal) neither enters the error history nor replaces the
+                   proposal (growth capped at 10 h): csrc/nfc_device.cuh:adj_accept_update */
+                const int cut = fixed_dt <= 0.f && h < dt_prop;
+                if (fixed_dt <= 0.f && !cut) qold = fmaxf(EEst, 1e-4f);
+                if (cut) dtnew = fmaxf(dtnew, fminf(dt_prop, 10.f * h));
                 ++*nacc;
-            } else ++*nrej;
+                rejrow = 0;
+            } else {
+                /* J(u(t))^T jumps in time where a gradient changes sign: there the error falls like h, not h^5; from the second rejection
+                   in a row on the new step assumes that (csrc/nfc_device.cuh:adj_reject_dt) */
+                if (rejrow >= 1 && isfinite(EEst)) dtnew = fminf(dtnew, fmaxf(0.2f * h, 0.9f * h / EEst));
+                ++rejrow;
+                ++*nrej;
+            }
             dt = dtnew;
             if (dt < 1e-12f) break;
         }
