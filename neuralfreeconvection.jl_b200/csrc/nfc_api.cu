@@ -449,6 +449,7 @@ int do_solve_ensemble(nfc_handle* h, const float* theta_members, int64_t E, int 
     P.Tout = Tout; P.naccept = nacc; P.nreject = nrej; P.status = status; P.counters = h->d_counters.p; P.B = B;
     P.n_save = h->cfg.n_save; P.max_iters = h->cfg.max_iters; P.use_kca = h->cfg.nde_type == NFC_NDE_CONVECTIVE_ADJUSTMENT;
     P.pref = pref; P.tf = h->saveat.back(); P.reltol = h->cfg.reltol; P.abstol = h->cfg.abstol; P.fixed_dt = h->cfg.fixed_dt;
+    P.nz = h->nz;
     NFC_CUDA(h, cudaMemsetAsync(h->d_counters.p, 0, sizeof(unsigned long long) * CTR_COUNT, st));
     NFC_CUDA(h, cudaEventRecord(h->ev[0], st));
     const int grid = (int)std::min<long long>(h->num_sms, E);

@@ -257,7 +257,7 @@ template <class N, bool RECORD, bool ENS>
 __device__ __forceinline__ void solve_warp(const SolveParams& P, const float* sW, float* ws, WarpSlots* sl, int lane, const MemberQueue& mq) {
     float u[CPW], ks[7][CPW], y[CPW];
     double lsum = 0.0;   // this warp's sum of squared residuals (RECORD mode)
-    const int nz = (!ENS && P.nz > 0) ? P.nz : NZ;
+    const int nz = P.nz > 0 ? P.nz : NZ;
     const float inz = 1.f / (float)nz;
 #pragma unroll
     for (int c = 0; c < CPW; ++c) {
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(NW * 32, 1) solve_ensemble_kernel(const SolveP
         const long long base = m * S;
         for (int g = warp; g * CPW < S; g += NW)
             rhs_init_group<N, 1>(sW, ws, base + g * CPW, base + S, P.T0, P.colp, k1_buf, dt_buf, P.pref, P.use_kca, P.reltol, P.abstol, P.tf,
-                                 P.fixed_dt, lane);
+                                 P.fixed_dt, lane, P.nz > 0 ? P.nz : NZ);     // run-time level count as in rhs_init_kernel / solve_kernel: one arithmetic, bit for bit
         __syncthreads();   // k1 / dt of the member's columns are visible to the whole CTA
         solve_warp<N, false, true>(P, sW, ws, &slots[warp], lane, MemberQueue{&s_next, base, S});
     }
