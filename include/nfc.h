@@ -176,6 +176,8 @@ int32_t nfc_get_adjoint_steps(nfc_handle* h, int32_t* out, int64_t n);
  *                    SM; 0 = never; forcing tc_tiles also bypasses it)
  *   adj_small_max    batches up to this many columns run the one-column-per-CTA backward kernel (default 7400; 0 = never)
  *   adj_tc           0: batch backward pass on the FP32 SIMT kernel instead of the tensor-core kernel
+ *   adj_heavy        how many of a chunk's longest columns (by the previous call's backward step counts) run on the one-column-per-CTA
+ *                    kernel next to the tensor-core backward kernel (default 48; 0 = none; chunks of at least 64 x adj_heavy columns)
  *   e2e_pieces       nfc_solve: pieces whose device->host copy overlaps the next piece's solve (0 = auto: 2 from 16384, 3 from 49152 columns)
  *   tc_split         0 = FP16x2 operands (3 MMAs per fp32 product, needs |T_scaled| <= 128; default), 1 = BF16x3 (6 MMAs, fp32's range)
  *   range_fallback   1 (default): nfc_solve re-solves columns that ended with status 5 on the BF16x3 split, nfc_loss_grad (no communicator)

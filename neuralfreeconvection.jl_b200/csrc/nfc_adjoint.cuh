@@ -34,6 +34,8 @@ namespace nfc { struct AdjParams; }
 // small batches of the default Chain: one column per CTA (nfc_adjoint_small.cuh); returns false when the batch kernel should run
 template <class N>
 bool adjoint_small_launch(nfc_handle* h, const nfc::AdjParams& A, int64_t nb, cudaStream_t st);
+// the n longest columns of a chunk on the one-column-per-CTA kernel, on the handle's high-priority side stream (default Chain)
+int adjoint_heavy_launch(nfc_handle* h, const nfc::AdjParams& A, int n, cudaStream_t st);
 
 namespace nfc {
 
@@ -55,6 +57,7 @@ struct AdjParams {
     long long B;
     int n_save, tape_cap, max_iters, use_kca, n_params;
     int nz;                     // vertical levels in use (<= 32; 0 means 32): adjoint_kernel only
+    int queue_ctr;              // index of this launch's queue head in counters[] (CTR_ADJ_QUEUE; the side launch of the longest columns has its own)
     float pref, tf, reltol, abstol, fixed_dt;
 };
 
@@ -616,8 +619,8 @@ int adjoint_loss_grad(nfc_handle* h, const float* T0, const float* colp, float p
     if (!loss_sum_dev || !grad_dev) return fail(h, -1, "null output");
     const int n_save = h->cfg.n_save, cap = h->cfg.adjoint_max_steps, grid = h->num_sms;
     NFC_CUDA(h, cudaMemsetAsync(loss_sum_dev, 0, 2 * sizeof(double), st));
-    NFC_CUDA(h, h->a_gacc.ensure((size_t)grid * h->n_params));
-    NFC_CUDA(h, cudaMemsetAsync(h->a_gacc.p, 0, sizeof(float) * (size_t)grid * h->n_params, st));
+    NFC_CUDA(h, h->a_gacc.ensure((size_t)2 * grid * h->n_params));        // rows [grid, 2 grid): the side launch of the longest columns
+    NFC_CUDA(h, cudaMemsetAsync(h->a_gacc.p, 0, sizeof(float) * (size_t)2 * grid * h->n_params, st));
     if (B == 0) {          // a rank without columns still takes part in the collective
         NFC_CUDA(h, cudaMemsetAsync(grad_dev, 0, sizeof(float) * h->n_params, st));
         if (h->nccl_comm) return comm_allreduce_grad(h, grad_dev, loss_sum_dev, st);
@@ -649,7 +652,7 @@ int adjoint_loss_grad(nfc_handle* h, const float* T0, const float* colp, float p
     h->a_off_host.clear();
     if (attempt > 0) {
         NFC_CUDA(h, cudaMemsetAsync(loss_sum_dev, 0, 2 * sizeof(double), st));
-        NFC_CUDA(h, cudaMemsetAsync(h->a_gacc.p, 0, sizeof(float) * (size_t)grid * h->n_params, st));
+        NFC_CUDA(h, cudaMemsetAsync(h->a_gacc.p, 0, sizeof(float) * (size_t)2 * grid * h->n_params, st));
     }
     if (compact) {
         if (!from_history) {
@@ -723,10 +726,11 @@ int adjoint_loss_grad(nfc_handle* h, const float* T0, const float* colp, float p
         // training loop solves the same columns every epoch), else the forward tape length (a forward-stiff column is usually
         // backward-stiff too, but outliers -- 1100 backward steps against a median of 350 -- are only known from history).
         const int* order = nullptr;
+        const int* key = nullptr;
         NFC_CUDA(h, h->a_adjsteps.ensure((size_t)B));
         if (h->a_adjhist_B != B) { h->a_adjhist_B = B; h->a_adjhist_valid = false; }
         if (h->use_sched && nb >= 2048) {
-            const int* key = h->a_adjhist_valid ? h->a_adjsteps.p + off : h->a_tlen.p;
+            key = h->a_adjhist_valid ? h->a_adjsteps.p + off : h->a_tlen.p;
             NFC_CUDA(h, h->d_order.ensure((size_t)nb));
             NFC_CUDA(h, h->d_hist.ensure(SCHED_BUCKETS));
             NFC_CUDA(h, cudaMemsetAsync(h->d_hist.p, 0, sizeof(int) * SCHED_BUCKETS, st));
@@ -744,14 +748,30 @@ int adjoint_loss_grad(nfc_handle* h, const float* T0, const float* colp, float p
         A.adj_steps = h->a_adjsteps.p + off;
         h->a_adjsteps_n = B;
         A.wpack = h->d_wpack.p; A.colp = colp + off * 3; A.saveat = h->d_saveat.p; A.resid = h->a_resid.p; A.tape = h->a_tape.p;
-        A.tape_off = tape_off; A.nz = h->nz;
+        A.tape_off = tape_off; A.nz = h->nz; A.queue_ctr = CTR_ADJ_QUEUE;
         A.tape_len = h->a_tlen.p; A.status = st_all + off; A.gacc = h->a_gacc.p; A.counters = h->d_counters.p; A.B = nb; A.n_save = n_save;
         A.tape_cap = cap; A.max_iters = h->cfg.max_iters; A.use_kca = h->cfg.nde_type == NFC_NDE_CONVECTIVE_ADJUSTMENT; A.n_params = (int)h->n_params;
         A.pref = pref; A.tf = h->saveat.back(); A.reltol = h->cfg.adjoint_reltol; A.abstol = h->cfg.adjoint_abstol; A.fixed_dt = h->cfg.fixed_dt;
         if (!adjoint_small_launch<N>(h, A, nb, st)) {
             // default Chain, FP16x2 operand scales available: the tensor-core backward kernel (nfc_adjoint_tc.cuh); else FP32 SIMT
             if (h->arch == ARCH_DEFAULT && h->use_tc && h->tc_fp16 && h->adj_tc && cap <= 32767) {
-                if (int rc = adjoint_tc_launch(h, A, h->atc_scales, nb, st)) return rc;
+                // Stragglers: a column with 4 x the median step count keeps its 128-column CTA alive alone (~ 75 us per pass).  Once the
+                // per-column backward step counts are known from the previous call, the adj_heavy longest columns (the head of the
+                // longest-first order) run on the one-column-per-CTA kernel instead (~ 20 us per pass), on a high-priority side stream next
+                // to the tensor-core kernel, whose CTAs on those SMs start when they are free (persistent CTAs, dynamic queue).
+                int n_heavy = 0;
+                if (order && key != h->a_tlen.p && h->adj_heavy > 0 && nb >= 64 * (int64_t)h->adj_heavy) n_heavy = (int)std::min<int64_t>(h->adj_heavy, h->num_sms);
+                if (n_heavy > 0) {
+                    if (int rc = adjoint_heavy_launch(h, A, n_heavy, st)) return rc;
+                    A.order = order + n_heavy;
+                    A.B = nb - n_heavy;
+                }
+                if (int rc = adjoint_tc_launch(h, A, h->atc_scales, A.B, st)) return rc;
+                if (n_heavy > 0) {
+                    NFC_CUDA(h, cudaEventRecord(h->ev_heavy[1], h->heavy_stream));
+                    NFC_CUDA(h, cudaStreamWaitEvent(st, h->ev_heavy[1], 0));
+                    h->last_launches += 1;
+                }
             } else adjoint_kernel<N, AdjLaunch<N>::WS><<<grid, ADJ_NW * 32, adj_smem_bytes<N>(), st>>>(A);
         }
         NFC_CUDA(h, cudaGetLastError());
@@ -764,7 +784,7 @@ int adjoint_loss_grad(nfc_handle* h, const float* T0, const float* colp, float p
     if (compact) h->a_count_valid = true;
     // with a communicator the sums stay un-normalised until the all-reduce has produced the global residual count
     const double ntot = h->nccl_comm ? 1.0 : (double)n_total_columns * n_save * h->nz;
-    grad_reduce_kernel<<<((int)h->n_params + 255) / 256, 256, 0, st>>>(h->a_gacc.p, grid, (int)h->n_params, 2.0 / ntot, grad_dev);
+    grad_reduce_kernel<<<((int)h->n_params + 255) / 256, 256, 0, st>>>(h->a_gacc.p, 2 * grid, (int)h->n_params, 2.0 / ntot, grad_dev);
     set_loss_count_kernel<<<1, 1, 0, st>>>(loss_sum_dev, (double)B * n_save * h->nz);
     NFC_CUDA(h, cudaGetLastError());
     if (h->nccl_comm) { if (int rc = comm_allreduce_grad(h, grad_dev, loss_sum_dev, st)) return rc; }

@@ -70,12 +70,14 @@ __global__ void __launch_bounds__(NT, 1) adjoint_small_kernel(const float* __res
     for (int j = 0; j < 7; ++j) kap[j] = 0.f;
     __syncthreads();
 
+    // side launch of a chunk's longest columns: tell the main stream that this kernel holds its SMs (wait_started_kernel, nfc_api.cu)
+    if (P.queue_ctr == CTR_ADJ_QUEUE_HEAVY && blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) atomicExch(&P.counters[CTR_HEAVY_STARTED], 1ULL);
     while (true) {
         // ---------------- next column (warp 0) ----------------
         if (warp == 0 && S.col < 0) {
             while (true) {
                 long long next = 0;
-                if (lane == 0) next = (long long)atomicAdd(&P.counters[CTR_ADJ_QUEUE], 1ULL);
+                if (lane == 0) next = (long long)atomicAdd(&P.counters[P.queue_ctr], 1ULL);
                 next = __shfl_sync(FULL, next, 0);
                 if (next >= P.B) break;
                 if (P.order) next = P.order[next];

@@ -339,7 +339,7 @@ __device__ __forceinline__ void atc_control(const AdjParams& P, AtcShared& S, in
         if (S.col[c] >= 0 || !queue_empty) fl |= AFL_NEWCOL;
         S.col[c] = -1; S.h[c] = 0.f; S.kk[c] = 0.f; S.mode[c] = 0; S.tlen[c] = 0; S.ipos[c] = 0; S.t[c] = 0.f; S.tstop[c] = 0.f;
         while (!queue_empty) {
-            long long next = (long long)atomicAdd(&P.counters[CTR_ADJ_QUEUE], 1ULL);
+            long long next = (long long)atomicAdd(&P.counters[P.queue_ctr], 1ULL);
             if (next >= P.B) { queue_empty = true; break; }
             if (P.order) next = P.order[next];
             const int len = P.tape_len[next];

@@ -343,6 +343,26 @@ bool adjoint_small_launch(nfc_handle* h, const nfc::AdjParams& A, int64_t nb, cu
         return false;
     }
 }
+// The tensor-core backward kernel behind the side launch must not take the SMs first (it would hold all 148 until its queue is empty):
+// the main stream waits until the side kernel's last CTA is running.
+static __global__ void wait_started_kernel(unsigned long long* flag) {
+    while (atomicAdd(flag, 0ULL) == 0ULL) __nanosleep(500);
+}
+int adjoint_heavy_launch(nfc_handle* h, const nfc::AdjParams& A, int n, cudaStream_t st) {
+    NFC_CUDA(h, cudaMemsetAsync(h->d_counters.p + nfc::CTR_ADJ_QUEUE_HEAVY, 0, 2 * sizeof(unsigned long long), st));     // queue head and the started flag
+    NFC_CUDA(h, cudaEventRecord(h->ev_heavy[0], st));                      // RECORD pass, order and the cleared queue head are in place
+    NFC_CUDA(h, cudaStreamWaitEvent(h->heavy_stream, h->ev_heavy[0], 0));
+    nfc::AdjParams H = A;
+    H.B = n;                                                               // the head of the longest-first order
+    H.gacc = A.gacc + (size_t)h->num_sms * h->n_params;                    // its own accumulator rows (plain read-modify-write at the kernel's end)
+    H.queue_ctr = nfc::CTR_ADJ_QUEUE_HEAVY;
+    nfc::adjs::adjoint_small_kernel<<<std::min(n, h->num_sms), nfc::adjs::NT, nfc::adjs::SMEM_BYTES, h->heavy_stream>>>(h->d_theta.p, H);
+    NFC_CUDA(h, cudaGetLastError());
+    wait_started_kernel<<<1, 1, 0, st>>>(h->d_counters.p + nfc::CTR_HEAVY_STARTED);
+    NFC_CUDA(h, cudaGetLastError());
+    h->last_launches += 1;
+    return 0;
+}
 namespace {
 
 // Chebyshev recurrences of the m-stage RKC formula for m = 2..MMAX in double, stored as float (oracle/nde_oracle.py:rkc_coefficients)
@@ -680,6 +700,12 @@ int32_t nfc_create(const nfc_config* cfg, nfc_handle** out) {
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking) != cudaSuccess) { h->err = "cudaStreamCreate failed"; return bail(-10); }
     for (auto& ev : h->ev_chunk) if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { h->err = "cudaEventCreate failed"; return bail(-10); }
+    {
+        int lo = 0, hi = 0;                                                  // numerically lowest = highest priority
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&h->heavy_stream, cudaStreamNonBlocking, hi) != cudaSuccess) { h->err = "cudaStreamCreate failed"; return bail(-10); }
+        for (auto& ev : h->ev_heavy) if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) { h->err = "cudaEventCreate failed"; return bail(-10); }
+    }
     for (auto& ev : h->ev) if (cudaEventCreate(&ev) != cudaSuccess) { h->err = "cudaEventCreate failed"; return bail(-10); }
     int rc = [&]() -> int { NFC_DISPATCH(h, arch_setup, h); }();
     if (rc) return bail(rc);
@@ -737,6 +763,7 @@ int32_t nfc_create(const nfc_config* cfg, nfc_handle** out) {
         h->use_tc = false; h->fwd_small_max = 0; h->adj_small_max = 0;
         for (int64_t m : h->theta_map) if (m < 0 || m >= h->n_params) { h->err = "internal: parameter map out of range"; return bail(-3); }
     }
+    if (const char* e = getenv("NFC_ADJ_HEAVY")) h->adj_heavy = std::max<long long>(0, atoll(e));
     if (const char* e = getenv("NFC_TAPE_MODE")) h->tape_mode = std::max(0, std::min(2, atoi(e)));     // adjoint tape: 0 auto, 1 dense, 2 compact
     if (h->d_theta.ensure(h->n_params) || h->d_wpack.ensure(h->n_packed) || h->d_saveat.ensure(h->saveat.size()) ||
         h->d_counters.ensure(CTR_COUNT)) { h->err = "cudaMalloc failed"; return bail(-10); }
@@ -760,6 +787,8 @@ int32_t nfc_destroy(nfc_handle* h) {
     for (auto& ev : h->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : h->ev_chunk) if (ev) cudaEventDestroy(ev);
     if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+    for (auto& ev : h->ev_heavy) if (ev) cudaEventDestroy(ev);
+    if (h->heavy_stream) cudaStreamDestroy(h->heavy_stream);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return 0;
@@ -899,9 +928,10 @@ int32_t nfc_set_option(nfc_handle* h, const char* name, int64_t value) {
         NFC_CUDA(h, cudaSetDevice(h->device));
         return switch_split(h, value == 0);
     }
+    else if (n == "adj_heavy") { if (value < 0) return fail(h, -2, "adj_heavy: >= 0"); h->adj_heavy = value; }
     else if (n == "tape_mode") { if (value < 0 || value > 2) return fail(h, -2, "tape_mode: 0 = compact tape when the dense one exceeds the budget, 1 = dense, 2 = compact"); h->tape_mode = (int)value; }
     else if (n == "tape_gib") { if (value < 0) return fail(h, -2, "tape_gib: >= 0 (0 = default 48)"); h->tape_gib = (double)value; }
-    else return fail(h, -2, "unknown option '%s' (tc, tc_tiles, tc_split, range_fallback, tc2_min_columns, tc_record, sched, adj_small_max, fwd_small_max, adj_tc, e2e_pieces, tape_gib, tape_mode)", name);
+    else return fail(h, -2, "unknown option '%s' (tc, tc_tiles, tc_split, range_fallback, tc2_min_columns, tc_record, sched, adj_small_max, fwd_small_max, adj_tc, adj_heavy, e2e_pieces, tape_gib, tape_mode)", name);
     return 0;
 }
 

@@ -12,7 +12,7 @@
 namespace nfc {
 
 enum : int { ST_OK = 0, ST_MAXITERS = 1, ST_NAN = 2, ST_DT_UNDERFLOW = 3, ST_TAPE_OVERFLOW = 4, ST_RANGE = 5 };   // ST_RANGE: FP16x2 operand range left (|T_scaled| > 128)
-enum : int { CTR_QUEUE = 0, CTR_ACCEPT = 1, CTR_REJECT = 2, CTR_ADJ_QUEUE = 3, CTR_ADJ_ACCEPT = 4, CTR_ADJ_REJECT = 5, CTR_COUNT = 8 };
+enum : int { CTR_QUEUE = 0, CTR_ACCEPT = 1, CTR_REJECT = 2, CTR_ADJ_QUEUE = 3, CTR_ADJ_ACCEPT = 4, CTR_ADJ_REJECT = 5, CTR_ADJ_QUEUE_HEAVY = 6, CTR_HEAVY_STARTED = 7, CTR_COUNT = 8 };
 
 struct SolveParams {
     const float* wpack;        // packed weights

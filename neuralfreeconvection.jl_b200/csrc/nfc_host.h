@@ -64,6 +64,9 @@ struct nfc_handle {
     bool in_pad = false;                    // a host-buffer call is running on padded copies of the caller's arrays
     bool weights_set = false;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t heavy_stream = nullptr;    // high priority: the longest columns of a loss_grad chunk, one column per CTA (nfc_adjoint.cuh)
+    cudaEvent_t ev_heavy[2] = {nullptr, nullptr};
+    int64_t adj_heavy = 48;                 // how many (0 = none); needs the previous call's per-column step counts
     cudaEvent_t ev_chunk[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     bool ev_fwd_valid = false, ev_adj_valid = false;

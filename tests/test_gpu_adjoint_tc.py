@@ -77,12 +77,15 @@ def test_tensor_core_backward_is_the_default_for_large_batches(nfc, gpu_ok, monk
     h = nfc.Handle(cw, layers, 1, sv)
     h.set_weights(theta)
     full = h.loss_grad(d["T0"], colp, d["glob"], Ttrue)
+    h.loss_grad(d["T0"], colp, d["glob"], Ttrue)             # steady state of a training loop: schedule and side launch from the previous call's step counts
     ms_tc = h.counters()["last_adjoint_ms"]
     monkeypatch.setenv("NFC_ADJ_TC", "0")
     h0 = nfc.Handle(cw, layers, 1, sv)
     h0.set_weights(theta)
     ref = h0.loss_grad(d["T0"], colp, d["glob"], Ttrue)
+    h0.loss_grad(d["T0"], colp, d["glob"], Ttrue)
     ms_simt = h0.counters()["last_adjoint_ms"]
+    print(f"8200 columns, second call: tensor-core backward {ms_tc:.1f} ms, FP32 SIMT {ms_simt:.1f} ms")
     assert (full["status"] == 0).all()
     assert _rel(full["grad"], ref["grad"]) < 3e-4      # measured 1e-4: step-sequence differences + BF16 contraction
     assert ms_tc < ms_simt                                   # it is the faster kernel, or it would not be the default
@@ -118,3 +121,26 @@ def test_tensor_core_backward_tight_tolerances_reach_truth(nfc, gpu_ok, monkeypa
     L, g, _ = O.loss_and_grad_autograd(d["T0"][:B], theta, cw, layers, colp[:B], d["glob"], sv, Ttrue[:B], fixed_dt=1 / 1024)
     assert abs(r["loss"] - L) / L < 1e-3
     assert _rel(r["grad"], g) < 2e-3          # 3 columns: the BF16 contraction has few terms to average over (FP32 kernel: 1e-3)
+
+
+def test_longest_columns_run_on_the_side_stream(nfc, gpu_ok, monkeypatch):
+    """Second call on the same batch: the backward step counts of the first call are known, the adj_heavy longest columns run one column
+    per CTA on the side stream next to the tensor-core kernel.  Same loss (same RECORD pass), same gradient; adj_heavy = 0 switches it off."""
+    p = _problem(nfc, 8200, 1.0, 2.0, n_save=9)
+    d, cw, layers, theta, sv, colp, Ttrue = p
+    monkeypatch.delenv("NFC_ADJ_SMALL_MAX", raising=False)
+    monkeypatch.delenv("NFC_ADJ_TC", raising=False)
+    h = nfc.Handle(cw, layers, 1, sv)
+    h.set_weights(theta)
+    r1 = h.loss_grad(d["T0"], colp, d["glob"], Ttrue)
+    l1 = h.counters()["kernel_launches"]
+    r2 = h.loss_grad(d["T0"], colp, d["glob"], Ttrue)
+    l2, c2 = h.counters()["kernel_launches"], h.counters()
+    assert (r2["status"] == 0).all() and r2["loss"] == r1["loss"]
+    assert l2 == l1 + 2                                                    # the side launch and the main stream's wait for it
+    assert _rel(r2["grad"], r1["grad"]) < 3e-4
+    steps = h.adjoint_steps(8200)
+    assert (steps > 0).all() and int(steps.sum()) == c2["adj_steps_accepted"] + c2["adj_steps_rejected"]      # every column was solved exactly once
+    h.set_option("adj_heavy", 0)
+    r3 = h.loss_grad(d["T0"], colp, d["glob"], Ttrue)
+    assert h.counters()["kernel_launches"] == l1 and _rel(r3["grad"], r1["grad"]) < 3e-4
