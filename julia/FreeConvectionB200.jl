@@ -135,16 +135,25 @@ function solve_nde(ds, NN, NDEType, nde_params, algorithm, T_scaling, wT_scaling
     return (T=inv(T_scaling).(Float64.(T)), wT=inv(wT_scaling).(Float64.(wT)))
 end
 
+"nfc_set_option: kernel selection and scratch budgets (the names are listed in include/nfc.h)."
+set_option(nde::NDEHandle, name::AbstractString, value::Integer) =
+    check(nde.ptr, ccall((:nfc_set_option, LIB), Int32, (Ptr{Cvoid}, Cstring, Int64), nde.ptr, name, value), "nfc_set_option")
+
 "Loss and dL/dθ of src/training.jl:45-48,70 for all simulations in one call; Ttrue is Nz x n_save x B (already T_scaling'ed)."
 function nde_loss_and_gradient(nde::NDEHandle, θ::Vector{Float32}, T₀::Matrix{Float32}, nde_params, Ttrue::Array{Float32,3})
     check(nde.ptr, ccall((:nfc_set_weights, LIB), Int32, (Ptr{Cvoid}, Ptr{Float32}, Int64), nde.ptr, θ, length(θ)), "nfc_set_weights")
     colp, glob = split_params(nde, nde_params); B = size(T₀, 2)
     loss = Ref{Float64}(0); grad = similar(θ); st = zeros(Int32, B)
-    rc = ccall((:nfc_loss_grad, LIB), Int32, (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ref{Float64}, Ptr{Float32}, Ptr{Int32}, Int64),
-               nde.ptr, T₀, colp, glob, Ttrue, loss, grad, st, B)
-    check(nde.ptr, rc, "nfc_loss_grad")
-    # a failed column is excluded from the gradient while its residuals stay in the loss: never train on that silently
-    any(==(4), st) && error("adjoint tape overflow for $(count(==(4), st)) columns: rebuild the NDE with a larger adjoint_max_steps")
+    call() = check(nde.ptr, ccall((:nfc_loss_grad, LIB), Int32, (Ptr{Cvoid}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ptr{Float32}, Ref{Float64}, Ptr{Float32}, Ptr{Int32}, Int64),
+                                  nde.ptr, T₀, colp, glob, Ttrue, loss, grad, st, B), "nfc_loss_grad")
+    call()
+    # a failed column is excluded from the gradient while its residuals stay in the loss: never train on that silently.  Status 4 = a column
+    # accepted more steps than the dense adjoint tape holds (adjoint_max_steps rows per column): the compact tape has no such cap
+    if any(==(4), st)
+        set_option(nde, "tape_mode", 2)
+        call()
+        any(==(4), st) && error("adjoint tape overflow for $(count(==(4), st)) columns (more than 32 765 accepted steps)")
+    end
     any(!=(0), st) && @warn "nfc_loss_grad: $(count(!=(0), st)) of $B columns failed (status $(unique(st[st .!= 0]))) and are missing from the gradient"
     return loss[], grad
 end

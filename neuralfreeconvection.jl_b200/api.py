@@ -295,17 +295,15 @@ def train_neural_differential_equation(NN, NDEType, nde_params, algorithm, datas
     theta, reconstruct = destructure(NN)
     best = (np.inf, theta.copy())
     history = []
-    tape_steps = 512                                                        # the C library's default adjoint_max_steps
     t0 = time.time()
     for epoch in range(1, epochs + 1):
         handle = nde.handle_for(alg)
         handle.set_weights(theta)
         res = handle.loss_grad(T0, colp, glob, true_sols)
-        while (res["status"] == 4).any() and tape_steps < 32768:
-            # adjoint tape overflow: the column's residuals are in the loss but its gradient is missing -- never train on that; keep more steps
-            tape_steps *= 2
-            handle = nde._handles[alg] = nde._mk(alg, adjoint_max_steps=tape_steps)
-            handle.set_weights(theta)
+        if (res["status"] == 4).any():
+            # adjoint tape overflow (a column accepted more steps than the dense tape's adjoint_max_steps rows): its residuals are in the loss
+            # but its gradient is missing -- never train on that.  The compact tape gives every column the rows it needs.
+            handle.set_option("tape_mode", 2)
             res = handle.loss_grad(T0, colp, glob, true_sols)
         _warn_status(res["status"], f"train_neural_differential_equation epoch {epoch}")
         if res["loss"] < best[0]:
