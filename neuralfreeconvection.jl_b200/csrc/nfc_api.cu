@@ -230,10 +230,10 @@ int launch_solve(nfc_handle* h, SolveParams& P, cudaStream_t st, bool reset_coun
     if (small_forward_batch(h, B)) {
         P.wpack = nullptr;
         if (int rc = launch_small_forward(h, P, st, RECORD)) return rc;
-    } else if (h->use_tc && h->arch != ARCH_DEFAULT && tc_forward_arch(h->arch) && !rec_sel && h->tc_fp16) {
-        // conv-2 / conv-4 / deeper Chain: one-tile tensor-core forward solve (the RECORD pass of loss_grad stays on the FP32 SIMT kernel)
+    } else if (h->use_tc && h->arch != ARCH_DEFAULT && tc_forward_arch(h->arch) && (!rec_sel || h->tc_record) && h->tc_fp16) {
+        // conv-2 / conv-4 / deeper Chain: one-tile tensor-core forward solve and RECORD pass of loss_grad (the backward pass is the FP32 SIMT kernel)
         const int gridt = (int)std::min<long long>(h->num_sms, (B + tc::TILE - 1) / tc::TILE);
-#define NFC_SOLVE_TC(SP) tc::solve_tc_kernel<SP, false><<<gridt, tc::NTHREADS, SP::IMG, st>>>(h->d_wimg.p, P)
+#define NFC_SOLVE_TC(SP) tc::solve_tc_kernel<SP, RECORD><<<gridt, tc::NTHREADS, SP::IMG, st>>>(h->d_wimg.p, P)
         NFC_TC_ARCH_DISPATCH(h, (void)0, NFC_SOLVE_TC(tc::SplitFP16x2T<2 NFC_COMMA 2>), NFC_SOLVE_TC(tc::SplitFP16x2T<2 NFC_COMMA 4>), NFC_SOLVE_TC(tc::SplitFP16x2T<3 NFC_COMMA 0>))
 #undef NFC_SOLVE_TC
     } else if (h->use_tc && h->arch == ARCH_DEFAULT && (!rec_sel || (h->tc_fp16 && h->tc_record))) {
@@ -750,7 +750,8 @@ int32_t nfc_create(const nfc_config* cfg, nfc_handle** out) {
         if (h->d_wimg.ensure(tc::IMG16_MAX)) { h->err = "cudaMalloc failed"; return bail(-10); }
         bool ok = true;
 #define NFC_TC_ATTR(SP) ok = ok && cudaFuncSetAttribute(tc::rhs_tc_kernel<SP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP::IMG) == cudaSuccess && \
-                          cudaFuncSetAttribute(tc::solve_tc_kernel<SP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP::IMG) == cudaSuccess
+                          cudaFuncSetAttribute(tc::solve_tc_kernel<SP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP::IMG) == cudaSuccess && \
+                          cudaFuncSetAttribute(tc::solve_tc_kernel<SP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SP::IMG) == cudaSuccess
         NFC_TC_ARCH_DISPATCH(h, (void)0, NFC_TC_ATTR(tc::SplitFP16x2T<2 NFC_COMMA 2>), NFC_TC_ATTR(tc::SplitFP16x2T<2 NFC_COMMA 4>), NFC_TC_ATTR(tc::SplitFP16x2T<3 NFC_COMMA 0>))
 #undef NFC_TC_ATTR
         if (!ok) { h->err = "cudaFuncSetAttribute(tc) failed"; return bail(-10); }
