@@ -91,3 +91,36 @@ def test_unsupported_combinations_fail_loudly(nfc, gpu_ok):
     h = nfc.Handle(cw, layers, 1, sv, Nz=16)
     with pytest.raises(nfc.NfcError):
         h.set_option("tc", 1)
+
+
+def test_training_loop_on_a_16_level_grid(nfc, gpu_ok):
+    """train_neural_differential_equation (src/training.jl:34-78) with --grid-points 16: datasets, Chain and parameter vector live on 16
+    levels; the host mirror passes Nz through to nfc_create."""
+    syn = nfc.synthetic
+    Nz, B, Nt = 16, 5, 65
+    Ts, wTs = syn.reference_scalings(Nz)
+    d = syn.make_columns("ocean", B=B, seed=7, Nz=Nz)
+    cw, layers = O.chain_spec("dense-default", Nz)
+    cp10 = d["colp"].copy()
+    cp10[:, 2] = 10.0
+    sv = syn.saveat(Nt)
+    truth = O.tsit5_solve(d["T0"], np.zeros(O.n_params(cw, layers)), cw, layers, cp10, d["glob"], sv, 1e-6, 1e-8, np.float64)["T"]      # [B, Nt, Nz]
+    zf = -256.0 + np.arange(Nz + 1) * (256.0 / Nz)
+    datasets, params = {}, {}
+    for i in range(B):
+        flux = float(wTs.inv(d["colp"][i, 1]))
+        datasets[i + 1] = nfc.ColumnDataset(T=Ts.inv(truth[i]).T, wT=np.zeros((Nz + 1, Nt)), zc=syn.cell_centres(Nz), zf=zf,
+                                            times=np.arange(Nt) * 600.0 * 1152 / (Nt - 1), metadata={"temperature_flux": flux})
+        params[i + 1] = nfc.ConvectiveAdjustmentNDEParameters(datasets[i + 1], Ts, wTs, 2)
+    NN = nfc.named_chain("dense-default", Nz=Nz, seed=0)
+    for p in NN.params():
+        p *= 1e-5
+    NN2 = nfc.train_neural_differential_equation(NN, nfc.ConvectiveAdjustmentNDE, params, nfc.Tsit5(), datasets, Ts, range(1, Nt + 1, 4), nfc.ADAM(), 4)
+    losses = [h["mean_loss"] for h in NN2.history]
+    assert len(losses) == 4 and np.isfinite(losses).all() and losses[-1] < losses[0]
+    theta2, _ = nfc.destructure(NN2)
+    assert theta2.size == O.n_params(cw, layers)
+    # solve_nde with the trained Chain returns Nz x n_save
+    nde = nfc.ConvectiveAdjustmentNDE(NN2, datasets[1], iterations=range(1, Nt + 1, 4))
+    sol = nfc.solve_nde(nde, NN2, Ts(datasets[1].T[:, 0]).astype(np.float32), nfc.Tsit5(), params[1])
+    assert np.asarray(sol).shape == (Nz, 17) and np.isfinite(sol).all()
