@@ -104,6 +104,18 @@ def test_adam_matches_flux_update_rule(nfc):
     th1 = opt.update(th, g)
     # first step of ADAM moves every non-zero-gradient coordinate by ~eta
     np.testing.assert_allclose(th1, th - 1e-3 * np.sign(g) * (np.abs(g) / (np.abs(g) + 1e-8)), rtol=1e-6)
+    # several steps with changing gradients against Flux's rule written out (Flux.Optimise.ADAM: eta 1e-3, beta (0.9, 0.999), eps 1e-8;
+    # m = b1 m + (1 - b1) g, v = b2 v + (1 - b2) g^2, theta -= eta * m / (1 - b1^t) / (sqrt(v / (1 - b2^t)) + eps))
+    opt, th = nfc.ADAM(), np.array([0.3, -1.2, 2.0, 0.0])
+    ref, m, v = th.copy(), np.zeros(4), np.zeros(4)
+    rng = np.random.default_rng(0)
+    for t in range(1, 8):
+        g = rng.standard_normal(4) * np.array([1.0, 10.0, 0.01, 0.0])
+        th = opt.update(th, g)
+        m = 0.9 * m + 0.1 * g
+        v = 0.999 * v + 0.001 * g * g
+        ref = ref - 1e-3 * (m / (1 - 0.9 ** t)) / (np.sqrt(v / (1 - 0.999 ** t)) + 1e-8)
+        np.testing.assert_allclose(th, ref, rtol=1e-12, atol=1e-15)
 
 
 def test_on_disk_formats_round_trip(tmp_path):
