@@ -174,10 +174,11 @@ int32_t nfc_get_adjoint_steps(nfc_handle* h, int32_t* out, int64_t n);
  *   sched            0: columns served in input order; 1 (default): longest first from the previous call's step counts
  *   fwd_small_max    forward solves / RECORD passes of at most this many columns (default Chain) run one column per CTA (default 148 = one per
  *                    SM; 0 = never; forcing tc_tiles also bypasses it)
- *   adj_small_max    batches up to this many columns run the one-column-per-CTA backward kernel (default 7400; 0 = never)
+ *   adj_small_max    batches up to this many columns run the one-column-per-CTA backward kernel (default 2000, half of it once the
+ *                    previous call's per-column step counts are known; 0 = never)
  *   adj_tc           0: batch backward pass on the FP32 SIMT kernel instead of the tensor-core kernel
  *   adj_heavy        how many of a chunk's longest columns (by the previous call's backward step counts) run on the one-column-per-CTA
- *                    kernel next to the tensor-core backward kernel (default 48; 0 = none; chunks of at least 64 x adj_heavy columns)
+ *                    kernel next to the tensor-core backward kernel (default 48, at most 1/16 of the chunk; 0 = none)
  *   e2e_pieces       nfc_solve: pieces whose device->host copy overlaps the next piece's solve (0 = auto: 2 from 16384, 3 from 49152 columns)
  *   tc_split         0 = FP16x2 operands (3 MMAs per fp32 product, needs |T_scaled| <= 128; default), 1 = BF16x3 (6 MMAs, fp32's range)
  *   range_fallback   1 (default): nfc_solve re-solves columns that ended with status 5 on the BF16x3 split, nfc_loss_grad (no communicator)

@@ -729,7 +729,7 @@ int adjoint_loss_grad(nfc_handle* h, const float* T0, const float* colp, float p
         const int* key = nullptr;
         NFC_CUDA(h, h->a_adjsteps.ensure((size_t)B));
         if (h->a_adjhist_B != B) { h->a_adjhist_B = B; h->a_adjhist_valid = false; }
-        if (h->use_sched && nb >= 2048) {
+        if (h->use_sched && nb >= 512) {
             key = h->a_adjhist_valid ? h->a_adjsteps.p + off : h->a_tlen.p;
             NFC_CUDA(h, h->d_order.ensure((size_t)nb));
             NFC_CUDA(h, h->d_hist.ensure(SCHED_BUCKETS));
@@ -760,7 +760,7 @@ int adjoint_loss_grad(nfc_handle* h, const float* T0, const float* colp, float p
                 // longest-first order) run on the one-column-per-CTA kernel instead (~ 20 us per pass), on a high-priority side stream next
                 // to the tensor-core kernel, whose CTAs on those SMs start when they are free (persistent CTAs, dynamic queue).
                 int n_heavy = 0;
-                if (order && key != h->a_tlen.p && h->adj_heavy > 0 && nb >= 64 * (int64_t)h->adj_heavy) n_heavy = (int)std::min<int64_t>(h->adj_heavy, h->num_sms);
+                if (order && key != h->a_tlen.p && h->adj_heavy > 0 && nb >= 512) n_heavy = (int)std::min<int64_t>(std::min<int64_t>(h->adj_heavy, nb / 16), h->num_sms);
                 if (n_heavy > 0) {
                     if (int rc = adjoint_heavy_launch(h, A, n_heavy, st)) return rc;
                     A.order = order + n_heavy;

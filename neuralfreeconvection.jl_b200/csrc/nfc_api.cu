@@ -334,8 +334,11 @@ int launch_small_forward(nfc_handle* h, const SolveParams& P, cudaStream_t st, b
 template <class N>
 bool adjoint_small_launch(nfc_handle* h, const nfc::AdjParams& A, int64_t nb, cudaStream_t st) {
     if constexpr (std::is_same<N, nfc::adjs::NetD>::value) {
-        // one column per CTA pays off while a CTA sees only a few columns: 2.5 us per stage against 40 us for a (mostly empty) 64-column CTA
-        if (nb > h->adj_small_max) return false;
+        // one column per CTA (20 us per pass) against the tensor-core kernel (72 us per pass of a 128-column tile, bound by its slowest column:
+        // ~ 75 ms for anything between 500 and 7000 columns) -- tools/gpu_adj_crossover.py: first call 40 / 61 / 88 ms at 1000 / 2000 / 3000
+        // columns against 75-80 ms; once the previous call's step counts put the longest columns on the side stream the tensor-core kernel
+        // needs 23 ms from 1000 columns on (one column per CTA: 27 ms at 1000)
+        if (nb > (h->a_adjhist_valid ? h->adj_small_max / 2 : h->adj_small_max)) return false;
         const int grid = (int)std::min<int64_t>(h->num_sms, nb);
         nfc::adjs::adjoint_small_kernel<<<grid, nfc::adjs::NT, nfc::adjs::SMEM_BYTES, st>>>(h->d_theta.p, A);
         return true;

@@ -277,6 +277,7 @@ def test_compact_tape_matches_dense_tape(nfc, gpu_ok, monkeypatch, B, env):
 def test_compact_tape_has_no_step_cap_and_chunks_by_budget(nfc, gpu_ok, monkeypatch):
     """adjoint_max_steps = 16 overflows the dense tape (status 4); the compact tape takes the steps a column needs.  A tiny budget forces
     several chunks of unequal size: same gradient."""
+    monkeypatch.setenv("NFC_ADJ_SMALL_MAX", "0")           # one kernel family whatever the chunk size (1024-column chunks would run one column per CTA)
     d, cw, layers, theta, sv, colp, Ttrue = _tape_problem(nfc, 3000, n_save=9)
     h = nfc.Handle(cw, layers, 1, sv, adjoint_max_steps=16)
     h.set_weights(theta)
@@ -329,6 +330,7 @@ def test_compact_tape_history_and_restart(nfc, gpu_ok, monkeypatch):
     n_ref = hd.counters()["steps_accepted"]
     h = nfc.Handle(cw, layers, 1, sv)
     h.set_option("tape_mode", 2)
+    h.set_option("adj_heavy", 0)                            # the launch counts below are about the tape, not about the side launch of the longest columns
     h.set_weights(theta * np.float32(1e-3))                 # a nearly static column: a handful of steps
     r0 = h.loss_grad(d["T0"], colp, d["glob"], Ttrue)
     l0, n0 = h.counters()["kernel_launches"], h.counters()["steps_accepted"]
