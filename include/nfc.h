@@ -172,7 +172,7 @@ int32_t nfc_get_adjoint_steps(nfc_handle* h, int32_t* out, int64_t n);
  *   tc2_min_columns  batch size from which tc_tiles = 0 picks two tiles (default 98304)
  *   tc_record        0: forward (RECORD) pass of nfc_loss_grad on the FP32 SIMT kernel
  *   sched            0: columns served in input order; 1 (default): longest first from the previous call's step counts
- *   fwd_small_max    forward solves / RECORD passes of at most this many columns (default Chain) run one column per CTA (default 148 = one per
+ *   fwd_small_max    forward solves / RECORD passes of at most this many columns (default Chain) run one column per CTA (default 592 = four per
  *                    SM; 0 = never; forcing tc_tiles also bypasses it)
  *   adj_small_max    batches up to this many columns run the one-column-per-CTA backward kernel (default 2000, half of it once the
  *                    previous call's per-column step counts are known; 0 = never)

@@ -109,7 +109,7 @@ struct nfc_handle {
     int tape_mode = 0;                         // 0 = compact tape when the dense one exceeds the budget, 1 = dense, 2 = compact
     bool count_pass = false;                   // launch_solve: pick the kernels of the RECORD pass for a non-RECORD solve
     int64_t a_adjsteps_n = 0;      // a_adjsteps: attempted backward steps per column of the last nfc_loss_grad batch (all chunks)
-    int64_t fwd_small_max = 148;   // forward solves / RECORD passes of at most this many columns (default Chain) run one column per CTA (nfc_forward_small.cuh)
+    int64_t fwd_small_max = 592;   // (4 per SM: tools/gpu_fwd_crossover.py) forward solves / RECORD passes of at most this many columns (default Chain) run one column per CTA (nfc_forward_small.cuh)
     int64_t adj_small_max = 2000;  // loss_grad chunks of at most this many columns (default Chain) use the one-column-per-CTA backward kernel (half of it once the step history is known)
     int64_t a_adjhist_B = -1;      // batch size that history belongs to; it is the next call's longest-first key
     bool a_adjhist_valid = false;

@@ -279,6 +279,7 @@ def test_tensor_core_out_of_range_input_is_flagged_or_resolved(nfc, gpu_ok, monk
     sv = nfc.synthetic.saveat(5)
     h, cw, layers = _handle(nfc, saveat=sv)
     h.set_weights(O.glorot_theta(cw, layers, 0, 0.3))
+    h.set_option("fwd_small_max", 0)           # a batch this small would run the FP32 one-column-per-CTA kernel, which has no range bound
     ok = h.solve(d["T0"], d["colp"], d["glob"])
     T0 = d["T0"].copy()
     T0[17] *= 120.0                            # |T_scaled| up to ~ 167: outside the FP16x2 operand range, harmless in fp32
@@ -392,6 +393,7 @@ def test_set_option_selects_kernels(nfc, gpu_ok):
     theta = O.glorot_theta(cw, layers, 0, 0.3)
     h = nfc.Handle(cw, layers, 1, syn.saveat(17))
     h.set_weights(theta)
+    h.set_option("tc_tiles", 1)                # the one-tile tensor-core kernel (300 columns would run one column per CTA: fwd_small_max)
     a = h.solve(d["T0"], d["colp"], d["glob"])
     h.set_option("tc", 0)                      # FP32 SIMT kernels
     b = h.solve(d["T0"], d["colp"], d["glob"])
