@@ -645,141 +645,141 @@ int adjoint_loss_grad(nfc_handle* h, const float* T0, const float* colp, float p
     if (compact) { NFC_CUDA(h, h->a_count.ensure((size_t)B)); NFC_CUDA(h, h->a_flag.ensure(1)); }
     if (h->a_count_B != B) { h->a_count_B = B; h->a_count_valid = false; }
     for (int attempt = 0;; ++attempt) {
-    const bool from_history = compact && attempt == 0 && h->a_count_valid;
-    bool restart = false;
-    int64_t max_cols = 0, max_rows = 0;
-    chunk_begin.clear();
-    h->a_off_host.clear();
-    if (attempt > 0) {
-        NFC_CUDA(h, cudaMemsetAsync(loss_sum_dev, 0, 2 * sizeof(double), st));
-        NFC_CUDA(h, cudaMemsetAsync(h->a_gacc.p, 0, sizeof(float) * (size_t)2 * grid * h->n_params, st));
-    }
-    if (compact) {
-        if (!from_history) {
-            SolveParams C{};
-            C.T0 = T0; C.colp = colp; C.pref = pref; C.B = B; C.naccept = h->a_count.p;
-            if (int rc = nfc_launch_count<N>(h, C, st)) return rc;
+        const bool from_history = compact && attempt == 0 && h->a_count_valid;
+        bool restart = false;
+        int64_t max_cols = 0, max_rows = 0;
+        chunk_begin.clear();
+        h->a_off_host.clear();
+        if (attempt > 0) {
+            NFC_CUDA(h, cudaMemsetAsync(loss_sum_dev, 0, 2 * sizeof(double), st));
+            NFC_CUDA(h, cudaMemsetAsync(h->a_gacc.p, 0, sizeof(float) * (size_t)2 * grid * h->n_params, st));
         }
-        std::vector<int> cnt((size_t)B);
-        NFC_CUDA(h, cudaMemcpyAsync(cnt.data(), h->a_count.p, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, st));
-        NFC_CUDA(h, cudaStreamSynchronize(st));
-        // offsets restart at 0 in every chunk; chunk k's nb + 1 offsets start at a_off[chunk_begin[k] + k]
-        std::vector<long long>& offs = h->a_off_host;
-        offs.reserve((size_t)B + 16);
-        const double resid_bytes = sizeof(float) * (double)n_save * NZ, row_bytes = sizeof(float) * (double)TAPE_STRIDE;
-        double used = 0.0;
-        long long rows = 0;
-        chunk_begin.push_back(0);
-        offs.push_back(0);
-        for (int64_t b = 0; b < B; ++b) {
-            const long long c = std::max(cnt[(size_t)b], 0);
-            const long long r = std::min<long long>(c + c / 8 + 6, 32767);     // the backward kernels index a column's rows with 15 bits
-            const double need = resid_bytes + row_bytes * (double)r;
-            if (used + need > budget_bytes && b - chunk_begin.back() >= 1024) {
-                max_cols = std::max(max_cols, b - chunk_begin.back()); max_rows = std::max<int64_t>(max_rows, rows);
-                chunk_begin.push_back(b); offs.push_back(0);
-                used = 0.0; rows = 0;
+        if (compact) {
+            if (!from_history) {
+                SolveParams C{};
+                C.T0 = T0; C.colp = colp; C.pref = pref; C.B = B; C.naccept = h->a_count.p;
+                if (int rc = nfc_launch_count<N>(h, C, st)) return rc;
             }
-            used += need; rows += r;
-            offs.push_back(rows);
-        }
-        max_cols = std::max(max_cols, B - chunk_begin.back()); max_rows = std::max<int64_t>(max_rows, rows);
-        chunk_begin.push_back(B);
-        NFC_CUDA(h, h->a_off.ensure(offs.size()));
-        NFC_CUDA(h, cudaMemcpyAsync(h->a_off.p, offs.data(), sizeof(long long) * offs.size(), cudaMemcpyHostToDevice, st));
-        NFC_CUDA(h, cudaStreamSynchronize(st));         // offs may be reallocated by the next call while the copy is in flight
-    } else {
-        int64_t chunk = (int64_t)(budget_bytes / (double)per_col);
-        if (chunk < 1024) chunk = 1024;
-        if (chunk > B) chunk = B;
-        for (int64_t off = 0; off < B; off += chunk) chunk_begin.push_back(off);
-        chunk_begin.push_back(B);
-        max_cols = chunk; max_rows = chunk * cap;
-    }
-    h->a_tape_rows = max_rows;
-    NFC_CUDA(h, h->a_tape.ensure((size_t)max_rows * TAPE_STRIDE));
-    NFC_CUDA(h, h->a_resid.ensure((size_t)max_cols * n_save * NZ));
-    NFC_CUDA(h, h->a_tlen.ensure((size_t)max_cols));
-    bool first = true;
-    for (size_t k = 0; k + 1 < chunk_begin.size(); ++k) {
-        const int64_t off = chunk_begin[k], nb = chunk_begin[k + 1] - off;
-        const long long* tape_off = compact ? h->a_off.p + off + (int64_t)k : nullptr;
-        if (compact && k + 2 == chunk_begin.size()) {     // nfc_get_tape reads the last chunk
-            h->a_off_host.erase(h->a_off_host.begin(), h->a_off_host.begin() + (off + (int64_t)k));
-        }
-        SolveParams P{};
-        P.T0 = T0 + off * NZ; P.colp = colp + off * 3; P.pref = pref; P.B = nb; P.status = st_all + off;
-        P.Ttrue = Ttrue + off * (int64_t)n_save * NZ; P.resid = h->a_resid.p; P.tape = h->a_tape.p; P.tape_len = h->a_tlen.p;
-        P.loss_sum = loss_sum_dev; P.tape_cap = cap; P.tape_off = tape_off;
-        if (compact) P.naccept = h->a_count.p + off;       // the next call's tape shares
-        if (int rc = nfc_launch_record<N>(h, P, st, first)) return rc;
-        if (from_history) {      // shares predicted from the previous call: did a column outgrow its rows?
-            int flag = 0;
-            NFC_CUDA(h, cudaMemsetAsync(h->a_flag.p, 0, sizeof(int), st));
-            count_status_kernel<<<(int)std::min<int64_t>(1024, (nb + 255) / 256), 256, 0, st>>>(st_all + off, nb, ST_TAPE_OVERFLOW, h->a_flag.p);
-            NFC_CUDA(h, cudaMemcpyAsync(&flag, h->a_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            std::vector<int> cnt((size_t)B);
+            NFC_CUDA(h, cudaMemcpyAsync(cnt.data(), h->a_count.p, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, st));
             NFC_CUDA(h, cudaStreamSynchronize(st));
-            h->last_launches += 1;
-            if (flag > 0) { restart = true; break; }
+            // offsets restart at 0 in every chunk; chunk k's nb + 1 offsets start at a_off[chunk_begin[k] + k]
+            std::vector<long long>& offs = h->a_off_host;
+            offs.reserve((size_t)B + 16);
+            const double resid_bytes = sizeof(float) * (double)n_save * NZ, row_bytes = sizeof(float) * (double)TAPE_STRIDE;
+            double used = 0.0;
+            long long rows = 0;
+            chunk_begin.push_back(0);
+            offs.push_back(0);
+            for (int64_t b = 0; b < B; ++b) {
+                const long long c = std::max(cnt[(size_t)b], 0);
+                const long long r = std::min<long long>(c + c / 8 + 6, 32767);     // the backward kernels index a column's rows with 15 bits
+                const double need = resid_bytes + row_bytes * (double)r;
+                if (used + need > budget_bytes && b - chunk_begin.back() >= 1024) {
+                    max_cols = std::max(max_cols, b - chunk_begin.back()); max_rows = std::max<int64_t>(max_rows, rows);
+                    chunk_begin.push_back(b); offs.push_back(0);
+                    used = 0.0; rows = 0;
+                }
+                used += need; rows += r;
+                offs.push_back(rows);
+            }
+            max_cols = std::max(max_cols, B - chunk_begin.back()); max_rows = std::max<int64_t>(max_rows, rows);
+            chunk_begin.push_back(B);
+            NFC_CUDA(h, h->a_off.ensure(offs.size()));
+            NFC_CUDA(h, cudaMemcpyAsync(h->a_off.p, offs.data(), sizeof(long long) * offs.size(), cudaMemcpyHostToDevice, st));
+            NFC_CUDA(h, cudaStreamSynchronize(st));         // offs may be reallocated by the next call while the copy is in flight
+        } else {
+            int64_t chunk = (int64_t)(budget_bytes / (double)per_col);
+            if (chunk < 1024) chunk = 1024;
+            if (chunk > B) chunk = B;
+            for (int64_t off = 0; off < B; off += chunk) chunk_begin.push_back(off);
+            chunk_begin.push_back(B);
+            max_cols = chunk; max_rows = chunk * cap;
         }
-        // backward queue, longest first.  Key: the per-column backward step counts of the previous call on the same batch size (a
-        // training loop solves the same columns every epoch), else the forward tape length (a forward-stiff column is usually
-        // backward-stiff too, but outliers -- 1100 backward steps against a median of 350 -- are only known from history).
-        const int* order = nullptr;
-        const int* key = nullptr;
-        NFC_CUDA(h, h->a_adjsteps.ensure((size_t)B));
-        if (h->a_adjhist_B != B) { h->a_adjhist_B = B; h->a_adjhist_valid = false; }
-        if (h->use_sched && nb >= 512) {
-            key = h->a_adjhist_valid ? h->a_adjsteps.p + off : h->a_tlen.p;
-            NFC_CUDA(h, h->d_order.ensure((size_t)nb));
-            NFC_CUDA(h, h->d_hist.ensure(SCHED_BUCKETS));
-            NFC_CUDA(h, cudaMemsetAsync(h->d_hist.p, 0, sizeof(int) * SCHED_BUCKETS, st));
-            const int nblk = (int)((nb + 255) / 256);
-            sched_hist_kernel<<<nblk, 256, 0, st>>>(key, h->d_hist.p, nb);
-            sched_scan_kernel<<<1, SCHED_BUCKETS, 0, st>>>(h->d_hist.p);
-            sched_scatter_kernel<<<nblk, 256, 0, st>>>(key, h->d_hist.p, h->d_order.p, nb);
+        h->a_tape_rows = max_rows;
+        NFC_CUDA(h, h->a_tape.ensure((size_t)max_rows * TAPE_STRIDE));
+        NFC_CUDA(h, h->a_resid.ensure((size_t)max_cols * n_save * NZ));
+        NFC_CUDA(h, h->a_tlen.ensure((size_t)max_cols));
+        bool first = true;
+        for (size_t k = 0; k + 1 < chunk_begin.size(); ++k) {
+            const int64_t off = chunk_begin[k], nb = chunk_begin[k + 1] - off;
+            const long long* tape_off = compact ? h->a_off.p + off + (int64_t)k : nullptr;
+            if (compact && k + 2 == chunk_begin.size()) {     // nfc_get_tape reads the last chunk
+                h->a_off_host.erase(h->a_off_host.begin(), h->a_off_host.begin() + (off + (int64_t)k));
+            }
+            SolveParams P{};
+            P.T0 = T0 + off * NZ; P.colp = colp + off * 3; P.pref = pref; P.B = nb; P.status = st_all + off;
+            P.Ttrue = Ttrue + off * (int64_t)n_save * NZ; P.resid = h->a_resid.p; P.tape = h->a_tape.p; P.tape_len = h->a_tlen.p;
+            P.loss_sum = loss_sum_dev; P.tape_cap = cap; P.tape_off = tape_off;
+            if (compact) P.naccept = h->a_count.p + off;       // the next call's tape shares
+            if (int rc = nfc_launch_record<N>(h, P, st, first)) return rc;
+            if (from_history) {      // shares predicted from the previous call: did a column outgrow its rows?
+                int flag = 0;
+                NFC_CUDA(h, cudaMemsetAsync(h->a_flag.p, 0, sizeof(int), st));
+                count_status_kernel<<<(int)std::min<int64_t>(1024, (nb + 255) / 256), 256, 0, st>>>(st_all + off, nb, ST_TAPE_OVERFLOW, h->a_flag.p);
+                NFC_CUDA(h, cudaMemcpyAsync(&flag, h->a_flag.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+                NFC_CUDA(h, cudaStreamSynchronize(st));
+                h->last_launches += 1;
+                if (flag > 0) { restart = true; break; }
+            }
+            // backward queue, longest first.  Key: the per-column backward step counts of the previous call on the same batch size (a
+            // training loop solves the same columns every epoch), else the forward tape length (a forward-stiff column is usually
+            // backward-stiff too, but outliers -- 1100 backward steps against a median of 350 -- are only known from history).
+            const int* order = nullptr;
+            const int* key = nullptr;
+            NFC_CUDA(h, h->a_adjsteps.ensure((size_t)B));
+            if (h->a_adjhist_B != B) { h->a_adjhist_B = B; h->a_adjhist_valid = false; }
+            if (h->use_sched && nb >= 512) {
+                key = h->a_adjhist_valid ? h->a_adjsteps.p + off : h->a_tlen.p;
+                NFC_CUDA(h, h->d_order.ensure((size_t)nb));
+                NFC_CUDA(h, h->d_hist.ensure(SCHED_BUCKETS));
+                NFC_CUDA(h, cudaMemsetAsync(h->d_hist.p, 0, sizeof(int) * SCHED_BUCKETS, st));
+                const int nblk = (int)((nb + 255) / 256);
+                sched_hist_kernel<<<nblk, 256, 0, st>>>(key, h->d_hist.p, nb);
+                sched_scan_kernel<<<1, SCHED_BUCKETS, 0, st>>>(h->d_hist.p);
+                sched_scatter_kernel<<<nblk, 256, 0, st>>>(key, h->d_hist.p, h->d_order.p, nb);
+                NFC_CUDA(h, cudaGetLastError());
+                order = h->d_order.p;
+                h->last_launches += 3;
+            }
+            AdjParams A{};
+            A.order = order;
+            NFC_CUDA(h, cudaMemsetAsync(h->a_adjsteps.p + off, 0, sizeof(int) * nb, st));     // after the order is built (stream order)
+            A.adj_steps = h->a_adjsteps.p + off;
+            h->a_adjsteps_n = B;
+            A.wpack = h->d_wpack.p; A.colp = colp + off * 3; A.saveat = h->d_saveat.p; A.resid = h->a_resid.p; A.tape = h->a_tape.p;
+            A.tape_off = tape_off; A.nz = h->nz; A.queue_ctr = CTR_ADJ_QUEUE;
+            A.tape_len = h->a_tlen.p; A.status = st_all + off; A.gacc = h->a_gacc.p; A.counters = h->d_counters.p; A.B = nb; A.n_save = n_save;
+            A.tape_cap = cap; A.max_iters = h->cfg.max_iters; A.use_kca = h->cfg.nde_type == NFC_NDE_CONVECTIVE_ADJUSTMENT; A.n_params = (int)h->n_params;
+            A.pref = pref; A.tf = h->saveat.back(); A.reltol = h->cfg.adjoint_reltol; A.abstol = h->cfg.adjoint_abstol; A.fixed_dt = h->cfg.fixed_dt;
+            if (!adjoint_small_launch<N>(h, A, nb, st)) {
+                // default Chain, FP16x2 operand scales available: the tensor-core backward kernel (nfc_adjoint_tc.cuh); else FP32 SIMT
+                if (h->arch == ARCH_DEFAULT && h->use_tc && h->tc_fp16 && h->adj_tc && cap <= 32767) {
+                    // Stragglers: a column with 4 x the median step count keeps its 128-column CTA alive alone (~ 75 us per pass).  Once the
+                    // per-column backward step counts are known from the previous call, the adj_heavy longest columns (the head of the
+                    // longest-first order) run on the one-column-per-CTA kernel instead (~ 20 us per pass), on a high-priority side stream next
+                    // to the tensor-core kernel, whose CTAs on those SMs start when they are free (persistent CTAs, dynamic queue).
+                    int n_heavy = 0;
+                    if (order && key != h->a_tlen.p && h->adj_heavy > 0 && nb >= 512) n_heavy = (int)std::min<int64_t>(std::min<int64_t>(h->adj_heavy, nb / 16), h->num_sms);
+                    if (n_heavy > 0) {
+                        if (int rc = adjoint_heavy_launch(h, A, n_heavy, st)) return rc;
+                        A.order = order + n_heavy;
+                        A.B = nb - n_heavy;
+                    }
+                    if (int rc = adjoint_tc_launch(h, A, h->atc_scales, A.B, st)) return rc;
+                    if (n_heavy > 0) {
+                        NFC_CUDA(h, cudaEventRecord(h->ev_heavy[1], h->heavy_stream));
+                        NFC_CUDA(h, cudaStreamWaitEvent(st, h->ev_heavy[1], 0));
+                        h->last_launches += 1;
+                    }
+                } else adjoint_kernel<N, AdjLaunch<N>::WS><<<grid, ADJ_NW * 32, adj_smem_bytes<N>(), st>>>(A);
+            }
             NFC_CUDA(h, cudaGetLastError());
-            order = h->d_order.p;
-            h->last_launches += 3;
+            h->last_launches += 1;
+            first = false;
         }
-        AdjParams A{};
-        A.order = order;
-        NFC_CUDA(h, cudaMemsetAsync(h->a_adjsteps.p + off, 0, sizeof(int) * nb, st));     // after the order is built (stream order)
-        A.adj_steps = h->a_adjsteps.p + off;
-        h->a_adjsteps_n = B;
-        A.wpack = h->d_wpack.p; A.colp = colp + off * 3; A.saveat = h->d_saveat.p; A.resid = h->a_resid.p; A.tape = h->a_tape.p;
-        A.tape_off = tape_off; A.nz = h->nz; A.queue_ctr = CTR_ADJ_QUEUE;
-        A.tape_len = h->a_tlen.p; A.status = st_all + off; A.gacc = h->a_gacc.p; A.counters = h->d_counters.p; A.B = nb; A.n_save = n_save;
-        A.tape_cap = cap; A.max_iters = h->cfg.max_iters; A.use_kca = h->cfg.nde_type == NFC_NDE_CONVECTIVE_ADJUSTMENT; A.n_params = (int)h->n_params;
-        A.pref = pref; A.tf = h->saveat.back(); A.reltol = h->cfg.adjoint_reltol; A.abstol = h->cfg.adjoint_abstol; A.fixed_dt = h->cfg.fixed_dt;
-        if (!adjoint_small_launch<N>(h, A, nb, st)) {
-            // default Chain, FP16x2 operand scales available: the tensor-core backward kernel (nfc_adjoint_tc.cuh); else FP32 SIMT
-            if (h->arch == ARCH_DEFAULT && h->use_tc && h->tc_fp16 && h->adj_tc && cap <= 32767) {
-                // Stragglers: a column with 4 x the median step count keeps its 128-column CTA alive alone (~ 75 us per pass).  Once the
-                // per-column backward step counts are known from the previous call, the adj_heavy longest columns (the head of the
-                // longest-first order) run on the one-column-per-CTA kernel instead (~ 20 us per pass), on a high-priority side stream next
-                // to the tensor-core kernel, whose CTAs on those SMs start when they are free (persistent CTAs, dynamic queue).
-                int n_heavy = 0;
-                if (order && key != h->a_tlen.p && h->adj_heavy > 0 && nb >= 512) n_heavy = (int)std::min<int64_t>(std::min<int64_t>(h->adj_heavy, nb / 16), h->num_sms);
-                if (n_heavy > 0) {
-                    if (int rc = adjoint_heavy_launch(h, A, n_heavy, st)) return rc;
-                    A.order = order + n_heavy;
-                    A.B = nb - n_heavy;
-                }
-                if (int rc = adjoint_tc_launch(h, A, h->atc_scales, A.B, st)) return rc;
-                if (n_heavy > 0) {
-                    NFC_CUDA(h, cudaEventRecord(h->ev_heavy[1], h->heavy_stream));
-                    NFC_CUDA(h, cudaStreamWaitEvent(st, h->ev_heavy[1], 0));
-                    h->last_launches += 1;
-                }
-            } else adjoint_kernel<N, AdjLaunch<N>::WS><<<grid, ADJ_NW * 32, adj_smem_bytes<N>(), st>>>(A);
-        }
-        NFC_CUDA(h, cudaGetLastError());
-        h->last_launches += 1;
-        first = false;
-    }
-    if (!restart) break;
-    h->a_count_valid = false;
+        if (!restart) break;
+        h->a_count_valid = false;
     }   // attempt
     if (compact) h->a_count_valid = true;
     // with a communicator the sums stay un-normalised until the all-reduce has produced the global residual count
