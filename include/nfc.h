@@ -183,6 +183,9 @@ int32_t nfc_get_adjoint_steps(nfc_handle* h, int32_t* out, int64_t n);
  *   tc_split         0 = FP16x2 operands (3 MMAs per fp32 product, needs |T_scaled| <= 128; default), 1 = BF16x3 (6 MMAs, fp32's range)
  *   range_fallback   1 (default): nfc_solve re-solves columns that ended with status 5 on the BF16x3 split, nfc_loss_grad (no communicator)
  *                    repeats a call that had such a column on the FP32 kernels; 0: status 5 is returned as it is (the *_dev calls always do)
+ *   reset_history    (any value) forget the per-column step counts kept from the previous calls: schedules, side launch and compact-tape
+ *                    shares are keyed by the batch size only -- call it when NEW columns arrive under an unchanged batch size (results never
+ *                    depend on the history, only the time does: a stale one costs ~ 8 % on the next call)
  *   tape_gib         tape budget of nfc_loss_grad in GiB; larger batches are processed in chunks (0 = default 48)
  *   tape_mode        layout of the adjoint tape: 1 = dense (every column owns adjoint_max_steps rows of 672 B: 344 KB at the default 512),
  *                    2 = compact (a counting pass -- the forward solve on the RECORD pass's kernels, no outputs -- sizes every column's

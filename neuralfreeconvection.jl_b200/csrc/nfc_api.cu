@@ -932,10 +932,13 @@ int32_t nfc_set_option(nfc_handle* h, const char* name, int64_t value) {
         NFC_CUDA(h, cudaSetDevice(h->device));
         return switch_split(h, value == 0);
     }
+    else if (n == "reset_history") {       // new columns behind an unchanged batch size: forget the per-column step counts of the previous calls
+        h->sched_valid.assign(8, false); h->a_adjhist_valid = false; h->a_count_valid = false;
+    }
     else if (n == "adj_heavy") { if (value < 0) return fail(h, -2, "adj_heavy: >= 0"); h->adj_heavy = value; }
     else if (n == "tape_mode") { if (value < 0 || value > 2) return fail(h, -2, "tape_mode: 0 = compact tape when the dense one exceeds the budget, 1 = dense, 2 = compact"); h->tape_mode = (int)value; }
     else if (n == "tape_gib") { if (value < 0) return fail(h, -2, "tape_gib: >= 0 (0 = default 48)"); h->tape_gib = (double)value; }
-    else return fail(h, -2, "unknown option '%s' (tc, tc_tiles, tc_split, range_fallback, tc2_min_columns, tc_record, sched, adj_small_max, fwd_small_max, adj_tc, adj_heavy, e2e_pieces, tape_gib, tape_mode)", name);
+    else return fail(h, -2, "unknown option '%s' (tc, tc_tiles, tc_split, range_fallback, tc2_min_columns, tc_record, sched, adj_small_max, fwd_small_max, adj_tc, adj_heavy, reset_history, e2e_pieces, tape_gib, tape_mode)", name);
     return 0;
 }
 

@@ -144,3 +144,7 @@ def test_longest_columns_run_on_the_side_stream(nfc, gpu_ok, monkeypatch):
     h.set_option("adj_heavy", 0)
     r3 = h.loss_grad(d["T0"], colp, d["glob"], Ttrue)
     assert h.counters()["kernel_launches"] == l1 and _rel(r3["grad"], r1["grad"]) < 3e-4
+    h.set_option("adj_heavy", 48)
+    h.set_option("reset_history", 1)                                       # as if new columns had arrived: a first call again
+    r4 = h.loss_grad(d["T0"], colp, d["glob"], Ttrue)
+    assert h.counters()["kernel_launches"] == l1 and _rel(r4["grad"], r1["grad"]) < 3e-4
