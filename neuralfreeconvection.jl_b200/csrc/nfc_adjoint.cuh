@@ -712,7 +712,10 @@ int adjoint_loss_grad(nfc_handle* h, const float* T0, const float* colp, float p
             P.Ttrue = Ttrue + off * (int64_t)n_save * NZ; P.resid = h->a_resid.p; P.tape = h->a_tape.p; P.tape_len = h->a_tlen.p;
             P.loss_sum = loss_sum_dev; P.tape_cap = cap; P.tape_off = tape_off;
             if (compact) P.naccept = h->a_count.p + off;       // the next call's tape shares
-            if (int rc = nfc_launch_record<N>(h, P, st, first)) return rc;
+            h->record_sched = chunk_begin.size() == 2;          // one chunk: longest-first from the previous call's step counts, like nfc_solve
+            const int rc_rec = nfc_launch_record<N>(h, P, st, first);
+            h->record_sched = false;
+            if (rc_rec) return rc_rec;
             if (from_history) {      // shares predicted from the previous call: did a column outgrow its rows?
                 int flag = 0;
                 NFC_CUDA(h, cudaMemsetAsync(h->a_flag.p, 0, sizeof(int), st));

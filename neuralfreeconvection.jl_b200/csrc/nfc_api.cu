@@ -197,7 +197,7 @@ int launch_solve(nfc_handle* h, SolveParams& P, cudaStream_t st, bool reset_coun
     // columns and the persistent CTAs finish together (the same columns are re-solved every epoch).  Results do not depend on it.
     P.order = nullptr; P.work = nullptr;
     const bool rec_sel = RECORD || h->count_pass;      // counting pass of the compact tape: the RECORD pass's kernel choice, so its step counts
-    if (!RECORD && h->use_sched && B >= 4096) {
+    if ((!RECORD || h->record_sched) && h->use_sched && B >= 4096) {       // RECORD pass: when the whole batch is one chunk (nfc_adjoint.cuh)
         if (h->sched_B != hist_total) {                      // new batch size: forget the history
             NFC_CUDA(h, cudaStreamSynchronize(st));
             h->d_work.release();

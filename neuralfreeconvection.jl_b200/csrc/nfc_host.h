@@ -93,6 +93,7 @@ struct nfc_handle {
     int64_t sched_B = -1;       // batch size d_work is valid for (-1: none)
     std::vector<bool> sched_valid = std::vector<bool>(8, false);   // per piece of a host-level batch: history present
     bool use_sched = true;
+    bool record_sched = false;     // set by nfc_loss_grad around a RECORD pass that covers the whole batch: it may use and feed the step history
     nfc::DevBuf<unsigned long long> d_counters;
     // host-call staging
     nfc::DevBuf<float> s_T0, s_colp, s_out, s_true, s_grad;
